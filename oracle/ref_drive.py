@@ -1,0 +1,166 @@
+"""Drive the UNMODIFIED reference functions on batches in this repo's flat layout.
+
+TEST SCAFFOLDING; needs /root/reference (build container only).  Converts a batch dict
+(dummynode4graphlearning_b200/synth.py layout) into the containers the reference expects
+(TU text files / fake igraph / fake DGL graphs), calls the reference's own code, converts
+the result back.  Used by oracle/gen_golden.py and tests/test_oracle_vs_reference.py.
+"""
+import os
+import tempfile
+
+import numpy as np
+import torch as th
+
+from . import refload
+from .shims import fake_dgl
+
+
+# ------------------------------------------------------------------------------------------
+# classification flavour (tu_data_processing.py)
+def write_tu_files(b, root, name="T"):
+    """TU text layout (what tu_data_processing.py:134-152 parses)."""
+    raw = os.path.join(root, name)
+    os.makedirs(raw, exist_ok=True)
+    assert int(b["vlabel"].min()) == 1 and int(b["elabel"].min()) == 1, "labels must already have min 1"
+
+    def w(suffix, rows):
+        with open(os.path.join(raw, "%s_%s.txt" % (name, suffix)), "w") as f:
+            for r in rows:
+                f.write(r + "\n")
+
+    w("A", ["%d, %d" % (s + 1, d + 1) for s, d in zip(b["src"], b["dst"])])
+    gi = np.repeat(np.arange(b["num_graphs"]) + 1, np.diff(b["node_ptr"]))
+    w("graph_indicator", [str(int(x)) for x in gi])
+    w("node_labels", [str(int(x) - 1) for x in b["vlabel"]])          # 0-based on disk -> +1 (line 158-159)
+    if b.get("has_edge_labels", True):
+        w("edge_labels", [str(int(x) - 1) for x in b["elabel"]])
+    if "vattr" in b:
+        w("node_attributes", [repr(float(x)) for x in b["vattr"]])
+    w("graph_labels", [str(int(x)) for x in b.get("y", np.zeros(b["num_graphs"], int))])
+    return raw
+
+
+def igraphs_to_batch(graphs):
+    B = len(graphs)
+    node_ptr = np.zeros(B + 1, np.int32)
+    edge_ptr = np.zeros(B + 1, np.int32)
+    src, dst = [], []
+    cols_v, cols_e = {}, {}
+    for i, g in enumerate(graphs):
+        node_ptr[i + 1] = node_ptr[i] + g.vcount()
+        edge_ptr[i + 1] = edge_ptr[i] + g.ecount()
+        el = g.get_edgelist()
+        src += [a + int(node_ptr[i]) for a, _ in el]
+        dst += [c + int(node_ptr[i]) for _, c in el]
+        for k in g.vertex_attributes():
+            cols_v.setdefault(k, []).extend(g.vs[k])
+        for k in g.edge_attributes():
+            cols_e.setdefault(k, []).extend(g.es[k])
+    o = dict(num_graphs=B, node_ptr=node_ptr, edge_ptr=edge_ptr,
+             src=np.asarray(src, np.int32), dst=np.asarray(dst, np.int32))
+    names = {"LABEL": "label", "IS_DUMMY": "_is_dummy", "ID": "id", "ATTR": "attr"}
+    for k, v in cols_v.items():
+        key = "v" + names[k] if k != "IS_DUMMY" else "v_is_dummy"
+        o[key] = np.asarray(v, np.float32 if k == "ATTR" else np.int32)
+    for k, v in cols_e.items():
+        key = "e" + names[k] if k != "IS_DUMMY" else "e_is_dummy"
+        o[key] = np.asarray(v, np.float32 if k == "ATTR" else np.int32)
+    return o
+
+
+def ref_tu_load(b, with_dummy):
+    """reference load_graph_data_from_TUDatadir (tu_data_processing.py:125-220) on batch b."""
+    tu = refload.classification().tu
+    with tempfile.TemporaryDirectory() as d:
+        raw = write_tu_files(b, d)
+        return tu.load_graph_data_from_TUDatadir(raw, with_dummy=with_dummy)
+
+
+def ref_tu_conjugate(graphs):
+    tu = refload.classification().tu
+    return [tu.convert_conjugate_graph_forward(g) for g in graphs]
+
+
+def ref_tu_save(graphs):
+    """reference save_graph_data (tu_data_processing.py:353-414) -> dict suffix -> lines."""
+    tu = refload.classification().tu
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "X", "raw")
+        os.makedirs(out)
+        tu.save_graph_data(graphs, out)
+        res = {}
+        for fn in sorted(os.listdir(out)):
+            with open(os.path.join(out, fn)) as f:
+                res[fn[len("X_"):-4]] = [ln.strip() for ln in f]
+        return res
+
+
+# ------------------------------------------------------------------------------------------
+# subgraph-isomorphism flavour (train.py / utils/graph.py) on fake DGL graphs
+def batch_to_dgl_list(b):
+    """per-graph fake DGLGraphs with ndata{id,label[,is_dummy]} / edata{id,label[,..]} (int64)."""
+    C = refload.subgraph().constants
+    gs = []
+    for g in range(b["num_graphs"]):
+        n0, n1 = int(b["node_ptr"][g]), int(b["node_ptr"][g + 1])
+        e0, e1 = int(b["edge_ptr"][g]), int(b["edge_ptr"][g + 1])
+        G = fake_dgl.DGLGraph(b["src"][e0:e1].astype(np.int64) - n0, b["dst"][e0:e1].astype(np.int64) - n0, n1 - n0)
+        G.ndata[C.NODEID] = th.from_numpy(b["vid"][n0:n1].astype(np.int64))
+        G.ndata[C.NODELABEL] = th.from_numpy(b["vlabel"][n0:n1].astype(np.int64))
+        G.edata[C.EDGEID] = th.from_numpy(b["eid"][e0:e1].astype(np.int64))
+        G.edata[C.EDGELABEL] = th.from_numpy(b["elabel"][e0:e1].astype(np.int64))
+        for k, fr, (a, z) in (("v_is_dummy", G.ndata, (n0, n1)), ("e_is_dummy", G.edata, (e0, e1))):
+            if k in b:
+                fr[C.DUMMYFLAG] = th.from_numpy(b[k][a:z].astype(bool))
+        if "e_is_reversed" in b:
+            G.edata[C.REVFLAG] = th.from_numpy(b["e_is_reversed"][e0:e1].astype(bool))
+        if "v_is_reversed" in b:
+            G.ndata[C.REVFLAG] = th.from_numpy(b["v_is_reversed"][n0:n1].astype(bool))
+        gs.append(G)
+    return gs
+
+
+def dgl_list_to_batch(gs):
+    C = refload.subgraph().constants
+    B = len(gs)
+    node_ptr = np.zeros(B + 1, np.int32)
+    edge_ptr = np.zeros(B + 1, np.int32)
+    for i, g in enumerate(gs):
+        node_ptr[i + 1] = node_ptr[i] + g.number_of_nodes()
+        edge_ptr[i + 1] = edge_ptr[i] + g.number_of_edges()
+    o = dict(num_graphs=B, node_ptr=node_ptr, edge_ptr=edge_ptr)
+    o["src"] = np.concatenate([g._u.numpy() + node_ptr[i] for i, g in enumerate(gs)]).astype(np.int32)
+    o["dst"] = np.concatenate([g._v.numpy() + node_ptr[i] for i, g in enumerate(gs)]).astype(np.int32)
+    nmap = {C.NODEID: "vid", C.NODELABEL: "vlabel", C.DUMMYFLAG: "v_is_dummy", C.REVFLAG: "v_is_reversed",
+            C.INDEGREE: "in_deg", C.OUTDEGREE: "out_deg"}
+    emap = {C.EDGEID: "eid", C.EDGELABEL: "elabel", C.DUMMYFLAG: "e_is_dummy", C.REVFLAG: "e_is_reversed"}
+    for k, name in nmap.items():
+        if all(k in g.ndata for g in gs):
+            o[name] = np.concatenate([g.ndata[k].numpy() for g in gs]).astype(np.int32)
+    for k, name in emap.items():
+        if all(k in g.edata for g in gs):
+            o[name] = np.concatenate([g.edata[k].numpy() for g in gs]).astype(np.int32)
+    return o
+
+
+def ref_sub_add_dummy(pattern_b, graph_b, cfg):
+    """reference add_dummy_nodes_edges, GraphAdj branch (train.py:404-474), called with the
+    dataset maxima exactly as train.py:1322-1334 does."""
+    tf = refload.subgraph().train_funcs
+    ps, gs = batch_to_dgl_list(pattern_b), batch_to_dgl_list(graph_b)
+    ds = tf.GraphAdjDataset(
+        [{"pattern": p, "graph": g, "counts": 0, "subisomorphisms": th.zeros((0, 0), dtype=th.long)}
+         for p, g in zip(ps, gs)])
+    tf.add_dummy_nodes_edges(ds, cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"],
+                             cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"])
+    return dgl_list_to_batch([x["pattern"] for x in ds]), dgl_list_to_batch([x["graph"] for x in ds])
+
+
+def ref_sub_conjugate(b):
+    """reference convert_conjugate_graph, DGL branch (utils/graph.py:77-175)."""
+    gu = refload.subgraph().graph_utils
+    return dgl_list_to_batch([gu.convert_conjugate_graph(g) for g in batch_to_dgl_list(b)])
+
+
+def ref_process_model_config(config):
+    return refload.subgraph().train_funcs.process_model_config(config)

@@ -1,0 +1,183 @@
+"""ctypes front-end of oracle/c/transforms.c (TEST INFRASTRUCTURE ONLY).
+
+Every function takes/returns host numpy int32 arrays in the batched layout described in
+the C file header and cites the reference lines its C body restates.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "c", "liborc.so")
+_lib = None
+
+_I = ctypes.POINTER(ctypes.c_int)
+_F = ctypes.POINTER(ctypes.c_float)
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.orc_pyg_coalesce.restype = ctypes.c_int64
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"], (a.dtype, a.flags)
+    return a.ctypes.data_as(_I)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def tu_add_dummy(b):
+    """tu_data_processing.py:186-214 (with_dummy=True).  b: raw TU batch dict."""
+    B = int(b["num_graphs"])
+    N, E = len(b["vlabel"]), len(b["src"])
+    o = dict(
+        num_graphs=B,
+        node_ptr=np.empty(B + 1, np.int32), edge_ptr=np.empty(B + 1, np.int32),
+        src=np.empty(E + 2 * N, np.int32), dst=np.empty(E + 2 * N, np.int32),
+        vlabel=np.empty(N + B, np.int32), v_is_dummy=np.empty(N + B, np.int32),
+        elabel=np.empty(E + 2 * N, np.int32), e_is_dummy=np.empty(E + 2 * N, np.int32),
+    )
+    lib().orc_tu_add_dummy(
+        B, _p(_i32(b["node_ptr"])), _p(_i32(b["edge_ptr"])), _p(_i32(b["src"])), _p(_i32(b["dst"])),
+        _p(_i32(b["vlabel"])), _p(_i32(b["elabel"])),
+        _p(o["node_ptr"]), _p(o["edge_ptr"]), _p(o["src"]), _p(o["dst"]),
+        _p(o["vlabel"]), _p(o["v_is_dummy"]), _p(o["elabel"]), _p(o["e_is_dummy"]))
+    if "vattr" in b:  # ATTR passthrough, dummy gets 0 (line 191)
+        va = np.zeros(N + B, np.float32)
+        real = np.ones(N + B, bool)
+        real[o["node_ptr"][1:] - 1] = False
+        va[real] = b["vattr"]
+        o["vattr"] = va
+    # ID = position within the graph (lines 213-214)
+    o["vid"] = (np.arange(N + B, dtype=np.int32) - np.repeat(o["node_ptr"][:-1], np.diff(o["node_ptr"]))).astype(np.int32)
+    o["eid"] = (np.arange(E + 2 * N, dtype=np.int32) - np.repeat(o["edge_ptr"][:-1], np.diff(o["edge_ptr"]))).astype(np.int32)
+    return o
+
+
+def _two_phase(fn, B, args):
+    node_ptr = np.empty(B + 1, np.int32)
+    edge_ptr = np.empty(B + 1, np.int32)
+    fn(*args, _p(node_ptr), _p(edge_ptr), None, None, None, None)
+    V, E = int(node_ptr[-1]), int(edge_ptr[-1])
+    src, dst = np.empty(E, np.int32), np.empty(E, np.int32)
+    v_origin, e_shared = np.empty(V, np.int32), np.empty(E, np.int32)
+    fn(*args, _p(node_ptr), _p(edge_ptr), _p(src), _p(dst), _p(v_origin), _p(e_shared))
+    return node_ptr, edge_ptr, src, dst, v_origin, e_shared
+
+
+def tu_conjugate(b):
+    """tu_data_processing.py:223-338.  b: a TU batch (raw -> LINE_, dummy-augmented -> CONJ_).
+    Returns the conjugate batch; vertex attributes come from the original edges
+    (lines 238-242), edge attributes from the shared original vertex (322-326)."""
+    B = int(b["num_graphs"])
+    keep = [_i32(b[k]) for k in ("node_ptr", "edge_ptr", "src", "dst", "vlabel")]
+    isd = _i32(b.get("e_is_dummy"))
+    args = [B] + [_p(a) for a in keep] + [_p(isd)]
+    node_ptr, edge_ptr, src, dst, v_origin, e_shared = _two_phase(lib().orc_tu_conjugate, B, args)
+    o = dict(num_graphs=B, node_ptr=node_ptr, edge_ptr=edge_ptr, src=src, dst=dst,
+             v_origin=v_origin, e_shared=e_shared)
+    o["vlabel"] = _i32(b["elabel"])[v_origin]
+    o["elabel"] = _i32(b["vlabel"])[e_shared]
+    eid = b["eid"] if "eid" in b else (np.arange(len(b["src"]), dtype=np.int32)
+                                       - np.repeat(b["edge_ptr"][:-1], np.diff(b["edge_ptr"])))
+    vid = b["vid"] if "vid" in b else (np.arange(len(b["vlabel"]), dtype=np.int32)
+                                       - np.repeat(b["node_ptr"][:-1], np.diff(b["node_ptr"])))
+    o["vid"] = _i32(eid)[v_origin]
+    o["eid"] = _i32(vid)[e_shared]
+    if isd is not None:
+        o["v_is_dummy"] = isd[v_origin]
+        o["e_is_dummy"] = _i32(b["v_is_dummy"])[e_shared]
+    if "vattr" in b:
+        o["eattr"] = b["vattr"][e_shared]
+    return o
+
+
+def sub_add_dummy(b, max_nv, max_nvl, max_ne, max_nel):
+    """train.py:404-474 (GraphAdj branch).  max_* are the PRE-augmentation dataset maxima
+    passed at train.py:1322-1334."""
+    B = int(b["num_graphs"])
+    N, E = len(b["vlabel"]), len(b["src"])
+    names_n = ("vid", "vlabel", "v_is_dummy")
+    names_e = ("eid", "elabel", "e_is_dummy", "e_is_reversed")
+    o = dict(num_graphs=B, node_ptr=np.empty(B + 1, np.int32), edge_ptr=np.empty(B + 1, np.int32),
+             src=np.empty(E + 2 * N, np.int32), dst=np.empty(E + 2 * N, np.int32))
+    for k in names_n:
+        o[k] = np.empty(N + B, np.int32)
+    for k in names_e:
+        o[k] = np.empty(E + 2 * N, np.int32)
+    lib().orc_sub_add_dummy(
+        B, _p(_i32(b["node_ptr"])), _p(_i32(b["edge_ptr"])), _p(_i32(b["src"])), _p(_i32(b["dst"])),
+        _p(_i32(b["vid"])), _p(_i32(b["vlabel"])), _p(_i32(b["eid"])), _p(_i32(b["elabel"])),
+        _p(_i32(b.get("e_is_reversed"))),
+        int(max_nv), int(max_nvl), int(max_ne), int(max_nel),
+        _p(o["node_ptr"]), _p(o["edge_ptr"]), _p(o["src"]), _p(o["dst"]),
+        _p(o["vid"]), _p(o["vlabel"]), _p(o["v_is_dummy"]),
+        _p(o["eid"]), _p(o["elabel"]), _p(o["e_is_dummy"]), _p(o["e_is_reversed"]))
+    return o
+
+
+def sub_conjugate(b):
+    """utils/graph.py:74-175.  Node/edge attribute names are swapped as at lines 155-165:
+    the conjugate's vertices carry the edge columns, its edges the shared vertex's columns."""
+    B = int(b["num_graphs"])
+    keep = [_i32(b[k]) for k in ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "eid")]
+    args = [B] + [_p(a) for a in keep]
+    node_ptr, edge_ptr, src, dst, v_origin, e_shared = _two_phase(lib().orc_sub_conjugate, B, args)
+    o = dict(num_graphs=B, node_ptr=node_ptr, edge_ptr=edge_ptr, src=src, dst=dst,
+             v_origin=v_origin, e_shared=e_shared)
+    for ek, vk in (("eid", "vid"), ("elabel", "vlabel"), ("e_is_dummy", "v_is_dummy"),
+                   ("e_is_reversed", "v_is_reversed")):
+        if ek in b:
+            o[vk] = _i32(b[ek])[v_origin]
+    for vk, ek in (("vid", "eid"), ("vlabel", "elabel"), ("v_is_dummy", "e_is_dummy")):
+        if vk in b:
+            o[ek] = _i32(b[vk])[e_shared]
+    return o
+
+
+def pyg_coalesce(src, dst, elabel0=None, num_rel=0):
+    """PyG read_tu_data: remove_self_loops + coalesce (sort by (row, col), merge duplicates,
+    summing one-hot attributes -> per-label multiplicities)."""
+    src, dst = _i32(src), _i32(dst)
+    el = _i32(elabel0)
+    E = len(src)
+    n = lib().orc_pyg_coalesce(ctypes.c_int64(E), _p(src), _p(dst), _p(el), int(num_rel), None, None, None, None)
+    o_src, o_dst, o_first = (np.empty(n, np.int32) for _ in range(3))
+    o_mult = np.zeros((n, num_rel), np.int32) if num_rel else None
+    lib().orc_pyg_coalesce(ctypes.c_int64(E), _p(src), _p(dst), _p(el), int(num_rel),
+                           _p(o_src), _p(o_dst), _p(o_first), _p(o_mult))
+    return o_src, o_dst, o_first, o_mult
+
+
+def csr_by_dst(N, src, dst):
+    src, dst = _i32(src), _i32(dst)
+    row_ptr = np.empty(N + 1, np.int32)
+    col, eid = np.empty(len(src), np.int32), np.empty(len(src), np.int32)
+    lib().orc_csr_by_dst(ctypes.c_int64(N), ctypes.c_int64(len(src)), _p(src), _p(dst),
+                         _p(row_ptr), _p(col), _p(eid))
+    return row_ptr, col, eid
+
+
+def spmm_sum(N, src, dst, x, self_scale=0.0):
+    src, dst = _i32(src), _i32(dst)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    lib().orc_spmm_sum_f32(ctypes.c_int64(N), ctypes.c_int64(len(src)), int(x.shape[1]), _p(src), _p(dst),
+                           x.ctypes.data_as(_F), ctypes.c_float(self_scale), out.ctypes.data_as(_F))
+    return out
