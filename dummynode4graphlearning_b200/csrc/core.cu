@@ -1,0 +1,360 @@
+// libdn4gl.so -- error plumbing, exclusive scan, stable CSR construction.
+#include "common.cuh"
+
+#include <string.h>
+
+// -------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void dn4gl_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int dn4gl_version(void) { return DN4GL_ABI_VERSION; }
+extern "C" const char *dn4gl_last_error(void) { return g_err; }
+
+extern "C" int dn4gl_set_device(int device) {
+    DN_CUDA(cudaSetDevice(device));
+    return DN4GL_OK;
+}
+
+int dn4gl_num_sms() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+// -------------------------------------------------------------------------------------------
+// exclusive scan (int32).  Tile = 1024 threads x 4 items.  n <= TILE: one launch.  Otherwise
+// reduce -> scan of tile sums (one CTA) -> downsweep: three launches, no atomics, deterministic.
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *smem /* 33 ints */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) smem[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < (blockDim.x >> 5)) ? smem[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        smem[lane] = wi - w;           // exclusive prefix of warp sums
+        if (lane == 31) smem[32] = wi;  // block total
+    }
+    __syncthreads();
+    int res = incl - v + smem[warp];
+    if (total) *total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const int32_t *__restrict__ in, int64_t n,
+                                                               int32_t *__restrict__ tile_sums) {
+    __shared__ int sm[33];
+    int64_t base = static_cast<int64_t>(blockIdx.x) * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) s += in[base + k];
+    int total;
+    block_exclusive_scan(s, &total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single CTA: in-place exclusive scan of m tile sums
+__global__ void __launch_bounds__(SCAN_THREADS) scan_of_sums(int32_t *__restrict__ sums, int64_t m) {
+    __shared__ int sm[33];
+    int carry = 0;
+    for (int64_t start = 0; start < m; start += SCAN_THREADS) {
+        int64_t i = start + threadIdx.x;
+        int v = (i < m) ? sums[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total, sm);
+        if (i < m) sums[i] = ex + carry;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep(const int32_t *in, int32_t *out, int64_t n,
+                                                               const int32_t *__restrict__ tile_offsets) {
+    __shared__ int sm[33];
+    int64_t base = static_cast<int64_t>(blockIdx.x) * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int ex = block_exclusive_scan(s, &total, sm) + (tile_offsets ? tile_offsets[blockIdx.x] : 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+        if (base + k == n - 1) out[n] = ex;  // grand total in the extra slot
+    }
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0;
+}
+
+extern "C" size_t dn4gl_scan_workspace_bytes(int64_t n) {
+    int64_t tiles = ceil_div64(n > 0 ? n : 1, SCAN_TILE);
+    return align_up(static_cast<size_t>(tiles) * sizeof(int32_t), 256);
+}
+
+extern "C" int dn4gl_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, void *ws, size_t ws_bytes,
+                                        void *stream) {
+    DN_ARG(n >= 0 && out != nullptr && (in != nullptr || n == 0));
+    cudaStream_t st = as_stream(stream);
+    int64_t tiles = ceil_div64(n > 0 ? n : 1, SCAN_TILE);
+    if (tiles == 1) {
+        scan_downsweep<<<1, SCAN_THREADS, 0, st>>>(in, out, n, nullptr);
+        DN_LAUNCHED();
+        return DN4GL_OK;
+    }
+    if (ws == nullptr || ws_bytes < dn4gl_scan_workspace_bytes(n)) {
+        dn4gl_set_error("dn4gl_exclusive_scan_i32: workspace too small");
+        return DN4GL_EWORKSPACE;
+    }
+    int32_t *sums = static_cast<int32_t *>(ws);
+    scan_tile_sums<<<static_cast<unsigned>(tiles), SCAN_THREADS, 0, st>>>(in, n, sums);
+    DN_LAUNCHED();
+    scan_of_sums<<<1, SCAN_THREADS, 0, st>>>(sums, tiles);
+    DN_LAUNCHED();
+    scan_downsweep<<<static_cast<unsigned>(tiles), SCAN_THREADS, 0, st>>>(in, out, n, sums);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// CSR build: histogram -> scan -> atomic scatter -> per-row sort by item id (restores the
+// stable order, which makes the result deterministic and equal to a sequential counting sort).
+__global__ void csr_histogram(const int32_t *__restrict__ key, int64_t E, int32_t *__restrict__ cnt) {
+    int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < E) atomicAdd(cnt + key[e], 1);
+}
+
+__global__ void csr_scatter(const int32_t *__restrict__ key, int64_t E, const int32_t *__restrict__ row_ptr,
+                            int32_t *__restrict__ cursor, int32_t *__restrict__ eid) {
+    int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < E) {
+        int k = key[e];
+        int p = row_ptr[k] + atomicAdd(cursor + k, 1);
+        eid[p] = static_cast<int32_t>(e);
+    }
+}
+
+// sort key of an item: (primary[item], item) lexicographic; primary == NULL -> item only
+__device__ __forceinline__ unsigned long long sort_key(const int32_t *__restrict__ primary, int item) {
+    unsigned long long hi = primary ? static_cast<unsigned int>(primary[item]) : 0u;
+    return (hi << 32) | static_cast<unsigned int>(item);
+}
+
+constexpr int LIGHT_SORT_MAX = 32;
+
+// one thread per row, rows with <= 32 items: insertion sort in local memory.  Longer rows are
+// appended to a work list for the CTA-per-row kernel.
+__global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, int32_t *__restrict__ items,
+                                const int32_t *__restrict__ primary, int32_t *__restrict__ worklist,
+                                int32_t *__restrict__ work_count) {
+    int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int beg = row_ptr[r], d = row_ptr[r + 1] - beg;
+    if (d <= 1) return;
+    if (d > LIGHT_SORT_MAX) {
+        worklist[atomicAdd(work_count, 1)] = static_cast<int32_t>(r);
+        return;
+    }
+    unsigned long long a[LIGHT_SORT_MAX];
+    for (int i = 0; i < d; ++i) a[i] = sort_key(primary, items[beg + i]);
+    for (int i = 1; i < d; ++i) {
+        unsigned long long k = a[i];
+        int j = i - 1;
+        while (j >= 0 && a[j] > k) { a[j + 1] = a[j]; --j; }
+        a[j + 1] = k;
+    }
+    for (int i = 0; i < d; ++i) items[beg + i] = static_cast<int32_t>(a[i] & 0xffffffffu);
+}
+
+// one CTA per listed row: rank sort in shared memory (keys are unique).  Rows longer than `cap`
+// are left to the next (larger) instantiation; rows longer than DN4GL_MAX_ROW_DEGREE raise err_flag.
+__global__ void __launch_bounds__(256) sort_rows_heavy(const int32_t *__restrict__ row_ptr,
+                                                       int32_t *__restrict__ items,
+                                                       const int32_t *__restrict__ primary,
+                                                       const int32_t *__restrict__ worklist,
+                                                       const int32_t *__restrict__ work_count, int lo, int cap,
+                                                       int32_t *err_flag) {
+    extern __shared__ unsigned long long skeys[];
+    const int n_work = *work_count;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int r = worklist[w];
+        int beg = row_ptr[r], d = row_ptr[r + 1] - beg;
+        if (d <= lo) continue;
+        if (d > cap) {
+            if (cap >= DN4GL_MAX_ROW_DEGREE && err_flag && threadIdx.x == 0) atomicExch(err_flag, DN4GL_ELIMIT);
+            continue;
+        }
+        for (int i = threadIdx.x; i < d; i += blockDim.x) skeys[i] = sort_key(primary, items[beg + i]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < d; i += blockDim.x) {
+            unsigned long long k = skeys[i];
+            int rank = 0;
+            for (int j = 0; j < d; ++j) rank += (skeys[j] < k);
+            items[beg + rank] = static_cast<int32_t>(k & 0xffffffffu);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void csr_fill_col(const int32_t *__restrict__ eid, const int32_t *__restrict__ val, int64_t E,
+                             int32_t *__restrict__ col) {
+    int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p < E) col[p] = val ? val[eid[p]] : eid[p];
+}
+
+constexpr int HEAVY_SORT_MID = 4096;
+
+// sorts the items of every row by (primary[item], item); shared by the CSR build and coalesce
+int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int32_t *primary,
+                    int32_t *worklist, int32_t *work_count, int32_t *err_flag, cudaStream_t st) {
+    if (N == 0) return DN4GL_OK;
+    DN_CUDA(cudaMemsetAsync(work_count, 0, sizeof(int32_t), st));
+    sort_rows_light<<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, N, items, primary, worklist,
+                                                                                work_count);
+    DN_LAUNCHED();
+    const int sms = dn4gl_num_sms();
+    sort_rows_heavy<<<sms * 4, 256, HEAVY_SORT_MID * sizeof(unsigned long long), st>>>(
+        row_ptr, items, primary, worklist, work_count, LIGHT_SORT_MAX, HEAVY_SORT_MID, err_flag);
+    DN_LAUNCHED();
+    // large instantiation: DN4GL_MAX_ROW_DEGREE 8-byte keys = 196608 B of dynamic shared memory
+    static bool attr_set = false;
+    const size_t big = static_cast<size_t>(DN4GL_MAX_ROW_DEGREE) * sizeof(unsigned long long);
+    if (!attr_set) {
+        DN_CUDA(cudaFuncSetAttribute(sort_rows_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big)));
+        attr_set = true;
+    }
+    sort_rows_heavy<<<sms, 256, big, st>>>(row_ptr, items, primary, worklist, work_count, HEAVY_SORT_MID,
+                                           DN4GL_MAX_ROW_DEGREE, err_flag);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+extern "C" size_t dn4gl_csr_workspace_bytes(int64_t N, int64_t E) {
+    (void)E;
+    size_t n = static_cast<size_t>(N > 0 ? N : 1);
+    return align_up(n * sizeof(int32_t), 256) * 2 + 256 + dn4gl_scan_workspace_bytes(N + 1);
+}
+
+extern "C" int dn4gl_build_csr(const int32_t *key, const int32_t *val, int64_t N, int64_t E, int32_t *row_ptr,
+                               int32_t *col, int32_t *eid, void *ws, size_t ws_bytes, int32_t *err_flag,
+                               void *stream) {
+    DN_ARG(N >= 0 && E >= 0 && N < INT32_MAX && E < INT32_MAX);
+    DN_ARG(row_ptr != nullptr && (E == 0 || (key != nullptr && eid != nullptr)));
+    cudaStream_t st = as_stream(stream);
+    WsCarver wsc(ws, ws_bytes);
+    int32_t *cursor = wsc.take<int32_t>(N > 0 ? N : 1);
+    int32_t *worklist = wsc.take<int32_t>(N > 0 ? N : 1);
+    int32_t *work_count = wsc.take<int32_t>(1);
+    size_t scan_bytes = dn4gl_scan_workspace_bytes(N + 1);
+    char *scan_ws = wsc.take<char>(scan_bytes);
+    if (!cursor || !worklist || !work_count || !scan_ws) {
+        dn4gl_set_error("dn4gl_build_csr: workspace too small (%zu < %zu)", ws_bytes, dn4gl_csr_workspace_bytes(N, E));
+        return DN4GL_EWORKSPACE;
+    }
+    DN_CUDA(cudaMemsetAsync(row_ptr, 0, static_cast<size_t>(N + 1) * sizeof(int32_t), st));
+    if (E > 0) {
+        csr_histogram<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(key, E, row_ptr);
+        DN_LAUNCHED();
+    }
+    int rc = dn4gl_exclusive_scan_i32(row_ptr, row_ptr, N, scan_ws, scan_bytes, stream);
+    if (rc != DN4GL_OK) return rc;
+    if (E == 0) return DN4GL_OK;
+    DN_CUDA(cudaMemsetAsync(cursor, 0, static_cast<size_t>(N) * sizeof(int32_t), st));
+    csr_scatter<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(key, E, row_ptr, cursor, eid);
+    DN_LAUNCHED();
+    rc = dn4gl_sort_rows(row_ptr, N, eid, nullptr, worklist, work_count, err_flag, st);
+    if (rc != DN4GL_OK) return rc;
+    if (col) {
+        csr_fill_col<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(eid, val, E, col);
+        DN_LAUNCHED();
+    }
+    return DN4GL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+__global__ void collect_heavy(const int32_t *__restrict__ row_ptr, int64_t N, int thr, int32_t *__restrict__ rows,
+                              int cap, int32_t *__restrict__ count) {
+    // CTA-wide compaction per 1024-row chunk, one atomic per chunk
+    __shared__ int sm[33];
+    __shared__ int base_sh;
+    for (int64_t start = static_cast<int64_t>(blockIdx.x) * blockDim.x; start < N;
+         start += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        int64_t r = start + threadIdx.x;
+        int flag = (r < N) && (row_ptr[r + 1] - row_ptr[r] > thr);
+        int total;
+        int ex = block_exclusive_scan(flag, &total, sm);
+        if (threadIdx.x == 0) base_sh = total ? atomicAdd(count, total) : 0;
+        __syncthreads();
+        if (flag && base_sh + ex < cap) rows[base_sh + ex] = static_cast<int32_t>(r);
+        __syncthreads();
+    }
+}
+
+extern "C" int dn4gl_collect_heavy_rows(const int32_t *row_ptr, int64_t N, int32_t threshold, int32_t *heavy_rows,
+                                        int32_t cap, int32_t *heavy_count, void *stream) {
+    DN_ARG(row_ptr && heavy_rows && heavy_count && cap >= 0 && N >= 0);
+    cudaStream_t st = as_stream(stream);
+    DN_CUDA(cudaMemsetAsync(heavy_count, 0, sizeof(int32_t), st));
+    if (N == 0) return DN4GL_OK;
+    // list order is arbitrary (CTAs append chunks as they finish); consumers reduce every listed row
+    // independently, so results do not depend on it.  cap must be >= E / threshold + 1.
+    unsigned grid = static_cast<unsigned>(ceil_div64(N, 1024));
+    if (grid > 4096u) grid = 4096u;
+    collect_heavy<<<grid, 1024, 0, st>>>(row_ptr, N, threshold, heavy_rows, cap, heavy_count);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const int32_t *__restrict__ idx, const float4 *__restrict__ x,
+                                   float4 *__restrict__ out, int64_t total, int Dv) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int64_t r = i / Dv;
+    int c = static_cast<int>(i - r * Dv);
+    out[i] = ldg4(x + static_cast<int64_t>(idx[r]) * Dv + c);
+}
+
+extern "C" int dn4gl_gather_rows_f32(const int32_t *idx, const float *x, float *out, int64_t n, int32_t D,
+                                     void *stream) {
+    DN_ARG(n >= 0 && D > 0 && D % 4 == 0);
+    if (n == 0) return DN4GL_OK;
+    DN_ARG(idx && x && out && aligned16(x) && aligned16(out));
+    int Dv = D / 4;
+    int64_t total = n * Dv;
+    gather_rows_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, as_stream(stream)>>>(
+        idx, reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(out), total, Dv);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}

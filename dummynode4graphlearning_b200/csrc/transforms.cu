@@ -1,0 +1,420 @@
+// libdn4gl.so -- integer graph transforms: dummy-node augmentation (both reference flavours),
+// edge-to-vertex ("conjugate") transform (both flavours), PyG-style coalesce.
+// All outputs are bit-exact with the reference's Python (checked against oracle/ + tests/golden/).
+#include "common.cuh"
+
+int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int32_t *primary, int32_t *worklist,
+                    int32_t *work_count, int32_t *err_flag, cudaStream_t st);
+
+// ===========================================================================================
+// a1: tu_data_processing.py:186-214.  One thread per output element; the graph of an element is
+// found by binary search in the (closed-form) output offsets  node: node_ptr[g]+g,
+// edge: edge_ptr[g]+2*node_ptr[g].
+struct TuDummyArgs {
+    int B;
+    const int32_t *node_ptr, *edge_ptr, *src, *dst, *vlabel, *elabel;
+    int64_t N, E;
+    int32_t *o_node_ptr, *o_edge_ptr, *o_src, *o_dst, *o_vlabel, *o_vdummy, *o_elabel, *o_edummy;
+};
+
+__device__ __forceinline__ int find_graph_by_out_node(const int32_t *__restrict__ node_ptr, int B, int64_t i) {
+    int lo = 0, hi = B;  // node_ptr[lo]+lo <= i < node_ptr[hi]+hi
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (static_cast<int64_t>(node_ptr[mid]) + mid <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int find_graph_by_out_edge(const int32_t *__restrict__ node_ptr,
+                                                      const int32_t *__restrict__ edge_ptr, int B, int64_t j) {
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (static_cast<int64_t>(edge_ptr[mid]) + 2ll * node_ptr[mid] <= j) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void tu_add_dummy_kernel(TuDummyArgs a) {
+    const int64_t n_out = a.N + a.B, e_out = a.E + 2 * a.N;
+    int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t <= a.B) {
+        a.o_node_ptr[t] = a.node_ptr[t] + static_cast<int32_t>(t);
+        a.o_edge_ptr[t] = a.edge_ptr[t] + 2 * a.node_ptr[t];
+    }
+    if (t < n_out) {
+        int g = find_graph_by_out_node(a.node_ptr, a.B, t);
+        int64_t local = t - (a.node_ptr[g] + g);
+        int n = a.node_ptr[g + 1] - a.node_ptr[g];
+        bool dummy = (local == n);
+        a.o_vlabel[t] = dummy ? 0 : a.vlabel[a.node_ptr[g] + local];
+        a.o_vdummy[t] = dummy ? 1 : 0;
+    }
+    if (t < e_out) {
+        int g = find_graph_by_out_edge(a.node_ptr, a.edge_ptr, a.B, t);
+        int n0 = a.node_ptr[g], n = a.node_ptr[g + 1] - n0;
+        int e0 = a.edge_ptr[g], m = a.edge_ptr[g + 1] - e0;
+        int64_t local = t - (static_cast<int64_t>(e0) + 2ll * n0);
+        int no = n0 + g;  // output node offset of graph g
+        if (local < m) {
+            a.o_src[t] = a.src[e0 + local] - n0 + no;
+            a.o_dst[t] = a.dst[e0 + local] - n0 + no;
+            a.o_elabel[t] = a.elabel[e0 + local];
+            a.o_edummy[t] = 0;
+        } else {
+            int k = static_cast<int>(local - m);
+            int v = k >> 1;
+            bool to_dummy = (k & 1);  // even: (n, v)   odd: (v, n)      line 193
+            a.o_src[t] = to_dummy ? no + v : no + n;
+            a.o_dst[t] = to_dummy ? no + n : no + v;
+            a.o_elabel[t] = 0;
+            a.o_edummy[t] = 1;
+        }
+    }
+}
+
+extern "C" int dn4gl_tu_add_dummy(int32_t B, const int32_t *node_ptr, const int32_t *edge_ptr, const int32_t *src,
+                                  const int32_t *dst, const int32_t *vlabel, const int32_t *elabel, int64_t N,
+                                  int64_t E, int32_t *o_node_ptr, int32_t *o_edge_ptr, int32_t *o_src,
+                                  int32_t *o_dst, int32_t *o_vlabel, int32_t *o_vdummy, int32_t *o_elabel,
+                                  int32_t *o_edummy, void *stream) {
+    DN_ARG(B >= 0 && N >= 0 && E >= 0 && E + 2 * N < INT32_MAX);
+    DN_ARG(node_ptr && edge_ptr && o_node_ptr && o_edge_ptr);
+    DN_ARG(N == 0 || (vlabel && o_vlabel && o_vdummy && o_src && o_dst && o_elabel && o_edummy));
+    DN_ARG(E == 0 || (src && dst && elabel));
+    TuDummyArgs a{B, node_ptr, edge_ptr, src, dst, vlabel, elabel, N, E, o_node_ptr, o_edge_ptr,
+                  o_src, o_dst, o_vlabel, o_vdummy, o_elabel, o_edummy};
+    int64_t total = E + 2 * N;
+    if (N + B > total) total = N + B;
+    if (B + 1 > total) total = B + 1;
+    tu_add_dummy_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, as_stream(stream)>>>(a);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+// ===========================================================================================
+// a4: train.py:404-474 (GraphAdj branch).  Blocked dummy edges [u->d]*n then [d->u]*n.
+struct SubDummyArgs {
+    int B;
+    const int32_t *node_ptr, *edge_ptr, *src, *dst, *vid, *vlabel, *eid, *elabel, *e_isrev;
+    int64_t N, E;
+    int max_nv, max_nvl, max_ne, max_nel;
+    int32_t *o_node_ptr, *o_edge_ptr, *o_src, *o_dst, *o_vid, *o_vlabel, *o_vdummy, *o_eid, *o_elabel, *o_edummy,
+        *o_erev;
+};
+
+__global__ void sub_add_dummy_kernel(SubDummyArgs a) {
+    const int64_t n_out = a.N + a.B, e_out = a.E + 2 * a.N;
+    int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t <= a.B) {
+        a.o_node_ptr[t] = a.node_ptr[t] + static_cast<int32_t>(t);
+        a.o_edge_ptr[t] = a.edge_ptr[t] + 2 * a.node_ptr[t];
+    }
+    if (t < n_out) {
+        int g = find_graph_by_out_node(a.node_ptr, a.B, t);
+        int64_t local = t - (a.node_ptr[g] + g);
+        int n = a.node_ptr[g + 1] - a.node_ptr[g];
+        bool dummy = (local == n);
+        int64_t v = a.node_ptr[g] + local;
+        a.o_vid[t] = dummy ? a.max_nv : a.vid[v];           // train.py:419
+        a.o_vlabel[t] = dummy ? a.max_nvl : a.vlabel[v];    // :420
+        a.o_vdummy[t] = dummy ? 1 : 0;                      // :421 (old rows zero-filled by DGL)
+    }
+    if (t < e_out) {
+        int g = find_graph_by_out_edge(a.node_ptr, a.edge_ptr, a.B, t);
+        int n0 = a.node_ptr[g], n = a.node_ptr[g + 1] - n0;
+        int e0 = a.edge_ptr[g], m = a.edge_ptr[g + 1] - e0;
+        int64_t local = t - (static_cast<int64_t>(e0) + 2ll * n0);
+        int no = n0 + g;
+        if (local < m) {
+            int64_t e = e0 + local;
+            a.o_src[t] = a.src[e] - n0 + no;
+            a.o_dst[t] = a.dst[e] - n0 + no;
+            a.o_eid[t] = a.eid[e];
+            a.o_elabel[t] = a.elabel[e];
+            a.o_edummy[t] = 0;
+            a.o_erev[t] = a.e_isrev ? a.e_isrev[e] : 0;
+        } else {
+            int k = static_cast<int>(local - m);
+            bool from_dummy = (k >= n);  // first n: u -> d, last n: d -> u      :409-426
+            int v = from_dummy ? k - n : k;
+            a.o_src[t] = from_dummy ? no + n : no + v;
+            a.o_dst[t] = from_dummy ? no + v : no + n;
+            a.o_eid[t] = a.max_ne + (from_dummy ? 1 : 0);       // :412-413
+            a.o_elabel[t] = a.max_nel + (from_dummy ? 1 : 0);   // :414-415
+            a.o_edummy[t] = 1;
+            a.o_erev[t] = from_dummy ? 1 : 0;                   // :431
+        }
+    }
+}
+
+extern "C" int dn4gl_sub_add_dummy(int32_t B, const int32_t *node_ptr, const int32_t *edge_ptr, const int32_t *src,
+                                   const int32_t *dst, const int32_t *vid, const int32_t *vlabel, const int32_t *eid,
+                                   const int32_t *elabel, const int32_t *e_isrev, int64_t N, int64_t E,
+                                   int32_t max_nv, int32_t max_nvl, int32_t max_ne, int32_t max_nel,
+                                   int32_t *o_node_ptr, int32_t *o_edge_ptr, int32_t *o_src, int32_t *o_dst,
+                                   int32_t *o_vid, int32_t *o_vlabel, int32_t *o_vdummy, int32_t *o_eid,
+                                   int32_t *o_elabel, int32_t *o_edummy, int32_t *o_erev, void *stream) {
+    DN_ARG(B >= 0 && N >= 0 && E >= 0 && E + 2 * N < INT32_MAX);
+    DN_ARG(node_ptr && edge_ptr && o_node_ptr && o_edge_ptr);
+    DN_ARG(N == 0 || (vid && vlabel && o_vid && o_vlabel && o_vdummy && o_src && o_dst && o_eid && o_elabel &&
+                      o_edummy && o_erev));
+    DN_ARG(E == 0 || (src && dst && eid && elabel));
+    SubDummyArgs a{B, node_ptr, edge_ptr, src, dst, vid, vlabel, eid, elabel, e_isrev, N, E,
+                   max_nv, max_nvl, max_ne, max_nel, o_node_ptr, o_edge_ptr, o_src, o_dst,
+                   o_vid, o_vlabel, o_vdummy, o_eid, o_elabel, o_edummy, o_erev};
+    int64_t total = E + 2 * N;
+    if (N + B > total) total = N + B;
+    if (B + 1 > total) total = B + 1;
+    sub_add_dummy_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, as_stream(stream)>>>(a);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+// ===========================================================================================
+// a2: tu_data_processing.py:223-338, closed-form survivor rule (DESIGN.md "conjugate transform"):
+// candidates are (e' -> e) for e in edge order, e' ascending over the in-edges of s = src(e).
+// With unique edge IDs the (uid,label,vid) key set (269-273) never fires; after all IS_DUMMY
+// edges collapse onto the graph's first dummy edge D (302-312) a candidate survives iff
+//   e', e real                      -> always
+//   e' dummy, e real   (D -> e)     -> e' is the FIRST dummy in-edge of s
+//   e' real,  e dummy  (e' -> D)    -> e  is the FIRST dummy out-edge of s
+//   both dummy         (D -> D)     -> never (306)
+// which reproduces "keep the first occurrence" (313-317) without a hash set.
+struct ConjWs {
+    int32_t *egraph;         // [E] graph of each edge
+    int32_t *first_dummy;    // [B] smallest dummy edge id per graph (INT_MAX if none)
+    int32_t *fd_in, *fd_out; // [N] first dummy in-/out-edge per node (INT_MAX if none)
+    int32_t *real_in;        // [N] number of non-dummy in-edges
+    int32_t *kept;           // [E+1] survivor flag of each edge-as-vertex, then its scan
+    char *scan_ws;
+    size_t scan_bytes;
+};
+
+static bool carve_conj_ws(void *ws, size_t ws_bytes, int32_t B, int64_t N, int64_t E, ConjWs *c) {
+    WsCarver w(ws, ws_bytes);
+    c->egraph = w.take<int32_t>(E + 1);
+    c->first_dummy = w.take<int32_t>(B + 1);
+    c->fd_in = w.take<int32_t>(N + 1);
+    c->fd_out = w.take<int32_t>(N + 1);
+    c->real_in = w.take<int32_t>(N + 1);
+    c->kept = w.take<int32_t>(E + 2);
+    c->scan_bytes = dn4gl_scan_workspace_bytes(E + 1);
+    c->scan_ws = w.take<char>(c->scan_bytes);
+    return c->egraph && c->first_dummy && c->fd_in && c->fd_out && c->real_in && c->kept && c->scan_ws;
+}
+
+extern "C" size_t dn4gl_conj_workspace_bytes(int32_t B, int64_t N, int64_t E) {
+    auto a = [](size_t n) { return align_up(n * sizeof(int32_t), 256); };
+    return a(E + 1) + a(B + 1) + 3 * a(N + 1) + a(E + 2) + dn4gl_scan_workspace_bytes(E + 1) + 256;
+}
+
+__global__ void fill_i32(int32_t *p, int64_t n, int32_t v) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void conj_edge_pass1(int B, const int32_t *__restrict__ edge_ptr, const int32_t *__restrict__ src,
+                                const int32_t *__restrict__ dst, const int32_t *__restrict__ isd, int64_t E,
+                                ConjWs c) {
+    int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int g = segment_of(edge_ptr, B, e);
+    c.egraph[e] = g;
+    bool d = isd && isd[e];
+    if (d) {
+        atomicMin(c.first_dummy + g, static_cast<int32_t>(e));
+        atomicMin(c.fd_in + dst[e], static_cast<int32_t>(e));
+        atomicMin(c.fd_out + src[e], static_cast<int32_t>(e));
+    } else {
+        atomicAdd(c.real_in + dst[e], 1);
+    }
+}
+
+// cand_cnt[e] (written into cand_off[e]) and kept[e]
+__global__ void conj_edge_pass2(const int32_t *__restrict__ src, const int32_t *__restrict__ isd, int64_t E,
+                                ConjWs c, int32_t *__restrict__ cand_cnt) {
+    int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int s = src[e];
+    bool d = isd && isd[e];
+    int cnt;
+    if (!d) cnt = c.real_in[s] + (c.fd_in[s] != INT32_MAX ? 1 : 0);
+    else cnt = (c.fd_out[s] == e) ? c.real_in[s] : 0;
+    cand_cnt[e] = cnt;
+    c.kept[e] = (!d || c.first_dummy[c.egraph[e]] == e) ? 1 : 0;
+}
+
+__global__ void conj_graph_offsets(int B, const int32_t *__restrict__ edge_ptr, const int32_t *__restrict__ kept_scan,
+                                   const int32_t *__restrict__ cand_off, int32_t *__restrict__ o_node_ptr,
+                                   int32_t *__restrict__ o_edge_ptr) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g <= B) {
+        o_node_ptr[g] = kept_scan[edge_ptr[g]];
+        o_edge_ptr[g] = cand_off[edge_ptr[g]];
+    }
+}
+
+// newid[e] = global conjugate vertex id that edge e maps to
+__global__ void conj_newid(const int32_t *__restrict__ isd, int64_t E, ConjWs c, int32_t *__restrict__ newid) {
+    int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    bool d = isd && isd[e];
+    int rep = d ? c.first_dummy[c.egraph[e]] : static_cast<int32_t>(e);
+    newid[e] = c.kept[rep];  // kept[] holds the exclusive scan by now
+}
+
+extern "C" int dn4gl_tu_conjugate_count(int32_t B, const int32_t *node_ptr, const int32_t *edge_ptr,
+                                        const int32_t *src, const int32_t *dst, const int32_t *e_isdummy, int64_t N,
+                                        int64_t E, const int32_t *in_ptr, const int32_t *in_eid, int32_t *cand_off,
+                                        int32_t *newid, int32_t *o_node_ptr, int32_t *o_edge_ptr, void *ws,
+                                        size_t ws_bytes, void *stream) {
+    (void)node_ptr; (void)in_ptr; (void)in_eid;
+    DN_ARG(B >= 0 && N >= 0 && E >= 0 && edge_ptr && cand_off && o_node_ptr && o_edge_ptr);
+    DN_ARG(E == 0 || (src && dst && newid));
+    cudaStream_t st = as_stream(stream);
+    ConjWs c;
+    if (!carve_conj_ws(ws, ws_bytes, B, N, E, &c)) {
+        dn4gl_set_error("dn4gl_tu_conjugate_count: workspace too small");
+        return DN4GL_EWORKSPACE;
+    }
+    auto blocks = [](int64_t n) { return static_cast<unsigned>(ceil_div64(n > 0 ? n : 1, 256)); };
+    fill_i32<<<blocks(B + 1), 256, 0, st>>>(c.first_dummy, B + 1, INT32_MAX);
+    fill_i32<<<blocks(N + 1), 256, 0, st>>>(c.fd_in, N + 1, INT32_MAX);
+    fill_i32<<<blocks(N + 1), 256, 0, st>>>(c.fd_out, N + 1, INT32_MAX);
+    DN_CUDA(cudaMemsetAsync(c.real_in, 0, static_cast<size_t>(N + 1) * sizeof(int32_t), st));
+    DN_LAUNCHED();
+    if (E > 0) {
+        conj_edge_pass1<<<blocks(E), 256, 0, st>>>(B, edge_ptr, src, dst, e_isdummy, E, c);
+        conj_edge_pass2<<<blocks(E), 256, 0, st>>>(src, e_isdummy, E, c, cand_off);
+        DN_LAUNCHED();
+    }
+    int rc = dn4gl_exclusive_scan_i32(cand_off, cand_off, E, c.scan_ws, c.scan_bytes, stream);
+    if (rc != DN4GL_OK) return rc;
+    rc = dn4gl_exclusive_scan_i32(c.kept, c.kept, E, c.scan_ws, c.scan_bytes, stream);
+    if (rc != DN4GL_OK) return rc;
+    conj_graph_offsets<<<blocks(B + 1), 256, 0, st>>>(B, edge_ptr, c.kept, cand_off, o_node_ptr, o_edge_ptr);
+    if (E > 0) conj_newid<<<blocks(E), 256, 0, st>>>(e_isdummy, E, c, newid);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+__global__ void conj_fill_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ isd, int64_t E,
+                                 const int32_t *__restrict__ in_ptr, const int32_t *__restrict__ in_eid,
+                                 const int32_t *__restrict__ cand_off, const int32_t *__restrict__ newid, ConjWs c,
+                                 int32_t *__restrict__ o_src, int32_t *__restrict__ o_dst,
+                                 int32_t *__restrict__ o_v_origin, int32_t *__restrict__ o_e_shared) {
+    int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    bool d = isd && isd[e];
+    // conjugate vertex <- original edge (survivors only; kept[] is the scan, so compare neighbours)
+    if (c.kept[e + 1] != c.kept[e]) o_v_origin[c.kept[e]] = static_cast<int32_t>(e);
+    int pos = cand_off[e];
+    if (cand_off[e + 1] == pos) return;
+    int s = src[e];
+    int me = newid[e];
+    int fd_in = c.fd_in[s];
+    for (int p = in_ptr[s]; p < in_ptr[s + 1]; ++p) {
+        int ep = in_eid[p];
+        bool dp = isd && isd[ep];
+        bool keep = d ? !dp : (!dp || ep == fd_in);
+        if (keep) {
+            o_src[pos] = newid[ep];
+            o_dst[pos] = me;
+            o_e_shared[pos] = s;
+            ++pos;
+        }
+    }
+}
+
+extern "C" int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const int32_t *edge_ptr,
+                                       const int32_t *src, const int32_t *dst, const int32_t *e_isdummy, int64_t N,
+                                       int64_t E, const int32_t *in_ptr, const int32_t *in_eid,
+                                       const int32_t *cand_off, const int32_t *newid, const int32_t *o_node_ptr,
+                                       const int32_t *o_edge_ptr, int32_t *o_src, int32_t *o_dst,
+                                       int32_t *o_v_origin, int32_t *o_e_shared, void *ws, size_t ws_bytes,
+                                       void *stream) {
+    (void)node_ptr; (void)edge_ptr; (void)dst; (void)o_node_ptr; (void)o_edge_ptr;
+    DN_ARG(B >= 0 && N >= 0 && E >= 0);
+    if (E == 0) return DN4GL_OK;
+    DN_ARG(src && in_ptr && in_eid && cand_off && newid && o_v_origin);
+    ConjWs c;
+    if (!carve_conj_ws(ws, ws_bytes, B, N, E, &c)) {  // same workspace as _count, contents preserved
+        dn4gl_set_error("dn4gl_tu_conjugate_fill: workspace too small");
+        return DN4GL_EWORKSPACE;
+    }
+    conj_fill_kernel<<<static_cast<unsigned>(ceil_div64(E, 128)), 128, 0, as_stream(stream)>>>(
+        src, e_isdummy, E, in_ptr, in_eid, cand_off, newid, c, o_src, o_dst, o_v_origin, o_e_shared);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+// ===========================================================================================
+// a3: PyG read_tu_data [ext, torch-geometric 2.0.2]: remove_self_loops + coalesce.
+// Input: the edge list (src, dst in edge-id order) and its by-src CSR (row_ptr, items = edge ids
+// from dn4gl_build_csr(key=src)).  Rows are sorted in place by (dst, edge id), self loops and
+// repeated (src,dst) pairs are flagged out, survivors are compacted in (src, dst) order.
+__global__ void coalesce_flags(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ items,
+                               const int32_t *__restrict__ dst, int64_t N, int32_t *__restrict__ keep) {
+    // one thread per row (coalesce runs once per batch, not per layer)
+    int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int prev = -1;
+    for (int p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
+        int d = dst[items[p]];
+        keep[p] = (d != r && d != prev) ? 1 : 0;
+        prev = d;
+    }
+}
+
+__global__ void coalesce_compact(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ items,
+                                 const int32_t *__restrict__ dst, int64_t N,
+                                 const int32_t *__restrict__ keep_scan, int32_t *__restrict__ o_src,
+                                 int32_t *__restrict__ o_dst, int32_t *__restrict__ o_first) {
+    int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    for (int p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
+        int q = keep_scan[p];
+        if (keep_scan[p + 1] != q) {
+            o_src[q] = static_cast<int32_t>(r);
+            o_dst[q] = dst[items[p]];
+            o_first[q] = items[p];
+        }
+    }
+}
+
+extern "C" size_t dn4gl_coalesce_workspace_bytes(int64_t N, int64_t E) {
+    return align_up(static_cast<size_t>(N > 0 ? N : 1) * sizeof(int32_t), 256) + 256 +
+           dn4gl_scan_workspace_bytes(E + 1);
+}
+
+extern "C" int dn4gl_coalesce(const int32_t *dst, int64_t N, int64_t E, const int32_t *row_ptr, int32_t *items,
+                              int32_t *keep_scan, int32_t *o_src, int32_t *o_dst, int32_t *o_first, void *ws,
+                              size_t ws_bytes, int32_t *err_flag, void *stream) {
+    DN_ARG(N >= 0 && E >= 0 && row_ptr && keep_scan);
+    cudaStream_t st = as_stream(stream);
+    if (E == 0) {
+        DN_CUDA(cudaMemsetAsync(keep_scan, 0, sizeof(int32_t), st));
+        return DN4GL_OK;
+    }
+    DN_ARG(dst && items && o_src && o_dst && o_first);
+    WsCarver w(ws, ws_bytes);
+    int32_t *worklist = w.take<int32_t>(N);
+    int32_t *work_count = w.take<int32_t>(1);
+    size_t scan_bytes = dn4gl_scan_workspace_bytes(E + 1);
+    char *scan_ws = w.take<char>(scan_bytes);
+    if (!worklist || !work_count || !scan_ws) {
+        dn4gl_set_error("dn4gl_coalesce: workspace too small");
+        return DN4GL_EWORKSPACE;
+    }
+    int rc = dn4gl_sort_rows(row_ptr, N, items, dst, worklist, work_count, err_flag, st);
+    if (rc != DN4GL_OK) return rc;
+    coalesce_flags<<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, items, dst, N, keep_scan);
+    DN_LAUNCHED();
+    rc = dn4gl_exclusive_scan_i32(keep_scan, keep_scan, E, scan_ws, scan_bytes, stream);
+    if (rc != DN4GL_OK) return rc;
+    coalesce_compact<<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, items, dst, N, keep_scan,
+                                                                                 o_src, o_dst, o_first);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}

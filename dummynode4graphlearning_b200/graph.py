@@ -1,0 +1,219 @@
+"""Batched (block-diagonal) graph container living in HBM.
+
+Replaces, for the hot path, what the reference gets from ``dgl.batch`` /
+``Graph(dgl.DGLGraph)`` (subgraph_isomorphism/dataset.py:1053-1373, 1604-1636) and from PyG's
+``Batch`` (graph_classification/graph_neural_networks/main.py:245): frames are dicts of
+tensors keyed by the reference's constants (``"id"``, ``"label"``, ``"is_dummy"``,
+``"is_reversed"``, ``"in_deg"``, ``"out_deg"`` -- subgraph_isomorphism/constants.py:12-35), and
+the structure is an immutable pair of int32 CSRs (by destination for the forward gather, by
+source for the backward) built ONCE per mini-batch by the CUDA builder kernels.
+
+Layout in HBM: ``src``/``dst`` int32[E] in edge-id order, ``node_ptr``/
+``edge_ptr`` int32[B+1], CSR ``row_ptr`` int32[N+1], ``col`` int32[E], ``eid`` int32[E]; features
+fp32 row-major.
+"""
+import torch
+
+from ._lib import lib, ptr
+
+HEAVY_THRESHOLD = 64  # rows with more in-edges than this are reduced by a whole CTA (dummy nodes)
+
+_dev_bound = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def bind_device(device):
+    """cudaSetDevice for the library's (statically linked) runtime on this host thread."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if _dev_bound.get("idx") != idx:
+        lib().call("dn4gl_set_device", idx)
+        _dev_bound["idx"] = idx
+
+
+def require_cuda(t, what="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError("dummynode4graphlearning_b200: %s must live on a CUDA device -- the hot path has no "
+                           "CPU fallback" % what)
+    bind_device(t.device)
+
+
+class CSR:
+    """row_ptr[n_rows+1], col[nnz], eid[nnz] (all int32, device) + the heavy-row list."""
+
+    __slots__ = ("row_ptr", "col", "eid", "n_rows", "nnz", "heavy_rows", "heavy_count", "heavy_thr")
+
+    def __init__(self, row_ptr, col, eid, n_rows, nnz):
+        self.row_ptr, self.col, self.eid, self.n_rows, self.nnz = row_ptr, col, eid, n_rows, nnz
+        self.heavy_rows = self.heavy_count = None
+        self.heavy_thr = 0
+
+
+def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD):
+    """Stable CSR of the items 0..E-1 grouped by key (see dn4gl_build_csr)."""
+    require_cuda(key, "CSR key")
+    L = lib()
+    E = int(key.numel())
+    dev = key.device
+    row_ptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    eid = torch.empty(E, dtype=torch.int32, device=dev)
+    ws_bytes = L.size("dn4gl_csr_workspace_bytes", n_rows, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.call("dn4gl_build_csr", ptr(key), ptr(val), n_rows, E, ptr(row_ptr), ptr(col), ptr(eid),
+           ptr(ws), ws_bytes, ptr(err), _stream())
+    csr = CSR(row_ptr, col, eid, n_rows, E)
+    csr_err = err  # checked lazily by check_errors()
+    if heavy_threshold and heavy_threshold > 0 and E > 0:
+        cap = E // heavy_threshold + 1
+        csr.heavy_rows = torch.empty(cap, dtype=torch.int32, device=dev)
+        csr.heavy_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        csr.heavy_thr = heavy_threshold
+        L.call("dn4gl_collect_heavy_rows", ptr(row_ptr), n_rows, heavy_threshold, ptr(csr.heavy_rows), cap,
+               ptr(csr.heavy_count), _stream())
+    _pending_err.append(csr_err)
+    return csr
+
+
+_pending_err = []
+
+
+def check_errors():
+    """Synchronising check of the asynchronous capacity flags raised by builder kernels."""
+    global _pending_err
+    flags, _pending_err = _pending_err, []
+    for f in flags:
+        code = int(f.item())
+        if code != 0:
+            raise RuntimeError("dn4gl builder kernel reported error %d (row degree above DN4GL_MAX_ROW_DEGREE)" % code)
+
+
+def _i32(t, device):
+    return torch.as_tensor(t).to(device=device, dtype=torch.int32).contiguous()
+
+
+class BatchedGraph:
+    """DGL-flavoured view of a batch: ``ndata`` / ``edata`` frames + cached CSRs.
+
+    The message-passing layers accept this object wherever the reference passes a batched
+    ``dgl.DGLGraph`` (rgin.py:156, dmpnn.py:158)."""
+
+    def __init__(self, src, dst, node_ptr, edge_ptr, ndata=None, edata=None):
+        require_cuda(src, "graph structure")
+        self.src, self.dst = src.to(torch.int32).contiguous(), dst.to(torch.int32).contiguous()
+        self.node_ptr, self.edge_ptr = node_ptr.to(torch.int32).contiguous(), edge_ptr.to(torch.int32).contiguous()
+        self.ndata = dict(ndata or {})
+        self.edata = dict(edata or {})
+        self._n = None
+        self._csr_in = self._csr_out = None
+        self._cache = {}
+        self._host_sizes = None
+
+    # ---- construction -----------------------------------------------------------------------
+    @staticmethod
+    def from_batch(b, device, flavour="subgraph"):
+        """from a flat batch dict (synth.py / transforms.py layout, numpy or tensors)."""
+        dev = torch.device(device)
+        g = BatchedGraph(_i32(b["src"], dev), _i32(b["dst"], dev), _i32(b["node_ptr"], dev), _i32(b["edge_ptr"], dev))
+        names_n = {"vid": "id", "vlabel": "label", "v_is_dummy": "is_dummy", "v_is_reversed": "is_reversed"}
+        names_e = {"eid": "id", "elabel": "label", "e_is_dummy": "is_dummy", "e_is_reversed": "is_reversed"}
+        for k, name in names_n.items():
+            if k in b:
+                t = torch.as_tensor(b[k]).to(dev)
+                g.ndata[name] = t.bool() if name.startswith("is_") else t.long()
+        for k, name in names_e.items():
+            if k in b:
+                t = torch.as_tensor(b[k]).to(dev)
+                g.edata[name] = t.bool() if name.startswith("is_") else t.long()
+        g._n = int(b["node_ptr"][-1])
+        g._host_sizes = (torch.as_tensor(b["node_ptr"]).cpu().long(), torch.as_tensor(b["edge_ptr"]).cpu().long())
+        return g
+
+    # ---- DGL-like queries -----------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.src.device
+
+    @property
+    def batch_size(self):
+        return int(self.node_ptr.numel()) - 1
+
+    def number_of_nodes(self):
+        if self._n is None:
+            self._n = int(self.node_ptr[-1].item())
+        return self._n
+
+    def number_of_edges(self):
+        return int(self.src.numel())
+
+    def host_ptrs(self):
+        """(node_ptr, edge_ptr) as host int64 tensors (one D2H copy per batch, cached)."""
+        if self._host_sizes is None:
+            self._host_sizes = (self.node_ptr.cpu().long(), self.edge_ptr.cpu().long())
+        return self._host_sizes
+
+    def batch_num_nodes(self):
+        p = self.node_ptr.long()
+        return p[1:] - p[:-1]
+
+    def batch_num_edges(self):
+        p = self.edge_ptr.long()
+        return p[1:] - p[:-1]
+
+    def max_num_nodes(self):
+        p = self.host_ptrs()[0]
+        return int((p[1:] - p[:-1]).max().item()) if p.numel() > 1 else 0
+
+    def max_num_edges(self):
+        p = self.host_ptrs()[1]
+        return int((p[1:] - p[:-1]).max().item()) if p.numel() > 1 else 0
+
+    def all_edges(self, form="uv", order="eid"):
+        if order != "eid":
+            raise NotImplementedError("only order='eid' is provided on the hot path")
+        u, v = self.src.long(), self.dst.long()
+        if form == "uv":
+            return u, v
+        if form == "all":
+            return u, v, torch.arange(u.numel(), device=u.device)
+        raise ValueError(form)
+
+    def to(self, device):
+        if torch.device(device) != self.device:
+            raise NotImplementedError("BatchedGraph is built directly in HBM; build it on the target device")
+        return self
+
+    # ---- structure caches ---------------------------------------------------------------------------
+    @property
+    def csr_in(self):
+        """in-edges of every node: row v lists (src, eid) of edges with dst = v, ascending eid."""
+        if self._csr_in is None:
+            self._csr_in = build_csr(self.dst, self.src, self.number_of_nodes())
+        return self._csr_in
+
+    @property
+    def csr_out(self):
+        """out-edges of every node (transpose): row u lists (dst, eid) of edges with src = u."""
+        if self._csr_out is None:
+            self._csr_out = build_csr(self.src, self.dst, self.number_of_nodes())
+        return self._csr_out
+
+    def in_degrees(self):
+        if "in_deg" not in self.ndata:
+            rp = self.csr_in.row_ptr.long()
+            self.ndata["in_deg"] = rp[1:] - rp[:-1]
+        return self.ndata["in_deg"]
+
+    def out_degrees(self):
+        if "out_deg" not in self.ndata:
+            rp = self.csr_out.row_ptr.long()
+            self.ndata["out_deg"] = rp[1:] - rp[:-1]
+        return self.ndata["out_deg"]
+
+    def cached(self, key, builder):
+        if key not in self._cache:
+            self._cache[key] = builder()
+        return self._cache[key]

@@ -1,0 +1,203 @@
+"""torch.autograd wrappers over the C-ABI kernels (forward AND hand-written backward).
+
+PyTorch supplies device memory, streams and the autograd tape; every aggregation, readout and
+per-edge op below runs in libdn4gl.so.  None of these functions has a CPU or pure-PyTorch
+implementation: tensors must be CUDA fp32, otherwise an error is raised.
+"""
+import torch
+
+from ._lib import lib, ptr
+from .graph import CSR, _stream, require_cuda
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError("expected float32, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def _spmm(csr: CSR, x, n_out, self_scale):
+    require_cuda(x, "features")
+    x = _f32c(x)
+    D = x.size(1)
+    out = torch.empty((n_out, D), dtype=torch.float32, device=x.device)
+    lib().call("dn4gl_spmm_sum_f32", ptr(csr.row_ptr), ptr(csr.col), ptr(x), ptr(out), n_out, x.size(0), D,
+               float(self_scale), ptr(csr.heavy_rows), ptr(csr.heavy_count), csr.heavy_thr, _stream())
+    return out
+
+
+class _SpmmSum(torch.autograd.Function):
+    """out[v] = self_scale * x[v] + sum_{p in row v} x[col[p]]   (K1).  The adjoint is the same
+    kernel on the transposed CSR, so the backward is deterministic and atomic-free."""
+
+    @staticmethod
+    def forward(ctx, x, csr_fwd, csr_bwd, self_scale):
+        ctx.csr_bwd, ctx.self_scale, ctx.n_src = csr_bwd, self_scale, x.size(0)
+        return _spmm(csr_fwd, x, csr_fwd.n_rows, self_scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _spmm(ctx.csr_bwd, g, ctx.n_src, ctx.self_scale), None, None, None
+
+
+def spmm_sum(x, csr_fwd, csr_bwd, self_scale=0.0):
+    """Sum aggregation over a CSR; ``csr_bwd`` must be the transpose of ``csr_fwd``."""
+    return _SpmmSum.apply(x, csr_fwd, csr_bwd, float(self_scale))
+
+
+def graph_sum_aggregate(graph, x, self_scale=0.0):
+    """agg[v] = self_scale*x[v] + sum over in-edges (u -> v) of x[u]: DGL ``update_all(copy_u, fn.sum)`` /
+    PyG ``propagate(aggr='add')``."""
+    return spmm_sum(x, graph.csr_in, graph.csr_out, self_scale)
+
+
+# ---------------------------------------------------------------------------------------------
+class _SegmentSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, seg_ptr, mask, mode):
+        require_cuda(x, "features")
+        x = _f32c(x)
+        B, D = seg_ptr.numel() - 1, x.size(1)
+        out = torch.empty((B, D), dtype=torch.float32, device=x.device)
+        lib().call("dn4gl_segment_sum_f32", ptr(seg_ptr), ptr(mask), ptr(x), ptr(out), B, D, mode, _stream())
+        ctx.seg_ptr, ctx.mask, ctx.mode, ctx.n = seg_ptr, mask, mode, x.size(0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        B, D = g.shape
+        gx = torch.empty((ctx.n, D), dtype=torch.float32, device=g.device)
+        lib().call("dn4gl_segment_bcast_f32", ptr(ctx.seg_ptr), ptr(ctx.mask), ptr(g), ptr(gx), B, ctx.n, D,
+                   ctx.mode, _stream())
+        return gx, None, None, None
+
+
+def segment_sum(x, seg_ptr, mask=None, mean=False):
+    """per-graph readout over contiguous segments (K3); mask: uint8/bool, 1 = skip row."""
+    if mask is not None:
+        mask = mask.to(torch.uint8).contiguous()
+    return _SegmentSum.apply(x, seg_ptr, mask, 1 if mean else 0)
+
+
+class _PadSegments(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, seg_ptr, mask, Lmax):
+        require_cuda(x, "features")
+        x = _f32c(x)
+        B, D = seg_ptr.numel() - 1, x.size(1)
+        out = torch.empty((B, Lmax, D), dtype=torch.float32, device=x.device)
+        lib().call("dn4gl_pad_segments_f32", ptr(seg_ptr), ptr(mask), ptr(x), ptr(out), B, Lmax, D, _stream())
+        ctx.seg_ptr, ctx.mask, ctx.n = seg_ptr, mask, x.size(0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        B, Lmax, D = g.shape
+        gx = torch.empty((ctx.n, D), dtype=torch.float32, device=g.device)
+        lib().call("dn4gl_unpad_segments_f32", ptr(ctx.seg_ptr), ptr(ctx.mask), ptr(g), ptr(gx), B, Lmax, D, ctx.n,
+                   _stream())
+        return gx, None, None, None
+
+
+def pad_segments(x, seg_ptr, Lmax, mask=None):
+    """left-padded (B, Lmax, D) batchify of ragged rows; rows with mask=1 are zeroed
+    (split_and_batchify_graph_feats(pre_pad=True) + masked_fill, utils/dl.py:51-81)."""
+    if mask is not None:
+        mask = mask.to(torch.uint8).contiguous()
+    return _PadSegments.apply(x, seg_ptr, mask, int(Lmax))
+
+
+def label_filter_gate(graph, pattern, Lp_max):
+    """(N_g, 1) float gate of ScalarFilter (filter.py:10-16) without the (B, Lg, Lp) temporary."""
+    g_label = graph.cached("label_i32", lambda: graph.ndata["label"].to(torch.int32).contiguous())
+    p_label = pattern.cached("label_i32", lambda: pattern.ndata["label"].to(torch.int32).contiguous())
+    require_cuda(g_label, "labels")
+    Ng = g_label.numel()
+    gate = torch.empty((Ng, 1), dtype=torch.float32, device=g_label.device)
+    lib().call("dn4gl_label_filter_gate", ptr(graph.node_ptr), ptr(g_label), ptr(pattern.node_ptr), ptr(p_label),
+               graph.batch_size, int(Lp_max), Ng, ptr(gate), _stream())
+    return gate
+
+
+# ---------------------------------------------------------------------------------------------
+def _rev_u8(graph):
+    if "is_reversed" not in graph.edata:
+        return None
+    return graph.cached("rev_u8", lambda: graph.edata["is_reversed"].to(torch.uint8).contiguous())
+
+
+class _DmpNodeAgg(torch.autograd.Function):
+    """S[v] = [sum_{in(v), rev} ef | sum_{in(v), !rev} ef]   (K4)."""
+
+    @staticmethod
+    def forward(ctx, ef, graph):
+        require_cuda(ef, "edge features")
+        ef = _f32c(ef)
+        N, D = graph.number_of_nodes(), ef.size(1)
+        csr = graph.csr_in
+        S = torch.empty((N, 2 * D), dtype=torch.float32, device=ef.device)
+        lib().call("dn4gl_dmp_node_agg_f32", ptr(csr.row_ptr), ptr(csr.eid), ptr(_rev_u8(graph)), ptr(ef), ptr(S), N, D,
+                   ptr(csr.heavy_rows), ptr(csr.heavy_count), csr.heavy_thr, _stream())
+        ctx.graph = graph
+        return S
+
+    @staticmethod
+    def backward(ctx, gS):
+        graph = ctx.graph
+        gS = _f32c(gS)
+        E, D = graph.number_of_edges(), gS.size(1) // 2
+        gef = torch.empty((E, D), dtype=torch.float32, device=gS.device)
+        lib().call("dn4gl_dmp_node_agg_bwd_f32", ptr(graph.dst), ptr(_rev_u8(graph)), ptr(gS), ptr(gef), E, D, _stream())
+        return gef, None
+
+
+def dmp_node_agg(ef, graph):
+    return _DmpNodeAgg.apply(ef, graph)
+
+
+class _DmpEdgeUpdate(torch.autograd.Function):
+    """out[e] = T[e,:D] + c_e T[e,D:] + (rev ? P[src]-Q[dst] : P[dst]-Q[src]) + bias   (K5)."""
+
+    @staticmethod
+    def forward(ctx, PQ, T, bias, graph):
+        require_cuda(PQ, "node projections")
+        PQ, T = _f32c(PQ), _f32c(T)
+        E, D = graph.number_of_edges(), T.size(1) // 2
+        out_deg = graph.cached("out_deg_i32", lambda: graph.out_degrees().to(torch.int32).contiguous())
+        out = torch.empty((E, D), dtype=torch.float32, device=T.device)
+        b = None if bias is None else _f32c(bias)
+        lib().call("dn4gl_dmp_edge_update_f32", ptr(graph.src), ptr(graph.dst), ptr(_rev_u8(graph)), ptr(out_deg),
+                   ptr(PQ), ptr(T), ptr(b), ptr(out), E, D, _stream())
+        ctx.graph, ctx.has_bias, ctx.out_deg = graph, bias is not None, out_deg
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        graph = ctx.graph
+        g = _f32c(g)
+        E, D = g.shape
+        N = graph.number_of_nodes()
+        gT = torch.empty((E, 2 * D), dtype=torch.float32, device=g.device)
+        lib().call("dn4gl_dmp_edge_update_bwd_T_f32", ptr(graph.dst), ptr(ctx.out_deg), ptr(g), ptr(gT), E, D, _stream())
+        gPQ = torch.empty((N, 2 * D), dtype=torch.float32, device=g.device)
+        ci, co = graph.csr_in, graph.csr_out
+        lib().call("dn4gl_dmp_edge_update_bwd_PQ_f32", ptr(ci.row_ptr), ptr(ci.eid), ptr(co.row_ptr), ptr(co.eid),
+                   ptr(_rev_u8(graph)), ptr(g), ptr(gPQ), N, D, _stream())
+        gb = g.sum(dim=0) if ctx.has_bias else None
+        return gPQ, gT, gb, None
+
+
+def dmp_edge_update(PQ, T, bias, graph):
+    return _DmpEdgeUpdate.apply(PQ, T, bias, graph)
+
+
+def gather_rows(x, idx_i32):
+    """out[i] = x[idx[i]] (no autograd; used for attribute plumbing of the transforms)."""
+    require_cuda(x, "rows")
+    x = _f32c(x)
+    n, D = idx_i32.numel(), x.size(1)
+    out = torch.empty((n, D), dtype=torch.float32, device=x.device)
+    lib().call("dn4gl_gather_rows_f32", ptr(idx_i32), ptr(x), ptr(out), n, D, _stream())
+    return out

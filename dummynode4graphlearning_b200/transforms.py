@@ -1,0 +1,219 @@
+"""GPU graph transforms (dummy-node augmentation, edge-to-vertex transform, PyG canonicalisation).
+
+Host-side mirror of the reference functions, operating on whole mini-batches in HBM:
+
+=========================================  ==================================================
+reference (file:line)                      here
+=========================================  ==================================================
+load_graph_data_from_TUDatadir(with_dummy) ``tu_add_dummy``      (tu_data_processing.py:186-214)
+convert_conjugate_graph_forward            ``tu_conjugate``      (tu_data_processing.py:223-338)
+PyG read_tu_data + set_dummy_flags         ``pyg_canonicalize``  (graph_neural_networks/dataset.py:118-151)
+add_dummy_nodes_edges (GraphAdj branch)    ``sub_add_dummy``     (subgraph_isomorphism/train.py:404-474)
+process_model_config                       ``process_model_config`` (train.py:38-81)
+=========================================  ==================================================
+
+Batches are dicts of int32 device tensors in the flat layout of ``synth.py``:
+``node_ptr, edge_ptr, src, dst`` (global ids) + attribute columns.  All index outputs are
+bit-exact with the reference (tests/test_transforms_gpu.py).
+"""
+import math
+from copy import deepcopy
+
+import torch
+
+from ._lib import lib, ptr
+from .graph import _pending_err, _stream, build_csr, require_cuda
+
+
+def to_device(b, device):
+    """numpy/tensor batch dict -> int32 (float32 for *attr) device tensors."""
+    dev = torch.device(device)
+    out = {}
+    for k, v in b.items():
+        if k in ("num_graphs", "has_edge_labels"):
+            out[k] = v
+        elif k.endswith("attr"):
+            out[k] = torch.as_tensor(v).to(dev, torch.float32).contiguous()
+        elif k == "y":
+            out[k] = torch.as_tensor(v).to(dev, torch.int64)
+        else:
+            out[k] = torch.as_tensor(v).to(dev, torch.int32).contiguous()
+    return out
+
+
+def _empty_i32(n, dev):
+    return torch.empty(int(n), dtype=torch.int32, device=dev)
+
+
+def _local_ids(ptrs, total, dev):
+    """position within the segment for every element (ID = range(...), tu_data_processing.py:213-214)."""
+    counts = (ptrs[1:] - ptrs[:-1]).long()
+    starts = torch.repeat_interleave(ptrs[:-1].long(), counts, output_size=int(total))
+    return (torch.arange(int(total), device=dev) - starts).to(torch.int32)
+
+
+def tu_add_dummy(b):
+    """+1 dummy node (LABEL 0) and 2n interleaved dummy edges per graph."""
+    require_cuda(b["src"], "batch")
+    dev = b["src"].device
+    B, N, E = int(b["num_graphs"]), int(b["vlabel"].numel()), int(b["src"].numel())
+    o = dict(num_graphs=B, node_ptr=_empty_i32(B + 1, dev), edge_ptr=_empty_i32(B + 1, dev),
+             src=_empty_i32(E + 2 * N, dev), dst=_empty_i32(E + 2 * N, dev),
+             vlabel=_empty_i32(N + B, dev), v_is_dummy=_empty_i32(N + B, dev),
+             elabel=_empty_i32(E + 2 * N, dev), e_is_dummy=_empty_i32(E + 2 * N, dev))
+    lib().call("dn4gl_tu_add_dummy", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
+               ptr(b["vlabel"]), ptr(b["elabel"]), N, E,
+               ptr(o["node_ptr"]), ptr(o["edge_ptr"]), ptr(o["src"]), ptr(o["dst"]),
+               ptr(o["vlabel"]), ptr(o["v_is_dummy"]), ptr(o["elabel"]), ptr(o["e_is_dummy"]), _stream())
+    o["vid"] = _local_ids(o["node_ptr"], N + B, dev)
+    o["eid"] = _local_ids(o["edge_ptr"], E + 2 * N, dev)
+    if "vattr" in b:  # dummy node gets attribute 0 (line 191)
+        va = torch.zeros(N + B, dtype=torch.float32, device=dev)
+        va[o["v_is_dummy"] == 0] = b["vattr"]
+        o["vattr"] = va
+    if "y" in b:
+        o["y"] = b["y"]
+    return o
+
+
+def tu_conjugate(b):
+    """edge-to-vertex transform of a TU-flavoured batch (raw -> LINE_, dummy-augmented -> CONJ_)."""
+    require_cuda(b["src"], "batch")
+    L = lib()
+    dev = b["src"].device
+    B, N, E = int(b["num_graphs"]), int(b["vlabel"].numel()), int(b["src"].numel())
+    isd = b.get("e_is_dummy")
+    csr_in = build_csr(b["dst"], b["src"], N, heavy_threshold=0)
+    ws_bytes = L.size("dn4gl_conj_workspace_bytes", B, N, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cand_off, newid = _empty_i32(E + 1, dev), _empty_i32(max(E, 1), dev)
+    o_node_ptr, o_edge_ptr = _empty_i32(B + 1, dev), _empty_i32(B + 1, dev)
+    L.call("dn4gl_tu_conjugate_count", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
+           ptr(isd), N, E, ptr(csr_in.row_ptr), ptr(csr_in.eid), ptr(cand_off), ptr(newid),
+           ptr(o_node_ptr), ptr(o_edge_ptr), ptr(ws), ws_bytes, _stream())
+    sizes = torch.stack([o_node_ptr[-1], o_edge_ptr[-1]]).cpu()  # the one D2H sync: output sizes
+    V2, E2 = int(sizes[0]), int(sizes[1])
+    o = dict(num_graphs=B, node_ptr=o_node_ptr, edge_ptr=o_edge_ptr,
+             src=_empty_i32(E2, dev), dst=_empty_i32(E2, dev),
+             v_origin=_empty_i32(V2, dev), e_shared=_empty_i32(E2, dev))
+    L.call("dn4gl_tu_conjugate_fill", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
+           ptr(isd), N, E, ptr(csr_in.row_ptr), ptr(csr_in.eid), ptr(cand_off), ptr(newid),
+           ptr(o_node_ptr), ptr(o_edge_ptr), ptr(o["src"]), ptr(o["dst"]), ptr(o["v_origin"]), ptr(o["e_shared"]),
+           ptr(ws), ws_bytes, _stream())
+    vo, es = o["v_origin"].long(), o["e_shared"].long()
+    # vertex attributes <- original edge attributes (lines 238-242), edge attributes <- shared vertex (322-326)
+    o["vlabel"] = b["elabel"][vo]
+    o["elabel"] = b["vlabel"][es]
+    eid = b["eid"] if "eid" in b else _local_ids(b["edge_ptr"], E, dev)
+    vid = b["vid"] if "vid" in b else _local_ids(b["node_ptr"], N, dev)
+    o["vid"], o["eid"] = eid[vo], vid[es]
+    if isd is not None:
+        o["v_is_dummy"] = isd[vo]
+        o["e_is_dummy"] = b["v_is_dummy"][es]
+    if "vattr" in b:
+        o["eattr"] = b["vattr"][es]
+    if "y" in b:
+        o["y"] = b["y"]
+    return o
+
+
+def sub_add_dummy(b, max_nv, max_nvl, max_ne, max_nel):
+    """subgraph-isomorphism dummy augmentation; max_* are the PRE-augmentation maxima passed at
+    train.py:1322-1334."""
+    require_cuda(b["src"], "batch")
+    dev = b["src"].device
+    B, N, E = int(b["num_graphs"]), int(b["vlabel"].numel()), int(b["src"].numel())
+    o = dict(num_graphs=B, node_ptr=_empty_i32(B + 1, dev), edge_ptr=_empty_i32(B + 1, dev),
+             src=_empty_i32(E + 2 * N, dev), dst=_empty_i32(E + 2 * N, dev))
+    for k in ("vid", "vlabel", "v_is_dummy"):
+        o[k] = _empty_i32(N + B, dev)
+    for k in ("eid", "elabel", "e_is_dummy", "e_is_reversed"):
+        o[k] = _empty_i32(E + 2 * N, dev)
+    lib().call("dn4gl_sub_add_dummy", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
+               ptr(b["vid"]), ptr(b["vlabel"]), ptr(b["eid"]), ptr(b["elabel"]), ptr(b.get("e_is_reversed")),
+               N, E, int(max_nv), int(max_nvl), int(max_ne), int(max_nel),
+               ptr(o["node_ptr"]), ptr(o["edge_ptr"]), ptr(o["src"]), ptr(o["dst"]),
+               ptr(o["vid"]), ptr(o["vlabel"]), ptr(o["v_is_dummy"]),
+               ptr(o["eid"]), ptr(o["elabel"]), ptr(o["e_is_dummy"]), ptr(o["e_is_reversed"]), _stream())
+    return o
+
+
+def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None):
+    """What PyG ``read_tu_data`` + ``PYGDataset.set_dummy_flags`` turn the saved TU files into
+    (graph_neural_networks/dataset.py:118-151): one-hot ``x`` (attribute column first, then labels
+    shifted to start at 0), ``edge_index`` int64 with self loops removed and coalesced = sorted by
+    (row, col) with duplicates merged, ``edge_attr`` (one-hot labels, summed over merged
+    duplicates), ``batch``, ``is_dummy_node`` / ``is_dummy_edge``."""
+    require_cuda(b["src"], "batch")
+    L = lib()
+    dev = b["src"].device
+    B, N, E = int(b["num_graphs"]), int(b["vlabel"].numel()), int(b["src"].numel())
+    csr_out = build_csr(b["src"], b["dst"], N, heavy_threshold=0)
+    keep_scan = _empty_i32(E + 1, dev)
+    o_src, o_dst, o_first = _empty_i32(E, dev), _empty_i32(E, dev), _empty_i32(E, dev)
+    ws_bytes = L.size("dn4gl_coalesce_workspace_bytes", N, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.call("dn4gl_coalesce", ptr(b["dst"]), N, E, ptr(csr_out.row_ptr), ptr(csr_out.eid), ptr(keep_scan),
+           ptr(o_src), ptr(o_dst), ptr(o_first), ptr(ws), ws_bytes, ptr(err), _stream())
+    _pending_err.append(err)
+    E2 = int(keep_scan[-1].item())
+    o_src, o_dst, o_first = o_src[:E2], o_dst[:E2], o_first[:E2]
+    # node features: [attr?, one_hot(label - min)]
+    vl = b["vlabel"].long()
+    vmin = int(vl.min().item()) if N else 0
+    nvl = int(num_node_labels) if num_node_labels is not None else (int(vl.max().item()) - vmin + 1 if N else 0)
+    x = torch.zeros((N, nvl), dtype=torch.float32, device=dev)
+    x.scatter_(1, (vl - vmin).view(-1, 1), 1.0)
+    n_attr = 0
+    if "vattr" in b:
+        x = torch.cat([b["vattr"].view(N, -1), x], dim=1)
+        n_attr = x.size(1) - nvl
+    out = dict(num_graphs=B, x=x, edge_index=torch.stack([o_src.long(), o_dst.long()]),
+               node_ptr=b["node_ptr"], src=o_src, dst=o_dst, first_edge=o_first,
+               batch=torch.repeat_interleave(torch.arange(B, device=dev),
+                                             (b["node_ptr"][1:] - b["node_ptr"][:-1]).long(), output_size=N))
+    if b.get("has_edge_labels", True) and E > 0:
+        el = b["elabel"].long()
+        emin = int(el.min().item())
+        nel = int(num_edge_labels) if num_edge_labels is not None else int(el.max().item()) - emin + 1
+        # summed one-hot attributes of merged duplicates = per-label multiplicity of the (src,dst) pair
+        oh = torch.zeros((E, nel), dtype=torch.float32, device=dev)
+        oh.scatter_(1, (el - emin).view(-1, 1), 1.0)
+        group = (keep_scan[1:].long() - 1)  # sorted position -> output edge
+        sorted_items = csr_out.eid.long()
+        valid = b["src"].long()[sorted_items] != b["dst"].long()[sorted_items]
+        edge_attr = torch.zeros((E2, nel), dtype=torch.float32, device=dev)
+        edge_attr.index_add_(0, group[valid], oh[sorted_items[valid]])
+        out["edge_attr"] = edge_attr
+        out["is_dummy_edge"] = edge_attr[:, 0].bool()  # set_dummy_flags: column num_edge_attributes (=0)
+    out["is_dummy_node"] = x[:, n_attr].bool()
+    if "y" in b:
+        out["y"] = b["y"]
+    return out
+
+
+def process_model_config(config):
+    """max_* bookkeeping of the augmentations (subgraph_isomorphism/train.py:38-81)."""
+    mc = deepcopy(config)
+    if config.get("add_rev", False):
+        for k in ("max_nge", "max_ngel", "max_npe", "max_npel"):
+            mc[k] *= 2
+    if config.get("add_dummy", False):
+        mc["max_nge"] += config["max_ngv"] * 2
+        mc["max_npe"] += config["max_npv"] * 2
+        mc["max_ngel"] += 2
+        mc["max_npel"] += 2
+        for k in ("max_ngv", "max_npv", "max_ngvl", "max_npvl"):
+            mc[k] += 1
+    if config.get("convert_conj", False):
+        max_ngv, max_npv = mc["max_ngv"], mc["max_npv"]
+        avg_gd = math.ceil(mc["max_nge"] / mc["max_ngv"])
+        avg_pd = math.ceil(mc["max_npe"] / mc["max_npv"])
+        mc["max_ngv"] = mc["max_nge"]
+        mc["max_nge"] = (avg_gd * avg_gd) * max_ngv // 2 - max_ngv
+        mc["max_npv"] = mc["max_npe"]
+        mc["max_npe"] = (avg_pd * avg_pd) * max_npv // 2 - max_npv
+        mc["max_ngvl"] = mc["max_ngel"]
+        mc["max_npvl"] = mc["max_npel"]
+    return mc

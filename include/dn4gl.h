@@ -1,0 +1,219 @@
+/*
+ * dn4gl.h -- C ABI of libdn4gl.so: the B200 (sm_100a) message-passing hot path of
+ * DummyNode4GraphLearning.
+ *
+ * The reference has no FFI of its own: its hot path sits behind Python operator boundaries
+ * into third-party extensions.  Each entry point below names the
+ * reference call site / third-party op it replaces.  A reference maintainer binds these with
+ * ctypes; dummynode4graphlearning_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the parameter name ends in _h;
+ *  - every function only enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *    returns immediately; nothing allocates, nothing synchronises, no global mutable state
+ *    except the thread-local error string;
+ *  - the caller owns all buffers (sizes documented per function; workspace sizes are queried);
+ *  - indices are int32 (the reference uses int64; the host converts once per batch and
+ *    checks N, E < 2^31), features are fp32 row-major contiguous with D % 4 == 0 and 16-byte
+ *    aligned base pointers (128-bit loads);
+ *  - return value: 0 on success, negative DN4GL_E* on failure, text via dn4gl_last_error();
+ *  - kernels are deterministic (no floating-point atomics): repeated runs are bit-identical.
+ */
+#ifndef DN4GL_H
+#define DN4GL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DN4GL_OK 0
+#define DN4GL_EINVAL (-1)   /* bad shape / alignment / null pointer                         */
+#define DN4GL_ECUDA (-2)    /* a CUDA runtime call or launch failed                         */
+#define DN4GL_ELIMIT (-3)   /* a documented capacity limit was exceeded                     */
+#define DN4GL_EWORKSPACE (-4) /* workspace too small                                        */
+
+#define DN4GL_ABI_VERSION 1
+
+int dn4gl_version(void);
+const char *dn4gl_last_error(void);
+/* binds the calling thread to `device` (cudaSetDevice); one process per GPU is the intended use */
+int dn4gl_set_device(int device);
+
+/* ---- integer plumbing ------------------------------------------------------------------- */
+
+size_t dn4gl_scan_workspace_bytes(int64_t n);
+/* out[i] = sum_{j<i} in[j]; out has n+1 elements (out[n] = total).  in may alias out.        */
+int dn4gl_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n,
+                             void *ws, size_t ws_bytes, void *stream);
+
+/* CSR build: groups the E items by key[e] in [0, N), STABLE in item order (row r lists its
+ * items with ascending e), which is the order DGL's gspmm / torch-scatter's CPU path and the
+ * reference's `sorted(graph.incident(v, "in"))` (tu_data_processing.py:266,
+ * utils/graph.py:123,219) iterate in.  row_ptr[N+1], col[E] = val[e] (or e if val NULL), eid[E].
+ * Limit: a single row may hold at most DN4GL_MAX_ROW_DEGREE items (DN4GL_ELIMIT is reported
+ * asynchronously through err_flag if exceeded; pass NULL to skip).                           */
+#define DN4GL_MAX_ROW_DEGREE 24576
+size_t dn4gl_csr_workspace_bytes(int64_t N, int64_t E);
+int dn4gl_build_csr(const int32_t *key, const int32_t *val, int64_t N, int64_t E,
+                    int32_t *row_ptr, int32_t *col, int32_t *eid,
+                    void *ws, size_t ws_bytes, int32_t *err_flag, void *stream);
+
+/* list of rows with degree > threshold (for the heavy-row path of the aggregation kernels):
+ * heavy_rows[cap], heavy_count[1]; cap >= E / threshold + 1; list order is unspecified.         */
+int dn4gl_collect_heavy_rows(const int32_t *row_ptr, int64_t N, int32_t threshold,
+                             int32_t *heavy_rows, int32_t cap, int32_t *heavy_count, void *stream);
+
+/* ---- a1 / a4: dummy-node augmentation ---------------------------------------------------- */
+
+/* classification flavour, replaces load_graph_data_from_TUDatadir(with_dummy=True)'s graph
+ * construction (graph_classification/data_processing/tu_data_processing.py:186-214):
+ * per graph +1 node (LABEL 0, IS_DUMMY 1) and 2n dummy edges INTERLEAVED (n,v),(v,n) after the
+ * m real edges.  Inputs: B graphs, node_ptr[B+1], edge_ptr[B+1], global src/dst[E], vlabel[N],
+ * elabel[E].  Outputs sized N+B nodes / E+2N edges (+ ptr arrays of B+1).                     */
+int dn4gl_tu_add_dummy(int32_t B, const int32_t *node_ptr, const int32_t *edge_ptr,
+                       const int32_t *src, const int32_t *dst,
+                       const int32_t *vlabel, const int32_t *elabel, int64_t N, int64_t E,
+                       int32_t *o_node_ptr, int32_t *o_edge_ptr, int32_t *o_src, int32_t *o_dst,
+                       int32_t *o_vlabel, int32_t *o_vdummy, int32_t *o_elabel, int32_t *o_edummy,
+                       void *stream);
+
+/* subgraph-isomorphism flavour, replaces add_dummy_nodes_edges, GraphAdj branch
+ * (subgraph_isomorphism/train.py:404-474; Graph.add_nodes/add_edges dataset.py:1238-1293):
+ * +1 node {id:max_nv, label:max_nvl, is_dummy:1}; 2n edges BLOCKED [u->d]*n then [d->u]*n with
+ * id max_ne / max_ne+1, label max_nel / max_nel+1, is_dummy 1, is_reversed 0..0 1..1.
+ * e_isrev may be NULL.                                                                       */
+int dn4gl_sub_add_dummy(int32_t B, const int32_t *node_ptr, const int32_t *edge_ptr,
+                        const int32_t *src, const int32_t *dst,
+                        const int32_t *vid, const int32_t *vlabel,
+                        const int32_t *eid, const int32_t *elabel, const int32_t *e_isrev,
+                        int64_t N, int64_t E,
+                        int32_t max_nv, int32_t max_nvl, int32_t max_ne, int32_t max_nel,
+                        int32_t *o_node_ptr, int32_t *o_edge_ptr, int32_t *o_src, int32_t *o_dst,
+                        int32_t *o_vid, int32_t *o_vlabel, int32_t *o_vdummy,
+                        int32_t *o_eid, int32_t *o_elabel, int32_t *o_edummy, int32_t *o_erev,
+                        void *stream);
+
+/* ---- a2 / a5: edge-to-vertex ("conjugate") transform -------------------------------------- */
+
+/* classification flavour, replaces convert_conjugate_graph_forward
+ * (tu_data_processing.py:223-338) for graphs whose edge IDs are their positions (what
+ * load_graph_data_from_TUDatadir produces).  Two phases so the caller can allocate:
+ *   _count: needs in_ptr/in_eid = dn4gl_build_csr(key=dst) and out-CSR row_ptr by src
+ *           (out_ptr); writes per-edge survivor counts' scan cand_off[E+1], per-graph vertex
+ *           and edge offsets o_node_ptr[B+1], o_edge_ptr[B+1], vertex renumbering newid[E].
+ *   _fill:  writes o_src/o_dst (global conjugate vertex ids), o_v_origin[V'] (original edge
+ *           of each conjugate vertex) and o_e_shared[E'] (shared original vertex of each
+ *           conjugate edge) in exactly the reference's order.
+ * e_isdummy may be NULL (LINE_ graphs).  ws from dn4gl_conj_workspace_bytes.                 */
+size_t dn4gl_conj_workspace_bytes(int32_t B, int64_t N, int64_t E);
+int dn4gl_tu_conjugate_count(int32_t B, const int32_t *node_ptr, const int32_t *edge_ptr,
+                             const int32_t *src, const int32_t *dst, const int32_t *e_isdummy,
+                             int64_t N, int64_t E,
+                             const int32_t *in_ptr, const int32_t *in_eid,
+                             int32_t *cand_off, int32_t *newid,
+                             int32_t *o_node_ptr, int32_t *o_edge_ptr,
+                             void *ws, size_t ws_bytes, void *stream);
+int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const int32_t *edge_ptr,
+                            const int32_t *src, const int32_t *dst, const int32_t *e_isdummy,
+                            int64_t N, int64_t E,
+                            const int32_t *in_ptr, const int32_t *in_eid,
+                            const int32_t *cand_off, const int32_t *newid,
+                            const int32_t *o_node_ptr, const int32_t *o_edge_ptr,
+                            int32_t *o_src, int32_t *o_dst, int32_t *o_v_origin, int32_t *o_e_shared,
+                            void *ws, size_t ws_bytes, void *stream);
+
+/* ---- a3: PyG read_tu_data canonicalisation ------------------------------------------------- */
+/* remove_self_loops + coalesce [torch-geometric 2.0.2 read_tu_data, called from
+ * graph_classification/graph_neural_networks/dataset.py:151]: given the edge list's destinations
+ * dst[E] (edge-id order) and its by-src CSR (row_ptr[N+1], items[E] = edge ids, from
+ * dn4gl_build_csr(key=src)), sorts every row in place by (dst, edge id), drops self loops, merges
+ * repeated (src,dst) pairs.  keep_scan[E+1] = exclusive scan of survivor flags in sorted order;
+ * survivors are written compacted in (src,dst) order: o_src/o_dst/o_first[<=E] (o_first = first
+ * original edge of each merged group).  E' = keep_scan[E].                                    */
+size_t dn4gl_coalesce_workspace_bytes(int64_t N, int64_t E);
+int dn4gl_coalesce(const int32_t *dst, int64_t N, int64_t E, const int32_t *row_ptr, int32_t *items,
+                   int32_t *keep_scan, int32_t *o_src, int32_t *o_dst, int32_t *o_first,
+                   void *ws, size_t ws_bytes, int32_t *err_flag, void *stream);
+
+/* ---- K1: sum aggregation -------------------------------------------------------------------- */
+/* out[v,:] = self_scale * x[v,:] + sum_{p in [row_ptr[v], row_ptr[v+1])} x[col[p],:]
+ * replaces torch_scatter.scatter(reduce='sum') under PyG GINConv.propagate (gconv.py:212) and
+ * DGL update_all(copy, fn.sum) -> gspmm (rgin.py:159).  With the transposed CSR it is its own
+ * backward.  x has n_src rows, out has N rows (x may be a different table than out: RGIN gathers
+ * from the (N*R, D) per-relation table).  Rows listed in heavy_rows (degree > heavy threshold,
+ * e.g. dummy nodes) are reduced by a whole CTA; pass heavy_rows = NULL to let the per-row path
+ * handle everything.  self_scale != 0 requires n_src == N.                                    */
+int dn4gl_spmm_sum_f32(const int32_t *row_ptr, const int32_t *col, const float *x, float *out,
+                       int64_t N, int64_t n_src, int32_t D, float self_scale,
+                       const int32_t *heavy_rows, const int32_t *heavy_count, int32_t heavy_threshold,
+                       void *stream);
+
+/* ---- K3: segment readout ------------------------------------------------------------------- */
+/* out[b,:] = scale_b * sum_{v in [seg_ptr[b], seg_ptr[b+1]), mask[v]==0} x[v,:]
+ * mode 0: sum (global_add_pool, gconv.py:176; SumPredictNet.agg_graph pred.py:215),
+ * mode 1: mean over the segment length (global_mean_pool).  mask (uint8, 1 = skip row, e.g.
+ * dummy nodes, basemodel.py:905-912) may be NULL.                                              */
+int dn4gl_segment_sum_f32(const int32_t *seg_ptr, const uint8_t *mask, const float *x, float *out,
+                          int32_t B, int32_t D, int32_t mode, void *stream);
+/* backward of the above: gx[v,:] = mask[v] ? 0 : scale_b * g[b(v),:]                            */
+int dn4gl_segment_bcast_f32(const int32_t *seg_ptr, const uint8_t *mask, const float *g, float *gx,
+                            int32_t B, int64_t N, int32_t D, int32_t mode, void *stream);
+
+/* left-padded dense batchify, replaces split_and_batchify_graph_feats(pre_pad=True)
+ * (subgraph_isomorphism/utils/dl.py:51-81): out[b, Lmax-len_b+i, :] = x[seg_ptr[b]+i, :] (0 on
+ * pads and on rows with mask[v]=1); inverse gather for the backward.                          */
+int dn4gl_pad_segments_f32(const int32_t *seg_ptr, const uint8_t *mask, const float *x, float *out,
+                           int32_t B, int32_t Lmax, int32_t D, void *stream);
+int dn4gl_unpad_segments_f32(const int32_t *seg_ptr, const uint8_t *mask, const float *g, float *gx,
+                             int32_t B, int32_t Lmax, int32_t D, int64_t N, void *stream);
+
+/* label filter gate, replaces ScalarFilter on the padded label matrices
+ * (models/filter.py:10-16, basemodel.py:830-847): gate[v] = 1 if label of graph node v occurs
+ * among the labels of its pattern, or equals 0 while the pattern is shorter than Lp_max
+ * (padding leak).                                                        */
+int dn4gl_label_filter_gate(const int32_t *g_ptr, const int32_t *g_label,
+                            const int32_t *p_ptr, const int32_t *p_label,
+                            int32_t B, int32_t Lp_max, int64_t Ng, float *gate, void *stream);
+
+/* ---- K4 / K5: DMPNN ------------------------------------------------------------------------ */
+/* node aggregation by linearity (dmpnn.py:111-127, reduce fn.sum :92):
+ *   S[v, 0:D]  = sum_{e in in(v),  is_rev[e]} ef[e,:]      (multiplies W_out)
+ *   S[v, D:2D] = sum_{e in in(v), !is_rev[e]} ef[e,:]      (multiplies -W_in)
+ * in_ptr/in_eid: CSR by destination.  S is (N, 2D).                                            */
+int dn4gl_dmp_node_agg_f32(const int32_t *in_ptr, const int32_t *in_eid, const uint8_t *is_rev,
+                           const float *ef, float *S, int64_t N, int32_t D,
+                           const int32_t *heavy_rows, const int32_t *heavy_count, int32_t heavy_threshold,
+                           void *stream);
+/* backward: gef[e,:] = is_rev[e] ? gS[dst[e], 0:D] : gS[dst[e], D:2D]                           */
+int dn4gl_dmp_node_agg_bwd_f32(const int32_t *dst, const uint8_t *is_rev, const float *gS, float *gef,
+                               int64_t E, int32_t D, void *stream);
+/* edge message + self terms (dmpnn.py:112,120,123,126 and 142-149), PQ = h @ [W_dst | W_src]
+ * (N, 2D), T = ef @ [W_eloop | W_src - W_dst] (E, 2D):
+ *   msg_e = is_rev ? P[src]-Q[dst] : P[dst]-Q[src]
+ *   out[e,:] = T[e,0:D] + 2*(1+log2(1+out_deg[dst[e]])) * T[e,D:2D] + msg_e + bias
+ * bias may be NULL.                                                                            */
+int dn4gl_dmp_edge_update_f32(const int32_t *src, const int32_t *dst, const uint8_t *is_rev,
+                              const int32_t *out_deg, const float *PQ, const float *T,
+                              const float *bias, float *out, int64_t E, int32_t D, void *stream);
+/* backward wrt T: gT[e,0:D] = g[e,:], gT[e,D:2D] = c_e * g[e,:]                                 */
+int dn4gl_dmp_edge_update_bwd_T_f32(const int32_t *dst, const int32_t *out_deg, const float *g,
+                                    float *gT, int64_t E, int32_t D, void *stream);
+/* backward wrt PQ (deterministic, per node over its in- and out-lists):
+ *   gPQ[v,0:D]  =  sum_{e in in(v),!rev} g_e + sum_{e in out(v), rev} g_e
+ *   gPQ[v,D:2D] = -sum_{e in in(v), rev} g_e - sum_{e in out(v),!rev} g_e                        */
+int dn4gl_dmp_edge_update_bwd_PQ_f32(const int32_t *in_ptr, const int32_t *in_eid,
+                                     const int32_t *out_ptr, const int32_t *out_eid,
+                                     const uint8_t *is_rev, const float *g, float *gPQ,
+                                     int64_t N, int32_t D, void *stream);
+
+/* ---- small fused elementwise helpers of the layers ------------------------------------------ */
+/* gather rows: out[i,:] = x[idx[i],:] (idx int32, n rows)                                       */
+int dn4gl_gather_rows_f32(const int32_t *idx, const float *x, float *out, int64_t n, int32_t D, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DN4GL_H */

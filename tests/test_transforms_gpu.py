@@ -1,0 +1,170 @@
+"""GPU parity (bit-exact) of the transform kernels against the oracle restatement, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from dummynode4graphlearning_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TU_KEYS = ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel", "v_is_dummy", "e_is_dummy", "vid", "eid")
+SUB_KEYS = ("node_ptr", "edge_ptr", "src", "dst", "vid", "vlabel", "v_is_dummy", "eid", "elabel", "e_is_dummy",
+            "e_is_reversed")
+
+
+def _eq(dev_batch, ora_batch, keys):
+    for k in keys:
+        a = dev_batch[k].cpu().numpy()
+        b = np.asarray(ora_batch[k])
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        assert np.array_equal(a, b), (k, np.flatnonzero(a != b)[:10])
+
+
+def _empty_graph_batch():
+    # ragged edge cases: a graph without edges in the middle, a single-node graph, a 2-cycle
+    return dict(num_graphs=4, node_ptr=np.array([0, 3, 4, 6, 9], np.int32), edge_ptr=np.array([0, 4, 4, 6, 10], np.int32),
+                src=np.array([0, 1, 1, 2, 4, 5, 6, 7, 7, 8], np.int32), dst=np.array([1, 0, 2, 1, 5, 4, 7, 6, 8, 7], np.int32),
+                vlabel=np.array([1, 2, 1, 3, 1, 1, 2, 2, 1], np.int32), elabel=np.array([1, 1, 2, 2, 1, 1, 3, 3, 1, 1], np.int32),
+                has_edge_labels=True)
+
+
+@pytest.mark.parametrize("case", ["appB", "ragged", "mutag", "proteins_small", "proteins_full"])
+def test_tu_dummy_and_conjugate(device, case):
+    from dummynode4graphlearning_b200 import transforms as T
+    from oracle import transforms as O
+
+    if case == "appB":  # SURVEY.md App. B golden vector
+        b = dict(num_graphs=2, node_ptr=np.array([0, 3, 5], np.int32), edge_ptr=np.array([0, 4, 6], np.int32),
+                 src=np.array([0, 1, 1, 2, 3, 4], np.int32), dst=np.array([1, 0, 2, 1, 4, 3], np.int32),
+                 vlabel=np.array([1, 2, 1, 2, 2], np.int32), elabel=np.ones(6, np.int32), has_edge_labels=False)
+    elif case == "ragged":
+        b = _empty_graph_batch()
+    elif case == "mutag":
+        b = synth.tu_batch("mutag", seed=0)
+    elif case == "proteins_small":
+        b = synth.tu_batch("proteins", 64, seed=3)
+    else:
+        b = synth.tu_batch("proteins", seed=0)   # BASELINE config C2 at full size
+    db = T.to_device(b, device)
+    o_d = O.tu_add_dummy(b)
+    g_d = T.tu_add_dummy(db)
+    _eq(g_d, o_d, TU_KEYS)
+    o_c = O.tu_conjugate(o_d)
+    g_c = T.tu_conjugate(g_d)
+    _eq(g_c, o_c, TU_KEYS + ("v_origin", "e_shared"))
+    if case == "appB":
+        assert g_c["src"].cpu().tolist()[:14] == [1, 4, 0, 3, 4, 0, 3, 4, 2, 4, 1, 0, 3, 2]
+        assert g_c["dst"].cpu().tolist()[:14] == [0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 4, 4, 4, 4]
+        assert g_c["elabel"].cpu().tolist() == [1, 1, 2, 2, 2, 2, 2, 2, 1, 1, 1, 2, 2, 1, 2, 2, 2, 2, 2, 2]
+    # LINE_ graphs (no dummy)
+    o_l = O.tu_conjugate(b)
+    g_l = T.tu_conjugate(db)
+    _eq(g_l, o_l, ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel", "vid", "eid"))
+    # closed forms: V' = m + 1 per graph with edges, E' = sum in*out + 2m
+    n = np.diff(b["node_ptr"]); m = np.diff(b["edge_ptr"])
+    indeg = np.bincount(b["dst"], minlength=b["node_ptr"][-1]); outdeg = np.bincount(b["src"], minlength=b["node_ptr"][-1])
+    gid = np.repeat(np.arange(len(n)), n)
+    prod = np.bincount(gid, weights=(indeg * outdeg).astype(np.float64), minlength=len(n)).astype(np.int64)
+    Vc = np.diff(g_c["node_ptr"].cpu().numpy()); Ec = np.diff(g_c["edge_ptr"].cpu().numpy())
+    assert np.array_equal(Vc, m + 1)
+    assert np.array_equal(Ec, prod + 2 * m)
+    torch.cuda.synchronize()
+    from dummynode4graphlearning_b200.graph import check_errors
+    check_errors()
+
+
+@pytest.mark.parametrize("shape,bs", [("small", 64), ("small", 512), ("large", 16)])
+def test_sub_add_dummy(device, shape, bs):
+    from dummynode4graphlearning_b200 import transforms as T
+    from oracle import transforms as O
+
+    p, g, _ = synth.counting_batch(shape, bs, seed=1)
+    cfg = synth.counting_config(shape)
+    for b, (nv, nvl, ne, nel) in ((p, (cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])),
+                                  (g, (cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"]))):
+        o = O.sub_add_dummy(b, nv, nvl, ne, nel)
+        d = T.sub_add_dummy(T.to_device(b, device), nv, nvl, ne, nel)
+        _eq(d, o, SUB_KEYS)
+
+
+def test_sub_add_dummy_golden_appB2(device):
+    """SURVEY.md App. B second vector (reference train.py:404-435 executed under the shims)."""
+    from dummynode4graphlearning_b200 import transforms as T
+
+    g = dict(num_graphs=1, node_ptr=np.array([0, 3], np.int32), edge_ptr=np.array([0, 3], np.int32),
+             src=np.array([0, 1, 1], np.int32), dst=np.array([1, 2, 2], np.int32), vid=np.arange(3, dtype=np.int32),
+             vlabel=np.array([0, 1, 0], np.int32), eid=np.arange(3, dtype=np.int32), elabel=np.array([0, 1, 0], np.int32))
+    d = T.sub_add_dummy(T.to_device(g, device), 4, 2, 6, 2)
+    assert d["src"].cpu().tolist() == [0, 1, 1, 0, 1, 2, 3, 3, 3]
+    assert d["dst"].cpu().tolist() == [1, 2, 2, 3, 3, 3, 0, 1, 2]
+    assert d["eid"].cpu().tolist() == [0, 1, 2, 6, 6, 6, 7, 7, 7]
+    assert d["elabel"].cpu().tolist() == [0, 1, 0, 2, 2, 2, 3, 3, 3]
+    assert d["e_is_reversed"].cpu().tolist() == [0, 0, 0, 0, 0, 0, 1, 1, 1]
+    assert d["vid"].cpu().tolist() == [0, 1, 2, 4] and d["vlabel"].cpu().tolist() == [0, 1, 0, 2]
+
+
+@pytest.mark.parametrize("case", ["mutag_dummy", "proteins_conj", "dups"])
+def test_pyg_canonicalize(device, case):
+    from dummynode4graphlearning_b200 import transforms as T
+    from oracle import transforms as O
+
+    if case == "mutag_dummy":
+        b = O.tu_add_dummy(synth.tu_batch("mutag", seed=0)); b["has_edge_labels"] = True
+    elif case == "proteins_conj":
+        b = O.tu_conjugate(O.tu_add_dummy(synth.tu_batch("proteins", 200, seed=5))); b["has_edge_labels"] = True
+    else:  # self loops + duplicate pairs with different labels
+        b = dict(num_graphs=1, node_ptr=np.array([0, 4], np.int32), edge_ptr=np.array([0, 8], np.int32),
+                 src=np.array([2, 0, 1, 0, 3, 0, 2, 1], np.int32), dst=np.array([1, 1, 1, 1, 3, 2, 1, 0], np.int32),
+                 vlabel=np.array([1, 2, 0, 1], np.int32), elabel=np.array([1, 2, 1, 1, 2, 2, 2, 1], np.int32),
+                 has_edge_labels=True)
+    d = T.pyg_canonicalize(T.to_device(b, device))
+    emin = int(b["elabel"].min()); R = int(b["elabel"].max()) - emin + 1
+    o_src, o_dst, o_first, o_mult = O.pyg_coalesce(b["src"], b["dst"], b["elabel"] - emin, R)
+    assert np.array_equal(d["edge_index"][0].cpu().numpy(), o_src)
+    assert np.array_equal(d["edge_index"][1].cpu().numpy(), o_dst)
+    assert np.array_equal(d["first_edge"].cpu().numpy(), o_first)
+    assert np.array_equal(d["edge_attr"].cpu().numpy(), o_mult.astype(np.float32))
+    vmin = int(b["vlabel"].min())
+    onehot = np.eye(int(b["vlabel"].max()) - vmin + 1, dtype=np.float32)[b["vlabel"] - vmin]
+    assert np.array_equal(d["x"].cpu().numpy(), onehot)
+    # sortedness + no self loops + uniqueness (size-independent properties)
+    ei = d["edge_index"].cpu().numpy()
+    key = ei[0].astype(np.int64) * (ei.max() + 1) + ei[1]
+    assert np.all(np.diff(key) > 0) and np.all(ei[0] != ei[1])
+
+
+@pytest.mark.parametrize("n,e", [(1, 0), (5, 0), (1000, 5000), (50000, 400000)])
+def test_build_csr_stable(device, n, e):
+    from dummynode4graphlearning_b200.graph import build_csr, check_errors
+    from oracle import transforms as O
+
+    rng = np.random.default_rng(n + e)
+    src = rng.integers(0, n, e).astype(np.int32); dst = rng.integers(0, n, e).astype(np.int32)
+    if e > 100:   # one very heavy row (exercises the CTA rank sort, both sizes)
+        dst[: min(e // 2, 6000)] = 0
+        dst[e // 2: e // 2 + 300] = n - 1
+    csr = build_csr(torch.from_numpy(dst).to(device), torch.from_numpy(src).to(device), n)
+    rp, col, eid = O.csr_by_dst(n, src, dst)
+    assert np.array_equal(csr.row_ptr.cpu().numpy(), rp)
+    assert np.array_equal(csr.eid.cpu().numpy(), eid)
+    assert np.array_equal(csr.col.cpu().numpy(), col)
+    if e > 0:
+        hv = set(csr.heavy_rows[: int(csr.heavy_count.item())].cpu().tolist())
+        assert hv == set(np.flatnonzero(np.diff(rp) > csr.heavy_thr).tolist())
+    check_errors()
+
+
+@pytest.mark.parametrize("n", [0, 1, 4095, 4096, 4097, 1 << 20, (1 << 22) + 3])
+def test_exclusive_scan(device, n):
+    from dummynode4graphlearning_b200._lib import lib, ptr
+
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 5, n).astype(np.int32)
+    x = torch.from_numpy(a).to(device)
+    out = torch.empty(n + 1, dtype=torch.int32, device=device)
+    L = lib()
+    wsb = L.size("dn4gl_scan_workspace_bytes", n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+    L.call("dn4gl_exclusive_scan_i32", ptr(x), ptr(out), n, ptr(ws), wsb, torch.cuda.current_stream().cuda_stream)
+    ref = np.concatenate([[0], np.cumsum(a, dtype=np.int64)]).astype(np.int32)
+    assert np.array_equal(out.cpu().numpy(), ref)
