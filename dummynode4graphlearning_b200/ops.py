@@ -109,14 +109,20 @@ def pad_segments(x, seg_ptr, Lmax, mask=None):
     return _PadSegments.apply(x, seg_ptr, mask, int(Lmax))
 
 
-def label_filter_gate(graph, pattern, Lp_max):
-    """(N_g, 1) float gate of ScalarFilter (filter.py:10-16) without the (B, Lg, Lp) temporary."""
-    g_label = graph.cached("label_i32", lambda: graph.ndata["label"].to(torch.int32).contiguous())
-    p_label = pattern.cached("label_i32", lambda: pattern.ndata["label"].to(torch.int32).contiguous())
+def label_filter_gate(graph, pattern, Lp_max, kind="node"):
+    """(N_g, 1) float gate of ScalarFilter (filter.py:10-16) without the (B, Lg, Lp) temporary.
+    kind="node": node labels vs the pattern's node labels (basemodel.py:830-847);
+    kind="edge": edge labels vs the pattern's edge labels (basemodel.py:1434-1442)."""
+    if kind == "node":
+        g_lab, p_lab, g_ptr, p_ptr = graph.ndata["label"], pattern.ndata["label"], graph.node_ptr, pattern.node_ptr
+    else:
+        g_lab, p_lab, g_ptr, p_ptr = graph.edata["label"], pattern.edata["label"], graph.edge_ptr, pattern.edge_ptr
+    g_label = graph.cached("label_i32_" + kind, lambda: g_lab.to(torch.int32).contiguous())
+    p_label = pattern.cached("label_i32_" + kind, lambda: p_lab.to(torch.int32).contiguous())
     require_cuda(g_label, "labels")
     Ng = g_label.numel()
     gate = torch.empty((Ng, 1), dtype=torch.float32, device=g_label.device)
-    lib().call("dn4gl_label_filter_gate", ptr(graph.node_ptr), ptr(g_label), ptr(pattern.node_ptr), ptr(p_label),
+    lib().call("dn4gl_label_filter_gate", ptr(g_ptr), ptr(g_label), ptr(p_ptr), ptr(p_label),
                graph.batch_size, int(Lp_max), Ng, ptr(gate), _stream())
     return gate
 

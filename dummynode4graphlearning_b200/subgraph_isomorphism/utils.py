@@ -1,0 +1,128 @@
+"""Host utilities the counting models need: activation registry and weight initialisers.
+
+Same names, argument meaning and numeric behaviour as the reference's
+``subgraph_isomorphism/utils/act.py:457-489`` (``map_activation_str_to_layer``; activations are
+shared singleton modules; ``leaky_relu`` slope is 1/5.5, act.py:27) and
+``utils/init.py:18-158`` (``init_weight`` / ``init_module``: Xavier-uniform / Kaiming-normal
+variants with the reference's gain table).  Pure host-side setup code: nothing here runs per step.
+"""
+import math
+
+import torch as th
+import torch.nn as nn
+
+LEAKY_RELU_A = 1 / 5.5
+
+
+class Identity(nn.Module):
+    def forward(self, x):
+        return x
+
+
+supported_act_funcs = {
+    "none": Identity(),
+    "softmax": nn.Softmax(dim=-1),
+    "sigmoid": nn.Sigmoid(),
+    "tanh": nn.Tanh(),
+    "relu": nn.ReLU(),
+    "relu6": nn.ReLU6(),
+    "leaky_relu": nn.LeakyReLU(negative_slope=LEAKY_RELU_A),
+    "prelu": nn.PReLU(init=LEAKY_RELU_A),
+    "elu": nn.ELU(),
+    "celu": nn.CELU(),
+    "selu": nn.SELU(),
+    "gelu": nn.GELU(),
+}
+
+
+def map_activation_str_to_layer(act_func, **kw):
+    if act_func not in supported_act_funcs:
+        raise NotImplementedError(act_func)
+    act = supported_act_funcs[act_func]
+    for k, v in kw.items():
+        if hasattr(act, k):
+            try:
+                setattr(act, k, v)
+            except Exception:
+                pass
+    return act
+
+
+def calculate_gain(activation):
+    if activation in ("none", "maximum", "minimum"):
+        kind = "linear"
+    elif activation in ("relu", "relu6", "elu", "selu", "celu", "gelu"):
+        kind = "relu"
+    elif activation in ("leaky_relu", "prelu"):
+        kind = "leaky_relu"
+    elif activation in ("softmax", "sparsemax", "gumbel_softmax"):
+        kind = "sigmoid"
+    elif activation in ("sigmoid", "tanh"):
+        kind = activation
+    else:
+        raise NotImplementedError(activation)
+    return nn.init.calculate_gain(kind, LEAKY_RELU_A)
+
+
+def _fans(x):
+    if x.dim() < 2:
+        x = x.unsqueeze(-1)
+    rf = x[0][0].numel() if x.dim() > 2 else 1
+    return x.size(1) * rf, x.size(0) * rf
+
+
+def _uniform(x, gain):
+    fan_in, fan_out = _fans(x)
+    a = math.sqrt(3.0) * gain * math.sqrt(2.0 / float(fan_in + fan_out))
+    return nn.init.uniform_(x, -a, a)
+
+
+def _normal(x, gain):
+    fan_in, _ = _fans(x)
+    return nn.init.normal_(x, 0, gain / math.sqrt(fan_in))
+
+
+_INITS = {
+    "zero": lambda x, gain: nn.init.zeros_(x),
+    "uniform": _uniform,
+    "normal": _normal,
+    "orthogonal": lambda x, gain: nn.init.orthogonal_(x, gain=1.0),
+}
+
+
+def init_weight(x, activation="none", init="uniform"):
+    if init not in _INITS:
+        raise ValueError("init=%s is not supported now." % init)
+    if isinstance(x, th.Tensor):
+        _INITS[init](x, calculate_gain(activation))
+
+
+def init_module(x, activation="none", init="uniform"):
+    if init not in _INITS:
+        raise ValueError("init=%s is not supported now." % init)
+    gain = calculate_gain(activation)
+    if isinstance(x, nn.Linear):
+        _INITS[init](x.weight, gain)
+        if x.bias is not None:
+            nn.init.zeros_(x.bias)
+    elif isinstance(x, (nn.BatchNorm1d, nn.LayerNorm)):
+        nn.init.ones_(x.weight)
+        nn.init.zeros_(x.bias)
+
+
+class OutputDict(dict):
+    """Model output: the reference's key set (models/container.py:14-101, basemodel.py:964-980);
+    readable both as ``out["pred_c"]`` and ``out.pred_c``; ``None`` entries are kept so that
+    ``output["pred_e"] is not None`` tests in train.py:779-800 keep working."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def to_tuple(self):
+        return tuple(v for v in self.values() if v is not None)
