@@ -1,0 +1,78 @@
+"""PyG-style mini-batch (``x, edge_index, edge_attr, batch, y, is_dummy_node, is_dummy_edge``) whose graph
+structure is compiled once into the int32 CSR pair the kernels consume.
+
+Stands in for ``torch_geometric.data.Batch`` as produced by PyG's ``DataLoader`` collate
+(graph_classification/graph_neural_networks/main.py:245) over ``PYGDataset`` items (dataset.py:118-139).
+"""
+import torch
+
+from ..graph import build_csr
+
+
+class GraphStructure:
+    """CSR by destination / by source + per-graph node offsets of a PyG-style batch."""
+
+    def __init__(self, edge_index, num_nodes, batch=None, node_ptr=None):
+        src = edge_index[0].to(torch.int32).contiguous()
+        dst = edge_index[1].to(torch.int32).contiguous()
+        self.src, self.dst, self.num_nodes = src, dst, int(num_nodes)
+        self.csr_in = build_csr(dst, src, self.num_nodes)
+        self.csr_out = build_csr(src, dst, self.num_nodes)
+        if node_ptr is None and batch is not None:
+            nb = int(batch[-1].item()) + 1 if batch.numel() else 0   # batch is sorted (PyG collate)
+            counts = torch.bincount(batch, minlength=nb)
+            node_ptr = torch.zeros(nb + 1, dtype=torch.int32, device=batch.device)
+            node_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        self.node_ptr = None if node_ptr is None else node_ptr.to(torch.int32).contiguous()
+        self._rel = {}
+
+    def relation_csr(self, edge_type, num_rels):
+        """CSR pair addressing the (N*R, D) per-relation table (see subgraph_isomorphism/models/rgin.py)."""
+        key = (edge_type.data_ptr(), int(num_rels))
+        if key not in self._rel:
+            from ..graph import CSR
+            base = self.csr_in
+            et = edge_type.long()
+            col = (base.col.long() * num_rels + et[base.eid.long()]).to(torch.int32)
+            fwd = CSR(base.row_ptr, col, base.eid, base.n_rows, base.nnz)
+            fwd.heavy_rows, fwd.heavy_count, fwd.heavy_thr = base.heavy_rows, base.heavy_count, base.heavy_thr
+            bwd = build_csr((self.src.long() * num_rels + et).to(torch.int32), self.dst, self.num_nodes * num_rels)
+            self._rel[key] = (fwd, bwd)
+        return self._rel[key]
+
+
+class Batch:
+    def __init__(self, x, edge_index, batch, edge_attr=None, y=None, is_dummy_node=None, is_dummy_edge=None,
+                 node_ptr=None):
+        self.x, self.edge_index, self.batch, self.edge_attr, self.y = x, edge_index, batch, edge_attr, y
+        self.is_dummy_node, self.is_dummy_edge = is_dummy_node, is_dummy_edge
+        self._node_ptr = node_ptr
+        self._structure = None
+
+    @property
+    def num_graphs(self):
+        return int(self.structure.node_ptr.numel()) - 1
+
+    @property
+    def structure(self):
+        if self._structure is None:
+            self._structure = GraphStructure(self.edge_index, self.x.size(0), self.batch, self._node_ptr)
+        return self._structure
+
+    @staticmethod
+    def from_canonical(d):
+        """from ``transforms.pyg_canonicalize`` output."""
+        return Batch(d["x"], d["edge_index"], d["batch"], d.get("edge_attr"), d.get("y"),
+                     d.get("is_dummy_node"), d.get("is_dummy_edge"), node_ptr=d["node_ptr"])
+
+
+def structure_of(data):
+    """GraphStructure of any object with ``x, edge_index, batch`` (cached on the object)."""
+    s = getattr(data, "_structure", None)
+    if s is None:
+        s = GraphStructure(data.edge_index, data.x.size(0), data.batch, getattr(data, "_node_ptr", None))
+        try:
+            data._structure = s
+        except AttributeError:
+            pass
+    return s

@@ -1,0 +1,112 @@
+"""GIN graph classifier on the B200 aggregation kernels.
+
+Drop-in for ``graph_classification/graph_neural_networks/models/gconv.py::GIN`` (:154-215) and for the PyG
+2.0.2 pieces it calls (``GINConv``, ``global_add_pool``, ``global_mean_pool`` -- gconv.py:161,197,210-213):
+same ``args`` fields, same sub-module names (``first_h, nns, convs[i].nn`` aliasing ``nns[i]``, ``convs[i].eps``,
+``linears``), same quirks (layer-0 dropout is applied without ``training=`` :210; ``train_eps`` defaults to
+``args.epochs`` :179; pooling includes the dummy node).
+
+Hot ops: ``GINConv`` = one K1 launch with the ``(1 + eps) * x`` self term fused (torch_scatter's
+index_select + atomic scatter_add in the reference), pooling = K3 segment readout.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from ..data import structure_of
+
+
+class GINConv(nn.Module):
+    """``out = nn((1 + eps) * x + sum_{j -> i} x_j)``.  ``forward`` takes the reference's ``(x, edge_index)``;
+    pass ``structure=`` to reuse a compiled CSR (otherwise it is compiled per distinct edge_index and cached)."""
+
+    def __init__(self, nn, eps=0.0, train_eps=False, **kw):
+        super().__init__()
+        self.nn = nn
+        self.initial_eps = eps
+        if train_eps:
+            self.eps = torch.nn.Parameter(torch.Tensor([eps]))
+        else:
+            self.register_buffer("eps", torch.Tensor([eps]))
+        self._cache = {}
+
+    def _structure(self, x, edge_index):
+        from ..data import GraphStructure
+        key = (edge_index.data_ptr(), edge_index.size(1), x.size(0))
+        if key not in self._cache:
+            self._cache.clear()
+            self._cache[key] = GraphStructure(edge_index, x.size(0))
+        return self._cache[key]
+
+    def forward(self, x, edge_index, structure=None):
+        s = structure if structure is not None else self._structure(x, edge_index)
+        if isinstance(self.eps, nn.Parameter) and self.eps.requires_grad:
+            # trainable eps: keep d/d eps on the autograd tape (agg + (1 + eps) * x); the self term is one
+            # elementwise op instead of being fused, the gather-sum is still K1.
+            out = ops.spmm_sum(x, s.csr_in, s.csr_out, 0.0) + (1 + self.eps) * x
+        else:
+            out = ops.spmm_sum(x, s.csr_in, s.csr_out, 1.0 + float(self.eps))
+        return self.nn(out)
+
+
+def _ptr_of(batch, size=None):
+    nb = (int(batch[-1].item()) + 1 if batch.numel() else 0) if size is None else size
+    ptr = torch.zeros(nb + 1, dtype=torch.int32, device=batch.device)
+    ptr[1:] = torch.cumsum(torch.bincount(batch, minlength=nb), 0).to(torch.int32)
+    return ptr
+
+
+def global_add_pool(x, batch, size=None, node_ptr=None):
+    return ops.segment_sum(x, node_ptr if node_ptr is not None else _ptr_of(batch, size), None, mean=False)
+
+
+def global_mean_pool(x, batch, size=None, node_ptr=None):
+    return ops.segment_sum(x, node_ptr if node_ptr is not None else _ptr_of(batch, size), None, mean=True)
+
+
+def _gin_mlp(din, dout):
+    return nn.Sequential(nn.Linear(din, dout), nn.BatchNorm1d(dout), nn.ReLU(),
+                         nn.Linear(dout, dout), nn.BatchNorm1d(dout), nn.ReLU())
+
+
+class GIN(torch.nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.num_features, self.hidden_dim, self.num_classes = args.num_features, args.hidden_dim, args.num_classes
+        self.dropout = args.dropout_ratio
+        config = args.additional if args.additional else {"train_eps": False, "num_layers": 2, "aggregation": "sum"}
+        agg = config.get("aggregation", "sum")
+        if agg == "sum":
+            self.pooling = global_add_pool
+        elif agg == "mean":
+            self.pooling = global_mean_pool
+        train_eps = config.get("train_eps", args.epochs)   # gconv.py:179
+        self.embeddings_dim = [self.hidden_dim for _ in range(config.get("num_layers", 2))]
+        self.no_layers = len(self.embeddings_dim)
+        nns, convs, linears = [], [], []
+        for layer, out_dim in enumerate(self.embeddings_dim):
+            if layer == 0:
+                self.first_h = _gin_mlp(self.num_features, out_dim)
+            else:
+                nns.append(_gin_mlp(self.embeddings_dim[layer - 1], out_dim))
+                convs.append(GINConv(nns[-1], train_eps=train_eps))
+            linears.append(nn.Linear(out_dim, self.num_classes))
+        self.nns = nn.ModuleList(nns)
+        self.convs = nn.ModuleList(convs)
+        self.linears = nn.ModuleList(linears)
+
+    def forward(self, data):
+        x = data.x
+        s = structure_of(data)
+        out = 0
+        for layer in range(self.no_layers):
+            if layer == 0:
+                x = self.first_h(x)
+                out += F.dropout(self.pooling(self.linears[layer](x), data.batch, node_ptr=s.node_ptr), p=self.dropout)
+            else:
+                x = self.convs[layer - 1](x, data.edge_index, structure=s)
+                out += F.dropout(self.linears[layer](self.pooling(x, data.batch, node_ptr=s.node_ptr)),
+                                 p=self.dropout, training=self.training)
+        return F.log_softmax(out, dim=-1)

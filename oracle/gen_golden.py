@@ -1,0 +1,147 @@
+"""Generate tests/golden/* by executing the UNMODIFIED reference under oracle/shims.
+
+Run in the build container only (needs /root/reference):   python -m oracle.gen_golden
+The fixtures pin (a) the transforms' exact index outputs and (b) forward values, loss and every parameter
+gradient of the reference's own GIN / RGIN(cls) / RGIN / DMPNN classes on small seeded batches.  They travel
+to the GPU box; nothing else of the reference does.
+"""
+import os
+import zlib
+from argparse import Namespace
+
+import numpy as np
+import torch as th
+import torch.nn.functional as F
+
+from dummynode4graphlearning_b200 import synth
+from dummynode4graphlearning_b200.transforms import process_model_config
+
+from . import ref_drive as rd
+from . import transforms as OT
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _np(d):
+    return {k: (np.asarray(v) if not isinstance(v, (int, bool)) else v) for k, v in d.items()}
+
+
+def gen_transforms():
+    out = {}
+    # SURVEY.md App. B, first vector
+    appb = dict(num_graphs=2, node_ptr=np.array([0, 3, 5], np.int32), edge_ptr=np.array([0, 4, 6], np.int32),
+                src=np.array([0, 1, 1, 2, 3, 4], np.int32), dst=np.array([1, 0, 2, 1, 4, 3], np.int32),
+                vlabel=np.array([1, 2, 1, 2, 2], np.int32), elabel=np.ones(6, np.int32), has_edge_labels=False)
+    cases = {"appB": appb, "mutag12": synth.tu_batch("mutag", 12, seed=11), "proteins8": synth.tu_batch("proteins", 8, seed=12)}
+    for name, b in cases.items():
+        gs = rd.ref_tu_load(b, True)
+        conj = rd.ref_tu_conjugate(gs)
+        line = rd.ref_tu_conjugate(rd.ref_tu_load(b, False))
+        out["tu/" + name] = dict(inp=_np(b), dummy=rd.igraphs_to_batch(gs), conj=rd.igraphs_to_batch(conj),
+                                 line=rd.igraphs_to_batch(line), conj_files=rd.ref_tu_save(conj))
+    for shape, bs, seed in (("small", 6, 21), ("large", 1, 22)):
+        p, g, _ = synth.counting_batch(shape, bs, seed=seed)
+        cfg = synth.counting_config(shape)
+        rp, rg = rd.ref_sub_add_dummy(p, g, cfg)
+        out["sub/%s" % shape] = dict(cfg=cfg, pattern=_np(p), graph=_np(g), pattern_dummy=rp, graph_dummy=rg,
+                                     pattern_conj=rd.ref_sub_conjugate(rp), graph_conj=rd.ref_sub_conjugate(rg))
+    # SURVEY.md App. B, second vector
+    g = dict(num_graphs=1, node_ptr=np.array([0, 3], np.int32), edge_ptr=np.array([0, 3], np.int32),
+             src=np.array([0, 1, 1], np.int32), dst=np.array([1, 2, 2], np.int32), vid=np.arange(3, dtype=np.int32),
+             vlabel=np.array([0, 1, 0], np.int32), eid=np.arange(3, dtype=np.int32), elabel=np.array([0, 1, 0], np.int32))
+    cfg = dict(max_npv=4, max_npvl=2, max_npe=6, max_npel=2, max_ngv=4, max_ngvl=2, max_nge=6, max_ngel=2)
+    _, rg = rd.ref_sub_add_dummy(g, g, cfg)
+    out["sub/appB2"] = dict(cfg=cfg, graph=_np(g), graph_dummy=rg, graph_conj=rd.ref_sub_conjugate(rg))
+    for base in (dict(add_rev=False, add_dummy=True, convert_conj=False), dict(add_rev=True, add_dummy=True, convert_conj=True)):
+        c = dict(synth.counting_config("small"), **base)
+        out["cfg/%s" % "-".join("%s%d" % (k[:5], v) for k, v in base.items())] = dict(inp=c, out=rd.ref_process_model_config(c))
+    th.save(out, os.path.join(OUT, "transforms.pt"))
+    print("transforms.pt:", list(out))
+
+
+def _grads(model):
+    return {n: (p.grad.clone() if p.grad is not None else None) for n, p in model.named_parameters()}
+
+
+def gen_counting():
+    out = {}
+    p, g, counts = synth.counting_batch("small", 8, seed=31)
+    cfg = dict(synth.counting_config("small"), add_dummy=True)
+    mc = process_model_config(cfg)
+    pd_ = OT.sub_add_dummy(p, cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])
+    gd_ = OT.sub_add_dummy(g, cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"])
+    variants = {
+        "RGIN/bdd4": ("RGIN", dict(hid_dim=16, pred_hid_dim=16)),
+        "RGIN/basis_full": ("RGIN", dict(hid_dim=16, pred_hid_dim=16, rep_rgin_regularizer="basis", rep_rgin_num_bases=-1,
+                                         pred_net="MeanPredictNet", pred_return_weights="none")),
+        "RGIN/basis4_unshared": ("RGIN", dict(hid_dim=16, pred_hid_dim=16, rep_rgin_regularizer="basis", rep_rgin_num_bases=4,
+                                              share_rep_net=False, rep_act_func="relu")),
+        "DMPNN/node": ("DMPNN", dict(hid_dim=16, pred_hid_dim=16, node_pred=True, edge_pred=False)),
+        "DMPNN/node_edge": ("DMPNN", dict(hid_dim=16, pred_hid_dim=16, node_pred=True, edge_pred=True,
+                                          pred_return_weights="node,edge", init_neigenv=5.0, init_eeigenv=6.0)),
+        "DMPNN/edge_max_nofilter": ("DMPNN", dict(hid_dim=16, pred_hid_dim=16, node_pred=False, edge_pred=True,
+                                                  pred_net="MaxPredictNet", filter_net="None", rep_residual=False)),
+    }
+    for tag, (name, over) in variants.items():
+        kw = rd.counting_kwargs({k: v for k, v in mc.items() if k.startswith("max_")}, **over)
+        model = rd.ref_counting_model(name, kw, seed=zlib.crc32(tag.encode()) % 1000)
+        o = model(rd.dgl_batched(pd_), rd.dgl_batched(gd_))
+        c = th.from_numpy(counts).float().view(-1, 1)
+        crit = lambda pred, target, slp: F.mse_loss(F.leaky_relu(pred, slp), target)   # train.py:624-625
+        loss = crit(o["pred_c"], c, 0.01)
+        reg = 0.0
+        for k in ("p_v_rep", "p_e_rep", "g_v_rep", "g_e_rep"):                          # train.py:801-809
+            if o[k] is not None:
+                reg = reg + crit(o[k], th.zeros_like(o[k]), 1) * o[k].size(1)
+        loss = loss + 1e-3 * reg
+        loss.backward()
+        out[tag] = dict(name=name, kwargs=kw, state_dict={k: v.clone() for k, v in model.state_dict().items()},
+                        outputs={k: (v.detach().clone() if isinstance(v, th.Tensor) else None) for k, v in o.items()},
+                        loss=loss.detach().clone(), grads=_grads(model))
+    out["_batch"] = dict(pattern=_np(pd_), graph=_np(gd_), counts=counts, cfg=cfg, model_cfg=mc)
+    th.save(out, os.path.join(OUT, "counting_models.pt"))
+    print("counting_models.pt:", [k for k in out if not k.startswith("_")])
+
+
+def gen_classification():
+    out = {}
+    raw = synth.tu_batch("mutag", 10, seed=41)
+    dummy = OT.tu_add_dummy(raw)
+    conj = OT.tu_conjugate(dummy)
+    for tag, b, model_name, add in (("GIN/mutag_dummy", dummy, "GIN", {"train_eps": False, "num_layers": 3, "aggregation": "sum"}),
+                                    ("GIN/mutag_conj_eps", conj, "GIN", {"train_eps": True, "num_layers": 2, "aggregation": "mean"}),
+                                    ("RGIN/mutag_dummy", dummy, "RGIN", {"num_layers": 2})):
+        # PyG read_tu_data view of the saved files (restated: oracle.transforms.pyg_coalesce + one-hot)
+        vmin, emin = int(b["vlabel"].min()), int(b["elabel"].min())
+        R = int(b["elabel"].max()) - emin + 1
+        s, d, first, mult = OT.pyg_coalesce(b["src"], b["dst"], b["elabel"] - emin, R)
+        x = th.from_numpy(np.eye(int(b["vlabel"].max()) - vmin + 1, dtype=np.float32)[b["vlabel"] - vmin])
+        edge_index = th.from_numpy(np.stack([s, d]).astype(np.int64))
+        edge_attr = th.from_numpy(mult.astype(np.float32))
+        batch = th.from_numpy(np.repeat(np.arange(b["num_graphs"]), np.diff(b["node_ptr"])).astype(np.int64))
+        y = th.from_numpy(raw["y"])
+        args = Namespace(num_features=x.size(1), hidden_dim=16, nhid=16, num_classes=2, dropout_ratio=0.0,
+                         additional=add, epochs=3, device="cpu", num_relations=R)
+        model = rd.ref_classifier(model_name, args, seed=len(tag))
+        with th.no_grad():
+            for n, p_ in model.named_parameters():
+                if n.endswith("eps"):
+                    p_.fill_(0.3)
+        model.train()
+        data = Namespace(x=x, edge_index=edge_index, edge_attr=edge_attr, batch=batch, y=y)
+        o = model(data)
+        loss = F.nll_loss(o, y)                                                        # main.py:41
+        loss.backward()
+        out[tag] = dict(name=model_name, args=vars(args), state_dict={k: v.clone() for k, v in model.state_dict().items()},
+                        data=dict(x=x, edge_index=edge_index, edge_attr=edge_attr, batch=batch, y=y,
+                                  node_ptr=th.from_numpy(b["node_ptr"].astype(np.int32))),
+                        out=o.detach().clone(), loss=loss.detach().clone(), grads=_grads(model))
+    th.save(out, os.path.join(OUT, "classification_models.pt"))
+    print("classification_models.pt:", list(out))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_transforms()
+    gen_counting()
+    gen_classification()

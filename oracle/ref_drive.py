@@ -164,3 +164,50 @@ def ref_sub_conjugate(b):
 
 def ref_process_model_config(config):
     return refload.subgraph().train_funcs.process_model_config(config)
+
+
+# ------------------------------------------------------------------------------------------
+# model-level drivers
+def dgl_batched(b):
+    """one batched fake DGLGraph with the frames the reference models read:
+    ndata id,label[,is_dummy],in_deg,out_deg ; edata id,label[,is_dummy,is_reversed]."""
+    C = refload.subgraph().constants
+    gs = batch_to_dgl_list(b)
+    for g in gs:
+        g.ndata[C.INDEGREE] = g.in_degrees()      # calculate_degrees, train.py:477-497 (post-augmentation)
+        g.ndata[C.OUTDEGREE] = g.out_degrees()
+    return fake_dgl.batch(gs)
+
+
+def counting_kwargs(model_cfg, **over):
+    """constructor kwargs as train.py:1401 passes them (process_model_config'ed maxima + CLI defaults)."""
+    kw = dict(model_cfg)
+    kw.update(hid_dim=64, rep_num_graph_layers=3, rep_num_pattern_layers=3, rep_act_func="leaky_relu",
+              pred_act_func="leaky_relu", pred_net="SumPredictNet", pred_hid_dim=64, emb_net="Equivariant",
+              enc_net="Multihot", filter_net="ScalarFilter", pred_with_enc=True, pred_with_deg=True,
+              rep_rgin_regularizer="bdd", rep_rgin_num_bases=4, rep_rgin_num_mlp_layers=2,
+              rep_dmpnn_num_mlp_layers=2, pred_return_weights="node", rep_residual=True, rep_dropout=0.0,
+              pred_dropout=0.0, share_rep_net=True, share_enc_net=True)
+    kw.update(over)
+    return kw
+
+
+def ref_counting_model(name, kw, seed=0):
+    """the reference's own RGIN / DMPNN class, pred_fc2 / weight_fc2 re-randomised (they are zero-initialised,
+    pred.py:50,53, which would make every output 0 -- SURVEY.md App. A-8)."""
+    ns = refload.subgraph()
+    th.manual_seed(seed)
+    model = {"RGIN": ns.rgin.RGIN, "DMPNN": ns.dmpnn.DMPNN}[name](**kw)
+    with th.no_grad():
+        for n, p in model.named_parameters():
+            if "pred_fc2" in n or "weight_fc2" in n:
+                p.normal_(0.0, 0.1)
+            if n.endswith("bias") and p.dim() == 1 and "fc" not in n:
+                p.normal_(0.0, 0.05)   # rep-layer biases are zero-initialised too; make them count
+    return model
+
+
+def ref_classifier(name, args, seed=0):
+    ns = refload.classification()
+    th.manual_seed(seed)
+    return {"GIN": ns.gconv.GIN, "RGIN": ns.rgconv.RGIN}[name](args)

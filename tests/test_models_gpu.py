@@ -1,0 +1,182 @@
+"""GPU parity of the drop-in modules (through the C ABI kernels) against
+ (1) the golden vectors produced by the UNMODIFIED reference classes (tests/golden/, oracle/gen_golden.py), and
+ (2) the oracle restatement on larger seeded batches,
+for forward values, loss and every parameter gradient.  Tolerance: 1e-5 relative (BASELINE.json north_star)
+measured as max-abs error over max-abs reference value per tensor (SURVEY.md section 2.2's measure)."""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import assert_close_rel, load_golden, oracle_cfg
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _counting_model(name, kw, state_dict, device):
+    from dummynode4graphlearning_b200.subgraph_isomorphism.models import DMPNN, RGIN
+    model = {"RGIN": RGIN, "DMPNN": DMPNN}[name](**kw)
+    missing, unexpected = model.load_state_dict(state_dict, strict=True)   # key compatibility (App. A-12)
+    assert not missing and not unexpected
+    return model.to(device).train()
+
+
+def _loss(out, counts, rep_reg_w=1e-3):
+    crit = lambda pred, target, slp: F.mse_loss(F.leaky_relu(pred, slp), target)
+    loss = crit(out["pred_c"], counts.float().view(-1, 1), 0.01)
+    reg = 0.0
+    for k in ("p_v_rep", "p_e_rep", "g_v_rep", "g_e_rep"):
+        if out[k] is not None:
+            reg = reg + crit(out[k], torch.zeros_like(out[k]), 1) * out[k].size(1)
+    return loss + rep_reg_w * reg
+
+
+def _check_outputs(out, ref):
+    for k, r in ref.items():
+        if r is None:
+            assert out[k] is None, k
+        elif r.dtype == torch.bool:
+            assert torch.equal(out[k].cpu(), r), k
+        elif k in ("pred_v", "pred_e"):   # padded / masked positions are don't-care (train.py:783-784 zero them)
+            m = ref["g_v_mask" if k == "pred_v" else "g_e_mask"]
+            assert_close_rel(out[k].cpu().masked_fill(~m, 0), r.masked_fill(~m, 0), TOL, k)
+        else:
+            assert_close_rel(out[k], r, TOL, k)
+
+
+@pytest.mark.parametrize("tag", ["RGIN/bdd4", "RGIN/basis_full", "RGIN/basis4_unshared", "DMPNN/node", "DMPNN/node_edge",
+                                 "DMPNN/edge_max_nofilter"])
+def test_counting_models_match_reference_golden(device, tag):
+    from dummynode4graphlearning_b200.graph import BatchedGraph
+    gold = load_golden("counting_models.pt")
+    g, b = gold[tag], gold["_batch"]
+    model = _counting_model(g["name"], g["kwargs"], g["state_dict"], device)
+    pattern = BatchedGraph.from_batch(b["pattern"], device)
+    graph = BatchedGraph.from_batch(b["graph"], device)
+    out = model(pattern, graph)
+    _check_outputs(out, g["outputs"])
+    loss = _loss(out, torch.from_numpy(b["counts"]).to(device))
+    assert_close_rel(loss, g["loss"], TOL, "loss")
+    loss.backward()
+    grads = dict(model.named_parameters())
+    assert set(grads) == set(g["grads"])
+    for n, ref in g["grads"].items():
+        if ref is None:
+            assert grads[n].grad is None, n     # frozen tables / row_vec stay gradient-free
+        else:
+            assert_close_rel(grads[n].grad, ref, TOL, "grad " + n)
+
+
+@pytest.mark.parametrize("name,shape,bs,over", [
+    ("RGIN", "small", 64, {}),
+    ("RGIN", "small", 512, dict(rep_rgin_regularizer="basis", rep_rgin_num_bases=-1)),   # BASELINE config C3, batch 512
+    ("DMPNN", "small", 64, dict(node_pred=True, edge_pred=True, pred_return_weights="node,edge")),
+    ("DMPNN", "large", 8, dict(node_pred=True, edge_pred=False)),                        # BASELINE config C4 shapes
+])
+def test_counting_models_match_oracle_live(device, name, shape, bs, over):
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.graph import BatchedGraph
+    from dummynode4graphlearning_b200.subgraph_isomorphism.models import DMPNN, RGIN
+    from oracle import models as OM
+
+    p, g, counts = synth.counting_batch(shape, bs, seed=5)
+    cfg = dict(synth.counting_config(shape), add_dummy=True)
+    mc = T.process_model_config(cfg)
+    # augmentation on the GPU (already bit-exact with the reference, test_transforms_gpu.py)
+    pd_ = T.sub_add_dummy(T.to_device(p, device), cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])
+    gd_ = T.sub_add_dummy(T.to_device(g, device), cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"])
+    kw = dict({k: v for k, v in mc.items() if k.startswith("max_")}, hid_dim=64, rep_num_graph_layers=3,
+              rep_num_pattern_layers=3, rep_act_func="leaky_relu", pred_act_func="leaky_relu", pred_net="SumPredictNet",
+              pred_hid_dim=64, emb_net="Equivariant", enc_net="Multihot", filter_net="ScalarFilter", pred_with_enc=True,
+              pred_with_deg=True, rep_rgin_regularizer="bdd", rep_rgin_num_bases=4, pred_return_weights="node",
+              init_neigenv=4.0, init_eeigenv=4.0)
+    kw.update(over)
+    torch.manual_seed(1)
+    model = {"RGIN": RGIN, "DMPNN": DMPNN}[name](**kw)
+    with torch.no_grad():
+        for n, q in model.named_parameters():
+            if "pred_fc2" in n or "weight_fc2" in n:
+                q.normal_(0.0, 0.1)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "enc_net" not in k) for k, v in model.state_dict().items()}
+    model = model.to(device).train()
+    pattern, graph = BatchedGraph.from_batch(pd_, device), BatchedGraph.from_batch(gd_, device)
+    out = model(pattern, graph)
+    loss = _loss(out, torch.from_numpy(counts).to(device))
+    loss.backward()
+
+    host = lambda b: {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in b.items()}
+    ref = OM.counting_model(sd, host(pd_), host(gd_), oracle_cfg(name, kw))
+    ref_loss = OM.counting_loss(ref, torch.from_numpy(counts), rep_reg_w=1e-3)
+    ref_loss.backward()
+    _check_outputs(out, {k: (v.detach() if isinstance(v, torch.Tensor) else None) for k, v in ref.items()})
+    assert_close_rel(loss, ref_loss, TOL, "loss")
+    for n, q in model.named_parameters():
+        if not q.requires_grad or q.grad is None:
+            continue
+        r = sd[n].grad
+        alias = n.replace("g_rep_net", "p_rep_net", 1) if n.startswith("g_rep_net") else None
+        if alias in sd and sd[alias].grad is not None and kw.get("share_rep_net", True):
+            r = r + sd[alias].grad if r is not None else sd[alias].grad
+        assert_close_rel(q.grad, r, TOL, "grad " + n)
+
+
+@pytest.mark.parametrize("tag", ["GIN/mutag_dummy", "GIN/mutag_conj_eps", "RGIN/mutag_dummy"])
+def test_classifiers_match_reference_golden(device, tag):
+    from dummynode4graphlearning_b200.graph_classification.data import Batch
+    from dummynode4graphlearning_b200.graph_classification.models import GIN, RGIN
+    g = load_golden("classification_models.pt")[tag]
+    args = Namespace(**g["args"])
+    model = {"GIN": GIN, "RGIN": RGIN}[g["name"]](args)
+    missing, unexpected = model.load_state_dict(g["state_dict"], strict=True)
+    assert not missing and not unexpected
+    model = model.to(device).train()
+    d = {k: v.to(device) for k, v in g["data"].items()}
+    data = Batch(d["x"], d["edge_index"], d["batch"], d["edge_attr"], d["y"], node_ptr=d["node_ptr"])
+    out = model(data)
+    assert_close_rel(out, g["out"], TOL, "log_softmax")
+    loss = F.nll_loss(out, d["y"])
+    assert_close_rel(loss, g["loss"], TOL, "loss")
+    loss.backward()
+    params = dict(model.named_parameters())
+    assert set(params) == set(g["grads"])
+    for n, ref in g["grads"].items():
+        if ref is not None:
+            assert_close_rel(params[n].grad, ref, 2e-5, "grad " + n)   # BatchNorm backward amplifies rounding
+
+
+def test_gin_full_size_c2_against_oracle(device):
+    """BASELINE config C2 at full size: CONJ transform (GPU) of 1113 PROTEINS-shaped graphs + GIN (hid 32, 4 layers)
+    forward/backward vs the oracle restatement."""
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.graph_classification.data import Batch
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+    from oracle import models as OM
+
+    raw = synth.tu_batch("proteins", seed=0)
+    conj = T.tu_conjugate(T.tu_add_dummy(T.to_device(raw, device)))
+    conj.pop("eattr", None); conj["has_edge_labels"] = True
+    can = T.pyg_canonicalize(conj)
+    data = Batch.from_canonical(can)
+    args = Namespace(num_features=can["x"].size(1), hidden_dim=32, num_classes=2, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": 4, "aggregation": "sum"}, epochs=3, device=str(device))
+    torch.manual_seed(0)
+    model = GIN(args)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in model.state_dict().items()}
+    model = model.to(device).train()
+    out = model(data)
+    loss = F.nll_loss(out, can["y"])
+    loss.backward()
+    ref = OM.gin_classifier(sd, can["x"].cpu(), can["edge_index"].cpu(), can["batch"].cpu(), can["num_graphs"], 4, "sum")
+    ref_loss = F.nll_loss(ref, can["y"].cpu())
+    ref_loss.backward()
+    assert_close_rel(out, ref, 2e-5, "log_softmax")
+    assert_close_rel(loss, ref_loss, 2e-5, "loss")
+    for n, q in model.named_parameters():
+        r = sd[n].grad
+        if r is None and n.startswith("convs.") and ".nn." in n:
+            r = sd[n.replace("convs.", "nns.").replace(".nn.", ".")].grad
+        assert_close_rel(q.grad, r, 1e-4, "grad " + n)   # 166k-row BatchNorm reductions: fp32 summation-order noise
