@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- train graphs/s of the hot path on BASELINE.json's config C2, plus the aggregation roofline.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (libdn4gl.so kernels; one process per GPU)
+  python bench.py --impl reference --steps K --warmup W    the reference's CPU path (oracle port) on host cores
+
+Workload "c2": 1113 synthetic PROTEINS-shaped graphs per GPU (seeded), one STEP = dummy-node augmentation +
+edge-to-vertex (CONJ) transform + PyG canonicalisation + CSR build + GIN (hidden 32, 4 layers, train_eps,
+sum pooling -- hyper_params.py:15) forward + nll_loss + backward [+ gradient all-reduce] + Adam step.
+`value`   : inputs (raw graphs) resident in HBM, L2 flushed between steps, device-timed, max over ranks.
+`e2e`     : same step through ClassificationPipeline.step(): pinned host buffers -> H2D -> ... -> loss D2H.
+`roofline`: the aggregation kernel (dn4gl_spmm_sum_f32 at D=32), algorithmic bytes / CUDA-event duration.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from argparse import Namespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+HID, LAYERS, CLASSES, LR = 32, 4, 2, 0.01   # hyper_params.py:15 (GIN / PROTEINS)
+NUM_NODE_LABELS = 2                          # CONJ graphs: vertex label = original edge label (1) or dummy (0)
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graphs", type=int, default=1113, help="graphs per GPU (C2: 1113)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (C transforms + torch-CPU GIN), all host threads
+def cpu_reference_run(raw, steps, warmup):
+    from oracle import models as OM
+    from oracle import transforms as OT
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+    torch.manual_seed(0)
+    args = Namespace(num_features=NUM_NODE_LABELS, hidden_dim=HID, num_classes=CLASSES, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": LAYERS, "aggregation": "sum"}, epochs=1, device="cpu")
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "num_batches" not in k)
+          for k, v in GIN(args).state_dict().items()}
+    params = []
+    seen = set()
+    for k, v in sd.items():   # nns.* / convs.*.nn.* alias: optimise each tensor once
+        if v.requires_grad and not (k.startswith("convs.") and ".nn." in k):
+            params.append(v)
+    opt = torch.optim.Adam(params, lr=LR)
+    y = torch.from_numpy(raw["y"])
+    B = raw["num_graphs"]
+    t_tr, t_md = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        conj = OT.tu_conjugate(OT.tu_add_dummy(raw))
+        s, d, _, _ = OT.pyg_coalesce(conj["src"], conj["dst"])
+        x = torch.from_numpy(np.eye(NUM_NODE_LABELS, dtype=np.float32)[conj["vlabel"]])
+        ei = torch.from_numpy(np.stack([s, d]).astype(np.int64))
+        batch = torch.from_numpy(np.repeat(np.arange(B), np.diff(conj["node_ptr"])).astype(np.int64))
+        t1 = time.perf_counter()
+        opt.zero_grad()
+        out = OM.gin_classifier(sd, x, ei, batch, B, LAYERS, "sum")
+        loss = F.nll_loss(out, y)
+        loss.backward()
+        opt.step()
+        t2 = time.perf_counter()
+        if it >= warmup:
+            t_tr.append(t1 - t0)
+            t_md.append(t2 - t1)
+    total = sum(t_tr) + sum(t_md)
+    return dict(graphs_per_s=B * steps / total, ms_per_step=1e3 * total / steps,
+                transform_ms=1e3 * statistics.mean(t_tr), train_ms=1e3 * statistics.mean(t_md),
+                cores=torch.get_num_threads())
+
+
+def reference_arm(a):
+    """rank 0 only: times the reference's CPU implementation (oracle port) on the host cores."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from dummynode4graphlearning_b200 import synth
+    raw = synth.tu_batch("proteins", a.graphs, seed=0)
+    r = cpu_reference_run(raw, a.steps, max(a.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "train graphs/sec", "value": r["graphs_per_s"], "unit": "graphs/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a.graphs, 1),
+        "cpu_baseline": {"value": r["graphs_per_s"], "unit": "graphs/s", "cores": r["cores"], "kind": "port",
+                         "sample": "full C2 batch (%d graphs) per step, %d steps; C restatement of the transforms "
+                                   "(oracle/c) + torch-CPU restatement of GIN fwd/bwd + Adam (oracle/models.py)"
+                                   % (a.graphs, a.steps),
+                         "transform_ms": r["transform_ms"], "train_ms": r["train_ms"]},
+        "e2e": {"value": r["graphs_per_s"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(graphs, n_gpus):
+    return {"workload": "c2: dummy + edge-to-vertex (CONJ) transform + GIN(hidden 32, 4 layers, train_eps, sum pool) "
+                        "train step on synthetic PROTEINS-shaped graphs", "graphs_per_gpu": graphs,
+            "global_batch": graphs * n_gpus, "avg_nodes": 39, "optimizer": "Adam(lr=0.01)",
+            "parallelism": "dp%d" % n_gpus, "l2": "flushed between steps (256 MiB write inside the timed region)"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.path = "/tmp/dn4gl_clocks_%d_%d.csv" % (os.getpid(), index)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for ln in open(self.path):
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class EntryPointTimer:
+    """CUDA-event pair around every C-ABI call (on the launching stream): per-entry-point device time."""
+
+    def __init__(self):
+        self.pending, self.stack = [], []
+
+    def before(self, name, args):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.stack.append(e)
+
+    def after(self, name, args):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        key = name
+        if name == "dn4gl_spmm_sum_f32":
+            key = "%s[D=%d]" % (name, args[6])
+        self.pending.append((key, self.stack.pop(), e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for key, e0, e1 in self.pending:
+            agg.setdefault(key, []).append(e0.elapsed_time(e1))
+        return {k: {"calls": len(v), "total_ms": sum(v), "avg_us": 1e3 * sum(v) / len(v)} for k, v in agg.items()}
+
+
+def ours(a):
+    import torch.distributed as dist
+    from dummynode4graphlearning_b200 import _lib, synth, transforms as T
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+    from dummynode4graphlearning_b200.parallel import max_over_ranks
+    from dummynode4graphlearning_b200.pipelines import ClassificationPipeline, host_bytes, pin_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    raw = synth.tu_batch("proteins", a.graphs, seed=rank)      # weak scaling: every rank owns its own 1113 graphs
+    host = pin_batch({k: v for k, v in raw.items() if k != "vattr"})
+    dev_batch = T.to_device({k: v for k, v in raw.items() if k != "vattr"}, dev)
+    torch.manual_seed(0)
+    args = Namespace(num_features=NUM_NODE_LABELS, hidden_dim=HID, num_classes=CLASSES, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": LAYERS, "aggregation": "sum"}, epochs=1, device=str(dev))
+    model = GIN(args).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=LR)
+    pipe = ClassificationPipeline(model, opt, mode="conj", num_node_labels=NUM_NODE_LABELS, node_label_min=0)
+    pipe.global_batch = a.graphs * world
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        flush.fill_(1)
+        pipe.step_resident(dev_batch)
+    # ---- timed region: EXACTLY K steps, device-timed ----------------------------------------------------
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    k0 = L.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        flush.fill_(1)
+        loss = pipe.step_resident(dev_batch)
+    e1.record()
+    barrier()
+    launches = L.kernel_launches() - k0
+    ms = max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
+    clk = clocks.stop() if clocks else None
+    value = a.graphs * world / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the public API, copies inside the timed region --------------------------
+    for _ in range(2):
+        pipe.step(host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush.fill_(1)
+        last = pipe.step(host)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / a.steps
+    e2e_value = a.graphs * world / (e2e_ms * 1e-3)
+
+    # ---- per-entry-point device times + breakdown (instrumented pass, not part of `value`) -----------------
+    timer = EntryPointTimer()
+    L.profiler = timer
+    tr0, tr1, tn1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    tr_ms, tn_ms = [], []
+    data = None
+    for _ in range(min(a.steps, 10)):
+        flush.fill_(1)
+        tr0.record()
+        data = pipe.transform(dev_batch)
+        tr1.record()
+        pipe.train_on(data)
+        tn1.record()
+        torch.cuda.synchronize()
+        tr_ms.append(tr0.elapsed_time(tr1)); tn_ms.append(tr1.elapsed_time(tn1))
+    L.profiler = None
+    per_entry = timer.summary()
+    # cold-cache duration of the dominant kernel: aggregation launches alone with an L2 flush before each
+    from dummynode4graphlearning_b200 import ops
+    s = data.structure
+    N, E = s.num_nodes, int(s.csr_in.nnz)
+    xh = torch.rand((N, HID), device=dev)
+    iso = []
+    for _ in range(10):
+        flush.fill_(1)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        ops.spmm_sum(xh, s.csr_in, s.csr_out, 1.0)
+        a1.record()
+        torch.cuda.synchronize()
+        iso.append(a0.elapsed_time(a1))
+    peaks, which = measured_peaks()
+    agg_bytes = 4 * HID * N * 2 + 4 * E + 4 * (N + 1)        # compulsory traffic
+    in_step = per_entry.get("dn4gl_spmm_sum_f32[D=%d]" % HID, {"avg_us": float("nan"), "calls": 0})
+    achieved = agg_bytes / (in_step["avg_us"] * 1e-6) / 1e9
+    roofline = {"kernel": "dn4gl_spmm_sum_f32 (spmm_rows_kernel<8,1> + spmm_heavy_kernel<8,1>), D=32, N=%d, E=%d" % (N, E),
+                "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                "algorithmic_bytes_per_launch": agg_bytes, "avg_launch_us_in_step": in_step["avg_us"],
+                "launches_timed": in_step["calls"], "cold_l2_launch_us": statistics.median(iso),
+                "cold_l2_gbs": agg_bytes / (statistics.median(iso) * 1e-6) / 1e9,
+                "gather_effective_gbs": (4 * HID * (E + N) + 4 * E + 4 * (N + 1)) / (in_step["avg_us"] * 1e-6) / 1e9,
+                "traffic": None}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        r = cpu_reference_run(raw, 10, 2)
+        cpu = {"value": r["graphs_per_s"], "unit": "graphs/s", "cores": r["cores"], "kind": "port",
+               "sample": "full C2 batch (%d graphs) per step, 10 timed steps after 2 warm-up" % a.graphs,
+               "transform_ms": r["transform_ms"], "train_ms": r["train_ms"]}
+    own_ms = sum(v["total_ms"] for v in per_entry.values()) / max(len(tr_ms), 1)
+    line = {
+        "metric": "train graphs/sec", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a.graphs, world),
+        "clocks": clk, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": host_bytes(host), "d2h_bytes_per_step": 4 + 8 + 4},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "breakdown": {"transform_ms": statistics.mean(tr_ms), "train_ms": statistics.mean(tn_ms),
+                      "own_kernels_ms_per_step": own_ms, "conj_nodes": N, "conj_edges": E,
+                      "final_loss": float(loss.item()), "e2e_last_loss": last,
+                      "entry_points": {k: {"calls_per_step": v["calls"] / max(len(tr_ms), 1), "avg_us": round(v["avg_us"], 2)}
+                                       for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1]["total_ms"])}},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        ours(a)

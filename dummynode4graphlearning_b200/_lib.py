@@ -71,12 +71,24 @@ class _Lib:
         return getattr(self._dll, name)
 
     def call(self, name, *args):
-        """status-returning entry point; raises Dn4glError with the library's message on failure."""
+        """status-returning entry point; raises Dn4glError with the library's message on failure.
+        If a profiler is installed (bench.py's per-entry-point CUDA-event timing) it brackets the call."""
+        prof = self.profiler
+        if prof is not None:
+            prof.before(name, args)
         rc = getattr(self._dll, name)(*args)
+        if prof is not None:
+            prof.after(name, args)
         self.launches += 1
         if rc != 0:
             msg = self._dll.dn4gl_last_error()
             raise Dn4glError("%s failed (%d): %s" % (name, rc, msg.decode() if msg else "?"))
+
+    profiler = None
+
+    def kernel_launches(self):
+        """CUDA kernels launched by the library so far in this process (dn4gl_launch_count)."""
+        return int(self._dll.dn4gl_launch_count())
 
     def size(self, name, *args):
         return int(getattr(self._dll, name)(*args))

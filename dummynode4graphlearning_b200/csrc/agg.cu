@@ -172,7 +172,7 @@ extern "C" int dn4gl_spmm_sum_f32(const int32_t *row_ptr, const int32_t *col, co
             return DN4GL_EINVAL;
     }
 #undef SPMM_CASE
-    DN_LAUNCHED();
+    DN_LAUNCHED_N((heavy_rows != nullptr && heavy_count != nullptr && heavy_threshold > 0) ? 2 : 1);
     return DN4GL_OK;
 }
 

@@ -26,14 +26,19 @@ void dn4gl_set_error(const char *fmt, ...);
         }                                                                                    \
     } while (0)
 
-#define DN_LAUNCHED()                                                                        \
+// checks the launches issued since the previous check and adds them to the process-wide kernel counter
+// (dn4gl_launch_count(); bench.py reports it as gpu_launches)
+void dn4gl_note_launches(int n);
+#define DN_LAUNCHED_N(n)                                                                     \
     do {                                                                                     \
         cudaError_t e__ = cudaGetLastError();                                                \
         if (e__ != cudaSuccess) {                                                            \
             dn4gl_set_error("%s: launch failed: %s", __func__, cudaGetErrorString(e__));     \
             return DN4GL_ECUDA;                                                              \
         }                                                                                    \
+        dn4gl_note_launches(n);                                                              \
     } while (0)
+#define DN_LAUNCHED() DN_LAUNCHED_N(1)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -13,6 +13,11 @@ void dn4gl_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void dn4gl_note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t dn4gl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 extern "C" int dn4gl_version(void) { return DN4GL_ABI_VERSION; }
 extern "C" const char *dn4gl_last_error(void) { return g_err; }
 

@@ -136,7 +136,7 @@ extern "C" int dn4gl_dmp_node_agg_f32(const int32_t *in_ptr, const int32_t *in_e
             return DN4GL_EINVAL;
     }
 #undef DMP_CASE
-    DN_LAUNCHED();
+    DN_LAUNCHED_N(heavy ? 2 : 1);
     return DN4GL_OK;
 }
 

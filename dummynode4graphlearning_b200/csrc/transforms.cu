@@ -283,11 +283,11 @@ extern "C" int dn4gl_tu_conjugate_count(int32_t B, const int32_t *node_ptr, cons
     fill_i32<<<blocks(N + 1), 256, 0, st>>>(c.fd_in, N + 1, INT32_MAX);
     fill_i32<<<blocks(N + 1), 256, 0, st>>>(c.fd_out, N + 1, INT32_MAX);
     DN_CUDA(cudaMemsetAsync(c.real_in, 0, static_cast<size_t>(N + 1) * sizeof(int32_t), st));
-    DN_LAUNCHED();
+    DN_LAUNCHED_N(3);
     if (E > 0) {
         conj_edge_pass1<<<blocks(E), 256, 0, st>>>(B, edge_ptr, src, dst, e_isdummy, E, c);
         conj_edge_pass2<<<blocks(E), 256, 0, st>>>(src, e_isdummy, E, c, cand_off);
-        DN_LAUNCHED();
+        DN_LAUNCHED_N(2);
     }
     int rc = dn4gl_exclusive_scan_i32(cand_off, cand_off, E, c.scan_ws, c.scan_bytes, stream);
     if (rc != DN4GL_OK) return rc;
@@ -295,7 +295,7 @@ extern "C" int dn4gl_tu_conjugate_count(int32_t B, const int32_t *node_ptr, cons
     if (rc != DN4GL_OK) return rc;
     conj_graph_offsets<<<blocks(B + 1), 256, 0, st>>>(B, edge_ptr, c.kept, cand_off, o_node_ptr, o_edge_ptr);
     if (E > 0) conj_newid<<<blocks(E), 256, 0, st>>>(e_isdummy, E, c, newid);
-    DN_LAUNCHED();
+    DN_LAUNCHED_N(E > 0 ? 2 : 1);
     return DN4GL_OK;
 }
 

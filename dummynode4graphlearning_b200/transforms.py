@@ -138,7 +138,7 @@ def sub_add_dummy(b, max_nv, max_nvl, max_ne, max_nel):
     return o
 
 
-def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None):
+def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_min=None, with_edge_attr=True):
     """What PyG ``read_tu_data`` + ``PYGDataset.set_dummy_flags`` turn the saved TU files into
     (graph_neural_networks/dataset.py:118-151): one-hot ``x`` (attribute column first, then labels
     shifted to start at 0), ``edge_index`` int64 with self loops removed and coalesced = sorted by
@@ -161,7 +161,10 @@ def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None):
     o_src, o_dst, o_first = o_src[:E2], o_dst[:E2], o_first[:E2]
     # node features: [attr?, one_hot(label - min)]
     vl = b["vlabel"].long()
-    vmin = int(vl.min().item()) if N else 0
+    if node_label_min is not None and num_node_labels is not None:
+        vmin = int(node_label_min)      # caller knows the label range: no device->host sync
+    else:
+        vmin = int(vl.min().item()) if N else 0
     nvl = int(num_node_labels) if num_node_labels is not None else (int(vl.max().item()) - vmin + 1 if N else 0)
     x = torch.zeros((N, nvl), dtype=torch.float32, device=dev)
     x.scatter_(1, (vl - vmin).view(-1, 1), 1.0)
@@ -173,7 +176,7 @@ def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None):
                node_ptr=b["node_ptr"], src=o_src, dst=o_dst, first_edge=o_first,
                batch=torch.repeat_interleave(torch.arange(B, device=dev),
                                              (b["node_ptr"][1:] - b["node_ptr"][:-1]).long(), output_size=N))
-    if b.get("has_edge_labels", True) and E > 0:
+    if with_edge_attr and b.get("has_edge_labels", True) and E > 0:
         el = b["elabel"].long()
         emin = int(el.min().item())
         nel = int(num_edge_labels) if num_edge_labels is not None else int(el.max().item()) - emin + 1

@@ -41,6 +41,8 @@ int dn4gl_version(void);
 const char *dn4gl_last_error(void);
 /* binds the calling thread to `device` (cudaSetDevice); one process per GPU is the intended use */
 int dn4gl_set_device(int device);
+/* number of CUDA kernels this library has launched in this process so far (monotonic counter) */
+int64_t dn4gl_launch_count(void);
 
 /* ---- integer plumbing ------------------------------------------------------------------- */
 

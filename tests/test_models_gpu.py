@@ -145,7 +145,7 @@ def test_classifiers_match_reference_golden(device, tag):
     assert set(params) == set(g["grads"])
     for n, ref in g["grads"].items():
         if ref is not None:
-            assert_close_rel(params[n].grad, ref, 2e-5, "grad " + n)   # BatchNorm backward amplifies rounding
+            assert_close_rel(params[n].grad, ref, 2e-5, "grad " + n, atol=2e-5)   # BN: pre-BN biases have zero gradient
 
 
 def test_gin_full_size_c2_against_oracle(device):
@@ -179,4 +179,4 @@ def test_gin_full_size_c2_against_oracle(device):
         r = sd[n].grad
         if r is None and n.startswith("convs.") and ".nn." in n:
             r = sd[n.replace("convs.", "nns.").replace(".nn.", ".")].grad
-        assert_close_rel(q.grad, r, 1e-4, "grad " + n)   # 166k-row BatchNorm reductions: fp32 summation-order noise
+        assert_close_rel(q.grad, r, 1e-4, "grad " + n, atol=1e-4)   # 166k-row BatchNorm reductions: fp32 summation-order noise

@@ -150,4 +150,4 @@ def test_classification_oracle_matches_reference_golden(tag):
         # nns.i.* and convs.i.nn.* alias the same parameters (gconv.py:195-197); the oracle reads nns.*
         if got is None and n.startswith("convs.") and ".nn." in n:
             got = sd[n.replace("convs.", "nns.").replace(".nn.", ".")].grad
-        assert_close_rel(got, ref, 2e-5, "grad " + n)
+        assert_close_rel(got, ref, 2e-5, "grad " + n, atol=2e-5)
