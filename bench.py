@@ -305,8 +305,8 @@ def ours(a):
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_launch": agg_bytes, "avg_launch_us_in_step": in_step["avg_us"],
-                "launches_timed": in_step["calls"], "cold_l2_launch_us": statistics.median(iso),
-                "cold_l2_gbs": agg_bytes / (statistics.median(iso) * 1e-6) / 1e9,
+                "launches_timed": in_step["calls"], "cold_l2_launch_us": 1e3 * statistics.median(iso),
+                "cold_l2_gbs": agg_bytes / (statistics.median(iso) * 1e-3) / 1e9,
                 "gather_effective_gbs": (4 * HID * (E + N) + 4 * E + 4 * (N + 1)) / (in_step["avg_us"] * 1e-6) / 1e9,
                 "traffic": None}
 

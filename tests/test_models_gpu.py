@@ -150,7 +150,11 @@ def test_classifiers_match_reference_golden(device, tag):
 
 def test_gin_full_size_c2_against_oracle(device):
     """BASELINE config C2 at full size: CONJ transform (GPU) of 1113 PROTEINS-shaped graphs + GIN (hid 32, 4 layers)
-    forward/backward vs the oracle restatement."""
+    forward/backward.  The synthetic CONJ features are degenerate (two distinct one-hot rows), so several BatchNorm
+    channels have ~zero variance and amplify fp32 rounding by 1/sqrt(eps) per layer: two correct fp32
+    implementations differ by far more than 1e-5 here.  The size-independent criterion is therefore accuracy against
+    exact arithmetic: the float64 oracle is the ground truth, and the CUDA path must be as close to it as the
+    fp32 CPU oracle (the reference's own arithmetic) is, within a factor 4."""
     from dummynode4graphlearning_b200 import synth, transforms as T
     from dummynode4graphlearning_b200.graph_classification.data import Batch
     from dummynode4graphlearning_b200.graph_classification.models import GIN
@@ -165,18 +169,33 @@ def test_gin_full_size_c2_against_oracle(device):
                      additional={"train_eps": True, "num_layers": 4, "aggregation": "sum"}, epochs=3, device=str(device))
     torch.manual_seed(0)
     model = GIN(args)
-    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in model.state_dict().items()}
+    base = model.state_dict()
+
+    def oracle_run(dtype):
+        sd = {k: (v.clone().to(dtype).requires_grad_("running" not in k) if v.is_floating_point() else v.clone())
+              for k, v in base.items()}
+        ref = OM.gin_classifier(sd, can["x"].cpu().to(dtype), can["edge_index"].cpu(), can["batch"].cpu(),
+                                can["num_graphs"], 4, "sum")
+        loss = F.nll_loss(ref, can["y"].cpu())
+        loss.backward()
+        return ref.detach(), loss.detach(), sd
+
+    r64, l64, sd64 = oracle_run(torch.float64)
+    r32, l32, sd32 = oracle_run(torch.float32)
     model = model.to(device).train()
     out = model(data)
     loss = F.nll_loss(out, can["y"])
     loss.backward()
-    ref = OM.gin_classifier(sd, can["x"].cpu(), can["edge_index"].cpu(), can["batch"].cpu(), can["num_graphs"], 4, "sum")
-    ref_loss = F.nll_loss(ref, can["y"].cpu())
-    ref_loss.backward()
-    assert_close_rel(out, ref, 2e-5, "log_softmax")
-    assert_close_rel(loss, ref_loss, 2e-5, "loss")
+
+    def err(a, b):
+        return float((a.detach().double().cpu() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
+
+    assert err(out, r64) <= 4 * err(r32, r64) + 1e-5, (err(out, r64), err(r32, r64))
+    assert err(loss, l64) <= 4 * err(l32, l64) + 1e-5
     for n, q in model.named_parameters():
-        r = sd[n].grad
-        if r is None and n.startswith("convs.") and ".nn." in n:
-            r = sd[n.replace("convs.", "nns.").replace(".nn.", ".")].grad
-        assert_close_rel(q.grad, r, 1e-4, "grad " + n, atol=1e-4)   # 166k-row BatchNorm reductions: fp32 summation-order noise
+        key = n if sd64[n].grad is not None else n.replace("convs.", "nns.").replace(".nn.", ".")
+        g64, g32 = sd64[key].grad, sd32[key].grad
+        scale = float(g64.abs().max())
+        e_gpu = float((q.grad.double().cpu() - g64).abs().max())
+        e_cpu = float((g32.double() - g64).abs().max())
+        assert e_gpu <= 4 * e_cpu + 1e-5 * max(scale, 1e-3), (n, e_gpu, e_cpu, scale)
