@@ -242,6 +242,36 @@ segment_sum_generic(const int32_t *__restrict__ seg_ptr, const uint8_t *__restri
     }
 }
 
+// narrow rows (D <= 8, e.g. per-class scores pooled at gconv.py:210): one warp per segment, lanes stride the ROWS,
+// every lane keeps all D column sums, fixed-shape shuffle tree at the end.
+template <int DMAX>
+__global__ void __launch_bounds__(256)
+segment_sum_narrow(const int32_t *__restrict__ seg_ptr, const uint8_t *__restrict__ mask, const float *__restrict__ x,
+                   float *__restrict__ out, int B, int D, int mode) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const int beg = seg_ptr[warp], end = seg_ptr[warp + 1];
+    float acc[DMAX];
+#pragma unroll
+    for (int c = 0; c < DMAX; ++c) acc[c] = 0.f;
+    for (int r = beg + lane; r < end; r += 32) {
+        if (mask && mask[r]) continue;
+#pragma unroll
+        for (int c = 0; c < DMAX; ++c)
+            if (c < D) acc[c] = __fadd_rn(acc[c], __ldg(x + static_cast<int64_t>(r) * D + c));
+    }
+#pragma unroll
+    for (int c = 0; c < DMAX; ++c)
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) acc[c] = __fadd_rn(acc[c], __shfl_xor_sync(0xffffffffu, acc[c], o));
+    if (lane == 0) {
+        const float sc = (mode == 1) ? 1.f / static_cast<float>(max(end - beg, 1)) : 1.f;
+#pragma unroll
+        for (int c = 0; c < DMAX; ++c)
+            if (c < D) out[static_cast<int64_t>(warp) * D + c] = (mode == 1) ? acc[c] * sc : acc[c];
+    }
+}
+
 extern "C" int dn4gl_segment_sum_f32(const int32_t *seg_ptr, const uint8_t *mask, const float *x, float *out,
                                      int32_t B, int32_t D, int32_t mode, void *stream) {
     DN_ARG(B >= 0 && D > 0 && (mode == 0 || mode == 1));
@@ -262,8 +292,12 @@ extern "C" int dn4gl_segment_sum_f32(const int32_t *seg_ptr, const uint8_t *mask
         case 64: SEG_CASE(32, 2);
         case 128: SEG_CASE(32, 4);
         default:
-            segment_sum_generic<<<static_cast<unsigned>(ceil_div64(static_cast<int64_t>(B) * 32, 256)), 256, 0, st>>>(
-                seg_ptr, mask, x, out, B, D, mode);
+            if (D <= 8)
+                segment_sum_narrow<8><<<static_cast<unsigned>(ceil_div64(static_cast<int64_t>(B) * 32, 256)), 256, 0, st>>>(
+                    seg_ptr, mask, x, out, B, D, mode);
+            else
+                segment_sum_generic<<<static_cast<unsigned>(ceil_div64(static_cast<int64_t>(B) * 32, 256)), 256, 0, st>>>(
+                    seg_ptr, mask, x, out, B, D, mode);
     }
 #undef SEG_CASE
     DN_LAUNCHED();

@@ -177,6 +177,7 @@ __device__ __forceinline__ unsigned long long sort_key(const int32_t *__restrict
 }
 
 constexpr int LIGHT_SORT_MAX = 32;
+constexpr int HEAVY_SORT_MID = 4096;
 
 // one thread per row, rows with <= 32 items: insertion sort in local memory.  Longer rows are
 // appended to a work list for the CTA-per-row kernel.
@@ -189,6 +190,7 @@ __global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, 
     if (d <= 1) return;
     if (d > LIGHT_SORT_MAX) {
         worklist[atomicAdd(work_count, 1)] = static_cast<int32_t>(r);
+        if (d > HEAVY_SORT_MID) atomicAdd(work_count + 1, 1);
         return;
     }
     unsigned long long a[LIGHT_SORT_MAX];
@@ -202,16 +204,20 @@ __global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, 
     for (int i = 0; i < d; ++i) items[beg + i] = static_cast<int32_t>(a[i] & 0xffffffffu);
 }
 
-// one CTA per listed row: rank sort in shared memory (keys are unique).  Rows longer than `cap`
-// are left to the next (larger) instantiation; rows longer than DN4GL_MAX_ROW_DEGREE raise err_flag.
+// one CTA per listed row: rank sort in shared memory on the unique key (primary[item], item).  Keys are kept as two
+// int32 arrays and compared four at a time (128-bit shared loads).  Rows longer than `cap` are left to the next
+// (larger) instantiation; rows longer than DN4GL_MAX_ROW_DEGREE raise err_flag.
+template <bool HAS_PRIMARY>
 __global__ void __launch_bounds__(256) sort_rows_heavy(const int32_t *__restrict__ row_ptr,
                                                        int32_t *__restrict__ items,
                                                        const int32_t *__restrict__ primary,
                                                        const int32_t *__restrict__ worklist,
                                                        const int32_t *__restrict__ work_count, int lo, int cap,
-                                                       int32_t *err_flag) {
-    extern __shared__ unsigned long long skeys[];
-    const int n_work = *work_count;
+                                                       int only_if_flagged, int32_t *err_flag) {
+    extern __shared__ __align__(16) int32_t skeys[];
+    int32_t *ki = skeys, *kp = skeys + cap;
+    if (only_if_flagged && work_count[1] == 0) return;   // no row exceeded the mid capacity: nothing to do
+    const int n_work = work_count[0];
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         int r = worklist[w];
         int beg = row_ptr[r], d = row_ptr[r + 1] - beg;
@@ -220,13 +226,32 @@ __global__ void __launch_bounds__(256) sort_rows_heavy(const int32_t *__restrict
             if (cap >= DN4GL_MAX_ROW_DEGREE && err_flag && threadIdx.x == 0) atomicExch(err_flag, DN4GL_ELIMIT);
             continue;
         }
-        for (int i = threadIdx.x; i < d; i += blockDim.x) skeys[i] = sort_key(primary, items[beg + i]);
+        const int dpad = (d + 3) & ~3;
+        for (int i = threadIdx.x; i < dpad; i += blockDim.x) {
+            int it = (i < d) ? items[beg + i] : INT32_MAX;
+            ki[i] = it;
+            if (HAS_PRIMARY) kp[i] = (i < d) ? primary[it] : INT32_MAX;
+        }
         __syncthreads();
+        const int4 *ki4 = reinterpret_cast<const int4 *>(ki);
+        const int4 *kp4 = reinterpret_cast<const int4 *>(kp);
         for (int i = threadIdx.x; i < d; i += blockDim.x) {
-            unsigned long long k = skeys[i];
+            const int k = ki[i];
             int rank = 0;
-            for (int j = 0; j < d; ++j) rank += (skeys[j] < k);
-            items[beg + rank] = static_cast<int32_t>(k & 0xffffffffu);
+            if (HAS_PRIMARY) {
+                const int p = kp[i];
+                for (int j = 0; j < dpad / 4; ++j) {
+                    int4 a = ki4[j], q = kp4[j];
+                    rank += (q.x < p || (q.x == p && a.x < k)) + (q.y < p || (q.y == p && a.y < k)) +
+                            (q.z < p || (q.z == p && a.z < k)) + (q.w < p || (q.w == p && a.w < k));
+                }
+            } else {
+                for (int j = 0; j < dpad / 4; ++j) {
+                    int4 a = ki4[j];
+                    rank += (a.x < k) + (a.y < k) + (a.z < k) + (a.w < k);
+                }
+            }
+            items[beg + rank] = k;
         }
         __syncthreads();
     }
@@ -238,30 +263,37 @@ __global__ void csr_fill_col(const int32_t *__restrict__ eid, const int32_t *__r
     if (p < E) col[p] = val ? val[eid[p]] : eid[p];
 }
 
-constexpr int HEAVY_SORT_MID = 4096;
-
 // sorts the items of every row by (primary[item], item); shared by the CSR build and coalesce
 int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int32_t *primary,
                     int32_t *worklist, int32_t *work_count, int32_t *err_flag, cudaStream_t st) {
     if (N == 0) return DN4GL_OK;
-    DN_CUDA(cudaMemsetAsync(work_count, 0, sizeof(int32_t), st));
+    DN_CUDA(cudaMemsetAsync(work_count, 0, 2 * sizeof(int32_t), st));
     sort_rows_light<<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, N, items, primary, worklist,
                                                                                 work_count);
     DN_LAUNCHED();
     const int sms = dn4gl_num_sms();
-    sort_rows_heavy<<<sms * 4, 256, HEAVY_SORT_MID * sizeof(unsigned long long), st>>>(
-        row_ptr, items, primary, worklist, work_count, LIGHT_SORT_MAX, HEAVY_SORT_MID, err_flag);
-    DN_LAUNCHED();
-    // large instantiation: DN4GL_MAX_ROW_DEGREE 8-byte keys = 196608 B of dynamic shared memory
+    const size_t mid = static_cast<size_t>(HEAVY_SORT_MID) * 2 * sizeof(int32_t);
+    // large instantiation: DN4GL_MAX_ROW_DEGREE keys x 2 int32 arrays = 196608 B of dynamic shared memory; it returns
+    // immediately unless the light pass flagged a row above the mid capacity
+    const size_t big = static_cast<size_t>(DN4GL_MAX_ROW_DEGREE) * 2 * sizeof(int32_t);
     static bool attr_set = false;
-    const size_t big = static_cast<size_t>(DN4GL_MAX_ROW_DEGREE) * sizeof(unsigned long long);
     if (!attr_set) {
-        DN_CUDA(cudaFuncSetAttribute(sort_rows_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big)));
+        DN_CUDA(cudaFuncSetAttribute(sort_rows_heavy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big)));
+        DN_CUDA(cudaFuncSetAttribute(sort_rows_heavy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big)));
         attr_set = true;
     }
-    sort_rows_heavy<<<sms, 256, big, st>>>(row_ptr, items, primary, worklist, work_count, HEAVY_SORT_MID,
-                                           DN4GL_MAX_ROW_DEGREE, err_flag);
-    DN_LAUNCHED();
+    if (primary) {
+        sort_rows_heavy<true><<<sms * 4, 256, mid, st>>>(row_ptr, items, primary, worklist, work_count, LIGHT_SORT_MAX,
+                                                         HEAVY_SORT_MID, 0, err_flag);
+        sort_rows_heavy<true><<<sms, 256, big, st>>>(row_ptr, items, primary, worklist, work_count, HEAVY_SORT_MID,
+                                                     DN4GL_MAX_ROW_DEGREE, 1, err_flag);
+    } else {
+        sort_rows_heavy<false><<<sms * 4, 256, mid, st>>>(row_ptr, items, primary, worklist, work_count, LIGHT_SORT_MAX,
+                                                          HEAVY_SORT_MID, 0, err_flag);
+        sort_rows_heavy<false><<<sms, 256, big, st>>>(row_ptr, items, primary, worklist, work_count, HEAVY_SORT_MID,
+                                                      DN4GL_MAX_ROW_DEGREE, 1, err_flag);
+    }
+    DN_LAUNCHED_N(2);
     return DN4GL_OK;
 }
 

@@ -354,32 +354,29 @@ extern "C" int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const
 // Input: the edge list (src, dst in edge-id order) and its by-src CSR (row_ptr, items = edge ids
 // from dn4gl_build_csr(key=src)).  Rows are sorted in place by (dst, edge id), self loops and
 // repeated (src,dst) pairs are flagged out, survivors are compacted in (src, dst) order.
+// one thread per CSR position p (rows are already sorted by (dst, edge id)): keep[p] = not a self loop and not a
+// repeat of the previous destination in the same row
 __global__ void coalesce_flags(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ items,
-                               const int32_t *__restrict__ dst, int64_t N, int32_t *__restrict__ keep) {
-    // one thread per row (coalesce runs once per batch, not per layer)
-    int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (r >= N) return;
-    int prev = -1;
-    for (int p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
-        int d = dst[items[p]];
-        keep[p] = (d != r && d != prev) ? 1 : 0;
-        prev = d;
-    }
+                               const int32_t *__restrict__ dst, int64_t N, int64_t E, int32_t *__restrict__ keep) {
+    int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= E) return;
+    int r = segment_of(row_ptr, static_cast<int>(N), p);
+    int d = dst[items[p]];
+    int prev = (p > row_ptr[r]) ? dst[items[p - 1]] : -1;
+    keep[p] = (d != r && d != prev) ? 1 : 0;
 }
 
 __global__ void coalesce_compact(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ items,
-                                 const int32_t *__restrict__ dst, int64_t N,
+                                 const int32_t *__restrict__ dst, int64_t N, int64_t E,
                                  const int32_t *__restrict__ keep_scan, int32_t *__restrict__ o_src,
                                  int32_t *__restrict__ o_dst, int32_t *__restrict__ o_first) {
-    int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (r >= N) return;
-    for (int p = row_ptr[r]; p < row_ptr[r + 1]; ++p) {
-        int q = keep_scan[p];
-        if (keep_scan[p + 1] != q) {
-            o_src[q] = static_cast<int32_t>(r);
-            o_dst[q] = dst[items[p]];
-            o_first[q] = items[p];
-        }
+    int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= E) return;
+    int q = keep_scan[p];
+    if (keep_scan[p + 1] != q) {
+        o_src[q] = segment_of(row_ptr, static_cast<int>(N), p);
+        o_dst[q] = dst[items[p]];
+        o_first[q] = items[p];
     }
 }
 
@@ -409,11 +406,11 @@ extern "C" int dn4gl_coalesce(const int32_t *dst, int64_t N, int64_t E, const in
     }
     int rc = dn4gl_sort_rows(row_ptr, N, items, dst, worklist, work_count, err_flag, st);
     if (rc != DN4GL_OK) return rc;
-    coalesce_flags<<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, items, dst, N, keep_scan);
+    coalesce_flags<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(row_ptr, items, dst, N, E, keep_scan);
     DN_LAUNCHED();
     rc = dn4gl_exclusive_scan_i32(keep_scan, keep_scan, E, scan_ws, scan_bytes, stream);
     if (rc != DN4GL_OK) return rc;
-    coalesce_compact<<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, items, dst, N, keep_scan,
+    coalesce_compact<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(row_ptr, items, dst, N, E, keep_scan,
                                                                                  o_src, o_dst, o_first);
     DN_LAUNCHED();
     return DN4GL_OK;

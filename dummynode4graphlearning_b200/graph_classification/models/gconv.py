@@ -66,8 +66,8 @@ def global_mean_pool(x, batch, size=None, node_ptr=None):
 
 
 def _gin_mlp(din, dout):
-    return nn.Sequential(nn.Linear(din, dout), nn.BatchNorm1d(dout), nn.ReLU(),
-                         nn.Linear(dout, dout), nn.BatchNorm1d(dout), nn.ReLU())
+    return nn.Sequential(ops.Linear(din, dout), nn.BatchNorm1d(dout), nn.ReLU(),
+                         ops.Linear(dout, dout), nn.BatchNorm1d(dout), nn.ReLU())
 
 
 class GIN(torch.nn.Module):
@@ -92,7 +92,7 @@ class GIN(torch.nn.Module):
             else:
                 nns.append(_gin_mlp(self.embeddings_dim[layer - 1], out_dim))
                 convs.append(GINConv(nns[-1], train_eps=train_eps))
-            linears.append(nn.Linear(out_dim, self.num_classes))
+            linears.append(ops.Linear(out_dim, self.num_classes))
         self.nns = nn.ModuleList(nns)
         self.convs = nn.ModuleList(convs)
         self.linears = nn.ModuleList(linears)

@@ -45,10 +45,10 @@ class RGCNConv(nn.Module):
             structure = GraphStructure(edge_index, x.size(0))
         R, I, O = self.num_relations, self.in_channels, self.out_channels
         fwd, bwd = structure.relation_csr(edge_type, R)
-        table = torch.matmul(x, self.weight.permute(1, 0, 2).reshape(I, R * O)).view(-1, O)
+        table = ops.matmul_xw(x, self.weight.permute(1, 0, 2).reshape(I, R * O)).view(-1, O)
         out = ops.spmm_sum(table, fwd, bwd)
         if self.root is not None:
-            out = out + torch.matmul(x, self.root)
+            out = out + ops.matmul_xw(x, self.root)
         if self.bias is not None:
             out = out + self.bias
         return out
@@ -76,7 +76,7 @@ class RGIN(torch.nn.Module):
             else:
                 nns.append(_gin_mlp(self.embeddings_dim[layer - 1], out_dim))
                 convs.append(RGCNConv(self.nhid, self.nhid, self.num_relations, aggr="add"))
-            linears.append(nn.Linear(out_dim, self.num_classes))
+            linears.append(ops.Linear(out_dim, self.num_classes))
         if ("weight_reg" in config) and (config["weight_reg"] > 1.1):
             with torch.no_grad():
                 for conv in convs:

@@ -207,3 +207,78 @@ def gather_rows(x, idx_i32):
     out = torch.empty((n, D), dtype=torch.float32, device=x.device)
     lib().call("dn4gl_gather_rows_f32", ptr(idx_i32), ptr(x), ptr(out), n, D, _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# dense helpers: forward / input-gradient GEMMs are plain library GEMMs (cuBLAS through torch); the WEIGHT gradient
+# is a reduction over all N rows with a tiny output and runs in libdn4gl (dn4gl_atb_f32).
+def atb_supported(ka, kb):
+    return ((ka + 3) // 4) * ((kb + 3) // 4) <= 256
+
+
+def atb(A, B, want_colsum=False):
+    """(A^T B, colsum(A) or None) for row-major A (N, Ka), B (N, Kb)."""
+    require_cuda(A, "activations")
+    A, B = _f32c(A), _f32c(B)
+    N, Ka = A.shape
+    Kb = B.size(1)
+    if not atb_supported(Ka, Kb):   # wide outputs (e.g. the (D, R*D) relation table) are regular GEMMs: library
+        return A.t() @ B, (A.sum(0) if want_colsum else None)
+    C = torch.empty((Ka, Kb), dtype=torch.float32, device=A.device)
+    cs = torch.empty(Ka, dtype=torch.float32, device=A.device) if want_colsum else None
+    L = lib()
+    wsb = L.size("dn4gl_atb_workspace_bytes", N, Ka, Kb)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=A.device)
+    L.call("dn4gl_atb_f32", ptr(A), ptr(B), ptr(C), ptr(cs), N, Ka, Kb, ptr(ws), wsb, _stream())
+    return C, cs
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.addmm(bias, x, weight.t()) if bias is not None else x @ weight.t()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = g @ weight
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = atb(g, x, want_colsum=ctx.has_bias)
+        return gx, gw, gb
+
+
+def linear(x, weight, bias=None):
+    """F.linear with the weight/bias gradient computed by the row-reduction kernel."""
+    lead = x.shape[:-1]
+    y = _Linear.apply(x.reshape(-1, x.size(-1)), weight, bias)
+    return y.view(lead + (weight.size(0),))
+
+
+class _MatmulXW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return x @ w
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gx = g @ w.t() if ctx.needs_input_grad[0] else None
+        gw = atb(x, g)[0] if ctx.needs_input_grad[1] else None
+        return gx, gw
+
+
+def matmul_xw(x, w):
+    """x (N, K) @ w (K, M) for a parameter (or parameter expression) w; dW = x^T g by the row-reduction kernel."""
+    return _MatmulXW.apply(x, w)
+
+
+class Linear(torch.nn.Linear):
+    """nn.Linear (same parameters / state_dict keys) whose backward uses dn4gl_atb_f32 for dW, db."""
+
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)

@@ -24,7 +24,7 @@ from .basemodel import GraphAdjModelV2
 def _mlp(hidden_dim, num_layers, batch_norm, act_func):
     mods = []
     for i in range(num_layers):
-        mods.append(nn.Linear(hidden_dim, hidden_dim))
+        mods.append(ops.Linear(hidden_dim, hidden_dim))
         if i != num_layers - 1:
             if batch_norm:
                 mods.append(nn.BatchNorm1d(hidden_dim))
@@ -68,15 +68,15 @@ class DMPLayer(nn.Module):
     def forward(self, graph, node_feat, edge_feat):
         # ---- node stream: update_all(message :111-127, fn.sum :92, update :129-140)
         S = ops.dmp_node_agg(edge_feat, graph)
-        agg = th.matmul(S, th.cat([self.out_weight, -self.in_weight], dim=0))
-        n_out = th.matmul(node_feat, self.nloop_weight) + agg
+        agg = ops.matmul_xw(S, th.cat([self.out_weight, -self.in_weight], dim=0))
+        n_out = ops.matmul_xw(node_feat, self.nloop_weight) + agg
         if self.nbias is not None:
             n_out = n_out + self.nbias
         n_out = self.nmlp(n_out) if len(self.nmlp) > 0 else self.act(n_out)
         n_out = self.drop(n_out)
         # ---- edge stream: EDGEAGG side effect (:126) + apply_edges(:142-156)
-        PQ = th.matmul(node_feat, th.cat([self.dst_weight, self.src_weight], dim=1))
-        T = th.matmul(edge_feat, th.cat([self.eloop_weight, self.src_weight - self.dst_weight], dim=1))
+        PQ = ops.matmul_xw(node_feat, th.cat([self.dst_weight, self.src_weight], dim=1))
+        T = ops.matmul_xw(edge_feat, th.cat([self.eloop_weight, self.src_weight - self.dst_weight], dim=1))
         e_out = ops.dmp_edge_update(PQ, T, self.ebias, graph)
         e_out = self.emlp(e_out) if len(self.emlp) > 0 else self.act(e_out)
         e_out = self.drop(e_out)

@@ -10,6 +10,7 @@ library GEMMs.
 import torch as th
 import torch.nn as nn
 
+from ... import ops
 from ..utils import init_module, map_activation_str_to_layer
 
 
@@ -19,8 +20,8 @@ class PredictNet(nn.Module):
         self.input_dim, self.hidden_dim = input_dim, hidden_dim
         self.act = map_activation_str_to_layer(act_func)
         self.drop = nn.Dropout(dropout)
-        self.p_fc = nn.Linear(input_dim, hidden_dim)
-        self.g_fc = nn.Linear(input_dim, hidden_dim)
+        self.p_fc = ops.Linear(input_dim, hidden_dim)
+        self.g_fc = ops.Linear(input_dim, hidden_dim)
         self.pred_fc1 = nn.Linear(hidden_dim * 4 + 4, hidden_dim)
         self.pred_fc2 = nn.Linear(hidden_dim + 4, 1)
         if return_weights:

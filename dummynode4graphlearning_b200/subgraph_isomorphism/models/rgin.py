@@ -57,7 +57,7 @@ class RGINLayer(nn.Module):
             self.register_parameter("bias", None)
         mlp = []
         for i in range(num_mlp_layers):
-            mlp.append(nn.Linear(hidden_dim, hidden_dim))
+            mlp.append(ops.Linear(hidden_dim, hidden_dim))
             if i != num_mlp_layers - 1:
                 if batch_norm:
                     mlp.append(nn.BatchNorm1d(hidden_dim))
@@ -108,10 +108,10 @@ class RGINLayer(nn.Module):
 
     def forward(self, g, node_feat, edge_type):
         fwd, bwd = relation_csr(g, edge_type, self.num_rels)
-        table = th.matmul(node_feat, self.relation_weights()).view(-1, self.hidden_dim)   # (N*R, H)
+        table = ops.matmul_xw(node_feat, self.relation_weights()).view(-1, self.hidden_dim)   # (N*R, H)
         out = ops.spmm_sum(table, fwd, bwd)                                                 # fn.sum, rgin.py:98
         if self.self_loop:
-            out = out + th.matmul(node_feat, self.loop_weight)
+            out = out + ops.matmul_xw(node_feat, self.loop_weight)
         if self.bias is not None:
             out = out + self.bias
         out = self.mlp(out) if len(self.mlp) > 0 else self.act(out)

@@ -211,6 +211,16 @@ int dn4gl_dmp_edge_update_bwd_PQ_f32(const int32_t *in_ptr, const int32_t *in_ei
                                      const uint8_t *is_rev, const float *g, float *gPQ,
                                      int64_t N, int32_t D, void *stream);
 
+/* ---- dense helpers of the MLPs ----------------------------------------------------------------- */
+/* C (Ka x Kb) = A^T B, colsum_A (Ka, may be NULL) = column sums of A; A (N x Ka), B (N x Kb) row-major.
+ * The weight gradient of every nn.Linear on the path (dW = G^T X, db = colsum G: gconv.py:190-196 MLPs,
+ * rgin.py:52 / dmpnn.py:47,55 MLPs) and of the raw-parameter matmuls (dW = X^T G: rgin.py:141, dmpnn.py:112-146),
+ * written as a deterministic row reduction instead of a large-K library GEMM.
+ * Limit: ceil(Ka/4) * ceil(Kb/4) <= 256 (e.g. 64 x 64); DN4GL_EINVAL otherwise (callers keep the library GEMM). */
+size_t dn4gl_atb_workspace_bytes(int64_t N, int32_t Ka, int32_t Kb);
+int dn4gl_atb_f32(const float *A, const float *B, float *C, float *colsum_A, int64_t N, int32_t Ka, int32_t Kb,
+                  void *ws, size_t ws_bytes, void *stream);
+
 /* ---- small fused elementwise helpers of the layers ------------------------------------------ */
 /* gather rows: out[i,:] = x[idx[i],:] (idx int32, n rows)                                       */
 int dn4gl_gather_rows_f32(const int32_t *idx, const float *x, float *out, int64_t n, int32_t D, void *stream);

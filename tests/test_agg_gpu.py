@@ -131,3 +131,38 @@ def test_pad_segments_matches_reference_batchify(device, D):
     gx, = torch.autograd.grad((out * w).sum(), x)
     gr, = torch.autograd.grad((ref * w).sum(), xr)
     assert torch.equal(gx, gr)
+
+
+@pytest.mark.parametrize("n,ka,kb", [(1, 32, 32), (1000, 32, 32), (156759, 32, 32), (50000, 64, 64), (4097, 2, 32),
+                                     (30000, 32, 2), (12345, 90, 64), (20000, 64, 128), (777, 7, 5)])
+def test_atb_row_reduction(device, n, ka, kb):
+    """dW = A^T B (+ colsum A) by the deterministic row reduction vs float64 torch."""
+    from dummynode4graphlearning_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(n + ka)
+    A = torch.rand((n, ka), device=device, generator=g) * 2 - 1
+    Bm = torch.rand((n, kb), device=device, generator=g) * 2 - 1
+    C, cs = ops.atb(A, Bm, want_colsum=True)
+    ref = A.double().t() @ Bm.double()
+    scale = float(ref.abs().max()) + 1e-12
+    assert float((C.double() - ref).abs().max()) / scale < 2e-6
+    assert float((cs.double() - A.double().sum(0)).abs().max()) / (float(A.double().sum(0).abs().max()) + 1e-12) < 2e-6
+    C2, _ = ops.atb(A, Bm, want_colsum=False)
+    assert torch.equal(C, C2)   # deterministic
+
+
+def test_linear_function_matches_torch(device):
+    from dummynode4graphlearning_b200 import ops
+
+    torch.manual_seed(0)
+    lin = ops.Linear(32, 48).to(device)
+    ref = torch.nn.Linear(32, 48).to(device)
+    ref.load_state_dict(lin.state_dict())
+    x = torch.randn(5000, 32, device=device, requires_grad=True)
+    xr = x.detach().clone().requires_grad_(True)
+    w = torch.randn(5000, 48, device=device)
+    (lin(x) * w).sum().backward()
+    (ref(xr) * w).sum().backward()
+    torch.testing.assert_close(x.grad, xr.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(lin.weight.grad, ref.weight.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(lin.bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-3)
