@@ -188,8 +188,8 @@ class EntryPointTimer:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         key = name
-        if name == "dn4gl_spmm_sum_f32":
-            key = "%s[D=%d]" % (name, args[6])
+        if name in ("dn4gl_spmm_sum_f32", "dn4gl_spmm_tiled_f32"):
+            key = "%s[D=%d]" % (name, args[6] if name == "dn4gl_spmm_sum_f32" else args[5])
         self.pending.append((key, self.stack.pop(), e1))
 
     def summary(self):
@@ -299,9 +299,12 @@ def ours(a):
         iso.append(a0.elapsed_time(a1))
     peaks, which = measured_peaks()
     agg_bytes = 4 * HID * N * 2 + 4 * E + 4 * (N + 1)        # compulsory traffic
-    in_step = per_entry.get("dn4gl_spmm_sum_f32[D=%d]" % HID, {"avg_us": float("nan"), "calls": 0})
+    agg_name = "dn4gl_spmm_tiled_f32" if ("dn4gl_spmm_tiled_f32[D=%d]" % HID) in per_entry else "dn4gl_spmm_sum_f32"
+    in_step = per_entry.get("%s[D=%d]" % (agg_name, HID), {"avg_us": float("nan"), "calls": 0})
     achieved = agg_bytes / (in_step["avg_us"] * 1e-6) / 1e9
-    roofline = {"kernel": "dn4gl_spmm_sum_f32 (spmm_rows_kernel<8,1> + spmm_heavy_kernel<8,1>), D=32, N=%d, E=%d" % (N, E),
+    kern = ("spmm_tiled_kernel<8,1> (cp.async.bulk staged tiles)" if agg_name.endswith("tiled_f32")
+            else "spmm_rows_kernel<8,1> + spmm_heavy_kernel<8,1>")
+    roofline = {"kernel": "%s (%s), D=32, N=%d, E=%d" % (agg_name, kern, N, E),
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_launch": agg_bytes, "avg_launch_us_in_step": in_step["avg_us"],

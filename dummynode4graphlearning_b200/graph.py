@@ -43,12 +43,29 @@ def require_cuda(t, what="tensor"):
 class CSR:
     """row_ptr[n_rows+1], col[nnz], eid[nnz] (all int32, device) + the heavy-row list."""
 
-    __slots__ = ("row_ptr", "col", "eid", "n_rows", "nnz", "heavy_rows", "heavy_count", "heavy_thr")
+    __slots__ = ("row_ptr", "col", "eid", "n_rows", "nnz", "heavy_rows", "heavy_count", "heavy_thr", "seg_ptr",
+                 "_tiles")
 
     def __init__(self, row_ptr, col, eid, n_rows, nnz):
         self.row_ptr, self.col, self.eid, self.n_rows, self.nnz = row_ptr, col, eid, n_rows, nnz
         self.heavy_rows = self.heavy_count = None
         self.heavy_thr = 0
+        self.seg_ptr = None   # per-graph row offsets when rows AND columns are block-diagonal over the same graphs
+        self._tiles = {}
+
+    def tiles(self, D, smem_bytes):
+        """graph-aligned row tiles for the shared-memory staged aggregation kernel (cached per feature width)."""
+        key = (D, smem_bytes)
+        if key not in self._tiles:
+            L = lib()
+            cap = L.size("dn4gl_spmm_tiled_cap_rows", D, smem_bytes)
+            window = max(cap // 2, 1)
+            T = (self.n_rows + window - 1) // window
+            tile_ptr = torch.empty(T + 1, dtype=torch.int32, device=self.row_ptr.device)
+            L.call("dn4gl_make_row_tiles", ptr(self.seg_ptr), int(self.seg_ptr.numel()) - 1, window, ptr(tile_ptr), T,
+                   _stream())
+            self._tiles[key] = (tile_ptr, T)
+        return self._tiles[key]
 
 
 def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD):
@@ -192,6 +209,7 @@ class BatchedGraph:
         """in-edges of every node: row v lists (src, eid) of edges with dst = v, ascending eid."""
         if self._csr_in is None:
             self._csr_in = build_csr(self.dst, self.src, self.number_of_nodes())
+            self._csr_in.seg_ptr = self.node_ptr
         return self._csr_in
 
     @property
@@ -199,6 +217,7 @@ class BatchedGraph:
         """out-edges of every node (transpose): row u lists (dst, eid) of edges with src = u."""
         if self._csr_out is None:
             self._csr_out = build_csr(self.src, self.dst, self.number_of_nodes())
+            self._csr_out.seg_ptr = self.node_ptr
         return self._csr_out
 
     def in_degrees(self):

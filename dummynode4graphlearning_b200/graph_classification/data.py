@@ -24,6 +24,7 @@ class GraphStructure:
             node_ptr = torch.zeros(nb + 1, dtype=torch.int32, device=batch.device)
             node_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
         self.node_ptr = None if node_ptr is None else node_ptr.to(torch.int32).contiguous()
+        self.csr_in.seg_ptr = self.csr_out.seg_ptr = self.node_ptr
         self._rel = {}
 
     def relation_csr(self, edge_type, num_rels):

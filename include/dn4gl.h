@@ -153,6 +153,20 @@ int dn4gl_spmm_sum_f32(const int32_t *row_ptr, const int32_t *col, const float *
                        const int32_t *heavy_rows, const int32_t *heavy_count, int32_t heavy_threshold,
                        void *stream);
 
+/* K1, tiled variant for block-diagonal batches (n_src == N): rows are cut into tiles of whole consecutive graphs
+ * (tile_ptr[num_tiles+1] from dn4gl_make_row_tiles over the per-graph node offsets seg_ptr[B+1]); a CTA stages its
+ * tile's feature rows into shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier) and resolves the
+ * neighbour indices there.  Same result contract as dn4gl_spmm_sum_f32; indices outside a tile or tiles above the
+ * shared-memory budget fall back to global loads inside the kernel (correct for any CSR).
+ * smem_bytes: dynamic shared memory per CTA, 16 KiB .. 190 KiB; dn4gl_spmm_tiled_cap_rows gives the rows of width D
+ * a tile can hold for that budget (pick window_rows <= cap_rows - largest graph).                               */
+int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t window_rows, int32_t *tile_ptr,
+                         int32_t num_tiles, void *stream);
+int32_t dn4gl_spmm_tiled_cap_rows(int32_t D, int32_t smem_bytes);
+int dn4gl_spmm_tiled_f32(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, int64_t N,
+                         int32_t D, float self_scale, const int32_t *tile_ptr, int32_t num_tiles,
+                         int32_t smem_bytes, void *stream);
+
 /* ---- K3: segment readout ------------------------------------------------------------------- */
 /* out[b,:] = scale_b * sum_{v in [seg_ptr[b], seg_ptr[b+1]), mask[v]==0} x[v,:]
  * mode 0: sum (global_add_pool, gconv.py:176; SumPredictNet.agg_graph pred.py:215),
