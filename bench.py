@@ -302,7 +302,7 @@ def ours(a):
     agg_name = "dn4gl_spmm_tiled_f32" if ("dn4gl_spmm_tiled_f32[D=%d]" % HID) in per_entry else "dn4gl_spmm_sum_f32"
     in_step = per_entry.get("%s[D=%d]" % (agg_name, HID), {"avg_us": float("nan"), "calls": 0})
     achieved = agg_bytes / (in_step["avg_us"] * 1e-6) / 1e9
-    kern = ("spmm_tiled_kernel<8,1> (cp.async.bulk staged tiles)" if agg_name.endswith("tiled_f32")
+    kern = ("spmm_pipe_kernel<8,1>: producer/consumer ring of cp.async.bulk staged tiles" if agg_name.endswith("tiled_f32")
             else "spmm_rows_kernel<8,1> + spmm_heavy_kernel<8,1>")
     roofline = {"kernel": "%s (%s), D=32, N=%d, E=%d" % (agg_name, kern, N, E),
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -112,29 +112,40 @@ atb_partial_kernel(const float *__restrict__ A, const float *__restrict__ B, int
     }
 }
 
-// C[i] = sum_p partial[p][i] in ascending p (fixed order); the colsum tail goes to `colsum` if requested
-__global__ void atb_reduce_kernel(const float *__restrict__ partial, int P, int KaKb, int Ka, float *__restrict__ C,
-                                  float *__restrict__ colsum) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = KaKb + Ka;
-    if (i >= total) return;
+// C[i] = sum_p partial[p][i]: a CTA owns 32 outputs; its 8 warps stride the partials (coalesced 128-byte rows), each
+// with 4 independent chains, and the 8 x 4 partial sums are combined in a fixed order (deterministic, no atomics)
+__global__ void __launch_bounds__(256)
+atb_reduce_kernel(const float *__restrict__ partial, int P, int KaKb, int Ka, float *__restrict__ C,
+                  float *__restrict__ colsum) {
+    __shared__ float red[8][33];
+    const int o = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + o;
+    const int total = KaKb + Ka;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int p = 0;
-    for (; p + 4 <= P; p += 4) {
-        s0 += partial[static_cast<int64_t>(p) * total + i];
-        s1 += partial[static_cast<int64_t>(p + 1) * total + i];
-        s2 += partial[static_cast<int64_t>(p + 2) * total + i];
-        s3 += partial[static_cast<int64_t>(p + 3) * total + i];
+    if (i < total) {
+        int p = w;
+        for (; p + 24 < P; p += 32) {
+            s0 += partial[static_cast<int64_t>(p) * total + i];
+            s1 += partial[static_cast<int64_t>(p + 8) * total + i];
+            s2 += partial[static_cast<int64_t>(p + 16) * total + i];
+            s3 += partial[static_cast<int64_t>(p + 24) * total + i];
+        }
+        for (; p < P; p += 8) s0 += partial[static_cast<int64_t>(p) * total + i];
     }
-    for (; p < P; ++p) s0 += partial[static_cast<int64_t>(p) * total + i];
-    float s = (s0 + s1) + (s2 + s3);
-    if (i < KaKb) C[i] = s;
-    else if (colsum) colsum[i - KaKb] = s;
+    red[w][o] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (w == 0 && i < total) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][o];
+        if (i < KaKb) C[i] = s;
+        else if (colsum) colsum[i - KaKb] = s;
+    }
 }
 
 static int atb_grid(int64_t N) {
     int64_t want = ceil_div64(N, 4 * ATB_ROWS);  // at least 128 rows per CTA
-    int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 4;
+    int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 2;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     return static_cast<int>(want);
@@ -169,7 +180,7 @@ extern "C" int dn4gl_atb_f32(const float *A, const float *B, float *C, float *co
     if (red > smem) smem = red;
     atb_partial_kernel<<<grid, ATB_THREADS, smem, st>>>(A, B, N, Ka, Kb, GA, GB, rows_per_cta, partial);
     const int total = Ka * Kb + Ka;
-    atb_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partial, grid, Ka * Kb, Ka, C, colsum_A);
+    atb_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(partial, grid, Ka * Kb, Ka, C, colsum_A);
     DN_LAUNCHED_N(2);
     return DN4GL_OK;
 }

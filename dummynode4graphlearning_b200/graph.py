@@ -12,11 +12,14 @@ Layout in HBM: ``src``/``dst`` int32[E] in edge-id order, 
 ``edge_ptr`` int32[B+1], CSR ``row_ptr`` int32[N+1], ``col`` int32[E], ``eid`` int32[E]; features
 fp32 row-major.
 """
+import os
+
 import torch
 
 from ._lib import lib, ptr
 
 HEAVY_THRESHOLD = 64  # rows with more in-edges than this are reduced by a whole CTA (dummy nodes)
+TILE_SMEM = int(os.environ.get("DN4GL_TILE_SMEM", str(200 * 1024)))   # shared-memory ring of the pipelined aggregation kernel
 
 _dev_bound = {}
 
@@ -44,28 +47,59 @@ class CSR:
     """row_ptr[n_rows+1], col[nnz], eid[nnz] (all int32, device) + the heavy-row list."""
 
     __slots__ = ("row_ptr", "col", "eid", "n_rows", "nnz", "heavy_rows", "heavy_count", "heavy_thr", "seg_ptr",
-                 "_tiles")
+                 "max_seg", "_tiles")
 
     def __init__(self, row_ptr, col, eid, n_rows, nnz):
         self.row_ptr, self.col, self.eid, self.n_rows, self.nnz = row_ptr, col, eid, n_rows, nnz
         self.heavy_rows = self.heavy_count = None
         self.heavy_thr = 0
         self.seg_ptr = None   # per-graph row offsets when rows AND columns are block-diagonal over the same graphs
+        self.max_seg = None   # rows of the largest graph if the host knows it (lets every tile be graph-aligned)
         self._tiles = {}
 
-    def tiles(self, D, smem_bytes):
-        """graph-aligned row tiles for the shared-memory staged aggregation kernel (cached per feature width)."""
+    def tiles(self, D, smem_bytes=None):
+        """tiling + launch configuration of the pipelined aggregation kernel for feature width D (cached).
+
+        One persistent CTA per SM owns `smem_bytes` of shared memory as a ring of `stages` buffers.  The window is
+        chosen so that a tile (window + the graph straddling its end) always fits one stage: cap - max_seg when the
+        host knows the largest graph, else cap / 2.  Graphs longer than the window are cut; rows with more than 64
+        neighbours inside cut tiles go on the heavy list (reduced CTA-wide inside the same launch)."""
+        smem_bytes = TILE_SMEM if smem_bytes is None else int(smem_bytes)
         key = (D, smem_bytes)
-        if key not in self._tiles:
-            L = lib()
-            cap = L.size("dn4gl_spmm_tiled_cap_rows", D, smem_bytes)
-            window = max(cap // 2, 1)
-            T = (self.n_rows + window - 1) // window
-            tile_ptr = torch.empty(T + 1, dtype=torch.int32, device=self.row_ptr.device)
-            L.call("dn4gl_make_row_tiles", ptr(self.seg_ptr), int(self.seg_ptr.numel()) - 1, window, ptr(tile_ptr), T,
-                   _stream())
-            self._tiles[key] = (tile_ptr, T)
-        return self._tiles[key]
+        if key in self._tiles:
+            return self._tiles[key]
+        L = lib()
+        npr = min(max(-(-self.nnz // max(self.n_rows, 1)) + 1, 2), 32)
+        stages = cap = None
+        for s in (4, 3, 2):
+            c = L.size("dn4gl_spmm_tiled_cap_rows", D, smem_bytes, s, npr)
+            if self.max_seg is None:
+                if s == 3:
+                    stages, cap = s, c
+                    break
+            elif 2 * self.max_seg <= c:
+                stages, cap = s, c
+                break
+        if stages is None:
+            stages, cap = 2, L.size("dn4gl_spmm_tiled_cap_rows", D, smem_bytes, 2, npr)
+        aligned = self.max_seg is not None and 2 * self.max_seg <= cap
+        window = max(cap - self.max_seg if aligned else cap // 2, 1)
+        T = (self.n_rows + window - 1) // window
+        dev = self.row_ptr.device
+        desc = torch.empty(4 * max(T, 1), dtype=torch.int32, device=dev)
+        heavy_list = heavy_count = None
+        heavy_cap = 0
+        scratch = 15 * (32 // min(D // 4, 32)) * D * 4       # CTA-wide reduction scratch must fit one stage
+        if not aligned and scratch <= ((smem_bytes // stages) & ~127):
+            heavy_cap = self.nnz // 64 + 1
+            heavy_list = torch.empty(heavy_cap, dtype=torch.int32, device=dev)
+            heavy_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call("dn4gl_make_row_tiles", ptr(self.seg_ptr), int(self.seg_ptr.numel()) - 1, window, ptr(self.row_ptr),
+               self.n_rows, ptr(desc), T, ptr(heavy_list), heavy_cap, ptr(heavy_count), _stream())
+        cfg = dict(desc=desc, T=T, heavy_list=heavy_list, heavy_count=heavy_count, heavy_cap=heavy_cap,
+                   smem=smem_bytes, stages=stages, npr=npr, window=window, cap_rows=cap)
+        self._tiles[key] = cfg
+        return cfg
 
 
 def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD):
@@ -209,7 +243,7 @@ class BatchedGraph:
         """in-edges of every node: row v lists (src, eid) of edges with dst = v, ascending eid."""
         if self._csr_in is None:
             self._csr_in = build_csr(self.dst, self.src, self.number_of_nodes())
-            self._csr_in.seg_ptr = self.node_ptr
+            self._csr_in.seg_ptr, self._csr_in.max_seg = self.node_ptr, self._max_seg()
         return self._csr_in
 
     @property
@@ -217,8 +251,12 @@ class BatchedGraph:
         """out-edges of every node (transpose): row u lists (dst, eid) of edges with src = u."""
         if self._csr_out is None:
             self._csr_out = build_csr(self.src, self.dst, self.number_of_nodes())
-            self._csr_out.seg_ptr = self.node_ptr
+            self._csr_out.seg_ptr, self._csr_out.max_seg = self.node_ptr, self._max_seg()
         return self._csr_out
+
+    def _max_seg(self):
+        """rows of the largest graph when the host already holds the sizes (no device sync otherwise)."""
+        return self.max_num_nodes() if self._host_sizes is not None else None
 
     def in_degrees(self):
         if "in_deg" not in self.ndata:

@@ -12,7 +12,7 @@ from ..graph import build_csr
 class GraphStructure:
     """CSR by destination / by source + per-graph node offsets of a PyG-style batch."""
 
-    def __init__(self, edge_index, num_nodes, batch=None, node_ptr=None):
+    def __init__(self, edge_index, num_nodes, batch=None, node_ptr=None, max_seg=None):
         src = edge_index[0].to(torch.int32).contiguous()
         dst = edge_index[1].to(torch.int32).contiguous()
         self.src, self.dst, self.num_nodes = src, dst, int(num_nodes)
@@ -25,6 +25,7 @@ class GraphStructure:
             node_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
         self.node_ptr = None if node_ptr is None else node_ptr.to(torch.int32).contiguous()
         self.csr_in.seg_ptr = self.csr_out.seg_ptr = self.node_ptr
+        self.csr_in.max_seg = self.csr_out.max_seg = max_seg   # rows of the largest graph, if the host knows it
         self._rel = {}
 
     def relation_csr(self, edge_type, num_rels):
@@ -44,10 +45,10 @@ class GraphStructure:
 
 class Batch:
     def __init__(self, x, edge_index, batch, edge_attr=None, y=None, is_dummy_node=None, is_dummy_edge=None,
-                 node_ptr=None):
+                 node_ptr=None, max_graph_nodes=None):
         self.x, self.edge_index, self.batch, self.edge_attr, self.y = x, edge_index, batch, edge_attr, y
         self.is_dummy_node, self.is_dummy_edge = is_dummy_node, is_dummy_edge
-        self._node_ptr = node_ptr
+        self._node_ptr, self._max_seg = node_ptr, max_graph_nodes
         self._structure = None
 
     @property
@@ -57,21 +58,23 @@ class Batch:
     @property
     def structure(self):
         if self._structure is None:
-            self._structure = GraphStructure(self.edge_index, self.x.size(0), self.batch, self._node_ptr)
+            self._structure = GraphStructure(self.edge_index, self.x.size(0), self.batch, self._node_ptr, self._max_seg)
         return self._structure
 
     @staticmethod
     def from_canonical(d):
         """from ``transforms.pyg_canonicalize`` output."""
         return Batch(d["x"], d["edge_index"], d["batch"], d.get("edge_attr"), d.get("y"),
-                     d.get("is_dummy_node"), d.get("is_dummy_edge"), node_ptr=d["node_ptr"])
+                     d.get("is_dummy_node"), d.get("is_dummy_edge"), node_ptr=d["node_ptr"],
+                     max_graph_nodes=d.get("max_graph_nodes"))
 
 
 def structure_of(data):
     """GraphStructure of any object with ``x, edge_index, batch`` (cached on the object)."""
     s = getattr(data, "_structure", None)
     if s is None:
-        s = GraphStructure(data.edge_index, data.x.size(0), data.batch, getattr(data, "_node_ptr", None))
+        s = GraphStructure(data.edge_index, data.x.size(0), data.batch, getattr(data, "_node_ptr", None),
+                           getattr(data, "_max_seg", None))
         try:
             data._structure = s
         except AttributeError:

@@ -18,8 +18,8 @@ def _f32c(t):
     return t.contiguous()
 
 
-SPMM_MODE = os.environ.get("DN4GL_SPMM", "tiled")          # "tiled" (shared-memory staged) | "rows" (per-row gathers)
-TILE_SMEM = int(os.environ.get("DN4GL_TILE_SMEM", str(96 * 1024)))
+SPMM_MODE = os.environ.get("DN4GL_SPMM", "tiled")          # "tiled" (pipelined shared-memory staging) | "rows" (per-row gathers)
+TILE_SMEM = None                                           # override of graph.TILE_SMEM (tests / sweeps)
 _TILED_D = (16, 32, 64, 128, 256, 512)
 
 
@@ -29,9 +29,10 @@ def _spmm(csr: CSR, x, n_out, self_scale):
     D = x.size(1)
     out = torch.empty((n_out, D), dtype=torch.float32, device=x.device)
     if SPMM_MODE == "tiled" and csr.seg_ptr is not None and x.size(0) == n_out and D in _TILED_D:
-        tile_ptr, T = csr.tiles(D, TILE_SMEM)
+        t = csr.tiles(D, TILE_SMEM)
         lib().call("dn4gl_spmm_tiled_f32", ptr(csr.row_ptr), ptr(csr.col), ptr(x), ptr(out), n_out, D,
-                   float(self_scale), ptr(tile_ptr), T, TILE_SMEM, _stream())
+                   float(self_scale), ptr(t["desc"]), t["T"], ptr(t["heavy_list"]), ptr(t["heavy_count"]),
+                   t["heavy_cap"], t["smem"], t["stages"], t["npr"], _stream())
         return out
     lib().call("dn4gl_spmm_sum_f32", ptr(csr.row_ptr), ptr(csr.col), ptr(x), ptr(out), n_out, x.size(0), D,
                float(self_scale), ptr(csr.heavy_rows), ptr(csr.heavy_count), csr.heavy_thr, _stream())

@@ -30,7 +30,7 @@ def to_device(b, device):
     dev = torch.device(device)
     out = {}
     for k, v in b.items():
-        if k in ("num_graphs", "has_edge_labels"):
+        if k in ("num_graphs", "has_edge_labels", "max_graph_nodes"):
             out[k] = v
         elif k.endswith("attr"):
             out[k] = torch.as_tensor(v).to(dev, torch.float32).contiguous()
@@ -73,6 +73,8 @@ def tu_add_dummy(b):
         o["vattr"] = va
     if "y" in b:
         o["y"] = b["y"]
+    if b.get("max_graph_nodes") is not None:
+        o["max_graph_nodes"] = int(b["max_graph_nodes"]) + 1
     return o
 
 
@@ -91,9 +93,10 @@ def tu_conjugate(b):
     L.call("dn4gl_tu_conjugate_count", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
            ptr(isd), N, E, ptr(csr_in.row_ptr), ptr(csr_in.eid), ptr(cand_off), ptr(newid),
            ptr(o_node_ptr), ptr(o_edge_ptr), ptr(ws), ws_bytes, _stream())
-    sizes = torch.stack([o_node_ptr[-1], o_edge_ptr[-1]]).cpu()  # the one D2H sync: output sizes
+    max_nodes = (o_node_ptr[1:] - o_node_ptr[:-1]).max() if B > 0 else o_node_ptr[-1]
+    sizes = torch.stack([o_node_ptr[-1], o_edge_ptr[-1], max_nodes]).cpu()  # the one D2H sync: output sizes
     V2, E2 = int(sizes[0]), int(sizes[1])
-    o = dict(num_graphs=B, node_ptr=o_node_ptr, edge_ptr=o_edge_ptr,
+    o = dict(num_graphs=B, max_graph_nodes=int(sizes[2]), node_ptr=o_node_ptr, edge_ptr=o_edge_ptr,
              src=_empty_i32(E2, dev), dst=_empty_i32(E2, dev),
              v_origin=_empty_i32(V2, dev), e_shared=_empty_i32(E2, dev))
     L.call("dn4gl_tu_conjugate_fill", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
@@ -191,6 +194,8 @@ def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_m
         out["edge_attr"] = edge_attr
         out["is_dummy_edge"] = edge_attr[:, 0].bool()  # set_dummy_flags: column num_edge_attributes (=0)
     out["is_dummy_node"] = x[:, n_attr].bool()
+    if b.get("max_graph_nodes") is not None:
+        out["max_graph_nodes"] = int(b["max_graph_nodes"])
     if "y" in b:
         out["y"] = b["y"]
     return out

@@ -153,19 +153,30 @@ int dn4gl_spmm_sum_f32(const int32_t *row_ptr, const int32_t *col, const float *
                        const int32_t *heavy_rows, const int32_t *heavy_count, int32_t heavy_threshold,
                        void *stream);
 
-/* K1, tiled variant for block-diagonal batches (n_src == N): rows are cut into tiles of whole consecutive graphs
- * (tile_ptr[num_tiles+1] from dn4gl_make_row_tiles over the per-graph node offsets seg_ptr[B+1]); a CTA stages its
- * tile's feature rows into shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier) and resolves the
- * neighbour indices there.  Same result contract as dn4gl_spmm_sum_f32; indices outside a tile or tiles above the
- * shared-memory budget fall back to global loads inside the kernel (correct for any CSR).
- * smem_bytes: dynamic shared memory per CTA, 16 KiB .. 190 KiB; dn4gl_spmm_tiled_cap_rows gives the rows of width D
- * a tile can hold for that budget (pick window_rows <= cap_rows - largest graph).                               */
-int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t window_rows, int32_t *tile_ptr,
-                         int32_t num_tiles, void *stream);
-int32_t dn4gl_spmm_tiled_cap_rows(int32_t D, int32_t smem_bytes);
+/* K1, tiled variant for block-diagonal batches (n_src == N): a warp-specialised producer/consumer pipeline.  Rows are
+ * cut into tiles of whole consecutive graphs (dn4gl_make_row_tiles over the per-graph row offsets seg_ptr[B+1]); a
+ * producer lane streams every tile's feature rows, row_ptr slice and col slice into a ring of `stages` shared-memory
+ * buffers with bulk asynchronous copies (cp.async.bulk + mbarrier), consumer warps resolve the neighbour indices
+ * there and stream the output rows.  Same result contract as dn4gl_spmm_sum_f32 and correct for ANY CSR (indices
+ * outside a staged window fall back to global loads); the tiling is a performance contract only.
+ *
+ * dn4gl_make_row_tiles: tile_desc[4*num_tiles] int32 = {r0, r1, e0, e1 | cut<<31} per tile, num_tiles >=
+ *   ceil(N / window_rows); window_rows <= cap_rows - (largest graph) keeps every tile inside one stage (cap_rows / 2
+ *   is always safe).  heavy_list[heavy_cap] / heavy_count[1] (optional, both or neither): rows with more than 64
+ *   neighbours inside tiles that had to cut a graph longer than the window; the kernel reduces them CTA-wide.
+ *   heavy_cap >= E / 64 + 1.
+ * dn4gl_spmm_tiled_f32: smem_bytes = dynamic shared memory per CTA (16 KiB .. 220 KiB; <= 110 KiB lets two CTAs share
+ *   an SM for D <= 128), stages in 1..4, nnz_per_row = col slots staged per row (about ceil(E/N) + 1).
+ * row_ptr and col must be 16-byte aligned and their allocations padded to a multiple of 16 bytes (bulk copies move
+ * whole 16-byte words; true for any cudaMalloc / torch allocation).                                                 */
+int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t window_rows, const int32_t *row_ptr, int64_t N,
+                         int32_t *tile_desc, int32_t num_tiles, int32_t *heavy_list, int32_t heavy_cap,
+                         int32_t *heavy_count, void *stream);
+int32_t dn4gl_spmm_tiled_cap_rows(int32_t D, int32_t smem_bytes, int32_t stages, int32_t nnz_per_row);
 int dn4gl_spmm_tiled_f32(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, int64_t N,
-                         int32_t D, float self_scale, const int32_t *tile_ptr, int32_t num_tiles,
-                         int32_t smem_bytes, void *stream);
+                         int32_t D, float self_scale, const int32_t *tile_desc, int32_t num_tiles,
+                         const int32_t *heavy_list, const int32_t *heavy_count, int32_t heavy_cap,
+                         int32_t smem_bytes, int32_t stages, int32_t nnz_per_row, void *stream);
 
 /* ---- K3: segment readout ------------------------------------------------------------------- */
 /* out[b,:] = scale_b * sum_{v in [seg_ptr[b], seg_ptr[b+1]), mask[v]==0} x[v,:]
