@@ -64,16 +64,31 @@ struct WsCarver {
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+// packed fp32 pairs (sm_100 add/mul.rn.f32x2 -> SASS FADD2 / FMUL2): two IEEE round-to-nearest results per issue slot
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 __device__ __forceinline__ void add4(float4 &a, const float4 &b) {
-    a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+    unsigned long long a0 = pack2(a.x, a.y), a1 = pack2(a.z, a.w);
+    const unsigned long long b0 = pack2(b.x, b.y), b1 = pack2(b.z, b.w);
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a0) : "l"(b0));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a1) : "l"(b1));
+    unpack2(a0, a.x, a.y);
+    unpack2(a1, a.z, a.w);
 }
 __device__ __forceinline__ void sub4(float4 &a, const float4 &b) {
     a.x = __fsub_rn(a.x, b.x); a.y = __fsub_rn(a.y, b.y); a.z = __fsub_rn(a.z, b.z); a.w = __fsub_rn(a.w, b.w);
 }
-// a += s * b with a separately rounded product (matches torch's  out + (1 + eps) * x )
+// a += s * b with a separately rounded product (matches torch's  out + (1 + eps) * x ).  The product stays scalar:
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (single rounding), __fmul_rn is never contracted.
 __device__ __forceinline__ void axpy4_rn(float4 &a, float s, const float4 &b) {
-    a.x = __fadd_rn(a.x, __fmul_rn(s, b.x)); a.y = __fadd_rn(a.y, __fmul_rn(s, b.y));
-    a.z = __fadd_rn(a.z, __fmul_rn(s, b.z)); a.w = __fadd_rn(a.w, __fmul_rn(s, b.w));
+    const float4 t = make_float4(__fmul_rn(s, b.x), __fmul_rn(s, b.y), __fmul_rn(s, b.z), __fmul_rn(s, b.w));
+    add4(a, t);
 }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 

@@ -27,8 +27,7 @@
 // bit-identical to the per-row kernel and to the sequential oracle.
 #include "common.cuh"
 
-constexpr int TP_THREADS = 512;
-constexpr int TP_NCW = TP_THREADS / 32 - 1;   // consumer warps
+constexpr int TP_NCW_MAX = 31;                // consumer warps: 15 (512 threads, <=128 registers) or 31 (1024 threads, 64)
 constexpr int TP_SPLIT = 64;                  // rows above this many neighbours are split (== graph.py HEAVY_THRESHOLD)
 constexpr int TP_MAX_STAGES = 4;
 constexpr uint32_t TP_BULK_CHUNK = 32768u;
@@ -61,7 +60,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TP_NCW * 32) : "memory"); }
+template <int NCW>
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
 
 // shared-memory carve-up of ONE stage: [cap_rows][DV] float4 feature rows | col slice | row_ptr slice
 struct TileCfg {
@@ -82,64 +82,92 @@ __host__ __device__ inline TileCfg tile_cfg(int smem_bytes, int stages, int DV, 
     return L;
 }
 
-template <int LANES, int VEC, bool STAGED>
-struct TileView {
-    const int32_t *__restrict__ row_ptr;
-    const int32_t *__restrict__ col;
-    const float4 *__restrict__ x;
-    const float4 *sx;
-    const int32_t *s_col;
-    const int32_t *s_rp;
-    int r0, r1, e0, a0, c0, nst;
+// explicit shared-state-space loads on 32-bit addresses: no generic->shared conversion and no 64-bit address
+// registers in the inner loops (the generic-pointer version spent most of its issue slots on address arithmetic,
+// profiles/r1b).  volatile keeps them behind the mbarrier wait.
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// butterfly over the sub-groups of a warp (fixed order -> deterministic); every sub-group ends with the total
+template <int LANES>
+__device__ __forceinline__ void subgroup_allreduce(float4 &acc) {
+#pragma unroll
+    for (int o = LANES; o < 32; o <<= 1) {
+        float4 t;
+        t.x = __shfl_xor_sync(0xffffffffu, acc.x, o); t.y = __shfl_xor_sync(0xffffffffu, acc.y, o);
+        t.z = __shfl_xor_sync(0xffffffffu, acc.z, o); t.w = __shfl_xor_sync(0xffffffffu, acc.w, o);
+        add4(acc, t);
+    }
+}
+
+// a staged tile seen through 32-bit shared addresses (all pre-offset so that absolute row / col positions index them):
+//   row_ptr[i]  at rp_a + 4*i      (i in [r0, r1])        col[q] at col_a + 4*q   (q in [e0, e0 + nst))
+//   x[c, lane's float4 k] at x_a + c*ROWB + k*LANES*16     (c in [r0, r1))
+template <int LANES, int VEC>
+struct TileAddr {
     static constexpr int DV = LANES * VEC;
-    __device__ __forceinline__ int rp(int i) const { return STAGED ? s_rp[i - a0] : __ldg(row_ptr + i); }
-    __device__ __forceinline__ int colv(int q) const {
-        return (STAGED && q - e0 < nst) ? s_col[q - c0] : __ldg(col + q);
-    }
-    __device__ __forceinline__ float4 xv(int c, int j) const {
-        return (STAGED && c >= r0 && c < r1) ? sx[static_cast<size_t>(c - r0) * DV + j]
-                                             : ldg4(x + static_cast<int64_t>(c) * DV + j);
-    }
+    static constexpr uint32_t ROWB = DV * 16u;
+    uint32_t rp_a, col_a, x_a;
+    int r0, r1, e0, nst;
 };
 
-// all rows of one tile, consumer warp cw; see the header comment for the three row classes
-template <int LANES, int VEC, bool STAGED>
-__device__ __forceinline__ void process_tile(const TileView<LANES, VEC, STAGED> &tv, float4 *__restrict__ out,
-                                             float self_scale, bool cut, int cw, int lane) {
+// CHECKED path (cut / unverified tiles, partially staged col slices, tiles larger than a stage when !STAGED):
+// every index is tested against the staged window and falls back to global loads.
+template <int LANES, int VEC, int NCW, bool STAGED>
+__device__ __forceinline__ void process_tile(const TileAddr<LANES, VEC> &ta, const int32_t *__restrict__ row_ptr,
+                                             const int32_t *__restrict__ col, const float4 *__restrict__ x,
+                                             float4 *__restrict__ out, float self_scale, bool cut, int cw, int lane) {
     constexpr int RPW = 32 / LANES;   // rows per warp iteration
     constexpr int DV = LANES * VEC;
-    constexpr int U = (VEC == 1) ? 4 : 2;
+    constexpr uint32_t ROWB = DV * 16u;
     const int sub = lane / LANES, sl = lane % LANES;
-    for (int rb = tv.r0 + cw * RPW; rb < tv.r1; rb += TP_NCW * RPW) {
+    auto colv = [&](int q) -> int {
+        return (STAGED && q - ta.e0 < ta.nst) ? lds32(ta.col_a + 4u * static_cast<uint32_t>(q)) : __ldg(col + q);
+    };
+    auto xv = [&](int c, int k) -> float4 {
+        return (STAGED && c >= ta.r0 && c < ta.r1) ? lds128(ta.x_a + static_cast<uint32_t>(c) * ROWB + k * (LANES * 16))
+                                                   : ldg4(x + static_cast<int64_t>(c) * DV + sl + k * LANES);
+    };
+#pragma unroll 1
+    for (int rb = ta.r0 + cw * RPW; rb < ta.r1; rb += NCW * RPW) {
         const int row = rb + sub;
-        const bool valid = row < tv.r1;
-        const int beg = valid ? tv.rp(row) : 0, end = valid ? tv.rp(row + 1) : 0;
+        const bool valid = row < ta.r1;
+        int beg = 0, end = 0;
+        if (valid) {
+            beg = STAGED ? lds32(ta.rp_a + 4u * static_cast<uint32_t>(row)) : __ldg(row_ptr + row);
+            end = STAGED ? lds32(ta.rp_a + 4u * static_cast<uint32_t>(row) + 4u) : __ldg(row_ptr + row + 1);
+        }
         const bool big = valid && (end - beg > TP_SPLIT);
-        const bool seq = valid && (!big || (LANES == 32 && !cut));
-        if (seq) {
+        if (valid && (!big || (LANES == 32 && !cut))) {
             float4 acc[VEC];
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc[k] = zero4();
-            for (int p = beg; p < end; p += U) {
-                int c[U];
+            int p = beg;
+#pragma unroll 1
+            for (; p + 2 <= end; p += 2) {
+                const int c0 = colv(p), c1 = colv(p + 1);
+                float4 v0[VEC], v1[VEC];
 #pragma unroll
-                for (int u = 0; u < U; ++u) c[u] = (p + u < end) ? tv.colv(p + u) : -1;
-                float4 v[U][VEC];
+                for (int k = 0; k < VEC; ++k) { v0[k] = xv(c0, k); v1[k] = xv(c1, k); }
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (c[u] < 0) continue;
+                for (int k = 0; k < VEC; ++k) { add4(acc[k], v0[k]); add4(acc[k], v1[k]); }
+            }
+            if (p < end) {
+                const int c0 = colv(p);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) v[u][k] = tv.xv(c[u], sl + k * LANES);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k)
-                        if (c[u] >= 0) add4(acc[k], v[u][k]);
+                for (int k = 0; k < VEC; ++k) add4(acc[k], xv(c0, k));
             }
             if (self_scale != 0.f) {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) axpy4_rn(acc[k], self_scale, tv.xv(row, sl + k * LANES));
+                for (int k = 0; k < VEC; ++k) axpy4_rn(acc[k], self_scale, xv(row, k));
             }
 #pragma unroll
             for (int k = 0; k < VEC; ++k) out[static_cast<int64_t>(row) * DV + sl + k * LANES] = acc[k];
@@ -149,31 +177,23 @@ __device__ __forceinline__ void process_tile(const TileView<LANES, VEC, STAGED> 
             unsigned m = __ballot_sync(0xffffffffu, big && !cut);
             while (m) {
                 const int src_lane = __ffs(m) - 1;   // first lane of the owning sub-group
-                m &= ~(((LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u)) << src_lane);
+                m &= ~(((1u << LANES) - 1u) << src_lane);
                 const int brow = rb + src_lane / LANES;
                 const int bbeg = __shfl_sync(0xffffffffu, beg, src_lane), bend = __shfl_sync(0xffffffffu, end, src_lane);
                 float4 acc = zero4();
-                for (int p = bbeg + sub; p < bend; p += RPW * 4) {
-                    int c[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) c[u] = (p + u * RPW < bend) ? tv.colv(p + u * RPW) : -1;
-                    float4 v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (c[u] >= 0) v[u] = tv.xv(c[u], sl);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (c[u] >= 0) add4(acc, v[u]);
+#pragma unroll 1
+                for (int p = bbeg + sub; p < bend; p += 2 * RPW) {
+                    const int c0 = colv(p);
+                    const int c1 = (p + RPW < bend) ? colv(p + RPW) : -1;
+                    const float4 v0 = xv(c0, 0);
+                    float4 v1 = zero4();
+                    if (c1 >= 0) v1 = xv(c1, 0);
+                    add4(acc, v0);
+                    if (c1 >= 0) add4(acc, v1);
                 }
-#pragma unroll
-                for (int o = LANES; o < 32; o <<= 1) {
-                    float4 t;
-                    t.x = __shfl_xor_sync(0xffffffffu, acc.x, o); t.y = __shfl_xor_sync(0xffffffffu, acc.y, o);
-                    t.z = __shfl_xor_sync(0xffffffffu, acc.z, o); t.w = __shfl_xor_sync(0xffffffffu, acc.w, o);
-                    add4(acc, t);
-                }
+                subgroup_allreduce<LANES>(acc);
                 if (sub == 0) {
-                    if (self_scale != 0.f) axpy4_rn(acc, self_scale, tv.xv(brow, sl));
+                    if (self_scale != 0.f) axpy4_rn(acc, self_scale, xv(brow, 0));
                     out[static_cast<int64_t>(brow) * DV + sl] = acc;
                 }
             }
@@ -181,15 +201,104 @@ __device__ __forceinline__ void process_tile(const TileView<LANES, VEC, STAGED> 
     }
 }
 
+// FAST path: a verified self-contained tile (every col index inside [r0, r1), checked once by dn4gl_make_row_tiles)
+// whose col slice is fully staged.  No window checks, no fallbacks: per neighbour one 32-bit and VEC 128-bit shared
+// loads, one integer multiply-add and 2*VEC packed adds.  This is the loop that bounds the kernel.
+template <int LANES, int VEC, int NCW>
+__device__ __forceinline__ void process_tile_fast(const TileAddr<LANES, VEC> &ta, float4 *__restrict__ out,
+                                                  float self_scale, int cw, int lane) {
+    constexpr int RPW = 32 / LANES;
+    constexpr int DV = LANES * VEC;
+    constexpr uint32_t ROWB = DV * 16u;
+    constexpr uint32_t KB = LANES * 16u;   // byte distance between a lane's consecutive float4 of one row
+    const int sub = lane / LANES, sl = lane % LANES;
+    const uint32_t xa = ta.x_a, ca_base = ta.col_a;
+    float4 *outl = out + sl;
+#pragma unroll 1
+    for (int rb = ta.r0 + cw * RPW; rb < ta.r1; rb += NCW * RPW) {
+        const int row = rb + sub;
+        const bool valid = row < ta.r1;
+        int beg = 0, end = 0;
+        if (valid) {
+            const uint32_t ra = ta.rp_a + 4u * static_cast<uint32_t>(row);
+            beg = lds32(ra);
+            end = lds32(ra + 4u);
+        }
+        const bool big = (LANES < 32) && (end - beg > TP_SPLIT);
+        if (valid && !big) {
+            float4 acc[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[k] = zero4();
+            uint32_t ca = ca_base + 4u * static_cast<uint32_t>(beg);
+            const uint32_t ce = ca_base + 4u * static_cast<uint32_t>(end);
+#pragma unroll 1
+            for (; ca + 16u <= ce; ca += 16u) {
+                const uint32_t a0 = xa + static_cast<uint32_t>(lds32(ca)) * ROWB;
+                const uint32_t a1 = xa + static_cast<uint32_t>(lds32(ca + 4u)) * ROWB;
+                const uint32_t a2 = xa + static_cast<uint32_t>(lds32(ca + 8u)) * ROWB;
+                const uint32_t a3 = xa + static_cast<uint32_t>(lds32(ca + 12u)) * ROWB;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const float4 v0 = lds128(a0 + k * KB), v1 = lds128(a1 + k * KB);
+                    const float4 v2 = lds128(a2 + k * KB), v3 = lds128(a3 + k * KB);
+                    add4(acc[k], v0); add4(acc[k], v1); add4(acc[k], v2); add4(acc[k], v3);
+                }
+            }
+#pragma unroll 1
+            for (; ca < ce; ca += 4u) {
+                const uint32_t a0 = xa + static_cast<uint32_t>(lds32(ca)) * ROWB;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) add4(acc[k], lds128(a0 + k * KB));
+            }
+            if (self_scale != 0.f) {
+                const uint32_t a0 = xa + static_cast<uint32_t>(row) * ROWB;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) axpy4_rn(acc[k], self_scale, lds128(a0 + k * KB));
+            }
+            float4 *o = outl + static_cast<int64_t>(row) * DV;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) o[k * LANES] = acc[k];
+        }
+        if constexpr (LANES < 32) {
+            unsigned m = __ballot_sync(0xffffffffu, valid && big);
+            while (m) {   // long rows of this iteration, split over the RPW sub-groups of the warp
+                const int src_lane = __ffs(m) - 1;
+                m &= ~(((1u << LANES) - 1u) << src_lane);
+                const int brow = rb + src_lane / LANES;
+                const int bbeg = __shfl_sync(0xffffffffu, beg, src_lane), bend = __shfl_sync(0xffffffffu, end, src_lane);
+                float4 acc = zero4();
+                uint32_t ca = ca_base + 4u * static_cast<uint32_t>(bbeg + sub);
+                const uint32_t ce = ca_base + 4u * static_cast<uint32_t>(bend);
+#pragma unroll 1
+                for (; ca + 12u * RPW < ce; ca += 16u * RPW) {
+                    const uint32_t a0 = xa + static_cast<uint32_t>(lds32(ca)) * ROWB;
+                    const uint32_t a1 = xa + static_cast<uint32_t>(lds32(ca + 4u * RPW)) * ROWB;
+                    const uint32_t a2 = xa + static_cast<uint32_t>(lds32(ca + 8u * RPW)) * ROWB;
+                    const uint32_t a3 = xa + static_cast<uint32_t>(lds32(ca + 12u * RPW)) * ROWB;
+                    const float4 v0 = lds128(a0), v1 = lds128(a1), v2 = lds128(a2), v3 = lds128(a3);
+                    add4(acc, v0); add4(acc, v1); add4(acc, v2); add4(acc, v3);
+                }
+#pragma unroll 1
+                for (; ca < ce; ca += 4u * RPW) add4(acc, lds128(xa + static_cast<uint32_t>(lds32(ca)) * ROWB));
+                subgroup_allreduce<LANES>(acc);
+                if (sub == 0) {
+                    if (self_scale != 0.f) axpy4_rn(acc, self_scale, lds128(xa + static_cast<uint32_t>(brow) * ROWB));
+                    outl[static_cast<int64_t>(brow) * DV] = acc;
+                }
+            }
+        }
+    }
+}
+
 // one listed long row of a cut tile, reduced by all consumer warps of the CTA through `scratch` (an idle stage)
-template <int LANES, int VEC>
+template <int LANES, int VEC, int NCW>
 __device__ __forceinline__ void process_heavy_row(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                                                   const float4 *__restrict__ x, float4 *__restrict__ out, int row,
                                                   float self_scale, float4 *scratch, int cw, int lane) {
     constexpr int RPW = 32 / LANES;
     constexpr int DV = LANES * VEC;
-    constexpr int SG = TP_NCW * RPW;   // sub-groups in the CTA
-    constexpr int UH = (VEC == 4) ? 2 : 4;
+    constexpr int SG = NCW * RPW;   // sub-groups in the CTA
+    constexpr int UH = (VEC == 4 || NCW > 15) ? 2 : 4;
     const int sub = lane / LANES, sl = lane % LANES;
     const int sg = cw * RPW + sub;
     const int beg = __ldg(row_ptr + row), end = __ldg(row_ptr + row + 1);
@@ -216,7 +325,7 @@ __device__ __forceinline__ void process_heavy_row(const int32_t *__restrict__ ro
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k) scratch[static_cast<size_t>(sg) * DV + sl + k * LANES] = acc[k];
-    consumer_bar_sync();
+    consumer_bar_sync<NCW>();
     if (cw == 0) {
         // sub-group `sub` adds the partials sub, sub+RPW, ... in ascending order, then a fixed butterfly over sub-groups
 #pragma unroll
@@ -247,8 +356,8 @@ __device__ __forceinline__ void process_heavy_row(const int32_t *__restrict__ ro
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <int LANES, int VEC>
-__global__ void __launch_bounds__(TP_THREADS, 1)
+template <int LANES, int VEC, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1)
 spmm_pipe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const float4 *__restrict__ x,
                  float4 *__restrict__ out, const int4 *__restrict__ tiles, int num_tiles,
                  const int32_t *__restrict__ heavy_list, const int32_t *__restrict__ heavy_count, float self_scale,
@@ -261,7 +370,7 @@ spmm_pipe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict_
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], TP_NCW);
+            mbar_init(&empty_bar[s], NCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -315,29 +424,31 @@ spmm_pipe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict_
         if (t < H) {
             const int row = __ldg(heavy_list + t);
             mbar_wait(&full_bar[s], use & 1u);
-            process_heavy_row<LANES, VEC>(row_ptr, col, x, out, row, self_scale, reinterpret_cast<float4 *>(base), cw, lane);
+            process_heavy_row<LANES, VEC, NCW>(row_ptr, col, x, out, row, self_scale, reinterpret_cast<float4 *>(base), cw, lane);
         } else {
             const int4 td = __ldg(tiles + (t - H));
             const int rows = td.y - td.x;
             mbar_wait(&full_bar[s], use & 1u);
             if (rows > 0) {
-                const bool cut = heavy_list != nullptr && td.w < 0;
-                if (rows <= L.cap_rows) {
-                    TileView<LANES, VEC, true> tv;
-                    tv.row_ptr = row_ptr; tv.col = col; tv.x = x;
-                    tv.sx = reinterpret_cast<const float4 *>(base);
-                    tv.s_col = reinterpret_cast<const int32_t *>(base + L.off_col);
-                    tv.s_rp = reinterpret_cast<const int32_t *>(base + L.off_rp);
-                    tv.r0 = td.x; tv.r1 = td.y; tv.e0 = td.z; tv.a0 = td.x & ~3; tv.c0 = td.z & ~3;
-                    tv.nst = min((td.w & 0x7fffffff) - td.z, L.cap_nnz);
-                    process_tile<LANES, VEC, true>(tv, out, self_scale, cut, cw, lane);
-                } else {
-                    TileView<LANES, VEC, false> tv;
-                    tv.row_ptr = row_ptr; tv.col = col; tv.x = x;
-                    tv.sx = nullptr; tv.s_col = nullptr; tv.s_rp = nullptr;
-                    tv.r0 = td.x; tv.r1 = td.y; tv.e0 = td.z; tv.a0 = 0; tv.c0 = 0; tv.nst = 0;
-                    process_tile<LANES, VEC, false>(tv, out, self_scale, cut, cw, lane);
+                const bool open = td.w < 0;                          // cut inside a graph or not verified self-contained
+                const bool cut = heavy_list != nullptr && open;      // its long rows are on the heavy list
+                const int nnz = (td.w & 0x7fffffff) - td.z;
+                TileAddr<LANES, VEC> ta;
+                {   // pre-offset 32-bit shared addresses (unsigned wrap-around is intended)
+                    const uint32_t sbase = smem_u32(base);
+                    const int a0 = td.x & ~3, c0 = td.z & ~3;
+                    ta.rp_a = sbase + L.off_rp - 4u * static_cast<uint32_t>(a0);
+                    ta.col_a = sbase + L.off_col - 4u * static_cast<uint32_t>(c0);
+                    ta.x_a = sbase + static_cast<uint32_t>(lane % LANES) * 16u -
+                             static_cast<uint32_t>(td.x) * TileAddr<LANES, VEC>::ROWB;
+                    ta.r0 = td.x; ta.r1 = td.y; ta.e0 = td.z; ta.nst = min(nnz, L.cap_nnz);
                 }
+                if (rows <= L.cap_rows && !open && nnz <= L.cap_nnz)
+                    process_tile_fast<LANES, VEC, NCW>(ta, out, self_scale, cw, lane);
+                else if (rows <= L.cap_rows)
+                    process_tile<LANES, VEC, NCW, true>(ta, row_ptr, col, x, out, self_scale, cut, cw, lane);
+                else
+                    process_tile<LANES, VEC, NCW, false>(ta, row_ptr, col, x, out, self_scale, cut, cw, lane);
             }
         }
         __syncwarp();
@@ -376,6 +487,21 @@ __global__ void make_row_tiles_kernel(const int32_t *__restrict__ seg_ptr, int B
     tiles[k] = make_int4(r0, r1, e0, e1 | (cut ? static_cast<int>(0x80000000u) : 0));
 }
 
+// one warp per graph-aligned tile: any column index outside [r0, r1) (seg_ptr was not a block partition of this CSR)
+// marks the tile "open", which keeps it off the unchecked fast path
+__global__ void verify_tiles_kernel(const int32_t *__restrict__ col, int4 *__restrict__ tiles, int T) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= T) return;
+    const int4 td = tiles[k];
+    if (td.w < 0) return;
+    bool bad = false;
+    for (int q = td.z + lane; q < td.w; q += 32) {
+        const int c = __ldg(col + q);
+        bad |= (c < td.x) || (c >= td.y);
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) tiles[k].w = td.w | static_cast<int>(0x80000000u);
+}
+
 // rows with more than TP_SPLIT neighbours that live in cut tiles -> heavy_list (order irrelevant, see kernel)
 __global__ void collect_cut_heavy_kernel(const int32_t *__restrict__ row_ptr, int N, int C, const int4 *__restrict__ tiles,
                                          int T, int32_t *__restrict__ heavy_list, int cap, int32_t *__restrict__ heavy_count) {
@@ -392,9 +518,10 @@ __global__ void collect_cut_heavy_kernel(const int32_t *__restrict__ row_ptr, in
 }
 
 extern "C" int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t window_rows, const int32_t *row_ptr,
-                                    int64_t N, int32_t *tile_desc, int32_t num_tiles, int32_t *heavy_list,
-                                    int32_t heavy_cap, int32_t *heavy_count, void *stream) {
-    DN_ARG(seg_ptr && row_ptr && tile_desc && B >= 0 && window_rows > 0 && num_tiles >= 0 && N >= 0 && N < (1ll << 31));
+                                    const int32_t *col, int64_t N, int32_t *tile_desc, int32_t num_tiles,
+                                    int32_t *heavy_list, int32_t heavy_cap, int32_t *heavy_count, void *stream) {
+    DN_ARG(seg_ptr && row_ptr && col && tile_desc && B >= 0 && window_rows > 0 && num_tiles >= 0 && N >= 0 &&
+           N < (1ll << 31));
     DN_ARG(static_cast<int64_t>(num_tiles) * window_rows >= N && aligned16(tile_desc));
     cudaStream_t st = as_stream(stream);
     int launched = 0;
@@ -402,7 +529,8 @@ extern "C" int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t w
     if (num_tiles > 0) {
         make_row_tiles_kernel<<<(num_tiles + 255) / 256, 256, 0, st>>>(seg_ptr, B, window_rows, row_ptr, static_cast<int>(N),
                                                                       reinterpret_cast<int4 *>(tile_desc), num_tiles);
-        ++launched;
+        verify_tiles_kernel<<<(num_tiles * 32 + 255) / 256, 256, 0, st>>>(col, reinterpret_cast<int4 *>(tile_desc), num_tiles);
+        launched += 2;
         if (heavy_list && heavy_count && N > 0) {
             collect_cut_heavy_kernel<<<static_cast<unsigned>(ceil_div64(N, 256)), 256, 0, st>>>(
                 row_ptr, static_cast<int>(N), window_rows, reinterpret_cast<const int4 *>(tile_desc), num_tiles, heavy_list,
@@ -420,22 +548,22 @@ extern "C" int32_t dn4gl_spmm_tiled_cap_rows(int32_t D, int32_t smem_bytes, int3
     return tile_cfg(smem_bytes, stages, D / 4, nnz_per_row).cap_rows;
 }
 
-template <int LANES, int VEC>
+template <int LANES, int VEC, int NCW>
 static int launch_pipe(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, const int32_t *tile_desc,
                        int num_tiles, const int32_t *heavy_list, const int32_t *heavy_count, int heavy_cap,
                        float self_scale, int smem_bytes, int stages, int nnz_per_row, cudaStream_t st) {
     static int attr_done = 0;
     if (attr_done < smem_bytes) {
-        if (cudaFuncSetAttribute(spmm_pipe_kernel<LANES, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) !=
-            cudaSuccess)
+        if (cudaFuncSetAttribute(spmm_pipe_kernel<LANES, VEC, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 smem_bytes) != cudaSuccess)
             return -1;
         attr_done = smem_bytes;
     }
-    const int per_sm = 1;   // one persistent CTA per SM: 15 consumer warps, up to 128 registers, the whole shared memory as ring
+    // one persistent CTA per SM: the whole shared memory is its ring
     int64_t want = static_cast<int64_t>(num_tiles) + (heavy_list ? heavy_cap : 0);
-    int grid = static_cast<int>(want < dn4gl_num_sms() * per_sm ? want : dn4gl_num_sms() * per_sm);
+    int grid = static_cast<int>(want < dn4gl_num_sms() ? want : dn4gl_num_sms());
     if (grid < 1) grid = 1;
-    spmm_pipe_kernel<LANES, VEC><<<grid, TP_THREADS, smem_bytes, st>>>(
+    spmm_pipe_kernel<LANES, VEC, NCW><<<grid, (NCW + 1) * 32, smem_bytes, st>>>(
         row_ptr, col, reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(out),
         reinterpret_cast<const int4 *>(tile_desc), num_tiles, heavy_list, heavy_count, self_scale, smem_bytes, stages,
         nnz_per_row);
@@ -445,23 +573,31 @@ static int launch_pipe(const int32_t *row_ptr, const int32_t *col, const float *
 extern "C" int dn4gl_spmm_tiled_f32(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, int64_t N,
                                     int32_t D, float self_scale, const int32_t *tile_desc, int32_t num_tiles,
                                     const int32_t *heavy_list, const int32_t *heavy_count, int32_t heavy_cap,
-                                    int32_t smem_bytes, int32_t stages, int32_t nnz_per_row, void *stream) {
+                                    int32_t smem_bytes, int32_t stages, int32_t nnz_per_row, int32_t warps,
+                                    void *stream) {
+    DN_ARG(warps == 16 || warps == 24 || warps == 32);
     DN_ARG(N >= 0 && D > 0 && D % 4 == 0 && num_tiles >= 0 && smem_bytes >= 16 * 1024 && smem_bytes <= 220 * 1024);
     DN_ARG(stages >= 1 && stages <= TP_MAX_STAGES && nnz_per_row >= 1 && nnz_per_row <= 64);
     if (N == 0 || num_tiles == 0) return DN4GL_OK;
     DN_ARG(row_ptr && col && x && out && tile_desc && aligned16(x) && aligned16(out) && aligned16(row_ptr) &&
            aligned16(col) && aligned16(tile_desc));
     DN_ARG((heavy_list == nullptr) == (heavy_count == nullptr));
-    {   // the CTA-wide reduction of listed rows uses one stage as scratch: 15 warps x (32/LANES) partial rows
+    {   // the CTA-wide reduction of listed rows uses one stage as scratch: (warps - 1) x (32/LANES) partial rows
         const int dv = D / 4, lanes = dv < 32 ? dv : 32;
-        const int64_t scratch = static_cast<int64_t>(TP_NCW) * (32 / lanes) * dv * 16;
+        const int64_t scratch = static_cast<int64_t>((dv <= 32 ? warps : 16) - 1) * (32 / lanes) * dv * 16;
         DN_ARG(heavy_list == nullptr || scratch <= ((smem_bytes / stages) & ~127));
     }
     cudaStream_t st = as_stream(stream);
     int rc = 0;
-#define PIPE_CASE(L, V)                                                                                              \
-    rc = launch_pipe<L, V>(row_ptr, col, x, out, tile_desc, num_tiles, heavy_list, heavy_count, heavy_cap, self_scale, \
-                           smem_bytes, stages, nnz_per_row, st);                                                     \
+#define PIPE_ARGS row_ptr, col, x, out, tile_desc, num_tiles, heavy_list, heavy_count, heavy_cap, self_scale, smem_bytes, stages, nnz_per_row, st
+#define PIPE_CASE(L, V)                                                          \
+    if constexpr (V == 1) {                                                      \
+        if (warps == 32) rc = launch_pipe<L, V, 31>(PIPE_ARGS);                  \
+        else if (warps == 24) rc = launch_pipe<L, V, 23>(PIPE_ARGS);             \
+        else rc = launch_pipe<L, V, 15>(PIPE_ARGS);                              \
+    } else {                                                                     \
+        rc = launch_pipe<L, V, 15>(PIPE_ARGS);                                   \
+    }                                                                            \
     break
     switch (D / 4) {
         case 4: PIPE_CASE(4, 1);
@@ -475,6 +611,7 @@ extern "C" int dn4gl_spmm_tiled_f32(const int32_t *row_ptr, const int32_t *col, 
             return DN4GL_EINVAL;
     }
 #undef PIPE_CASE
+#undef PIPE_ARGS
     if (rc != 0) {
         dn4gl_set_error("dn4gl_spmm_tiled_f32: cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%d) failed", smem_bytes);
         return DN4GL_ECUDA;

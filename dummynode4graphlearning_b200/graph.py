@@ -20,6 +20,7 @@ from ._lib import lib, ptr
 
 HEAVY_THRESHOLD = 64  # rows with more in-edges than this are reduced by a whole CTA (dummy nodes)
 TILE_SMEM = int(os.environ.get("DN4GL_TILE_SMEM", str(200 * 1024)))   # shared-memory ring of the pipelined aggregation kernel
+TILE_WARPS = int(os.environ.get("DN4GL_TILE_WARPS", "32"))             # warps per CTA for D <= 128 (16 | 32)
 
 _dev_bound = {}
 
@@ -89,15 +90,16 @@ class CSR:
         desc = torch.empty(4 * max(T, 1), dtype=torch.int32, device=dev)
         heavy_list = heavy_count = None
         heavy_cap = 0
-        scratch = 15 * (32 // min(D // 4, 32)) * D * 4       # CTA-wide reduction scratch must fit one stage
+        warps = TILE_WARPS if D <= 128 else 16
+        scratch = (warps - 1) * (32 // min(D // 4, 32)) * D * 4   # CTA-wide reduction scratch must fit one stage
         if not aligned and scratch <= ((smem_bytes // stages) & ~127):
             heavy_cap = self.nnz // 64 + 1
             heavy_list = torch.empty(heavy_cap, dtype=torch.int32, device=dev)
             heavy_count = torch.zeros(1, dtype=torch.int32, device=dev)
         L.call("dn4gl_make_row_tiles", ptr(self.seg_ptr), int(self.seg_ptr.numel()) - 1, window, ptr(self.row_ptr),
-               self.n_rows, ptr(desc), T, ptr(heavy_list), heavy_cap, ptr(heavy_count), _stream())
+               ptr(self.col), self.n_rows, ptr(desc), T, ptr(heavy_list), heavy_cap, ptr(heavy_count), _stream())
         cfg = dict(desc=desc, T=T, heavy_list=heavy_list, heavy_count=heavy_count, heavy_cap=heavy_cap,
-                   smem=smem_bytes, stages=stages, npr=npr, window=window, cap_rows=cap)
+                   smem=smem_bytes, stages=stages, npr=npr, window=window, cap_rows=cap, warps=warps)
         self._tiles[key] = cfg
         return cfg
 

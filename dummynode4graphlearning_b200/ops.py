@@ -32,7 +32,7 @@ def _spmm(csr: CSR, x, n_out, self_scale):
         t = csr.tiles(D, TILE_SMEM)
         lib().call("dn4gl_spmm_tiled_f32", ptr(csr.row_ptr), ptr(csr.col), ptr(x), ptr(out), n_out, D,
                    float(self_scale), ptr(t["desc"]), t["T"], ptr(t["heavy_list"]), ptr(t["heavy_count"]),
-                   t["heavy_cap"], t["smem"], t["stages"], t["npr"], _stream())
+                   t["heavy_cap"], t["smem"], t["stages"], t["npr"], t["warps"], _stream())
         return out
     lib().call("dn4gl_spmm_sum_f32", ptr(csr.row_ptr), ptr(csr.col), ptr(x), ptr(out), n_out, x.size(0), D,
                float(self_scale), ptr(csr.heavy_rows), ptr(csr.heavy_count), csr.heavy_thr, _stream())

@@ -164,19 +164,21 @@ int dn4gl_spmm_sum_f32(const int32_t *row_ptr, const int32_t *col, const float *
  *   ceil(N / window_rows); window_rows <= cap_rows - (largest graph) keeps every tile inside one stage (cap_rows / 2
  *   is always safe).  heavy_list[heavy_cap] / heavy_count[1] (optional, both or neither): rows with more than 64
  *   neighbours inside tiles that had to cut a graph longer than the window; the kernel reduces them CTA-wide.
- *   heavy_cap >= E / 64 + 1.
+ *   heavy_cap >= E / 64 + 1.  The tiling must be rebuilt when row_ptr / col change.
  * dn4gl_spmm_tiled_f32: smem_bytes = dynamic shared memory per CTA (16 KiB .. 220 KiB; <= 110 KiB lets two CTAs share
- *   an SM for D <= 128), stages in 1..4, nnz_per_row = col slots staged per row (about ceil(E/N) + 1).
+ *   an SM for D <= 128), stages in 1..4, nnz_per_row = col slots staged per row (about ceil(E/N) + 1), warps = 16, 24
+ *   or 32 per CTA (one producer + 15 / 23 / 31 consumers; more than 16 only applies to D <= 128).  Tiles whose columns were verified to
+ *   stay inside the tile (done by dn4gl_make_row_tiles) run an unchecked shared-memory-only loop.
  * row_ptr and col must be 16-byte aligned and their allocations padded to a multiple of 16 bytes (bulk copies move
  * whole 16-byte words; true for any cudaMalloc / torch allocation).                                                 */
-int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t window_rows, const int32_t *row_ptr, int64_t N,
-                         int32_t *tile_desc, int32_t num_tiles, int32_t *heavy_list, int32_t heavy_cap,
-                         int32_t *heavy_count, void *stream);
+int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t window_rows, const int32_t *row_ptr,
+                         const int32_t *col, int64_t N, int32_t *tile_desc, int32_t num_tiles, int32_t *heavy_list,
+                         int32_t heavy_cap, int32_t *heavy_count, void *stream);
 int32_t dn4gl_spmm_tiled_cap_rows(int32_t D, int32_t smem_bytes, int32_t stages, int32_t nnz_per_row);
 int dn4gl_spmm_tiled_f32(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, int64_t N,
                          int32_t D, float self_scale, const int32_t *tile_desc, int32_t num_tiles,
                          const int32_t *heavy_list, const int32_t *heavy_count, int32_t heavy_cap,
-                         int32_t smem_bytes, int32_t stages, int32_t nnz_per_row, void *stream);
+                         int32_t smem_bytes, int32_t stages, int32_t nnz_per_row, int32_t warps, void *stream);
 
 /* ---- K3: segment readout ------------------------------------------------------------------- */
 /* out[b,:] = scale_b * sum_{v in [seg_ptr[b], seg_ptr[b+1]), mask[v]==0} x[v,:]

@@ -168,22 +168,24 @@ def test_linear_function_matches_torch(device):
     torch.testing.assert_close(lin.bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-3)
 
 
-@pytest.mark.parametrize("mode,smem,known", [("rows", None, True), ("tiled", None, True), ("tiled", None, False),
-                                             ("tiled", 96 * 1024, True), ("tiled", 48 * 1024, False),
-                                             ("tiled", 16 * 1024, True), ("tiled", 16 * 1024, False)])
+@pytest.mark.parametrize("mode,smem,known,warps", [("rows", None, True, 32), ("tiled", None, True, 32), ("tiled", None, False, 32),
+                                                   ("tiled", None, True, 16), ("tiled", None, False, 24),
+                                                   ("tiled", 96 * 1024, True, 32), ("tiled", 48 * 1024, False, 16),
+                                                   ("tiled", 16 * 1024, True, 24), ("tiled", 16 * 1024, False, 32)])
 @pytest.mark.parametrize("shape,nb,D", [("proteins", 150, 32), ("proteins", 40, 128), ("mutag", 700, 64), ("mutag", 300, 512),
                                         ("proteins", 60, 16), ("mutag", 100, 256)])
-def test_spmm_variants_agree_with_oracle(device, monkeypatch, mode, smem, known, shape, nb, D):
+def test_spmm_variants_agree_with_oracle(device, monkeypatch, mode, smem, known, warps, shape, nb, D):
     """per-row gather kernel and the pipelined shared-memory staged kernel against the sequential oracle, forward and
     adjoint: default ring, smaller rings (graphs longer than the window are cut -> heavy-row list, global fallbacks,
     tiles of one or two rows), with and without the host knowing the largest graph (graph-aligned vs half-stage
     windows)."""
-    from dummynode4graphlearning_b200 import ops
+    from dummynode4graphlearning_b200 import graph as graph_mod, ops
     from dummynode4graphlearning_b200.graph import BatchedGraph
     from oracle import transforms as O
 
     monkeypatch.setattr(ops, "SPMM_MODE", mode)
     monkeypatch.setattr(ops, "TILE_SMEM", smem)
+    monkeypatch.setattr(graph_mod, "TILE_WARPS", warps)
     b = O.tu_conjugate(O.tu_add_dummy(synth.tu_batch(shape, nb, seed=3)))
     g = BatchedGraph.from_batch(b, device)
     if not known:

@@ -47,10 +47,11 @@ def main():
     ap.add_argument("--shape", default="mutag")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--warps", default="32", help="warps per CTA of the tiled kernel (16,24,32)")
     ap.add_argument("--known", type=int, default=1, help="1: the host knows the largest graph (graph-aligned tiles)")
     a = ap.parse_args()
 
-    from dummynode4graphlearning_b200 import ops, synth, transforms as T
+    from dummynode4graphlearning_b200 import graph as graph_mod, ops, synth, transforms as T
     from dummynode4graphlearning_b200.graph import BatchedGraph
 
     dev = torch.device("cuda:0")
@@ -75,10 +76,13 @@ def main():
             x = torch.rand((N, D), device=dev) * 2 - 1
             bytes_alg = 4 * D * N * 2 + 4 * E + 4 * (N + 1)
             for mode in a.modes.split(","):
-                for smem_kb in ([int(s) for s in a.smem.split(",")] if mode == "tiled" else [0]):
+                cfgs = [(int(s), int(w)) for s in a.smem.split(",") for w in a.warps.split(",")] if mode == "tiled" else [(0, 0)]
+                for smem_kb, warps in cfgs:
                     ops.SPMM_MODE = mode
                     if smem_kb:
                         ops.TILE_SMEM = smem_kb * 1024
+                        graph_mod.TILE_WARPS = warps
+                        g.csr_in._tiles.clear()
                     for _ in range(3):
                         ops.graph_sum_aggregate(g, x, 1.0)
                     ts = []
@@ -91,7 +95,7 @@ def main():
                         torch.cuda.synchronize()
                         ts.append(e0.elapsed_time(e1))
                     us = 1e3 * statistics.median(ts)
-                    r = {"graphs": B, "N": N, "E": E, "D": D, "mode": mode, "smem_kb": smem_kb, "us": round(us, 2),
+                    r = {"graphs": B, "N": N, "E": E, "D": D, "mode": mode, "smem_kb": smem_kb, "warps": warps, "us": round(us, 2),
                          "alg_MB": round(bytes_alg / 1e6, 2), "alg_GBs": round(bytes_alg / us / 1e3, 1),
                          "frac_of_measured_peak": round(bytes_alg / us / 1e3 / peak, 4),
                          "graphs_per_s": round(B / us * 1e6)}
