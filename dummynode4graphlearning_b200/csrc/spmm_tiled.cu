@@ -151,6 +151,14 @@ __device__ __forceinline__ void process_tile(const TileAddr<LANES, VEC> &ta, con
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc[k] = zero4();
             int p = beg;
+            if constexpr (VEC == 1) {   // four neighbours in flight: out-of-window rows come from L2 / HBM
+#pragma unroll 1
+                for (; p + 4 <= end; p += 4) {
+                    const int c0 = colv(p), c1 = colv(p + 1), c2 = colv(p + 2), c3 = colv(p + 3);
+                    const float4 v0 = xv(c0, 0), v1 = xv(c1, 0), v2 = xv(c2, 0), v3 = xv(c3, 0);
+                    add4(acc[0], v0); add4(acc[0], v1); add4(acc[0], v2); add4(acc[0], v3);
+                }
+            }
 #pragma unroll 1
             for (; p + 2 <= end; p += 2) {
                 const int c0 = colv(p), c1 = colv(p + 1);

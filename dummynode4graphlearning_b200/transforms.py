@@ -9,6 +9,7 @@ load_graph_data_from_TUDatadir(with_dummy) ``tu_add_dummy``      (tu_data_proces
 convert_conjugate_graph_forward            ``tu_conjugate``      (tu_data_processing.py:223-338)
 PyG read_tu_data + set_dummy_flags         ``pyg_canonicalize``  (graph_neural_networks/dataset.py:118-151)
 add_dummy_nodes_edges (GraphAdj branch)    ``sub_add_dummy``     (subgraph_isomorphism/train.py:404-474)
+convert_conjugate_graph / _to_conjugate    ``sub_conjugate``     (utils/graph.py:77-175, train.py:564-593)
 process_model_config                       ``process_model_config`` (train.py:38-81)
 =========================================  ==================================================
 
@@ -138,6 +139,57 @@ def sub_add_dummy(b, max_nv, max_nvl, max_ne, max_nel):
                ptr(o["node_ptr"]), ptr(o["edge_ptr"]), ptr(o["src"]), ptr(o["dst"]),
                ptr(o["vid"]), ptr(o["vlabel"]), ptr(o["v_is_dummy"]),
                ptr(o["eid"]), ptr(o["elabel"]), ptr(o["e_is_dummy"]), ptr(o["e_is_reversed"]), _stream())
+    return o
+
+
+def sub_conjugate(b, id_bound=None):
+    """edge-to-vertex transform of a subgraph-isomorphism batch (``convert_conjugate_graph``, utils/graph.py:77-175,
+    as applied by ``convert_to_conjugate``, train.py:564-593): edges with equal ``eid`` merge into one vertex, duplicate
+    ``(eid[e'], vlabel[shared], eid[e])`` conjugate edges are dropped keeping the first, and the node / edge attribute
+    names are swapped (:155-165).  ``id_bound``: exclusive upper bound of the edge ids (``max_nge`` after augmentation,
+    i.e. ``process_model_config(...)["max_nge"]``); read from the data (one extra sync) when omitted."""
+    require_cuda(b["src"], "batch")
+    L = lib()
+    dev = b["src"].device
+    B, N, E = int(b["num_graphs"]), int(b["vlabel"].numel()), int(b["src"].numel())
+    if id_bound is None:
+        id_bound = int(b["eid"].max().item()) + 1 if E else 1
+    id_bound = max(int(id_bound), 1)
+    csr_in = build_csr(b["dst"], b["src"], N, heavy_threshold=0)
+    ws_bytes = L.size("dn4gl_sub_conj_workspace_bytes", B, E, id_bound)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ev, cand_off = _empty_i32(max(E, 1), dev), _empty_i32(E + 1, dev)
+    o_node_ptr, o_edge_ptr = _empty_i32(B + 1, dev), _empty_i32(B + 1, dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.call("dn4gl_sub_conj_count", B, ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["eid"]), N, E, id_bound,
+           ptr(csr_in.row_ptr), ptr(ev), ptr(cand_off), ptr(o_node_ptr), ptr(ws), ws_bytes, ptr(err), _stream())
+    sizes = torch.stack([o_node_ptr[-1], cand_off[-1], err[0]]).cpu()           # sync 1: V', ncand
+    V2, ncand = int(sizes[0]), int(sizes[1])
+    if int(sizes[2]) != 0:
+        raise RuntimeError("sub_conjugate: an edge id lies outside [0, id_bound=%d)" % id_bound)
+    slots = 2
+    while slots < 2 * ncand:
+        slots *= 2
+    table = torch.empty(slots, dtype=torch.int64, device=dev)
+    keep_scan = _empty_i32(ncand + 1, dev)
+    sws_bytes = L.size("dn4gl_scan_workspace_bytes", ncand + 1)
+    sws = torch.empty(sws_bytes, dtype=torch.uint8, device=dev)
+    L.call("dn4gl_sub_conj_mark", B, ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["vlabel"]), E, ptr(csr_in.row_ptr),
+           ptr(csr_in.eid), ptr(ev), ptr(cand_off), ncand, ptr(table), slots, ptr(keep_scan), ptr(o_edge_ptr),
+           ptr(sws), sws_bytes, _stream())
+    E2 = int(o_edge_ptr[-1].item())                                              # sync 2: E'
+    o = dict(num_graphs=B, node_ptr=o_node_ptr, edge_ptr=o_edge_ptr, src=_empty_i32(E2, dev), dst=_empty_i32(E2, dev),
+             v_origin=_empty_i32(V2, dev), e_shared=_empty_i32(E2, dev))
+    L.call("dn4gl_sub_conj_fill", B, ptr(b["src"]), E, id_bound, ptr(csr_in.row_ptr), ptr(csr_in.eid), ptr(ev),
+           ptr(cand_off), ptr(keep_scan), ptr(o["src"]), ptr(o["dst"]), ptr(o["v_origin"]), ptr(o["e_shared"]),
+           ptr(ws), ws_bytes, _stream())
+    vo, es = o["v_origin"].long(), o["e_shared"].long()
+    for ek, vk in (("eid", "vid"), ("elabel", "vlabel"), ("e_is_dummy", "v_is_dummy"), ("e_is_reversed", "v_is_reversed")):
+        if ek in b:
+            o[vk] = b[ek][vo]
+    for vk, ek in (("vid", "eid"), ("vlabel", "elabel"), ("v_is_dummy", "e_is_dummy")):
+        if vk in b:
+            o[ek] = b[vk][es]
     return o
 
 

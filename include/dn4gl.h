@@ -127,6 +127,33 @@ int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const int32_t *e
                             int32_t *o_src, int32_t *o_dst, int32_t *o_v_origin, int32_t *o_e_shared,
                             void *ws, size_t ws_bytes, void *stream);
 
+/* subgraph-isomorphism flavour, replaces convert_conjugate_graph, DGL branch (subgraph_isomorphism/utils/graph.py:
+ * 77-175; igraph branch :177-267 is the same rule), called per graph by convert_to_conjugate (train.py:564-593).
+ * Edges with equal eid merge into one conjugate vertex (numbered by ascending id, attributes of the first such edge);
+ * candidate conjugate edges (e' -> e), e in edge order, e' ascending over the in-edges of src(e), are kept on the FIRST
+ * occurrence of the key (eid[e'], vlabel[src e], eid[e]).  Three phases (two data-dependent sizes):
+ *   _count: in_ptr = row_ptr of dn4gl_build_csr(key=dst).  id_bound > every eid.  Writes ev[E] (conjugate vertex of
+ *           every edge, global numbering), cand_off[E+1], o_node_ptr[B+1].  Host then reads V' = o_node_ptr[B] and
+ *           ncand = cand_off[E].  ws from dn4gl_sub_conj_workspace_bytes and must be kept untouched until _fill.
+ *   _mark : table = table_slots 64-bit words (power of two >= 2 * ncand), keep_scan[ncand+1]; ws here is a SEPARATE
+ *           scan workspace of dn4gl_scan_workspace_bytes(ncand + 1).  Writes o_edge_ptr[B+1]; E' = o_edge_ptr[B].
+ *   _fill : o_src/o_dst[E'] (global conjugate vertex ids), o_v_origin[V'] (original edge of each conjugate vertex),
+ *           o_e_shared[E'] (shared original vertex of each conjugate edge), in exactly the reference's order.
+ * err_flag receives DN4GL_ELIMIT if an eid falls outside [0, id_bound).                                          */
+size_t dn4gl_sub_conj_workspace_bytes(int32_t B, int64_t E, int32_t id_bound);
+int dn4gl_sub_conj_count(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *eid,
+                         int64_t N, int64_t E, int32_t id_bound, const int32_t *in_ptr, int32_t *ev,
+                         int32_t *cand_off, int32_t *o_node_ptr, void *ws, size_t ws_bytes,
+                         int32_t *err_flag, void *stream);
+int dn4gl_sub_conj_mark(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *vlabel,
+                        int64_t E, const int32_t *in_ptr, const int32_t *in_eid, const int32_t *ev,
+                        const int32_t *cand_off, int64_t ncand, void *table, int64_t table_slots,
+                        int32_t *keep_scan, int32_t *o_edge_ptr, void *ws, size_t ws_bytes, void *stream);
+int dn4gl_sub_conj_fill(int32_t B, const int32_t *src, int64_t E, int32_t id_bound, const int32_t *in_ptr,
+                        const int32_t *in_eid, const int32_t *ev, const int32_t *cand_off,
+                        const int32_t *keep_scan, int32_t *o_src, int32_t *o_dst, int32_t *o_v_origin,
+                        int32_t *o_e_shared, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- a3: PyG read_tu_data canonicalisation ------------------------------------------------- */
 /* remove_self_loops + coalesce [torch-geometric 2.0.2 read_tu_data, called from
  * graph_classification/graph_neural_networks/dataset.py:151]: given the edge list's destinations

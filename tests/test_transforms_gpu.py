@@ -103,6 +103,63 @@ def test_sub_add_dummy_golden_appB2(device):
     assert d["vid"].cpu().tolist() == [0, 1, 2, 4] and d["vlabel"].cpu().tolist() == [0, 1, 0, 2]
 
 
+SUB_CONJ_KEYS = ("node_ptr", "edge_ptr", "src", "dst", "v_origin", "e_shared", "vid", "vlabel", "v_is_dummy", "v_is_reversed",
+                 "eid", "elabel", "e_is_dummy")
+
+
+@pytest.mark.parametrize("shape,bs,dummy", [("small", 64, True), ("small", 512, True), ("small", 200, False), ("large", 16, True),
+                                            ("large", 8, False)])
+def test_sub_conjugate(device, shape, bs, dummy):
+    """a5: convert_conjugate_graph (utils/graph.py:77-175) on pattern and graph batches, with and without the dummy
+    augmentation (whose n^2 equal-key candidates must collapse to one edge), bit-exact incl. edge order."""
+    from dummynode4graphlearning_b200 import transforms as T
+    from oracle import transforms as O
+
+    p, g, _ = synth.counting_batch(shape, bs, seed=2)
+    cfg = synth.counting_config(shape)
+    for b, (nv, nvl, ne, nel) in ((p, (cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])),
+                                  (g, (cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"]))):
+        ob = O.sub_add_dummy(b, nv, nvl, ne, nel) if dummy else b
+        db = T.to_device(ob, device)
+        keys = [k for k in SUB_CONJ_KEYS if k in O.sub_conjugate(ob)]
+        _eq(T.sub_conjugate(db, id_bound=ne + 2), O.sub_conjugate(ob), keys)
+        _eq(T.sub_conjugate(db), O.sub_conjugate(ob), keys)       # id bound read from the data
+
+
+def test_sub_conjugate_duplicate_ids_and_empty_graphs(device):
+    """repeated edge ids inside a graph (vertex merge + key dedupe across different shared vertices), a graph without
+    edges in the middle of the batch, and the App. B second golden vector."""
+    from dummynode4graphlearning_b200 import transforms as T
+    from oracle import transforms as O
+
+    rng = np.random.default_rng(5)
+    graphs = []
+    for n, m in ((6, 14), (3, 0), (9, 30), (1, 0), (5, 12)):
+        s = rng.integers(0, n, m); d = rng.integers(0, n, m)
+        graphs.append((s, d, rng.integers(0, 2, n), rng.integers(0, 3, m), rng.integers(0, max(m // 3, 1), m)))
+    node_ptr = np.cumsum([0] + [len(g[2]) for g in graphs]).astype(np.int32)
+    edge_ptr = np.cumsum([0] + [len(g[0]) for g in graphs]).astype(np.int32)
+    b = dict(num_graphs=len(graphs), node_ptr=node_ptr, edge_ptr=edge_ptr,
+             src=np.concatenate([g[0] + node_ptr[i] for i, g in enumerate(graphs)]).astype(np.int32),
+             dst=np.concatenate([g[1] + node_ptr[i] for i, g in enumerate(graphs)]).astype(np.int32),
+             vid=np.concatenate([np.arange(len(g[2])) for g in graphs]).astype(np.int32),
+             vlabel=np.concatenate([g[2] for g in graphs]).astype(np.int32),
+             elabel=np.concatenate([g[3] for g in graphs]).astype(np.int32),
+             eid=np.concatenate([g[4] for g in graphs]).astype(np.int32))
+    ref = O.sub_conjugate(b)
+    _eq(T.sub_conjugate(T.to_device(b, device)), ref, [k for k in SUB_CONJ_KEYS if k in ref])
+
+    g = dict(num_graphs=1, node_ptr=np.array([0, 3], np.int32), edge_ptr=np.array([0, 3], np.int32),
+             src=np.array([0, 1, 1], np.int32), dst=np.array([1, 2, 2], np.int32), vid=np.arange(3, dtype=np.int32),
+             vlabel=np.array([0, 1, 0], np.int32), eid=np.arange(3, dtype=np.int32), elabel=np.array([0, 1, 0], np.int32))
+    c = T.sub_conjugate(T.sub_add_dummy(T.to_device(g, device), 4, 2, 6, 2), id_bound=8)
+    assert c["vid"].cpu().tolist() == [0, 1, 2, 6, 7] and c["vlabel"].cpu().tolist() == [0, 1, 0, 2, 3]
+    assert list(zip(c["src"].cpu().tolist(), c["dst"].cpu().tolist())) == [(4, 0), (0, 1), (4, 1), (0, 2), (4, 2), (4, 3), (0, 3),
+                                                                         (4, 3), (1, 3), (2, 3), (3, 4)]
+    assert c["eid"].cpu().tolist() == [0, 1, 1, 1, 1, 0, 1, 1, 2, 2, 4]
+    assert c["e_is_dummy"].cpu().tolist() == [0] * 10 + [1] and c["v_is_reversed"].cpu().tolist() == [0, 0, 0, 0, 1]
+
+
 @pytest.mark.parametrize("case", ["mutag_dummy", "proteins_conj", "dups"])
 def test_pyg_canonicalize(device, case):
     from dummynode4graphlearning_b200 import transforms as T
