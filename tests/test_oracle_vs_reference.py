@@ -1,0 +1,88 @@
+"""Live pin of the oracle: executes the UNMODIFIED reference from /root/reference under oracle/shims on fresh seeds
+(not the committed golden ones) and compares with the standalone restatement (oracle/transforms.py, oracle/models.py).
+Build container only -- skipped wherever /root/reference does not exist (e.g. the GPU box)."""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from dummynode4graphlearning_b200 import synth
+from dummynode4graphlearning_b200.transforms import process_model_config
+from helpers import assert_close_rel, batches_equal, oracle_cfg
+from oracle import models as OM
+from oracle import transforms as OT
+
+pytestmark = pytest.mark.reference_live
+
+TU_KEYS = ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel", "vid", "eid", "v_is_dummy", "e_is_dummy")
+SUB_KEYS = ("node_ptr", "edge_ptr", "src", "dst", "vid", "vlabel", "v_is_dummy", "eid", "elabel", "e_is_dummy", "e_is_reversed")
+CONJ_KEYS = ("node_ptr", "edge_ptr", "src", "dst", "vid", "vlabel", "v_is_dummy", "v_is_reversed", "eid", "elabel", "e_is_dummy")
+
+
+@pytest.mark.parametrize("shape,nb,seed", [("mutag", 9, 101), ("proteins", 5, 102), ("mutag", 3, 103)])
+def test_tu_transforms_live(shape, nb, seed):
+    from oracle import ref_drive as rd
+    b = synth.tu_batch(shape, nb, seed=seed)
+    ref_dummy = rd.ref_tu_load(b, True)
+    batches_equal(OT.tu_add_dummy(b), rd.igraphs_to_batch(ref_dummy), [k for k in TU_KEYS if k in ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel", "v_is_dummy", "e_is_dummy")])
+    ref_conj = rd.igraphs_to_batch(rd.ref_tu_conjugate(ref_dummy))
+    got = OT.tu_conjugate(OT.tu_add_dummy(b))
+    batches_equal(got, ref_conj, [k for k in TU_KEYS if k in ref_conj and k in got])
+    ref_line = rd.igraphs_to_batch(rd.ref_tu_conjugate(rd.ref_tu_load(b, False)))
+    got = OT.tu_conjugate(b)
+    batches_equal(got, ref_line, [k for k in ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel") if k in ref_line])
+
+
+@pytest.mark.parametrize("shape,bs,seed", [("small", 5, 111), ("small", 3, 112)])
+def test_sub_transforms_live(shape, bs, seed):
+    from oracle import ref_drive as rd
+    p, g, _ = synth.counting_batch(shape, bs, seed=seed)
+    cfg = synth.counting_config(shape)
+    rp, rg = rd.ref_sub_add_dummy(p, g, cfg)
+    pd_ = OT.sub_add_dummy(p, cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])
+    gd_ = OT.sub_add_dummy(g, cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"])
+    batches_equal(pd_, rp, SUB_KEYS)
+    batches_equal(gd_, rg, SUB_KEYS)
+    batches_equal(OT.sub_conjugate(pd_), rd.ref_sub_conjugate(rp), CONJ_KEYS)
+    batches_equal(OT.sub_conjugate(gd_), rd.ref_sub_conjugate(rg), CONJ_KEYS)
+    c = dict(cfg, add_rev=False, add_dummy=True, convert_conj=True)
+    assert process_model_config(c) == rd.ref_process_model_config(c)
+
+
+@pytest.mark.parametrize("tag,name,over", [
+    ("live/RGIN", "RGIN", dict(hid_dim=16, pred_hid_dim=16)),
+    ("live/DMPNN", "DMPNN", dict(hid_dim=16, pred_hid_dim=16, node_pred=True, edge_pred=True, pred_return_weights="node,edge")),
+])
+def test_counting_models_live(tag, name, over):
+    """the reference's own RGIN / DMPNN classes (fake-DGL graph drives their message / update UDFs) vs the functional
+    restatement: forward tensors, loss and every parameter gradient."""
+    import torch.nn.functional as F
+    from oracle import ref_drive as rd
+    p, g, counts = synth.counting_batch("small", 6, seed=121)
+    cfg = dict(synth.counting_config("small"), add_dummy=True)
+    mc = process_model_config(cfg)
+    pd_ = OT.sub_add_dummy(p, cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])
+    gd_ = OT.sub_add_dummy(g, cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"])
+    kw = rd.counting_kwargs({k: v for k, v in mc.items() if k.startswith("max_")}, **over)
+    model = rd.ref_counting_model(name, kw, seed=zlib.crc32(tag.encode()) % 1000)
+    o = model(rd.dgl_batched(pd_), rd.dgl_batched(gd_))
+    c = torch.from_numpy(counts).float().view(-1, 1)
+    loss = F.mse_loss(F.leaky_relu(o["pred_c"], 0.01), c)
+    loss.backward()
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    out = OM.counting_model(sd, pd_, gd_, oracle_cfg(name, kw))
+    for k in ("pred_c", "p_v_rep", "g_v_rep", "g_e_rep"):
+        if o[k] is not None:
+            assert_close_rel(out[k], o[k].detach(), 1e-6, k)
+    mine = OM.counting_loss(out, torch.from_numpy(counts), rep_reg_w=0.0)
+    assert_close_rel(mine, loss.detach(), 1e-6, "loss")
+    mine.backward()
+    for n, pp in model.named_parameters():
+        if pp.grad is None:
+            continue
+        got = sd[n].grad
+        alias = n.replace("g_rep_net", "p_rep_net", 1) if n.startswith("g_rep_net") else None
+        if alias in sd and sd[alias].grad is not None:
+            got = got + sd[alias].grad if got is not None else sd[alias].grad
+        assert_close_rel(got, pp.grad, 1e-5, "grad " + n)
