@@ -1,0 +1,910 @@
+// libdn4gl.so -- the dense per-node / per-edge MLP stages on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// The MLPs on the path (gconv.py:190-196 Linear,BN,ReLU,Linear,BN,ReLU; rgin.py:52 / dmpnn.py:47,55 Linear,act,Linear)
+// multiply a tall matrix of node / edge rows (1e4..1e7 x D) by a tiny D x D weight: 8..64 flop per byte, i.e. above what
+// the fp32 FMA pipe delivers at full HBM rate, far below the tensor pipe.  Each "stage" kernel therefore streams row
+// tiles of 128 rows ONCE through shared memory, does the GEMM as 3xTF32 (error-compensated split x = hi + lo, three
+// tcgen05.mma.kind::tf32 passes hi*hi + lo*hi + hi*lo accumulated in fp32 in tensor memory; products are exact to
+// ~2^-21) and fuses everything elementwise around it:
+//
+//   dn4gl_lin_fwd_f32   Y = act(bn_in(X)) W^T + b        prologue: BatchNorm-apply + activation of the PREVIOUS stage
+//                                                        epilogue: bias, per-channel batch statistics of Y -> the
+//                                                        BatchNorm record {mean, rstd, gamma*rstd, beta} (+ running stats)
+//   dn4gl_lin_bwd_f32   gX = (gY W) * act'(bn_in(X)),  dW = gY^T act(bn_in(X)),  db = colsum gY
+//                                                        prologue: BatchNorm backward of the stage output (gY from the
+//                                                        upstream gradient, Y and the two batch sums), epilogue:
+//                                                        activation mask + the batch sums the previous stage needs;
+//                                                        dW accumulates in tensor memory over all tiles of the CTA.
+//
+// Operand tiles live in shared memory in the canonical 128-byte-swizzled layout ("panels" of 32 floats x rows, 16-byte
+// chunk index XOR (row & 7)); the same physical tile is read K-major (rows = M) by the data GEMM and MN-major
+// (rows = K) by the weight-gradient GEMM.  One thread issues the MMAs; completion arrives on an mbarrier through
+// tcgen05.commit; accumulators come back with tcgen05.ld (32 lanes x 32 columns per warp) and leave through a staging
+// tile so that global stores are 128-bit and coalesced.  All reductions are fixed-order (no float atomics).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_THREADS = 128;          // 4 warps <-> the 128 TMEM lanes
+constexpr uint32_t PANEL128 = 128u * 128u;   // bytes of one 128-row panel (32 floats per row)
+
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ bool aligned16_dev(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_alloc(uint32_t smem_dst, uint32_t cols) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t cols) {    // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// this warp's 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = lane = accumulator row)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_32B = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = LAYOUT_SW128) {
+    uint64_t d = static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    d |= static_cast<uint64_t>(layout) << 61;
+    return d;
+}
+// MN-major operand (the contraction index runs over tile ROWS): 32-bit types must use the 128B-swizzle with 32-byte
+// base (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B; atoms of 32 floats x 4 rows, Swizzle<2,5,2> on byte addresses).
+// LBO = stride between 32-float blocks of the MN index (a panel), SBO = stride between groups of 4 rows (512 B).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t panel_bytes) {
+    return make_desc(saddr, panel_bytes, 512u, LAYOUT_SW128_32B);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=b=tf32 [7,10)/[10,13), a/b major (1 = MN)
+// [15]/[16], N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// byte offset of 16-byte chunk `chunk` (4 floats) of row `row` in a swizzled tile whose panels hold `panel_rows` rows
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk, int panel_rows) {
+    return static_cast<uint32_t>(chunk >> 3) * static_cast<uint32_t>(panel_rows * 128) + static_cast<uint32_t>(row) * 128u +
+           static_cast<uint32_t>(((chunk & 7) ^ (row & 7)) << 4);
+}
+// the same tile shape in the MN-major swizzle: 32-byte unit index XOR (row & 3)
+__device__ __forceinline__ uint32_t tile_off_mn(int row, int chunk, int panel_rows) {
+    return static_cast<uint32_t>(chunk >> 3) * static_cast<uint32_t>(panel_rows * 128) + static_cast<uint32_t>(row) * 128u +
+           static_cast<uint32_t>(((chunk & 7) ^ ((row & 3) << 1)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4 &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128s(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+// x = hi + lo (+ O(2^-22 |x|)), both exactly representable in tf32 (round-to-nearest split)
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    const float r = x - hi;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+    lo = __uint_as_float(l);
+}
+__device__ __forceinline__ void store_split(uint32_t hi_base, uint32_t lo_base, uint32_t off, const float4 &v) {
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    sts128(hi_base + off, h);
+    sts128(lo_base + off, l);
+}
+// the same split value into two differently swizzled tiles (K-major copy + MN-major copy)
+__device__ __forceinline__ void store_split2(uint32_t hi_a, uint32_t lo_a, uint32_t off_a, uint32_t hi_b, uint32_t lo_b,
+                                             uint32_t off_b, const float4 &v) {
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    sts128(hi_a + off_a, h); sts128(lo_a + off_a, l);
+    sts128(hi_b + off_b, h); sts128(lo_b + off_b, l);
+}
+// 4 consecutive floats of a row-major (rows x ncols, leading dimension ncols) matrix, zero beyond ncols
+__device__ __forceinline__ float4 load_chunk(const float *__restrict__ base, int64_t row, int ncols, int c, bool vec) {
+    float4 v = zero4();
+    const int c0 = 4 * c;
+    if (c0 >= ncols) return v;
+    const float *p = base + row * ncols + c0;
+    if (vec) return __ldg(reinterpret_cast<const float4 *>(p));
+    v.x = __ldg(p);
+    if (c0 + 1 < ncols) v.y = __ldg(p + 1);
+    if (c0 + 2 < ncols) v.z = __ldg(p + 2);
+    if (c0 + 3 < ncols) v.w = __ldg(p + 3);
+    return v;
+}
+__device__ __forceinline__ void store_chunk(float *__restrict__ base, int64_t row, int ncols, int c, const float4 &v, bool vec) {
+    const int c0 = 4 * c;
+    if (c0 >= ncols) return;
+    float *p = base + row * ncols + c0;
+    if (vec) { *reinterpret_cast<float4 *>(p) = v; return; }
+    p[0] = v.x;
+    if (c0 + 1 < ncols) p[1] = v.y;
+    if (c0 + 2 < ncols) p[2] = v.z;
+    if (c0 + 3 < ncols) p[3] = v.w;
+}
+// per-channel vector (length n) -> the 4 channels of chunk c, zero beyond n
+__device__ __forceinline__ float4 load_vec4(const float *__restrict__ v, int n, int c) {
+    float4 r = zero4();
+    if (v == nullptr) return r;
+    const int c0 = 4 * c;
+    if (c0 < n) r.x = __ldg(v + c0);
+    if (c0 + 1 < n) r.y = __ldg(v + c0 + 1);
+    if (c0 + 2 < n) r.z = __ldg(v + c0 + 2);
+    if (c0 + 3 < n) r.w = __ldg(v + c0 + 3);
+    return r;
+}
+
+__device__ __forceinline__ float act_f(float x, int act, float slope) {
+    if (act == DN4GL_ACT_RELU) return fmaxf(x, 0.f);
+    if (act == DN4GL_ACT_LEAKY_RELU) return x > 0.f ? x : slope * x;
+    return x;
+}
+__device__ __forceinline__ float dact_f(float x, int act, float slope) {   // derivative at the pre-activation x
+    if (act == DN4GL_ACT_RELU) return x > 0.f ? 1.f : 0.f;
+    if (act == DN4GL_ACT_LEAKY_RELU) return x > 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+// BatchNorm record of one normalisation over C channels: rec[0:C) mean, [C:2C) rstd, [2C:3C) k = gamma*rstd, [3C:4C) beta
+struct Bn4 {
+    float4 mean, rstd, k, beta;
+};
+__device__ __forceinline__ Bn4 load_bn4(const float *rec, int C, int c) {
+    Bn4 b;
+    b.mean = load_vec4(rec, C, c);
+    b.rstd = load_vec4(rec == nullptr ? nullptr : rec + C, C, c);
+    b.k = load_vec4(rec == nullptr ? nullptr : rec + 2 * C, C, c);
+    b.beta = load_vec4(rec == nullptr ? nullptr : rec + 3 * C, C, c);
+    return b;
+}
+__device__ __forceinline__ float4 bn_apply(const float4 &x, const Bn4 &b) {
+    return make_float4(fmaf(x.x - b.mean.x, b.k.x, b.beta.x), fmaf(x.y - b.mean.y, b.k.y, b.beta.y),
+                       fmaf(x.z - b.mean.z, b.k.z, b.beta.z), fmaf(x.w - b.mean.w, b.k.w, b.beta.w));
+}
+
+// sum over the lanes of a warp that hold the same chunk (lanes l, l + CH, l + 2CH, ...), fixed butterfly
+template <int CH>
+__device__ __forceinline__ void chunk_allreduce(float4 &v) {
+#pragma unroll
+    for (int o = CH; o < 32; o <<= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward stage
+// ------------------------------------------------------------------------------------------------------------------
+struct LinFwdArgs {
+    const float *X; int64_t N; int K;
+    const float *in_bn; int in_act; float in_slope;
+    const float *W; const float *bias; int M;
+    float *Y;
+    const float *gamma; const float *beta; float eps; float momentum;
+    float *bn_out; float *run_mean; float *run_var; long long *nbt;
+    float *part; int *counter;
+    int num_tiles;
+};
+
+template <int KP, int MP>
+__global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int PK = KP / 32, PM = MP / 32;
+    constexpr uint32_t A_BYTES = PK * PANEL128, B_BYTES = PK * MP * 128u;
+    const uint32_t base = (s_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sAh = base, sAl = sAh + A_BYTES, sBh = sAl + A_BYTES, sBl = sBh + B_BYTES, sStage = sBl + B_BYTES;
+    __shared__ __align__(8) uint64_t bar_mem;
+    __shared__ uint32_t tmem_ptr;
+    __shared__ int is_last;
+    __shared__ float red[4][MP * 2];
+    __shared__ float shift_s[MP];
+    __shared__ double fin[TC_THREADS * 2];
+
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const uint32_t bar = s_u32(&bar_mem);
+    if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (w == 0) tc_alloc(s_u32(&tmem_ptr), MP);
+    // weights: W (M x K) row-major = K-major B operand; zero-padded to MP x KP, split once
+    const bool vecW = (a.K % 4 == 0) && aligned16_dev(a.W);
+    for (int i = t; i < MP * (KP / 4); i += TC_THREADS) {
+        const int m = i / (KP / 4), c = i % (KP / 4);
+        const float4 v = (m < a.M) ? load_chunk(a.W, m, a.K, c, vecW) : zero4();
+        store_split(sBh, sBl, tile_off(m, c, MP), v);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_ptr;
+
+    constexpr int CH = KP / 4, RP = TC_THREADS / CH;       // input: chunks per row, rows per pass (CH passes)
+    constexpr int CHo = MP / 4, RPo = TC_THREADS / CHo;    // output
+    const int c_in = t % CH, r_in = t / CH, c_out = t % CHo, r_out = t / CHo;
+    const bool vecX = (a.K % 4 == 0) && aligned16_dev(a.X), vecY = (a.M % 4 == 0) && aligned16_dev(a.Y);
+    const bool has_bn_in = a.in_bn != nullptr, stats = a.bn_out != nullptr;
+    const Bn4 bi = load_bn4(a.in_bn, a.K, c_in);
+    const float4 bias4 = load_vec4(a.bias, a.M, c_out);
+    float4 S1 = zero4(), S2 = zero4(), shift4 = zero4();
+    bool have_shift = false;
+    float n_cta = 0.f;
+    constexpr uint32_t IDESC = make_idesc(128, MP, 0, 0);
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int64_t row0 = static_cast<int64_t>(tile) * 128;
+        // ---- prologue: X tile -> bn/act -> hi/lo operand tiles
+#pragma unroll 4
+        for (int i = 0; i < CH; ++i) {
+            const int r = r_in + RP * i;
+            const int64_t gr = row0 + r;
+            float4 v = zero4();
+            if (gr < a.N) v = load_chunk(a.X, gr, a.K, c_in, vecX);
+            if (has_bn_in) v = bn_apply(v, bi);
+            v.x = act_f(v.x, a.in_act, a.in_slope); v.y = act_f(v.y, a.in_act, a.in_slope);
+            v.z = act_f(v.z, a.in_act, a.in_slope); v.w = act_f(v.w, a.in_act, a.in_slope);
+            store_split(sAh, sAl, tile_off(r, c_in, 128), v);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < KP / 8; ++j) {
+                const uint32_t aoff = (j >> 2) * PANEL128 + (j & 3) * 32u, boff = (j >> 2) * (MP * 128u) + (j & 3) * 32u;
+                const uint64_t ah = make_desc(sAh + aoff, 16, 1024), al = make_desc(sAl + aoff, 16, 1024);
+                const uint64_t bh = make_desc(sBh + boff, 16, 1024), bl = make_desc(sBl + boff, 16, 1024);
+                tc_mma_tf32(tmem, ah, bh, IDESC, acc);
+                acc = 1;
+                tc_mma_tf32(tmem, al, bh, IDESC, 1);
+                tc_mma_tf32(tmem, ah, bl, IDESC, 1);
+            }
+            tc_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        __syncwarp();
+        tc_fence_after();
+        // ---- accumulators -> staging tile (thread = row)
+#pragma unroll
+        for (int cb = 0; cb < PM; ++cb) {
+            float v[32];
+            tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                sts128(sStage + tile_off(t, cb * 8 + q, 128), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- cooperative epilogue (thread = fixed 4 channels): bias, statistics, coalesced 128-bit stores
+        if (stats && !have_shift) {
+            const float4 s = lds128s(sStage + tile_off(0, c_out, 128));
+            shift4 = make_float4(s.x + bias4.x, s.y + bias4.y, s.z + bias4.z, s.w + bias4.w);
+            have_shift = true;
+        }
+#pragma unroll 4
+        for (int i = 0; i < CHo; ++i) {
+            const int r = r_out + RPo * i;
+            const int64_t gr = row0 + r;
+            if (gr < a.N) {
+                float4 v = lds128s(sStage + tile_off(r, c_out, 128));
+                v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                store_chunk(a.Y, gr, a.M, c_out, v, vecY);
+                if (stats) {
+                    const float dx = v.x - shift4.x, dy = v.y - shift4.y, dz = v.z - shift4.z, dw = v.w - shift4.w;
+                    S1.x += dx; S1.y += dy; S1.z += dz; S1.w += dw;
+                    S2.x = fmaf(dx, dx, S2.x); S2.y = fmaf(dy, dy, S2.y); S2.z = fmaf(dz, dz, S2.z); S2.w = fmaf(dw, dw, S2.w);
+                }
+            }
+        }
+        const int64_t left = a.N - row0;
+        n_cta += left < 128 ? static_cast<float>(left) : 128.f;
+    }
+
+    if (stats) {
+        // per-CTA partial (n, shift, S1, S2) per channel, then the last CTA merges all partials in a fixed order
+        chunk_allreduce<CHo>(S1);
+        chunk_allreduce<CHo>(S2);
+        if (lane < (CHo < 32 ? CHo : 32)) {
+            float *p = &red[w][0];
+            const int c0 = 4 * c_out;
+            p[c0] = S1.x; p[c0 + 1] = S1.y; p[c0 + 2] = S1.z; p[c0 + 3] = S1.w;
+            p[MP + c0] = S2.x; p[MP + c0 + 1] = S2.y; p[MP + c0 + 2] = S2.z; p[MP + c0 + 3] = S2.w;
+        }
+        if (r_out == 0) {
+            const int c0 = 4 * c_out;
+            shift_s[c0] = shift4.x; shift_s[c0 + 1] = shift4.y; shift_s[c0 + 2] = shift4.z; shift_s[c0 + 3] = shift4.w;
+        }
+        __syncthreads();
+        if (t < MP) {
+            // CHo < 32: every warp saw every chunk; CHo == 32: likewise (one row per warp per pass)
+            const float s1 = red[0][t] + red[1][t] + red[2][t] + red[3][t];
+            const float s2 = red[0][MP + t] + red[1][MP + t] + red[2][MP + t] + red[3][MP + t];
+            float *p = a.part + (static_cast<size_t>(blockIdx.x) * MP + t) * 4;
+            p[0] = n_cta; p[1] = shift_s[t]; p[2] = s1; p[3] = s2;
+        }
+        __threadfence();
+        __syncthreads();
+        if (t == 0) is_last = (atomicAdd(a.counter, 1) == static_cast<int>(gridDim.x) - 1);
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            constexpr int G = TC_THREADS / MP;     // partial-sum groups per channel
+            const int c = t % MP, g = t / MP;
+            const volatile float *part = a.part;
+            const double n0 = part[(0 * MP + c) * 4], k0 = part[(0 * MP + c) * 4 + 1];
+            const double kstar = k0 + static_cast<double>(part[(0 * MP + c) * 4 + 2]) / n0;   // mean of CTA 0
+            double A1 = 0.0, A2 = 0.0;
+            for (int i = g; i < static_cast<int>(gridDim.x); i += G) {
+                const volatile float *p = part + (static_cast<size_t>(i) * MP + c) * 4;
+                const double n = p[0];
+                if (n > 0.0) {
+                    const double s1 = p[2], s2 = p[3];
+                    const double mean_i = static_cast<double>(p[1]) + s1 / n, m2_i = s2 - s1 * s1 / n;
+                    const double d = mean_i - kstar;
+                    A1 += n * d;
+                    A2 += (m2_i > 0.0 ? m2_i : 0.0) + n * d * d;
+                }
+            }
+            fin[t * 2] = A1; fin[t * 2 + 1] = A2;
+            __syncthreads();
+            if (g == 0 && c < a.M) {
+                double a1 = 0.0, a2 = 0.0;
+                for (int gg = 0; gg < G; ++gg) { a1 += fin[(gg * MP + c) * 2]; a2 += fin[(gg * MP + c) * 2 + 1]; }
+                const double Nd = static_cast<double>(a.N);
+                const double mean = kstar + a1 / Nd;
+                double m2 = a2 - a1 * a1 / Nd;
+                if (m2 < 0.0) m2 = 0.0;
+                const double var = m2 / Nd;
+                const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+                const float gam = a.gamma ? a.gamma[c] : 1.f, bet = a.beta ? a.beta[c] : 0.f;
+                a.bn_out[c] = static_cast<float>(mean);
+                a.bn_out[a.M + c] = rstd;
+                a.bn_out[2 * a.M + c] = gam * rstd;
+                a.bn_out[3 * a.M + c] = bet;
+                if (a.run_mean) a.run_mean[c] = (1.f - a.momentum) * a.run_mean[c] + a.momentum * static_cast<float>(mean);
+                if (a.run_var) {
+                    const double unb = a.N > 1 ? m2 / (Nd - 1.0) : var;
+                    a.run_var[c] = (1.f - a.momentum) * a.run_var[c] + a.momentum * static_cast<float>(unb);
+                }
+            }
+            if (t == 0) {
+                if (a.nbt) *a.nbt += 1;
+                *a.counter = 0;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (w == 0) tc_dealloc(tmem, MP);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward stage
+// ------------------------------------------------------------------------------------------------------------------
+struct LinBwdArgs {
+    const float *G; const float *Yo; int64_t N; int M;
+    const float *bn; const float *sums; int g_masked;
+    const float *W; int K;
+    const float *X; const float *in_bn; int in_act; float in_slope;
+    float *GX;
+    float *part;
+    int num_tiles;
+};
+
+template <int KP, int MP>
+__global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int PK = KP / 32, PM = MP / 32;
+    constexpr uint32_t G_BYTES = PM * PANEL128, X_BYTES = PK * PANEL128, W_BYTES = PK * MP * 128u;
+    const uint32_t base = (s_u32(smem_raw) + 1023u) & ~1023u;
+    // gY is kept twice: MN-major copy (weight gradient, contraction over rows) first -- its M = 128 MMA reads 4 panels
+    // from each base, so everything it can touch stays inside the allocation -- then the K-major copy (data gradient)
+    const uint32_t sGmh = base, sGml = sGmh + G_BYTES, sGh = sGml + G_BYTES, sGl = sGh + G_BYTES;
+    const uint32_t sXh = sGl + G_BYTES, sXl = sXh + X_BYTES, sWh = sXl + X_BYTES, sWl = sWh + W_BYTES;
+    const uint32_t sStage = sGh;        // the K-major gY copy is dead once the tile's MMAs have completed
+    static_assert(2 * PM >= PK, "staging tile must fit the K-major gY copy");
+    __shared__ __align__(8) uint64_t bar_mem;
+    __shared__ uint32_t tmem_ptr;
+    float (*red)[MP + 2 * KP] = reinterpret_cast<float (*)[MP + 2 * KP]>(smem_raw + (sXh - s_u32(smem_raw)));   // used after the last MMA
+
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const uint32_t bar = s_u32(&bar_mem);
+    constexpr uint32_t TCOLS = 2 * KP;
+    if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (w == 0) tc_alloc(s_u32(&tmem_ptr), TCOLS);
+    const bool want_gx = a.GX != nullptr;
+    // weights as they are stored: rows m (the data GEMM's K), k contiguous (its N) -> MN-major B operand
+    const bool vecW = (a.K % 4 == 0) && aligned16_dev(a.W);
+    if (want_gx) {
+        for (int i = t; i < MP * (KP / 4); i += TC_THREADS) {
+            const int m = i / (KP / 4), c = i % (KP / 4);
+            const float4 v = (m < a.M) ? load_chunk(a.W, m, a.K, c, vecW) : zero4();
+            store_split(sWh, sWl, tile_off_mn(m, c, MP), v);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_ptr;
+
+    constexpr int CHm = MP / 4, RPm = TC_THREADS / CHm;    // gradient / output-channel side
+    constexpr int CHk = KP / 4, RPk = TC_THREADS / CHk;    // input-channel side
+    const int c_m = t % CHm, r_m = t / CHm, c_k = t % CHk, r_k = t / CHk;
+    const bool vecG = (a.M % 4 == 0) && aligned16_dev(a.G) && (a.Yo == nullptr || aligned16_dev(a.Yo));
+    const bool vecX = (a.K % 4 == 0) && aligned16_dev(a.X), vecGX = (a.K % 4 == 0) && aligned16_dev(a.GX);
+    const bool has_bn = a.bn != nullptr, has_bn_in = a.in_bn != nullptr;
+    const Bn4 bo = load_bn4(a.bn, a.M, c_m), bi = load_bn4(a.in_bn, a.K, c_k);
+    float4 m1 = zero4(), m2 = zero4();
+    if (has_bn) {
+        const float invN = 1.f / static_cast<float>(a.N);
+        const float4 s1 = load_vec4(a.sums, a.M, c_m), s2 = load_vec4(a.sums + a.M, a.M, c_m);
+        m1 = make_float4(s1.x * invN, s1.y * invN, s1.z * invN, s1.w * invN);
+        m2 = make_float4(s2.x * invN, s2.y * invN, s2.z * invN, s2.w * invN);
+    }
+    float4 db4 = zero4(), sp1 = zero4(), sp2 = zero4();
+    constexpr uint32_t IDESC_DATA = make_idesc(128, KP, 0, 1);   // gY (K-major) x W (MN-major)
+    constexpr uint32_t IDESC_WGT = make_idesc(128, KP, 1, 1);    // gY^T (MN-major) x X' (MN-major)
+    uint32_t phase = 0;
+    bool first = true;
+
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int64_t row0 = static_cast<int64_t>(tile) * 128;
+        // ---- prologue A: gradient of the stage's linear output, gY (BatchNorm backward folded in)
+#pragma unroll 4
+        for (int i = 0; i < CHm; ++i) {
+            const int r = r_m + RPm * i;
+            const int64_t gr = row0 + r;
+            float4 g = zero4();
+            if (gr < a.N) {
+                g = load_chunk(a.G, gr, a.M, c_m, vecG);
+                if (has_bn) {
+                    const float4 y = load_chunk(a.Yo, gr, a.M, c_m, vecG);
+                    const float4 xc = make_float4(y.x - bo.mean.x, y.y - bo.mean.y, y.z - bo.mean.z, y.w - bo.mean.w);
+                    if (!a.g_masked) {
+                        if (!(fmaf(xc.x, bo.k.x, bo.beta.x) > 0.f)) g.x = 0.f;
+                        if (!(fmaf(xc.y, bo.k.y, bo.beta.y) > 0.f)) g.y = 0.f;
+                        if (!(fmaf(xc.z, bo.k.z, bo.beta.z) > 0.f)) g.z = 0.f;
+                        if (!(fmaf(xc.w, bo.k.w, bo.beta.w) > 0.f)) g.w = 0.f;
+                    }
+                    g.x = bo.k.x * (g.x - m1.x - xc.x * bo.rstd.x * m2.x);
+                    g.y = bo.k.y * (g.y - m1.y - xc.y * bo.rstd.y * m2.y);
+                    g.z = bo.k.z * (g.z - m1.z - xc.z * bo.rstd.z * m2.z);
+                    g.w = bo.k.w * (g.w - m1.w - xc.w * bo.rstd.w * m2.w);
+                }
+                db4.x += g.x; db4.y += g.y; db4.z += g.z; db4.w += g.w;
+            }
+            store_split2(sGh, sGl, tile_off(r, c_m, 128), sGmh, sGml, tile_off_mn(r, c_m, 128), g);
+        }
+        // ---- prologue B: the stage's forward input as the GEMM saw it, X' = act(bn_in(X))
+#pragma unroll 4
+        for (int i = 0; i < CHk; ++i) {
+            const int r = r_k + RPk * i;
+            const int64_t gr = row0 + r;
+            float4 v = zero4();
+            if (gr < a.N) {
+                v = load_chunk(a.X, gr, a.K, c_k, vecX);
+                if (has_bn_in) v = bn_apply(v, bi);
+                v.x = act_f(v.x, a.in_act, a.in_slope); v.y = act_f(v.y, a.in_act, a.in_slope);
+                v.z = act_f(v.z, a.in_act, a.in_slope); v.w = act_f(v.w, a.in_act, a.in_slope);
+            }
+            store_split(sXh, sXl, tile_off_mn(r, c_k, 128), v);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+            if (want_gx) {
+                // data gradient: (128 x MP) x (MP x KP); k-steps of 8 output channels
+                uint32_t acc = 0;
+#pragma unroll
+                for (int j = 0; j < MP / 8; ++j) {
+                    const uint32_t aoff = (j >> 2) * PANEL128 + (j & 3) * 32u, boff = j * 1024u;
+                    const uint64_t ah = make_desc(sGh + aoff, 16, 1024), al = make_desc(sGl + aoff, 16, 1024);
+                    const uint64_t bh = make_desc_mn(sWh + boff, MP * 128u), bl = make_desc_mn(sWl + boff, MP * 128u);
+                    tc_mma_tf32(tmem, ah, bh, IDESC_DATA, acc);
+                    acc = 1;
+                    tc_mma_tf32(tmem, al, bh, IDESC_DATA, 1);
+                    tc_mma_tf32(tmem, ah, bl, IDESC_DATA, 1);
+                }
+            }
+            // weight gradient: (MP [128 lanes] x 128 rows) x (128 rows x KP); k-steps of 8 rows, accumulated over tiles
+            uint32_t accw = first ? 0u : 1u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t off = j * 1024u;
+                const uint64_t ah = make_desc_mn(sGmh + off, PANEL128), al = make_desc_mn(sGml + off, PANEL128);
+                const uint64_t bh = make_desc_mn(sXh + off, PANEL128), bl = make_desc_mn(sXl + off, PANEL128);
+                tc_mma_tf32(tmem + KP, ah, bh, IDESC_WGT, accw);
+                accw = 1;
+                tc_mma_tf32(tmem + KP, al, bh, IDESC_WGT, 1);
+                tc_mma_tf32(tmem + KP, ah, bl, IDESC_WGT, 1);
+            }
+            tc_commit(bar);
+        }
+        first = false;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        __syncwarp();
+        tc_fence_after();
+        if (want_gx) {
+#pragma unroll
+            for (int cb = 0; cb < PK; ++cb) {
+                float v[32];
+                tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, v);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    sts128(sStage + tile_off(t, cb * 8 + q, 128), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            }
+            tc_fence_before();
+            __syncthreads();
+            // ---- cooperative epilogue: activation mask of the previous stage + its BatchNorm-backward sums
+#pragma unroll 4
+            for (int i = 0; i < CHk; ++i) {
+                const int r = r_k + RPk * i;
+                const int64_t gr = row0 + r;
+                if (gr < a.N) {
+                    float4 g = lds128s(sStage + tile_off(r, c_k, 128));
+                    if (a.in_act != DN4GL_ACT_NONE || has_bn_in) {
+                        const float4 x = load_chunk(a.X, gr, a.K, c_k, vecX);
+                        if (has_bn_in) {
+                            const float4 xc = make_float4(x.x - bi.mean.x, x.y - bi.mean.y, x.z - bi.mean.z, x.w - bi.mean.w);
+                            g.x *= dact_f(fmaf(xc.x, bi.k.x, bi.beta.x), a.in_act, a.in_slope);
+                            g.y *= dact_f(fmaf(xc.y, bi.k.y, bi.beta.y), a.in_act, a.in_slope);
+                            g.z *= dact_f(fmaf(xc.z, bi.k.z, bi.beta.z), a.in_act, a.in_slope);
+                            g.w *= dact_f(fmaf(xc.w, bi.k.w, bi.beta.w), a.in_act, a.in_slope);
+                            sp1.x += g.x; sp1.y += g.y; sp1.z += g.z; sp1.w += g.w;
+                            sp2.x = fmaf(g.x, xc.x * bi.rstd.x, sp2.x); sp2.y = fmaf(g.y, xc.y * bi.rstd.y, sp2.y);
+                            sp2.z = fmaf(g.z, xc.z * bi.rstd.z, sp2.z); sp2.w = fmaf(g.w, xc.w * bi.rstd.w, sp2.w);
+                        } else {
+                            g.x *= dact_f(x.x, a.in_act, a.in_slope); g.y *= dact_f(x.y, a.in_act, a.in_slope);
+                            g.z *= dact_f(x.z, a.in_act, a.in_slope); g.w *= dact_f(x.w, a.in_act, a.in_slope);
+                        }
+                    }
+                    store_chunk(a.GX, gr, a.K, c_k, g, vecGX);
+                }
+            }
+            __syncthreads();   // the staging tile aliases the K-major gY copy the next prologue overwrites
+        }
+    }
+
+    // ---- per-CTA partials: dW (MP x KP, from tensor memory), db (MP), previous-stage sums (2 KP)
+    float *part = a.part + static_cast<size_t>(blockIdx.x) * (MP * KP + MP + 2 * KP);
+    if (w * 32 < MP) {
+#pragma unroll
+        for (int cb = 0; cb < PK; ++cb) {
+            float v[32];
+            tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + KP + cb * 32, v);
+            float4 *dst = reinterpret_cast<float4 *>(part + t * KP + cb * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    }
+    __syncthreads();
+    chunk_allreduce<CHm>(db4);
+    chunk_allreduce<CHk>(sp1);
+    chunk_allreduce<CHk>(sp2);
+    if (lane < (CHm < 32 ? CHm : 32)) {
+        const int c0 = 4 * c_m;
+        red[w][c0] = db4.x; red[w][c0 + 1] = db4.y; red[w][c0 + 2] = db4.z; red[w][c0 + 3] = db4.w;
+    }
+    if (lane < (CHk < 32 ? CHk : 32)) {
+        const int c0 = MP + 4 * c_k;
+        red[w][c0] = sp1.x; red[w][c0 + 1] = sp1.y; red[w][c0 + 2] = sp1.z; red[w][c0 + 3] = sp1.w;
+        red[w][KP + c0] = sp2.x; red[w][KP + c0 + 1] = sp2.y; red[w][KP + c0 + 2] = sp2.z; red[w][KP + c0 + 3] = sp2.w;
+    }
+    __syncthreads();
+    for (int i = t; i < MP + 2 * KP; i += TC_THREADS)
+        part[MP * KP + i] = red[0][i] + red[1][i] + red[2][i] + red[3][i];
+    tc_fence_before();
+    __syncthreads();
+    if (w == 0) tc_dealloc(tmem, TCOLS);
+}
+
+// dW / db / previous-stage sums = fixed-order sum of the per-CTA partials
+__global__ void lin_bwd_reduce_kernel(const float *__restrict__ part, int nparts, int MP, int KP, int M, int K,
+                                      float *__restrict__ dW, float *__restrict__ db, float *__restrict__ sums_prev) {
+    const int stride = MP * KP + MP + 2 * KP;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= stride) return;
+    float *dst = nullptr;
+    if (e < MP * KP) {
+        const int m = e / KP, k = e % KP;
+        if (m < M && k < K && dW) dst = dW + m * K + k;
+    } else if (e < MP * KP + MP) {
+        const int m = e - MP * KP;
+        if (m < M && db) dst = db + m;
+    } else {
+        const int i = e - MP * KP - MP, which = i / KP, k = i % KP;
+        if (k < K && sums_prev) dst = sums_prev + which * K + k;
+    }
+    if (dst == nullptr) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += static_cast<double>(__ldg(part + static_cast<size_t>(p) * stride + e));
+    *dst = static_cast<float>(s);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// elementwise companions
+// ------------------------------------------------------------------------------------------------------------------
+// out = act(bn(Y))  (the activation a stage hands to a non-MLP consumer: aggregation, readout)
+__global__ void bn_act_kernel(const float *__restrict__ Y, int64_t N, int M, const float *__restrict__ bn, int act, float slope,
+                              float *__restrict__ out) {
+    const int CH = (M + 3) / 4;
+    const bool vec = (M % 4 == 0) && aligned16_dev(Y) && aligned16_dev(out);
+    const int64_t total = N * CH;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / CH;
+        const int c = static_cast<int>(i % CH);
+        const Bn4 b = load_bn4(bn, M, c);
+        float4 v = load_chunk(Y, r, M, c, vec);
+        if (bn) v = bn_apply(v, b);
+        v.x = act_f(v.x, act, slope); v.y = act_f(v.y, act, slope); v.z = act_f(v.z, act, slope); v.w = act_f(v.w, act, slope);
+        store_chunk(out, r, M, c, v, vec);
+    }
+}
+
+// BatchNorm-backward batch sums of a stage whose gradient arrives from outside the MLP:
+// s1[c] = sum_r gm, s2[c] = sum_r gm * xhat, gm = G * act'(bn(Y)), xhat = (Y - mean) * rstd.  Per-CTA partials.
+template <int CHP>   // chunks per row rounded up to a power of two (<= 32)
+__global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restrict__ G, const float *__restrict__ Y, int64_t N, int M,
+                                                          const float *__restrict__ bn, int act, float slope,
+                                                          float *__restrict__ part /* [grid][2*4*CHP] */) {
+    constexpr int RP = 256 / CHP;
+    __shared__ float red[8][8 * CHP];
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31, c = t % CHP, r0 = t / CHP;
+    const bool vec = (M % 4 == 0) && aligned16_dev(G) && aligned16_dev(Y);
+    const Bn4 b = load_bn4(bn, M, c);
+    float4 s1 = zero4(), s2 = zero4();
+    if (4 * c < M) {
+        for (int64_t r = static_cast<int64_t>(blockIdx.x) * RP + r0; r < N; r += static_cast<int64_t>(gridDim.x) * RP) {
+            float4 g = load_chunk(G, r, M, c, vec);
+            const float4 y = load_chunk(Y, r, M, c, vec);
+            const float4 xc = make_float4(y.x - b.mean.x, y.y - b.mean.y, y.z - b.mean.z, y.w - b.mean.w);
+            g.x *= dact_f(fmaf(xc.x, b.k.x, b.beta.x), act, slope); g.y *= dact_f(fmaf(xc.y, b.k.y, b.beta.y), act, slope);
+            g.z *= dact_f(fmaf(xc.z, b.k.z, b.beta.z), act, slope); g.w *= dact_f(fmaf(xc.w, b.k.w, b.beta.w), act, slope);
+            s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
+            s2.x = fmaf(g.x, xc.x * b.rstd.x, s2.x); s2.y = fmaf(g.y, xc.y * b.rstd.y, s2.y);
+            s2.z = fmaf(g.z, xc.z * b.rstd.z, s2.z); s2.w = fmaf(g.w, xc.w * b.rstd.w, s2.w);
+        }
+    }
+    chunk_allreduce<CHP>(s1);
+    chunk_allreduce<CHP>(s2);
+    if (lane < CHP) {
+        const int c0 = 4 * c;
+        red[w][c0] = s1.x; red[w][c0 + 1] = s1.y; red[w][c0 + 2] = s1.z; red[w][c0 + 3] = s1.w;
+        red[w][4 * CHP + c0] = s2.x; red[w][4 * CHP + c0 + 1] = s2.y; red[w][4 * CHP + c0 + 2] = s2.z; red[w][4 * CHP + c0 + 3] = s2.w;
+    }
+    __syncthreads();
+    for (int i = t; i < 8 * CHP; i += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) s += red[ww][i];
+        part[static_cast<size_t>(blockIdx.x) * 8 * CHP + i] = s;
+    }
+}
+__global__ void bn_bwd_sums_reduce_kernel(const float *__restrict__ part, int nparts, int CHP, int M, float *__restrict__ sums) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 8 * CHP) return;
+    const int which = e / (4 * CHP), ch = e % (4 * CHP);
+    if (ch >= M) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += static_cast<double>(__ldg(part + static_cast<size_t>(p) * 8 * CHP + e));
+    sums[which * M + ch] = static_cast<float>(s);
+}
+
+constexpr int pad32(int x) { return x <= 32 ? 32 : (x <= 64 ? 64 : 128); }   // padded channel counts: whole power-of-two panels
+
+size_t fwd_smem(int KP, int MP) { return 1024 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128 + (MP / 32) * PANEL128; }
+size_t bwd_smem(int KP, int MP) {
+    return 1024 + 4 * (MP / 32) * PANEL128 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128;
+}
+int fwd_ctas_per_sm(size_t smem) { int n = static_cast<int>((220 * 1024) / smem); return n < 1 ? 1 : (n > 4 ? 4 : n); }
+
+template <int KP, int MP>
+int launch_fwd(const LinFwdArgs &a, int grid, cudaStream_t s) {
+    const size_t smem = fwd_smem(KP, MP);
+    DN_CUDA(cudaFuncSetAttribute(lin_fwd_kernel<KP, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    lin_fwd_kernel<KP, MP><<<grid, TC_THREADS, smem, s>>>(a);
+    return 0;
+}
+template <int KP, int MP>
+int launch_bwd(const LinBwdArgs &a, int grid, cudaStream_t s) {
+    const size_t smem = bwd_smem(KP, MP);
+    DN_CUDA(cudaFuncSetAttribute(lin_bwd_kernel<KP, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    lin_bwd_kernel<KP, MP><<<grid, TC_THREADS, smem, s>>>(a);
+    return 0;
+}
+
+int tc_grid(int64_t N, size_t smem) {
+    const int64_t tiles = ceil_div64(N, 128);
+    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * fwd_ctas_per_sm(smem);
+    return static_cast<int>(tiles < cap ? tiles : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t dn4gl_lin_supported(int32_t K, int32_t M) { return (K >= 1 && M >= 1 && K <= 64 && M <= 64) ? 1 : 0; }
+
+size_t dn4gl_lin_workspace_bytes(int64_t N, int32_t K, int32_t M) {
+    if (!dn4gl_lin_supported(K, M)) return 0;
+    const int KP = pad32(K), MP = pad32(M);
+    const size_t ctas = static_cast<size_t>(dn4gl_num_sms()) * 4;
+    const size_t fwd = ctas * MP * 4 * sizeof(float);
+    const size_t bwd = ctas * (static_cast<size_t>(MP) * KP + MP + 2 * KP) * sizeof(float);
+    (void)N;
+    return align_up(fwd > bwd ? fwd : bwd, 256);
+}
+
+int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, int32_t in_act, float in_slope,
+                      const float *W, const float *bias, int32_t M, float *Y,
+                      const float *gamma, const float *beta, float eps, float momentum, float *bn_out,
+                      float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                      void *ws, size_t ws_bytes, int32_t *counter, void *stream) {
+    DN_ARG(N >= 0 && X != nullptr && W != nullptr && Y != nullptr);
+    DN_ARG(dn4gl_lin_supported(K, M));
+    DN_ARG(in_act >= DN4GL_ACT_NONE && in_act <= DN4GL_ACT_LEAKY_RELU);
+    DN_ARG(bn_out == nullptr || (ws != nullptr && counter != nullptr && ws_bytes >= dn4gl_lin_workspace_bytes(N, K, M)));
+    if (N == 0) return DN4GL_OK;
+    DN_ARG(N < (static_cast<int64_t>(1) << 31) * 128);
+    const int KP = pad32(K), MP = pad32(M);
+    LinFwdArgs a;
+    a.X = X; a.N = N; a.K = K; a.in_bn = in_bn; a.in_act = in_act; a.in_slope = in_slope;
+    a.W = W; a.bias = bias; a.M = M; a.Y = Y;
+    a.gamma = gamma; a.beta = beta; a.eps = eps; a.momentum = momentum;
+    a.bn_out = bn_out; a.run_mean = running_mean; a.run_var = running_var;
+    a.nbt = reinterpret_cast<long long *>(num_batches_tracked);
+    a.part = static_cast<float *>(ws); a.counter = counter;
+    a.num_tiles = static_cast<int>(ceil_div64(N, 128));
+    const int grid = tc_grid(N, fwd_smem(KP, MP));
+    cudaStream_t s = as_stream(stream);
+    int rc = 0;
+#define DN_FWD_CASE(kp, mp) if (KP == kp && MP == mp) rc = launch_fwd<kp, mp>(a, grid, s); else
+    DN_FWD_CASE(32, 32) DN_FWD_CASE(32, 64) DN_FWD_CASE(64, 32) DN_FWD_CASE(64, 64)
+    { dn4gl_set_error("dn4gl_lin_fwd_f32: no instantiation for K=%d M=%d", K, M); return DN4GL_EINVAL; }
+#undef DN_FWD_CASE
+    if (rc) return rc;
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+int dn4gl_lin_bwd_f32(const float *G, const float *Yout, int64_t N, int32_t M,
+                      const float *bn, const float *sums, int32_t g_masked,
+                      const float *W, int32_t K,
+                      const float *X, const float *in_bn, int32_t in_act, float in_slope,
+                      float *GX, float *sums_prev, float *dW, float *db,
+                      void *ws, size_t ws_bytes, void *stream) {
+    DN_ARG(N >= 0 && G != nullptr && W != nullptr && X != nullptr && ws != nullptr);
+    DN_ARG(dn4gl_lin_supported(K, M));
+    DN_ARG(bn == nullptr || (Yout != nullptr && sums != nullptr));
+    DN_ARG(sums_prev == nullptr || in_bn != nullptr);
+    DN_ARG(in_act >= DN4GL_ACT_NONE && in_act <= DN4GL_ACT_LEAKY_RELU);
+    DN_ARG(ws_bytes >= dn4gl_lin_workspace_bytes(N, K, M));
+    const int KP = pad32(K), MP = pad32(M);
+    // the canonical layouts used here need MP and KP to be whole 32-float panels and tcgen05 needs N % 16 == 0
+    cudaStream_t s = as_stream(stream);
+    if (N == 0) {
+        if (dW) DN_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * M * K, s));
+        if (db) DN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * M, s));
+        if (sums_prev) DN_CUDA(cudaMemsetAsync(sums_prev, 0, sizeof(float) * 2 * K, s));
+        return DN4GL_OK;
+    }
+    LinBwdArgs a;
+    a.G = G; a.Yo = Yout; a.N = N; a.M = M; a.bn = bn; a.sums = sums; a.g_masked = g_masked;
+    a.W = W; a.K = K; a.X = X; a.in_bn = in_bn; a.in_act = in_act; a.in_slope = in_slope;
+    a.GX = GX; a.part = static_cast<float *>(ws);
+    a.num_tiles = static_cast<int>(ceil_div64(N, 128));
+    const int grid = tc_grid(N, bwd_smem(KP, MP));
+    int rc = 0;
+#define DN_BWD_CASE(kp, mp) if (KP == kp && MP == mp) rc = launch_bwd<kp, mp>(a, grid, s); else
+    DN_BWD_CASE(32, 32) DN_BWD_CASE(32, 64) DN_BWD_CASE(64, 32) DN_BWD_CASE(64, 64)
+    { dn4gl_set_error("dn4gl_lin_bwd_f32: no instantiation for K=%d M=%d", K, M); return DN4GL_EINVAL; }
+#undef DN_BWD_CASE
+    if (rc) return rc;
+    const int elems = MP * KP + MP + 2 * KP;
+    lin_bwd_reduce_kernel<<<(elems + 127) / 128, 128, 0, s>>>(a.part, grid, MP, KP, M, K, dW, db, sums_prev);
+    DN_LAUNCHED_N(2);
+    return DN4GL_OK;
+}
+
+int dn4gl_bn_act_f32(const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope, float *out,
+                     void *stream) {
+    DN_ARG(N >= 0 && M >= 1 && Y != nullptr && out != nullptr);
+    DN_ARG(act >= DN4GL_ACT_NONE && act <= DN4GL_ACT_LEAKY_RELU);
+    if (N == 0) return DN4GL_OK;
+    const int64_t total = N * ((M + 3) / 4);
+    const int64_t want = ceil_div64(total, 256 * 4);
+    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 8;
+    bn_act_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(Y, N, M, bn, act, slope, out);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+size_t dn4gl_bn_bwd_sums_workspace_bytes(int64_t N, int32_t M) {
+    (void)N;
+    (void)M;
+    return static_cast<size_t>(dn4gl_num_sms()) * 4 * 8 * 32 * sizeof(float);
+}
+
+int dn4gl_bn_bwd_sums_f32(const float *G, const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope,
+                          float *sums, void *ws, size_t ws_bytes, void *stream) {
+    DN_ARG(N >= 0 && M >= 1 && M <= 128 && G != nullptr && Y != nullptr && bn != nullptr && sums != nullptr && ws != nullptr);
+    DN_ARG(ws_bytes >= dn4gl_bn_bwd_sums_workspace_bytes(N, M));
+    cudaStream_t s = as_stream(stream);
+    if (N == 0) { DN_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * M, s)); return DN4GL_OK; }
+    const int CH = (M + 3) / 4;
+    int CHP = 1;
+    while (CHP < CH) CHP <<= 1;
+    const int RP = 256 / CHP;
+    const int64_t want = ceil_div64(N, static_cast<int64_t>(RP) * 8);
+    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 4;
+    const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
+    float *part = static_cast<float *>(ws);
+    switch (CHP) {
+    case 1: bn_bwd_sums_kernel<1><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
+    case 2: bn_bwd_sums_kernel<2><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
+    case 4: bn_bwd_sums_kernel<4><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
+    case 8: bn_bwd_sums_kernel<8><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
+    case 16: bn_bwd_sums_kernel<16><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
+    default: bn_bwd_sums_kernel<32><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
+    }
+    bn_bwd_sums_reduce_kernel<<<(8 * CHP + 127) / 128, 128, 0, s>>>(part, grid, CHP, M, sums);
+    DN_LAUNCHED_N(2);
+    return DN4GL_OK;
+}
+
+}  // extern "C"

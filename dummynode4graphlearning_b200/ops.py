@@ -295,3 +295,148 @@ class Linear(torch.nn.Linear):
 
     def forward(self, x):
         return linear(x, self.weight, self.bias)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core MLP stages (csrc/mlp_tc.cu): Linear with the neighbouring BatchNorm / activation folded in
+ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
+_tc_scratch = {}
+
+
+def lin_supported(K, M):
+    return bool(lib().raw("dn4gl_lin_supported")(int(K), int(M)))
+
+
+def _tc_ws(device, nbytes):
+    """(workspace, zeroed int32 counter) per (device, stream): the kernels consume the workspace before the next
+    launch on the same stream starts, and leave the counter at zero."""
+    key = (device.index, _stream())
+    ent = _tc_scratch.get(key)
+    if ent is None or ent[0].numel() < nbytes:
+        ent = (torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device),
+               ent[1] if ent is not None else torch.zeros(1, dtype=torch.int32, device=device))
+        _tc_scratch[key] = ent
+    return ent
+
+
+def lin_fwd(x, weight, bias=None, in_bn=None, in_act=ACT_NONE, in_slope=0.0, bn=None):
+    """Y = act(bn_in(x)) W^T + b on the tensor cores (3xTF32).  bn = None, or a dict(gamma, beta, eps, momentum,
+    running_mean, running_var, num_batches_tracked) -> also returns the BatchNorm record of Y's batch statistics
+    (and updates the running buffers in place).  Returns (Y, record | None)."""
+    require_cuda(x, "rows")
+    x = _f32c(x)
+    N, K = x.shape
+    M = weight.size(0)
+    L = lib()
+    Y = torch.empty((N, M), dtype=torch.float32, device=x.device)
+    rec = None
+    wsb = L.size("dn4gl_lin_workspace_bytes", N, K, M)
+    ws, counter = _tc_ws(x.device, wsb)
+    g = b = rm = rv = nbt = None
+    eps = mom = 0.0
+    if bn is not None:
+        rec = torch.empty(4 * M, dtype=torch.float32, device=x.device)
+        g, b, eps, mom = bn.get("gamma"), bn.get("beta"), float(bn["eps"]), float(bn.get("momentum") or 0.0)
+        rm, rv, nbt = bn.get("running_mean"), bn.get("running_var"), bn.get("num_batches_tracked")
+    L.call("dn4gl_lin_fwd_f32", ptr(x), N, K, ptr(in_bn), int(in_act), float(in_slope), ptr(_f32c(weight)),
+           ptr(None if bias is None else _f32c(bias)), M, ptr(Y), ptr(g), ptr(b), eps, mom, ptr(rec), ptr(rm), ptr(rv),
+           ptr(nbt), ptr(ws), wsb, ptr(counter), _stream())
+    return Y, rec
+
+
+def lin_bwd(G, weight, X, Yout=None, bn=None, sums=None, g_masked=False, in_bn=None, in_act=ACT_NONE, in_slope=0.0,
+            want_gx=True, want_dw=True, want_db=True):
+    """backward of one stage (see include/dn4gl.h): -> (GX | None, sums_prev | None, dW | None, db | None)."""
+    require_cuda(G, "gradient rows")
+    G, X = _f32c(G), _f32c(X)
+    N, M = G.shape
+    K = X.size(1)
+    dev = G.device
+    L = lib()
+    GX = torch.empty((N, K), dtype=torch.float32, device=dev) if want_gx else None
+    sp = torch.empty(2 * K, dtype=torch.float32, device=dev) if (want_gx and in_bn is not None) else None
+    dW = torch.empty((M, K), dtype=torch.float32, device=dev) if want_dw else None
+    db = torch.empty(M, dtype=torch.float32, device=dev) if want_db else None
+    wsb = L.size("dn4gl_lin_workspace_bytes", N, K, M)
+    ws, _ = _tc_ws(dev, wsb)
+    L.call("dn4gl_lin_bwd_f32", ptr(G), ptr(None if Yout is None else _f32c(Yout)), N, M, ptr(bn), ptr(sums),
+           1 if g_masked else 0, ptr(_f32c(weight)), K, ptr(X), ptr(in_bn), int(in_act), float(in_slope), ptr(GX), ptr(sp),
+           ptr(dW), ptr(db), ptr(ws), wsb, _stream())
+    return GX, sp, dW, db
+
+
+def bn_act(Y, rec, act=ACT_RELU, slope=0.0):
+    """act(bn(Y)) elementwise (rec None = identity normalisation)."""
+    require_cuda(Y, "rows")
+    Y = _f32c(Y)
+    out = torch.empty_like(Y)
+    lib().call("dn4gl_bn_act_f32", ptr(Y), Y.size(0), Y.size(1), ptr(rec), int(act), float(slope), ptr(out), _stream())
+    return out
+
+
+def bn_bwd_sums(G, Y, rec, act=ACT_RELU, slope=0.0):
+    """{sum gm, sum gm * xhat} (2*M) with gm = G * act'(bn(Y))."""
+    G, Y = _f32c(G), _f32c(Y)
+    N, M = Y.shape
+    L = lib()
+    sums = torch.empty(2 * M, dtype=torch.float32, device=Y.device)
+    wsb = L.size("dn4gl_bn_bwd_sums_workspace_bytes", N, M)
+    ws, _ = _tc_ws(Y.device, wsb)
+    L.call("dn4gl_bn_bwd_sums_f32", ptr(G), ptr(Y), N, M, ptr(rec), int(act), float(slope), ptr(sums), ptr(ws), wsb,
+           _stream())
+    return sums
+
+
+def _bn_dict(bn):
+    return dict(gamma=bn.weight, beta=bn.bias, eps=bn.eps, momentum=bn.momentum, running_mean=bn.running_mean,
+                running_var=bn.running_var, num_batches_tracked=bn.num_batches_tracked)
+
+
+class _GinMlp(torch.autograd.Function):
+    """h = ReLU(BN2(Linear2(ReLU(BN1(Linear1(z))))))  in training mode (batch statistics), three launches forward
+    (two tensor-core stages + one elementwise), five backward; gconv.py:190-196."""
+
+    @staticmethod
+    def forward(ctx, z, W1, b1, g1, be1, W2, b2, g2, be2, bn1, bn2):
+        y1, rec1 = lin_fwd(z, W1, b1, bn=bn1)
+        y2, rec2 = lin_fwd(y1, W2, b2, in_bn=rec1, in_act=ACT_RELU, bn=bn2)
+        h = bn_act(y2, rec2, ACT_RELU)
+        ctx.save_for_backward(z, y1, y2, rec1, rec2, W1, W2)
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        z, y1, y2, rec1, rec2, W1, W2 = ctx.saved_tensors
+        D1, D2 = W1.size(0), W2.size(0)
+        gh = _f32c(gh)
+        sums2 = bn_bwd_sums(gh, y2, rec2, ACT_RELU)
+        ga1, sums1, dW2, db2 = lin_bwd(gh, W2, y1, Yout=y2, bn=rec2, sums=sums2, g_masked=False, in_bn=rec1,
+                                       in_act=ACT_RELU)
+        gz, _, dW1, db1 = lin_bwd(ga1, W1, z, Yout=y1, bn=rec1, sums=sums1, g_masked=True,
+                                  want_gx=ctx.needs_input_grad[0])
+        return (gz, dW1, db1, sums1[D1:], sums1[:D1], dW2, db2, sums2[D2:], sums2[:D2], None, None)
+
+
+def gin_mlp_fusable(seq):
+    """True if `seq` is the reference's GIN MLP (Linear, BatchNorm1d, ReLU, Linear, BatchNorm1d, ReLU) in a state
+    the fused stages reproduce: training-mode batch statistics with a fixed momentum, affine BN, supported widths."""
+    import torch.nn as nn
+    if not (isinstance(seq, nn.Sequential) and len(seq) == 6):
+        return False
+    l1, n1, a1, l2, n2, a2 = seq
+    if not (isinstance(l1, nn.Linear) and isinstance(l2, nn.Linear) and isinstance(n1, nn.BatchNorm1d)
+            and isinstance(n2, nn.BatchNorm1d) and isinstance(a1, nn.ReLU) and isinstance(a2, nn.ReLU)):
+        return False
+    for n in (n1, n2):
+        if not (n.training and n.affine and n.track_running_stats and n.momentum is not None):
+            return False
+    if l1.bias is None or l2.bias is None:
+        return False
+    return lin_supported(l1.in_features, l1.out_features) and lin_supported(l2.in_features, l2.out_features)
+
+
+def gin_mlp(seq, z):
+    """apply the GIN MLP `seq` to z through the fused tensor-core stages (gin_mlp_fusable(seq) must hold)."""
+    l1, n1, _, l2, n2, _ = seq
+    return _GinMlp.apply(z, l1.weight, l1.bias, n1.weight, n1.bias, l2.weight, l2.bias, n2.weight, n2.bias,
+                         _bn_dict(n1), _bn_dict(n2))

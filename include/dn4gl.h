@@ -275,6 +275,54 @@ size_t dn4gl_atb_workspace_bytes(int64_t N, int32_t Ka, int32_t Kb);
 int dn4gl_atb_f32(const float *A, const float *B, float *C, float *colsum_A, int64_t N, int32_t Ka, int32_t Kb,
                   void *ws, size_t ws_bytes, void *stream);
 
+/* ---- tensor-core stages of the per-node / per-edge MLPs (tcgen05, 3xTF32) --------------------- */
+/* Replaces, on the layer's MLP (gconv.py:190-196 `Linear, BatchNorm1d, ReLU, Linear, BatchNorm1d, ReLU`;
+ * rgin.py:52, dmpnn.py:47,55 `Linear, act, Linear`), the chain nn.Linear -> F.batch_norm -> activation and its
+ * autograd backward (cuBLAS SGEMMs + ATen batch-norm / elementwise kernels in the reference's stack).
+ *
+ * A BatchNorm "record" over C channels is 4*C floats: mean[C], rstd[C], k[C] = gamma*rstd, beta[C]; applying it is
+ * (x - mean) * k + beta.  Activations: */
+#define DN4GL_ACT_NONE 0
+#define DN4GL_ACT_RELU 1
+#define DN4GL_ACT_LEAKY_RELU 2
+/* 1 if (K inputs, M outputs) is inside the kernels' tile limits (currently K, M <= 64)               */
+int32_t dn4gl_lin_supported(int32_t K, int32_t M);
+size_t dn4gl_lin_workspace_bytes(int64_t N, int32_t K, int32_t M);
+/* Y (N x M) = act_in(bn_in(X)) W^T + bias.   X (N x K) row-major; in_bn NULL or the record (over K) of the previous
+ * stage's BatchNorm; W (M x K) as nn.Linear stores it; bias NULL or (M).
+ * If bn_out != NULL the per-channel batch statistics of Y (biased variance, eps) are reduced in a fixed order and
+ * the record {mean, rstd, gamma*rstd, beta} (gamma / beta NULL = 1 / 0) is written to bn_out[4*M]; running_mean /
+ * running_var (momentum, unbiased variance) and num_batches_tracked are updated in place when non-NULL -- the
+ * training-mode semantics of nn.BatchNorm1d.  ws: dn4gl_lin_workspace_bytes; counter: one int32 that is 0 on entry
+ * (the kernel leaves it 0).                                                                          */
+int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, int32_t in_act, float in_slope,
+                      const float *W, const float *bias, int32_t M, float *Y,
+                      const float *gamma, const float *beta, float eps, float momentum, float *bn_out,
+                      float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                      void *ws, size_t ws_bytes, int32_t *counter, void *stream);
+/* Backward of one stage  Y = X' W^T + b,  X' = act_in(bn_in(X)):
+ *   gY = G                                  (bn == NULL), or the BatchNorm(+ReLU) backward of the stage OUTPUT:
+ *        gm = G * [bn(Y) > 0] (skipped when g_masked), gY = k * (gm - s1/N - xhat * s2/N), xhat = (Y - mean) * rstd,
+ *        sums = {s1[M], s2[M]} = {sum gm, sum gm*xhat} (dn4gl_bn_bwd_sums_f32 or the sums_prev of the stage after);
+ *   dW (M x K) = gY^T X',  db (M) = colsum gY   (either may be NULL);
+ *   GX (N x K) = (gY W) * act_in'(bn_in(X))     (NULL: not needed), and when in_bn != NULL also
+ *   sums_prev[2*K] = {sum GX, sum GX * xhat_in}: the batch sums the previous stage's backward needs, so the chain
+ *   needs no separate reduction pass.  dgamma = s2, dbeta = s1 of the stage's own sums.               */
+int dn4gl_lin_bwd_f32(const float *G, const float *Yout, int64_t N, int32_t M,
+                      const float *bn, const float *sums, int32_t g_masked,
+                      const float *W, int32_t K,
+                      const float *X, const float *in_bn, int32_t in_act, float in_slope,
+                      float *GX, float *sums_prev, float *dW, float *db,
+                      void *ws, size_t ws_bytes, void *stream);
+/* out = act(bn(Y))  (bn NULL = identity): the activation a stage hands to the aggregation / readout kernels      */
+int dn4gl_bn_act_f32(const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope, float *out,
+                     void *stream);
+/* sums[2*M] = {sum_r gm, sum_r gm * xhat}, gm = G * act'(bn(Y)): the batch sums of a BatchNorm whose output
+ * gradient G arrives from outside the MLP (aggregation / readout backward)                                        */
+size_t dn4gl_bn_bwd_sums_workspace_bytes(int64_t N, int32_t M);
+int dn4gl_bn_bwd_sums_f32(const float *G, const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope,
+                          float *sums, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- small fused elementwise helpers of the layers ------------------------------------------ */
 /* gather rows: out[i,:] = x[idx[i],:] (idx int32, n rows)                                       */
 int dn4gl_gather_rows_f32(const int32_t *idx, const float *x, float *out, int64_t n, int32_t D, void *stream);
