@@ -13,7 +13,8 @@
 template <int LANES, int VEC>
 __global__ void __launch_bounds__(256)
 spmm_rows_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const float4 *__restrict__ x,
-                 float4 *__restrict__ out, int64_t N, float self_scale, int heavy_thr) {
+                 float4 *__restrict__ out, int64_t N, float self_scale, const float *__restrict__ eps_dev, int heavy_thr) {
+    if (eps_dev != nullptr) self_scale = 1.f + __ldg(eps_dev);
     constexpr int ROWS = 256 / LANES;
     constexpr int U = (VEC == 1) ? 8 : (VEC == 2 ? 4 : 2);
     constexpr int DV = LANES * VEC;  // float4 per row
@@ -69,8 +70,9 @@ spmm_rows_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict_
 template <int LANES, int VEC>
 __global__ void __launch_bounds__(256)
 spmm_heavy_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const float4 *__restrict__ x,
-                  float4 *__restrict__ out, float self_scale, const int32_t *__restrict__ heavy_rows,
-                  const int32_t *__restrict__ heavy_count) {
+                  float4 *__restrict__ out, float self_scale, const float *__restrict__ eps_dev,
+                  const int32_t *__restrict__ heavy_rows, const int32_t *__restrict__ heavy_count) {
+    if (eps_dev != nullptr) self_scale = 1.f + __ldg(eps_dev);
     constexpr int SUBS = 256 / LANES;
     constexpr int DV = LANES * VEC;
     __shared__ float4 part[256 * VEC];
@@ -131,32 +133,32 @@ spmm_heavy_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict
 
 template <int LANES, int VEC>
 static int launch_spmm(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, int64_t N,
-                       float self_scale, const int32_t *heavy_rows, const int32_t *heavy_count, int heavy_thr,
-                       cudaStream_t st) {
+                       float self_scale, const float *eps_dev, const int32_t *heavy_rows, const int32_t *heavy_count,
+                       int heavy_thr, cudaStream_t st) {
     constexpr int ROWS = 256 / LANES;
     const bool heavy = heavy_rows != nullptr && heavy_count != nullptr && heavy_thr > 0;
     spmm_rows_kernel<LANES, VEC><<<static_cast<unsigned>(ceil_div64(N, ROWS)), 256, 0, st>>>(
-        row_ptr, col, reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(out), N, self_scale,
+        row_ptr, col, reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(out), N, self_scale, eps_dev,
         heavy ? heavy_thr : 0);
     if (heavy) {
         spmm_heavy_kernel<LANES, VEC><<<dn4gl_num_sms() * 4, 256, 0, st>>>(
-            row_ptr, col, reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(out), self_scale,
+            row_ptr, col, reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(out), self_scale, eps_dev,
             heavy_rows, heavy_count);
     }
     return 0;
 }
 
 extern "C" int dn4gl_spmm_sum_f32(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, int64_t N,
-                                  int64_t n_src, int32_t D, float self_scale, const int32_t *heavy_rows,
+                                  int64_t n_src, int32_t D, float self_scale, const float *eps_dev, const int32_t *heavy_rows,
                                   const int32_t *heavy_count, int32_t heavy_threshold, void *stream) {
     DN_ARG(N >= 0 && n_src >= 0 && D > 0 && D % 4 == 0);
     if (N == 0) return DN4GL_OK;
     DN_ARG(row_ptr && x && out && aligned16(x) && aligned16(out));
-    DN_ARG(self_scale == 0.f || n_src == N);
+    DN_ARG((self_scale == 0.f && eps_dev == nullptr) || n_src == N);
     cudaStream_t st = as_stream(stream);
     const int dv = D / 4;
 #define SPMM_CASE(L, V)                                                                                       \
-    launch_spmm<L, V>(row_ptr, col, x, out, N, self_scale, heavy_rows, heavy_count, heavy_threshold, st);     \
+    launch_spmm<L, V>(row_ptr, col, x, out, N, self_scale, eps_dev, heavy_rows, heavy_count, heavy_threshold, st); \
     break
     switch (dv) {
         case 1: SPMM_CASE(1, 1);

@@ -234,7 +234,7 @@ struct LinFwdArgs {
     float *Y;
     const float *gamma; const float *beta; float eps; float momentum;
     float *bn_out; float *run_mean; float *run_var; long long *nbt;
-    float *part; int *counter;
+    float *part;
     int num_tiles;
 };
 
@@ -244,13 +244,13 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
     constexpr int PK = KP / 32, PM = MP / 32;
     constexpr uint32_t A_BYTES = PK * PANEL128, B_BYTES = PK * MP * 128u;
     const uint32_t base = (s_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sAh = base, sAl = sAh + A_BYTES, sBh = sAl + A_BYTES, sBl = sBh + B_BYTES, sStage = sBl + B_BYTES;
+    const uint32_t sAh = base, sAl = sAh + A_BYTES, sBh = sAl + A_BYTES, sBl = sBh + B_BYTES;
+    const uint32_t sStage = sAh;      // the operand tiles are dead once the tile's MMAs have completed
+    static_assert(2 * PK >= PM, "staging tile must fit the A operand tiles");
     __shared__ __align__(8) uint64_t bar_mem;
     __shared__ uint32_t tmem_ptr;
-    __shared__ int is_last;
     __shared__ float red[4][MP * 2];
     __shared__ float shift_s[MP];
-    __shared__ double fin[TC_THREADS * 2];
 
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     const uint32_t bar = s_u32(&bar_mem);
@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
         }
         const int64_t left = a.N - row0;
         n_cta += left < 128 ? static_cast<float>(left) : 128.f;
+        __syncthreads();   // the staging tile aliases the operand tiles the next prologue overwrites
     }
 
     if (stats) {
@@ -371,58 +372,7 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
             // CHo < 32: every warp saw every chunk; CHo == 32: likewise (one row per warp per pass)
             const float s1 = red[0][t] + red[1][t] + red[2][t] + red[3][t];
             const float s2 = red[0][MP + t] + red[1][MP + t] + red[2][MP + t] + red[3][MP + t];
-            float *p = a.part + (static_cast<size_t>(blockIdx.x) * MP + t) * 4;
-            p[0] = n_cta; p[1] = shift_s[t]; p[2] = s1; p[3] = s2;
-        }
-        __threadfence();
-        __syncthreads();
-        if (t == 0) is_last = (atomicAdd(a.counter, 1) == static_cast<int>(gridDim.x) - 1);
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            constexpr int G = TC_THREADS / MP;     // partial-sum groups per channel
-            const int c = t % MP, g = t / MP;
-            const volatile float *part = a.part;
-            const double n0 = part[(0 * MP + c) * 4], k0 = part[(0 * MP + c) * 4 + 1];
-            const double kstar = k0 + static_cast<double>(part[(0 * MP + c) * 4 + 2]) / n0;   // mean of CTA 0
-            double A1 = 0.0, A2 = 0.0;
-            for (int i = g; i < static_cast<int>(gridDim.x); i += G) {
-                const volatile float *p = part + (static_cast<size_t>(i) * MP + c) * 4;
-                const double n = p[0];
-                if (n > 0.0) {
-                    const double s1 = p[2], s2 = p[3];
-                    const double mean_i = static_cast<double>(p[1]) + s1 / n, m2_i = s2 - s1 * s1 / n;
-                    const double d = mean_i - kstar;
-                    A1 += n * d;
-                    A2 += (m2_i > 0.0 ? m2_i : 0.0) + n * d * d;
-                }
-            }
-            fin[t * 2] = A1; fin[t * 2 + 1] = A2;
-            __syncthreads();
-            if (g == 0 && c < a.M) {
-                double a1 = 0.0, a2 = 0.0;
-                for (int gg = 0; gg < G; ++gg) { a1 += fin[(gg * MP + c) * 2]; a2 += fin[(gg * MP + c) * 2 + 1]; }
-                const double Nd = static_cast<double>(a.N);
-                const double mean = kstar + a1 / Nd;
-                double m2 = a2 - a1 * a1 / Nd;
-                if (m2 < 0.0) m2 = 0.0;
-                const double var = m2 / Nd;
-                const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
-                const float gam = a.gamma ? a.gamma[c] : 1.f, bet = a.beta ? a.beta[c] : 0.f;
-                a.bn_out[c] = static_cast<float>(mean);
-                a.bn_out[a.M + c] = rstd;
-                a.bn_out[2 * a.M + c] = gam * rstd;
-                a.bn_out[3 * a.M + c] = bet;
-                if (a.run_mean) a.run_mean[c] = (1.f - a.momentum) * a.run_mean[c] + a.momentum * static_cast<float>(mean);
-                if (a.run_var) {
-                    const double unb = a.N > 1 ? m2 / (Nd - 1.0) : var;
-                    a.run_var[c] = (1.f - a.momentum) * a.run_var[c] + a.momentum * static_cast<float>(unb);
-                }
-            }
-            if (t == 0) {
-                if (a.nbt) *a.nbt += 1;
-                *a.counter = 0;
-            }
+            reinterpret_cast<float4 *>(a.part)[static_cast<size_t>(blockIdx.x) * MP + t] = make_float4(n_cta, shift_s[t], s1, s2);
         }
     }
     tc_fence_before();
@@ -652,12 +602,36 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
     if (w == 0) tc_dealloc(tmem, TCOLS);
 }
 
-// dW / db / previous-stage sums = fixed-order sum of the per-CTA partials
-__global__ void lin_bwd_reduce_kernel(const float *__restrict__ part, int nparts, int MP, int KP, int M, int K,
-                                      float *__restrict__ dW, float *__restrict__ db, float *__restrict__ sums_prev) {
+// Fixed-order sums of per-CTA partials.  A block is 32 output elements x 32 partial groups: thread (lane, g) adds
+// partials g, g+32, ... (independent coalesced loads, double accumulation), the groups are then added in index order.
+__device__ __forceinline__ double partial_column_sum(const float *__restrict__ part, int nparts, int stride, int e, int g) {
+    double s = 0.0;
+    int p = g;
+    for (; p + 96 < nparts; p += 128) {
+        const float v0 = __ldcg(part + static_cast<size_t>(p) * stride + e), v1 = __ldcg(part + static_cast<size_t>(p + 32) * stride + e);
+        const float v2 = __ldcg(part + static_cast<size_t>(p + 64) * stride + e), v3 = __ldcg(part + static_cast<size_t>(p + 96) * stride + e);
+        s += static_cast<double>(v0); s += static_cast<double>(v1); s += static_cast<double>(v2); s += static_cast<double>(v3);
+    }
+    for (; p < nparts; p += 32) s += static_cast<double>(__ldcg(part + static_cast<size_t>(p) * stride + e));
+    return s;
+}
+__device__ __forceinline__ double group_sum(double (*sm)[33], int lane, int g, double s) {
+    sm[g][lane] = s;
+    __syncthreads();
+    double tot = 0.0;
+    if (g == 0)
+        for (int gg = 0; gg < 32; ++gg) tot += sm[gg][lane];
+    return tot;
+}
+
+// dW / db / previous-stage sums
+__global__ void __launch_bounds__(1024)
+lin_bwd_reduce_kernel(const float *__restrict__ part, int nparts, int MP, int KP, int M, int K,
+                      float *__restrict__ dW, float *__restrict__ db, float *__restrict__ sums_prev) {
+    __shared__ double sm[32][33];
     const int stride = MP * KP + MP + 2 * KP;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= stride) return;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
     float *dst = nullptr;
     if (e < MP * KP) {
         const int m = e / KP, k = e % KP;
@@ -665,14 +639,60 @@ __global__ void lin_bwd_reduce_kernel(const float *__restrict__ part, int nparts
     } else if (e < MP * KP + MP) {
         const int m = e - MP * KP;
         if (m < M && db) dst = db + m;
-    } else {
+    } else if (e < stride) {
         const int i = e - MP * KP - MP, which = i / KP, k = i % KP;
         if (k < K && sums_prev) dst = sums_prev + which * K + k;
     }
-    if (dst == nullptr) return;
-    double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += static_cast<double>(__ldg(part + static_cast<size_t>(p) * stride + e));
-    *dst = static_cast<float>(s);
+    const double s = dst != nullptr ? partial_column_sum(part, nparts, stride, e, g) : 0.0;
+    const double tot = group_sum(sm, lane, g, s);
+    if (g == 0 && dst != nullptr) *dst = static_cast<float>(tot);
+}
+
+// BatchNorm record from the per-CTA (n, shift, S1, S2) partials of lin_fwd_kernel: every partial is re-centred on the
+// mean of CTA 0 (exact in double), so the merge is a plain fixed-order sum and cancellation-free.
+__global__ void __launch_bounds__(1024)
+bn_finalize_kernel(const float4 *__restrict__ part, int nparts, int MP, int M, int64_t N,
+                   const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
+                   float *__restrict__ bn_out, float *__restrict__ run_mean, float *__restrict__ run_var, long long *nbt) {
+    __shared__ double sm[32][33];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;     // < MP (MP is a multiple of 32)
+    const float4 p0 = __ldcg(part + c);
+    const double kstar = static_cast<double>(p0.y) + static_cast<double>(p0.z) / static_cast<double>(p0.x);
+    double A1 = 0.0, A2 = 0.0;
+    for (int p = g; p < nparts; p += 32) {
+        const float4 v = __ldcg(part + static_cast<size_t>(p) * MP + c);
+        const double n = v.x;
+        if (n > 0.0) {
+            const double s1 = v.z, s2 = v.w;
+            const double mean_i = static_cast<double>(v.y) + s1 / n, m2_i = s2 - s1 * s1 / n;
+            const double d = mean_i - kstar;
+            A1 += n * d;
+            A2 += (m2_i > 0.0 ? m2_i : 0.0) + n * d * d;
+        }
+    }
+    const double a1 = group_sum(sm, lane, g, A1);
+    __syncthreads();
+    const double a2 = group_sum(sm, lane, g, A2);
+    if (g == 0 && c < M) {
+        const double Nd = static_cast<double>(N);
+        const double mean = kstar + a1 / Nd;
+        double m2 = a2 - a1 * a1 / Nd;
+        if (m2 < 0.0) m2 = 0.0;
+        const double var = m2 / Nd;
+        const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        const float gam = gamma ? gamma[c] : 1.f, bet = beta ? beta[c] : 0.f;
+        bn_out[c] = static_cast<float>(mean);
+        bn_out[M + c] = rstd;
+        bn_out[2 * M + c] = gam * rstd;
+        bn_out[3 * M + c] = bet;
+        if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * static_cast<float>(mean);
+        if (run_var) {
+            const double unb = N > 1 ? m2 / (Nd - 1.0) : var;
+            run_var[c] = (1.f - momentum) * run_var[c] + momentum * static_cast<float>(unb);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -735,23 +755,74 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restric
         part[static_cast<size_t>(blockIdx.x) * 8 * CHP + i] = s;
     }
 }
-__global__ void bn_bwd_sums_reduce_kernel(const float *__restrict__ part, int nparts, int CHP, int M, float *__restrict__ sums) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 8 * CHP) return;
+__global__ void __launch_bounds__(1024)
+bn_bwd_sums_reduce_kernel(const float *__restrict__ part, int nparts, int CHP, int M, float *__restrict__ sums) {
+    __shared__ double sm[32][33];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
     const int which = e / (4 * CHP), ch = e % (4 * CHP);
-    if (ch >= M) return;
-    double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += static_cast<double>(__ldg(part + static_cast<size_t>(p) * 8 * CHP + e));
-    sums[which * M + ch] = static_cast<float>(s);
+    const bool ok = e < 8 * CHP && ch < M;
+    const double s = ok ? partial_column_sum(part, nparts, 8 * CHP, e, g) : 0.0;
+    const double tot = group_sum(sm, lane, g, s);
+    if (g == 0 && ok) sums[which * M + ch] = static_cast<float>(tot);
+}
+
+// fixed-order dot product: per-CTA partial (tree in shared memory), the last CTA adds the partials in index order
+__global__ void __launch_bounds__(256) dot_kernel(const float *__restrict__ a, const float *__restrict__ b, int64_t n,
+                                                  float *__restrict__ out, float *__restrict__ part, int *counter) {
+    __shared__ float red[256];
+    __shared__ int is_last;
+    const int t = threadIdx.x;
+    const bool vec = aligned16_dev(a) && aligned16_dev(b);
+    float s = 0.f;
+    if (vec) {
+        const int64_t n4 = n / 4;
+        const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b);
+        for (int64_t i = blockIdx.x * 256ll + t; i < n4; i += gridDim.x * 256ll) {
+            const float4 u = __ldg(a4 + i), v = __ldg(b4 + i);
+            s = fmaf(u.x, v.x, s); s = fmaf(u.y, v.y, s); s = fmaf(u.z, v.z, s); s = fmaf(u.w, v.w, s);
+        }
+        for (int64_t i = n4 * 4 + blockIdx.x * 256ll + t; i < n; i += gridDim.x * 256ll) s = fmaf(__ldg(a + i), __ldg(b + i), s);
+    } else {
+        for (int64_t i = blockIdx.x * 256ll + t; i < n; i += gridDim.x * 256ll) s = fmaf(__ldg(a + i), __ldg(b + i), s);
+    }
+    red[t] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) red[t] += red[t + o];
+        __syncthreads();
+    }
+    if (t == 0) {
+        part[blockIdx.x] = red[0];
+        __threadfence();
+        is_last = (atomicAdd(counter, 1) == static_cast<int>(gridDim.x) - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        __shared__ double dred[256];
+        double tot = 0.0;
+        for (int i = t; i < static_cast<int>(gridDim.x); i += 256) tot += static_cast<double>(__ldcg(part + i));
+        dred[t] = tot;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (t < o) dred[t] += dred[t + o];
+            __syncthreads();
+        }
+        if (t == 0) {
+            out[0] = static_cast<float>(dred[0]);
+            *counter = 0;
+        }
+    }
 }
 
 constexpr int pad32(int x) { return x <= 32 ? 32 : (x <= 64 ? 64 : 128); }   // padded channel counts: whole power-of-two panels
 
-size_t fwd_smem(int KP, int MP) { return 1024 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128 + (MP / 32) * PANEL128; }
+size_t fwd_smem(int KP, int MP) { return 1024 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128; }
 size_t bwd_smem(int KP, int MP) {
     return 1024 + 4 * (MP / 32) * PANEL128 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128;
 }
-int fwd_ctas_per_sm(size_t smem) { int n = static_cast<int>((220 * 1024) / smem); return n < 1 ? 1 : (n > 4 ? 4 : n); }
+int fwd_ctas_per_sm(size_t smem) { int n = static_cast<int>((224 * 1024) / (smem + 1024)); return n < 1 ? 1 : (n > 6 ? 6 : n); }
 
 template <int KP, int MP>
 int launch_fwd(const LinFwdArgs &a, int grid, cudaStream_t s) {
@@ -783,7 +854,7 @@ int32_t dn4gl_lin_supported(int32_t K, int32_t M) { return (K >= 1 && M >= 1 && 
 size_t dn4gl_lin_workspace_bytes(int64_t N, int32_t K, int32_t M) {
     if (!dn4gl_lin_supported(K, M)) return 0;
     const int KP = pad32(K), MP = pad32(M);
-    const size_t ctas = static_cast<size_t>(dn4gl_num_sms()) * 4;
+    const size_t ctas = static_cast<size_t>(dn4gl_num_sms()) * 6;
     const size_t fwd = ctas * MP * 4 * sizeof(float);
     const size_t bwd = ctas * (static_cast<size_t>(MP) * KP + MP + 2 * KP) * sizeof(float);
     (void)N;
@@ -794,11 +865,11 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
                       const float *W, const float *bias, int32_t M, float *Y,
                       const float *gamma, const float *beta, float eps, float momentum, float *bn_out,
                       float *running_mean, float *running_var, int64_t *num_batches_tracked,
-                      void *ws, size_t ws_bytes, int32_t *counter, void *stream) {
+                      void *ws, size_t ws_bytes, void *stream) {
     DN_ARG(N >= 0 && X != nullptr && W != nullptr && Y != nullptr);
     DN_ARG(dn4gl_lin_supported(K, M));
     DN_ARG(in_act >= DN4GL_ACT_NONE && in_act <= DN4GL_ACT_LEAKY_RELU);
-    DN_ARG(bn_out == nullptr || (ws != nullptr && counter != nullptr && ws_bytes >= dn4gl_lin_workspace_bytes(N, K, M)));
+    DN_ARG(bn_out == nullptr || (ws != nullptr && ws_bytes >= dn4gl_lin_workspace_bytes(N, K, M)));
     if (N == 0) return DN4GL_OK;
     DN_ARG(N < (static_cast<int64_t>(1) << 31) * 128);
     const int KP = pad32(K), MP = pad32(M);
@@ -808,7 +879,7 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
     a.gamma = gamma; a.beta = beta; a.eps = eps; a.momentum = momentum;
     a.bn_out = bn_out; a.run_mean = running_mean; a.run_var = running_var;
     a.nbt = reinterpret_cast<long long *>(num_batches_tracked);
-    a.part = static_cast<float *>(ws); a.counter = counter;
+    a.part = static_cast<float *>(ws);
     a.num_tiles = static_cast<int>(ceil_div64(N, 128));
     const int grid = tc_grid(N, fwd_smem(KP, MP));
     cudaStream_t s = as_stream(stream);
@@ -818,7 +889,13 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
     { dn4gl_set_error("dn4gl_lin_fwd_f32: no instantiation for K=%d M=%d", K, M); return DN4GL_EINVAL; }
 #undef DN_FWD_CASE
     if (rc) return rc;
-    DN_LAUNCHED();
+    if (bn_out != nullptr) {
+        bn_finalize_kernel<<<MP / 32, 1024, 0, s>>>(reinterpret_cast<const float4 *>(a.part), grid, MP, M, N, gamma, beta, eps,
+                                                    momentum, bn_out, running_mean, running_var, a.nbt);
+        DN_LAUNCHED_N(2);
+    } else {
+        DN_LAUNCHED();
+    }
     return DN4GL_OK;
 }
 
@@ -856,7 +933,7 @@ int dn4gl_lin_bwd_f32(const float *G, const float *Yout, int64_t N, int32_t M,
 #undef DN_BWD_CASE
     if (rc) return rc;
     const int elems = MP * KP + MP + 2 * KP;
-    lin_bwd_reduce_kernel<<<(elems + 127) / 128, 128, 0, s>>>(a.part, grid, MP, KP, M, K, dW, db, sums_prev);
+    lin_bwd_reduce_kernel<<<(elems + 31) / 32, 1024, 0, s>>>(a.part, grid, MP, KP, M, K, dW, db, sums_prev);
     DN_LAUNCHED_N(2);
     return DN4GL_OK;
 }
@@ -870,6 +947,22 @@ int dn4gl_bn_act_f32(const float *Y, int64_t N, int32_t M, const float *bn, int3
     const int64_t want = ceil_div64(total, 256 * 4);
     const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 8;
     bn_act_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(Y, N, M, bn, act, slope, out);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+size_t dn4gl_dot_workspace_bytes(int64_t n) {
+    (void)n;
+    return static_cast<size_t>(dn4gl_num_sms()) * 4 * sizeof(float);
+}
+
+int dn4gl_dot_f32(const float *a, const float *b, int64_t n, float *out, void *ws, size_t ws_bytes, int32_t *counter,
+                  void *stream) {
+    DN_ARG(n >= 0 && a != nullptr && b != nullptr && out != nullptr && ws != nullptr && counter != nullptr);
+    DN_ARG(ws_bytes >= dn4gl_dot_workspace_bytes(n));
+    const int64_t want = ceil_div64(n > 0 ? n : 1, 256 * 16);
+    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 4;
+    dot_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(a, b, n, out, static_cast<float *>(ws), counter);
     DN_LAUNCHED();
     return DN4GL_OK;
 }
@@ -902,7 +995,7 @@ int dn4gl_bn_bwd_sums_f32(const float *G, const float *Y, int64_t N, int32_t M, 
     case 16: bn_bwd_sums_kernel<16><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
     default: bn_bwd_sums_kernel<32><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
     }
-    bn_bwd_sums_reduce_kernel<<<(8 * CHP + 127) / 128, 128, 0, s>>>(part, grid, CHP, M, sums);
+    bn_bwd_sums_reduce_kernel<<<(8 * CHP + 31) / 32, 1024, 0, s>>>(part, grid, CHP, M, sums);
     DN_LAUNCHED_N(2);
     return DN4GL_OK;
 }

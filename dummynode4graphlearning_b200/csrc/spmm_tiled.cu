@@ -369,8 +369,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1)
 spmm_pipe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const float4 *__restrict__ x,
                  float4 *__restrict__ out, const int4 *__restrict__ tiles, int num_tiles,
                  const int32_t *__restrict__ heavy_list, const int32_t *__restrict__ heavy_count, float self_scale,
-                 int smem_bytes, int stages, int nnz_per_row) {
+                 const float *__restrict__ eps_dev, int smem_bytes, int stages, int nnz_per_row) {
     constexpr int DV = LANES * VEC;
+    if (eps_dev != nullptr) self_scale = 1.f + __ldg(eps_dev);   // trainable GIN eps lives on the device
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[TP_MAX_STAGES], empty_bar[TP_MAX_STAGES];
     const TileCfg L = tile_cfg(smem_bytes, stages, DV, nnz_per_row);
@@ -559,7 +560,7 @@ extern "C" int32_t dn4gl_spmm_tiled_cap_rows(int32_t D, int32_t smem_bytes, int3
 template <int LANES, int VEC, int NCW>
 static int launch_pipe(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, const int32_t *tile_desc,
                        int num_tiles, const int32_t *heavy_list, const int32_t *heavy_count, int heavy_cap,
-                       float self_scale, int smem_bytes, int stages, int nnz_per_row, cudaStream_t st) {
+                       float self_scale, const float *eps_dev, int smem_bytes, int stages, int nnz_per_row, cudaStream_t st) {
     static int attr_done = 0;
     if (attr_done < smem_bytes) {
         if (cudaFuncSetAttribute(spmm_pipe_kernel<LANES, VEC, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -573,13 +574,13 @@ static int launch_pipe(const int32_t *row_ptr, const int32_t *col, const float *
     if (grid < 1) grid = 1;
     spmm_pipe_kernel<LANES, VEC, NCW><<<grid, (NCW + 1) * 32, smem_bytes, st>>>(
         row_ptr, col, reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(out),
-        reinterpret_cast<const int4 *>(tile_desc), num_tiles, heavy_list, heavy_count, self_scale, smem_bytes, stages,
+        reinterpret_cast<const int4 *>(tile_desc), num_tiles, heavy_list, heavy_count, self_scale, eps_dev, smem_bytes, stages,
         nnz_per_row);
     return 0;
 }
 
 extern "C" int dn4gl_spmm_tiled_f32(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, int64_t N,
-                                    int32_t D, float self_scale, const int32_t *tile_desc, int32_t num_tiles,
+                                    int32_t D, float self_scale, const float *eps_dev, const int32_t *tile_desc, int32_t num_tiles,
                                     const int32_t *heavy_list, const int32_t *heavy_count, int32_t heavy_cap,
                                     int32_t smem_bytes, int32_t stages, int32_t nnz_per_row, int32_t warps,
                                     void *stream) {
@@ -597,7 +598,7 @@ extern "C" int dn4gl_spmm_tiled_f32(const int32_t *row_ptr, const int32_t *col, 
     }
     cudaStream_t st = as_stream(stream);
     int rc = 0;
-#define PIPE_ARGS row_ptr, col, x, out, tile_desc, num_tiles, heavy_list, heavy_count, heavy_cap, self_scale, smem_bytes, stages, nnz_per_row, st
+#define PIPE_ARGS row_ptr, col, x, out, tile_desc, num_tiles, heavy_list, heavy_count, heavy_cap, self_scale, eps_dev, smem_bytes, stages, nnz_per_row, st
 #define PIPE_CASE(L, V)                                                          \
     if constexpr (V == 1) {                                                      \
         if (warps == 32) rc = launch_pipe<L, V, 31>(PIPE_ARGS);                  \

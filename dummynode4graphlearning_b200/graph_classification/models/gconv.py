@@ -41,6 +41,9 @@ class GINConv(nn.Module):
 
     def forward(self, x, edge_index, structure=None):
         s = structure if structure is not None else self._structure(x, edge_index)
+        if x.is_cuda and ops.gin_mlp_fusable(self.nn):
+            # aggregation + Linear/BN/ReLU stages as one autograd node (tensor-core stages, eps read on the device)
+            return ops.gin_conv(self.nn, x, self.eps, s.csr_in, s.csr_out)
         if isinstance(self.eps, nn.Parameter) and self.eps.requires_grad:
             # trainable eps: keep d/d eps on the autograd tape (agg + (1 + eps) * x); the self term is one
             # elementwise op instead of being fused, the gather-sum is still K1.
@@ -103,6 +106,19 @@ class GIN(torch.nn.Module):
         out = 0
         for layer in range(self.no_layers):
             if layer == 0:
+                if x.is_cuda and ops.gin_mlp_fusable(self.first_h):
+                    x = ops.gin_mlp(self.first_h, x)
+                    # pool(Linear(x)) = Linear(pool(x)) with the bias counted once per pooled row: the class-score
+                    # GEMM runs on B rows instead of N
+                    lin = self.linears[0]
+                    pooled = self.pooling(x, data.batch, node_ptr=s.node_ptr)
+                    if self.pooling is global_add_pool:
+                        cnt = (s.node_ptr[1:] - s.node_ptr[:-1]).to(pooled.dtype).unsqueeze(1)
+                        score = ops.linear(pooled, lin.weight, None) + cnt * lin.bias
+                    else:
+                        score = lin(pooled)
+                    out += F.dropout(score, p=self.dropout)
+                    continue
                 x = self.first_h(x)
                 out += F.dropout(self.pooling(self.linears[layer](x), data.batch, node_ptr=s.node_ptr), p=self.dropout)
             else:

@@ -23,7 +23,8 @@ TILE_SMEM = None                                           # override of graph.T
 _TILED_D = (16, 32, 64, 128, 256, 512)
 
 
-def _spmm(csr: CSR, x, n_out, self_scale):
+def _spmm(csr: CSR, x, n_out, self_scale, eps_dev=None):
+    """eps_dev: optional device scalar; the kernel then uses self_scale = 1 + eps_dev (no host read)."""
     require_cuda(x, "features")
     x = _f32c(x)
     D = x.size(1)
@@ -31,11 +32,11 @@ def _spmm(csr: CSR, x, n_out, self_scale):
     if SPMM_MODE == "tiled" and csr.seg_ptr is not None and x.size(0) == n_out and D in _TILED_D:
         t = csr.tiles(D, TILE_SMEM)
         lib().call("dn4gl_spmm_tiled_f32", ptr(csr.row_ptr), ptr(csr.col), ptr(x), ptr(out), n_out, D,
-                   float(self_scale), ptr(t["desc"]), t["T"], ptr(t["heavy_list"]), ptr(t["heavy_count"]),
+                   float(self_scale), ptr(eps_dev), ptr(t["desc"]), t["T"], ptr(t["heavy_list"]), ptr(t["heavy_count"]),
                    t["heavy_cap"], t["smem"], t["stages"], t["npr"], t["warps"], _stream())
         return out
     lib().call("dn4gl_spmm_sum_f32", ptr(csr.row_ptr), ptr(csr.col), ptr(x), ptr(out), n_out, x.size(0), D,
-               float(self_scale), ptr(csr.heavy_rows), ptr(csr.heavy_count), csr.heavy_thr, _stream())
+               float(self_scale), ptr(eps_dev), ptr(csr.heavy_rows), ptr(csr.heavy_count), csr.heavy_thr, _stream())
     return out
 
 
@@ -331,7 +332,7 @@ def lin_fwd(x, weight, bias=None, in_bn=None, in_act=ACT_NONE, in_slope=0.0, bn=
     Y = torch.empty((N, M), dtype=torch.float32, device=x.device)
     rec = None
     wsb = L.size("dn4gl_lin_workspace_bytes", N, K, M)
-    ws, counter = _tc_ws(x.device, wsb)
+    ws, _ = _tc_ws(x.device, wsb)
     g = b = rm = rv = nbt = None
     eps = mom = 0.0
     if bn is not None:
@@ -340,7 +341,7 @@ def lin_fwd(x, weight, bias=None, in_bn=None, in_act=ACT_NONE, in_slope=0.0, bn=
         rm, rv, nbt = bn.get("running_mean"), bn.get("running_var"), bn.get("num_batches_tracked")
     L.call("dn4gl_lin_fwd_f32", ptr(x), N, K, ptr(in_bn), int(in_act), float(in_slope), ptr(_f32c(weight)),
            ptr(None if bias is None else _f32c(bias)), M, ptr(Y), ptr(g), ptr(b), eps, mom, ptr(rec), ptr(rm), ptr(rv),
-           ptr(nbt), ptr(ws), wsb, ptr(counter), _stream())
+           ptr(nbt), ptr(ws), wsb, _stream())
     return Y, rec
 
 
@@ -415,6 +416,54 @@ class _GinMlp(torch.autograd.Function):
         gz, _, dW1, db1 = lin_bwd(ga1, W1, z, Yout=y1, bn=rec1, sums=sums1, g_masked=True,
                                   want_gx=ctx.needs_input_grad[0])
         return (gz, dW1, db1, sums1[D1:], sums1[:D1], dW2, db2, sums2[D2:], sums2[:D2], None, None)
+
+
+def dot(a, b):
+    """sum(a * b) as a 1-element tensor, fixed-order."""
+    a, b = _f32c(a), _f32c(b)
+    L = lib()
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    wsb = L.size("dn4gl_dot_workspace_bytes", a.numel())
+    ws, counter = _tc_ws(a.device, wsb)
+    L.call("dn4gl_dot_f32", ptr(a), ptr(b), a.numel(), ptr(out), ptr(ws), wsb, ptr(counter), _stream())
+    return out
+
+
+class _GinConv(torch.autograd.Function):
+    """one GIN layer as ONE autograd node: h = MLP((1 + eps) x + sum_{j->i} x_j)  (gconv.py:212 + :190-196).
+    eps is a device scalar (Parameter or buffer) read by the aggregation kernel; d eps = sum(g_z * x)."""
+
+    @staticmethod
+    def forward(ctx, x, eps, W1, b1, g1, be1, W2, b2, g2, be2, bn1, bn2, csr_in, csr_out):
+        x = _f32c(x)
+        z = _spmm(csr_in, x, csr_in.n_rows, 1.0, eps)
+        y1, rec1 = lin_fwd(z, W1, b1, bn=bn1)
+        y2, rec2 = lin_fwd(y1, W2, b2, in_bn=rec1, in_act=ACT_RELU, bn=bn2)
+        h = bn_act(y2, rec2, ACT_RELU)
+        ctx.save_for_backward(x, eps, z, y1, y2, rec1, rec2, W1, W2)
+        ctx.csr_out = csr_out
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        x, eps, z, y1, y2, rec1, rec2, W1, W2 = ctx.saved_tensors
+        D1, D2 = W1.size(0), W2.size(0)
+        gh = _f32c(gh)
+        sums2 = bn_bwd_sums(gh, y2, rec2, ACT_RELU)
+        ga1, sums1, dW2, db2 = lin_bwd(gh, W2, y1, Yout=y2, bn=rec2, sums=sums2, g_masked=False, in_bn=rec1,
+                                       in_act=ACT_RELU)
+        need_z = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gz, _, dW1, db1 = lin_bwd(ga1, W1, z, Yout=y1, bn=rec1, sums=sums1, g_masked=True, want_gx=need_z)
+        gx = _spmm(ctx.csr_out, gz, x.size(0), 1.0, eps) if ctx.needs_input_grad[0] else None
+        geps = dot(gz, x).view_as(eps) if ctx.needs_input_grad[1] else None
+        return (gx, geps, dW1, db1, sums1[D1:], sums1[:D1], dW2, db2, sums2[D2:], sums2[:D2], None, None, None, None)
+
+
+def gin_conv(seq, x, eps, csr_in, csr_out):
+    """fused GINConv (aggregation + MLP); gin_mlp_fusable(seq) must hold and x.size(1) must be a tiled width."""
+    l1, n1, _, l2, n2, _ = seq
+    return _GinConv.apply(x, eps, l1.weight, l1.bias, n1.weight, n1.bias, l2.weight, l2.bias, n2.weight, n2.bias,
+                          _bn_dict(n1), _bn_dict(n2), csr_in, csr_out)
 
 
 def gin_mlp_fusable(seq):

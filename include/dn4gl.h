@@ -174,9 +174,11 @@ int dn4gl_coalesce(const int32_t *dst, int64_t N, int64_t E, const int32_t *row_
  * backward.  x has n_src rows, out has N rows (x may be a different table than out: RGIN gathers
  * from the (N*R, D) per-relation table).  Rows listed in heavy_rows (degree > heavy threshold,
  * e.g. dummy nodes) are reduced by a whole CTA; pass heavy_rows = NULL to let the per-row path
- * handle everything.  self_scale != 0 requires n_src == N.                                    */
+ * handle everything.  self_scale != 0 requires n_src == N.  eps_dev (may be NULL): a device scalar;
+ * when given, self_scale = 1 + *eps_dev is read by the kernel (GINConv(train_eps=True): eps is a
+ * Parameter on the device, gconv.py:197, and reading it on the host would synchronise).        */
 int dn4gl_spmm_sum_f32(const int32_t *row_ptr, const int32_t *col, const float *x, float *out,
-                       int64_t N, int64_t n_src, int32_t D, float self_scale,
+                       int64_t N, int64_t n_src, int32_t D, float self_scale, const float *eps_dev,
                        const int32_t *heavy_rows, const int32_t *heavy_count, int32_t heavy_threshold,
                        void *stream);
 
@@ -203,7 +205,7 @@ int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t window_rows,
                          int32_t heavy_cap, int32_t *heavy_count, void *stream);
 int32_t dn4gl_spmm_tiled_cap_rows(int32_t D, int32_t smem_bytes, int32_t stages, int32_t nnz_per_row);
 int dn4gl_spmm_tiled_f32(const int32_t *row_ptr, const int32_t *col, const float *x, float *out, int64_t N,
-                         int32_t D, float self_scale, const int32_t *tile_desc, int32_t num_tiles,
+                         int32_t D, float self_scale, const float *eps_dev, const int32_t *tile_desc, int32_t num_tiles,
                          const int32_t *heavy_list, const int32_t *heavy_count, int32_t heavy_cap,
                          int32_t smem_bytes, int32_t stages, int32_t nnz_per_row, int32_t warps, void *stream);
 
@@ -293,13 +295,12 @@ size_t dn4gl_lin_workspace_bytes(int64_t N, int32_t K, int32_t M);
  * If bn_out != NULL the per-channel batch statistics of Y (biased variance, eps) are reduced in a fixed order and
  * the record {mean, rstd, gamma*rstd, beta} (gamma / beta NULL = 1 / 0) is written to bn_out[4*M]; running_mean /
  * running_var (momentum, unbiased variance) and num_batches_tracked are updated in place when non-NULL -- the
- * training-mode semantics of nn.BatchNorm1d.  ws: dn4gl_lin_workspace_bytes; counter: one int32 that is 0 on entry
- * (the kernel leaves it 0).                                                                          */
+ * training-mode semantics of nn.BatchNorm1d.  ws: dn4gl_lin_workspace_bytes.                          */
 int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, int32_t in_act, float in_slope,
                       const float *W, const float *bias, int32_t M, float *Y,
                       const float *gamma, const float *beta, float eps, float momentum, float *bn_out,
                       float *running_mean, float *running_var, int64_t *num_batches_tracked,
-                      void *ws, size_t ws_bytes, int32_t *counter, void *stream);
+                      void *ws, size_t ws_bytes, void *stream);
 /* Backward of one stage  Y = X' W^T + b,  X' = act_in(bn_in(X)):
  *   gY = G                                  (bn == NULL), or the BatchNorm(+ReLU) backward of the stage OUTPUT:
  *        gm = G * [bn(Y) > 0] (skipped when g_masked), gY = k * (gm - s1/N - xhat * s2/N), xhat = (Y - mean) * rstd,
@@ -322,6 +323,12 @@ int dn4gl_bn_act_f32(const float *Y, int64_t N, int32_t M, const float *bn, int3
 size_t dn4gl_bn_bwd_sums_workspace_bytes(int64_t N, int32_t M);
 int dn4gl_bn_bwd_sums_f32(const float *G, const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope,
                           float *sums, void *ws, size_t ws_bytes, void *stream);
+
+/* out[0] = sum_i a[i] * b[i] over n floats, fixed-order (the gradient of GINConv's trainable eps: sum(g_z * x)).
+ * ws: dn4gl_dot_workspace_bytes; counter: one int32 that is 0 on entry (left 0).                                  */
+size_t dn4gl_dot_workspace_bytes(int64_t n);
+int dn4gl_dot_f32(const float *a, const float *b, int64_t n, float *out, void *ws, size_t ws_bytes, int32_t *counter,
+                  void *stream);
 
 /* ---- small fused elementwise helpers of the layers ------------------------------------------ */
 /* gather rows: out[i,:] = x[idx[i],:] (idx int32, n rows)                                       */
