@@ -81,10 +81,10 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
@@ -137,11 +137,13 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
     lo = __uint_as_float(l);
 }
-__device__ __forceinline__ void store_split(uint32_t hi_base, uint32_t lo_base, uint32_t off, const float4 &v) {
+// hi part to hi_base + off + off_hi, lo part to lo_base + off + off_lo
+__device__ __forceinline__ void store_split(uint32_t hi_base, uint32_t lo_base, uint32_t off, const float4 &v, uint32_t off_hi,
+                                            uint32_t off_lo) {
     float4 h, l;
     split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    sts128(hi_base + off, h);
-    sts128(lo_base + off, l);
+    sts128(hi_base + off + off_hi, h);
+    sts128(lo_base + off + off_lo, l);
 }
 // the same split value into two differently swizzled tiles (K-major copy + MN-major copy)
 __device__ __forceinline__ void store_split2(uint32_t hi_a, uint32_t lo_a, uint32_t off_a, uint32_t hi_b, uint32_t lo_b,
@@ -225,6 +227,25 @@ __device__ __forceinline__ void chunk_allreduce(float4 &v) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// raw-tile ring: a row tile of a row-major matrix is one contiguous slab, so ONE bulk asynchronous copy (TMA engine,
+// cp.async.bulk ... mbarrier::complete_tx) per matrix brings it into shared memory, RING tiles ahead of its use; the
+// global-load latency that bounded the first version of these kernels (profiles/r1c: long_scoreboard) is hidden.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// chunk c (16 bytes) of row r of a raw slab with `ncols` floats per row (ncols % 4 == 0), zero beyond ncols
+__device__ __forceinline__ float4 raw_chunk(uint32_t slab, int r, int ncols, int c) {
+    if (4 * c >= ncols) return zero4();
+    return lds128s(slab + static_cast<uint32_t>(r * ncols * 4 + c * 16));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // forward stage
 // ------------------------------------------------------------------------------------------------------------------
 struct LinFwdArgs {
@@ -232,36 +253,57 @@ struct LinFwdArgs {
     const float *in_bn; int in_act; float in_slope;
     const float *W; const float *bias; int M;
     float *Y;
-    const float *gamma; const float *beta; float eps; float momentum;
-    float *bn_out; float *run_mean; float *run_var; long long *nbt;
+    int stats;
     float *part;
     int num_tiles;
 };
 
-template <int KP, int MP>
+// B operand tile: per 32-float K panel the MP hi rows then the MP lo rows, so that ONE MMA with N = 2 MP multiplies
+// an A tile with [W_hi | W_lo]; accumulator columns [0, MP) and [MP, 2 MP) are added in the epilogue (all four
+// hi/lo products: 2 MMAs per k-step instead of 3, and the lo*lo term comes for free).
+template <int KP, int MP, int RING>
 __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int PK = KP / 32, PM = MP / 32;
-    constexpr uint32_t A_BYTES = PK * PANEL128, B_BYTES = PK * MP * 128u;
+    constexpr uint32_t A_BYTES = PK * PANEL128, B_BYTES = PK * 2 * MP * 128u, RAW_BYTES = 128u * KP * 4u;
     const uint32_t base = (s_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sAh = base, sAl = sAh + A_BYTES, sBh = sAl + A_BYTES, sBl = sBh + B_BYTES;
+    const uint32_t sAh = base, sAl = sAh + A_BYTES, sB = sAl + A_BYTES, sRing = sB + B_BYTES;
     const uint32_t sStage = sAh;      // the operand tiles are dead once the tile's MMAs have completed
     static_assert(2 * PK >= PM, "staging tile must fit the A operand tiles");
     __shared__ __align__(8) uint64_t bar_mem;
+    __shared__ __align__(8) uint64_t full_mem[RING > 0 ? RING : 1];
     __shared__ uint32_t tmem_ptr;
     __shared__ float red[4][MP * 2];
     __shared__ float shift_s[MP];
 
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     const uint32_t bar = s_u32(&bar_mem);
-    if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-    if (w == 0) tc_alloc(s_u32(&tmem_ptr), MP);
+    constexpr uint32_t TCOLS = 2 * MP;
+    if (t == 0) {
+        mbar_init(bar, 1);
+        for (int s = 0; s < RING; ++s) mbar_init(s_u32(&full_mem[s]), 1);
+        fence_barrier_init();
+    }
+    if (w == 0) tc_alloc(s_u32(&tmem_ptr), TCOLS);
+    __syncthreads();
+    // raw ring: tile j of this CTA lives in slot j % RING
+    auto issue = [&](int j) {
+        const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(j) * gridDim.x;
+        if (tile >= a.num_tiles) return;
+        const int64_t row0 = tile * 128, left = a.N - row0;
+        const uint32_t bytes = static_cast<uint32_t>((left < 128 ? left : 128) * a.K * 4);
+        const uint32_t fb = s_u32(&full_mem[j % (RING > 0 ? RING : 1)]);
+        mbar_expect_tx(fb, bytes);
+        bulk_g2s(sRing + (j % (RING > 0 ? RING : 1)) * RAW_BYTES, a.X + row0 * a.K, bytes, fb);
+    };
+    if (RING > 0 && t == 0)
+        for (int j = 0; j < RING - 1; ++j) issue(j);
     // weights: W (M x K) row-major = K-major B operand; zero-padded to MP x KP, split once
     const bool vecW = (a.K % 4 == 0) && aligned16_dev(a.W);
     for (int i = t; i < MP * (KP / 4); i += TC_THREADS) {
         const int m = i / (KP / 4), c = i % (KP / 4);
         const float4 v = (m < a.M) ? load_chunk(a.W, m, a.K, c, vecW) : zero4();
-        store_split(sBh, sBl, tile_off(m, c, MP), v);
+        store_split(sB, sB, 0, v, tile_off(m, c, 2 * MP), tile_off(MP + m, c, 2 * MP));
     }
     tc_fence_before();
     __syncthreads();
@@ -272,28 +314,36 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
     constexpr int CHo = MP / 4, RPo = TC_THREADS / CHo;    // output
     const int c_in = t % CH, r_in = t / CH, c_out = t % CHo, r_out = t / CHo;
     const bool vecX = (a.K % 4 == 0) && aligned16_dev(a.X), vecY = (a.M % 4 == 0) && aligned16_dev(a.Y);
-    const bool has_bn_in = a.in_bn != nullptr, stats = a.bn_out != nullptr;
+    const bool has_bn_in = a.in_bn != nullptr, stats = a.stats != 0;
     const Bn4 bi = load_bn4(a.in_bn, a.K, c_in);
     const float4 bias4 = load_vec4(a.bias, a.M, c_out);
     float4 S1 = zero4(), S2 = zero4(), shift4 = zero4();
     bool have_shift = false;
     float n_cta = 0.f;
-    constexpr uint32_t IDESC = make_idesc(128, MP, 0, 0);
+    constexpr uint32_t IDESC = make_idesc(128, 2 * MP, 0, 0);
     uint32_t phase = 0;
 
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    int j = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
         const int64_t row0 = static_cast<int64_t>(tile) * 128;
+        uint32_t slab = 0;
+        if (RING > 0) {
+            if (t == 0) issue(j + RING - 1);
+            mbar_wait(s_u32(&full_mem[j % (RING > 0 ? RING : 1)]), (j / (RING > 0 ? RING : 1)) & 1);
+            slab = sRing + (j % (RING > 0 ? RING : 1)) * RAW_BYTES;
+        }
         // ---- prologue: X tile -> bn/act -> hi/lo operand tiles
 #pragma unroll 4
         for (int i = 0; i < CH; ++i) {
             const int r = r_in + RP * i;
             const int64_t gr = row0 + r;
             float4 v = zero4();
-            if (gr < a.N) v = load_chunk(a.X, gr, a.K, c_in, vecX);
+            if (gr < a.N) v = RING > 0 ? raw_chunk(slab, r, a.K, c_in) : load_chunk(a.X, gr, a.K, c_in, vecX);
             if (has_bn_in) v = bn_apply(v, bi);
             v.x = act_f(v.x, a.in_act, a.in_slope); v.y = act_f(v.y, a.in_act, a.in_slope);
             v.z = act_f(v.z, a.in_act, a.in_slope); v.w = act_f(v.w, a.in_act, a.in_slope);
-            store_split(sAh, sAl, tile_off(r, c_in, 128), v);
+            const uint32_t off = tile_off(r, c_in, 128);
+            store_split(sAh, sAl, off, v, 0, 0);
         }
         fence_async_smem();
         __syncthreads();
@@ -301,14 +351,12 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
             tc_fence_after();
             uint32_t acc = 0;
 #pragma unroll
-            for (int j = 0; j < KP / 8; ++j) {
-                const uint32_t aoff = (j >> 2) * PANEL128 + (j & 3) * 32u, boff = (j >> 2) * (MP * 128u) + (j & 3) * 32u;
-                const uint64_t ah = make_desc(sAh + aoff, 16, 1024), al = make_desc(sAl + aoff, 16, 1024);
-                const uint64_t bh = make_desc(sBh + boff, 16, 1024), bl = make_desc(sBl + boff, 16, 1024);
-                tc_mma_tf32(tmem, ah, bh, IDESC, acc);
+            for (int jj = 0; jj < KP / 8; ++jj) {
+                const uint32_t aoff = (jj >> 2) * PANEL128 + (jj & 3) * 32u, boff = (jj >> 2) * (2 * MP * 128u) + (jj & 3) * 32u;
+                const uint64_t bd = make_desc(sB + boff, 16, 1024);
+                tc_mma_tf32(tmem, make_desc(sAh + aoff, 16, 1024), bd, IDESC, acc);
                 acc = 1;
-                tc_mma_tf32(tmem, al, bh, IDESC, 1);
-                tc_mma_tf32(tmem, ah, bl, IDESC, 1);
+                tc_mma_tf32(tmem, make_desc(sAl + aoff, 16, 1024), bd, IDESC, 1);
             }
             tc_commit(bar);
         }
@@ -316,14 +364,17 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
         phase ^= 1;
         __syncwarp();
         tc_fence_after();
-        // ---- accumulators -> staging tile (thread = row)
+        // ---- accumulators -> staging tile (thread = row): columns c and MP + c are the [W_hi | W_lo] halves
 #pragma unroll
         for (int cb = 0; cb < PM; ++cb) {
-            float v[32];
+            float v[32], u[32];
             tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, v);
+            tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + MP + cb * 32, u);
+            tc_wait_ld();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                sts128(sStage + tile_off(t, cb * 8 + q, 128), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                sts128(sStage + tile_off(t, cb * 8 + q, 128),
+                       make_float4(v[4 * q] + u[4 * q], v[4 * q + 1] + u[4 * q + 1], v[4 * q + 2] + u[4 * q + 2], v[4 * q + 3] + u[4 * q + 3]));
         }
         tc_fence_before();
         __syncthreads();
@@ -354,7 +405,7 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
     }
 
     if (stats) {
-        // per-CTA partial (n, shift, S1, S2) per channel, then the last CTA merges all partials in a fixed order
+        // per-CTA partial (n, shift, S1, S2) per channel; bn_finalize_kernel merges all partials in a fixed order
         chunk_allreduce<CHo>(S1);
         chunk_allreduce<CHo>(S2);
         if (lane < (CHo < 32 ? CHo : 32)) {
@@ -369,7 +420,6 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
         }
         __syncthreads();
         if (t < MP) {
-            // CHo < 32: every warp saw every chunk; CHo == 32: likewise (one row per warp per pass)
             const float s1 = red[0][t] + red[1][t] + red[2][t] + red[3][t];
             const float s2 = red[0][MP + t] + red[1][MP + t] + red[2][MP + t] + red[3][MP + t];
             reinterpret_cast<float4 *>(a.part)[static_cast<size_t>(blockIdx.x) * MP + t] = make_float4(n_cta, shift_s[t], s1, s2);
@@ -377,7 +427,7 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
     }
     tc_fence_before();
     __syncthreads();
-    if (w == 0) tc_dealloc(tmem, MP);
+    if (w == 0) tc_dealloc(tmem, TCOLS);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -393,35 +443,61 @@ struct LinBwdArgs {
     int num_tiles;
 };
 
-template <int KP, int MP>
+// per-CTA partial record: dW as the four hi/lo blocks the MMA produces ([2 MP] x [2 KP]), db (MP), previous sums (2 KP)
+__host__ __device__ constexpr int bwd_part_floats(int KP, int MP) { return 4 * MP * KP + MP + 2 * KP; }
+
+template <int KP, int MP, int RING>
 __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int PK = KP / 32, PM = MP / 32;
     constexpr uint32_t G_BYTES = PM * PANEL128, X_BYTES = PK * PANEL128, W_BYTES = PK * MP * 128u;
+    constexpr uint32_t RAW_G = 128u * MP * 4u, RAW_X = 128u * KP * 4u, RAW_SLOT = 2 * RAW_G + RAW_X;
     const uint32_t base = (s_u32(smem_raw) + 1023u) & ~1023u;
-    // gY is kept twice: MN-major copy (weight gradient, contraction over rows) first -- its M = 128 MMA reads 4 panels
-    // from each base, so everything it can touch stays inside the allocation -- then the K-major copy (data gradient)
+    // gY is kept twice: MN-major copy (weight gradient, contraction over rows; hi panels then lo panels = the M blocks
+    // of ONE MMA) first, then the K-major copy (data gradient).  X' hi then lo panels = the N blocks of that MMA.
     const uint32_t sGmh = base, sGml = sGmh + G_BYTES, sGh = sGml + G_BYTES, sGl = sGh + G_BYTES;
-    const uint32_t sXh = sGl + G_BYTES, sXl = sXh + X_BYTES, sWh = sXl + X_BYTES, sWl = sWh + W_BYTES;
+    const uint32_t sXh = sGl + G_BYTES, sXl = sXh + X_BYTES, sWh = sXl + X_BYTES, sWl = sWh + W_BYTES, sRing = sWl + W_BYTES;
     const uint32_t sStage = sGh;        // the K-major gY copy is dead once the tile's MMAs have completed
     static_assert(2 * PM >= PK, "staging tile must fit the K-major gY copy");
+    static_assert(2 * MP <= 128, "the weight-gradient MMA stacks gY hi and lo along M = 128");
     __shared__ __align__(8) uint64_t bar_mem;
+    __shared__ __align__(8) uint64_t full_mem[RING > 0 ? RING : 1];
     __shared__ uint32_t tmem_ptr;
     float (*red)[MP + 2 * KP] = reinterpret_cast<float (*)[MP + 2 * KP]>(smem_raw + (sXh - s_u32(smem_raw)));   // used after the last MMA
 
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     const uint32_t bar = s_u32(&bar_mem);
-    constexpr uint32_t TCOLS = 2 * KP;
-    if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    constexpr uint32_t TCOLS = 4 * KP;          // data accumulator [0, 2 KP), weight accumulator [2 KP, 4 KP)
+    if (t == 0) {
+        mbar_init(bar, 1);
+        for (int s = 0; s < RING; ++s) mbar_init(s_u32(&full_mem[s]), 1);
+        fence_barrier_init();
+    }
     if (w == 0) tc_alloc(s_u32(&tmem_ptr), TCOLS);
-    const bool want_gx = a.GX != nullptr;
-    // weights as they are stored: rows m (the data GEMM's K), k contiguous (its N) -> MN-major B operand
+    __syncthreads();
+    const bool want_gx = a.GX != nullptr, has_bn = a.bn != nullptr, has_bn_in = a.in_bn != nullptr;
+    auto issue = [&](int j) {
+        const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(j) * gridDim.x;
+        if (tile >= a.num_tiles) return;
+        const int64_t row0 = tile * 128, left = a.N - row0;
+        const uint32_t rows = static_cast<uint32_t>(left < 128 ? left : 128);
+        const uint32_t gb = rows * a.M * 4u, xb = rows * a.K * 4u;
+        const uint32_t slot = sRing + (j % (RING > 0 ? RING : 1)) * RAW_SLOT, fb = s_u32(&full_mem[j % (RING > 0 ? RING : 1)]);
+        mbar_expect_tx(fb, gb * (has_bn ? 2u : 1u) + xb);
+        bulk_g2s(slot, a.G + row0 * a.M, gb, fb);
+        if (has_bn) bulk_g2s(slot + RAW_G, a.Yo + row0 * a.M, gb, fb);
+        bulk_g2s(slot + 2 * RAW_G, a.X + row0 * a.K, xb, fb);
+    };
+    if (RING > 0 && t == 0)
+        for (int j = 0; j < RING - 1; ++j) issue(j);
+    // weights as they are stored: rows m (the data GEMM's K), k contiguous (its N) -> MN-major B operand,
+    // hi panels then lo panels = the N blocks of one MMA
     const bool vecW = (a.K % 4 == 0) && aligned16_dev(a.W);
     if (want_gx) {
         for (int i = t; i < MP * (KP / 4); i += TC_THREADS) {
             const int m = i / (KP / 4), c = i % (KP / 4);
             const float4 v = (m < a.M) ? load_chunk(a.W, m, a.K, c, vecW) : zero4();
-            store_split(sWh, sWl, tile_off_mn(m, c, MP), v);
+            store_split(sWh, sWl, tile_off_mn(m, c, MP), v, 0, 0);
         }
     }
     tc_fence_before();
@@ -434,7 +510,6 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
     const int c_m = t % CHm, r_m = t / CHm, c_k = t % CHk, r_k = t / CHk;
     const bool vecG = (a.M % 4 == 0) && aligned16_dev(a.G) && (a.Yo == nullptr || aligned16_dev(a.Yo));
     const bool vecX = (a.K % 4 == 0) && aligned16_dev(a.X), vecGX = (a.K % 4 == 0) && aligned16_dev(a.GX);
-    const bool has_bn = a.bn != nullptr, has_bn_in = a.in_bn != nullptr;
     const Bn4 bo = load_bn4(a.bn, a.M, c_m), bi = load_bn4(a.in_bn, a.K, c_k);
     float4 m1 = zero4(), m2 = zero4();
     if (has_bn) {
@@ -444,13 +519,20 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
         m2 = make_float4(s2.x * invN, s2.y * invN, s2.z * invN, s2.w * invN);
     }
     float4 db4 = zero4(), sp1 = zero4(), sp2 = zero4();
-    constexpr uint32_t IDESC_DATA = make_idesc(128, KP, 0, 1);   // gY (K-major) x W (MN-major)
-    constexpr uint32_t IDESC_WGT = make_idesc(128, KP, 1, 1);    // gY^T (MN-major) x X' (MN-major)
+    constexpr uint32_t IDESC_DATA = make_idesc(128, 2 * KP, 0, 1);   // gY (K-major) x [W_hi | W_lo] (MN-major)
+    constexpr uint32_t IDESC_WGT = make_idesc(128, 2 * KP, 1, 1);    // [gY_hi ; gY_lo]^T (MN-major) x [X'_hi | X'_lo] (MN-major)
     uint32_t phase = 0;
     bool first = true;
 
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    int j = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
         const int64_t row0 = static_cast<int64_t>(tile) * 128;
+        uint32_t slab = 0;
+        if (RING > 0) {
+            if (t == 0) issue(j + RING - 1);
+            mbar_wait(s_u32(&full_mem[j % (RING > 0 ? RING : 1)]), (j / (RING > 0 ? RING : 1)) & 1);
+            slab = sRing + (j % (RING > 0 ? RING : 1)) * RAW_SLOT;
+        }
         // ---- prologue A: gradient of the stage's linear output, gY (BatchNorm backward folded in)
 #pragma unroll 4
         for (int i = 0; i < CHm; ++i) {
@@ -458,9 +540,9 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
             const int64_t gr = row0 + r;
             float4 g = zero4();
             if (gr < a.N) {
-                g = load_chunk(a.G, gr, a.M, c_m, vecG);
+                g = RING > 0 ? raw_chunk(slab, r, a.M, c_m) : load_chunk(a.G, gr, a.M, c_m, vecG);
                 if (has_bn) {
-                    const float4 y = load_chunk(a.Yo, gr, a.M, c_m, vecG);
+                    const float4 y = RING > 0 ? raw_chunk(slab + RAW_G, r, a.M, c_m) : load_chunk(a.Yo, gr, a.M, c_m, vecG);
                     const float4 xc = make_float4(y.x - bo.mean.x, y.y - bo.mean.y, y.z - bo.mean.z, y.w - bo.mean.w);
                     if (!a.g_masked) {
                         if (!(fmaf(xc.x, bo.k.x, bo.beta.x) > 0.f)) g.x = 0.f;
@@ -484,42 +566,37 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
             const int64_t gr = row0 + r;
             float4 v = zero4();
             if (gr < a.N) {
-                v = load_chunk(a.X, gr, a.K, c_k, vecX);
+                v = RING > 0 ? raw_chunk(slab + 2 * RAW_G, r, a.K, c_k) : load_chunk(a.X, gr, a.K, c_k, vecX);
                 if (has_bn_in) v = bn_apply(v, bi);
                 v.x = act_f(v.x, a.in_act, a.in_slope); v.y = act_f(v.y, a.in_act, a.in_slope);
                 v.z = act_f(v.z, a.in_act, a.in_slope); v.w = act_f(v.w, a.in_act, a.in_slope);
             }
-            store_split(sXh, sXl, tile_off_mn(r, c_k, 128), v);
+            store_split(sXh, sXl, tile_off_mn(r, c_k, 128), v, 0, 0);
         }
         fence_async_smem();
         __syncthreads();
         if (t == 0) {
             tc_fence_after();
             if (want_gx) {
-                // data gradient: (128 x MP) x (MP x KP); k-steps of 8 output channels
+                // data gradient: (128 x MP) x (MP x [KP hi | KP lo]); k-steps of 8 output channels
                 uint32_t acc = 0;
 #pragma unroll
-                for (int j = 0; j < MP / 8; ++j) {
-                    const uint32_t aoff = (j >> 2) * PANEL128 + (j & 3) * 32u, boff = j * 1024u;
-                    const uint64_t ah = make_desc(sGh + aoff, 16, 1024), al = make_desc(sGl + aoff, 16, 1024);
-                    const uint64_t bh = make_desc_mn(sWh + boff, MP * 128u), bl = make_desc_mn(sWl + boff, MP * 128u);
-                    tc_mma_tf32(tmem, ah, bh, IDESC_DATA, acc);
+                for (int jj = 0; jj < MP / 8; ++jj) {
+                    const uint32_t aoff = (jj >> 2) * PANEL128 + (jj & 3) * 32u;
+                    const uint64_t bd = make_desc_mn(sWh + jj * 1024u, MP * 128u);
+                    tc_mma_tf32(tmem, make_desc(sGh + aoff, 16, 1024), bd, IDESC_DATA, acc);
                     acc = 1;
-                    tc_mma_tf32(tmem, al, bh, IDESC_DATA, 1);
-                    tc_mma_tf32(tmem, ah, bl, IDESC_DATA, 1);
+                    tc_mma_tf32(tmem, make_desc(sGl + aoff, 16, 1024), bd, IDESC_DATA, 1);
                 }
             }
-            // weight gradient: (MP [128 lanes] x 128 rows) x (128 rows x KP); k-steps of 8 rows, accumulated over tiles
+            // weight gradient: ([MP hi ; MP lo ; ...] x 128 rows) x (128 rows x [KP hi | KP lo]); k-steps of 8 rows,
+            // accumulated over all tiles of this CTA
             uint32_t accw = first ? 0u : 1u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t off = j * 1024u;
-                const uint64_t ah = make_desc_mn(sGmh + off, PANEL128), al = make_desc_mn(sGml + off, PANEL128);
-                const uint64_t bh = make_desc_mn(sXh + off, PANEL128), bl = make_desc_mn(sXl + off, PANEL128);
-                tc_mma_tf32(tmem + KP, ah, bh, IDESC_WGT, accw);
+            for (int jj = 0; jj < 16; ++jj) {
+                tc_mma_tf32(tmem + 2 * KP, make_desc_mn(sGmh + jj * 1024u, PANEL128), make_desc_mn(sXh + jj * 1024u, PANEL128),
+                            IDESC_WGT, accw);
                 accw = 1;
-                tc_mma_tf32(tmem + KP, al, bh, IDESC_WGT, 1);
-                tc_mma_tf32(tmem + KP, ah, bl, IDESC_WGT, 1);
             }
             tc_commit(bar);
         }
@@ -531,11 +608,14 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
         if (want_gx) {
 #pragma unroll
             for (int cb = 0; cb < PK; ++cb) {
-                float v[32];
+                float v[32], u[32];
                 tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, v);
+                tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + KP + cb * 32, u);
+                tc_wait_ld();
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    sts128(sStage + tile_off(t, cb * 8 + q, 128), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                    sts128(sStage + tile_off(t, cb * 8 + q, 128),
+                           make_float4(v[4 * q] + u[4 * q], v[4 * q + 1] + u[4 * q + 1], v[4 * q + 2] + u[4 * q + 2], v[4 * q + 3] + u[4 * q + 3]));
             }
             tc_fence_before();
             __syncthreads();
@@ -547,7 +627,7 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
                 if (gr < a.N) {
                     float4 g = lds128s(sStage + tile_off(r, c_k, 128));
                     if (a.in_act != DN4GL_ACT_NONE || has_bn_in) {
-                        const float4 x = load_chunk(a.X, gr, a.K, c_k, vecX);
+                        const float4 x = RING > 0 ? raw_chunk(slab + 2 * RAW_G, r, a.K, c_k) : load_chunk(a.X, gr, a.K, c_k, vecX);
                         if (has_bn_in) {
                             const float4 xc = make_float4(x.x - bi.mean.x, x.y - bi.mean.y, x.z - bi.mean.z, x.w - bi.mean.w);
                             g.x *= dact_f(fmaf(xc.x, bi.k.x, bi.beta.x), a.in_act, a.in_slope);
@@ -565,18 +645,19 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
                     store_chunk(a.GX, gr, a.K, c_k, g, vecGX);
                 }
             }
-            __syncthreads();   // the staging tile aliases the K-major gY copy the next prologue overwrites
         }
+        __syncthreads();   // staging aliases the K-major gY copy; the ring slot of this tile is refilled next iteration
     }
 
-    // ---- per-CTA partials: dW (MP x KP, from tensor memory), db (MP), previous-stage sums (2 KP)
-    float *part = a.part + static_cast<size_t>(blockIdx.x) * (MP * KP + MP + 2 * KP);
-    if (w * 32 < MP) {
+    // ---- per-CTA partials: dW blocks (2 MP x 2 KP, from tensor memory), db (MP), previous-stage sums (2 KP)
+    float *part = a.part + static_cast<size_t>(blockIdx.x) * bwd_part_floats(KP, MP);
+    if (w * 32 < 2 * MP) {
 #pragma unroll
-        for (int cb = 0; cb < PK; ++cb) {
+        for (int cb = 0; cb < 2 * PK; ++cb) {
             float v[32];
-            tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + KP + cb * 32, v);
-            float4 *dst = reinterpret_cast<float4 *>(part + t * KP + cb * 32);
+            tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + 2 * KP + cb * 32, v);
+            tc_wait_ld();
+            float4 *dst = reinterpret_cast<float4 *>(part + t * (2 * KP) + cb * 32);
 #pragma unroll
             for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
@@ -596,7 +677,7 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
     }
     __syncthreads();
     for (int i = t; i < MP + 2 * KP; i += TC_THREADS)
-        part[MP * KP + i] = red[0][i] + red[1][i] + red[2][i] + red[3][i];
+        part[4 * MP * KP + i] = red[0][i] + red[1][i] + red[2][i] + red[3][i];
     tc_fence_before();
     __syncthreads();
     if (w == 0) tc_dealloc(tmem, TCOLS);
@@ -624,26 +705,31 @@ __device__ __forceinline__ double group_sum(double (*sm)[33], int lane, int g, d
     return tot;
 }
 
-// dW / db / previous-stage sums
+// dW / db / previous-stage sums.  dW[m][k] is the sum of the four hi/lo blocks of the weight accumulator.
 __global__ void __launch_bounds__(1024)
 lin_bwd_reduce_kernel(const float *__restrict__ part, int nparts, int MP, int KP, int M, int K,
                       float *__restrict__ dW, float *__restrict__ db, float *__restrict__ sums_prev) {
     __shared__ double sm[32][33];
-    const int stride = MP * KP + MP + 2 * KP;
+    const int stride = bwd_part_floats(KP, MP);
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int e = blockIdx.x * 32 + lane;
+    const int e = blockIdx.x * 32 + lane;                 // logical element: [MP*KP dW | MP db | 2 KP sums]
     float *dst = nullptr;
+    double s = 0.0;
     if (e < MP * KP) {
         const int m = e / KP, k = e % KP;
-        if (m < M && k < K && dW) dst = dW + m * K + k;
+        if (m < M && k < K && dW) {
+            dst = dW + m * K + k;
+            s = partial_column_sum(part, nparts, stride, m * 2 * KP + k, g) + partial_column_sum(part, nparts, stride, m * 2 * KP + KP + k, g) +
+                partial_column_sum(part, nparts, stride, (MP + m) * 2 * KP + k, g) +
+                partial_column_sum(part, nparts, stride, (MP + m) * 2 * KP + KP + k, g);
+        }
     } else if (e < MP * KP + MP) {
         const int m = e - MP * KP;
-        if (m < M && db) dst = db + m;
-    } else if (e < stride) {
+        if (m < M && db) { dst = db + m; s = partial_column_sum(part, nparts, stride, 4 * MP * KP + m, g); }
+    } else if (e < MP * KP + MP + 2 * KP) {
         const int i = e - MP * KP - MP, which = i / KP, k = i % KP;
-        if (k < K && sums_prev) dst = sums_prev + which * K + k;
+        if (k < K && sums_prev) { dst = sums_prev + which * K + k; s = partial_column_sum(part, nparts, stride, 4 * MP * KP + MP + i, g); }
     }
-    const double s = dst != nullptr ? partial_column_sum(part, nparts, stride, e, g) : 0.0;
     const double tot = group_sum(sm, lane, g, s);
     if (g == 0 && dst != nullptr) *dst = static_cast<float>(tot);
 }
@@ -818,31 +904,65 @@ __global__ void __launch_bounds__(256) dot_kernel(const float *__restrict__ a, c
 
 constexpr int pad32(int x) { return x <= 32 ? 32 : (x <= 64 ? 64 : 128); }   // padded channel counts: whole power-of-two panels
 
-size_t fwd_smem(int KP, int MP) { return 1024 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128; }
-size_t bwd_smem(int KP, int MP) {
-    return 1024 + 4 * (MP / 32) * PANEL128 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128;
+constexpr int RING_FWD = 3, RING_BWD = 2;
+constexpr size_t fwd_smem_c(int KP, int MP, int ring) {
+    return 1024 + 2 * (KP / 32) * 16384 + 2 * (KP / 32) * MP * 128 + static_cast<size_t>(ring) * 128 * KP * 4;
 }
-int fwd_ctas_per_sm(size_t smem) { int n = static_cast<int>((224 * 1024) / (smem + 1024)); return n < 1 ? 1 : (n > 6 ? 6 : n); }
-
-template <int KP, int MP>
-int launch_fwd(const LinFwdArgs &a, int grid, cudaStream_t s) {
-    const size_t smem = fwd_smem(KP, MP);
-    DN_CUDA(cudaFuncSetAttribute(lin_fwd_kernel<KP, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    lin_fwd_kernel<KP, MP><<<grid, TC_THREADS, smem, s>>>(a);
-    return 0;
+constexpr size_t bwd_smem_c(int KP, int MP, int ring) {
+    return 1024 + 4 * (MP / 32) * 16384 + 2 * (KP / 32) * 16384 + 2 * (KP / 32) * MP * 128 + static_cast<size_t>(ring) * 128 * (2 * MP + KP) * 4;
 }
-template <int KP, int MP>
-int launch_bwd(const LinBwdArgs &a, int grid, cudaStream_t s) {
-    const size_t smem = bwd_smem(KP, MP);
-    DN_CUDA(cudaFuncSetAttribute(lin_bwd_kernel<KP, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    lin_bwd_kernel<KP, MP><<<grid, TC_THREADS, smem, s>>>(a);
-    return 0;
+constexpr size_t SMEM_CAP = 227 * 1024 - 4096;     // dynamic shared memory a CTA may ask for (static part + slack kept back)
+size_t fwd_smem(int KP, int MP, int ring) {
+    return 1024 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128 + static_cast<size_t>(ring) * 128 * KP * 4;
 }
-
-int tc_grid(int64_t N, size_t smem) {
+size_t bwd_smem(int KP, int MP, int ring) {
+    return 1024 + 4 * (MP / 32) * PANEL128 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128 +
+           static_cast<size_t>(ring) * 128 * (2 * MP + KP) * 4;
+}
+int ctas_per_sm(size_t smem, int tmem_cols) {
+    int n = static_cast<int>((227 * 1024) / (smem + 2048));
+    const int by_tmem = 512 / tmem_cols;
+    if (n > by_tmem) n = by_tmem;
+    return n < 1 ? 1 : (n > 4 ? 4 : n);
+}
+int tc_grid(int64_t N, size_t smem, int tmem_cols) {
     const int64_t tiles = ceil_div64(N, 128);
-    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * fwd_ctas_per_sm(smem);
+    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * ctas_per_sm(smem, tmem_cols);
     return static_cast<int>(tiles < cap ? tiles : cap);
+}
+
+template <int KP, int MP, int RING>
+int launch_fwd(const LinFwdArgs &a, int *grid_out, cudaStream_t s) {
+    const size_t smem = fwd_smem(KP, MP, RING);
+    const int grid = tc_grid(a.N, smem, 2 * MP);
+    DN_CUDA(cudaFuncSetAttribute(lin_fwd_kernel<KP, MP, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    lin_fwd_kernel<KP, MP, RING><<<grid, TC_THREADS, smem, s>>>(a);
+    *grid_out = grid;
+    return 0;
+}
+template <int KP, int MP, int RING>
+int launch_bwd(const LinBwdArgs &a, int *grid_out, cudaStream_t s) {
+    const size_t smem = bwd_smem(KP, MP, RING);
+    const int grid = tc_grid(a.N, smem, 4 * KP);
+    DN_CUDA(cudaFuncSetAttribute(lin_bwd_kernel<KP, MP, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    lin_bwd_kernel<KP, MP, RING><<<grid, TC_THREADS, smem, s>>>(a);
+    *grid_out = grid;
+    return 0;
+}
+// the raw ring needs 16-byte slabs (row length a multiple of 4 floats, aligned bases) and room in shared memory
+template <int KP, int MP>
+int dispatch_fwd(const LinFwdArgs &a, bool ring_ok, int *grid_out, cudaStream_t s) {
+    if constexpr (fwd_smem_c(KP, MP, RING_FWD) <= SMEM_CAP) {
+        if (ring_ok) return launch_fwd<KP, MP, RING_FWD>(a, grid_out, s);
+    }
+    return launch_fwd<KP, MP, 0>(a, grid_out, s);
+}
+template <int KP, int MP>
+int dispatch_bwd(const LinBwdArgs &a, bool ring_ok, int *grid_out, cudaStream_t s) {
+    if constexpr (bwd_smem_c(KP, MP, RING_BWD) <= SMEM_CAP) {
+        if (ring_ok) return launch_bwd<KP, MP, RING_BWD>(a, grid_out, s);
+    }
+    return launch_bwd<KP, MP, 0>(a, grid_out, s);
 }
 
 }  // namespace
@@ -854,9 +974,9 @@ int32_t dn4gl_lin_supported(int32_t K, int32_t M) { return (K >= 1 && M >= 1 && 
 size_t dn4gl_lin_workspace_bytes(int64_t N, int32_t K, int32_t M) {
     if (!dn4gl_lin_supported(K, M)) return 0;
     const int KP = pad32(K), MP = pad32(M);
-    const size_t ctas = static_cast<size_t>(dn4gl_num_sms()) * 6;
+    const size_t ctas = static_cast<size_t>(dn4gl_num_sms()) * 4;
     const size_t fwd = ctas * MP * 4 * sizeof(float);
-    const size_t bwd = ctas * (static_cast<size_t>(MP) * KP + MP + 2 * KP) * sizeof(float);
+    const size_t bwd = ctas * static_cast<size_t>(bwd_part_floats(KP, MP)) * sizeof(float);
     (void)N;
     return align_up(fwd > bwd ? fwd : bwd, 256);
 }
@@ -876,22 +996,21 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
     LinFwdArgs a;
     a.X = X; a.N = N; a.K = K; a.in_bn = in_bn; a.in_act = in_act; a.in_slope = in_slope;
     a.W = W; a.bias = bias; a.M = M; a.Y = Y;
-    a.gamma = gamma; a.beta = beta; a.eps = eps; a.momentum = momentum;
-    a.bn_out = bn_out; a.run_mean = running_mean; a.run_var = running_var;
-    a.nbt = reinterpret_cast<long long *>(num_batches_tracked);
+    a.stats = bn_out != nullptr ? 1 : 0;
     a.part = static_cast<float *>(ws);
     a.num_tiles = static_cast<int>(ceil_div64(N, 128));
-    const int grid = tc_grid(N, fwd_smem(KP, MP));
     cudaStream_t s = as_stream(stream);
-    int rc = 0;
-#define DN_FWD_CASE(kp, mp) if (KP == kp && MP == mp) rc = launch_fwd<kp, mp>(a, grid, s); else
+    const bool ring_ok = (K % 4 == 0) && aligned16(X);
+    int rc = 0, grid = 0;
+#define DN_FWD_CASE(kp, mp) if (KP == kp && MP == mp) rc = dispatch_fwd<kp, mp>(a, ring_ok, &grid, s); else
     DN_FWD_CASE(32, 32) DN_FWD_CASE(32, 64) DN_FWD_CASE(64, 32) DN_FWD_CASE(64, 64)
     { dn4gl_set_error("dn4gl_lin_fwd_f32: no instantiation for K=%d M=%d", K, M); return DN4GL_EINVAL; }
 #undef DN_FWD_CASE
     if (rc) return rc;
     if (bn_out != nullptr) {
         bn_finalize_kernel<<<MP / 32, 1024, 0, s>>>(reinterpret_cast<const float4 *>(a.part), grid, MP, M, N, gamma, beta, eps,
-                                                    momentum, bn_out, running_mean, running_var, a.nbt);
+                                                    momentum, bn_out, running_mean, running_var,
+                                                    reinterpret_cast<long long *>(num_batches_tracked));
         DN_LAUNCHED_N(2);
     } else {
         DN_LAUNCHED();
@@ -925,9 +1044,9 @@ int dn4gl_lin_bwd_f32(const float *G, const float *Yout, int64_t N, int32_t M,
     a.W = W; a.K = K; a.X = X; a.in_bn = in_bn; a.in_act = in_act; a.in_slope = in_slope;
     a.GX = GX; a.part = static_cast<float *>(ws);
     a.num_tiles = static_cast<int>(ceil_div64(N, 128));
-    const int grid = tc_grid(N, bwd_smem(KP, MP));
-    int rc = 0;
-#define DN_BWD_CASE(kp, mp) if (KP == kp && MP == mp) rc = launch_bwd<kp, mp>(a, grid, s); else
+    const bool ring_ok = (K % 4 == 0) && (M % 4 == 0) && aligned16(X) && aligned16(G) && (Yout == nullptr || aligned16(Yout));
+    int rc = 0, grid = 0;
+#define DN_BWD_CASE(kp, mp) if (KP == kp && MP == mp) rc = dispatch_bwd<kp, mp>(a, ring_ok, &grid, s); else
     DN_BWD_CASE(32, 32) DN_BWD_CASE(32, 64) DN_BWD_CASE(64, 32) DN_BWD_CASE(64, 64)
     { dn4gl_set_error("dn4gl_lin_bwd_f32: no instantiation for K=%d M=%d", K, M); return DN4GL_EINVAL; }
 #undef DN_BWD_CASE
