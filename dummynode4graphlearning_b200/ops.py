@@ -311,6 +311,9 @@ def lin_supported(K, M):
 def _tc_ws(device, nbytes):
     """(workspace, zeroed int32 counter) per (device, stream): the kernels consume the workspace before the next
     launch on the same stream starts, and leave the counter at zero."""
+    if torch.cuda.is_current_stream_capturing():   # a CUDA graph owns its scratch (allocated from the graph's pool)
+        return (torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device),
+                torch.zeros(1, dtype=torch.int32, device=device))
     key = (device.index, _stream())
     ent = _tc_scratch.get(key)
     if ent is None or ent[0].numel() < nbytes:

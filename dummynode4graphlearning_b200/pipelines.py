@@ -14,8 +14,9 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import ops
 from . import transforms as T
-from .graph import BatchedGraph
+from .graph import CSR, BatchedGraph
 from .graph_classification.data import Batch
 from .parallel import GradientBucket, is_distributed
 
@@ -45,16 +46,97 @@ def upload(b, device):
     return out
 
 
+def _structure_tensors(data):
+    """every device tensor the GIN / RGIN train step reads from a compiled Batch, in a fixed order, plus the host
+    scalars that are baked into kernel arguments (the CUDA-graph signature)."""
+    s = data.structure
+    tensors = [data.x, data.y, s.node_ptr]
+    scalars = [s.num_nodes]
+    for csr in (s.csr_in, s.csr_out):
+        tensors += [csr.row_ptr, csr.col, csr.heavy_rows, csr.heavy_count]
+        scalars += [csr.n_rows, csr.nnz, csr.heavy_thr, csr.max_seg]
+        for key in sorted(csr._tiles):
+            t = csr._tiles[key]
+            tensors += [t["desc"], t["heavy_list"], t["heavy_count"]]
+            scalars += [key] + [t[k] for k in ("T", "heavy_cap", "smem", "stages", "npr", "window", "cap_rows", "warps")]
+    return tensors, scalars
+
+
+def _signature(data):
+    tensors, scalars = _structure_tensors(data)
+    return (tuple(None if t is None else (tuple(t.shape), t.dtype) for t in tensors), tuple(scalars))
+
+
+def _static_clone(data):
+    """a Batch with the same compiled structure whose tensors are private copies (the buffers a captured CUDA graph
+    reads); returns (batch, tensor list in _structure_tensors order)."""
+    import copy
+    s0 = data.structure
+    d = Batch(data.x.clone(), None, None, y=data.y.clone())
+    s = copy.copy(s0)
+    s.node_ptr = s0.node_ptr.clone()
+    s._rel = {}
+    for name in ("csr_in", "csr_out"):
+        c0 = getattr(s0, name)
+        c = CSR(c0.row_ptr.clone(), c0.col.clone(), None, c0.n_rows, c0.nnz)
+        c.heavy_rows = None if c0.heavy_rows is None else c0.heavy_rows.clone()
+        c.heavy_count = None if c0.heavy_count is None else c0.heavy_count.clone()
+        c.heavy_thr, c.seg_ptr, c.max_seg = c0.heavy_thr, s.node_ptr, c0.max_seg
+        for key, t in c0._tiles.items():
+            c._tiles[key] = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in t.items()}
+        setattr(s, name, c)
+    d._structure = s
+    return d, _structure_tensors(d)[0]
+
+
+class _CapturedStep:
+    """one CUDA graph of (forward, loss, backward, gradient all-reduce, optimizer step) for ONE batch signature.
+    Replaying it does all of that work again on the data currently held by the static buffers."""
+
+    def __init__(self, pipe, data):
+        self.batch, self.static = _static_clone(data)
+        self.replays = 0
+        self.graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        from ._lib import lib
+        k0 = lib().kernel_launches()
+        # the AccumulateGrad nodes were created by the eager steps on the default stream; capture runs them on the
+        # capture stream, which is intended here
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        with torch.cuda.graph(self.graph):
+            self.loss = pipe._train_body(self.batch)
+        self.library_kernels = lib().kernel_launches() - k0   # libdn4gl kernels inside the graph (launched per replay)
+
+    def run(self, data):
+        src = _structure_tensors(data)[0]
+        pairs = [(d, s) for d, s in zip(self.static, src) if d is not None]
+        torch._foreach_copy_([d for d, _ in pairs], [s for _, s in pairs])
+        self.graph.replay()
+        self.replays += 1
+        return self.loss
+
+
 class ClassificationPipeline:
     def __init__(self, model, optimizer, mode="conj", num_node_labels=None, num_edge_labels=None,
-                 node_label_min=None, with_edge_attr=False):
-        """mode: 'dummy' (DUMMY_ graphs), 'conj' (CONJ_: dummy + edge-to-vertex), 'line' (LINE_), 'raw'."""
+                 node_label_min=None, with_edge_attr=False, cuda_graphs=None, max_graphs=8):
+        """mode: 'dummy' (DUMMY_ graphs), 'conj' (CONJ_: dummy + edge-to-vertex), 'line' (LINE_), 'raw'.
+
+        cuda_graphs: replay the train step (forward + loss + backward + all-reduce + optimizer) as a CUDA graph when a
+        batch has the same signature (tensor shapes + tiling scalars) as an earlier one: the first occurrence of a
+        signature runs eagerly, the second is captured, later ones are replayed (a ~300-launch step is host-bound
+        otherwise, profiles/).  Needs an optimizer whose step is capturable (``torch.optim.Adam(capturable=True)``);
+        default: on exactly when the optimizer is."""
         self.model, self.opt, self.mode = model, optimizer, mode
         self.nvl, self.nel = num_node_labels, num_edge_labels
         self.node_label_min, self.with_edge_attr = node_label_min, with_edge_attr
         self.bucket = GradientBucket(model.parameters())
         self.device = next(model.parameters()).device
         self.global_batch = None
+        capturable = all(g.get("capturable", False) for g in optimizer.param_groups)
+        self.cuda_graphs = capturable if cuda_graphs is None else bool(cuda_graphs)
+        if self.cuda_graphs and not capturable:
+            raise ValueError("cuda_graphs=True needs an optimizer built with capturable=True")
+        self._graphs, self._max_graphs = {}, max_graphs
 
     def transform(self, dev_batch):
         """raw TU-shaped device batch -> PyG-style Batch with compiled structure."""
@@ -69,20 +151,42 @@ class ClassificationPipeline:
         can = T.pyg_canonicalize(b, self.nvl, self.nel, node_label_min=self.node_label_min,
                                  with_edge_attr=self.with_edge_attr)
         data = Batch.from_canonical(can)
-        data.structure  # compile the CSR pair now (part of the transform cost)
+        s = data.structure  # compile the CSR pair now (part of the transform cost)
+        hid = getattr(self.model, "hidden_dim", None)
+        if hid in ops._TILED_D and s.node_ptr is not None:   # ... and the aggregation tiling for the model's width
+            s.csr_in.tiles(hid)
+            s.csr_out.tiles(hid)
         return data
 
-    def train_on(self, data):
-        self.model.train()
+    def _train_body(self, data):
         self.bucket.zero()
         out = self.model(data)
         loss = F.nll_loss(out, data.y)                      # main.py:41
         loss.backward()
+        self.bucket._ensure()                               # gradients live in one flat buffer from the first step on
         if is_distributed():
             gb = self.global_batch or data.num_graphs * torch.distributed.get_world_size()
             self.bucket.all_reduce(data.num_graphs / gb)
         self.opt.step()                                     # main.py:43
         return loss
+
+    def replayed_library_kernels(self):
+        """libdn4gl kernels launched through CUDA-graph replays so far (they bypass the library's launch counter)."""
+        return sum(e.replays * e.library_kernels for e in self._graphs.values() if isinstance(e, _CapturedStep))
+
+    def train_on(self, data):
+        self.model.train()
+        if not self.cuda_graphs:
+            return self._train_body(data)
+        sig = _signature(data)
+        ent = self._graphs.get(sig)
+        if ent is None:                                     # first time this signature is seen: a normal eager step
+            if len(self._graphs) < self._max_graphs:
+                self._graphs[sig] = "seen"
+            return self._train_body(data)
+        if ent == "seen":
+            ent = self._graphs[sig] = _CapturedStep(self, data)
+        return ent.run(data)
 
     def step_resident(self, dev_batch):
         """inputs already in HBM: transform + train step; returns the loss tensor (no host sync)."""

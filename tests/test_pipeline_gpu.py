@@ -1,0 +1,53 @@
+"""ClassificationPipeline: the CUDA-graph replay of the train step must be the same computation as the eager step."""
+from argparse import Namespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cuda_graphs, steps, seeds):
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+    from dummynode4graphlearning_b200.pipelines import ClassificationPipeline
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    args = Namespace(num_features=4, hidden_dim=32, num_classes=2, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": 3, "aggregation": "sum"}, epochs=1, device="cuda:0")
+    model = GIN(args).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, capturable=True)
+    pipe = ClassificationPipeline(model, opt, mode="conj", num_node_labels=4, node_label_min=0, cuda_graphs=cuda_graphs)
+    batches = {s: T.to_device({k: v for k, v in synth.tu_batch("proteins", 48, seed=s).items() if k != "vattr"}, dev)
+               for s in set(seeds)}
+    losses = []
+    for i in range(steps):
+        losses.append(float(pipe.step_resident(batches[seeds[i % len(seeds)]]).item()))
+    return losses, {k: v.detach().clone() for k, v in model.state_dict().items()}, pipe
+
+
+def test_graph_replay_equals_eager_steps():
+    seeds = [1, 2, 1, 1, 2, 1, 2, 2]          # two signatures, interleaved: eager, eager, capture, replay, capture, ...
+    le, se, _ = _run(False, len(seeds), seeds)
+    lg, sg, pipe = _run(True, len(seeds), seeds)
+    assert pipe.replayed_library_kernels() > 0, "no CUDA graph was replayed"
+    for a, b in zip(le, lg):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (le, lg)
+    for k in se:
+        if se[k].is_floating_point():
+            denom = float(se[k].abs().max().clamp_min(1e-12))
+            assert float((se[k] - sg[k]).abs().max()) / denom <= 1e-5, k
+        else:
+            assert torch.equal(se[k], sg[k]), k
+
+
+def test_graphs_need_capturable_optimizer():
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+    from dummynode4graphlearning_b200.pipelines import ClassificationPipeline
+    args = Namespace(num_features=4, hidden_dim=32, num_classes=2, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": 2, "aggregation": "sum"}, epochs=1, device="cuda:0")
+    model = GIN(args).to("cuda:0")
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    assert ClassificationPipeline(model, opt).cuda_graphs is False
+    with pytest.raises(ValueError):
+        ClassificationPipeline(model, opt, cuda_graphs=True)
