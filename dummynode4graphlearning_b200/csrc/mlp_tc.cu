@@ -261,8 +261,8 @@ struct LinFwdArgs {
 // B operand tile: per 32-float K panel the MP hi rows then the MP lo rows, so that ONE MMA with N = 2 MP multiplies
 // an A tile with [W_hi | W_lo]; accumulator columns [0, MP) and [MP, 2 MP) are added in the epilogue (all four
 // hi/lo products: 2 MMAs per k-step instead of 3, and the lo*lo term comes for free).
-template <int KP, int MP, int RING>
-__global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a) {
+template <int KP, int MP, int RING, int NT>
+__global__ void __launch_bounds__(NT) lin_fwd_kernel(const LinFwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int PK = KP / 32, PM = MP / 32;
     constexpr uint32_t A_BYTES = PK * PANEL128, B_BYTES = PK * 2 * MP * 128u, RAW_BYTES = 128u * KP * 4u;
@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
     __shared__ __align__(8) uint64_t bar_mem;
     __shared__ __align__(8) uint64_t full_mem[RING > 0 ? RING : 1];
     __shared__ uint32_t tmem_ptr;
-    __shared__ float red[4][MP * 2];
+    constexpr int NW = NT / 32;
+    __shared__ float red[NW][MP * 2];
     __shared__ float shift_s[MP];
 
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
         for (int j = 0; j < RING - 1; ++j) issue(j);
     // weights: W (M x K) row-major = K-major B operand; zero-padded to MP x KP, split once
     const bool vecW = (a.K % 4 == 0) && aligned16_dev(a.W);
-    for (int i = t; i < MP * (KP / 4); i += TC_THREADS) {
+    for (int i = t; i < MP * (KP / 4); i += NT) {
         const int m = i / (KP / 4), c = i % (KP / 4);
         const float4 v = (m < a.M) ? load_chunk(a.W, m, a.K, c, vecW) : zero4();
         store_split(sB, sB, 0, v, tile_off(m, c, 2 * MP), tile_off(MP + m, c, 2 * MP));
@@ -310,8 +311,8 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
     tc_fence_after();
     const uint32_t tmem = tmem_ptr;
 
-    constexpr int CH = KP / 4, RP = TC_THREADS / CH;       // input: chunks per row, rows per pass (CH passes)
-    constexpr int CHo = MP / 4, RPo = TC_THREADS / CHo;    // output
+    constexpr int CH = KP / 4, RP = NT / CH;       // input: chunks per row, rows per pass (CH passes)
+    constexpr int CHo = MP / 4, RPo = NT / CHo;    // output
     const int c_in = t % CH, r_in = t / CH, c_out = t % CHo, r_out = t / CHo;
     const bool vecX = (a.K % 4 == 0) && aligned16_dev(a.X), vecY = (a.M % 4 == 0) && aligned16_dev(a.Y);
     const bool has_bn_in = a.in_bn != nullptr, stats = a.stats != 0;
@@ -333,8 +334,8 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
             slab = sRing + (j % (RING > 0 ? RING : 1)) * RAW_BYTES;
         }
         // ---- prologue: X tile -> bn/act -> hi/lo operand tiles
-#pragma unroll 4
-        for (int i = 0; i < CH; ++i) {
+#pragma unroll
+        for (int i = 0; i < 128 / RP; ++i) {
             const int r = r_in + RP * i;
             const int64_t gr = row0 + r;
             float4 v = zero4();
@@ -364,9 +365,10 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
         phase ^= 1;
         __syncwarp();
         tc_fence_after();
-        // ---- accumulators -> staging tile (thread = row): columns c and MP + c are the [W_hi | W_lo] halves
+        // ---- accumulators -> staging tile (thread = row, warps 0..3 own the TMEM lane quadrants): columns c and
+        // MP + c are the [W_hi | W_lo] halves
 #pragma unroll
-        for (int cb = 0; cb < PM; ++cb) {
+        for (int cb = 0; cb < (w < 4 ? PM : 0); ++cb) {
             float v[32], u[32];
             tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, v);
             tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + MP + cb * 32, u);
@@ -384,8 +386,8 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
             shift4 = make_float4(s.x + bias4.x, s.y + bias4.y, s.z + bias4.z, s.w + bias4.w);
             have_shift = true;
         }
-#pragma unroll 4
-        for (int i = 0; i < CHo; ++i) {
+#pragma unroll
+        for (int i = 0; i < 128 / RPo; ++i) {
             const int r = r_out + RPo * i;
             const int64_t gr = row0 + r;
             if (gr < a.N) {
@@ -420,8 +422,9 @@ __global__ void __launch_bounds__(TC_THREADS) lin_fwd_kernel(const LinFwdArgs a)
         }
         __syncthreads();
         if (t < MP) {
-            const float s1 = red[0][t] + red[1][t] + red[2][t] + red[3][t];
-            const float s2 = red[0][MP + t] + red[1][MP + t] + red[2][MP + t] + red[3][MP + t];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) { s1 += red[ww][t]; s2 += red[ww][MP + t]; }
             reinterpret_cast<float4 *>(a.part)[static_cast<size_t>(blockIdx.x) * MP + t] = make_float4(n_cta, shift_s[t], s1, s2);
         }
     }
@@ -446,8 +449,8 @@ struct LinBwdArgs {
 // per-CTA partial record: dW as the four hi/lo blocks the MMA produces ([2 MP] x [2 KP]), db (MP), previous sums (2 KP)
 __host__ __device__ constexpr int bwd_part_floats(int KP, int MP) { return 4 * MP * KP + MP + 2 * KP; }
 
-template <int KP, int MP, int RING>
-__global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a) {
+template <int KP, int MP, int RING, int NT>
+__global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int PK = KP / 32, PM = MP / 32;
     constexpr uint32_t G_BYTES = PM * PANEL128, X_BYTES = PK * PANEL128, W_BYTES = PK * MP * 128u;
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
     // hi panels then lo panels = the N blocks of one MMA
     const bool vecW = (a.K % 4 == 0) && aligned16_dev(a.W);
     if (want_gx) {
-        for (int i = t; i < MP * (KP / 4); i += TC_THREADS) {
+        for (int i = t; i < MP * (KP / 4); i += NT) {
             const int m = i / (KP / 4), c = i % (KP / 4);
             const float4 v = (m < a.M) ? load_chunk(a.W, m, a.K, c, vecW) : zero4();
             store_split(sWh, sWl, tile_off_mn(m, c, MP), v, 0, 0);
@@ -505,8 +508,8 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
     tc_fence_after();
     const uint32_t tmem = tmem_ptr;
 
-    constexpr int CHm = MP / 4, RPm = TC_THREADS / CHm;    // gradient / output-channel side
-    constexpr int CHk = KP / 4, RPk = TC_THREADS / CHk;    // input-channel side
+    constexpr int CHm = MP / 4, RPm = NT / CHm;    // gradient / output-channel side
+    constexpr int CHk = KP / 4, RPk = NT / CHk;    // input-channel side
     const int c_m = t % CHm, r_m = t / CHm, c_k = t % CHk, r_k = t / CHk;
     const bool vecG = (a.M % 4 == 0) && aligned16_dev(a.G) && (a.Yo == nullptr || aligned16_dev(a.Yo));
     const bool vecX = (a.K % 4 == 0) && aligned16_dev(a.X), vecGX = (a.K % 4 == 0) && aligned16_dev(a.GX);
@@ -534,8 +537,8 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
             slab = sRing + (j % (RING > 0 ? RING : 1)) * RAW_SLOT;
         }
         // ---- prologue A: gradient of the stage's linear output, gY (BatchNorm backward folded in)
-#pragma unroll 4
-        for (int i = 0; i < CHm; ++i) {
+#pragma unroll
+        for (int i = 0; i < 128 / RPm; ++i) {
             const int r = r_m + RPm * i;
             const int64_t gr = row0 + r;
             float4 g = zero4();
@@ -560,8 +563,8 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
             store_split2(sGh, sGl, tile_off(r, c_m, 128), sGmh, sGml, tile_off_mn(r, c_m, 128), g);
         }
         // ---- prologue B: the stage's forward input as the GEMM saw it, X' = act(bn_in(X))
-#pragma unroll 4
-        for (int i = 0; i < CHk; ++i) {
+#pragma unroll
+        for (int i = 0; i < 128 / RPk; ++i) {
             const int r = r_k + RPk * i;
             const int64_t gr = row0 + r;
             float4 v = zero4();
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
         tc_fence_after();
         if (want_gx) {
 #pragma unroll
-            for (int cb = 0; cb < PK; ++cb) {
+            for (int cb = 0; cb < (w < 4 ? PK : 0); ++cb) {
                 float v[32], u[32];
                 tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, v);
                 tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + KP + cb * 32, u);
@@ -620,8 +623,8 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
             tc_fence_before();
             __syncthreads();
             // ---- cooperative epilogue: activation mask of the previous stage + its BatchNorm-backward sums
-#pragma unroll 4
-            for (int i = 0; i < CHk; ++i) {
+#pragma unroll
+            for (int i = 0; i < 128 / RPk; ++i) {
                 const int r = r_k + RPk * i;
                 const int64_t gr = row0 + r;
                 if (gr < a.N) {
@@ -676,8 +679,12 @@ __global__ void __launch_bounds__(TC_THREADS) lin_bwd_kernel(const LinBwdArgs a)
         red[w][KP + c0] = sp2.x; red[w][KP + c0 + 1] = sp2.y; red[w][KP + c0 + 2] = sp2.z; red[w][KP + c0 + 3] = sp2.w;
     }
     __syncthreads();
-    for (int i = t; i < MP + 2 * KP; i += TC_THREADS)
-        part[4 * MP * KP + i] = red[0][i] + red[1][i] + red[2][i] + red[3][i];
+    for (int i = t; i < MP + 2 * KP; i += NT) {
+        float sum = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < NT / 32; ++ww) sum += red[ww][i];
+        part[4 * MP * KP + i] = sum;
+    }
     tc_fence_before();
     __syncthreads();
     if (w == 0) tc_dealloc(tmem, TCOLS);
@@ -919,33 +926,35 @@ size_t bwd_smem(int KP, int MP, int ring) {
     return 1024 + 4 * (MP / 32) * PANEL128 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128 +
            static_cast<size_t>(ring) * 128 * (2 * MP + KP) * 4;
 }
-int ctas_per_sm(size_t smem, int tmem_cols) {
+int ctas_per_sm(size_t smem, int tmem_cols, int threads) {
     int n = static_cast<int>((227 * 1024) / (smem + 2048));
-    const int by_tmem = 512 / tmem_cols;
+    const int by_tmem = 512 / tmem_cols, by_threads = 1024 / threads;
     if (n > by_tmem) n = by_tmem;
+    if (n > by_threads) n = by_threads;
     return n < 1 ? 1 : (n > 4 ? 4 : n);
 }
-int tc_grid(int64_t N, size_t smem, int tmem_cols) {
+int tc_grid(int64_t N, size_t smem, int tmem_cols, int threads) {
     const int64_t tiles = ceil_div64(N, 128);
-    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * ctas_per_sm(smem, tmem_cols);
+    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * ctas_per_sm(smem, tmem_cols, threads);
     return static_cast<int>(tiles < cap ? tiles : cap);
 }
 
+constexpr int NT_FWD = 256, NT_BWD = 512;
 template <int KP, int MP, int RING>
 int launch_fwd(const LinFwdArgs &a, int *grid_out, cudaStream_t s) {
     const size_t smem = fwd_smem(KP, MP, RING);
-    const int grid = tc_grid(a.N, smem, 2 * MP);
-    DN_CUDA(cudaFuncSetAttribute(lin_fwd_kernel<KP, MP, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    lin_fwd_kernel<KP, MP, RING><<<grid, TC_THREADS, smem, s>>>(a);
+    const int grid = tc_grid(a.N, smem, 2 * MP, NT_FWD);
+    DN_CUDA(cudaFuncSetAttribute(lin_fwd_kernel<KP, MP, RING, NT_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    lin_fwd_kernel<KP, MP, RING, NT_FWD><<<grid, NT_FWD, smem, s>>>(a);
     *grid_out = grid;
     return 0;
 }
 template <int KP, int MP, int RING>
 int launch_bwd(const LinBwdArgs &a, int *grid_out, cudaStream_t s) {
     const size_t smem = bwd_smem(KP, MP, RING);
-    const int grid = tc_grid(a.N, smem, 4 * KP);
-    DN_CUDA(cudaFuncSetAttribute(lin_bwd_kernel<KP, MP, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    lin_bwd_kernel<KP, MP, RING><<<grid, TC_THREADS, smem, s>>>(a);
+    const int grid = tc_grid(a.N, smem, 4 * KP, NT_BWD);
+    DN_CUDA(cudaFuncSetAttribute(lin_bwd_kernel<KP, MP, RING, NT_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    lin_bwd_kernel<KP, MP, RING, NT_BWD><<<grid, NT_BWD, smem, s>>>(a);
     *grid_out = grid;
     return 0;
 }
