@@ -12,9 +12,11 @@ from ..graph import build_csr
 class GraphStructure:
     """CSR by destination / by source + per-graph node offsets of a PyG-style batch."""
 
-    def __init__(self, edge_index, num_nodes, batch=None, node_ptr=None, max_seg=None):
-        src = edge_index[0].to(torch.int32).contiguous()
-        dst = edge_index[1].to(torch.int32).contiguous()
+    def __init__(self, edge_index, num_nodes, batch=None, node_ptr=None, max_seg=None, src=None, dst=None):
+        """edge_index (2, E) int64 as PyG carries it, or the int32 endpoint arrays src / dst directly."""
+        if src is None:
+            src = edge_index[0].to(torch.int32).contiguous()
+            dst = edge_index[1].to(torch.int32).contiguous()
         self.src, self.dst, self.num_nodes = src, dst, int(num_nodes)
         self.csr_in = build_csr(dst, src, self.num_nodes)
         self.csr_out = build_csr(src, dst, self.num_nodes)
@@ -44,12 +46,27 @@ class GraphStructure:
 
 
 class Batch:
+    """``edge_index`` / ``batch`` / ``is_dummy_node`` may be given as zero-argument callables: they are then built on
+    first access (the GIN train step never reads them -- it uses the compiled structure)."""
+
     def __init__(self, x, edge_index, batch, edge_attr=None, y=None, is_dummy_node=None, is_dummy_edge=None,
-                 node_ptr=None, max_graph_nodes=None):
-        self.x, self.edge_index, self.batch, self.edge_attr, self.y = x, edge_index, batch, edge_attr, y
-        self.is_dummy_node, self.is_dummy_edge = is_dummy_node, is_dummy_edge
+                 node_ptr=None, max_graph_nodes=None, src=None, dst=None):
+        self.x, self.edge_attr, self.y = x, edge_attr, y
+        self._lazy = dict(edge_index=edge_index, batch=batch, is_dummy_node=is_dummy_node)
+        self.is_dummy_edge = is_dummy_edge
         self._node_ptr, self._max_seg = node_ptr, max_graph_nodes
+        self._src, self._dst = src, dst
         self._structure = None
+
+    def _get(self, name):
+        v = self._lazy[name]
+        if callable(v):
+            v = self._lazy[name] = v()
+        return v
+
+    edge_index = property(lambda self: self._get("edge_index"))
+    batch = property(lambda self: self._get("batch"))
+    is_dummy_node = property(lambda self: self._get("is_dummy_node"))
 
     @property
     def num_graphs(self):
@@ -58,15 +75,20 @@ class Batch:
     @property
     def structure(self):
         if self._structure is None:
-            self._structure = GraphStructure(self.edge_index, self.x.size(0), self.batch, self._node_ptr, self._max_seg)
+            if self._src is not None:
+                self._structure = GraphStructure(None, self.x.size(0), None if self._node_ptr is not None else self.batch,
+                                                 self._node_ptr, self._max_seg, src=self._src, dst=self._dst)
+            else:
+                self._structure = GraphStructure(self.edge_index, self.x.size(0), self.batch, self._node_ptr, self._max_seg)
         return self._structure
 
     @staticmethod
     def from_canonical(d):
         """from ``transforms.pyg_canonicalize`` output."""
-        return Batch(d["x"], d["edge_index"], d["batch"], d.get("edge_attr"), d.get("y"),
-                     d.get("is_dummy_node"), d.get("is_dummy_edge"), node_ptr=d["node_ptr"],
-                     max_graph_nodes=d.get("max_graph_nodes"))
+        lazy = lambda k: (lambda: d[k]) if k in d else None
+        return Batch(d["x"], lazy("edge_index"), lazy("batch"), d.get("edge_attr"), d.get("y"),
+                     lazy("is_dummy_node"), d.get("is_dummy_edge"), node_ptr=d["node_ptr"],
+                     max_graph_nodes=d.get("max_graph_nodes"), src=d.get("src"), dst=d.get("dst"))
 
 
 def structure_of(data):

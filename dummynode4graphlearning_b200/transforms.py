@@ -26,6 +26,62 @@ from ._lib import lib, ptr
 from .graph import _pending_err, _stream, build_csr, require_cuda
 
 
+class LazyDict(dict):
+    """batch dict whose derived columns (ids, flags, int64 views, ...) are computed on first access: the train step of
+    GIN reads only a few of the columns the reference's files carry, and every skipped column is a few launches."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._lazy = {}
+
+    def lazy(self, key, fn):
+        self._lazy[key] = fn
+
+    def __missing__(self, key):
+        fn = self._lazy.pop(key, None)
+        if fn is None:
+            raise KeyError(key)
+        v = fn()
+        self[key] = v
+        return v
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def pop(self, key, *default):
+        self._lazy.pop(key, None)
+        return dict.pop(self, key, *default)
+
+    def materialize(self):
+        for k in list(self._lazy):
+            self[k]
+        return self
+
+    def keys(self):
+        self.materialize()
+        return dict.keys(self)
+
+    def items(self):
+        self.materialize()
+        return dict.items(self)
+
+    def values(self):
+        self.materialize()
+        return dict.values(self)
+
+    def __iter__(self):
+        self.materialize()
+        return dict.__iter__(self)
+
+
+def _take(t, idx_i32):
+    """t[idx] for an int32 index tensor (one launch, no int64 copy of the index)."""
+    return torch.index_select(t, 0, idx_i32)
+
+
 def to_device(b, device):
     """numpy/tensor batch dict -> int32 (float32 for *attr) device tensors."""
     dev = torch.device(device)
@@ -58,16 +114,16 @@ def tu_add_dummy(b):
     require_cuda(b["src"], "batch")
     dev = b["src"].device
     B, N, E = int(b["num_graphs"]), int(b["vlabel"].numel()), int(b["src"].numel())
-    o = dict(num_graphs=B, node_ptr=_empty_i32(B + 1, dev), edge_ptr=_empty_i32(B + 1, dev),
-             src=_empty_i32(E + 2 * N, dev), dst=_empty_i32(E + 2 * N, dev),
-             vlabel=_empty_i32(N + B, dev), v_is_dummy=_empty_i32(N + B, dev),
-             elabel=_empty_i32(E + 2 * N, dev), e_is_dummy=_empty_i32(E + 2 * N, dev))
+    o = LazyDict(num_graphs=B, node_ptr=_empty_i32(B + 1, dev), edge_ptr=_empty_i32(B + 1, dev),
+                 src=_empty_i32(E + 2 * N, dev), dst=_empty_i32(E + 2 * N, dev),
+                 vlabel=_empty_i32(N + B, dev), v_is_dummy=_empty_i32(N + B, dev),
+                 elabel=_empty_i32(E + 2 * N, dev), e_is_dummy=_empty_i32(E + 2 * N, dev))
     lib().call("dn4gl_tu_add_dummy", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
                ptr(b["vlabel"]), ptr(b["elabel"]), N, E,
                ptr(o["node_ptr"]), ptr(o["edge_ptr"]), ptr(o["src"]), ptr(o["dst"]),
                ptr(o["vlabel"]), ptr(o["v_is_dummy"]), ptr(o["elabel"]), ptr(o["e_is_dummy"]), _stream())
-    o["vid"] = _local_ids(o["node_ptr"], N + B, dev)
-    o["eid"] = _local_ids(o["edge_ptr"], E + 2 * N, dev)
+    o.lazy("vid", lambda: _local_ids(o["node_ptr"], N + B, dev))
+    o.lazy("eid", lambda: _local_ids(o["edge_ptr"], E + 2 * N, dev))
     if "vattr" in b:  # dummy node gets attribute 0 (line 191)
         va = torch.zeros(N + B, dtype=torch.float32, device=dev)
         va[o["v_is_dummy"] == 0] = b["vattr"]
@@ -97,25 +153,25 @@ def tu_conjugate(b):
     max_nodes = (o_node_ptr[1:] - o_node_ptr[:-1]).max() if B > 0 else o_node_ptr[-1]
     sizes = torch.stack([o_node_ptr[-1], o_edge_ptr[-1], max_nodes]).cpu()  # the one D2H sync: output sizes
     V2, E2 = int(sizes[0]), int(sizes[1])
-    o = dict(num_graphs=B, max_graph_nodes=int(sizes[2]), node_ptr=o_node_ptr, edge_ptr=o_edge_ptr,
-             src=_empty_i32(E2, dev), dst=_empty_i32(E2, dev),
-             v_origin=_empty_i32(V2, dev), e_shared=_empty_i32(E2, dev))
+    o = LazyDict(num_graphs=B, max_graph_nodes=int(sizes[2]), node_ptr=o_node_ptr, edge_ptr=o_edge_ptr,
+                 src=_empty_i32(E2, dev), dst=_empty_i32(E2, dev),
+                 v_origin=_empty_i32(V2, dev), e_shared=_empty_i32(E2, dev))
     L.call("dn4gl_tu_conjugate_fill", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
            ptr(isd), N, E, ptr(csr_in.row_ptr), ptr(csr_in.eid), ptr(cand_off), ptr(newid),
            ptr(o_node_ptr), ptr(o_edge_ptr), ptr(o["src"]), ptr(o["dst"]), ptr(o["v_origin"]), ptr(o["e_shared"]),
            ptr(ws), ws_bytes, _stream())
-    vo, es = o["v_origin"].long(), o["e_shared"].long()
-    # vertex attributes <- original edge attributes (lines 238-242), edge attributes <- shared vertex (322-326)
-    o["vlabel"] = b["elabel"][vo]
-    o["elabel"] = b["vlabel"][es]
-    eid = b["eid"] if "eid" in b else _local_ids(b["edge_ptr"], E, dev)
-    vid = b["vid"] if "vid" in b else _local_ids(b["node_ptr"], N, dev)
-    o["vid"], o["eid"] = eid[vo], vid[es]
+    vo, es = o["v_origin"], o["e_shared"]
+    # vertex attributes <- original edge attributes (lines 238-242), edge attributes <- shared vertex (322-326);
+    # derived lazily: a consumer that only needs the structure and the vertex labels pays for nothing else
+    o.lazy("vlabel", lambda: _take(b["elabel"], vo))
+    o.lazy("elabel", lambda: _take(b["vlabel"], es))
+    o.lazy("vid", lambda: _take(b["eid"] if "eid" in b else _local_ids(b["edge_ptr"], E, dev), vo))
+    o.lazy("eid", lambda: _take(b["vid"] if "vid" in b else _local_ids(b["node_ptr"], N, dev), es))
     if isd is not None:
-        o["v_is_dummy"] = isd[vo]
-        o["e_is_dummy"] = b["v_is_dummy"][es]
+        o.lazy("v_is_dummy", lambda: _take(isd, vo))
+        o.lazy("e_is_dummy", lambda: _take(b["v_is_dummy"], es))
     if "vattr" in b:
-        o["eattr"] = b["vattr"][es]
+        o.lazy("eattr", lambda: _take(b["vattr"], es))
     if "y" in b:
         o["y"] = b["y"]
     return o
@@ -215,22 +271,21 @@ def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_m
     E2 = int(keep_scan[-1].item())
     o_src, o_dst, o_first = o_src[:E2], o_dst[:E2], o_first[:E2]
     # node features: [attr?, one_hot(label - min)]
-    vl = b["vlabel"].long()
+    vl = b["vlabel"]
     if node_label_min is not None and num_node_labels is not None:
         vmin = int(node_label_min)      # caller knows the label range: no device->host sync
     else:
         vmin = int(vl.min().item()) if N else 0
     nvl = int(num_node_labels) if num_node_labels is not None else (int(vl.max().item()) - vmin + 1 if N else 0)
-    x = torch.zeros((N, nvl), dtype=torch.float32, device=dev)
-    x.scatter_(1, (vl - vmin).view(-1, 1), 1.0)
+    x = (vl.view(-1, 1) == torch.arange(vmin, vmin + nvl, dtype=vl.dtype, device=dev)).to(torch.float32)
     n_attr = 0
     if "vattr" in b:
         x = torch.cat([b["vattr"].view(N, -1), x], dim=1)
         n_attr = x.size(1) - nvl
-    out = dict(num_graphs=B, x=x, edge_index=torch.stack([o_src.long(), o_dst.long()]),
-               node_ptr=b["node_ptr"], src=o_src, dst=o_dst, first_edge=o_first,
-               batch=torch.repeat_interleave(torch.arange(B, device=dev),
-                                             (b["node_ptr"][1:] - b["node_ptr"][:-1]).long(), output_size=N))
+    out = LazyDict(num_graphs=B, x=x, node_ptr=b["node_ptr"], src=o_src, dst=o_dst, first_edge=o_first)
+    out.lazy("edge_index", lambda: torch.stack([o_src.long(), o_dst.long()]))
+    out.lazy("batch", lambda: torch.repeat_interleave(torch.arange(B, device=dev),
+                                                      (b["node_ptr"][1:] - b["node_ptr"][:-1]).long(), output_size=N))
     if with_edge_attr and b.get("has_edge_labels", True) and E > 0:
         el = b["elabel"].long()
         emin = int(el.min().item())
@@ -245,7 +300,7 @@ def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_m
         edge_attr.index_add_(0, group[valid], oh[sorted_items[valid]])
         out["edge_attr"] = edge_attr
         out["is_dummy_edge"] = edge_attr[:, 0].bool()  # set_dummy_flags: column num_edge_attributes (=0)
-    out["is_dummy_node"] = x[:, n_attr].bool()
+    out.lazy("is_dummy_node", lambda: x[:, n_attr].bool())
     if b.get("max_graph_nodes") is not None:
         out["max_graph_nodes"] = int(b["max_graph_nodes"])
     if "y" in b:
