@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(NT) lin_fwd_kernel(const LinFwdArgs a) {
 // backward stage
 // ------------------------------------------------------------------------------------------------------------------
 struct LinBwdArgs {
-    const float *G; const float *Yo; int64_t N; int M;
+    const float *G; const float *Gseg; const int32_t *row2seg; const float *Yo; int64_t N; int M;
     const float *bn; const float *sums; int g_masked;
     const float *W; int K;
     const float *X; const float *in_bn; int in_act; float in_slope;
@@ -486,8 +486,8 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
         const uint32_t rows = static_cast<uint32_t>(left < 128 ? left : 128);
         const uint32_t gb = rows * a.M * 4u, xb = rows * a.K * 4u;
         const uint32_t slot = sRing + (j % (RING > 0 ? RING : 1)) * RAW_SLOT, fb = s_u32(&full_mem[j % (RING > 0 ? RING : 1)]);
-        mbar_expect_tx(fb, gb * (has_bn ? 2u : 1u) + xb);
-        bulk_g2s(slot, a.G + row0 * a.M, gb, fb);
+        mbar_expect_tx(fb, gb * ((has_bn ? 1u : 0u) + (a.G != nullptr ? 1u : 0u)) + xb);
+        if (a.G != nullptr) bulk_g2s(slot, a.G + row0 * a.M, gb, fb);
         if (has_bn) bulk_g2s(slot + RAW_G, a.Yo + row0 * a.M, gb, fb);
         bulk_g2s(slot + 2 * RAW_G, a.X + row0 * a.K, xb, fb);
     };
@@ -512,6 +512,7 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
     constexpr int CHk = KP / 4, RPk = NT / CHk;    // input-channel side
     const int c_m = t % CHm, r_m = t / CHm, c_k = t % CHk, r_k = t / CHk;
     const bool vecG = (a.M % 4 == 0) && aligned16_dev(a.G) && (a.Yo == nullptr || aligned16_dev(a.Yo));
+    const bool vecGs = (a.M % 4 == 0) && aligned16_dev(a.Gseg);
     const bool vecX = (a.K % 4 == 0) && aligned16_dev(a.X), vecGX = (a.K % 4 == 0) && aligned16_dev(a.GX);
     const Bn4 bo = load_bn4(a.bn, a.M, c_m), bi = load_bn4(a.in_bn, a.K, c_k);
     float4 m1 = zero4(), m2 = zero4();
@@ -543,7 +544,11 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
             const int64_t gr = row0 + r;
             float4 g = zero4();
             if (gr < a.N) {
-                g = RING > 0 ? raw_chunk(slab, r, a.M, c_m) : load_chunk(a.G, gr, a.M, c_m, vecG);
+                if (a.G != nullptr) g = RING > 0 ? raw_chunk(slab, r, a.M, c_m) : load_chunk(a.G, gr, a.M, c_m, vecG);
+                if (a.Gseg != nullptr) {   // + the readout gradient of this row's graph (global_add/mean_pool backward)
+                    const float4 gs = load_chunk(a.Gseg, __ldg(a.row2seg + gr), a.M, c_m, vecGs);
+                    g.x += gs.x; g.y += gs.y; g.z += gs.z; g.w += gs.w;
+                }
                 if (has_bn) {
                     const float4 y = RING > 0 ? raw_chunk(slab + RAW_G, r, a.M, c_m) : load_chunk(a.Yo, gr, a.M, c_m, vecG);
                     const float4 xc = make_float4(y.x - bo.mean.x, y.y - bo.mean.y, y.z - bo.mean.z, y.w - bo.mean.w);
@@ -809,21 +814,74 @@ __global__ void bn_act_kernel(const float *__restrict__ Y, int64_t N, int M, con
     }
 }
 
+// out = act(bn(Y)) AND the per-graph readout of out in the same pass (global_add_pool / global_mean_pool over contiguous
+// row segments, gconv.py:175-178,213): one CTA per graph, thread = fixed 4 channels x strided rows, fixed-order combine.
+template <int CHP>
+__global__ void __launch_bounds__(256) bn_act_pool_kernel(const float *__restrict__ Y, int M, const float *__restrict__ bn, int act,
+                                                          float slope, float *__restrict__ out, const int32_t *__restrict__ seg_ptr,
+                                                          int B, int mode, float *__restrict__ pooled) {
+    constexpr int RP = 256 / CHP;
+    __shared__ float red[8][4 * CHP];
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31, c = t % CHP, r0 = t / CHP;
+    const bool vec = (M % 4 == 0) && aligned16_dev(Y) && aligned16_dev(out);
+    const Bn4 b = load_bn4(bn, M, c);
+    for (int g = blockIdx.x; g < B; g += gridDim.x) {
+        const int beg = __ldg(seg_ptr + g), end = __ldg(seg_ptr + g + 1);
+        float4 acc = zero4();
+        if (4 * c < M) {
+            for (int r = beg + r0; r < end; r += RP) {
+                float4 v = load_chunk(Y, r, M, c, vec);
+                if (bn) v = bn_apply(v, b);
+                v.x = act_f(v.x, act, slope); v.y = act_f(v.y, act, slope); v.z = act_f(v.z, act, slope); v.w = act_f(v.w, act, slope);
+                store_chunk(out, r, M, c, v, vec);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        chunk_allreduce<CHP>(acc);
+        if (lane < CHP) {
+            const int c0 = 4 * c;
+            red[w][c0] = acc.x; red[w][c0 + 1] = acc.y; red[w][c0 + 2] = acc.z; red[w][c0 + 3] = acc.w;
+        }
+        __syncthreads();
+        if (t < M) {
+            // CHP >= 32 never occurs with 8-lane groups sharing a warp only when CHP < 32; for CHP == 32 every warp holds
+            // distinct rows of all chunks, so the sum over warps is still the right combine
+            float sum = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) sum += red[ww][t];
+            if (mode == 1) sum *= 1.f / static_cast<float>(max(end - beg, 1));
+            pooled[static_cast<int64_t>(g) * M + t] = sum;
+        }
+        __syncthreads();
+    }
+}
+
+// row -> segment index for contiguous segments (the `batch` vector of a PyG batch, as int32)
+__global__ void segment_ids_kernel(const int32_t *__restrict__ seg_ptr, int B, int64_t N, int32_t *__restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = segment_of(seg_ptr, B, i);
+}
+
 // BatchNorm-backward batch sums of a stage whose gradient arrives from outside the MLP:
 // s1[c] = sum_r gm, s2[c] = sum_r gm * xhat, gm = G * act'(bn(Y)), xhat = (Y - mean) * rstd.  Per-CTA partials.
 template <int CHP>   // chunks per row rounded up to a power of two (<= 32)
-__global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restrict__ G, const float *__restrict__ Y, int64_t N, int M,
-                                                          const float *__restrict__ bn, int act, float slope,
+__global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restrict__ G, const float *__restrict__ Gseg,
+                                                          const int32_t *__restrict__ row2seg, const float *__restrict__ Y,
+                                                          int64_t N, int M, const float *__restrict__ bn, int act, float slope,
                                                           float *__restrict__ part /* [grid][2*4*CHP] */) {
     constexpr int RP = 256 / CHP;
     __shared__ float red[8][8 * CHP];
     const int t = threadIdx.x, w = t >> 5, lane = t & 31, c = t % CHP, r0 = t / CHP;
-    const bool vec = (M % 4 == 0) && aligned16_dev(G) && aligned16_dev(Y);
+    const bool vec = (M % 4 == 0) && aligned16_dev(G) && aligned16_dev(Y) && aligned16_dev(Gseg);
     const Bn4 b = load_bn4(bn, M, c);
     float4 s1 = zero4(), s2 = zero4();
     if (4 * c < M) {
         for (int64_t r = static_cast<int64_t>(blockIdx.x) * RP + r0; r < N; r += static_cast<int64_t>(gridDim.x) * RP) {
-            float4 g = load_chunk(G, r, M, c, vec);
+            float4 g = G != nullptr ? load_chunk(G, r, M, c, vec) : zero4();
+            if (Gseg != nullptr) {
+                const float4 gs = load_chunk(Gseg, __ldg(row2seg + r), M, c, vec);
+                g.x += gs.x; g.y += gs.y; g.z += gs.z; g.w += gs.w;
+            }
             const float4 y = load_chunk(Y, r, M, c, vec);
             const float4 xc = make_float4(y.x - b.mean.x, y.y - b.mean.y, y.z - b.mean.z, y.w - b.mean.w);
             g.x *= dact_f(fmaf(xc.x, b.k.x, b.beta.x), act, slope); g.y *= dact_f(fmaf(xc.y, b.k.y, b.beta.y), act, slope);
@@ -1027,13 +1085,14 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
     return DN4GL_OK;
 }
 
-int dn4gl_lin_bwd_f32(const float *G, const float *Yout, int64_t N, int32_t M,
+int dn4gl_lin_bwd_f32(const float *G, const float *Gseg, const int32_t *row2seg, const float *Yout, int64_t N, int32_t M,
                       const float *bn, const float *sums, int32_t g_masked,
                       const float *W, int32_t K,
                       const float *X, const float *in_bn, int32_t in_act, float in_slope,
                       float *GX, float *sums_prev, float *dW, float *db,
                       void *ws, size_t ws_bytes, void *stream) {
-    DN_ARG(N >= 0 && G != nullptr && W != nullptr && X != nullptr && ws != nullptr);
+    DN_ARG(N >= 0 && (G != nullptr || Gseg != nullptr) && W != nullptr && X != nullptr && ws != nullptr);
+    DN_ARG((Gseg == nullptr) == (row2seg == nullptr));
     DN_ARG(dn4gl_lin_supported(K, M));
     DN_ARG(bn == nullptr || (Yout != nullptr && sums != nullptr));
     DN_ARG(sums_prev == nullptr || in_bn != nullptr);
@@ -1049,11 +1108,11 @@ int dn4gl_lin_bwd_f32(const float *G, const float *Yout, int64_t N, int32_t M,
         return DN4GL_OK;
     }
     LinBwdArgs a;
-    a.G = G; a.Yo = Yout; a.N = N; a.M = M; a.bn = bn; a.sums = sums; a.g_masked = g_masked;
+    a.G = G; a.Gseg = Gseg; a.row2seg = row2seg; a.Yo = Yout; a.N = N; a.M = M; a.bn = bn; a.sums = sums; a.g_masked = g_masked;
     a.W = W; a.K = K; a.X = X; a.in_bn = in_bn; a.in_act = in_act; a.in_slope = in_slope;
     a.GX = GX; a.part = static_cast<float *>(ws);
     a.num_tiles = static_cast<int>(ceil_div64(N, 128));
-    const bool ring_ok = (K % 4 == 0) && (M % 4 == 0) && aligned16(X) && aligned16(G) && (Yout == nullptr || aligned16(Yout));
+    const bool ring_ok = (K % 4 == 0) && (M % 4 == 0) && aligned16(X) && (G == nullptr || aligned16(G)) && (Yout == nullptr || aligned16(Yout));
     int rc = 0, grid = 0;
 #define DN_BWD_CASE(kp, mp) if (KP == kp && MP == mp) rc = dispatch_bwd<kp, mp>(a, ring_ok, &grid, s); else
     DN_BWD_CASE(32, 32) DN_BWD_CASE(32, 64) DN_BWD_CASE(64, 32) DN_BWD_CASE(64, 64)
@@ -1075,6 +1134,39 @@ int dn4gl_bn_act_f32(const float *Y, int64_t N, int32_t M, const float *bn, int3
     const int64_t want = ceil_div64(total, 256 * 4);
     const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 8;
     bn_act_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(Y, N, M, bn, act, slope, out);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+int dn4gl_bn_act_pool_f32(const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope, float *out,
+                          const int32_t *seg_ptr, int32_t B, int32_t mode, float *pooled, void *stream) {
+    DN_ARG(N >= 0 && M >= 1 && M <= 128 && B >= 0 && (mode == 0 || mode == 1));
+    DN_ARG(act >= DN4GL_ACT_NONE && act <= DN4GL_ACT_LEAKY_RELU);
+    if (B == 0) return DN4GL_OK;
+    DN_ARG(Y != nullptr && out != nullptr && seg_ptr != nullptr && pooled != nullptr);
+    const int CH = (M + 3) / 4;
+    int CHP = 1;
+    while (CHP < CH) CHP <<= 1;
+    const int cap = dn4gl_num_sms() * 8;
+    const int grid = B < cap ? B : cap;
+    cudaStream_t s = as_stream(stream);
+    switch (CHP) {
+    case 1: bn_act_pool_kernel<1><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    case 2: bn_act_pool_kernel<2><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    case 4: bn_act_pool_kernel<4><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    case 8: bn_act_pool_kernel<8><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    case 16: bn_act_pool_kernel<16><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    default: bn_act_pool_kernel<32><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    }
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+int dn4gl_segment_ids_i32(const int32_t *seg_ptr, int32_t B, int64_t N, int32_t *out, void *stream) {
+    DN_ARG(B >= 0 && N >= 0);
+    if (N == 0) return DN4GL_OK;
+    DN_ARG(seg_ptr != nullptr && out != nullptr && B >= 1);
+    segment_ids_kernel<<<static_cast<unsigned>(ceil_div64(N, 256)), 256, 0, as_stream(stream)>>>(seg_ptr, B, N, out);
     DN_LAUNCHED();
     return DN4GL_OK;
 }
@@ -1101,9 +1193,10 @@ size_t dn4gl_bn_bwd_sums_workspace_bytes(int64_t N, int32_t M) {
     return static_cast<size_t>(dn4gl_num_sms()) * 4 * 8 * 32 * sizeof(float);
 }
 
-int dn4gl_bn_bwd_sums_f32(const float *G, const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope,
-                          float *sums, void *ws, size_t ws_bytes, void *stream) {
-    DN_ARG(N >= 0 && M >= 1 && M <= 128 && G != nullptr && Y != nullptr && bn != nullptr && sums != nullptr && ws != nullptr);
+int dn4gl_bn_bwd_sums_f32(const float *G, const float *Gseg, const int32_t *row2seg, const float *Y, int64_t N, int32_t M,
+                          const float *bn, int32_t act, float slope, float *sums, void *ws, size_t ws_bytes, void *stream) {
+    DN_ARG(N >= 0 && M >= 1 && M <= 128 && (G != nullptr || Gseg != nullptr) && Y != nullptr && bn != nullptr && sums != nullptr && ws != nullptr);
+    DN_ARG((Gseg == nullptr) == (row2seg == nullptr));
     DN_ARG(ws_bytes >= dn4gl_bn_bwd_sums_workspace_bytes(N, M));
     cudaStream_t s = as_stream(stream);
     if (N == 0) { DN_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * M, s)); return DN4GL_OK; }
@@ -1116,12 +1209,12 @@ int dn4gl_bn_bwd_sums_f32(const float *G, const float *Y, int64_t N, int32_t M, 
     const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
     float *part = static_cast<float *>(ws);
     switch (CHP) {
-    case 1: bn_bwd_sums_kernel<1><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
-    case 2: bn_bwd_sums_kernel<2><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
-    case 4: bn_bwd_sums_kernel<4><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
-    case 8: bn_bwd_sums_kernel<8><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
-    case 16: bn_bwd_sums_kernel<16><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
-    default: bn_bwd_sums_kernel<32><<<grid, 256, 0, s>>>(G, Y, N, M, bn, act, slope, part); break;
+    case 1: bn_bwd_sums_kernel<1><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 2: bn_bwd_sums_kernel<2><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 4: bn_bwd_sums_kernel<4><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 8: bn_bwd_sums_kernel<8><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 16: bn_bwd_sums_kernel<16><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    default: bn_bwd_sums_kernel<32><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
     }
     bn_bwd_sums_reduce_kernel<<<(8 * CHP + 31) / 32, 1024, 0, s>>>(part, grid, CHP, M, sums);
     DN_LAUNCHED_N(2);

@@ -29,6 +29,15 @@ class GraphStructure:
         self.csr_in.seg_ptr = self.csr_out.seg_ptr = self.node_ptr
         self.csr_in.max_seg = self.csr_out.max_seg = max_seg   # rows of the largest graph, if the host knows it
         self._rel = {}
+        self._row2seg = None
+
+    @property
+    def row2seg(self):
+        """int32 row -> graph index (``batch`` as the kernels read it); built once per batch."""
+        if self._row2seg is None and self.node_ptr is not None:
+            from .. import ops
+            self._row2seg = ops.segment_ids(self.node_ptr, self.num_nodes)
+        return self._row2seg
 
     def relation_csr(self, edge_type, num_rels):
         """CSR pair addressing the (N*R, D) per-relation table (see subgraph_isomorphism/models/rgin.py)."""

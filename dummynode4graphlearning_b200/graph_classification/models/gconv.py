@@ -100,25 +100,40 @@ class GIN(torch.nn.Module):
         self.convs = nn.ModuleList(convs)
         self.linears = nn.ModuleList(linears)
 
+    def _fused(self):
+        """the tensor-core GIN layers apply when every MLP is the reference's Linear/BN/ReLU stack in training mode."""
+        return ops.gin_mlp_fusable(self.first_h) and all(ops.gin_mlp_fusable(m) for m in self.nns)
+
+    def _forward_fused(self, data, s):
+        """each layer is one autograd node producing (h, pooled h); the class scores are Linear(pooled) -- for layer 0
+        pool(Linear(h)) = Linear(pool(h)) with the bias counted once per pooled row (gconv.py:210), so that GEMM runs on
+        B rows instead of N."""
+        mean = self.pooling is global_mean_pool
+        x, out = data.x, 0
+        for layer in range(self.no_layers):
+            if layer == 0:
+                x, pooled = ops.gin_layer(self.first_h, x, seg_ptr=s.node_ptr, row2seg=s.row2seg, mean=mean)
+                lin = self.linears[0]
+                if mean:
+                    score = lin(pooled)
+                else:
+                    cnt = (s.node_ptr[1:] - s.node_ptr[:-1]).to(pooled.dtype).unsqueeze(1)
+                    score = ops.linear(pooled, lin.weight, None) + cnt * lin.bias
+                out = out + F.dropout(score, p=self.dropout)                                   # gconv.py:210 (no training=)
+            else:
+                conv = self.convs[layer - 1]
+                x, pooled = ops.gin_layer(conv.nn, x, conv.eps, s.csr_in, s.csr_out, s.node_ptr, s.row2seg, mean)
+                out = out + F.dropout(self.linears[layer](pooled), p=self.dropout, training=self.training)
+        return F.log_softmax(out, dim=-1)
+
     def forward(self, data):
         x = data.x
         s = structure_of(data)
+        if x.is_cuda and s.node_ptr is not None and self._fused():
+            return self._forward_fused(data, s)
         out = 0
         for layer in range(self.no_layers):
             if layer == 0:
-                if x.is_cuda and ops.gin_mlp_fusable(self.first_h):
-                    x = ops.gin_mlp(self.first_h, x)
-                    # pool(Linear(x)) = Linear(pool(x)) with the bias counted once per pooled row: the class-score
-                    # GEMM runs on B rows instead of N
-                    lin = self.linears[0]
-                    pooled = self.pooling(x, data.batch, node_ptr=s.node_ptr)
-                    if self.pooling is global_add_pool:
-                        cnt = (s.node_ptr[1:] - s.node_ptr[:-1]).to(pooled.dtype).unsqueeze(1)
-                        score = ops.linear(pooled, lin.weight, None) + cnt * lin.bias
-                    else:
-                        score = lin(pooled)
-                    out += F.dropout(score, p=self.dropout)
-                    continue
                 x = self.first_h(x)
                 out += F.dropout(self.pooling(self.linears[layer](x), data.batch, node_ptr=s.node_ptr), p=self.dropout)
             else:

@@ -349,13 +349,15 @@ def lin_fwd(x, weight, bias=None, in_bn=None, in_act=ACT_NONE, in_slope=0.0, bn=
 
 
 def lin_bwd(G, weight, X, Yout=None, bn=None, sums=None, g_masked=False, in_bn=None, in_act=ACT_NONE, in_slope=0.0,
-            want_gx=True, want_dw=True, want_db=True):
-    """backward of one stage (see include/dn4gl.h): -> (GX | None, sums_prev | None, dW | None, db | None)."""
-    require_cuda(G, "gradient rows")
-    G, X = _f32c(G), _f32c(X)
-    N, M = G.shape
-    K = X.size(1)
-    dev = G.device
+            want_gx=True, want_dw=True, want_db=True, gseg=None, row2seg=None):
+    """backward of one stage (see include/dn4gl.h): -> (GX | None, sums_prev | None, dW | None, db | None).
+    The upstream gradient is G (N x M, may be None) + gseg[row2seg] (per-graph readout gradient, may be None)."""
+    X = _f32c(X)
+    require_cuda(X, "rows")
+    G = None if G is None else _f32c(G)
+    N, K = X.shape
+    M = weight.size(0)
+    dev = X.device
     L = lib()
     GX = torch.empty((N, K), dtype=torch.float32, device=dev) if want_gx else None
     sp = torch.empty(2 * K, dtype=torch.float32, device=dev) if (want_gx and in_bn is not None) else None
@@ -363,7 +365,8 @@ def lin_bwd(G, weight, X, Yout=None, bn=None, sums=None, g_masked=False, in_bn=N
     db = torch.empty(M, dtype=torch.float32, device=dev) if want_db else None
     wsb = L.size("dn4gl_lin_workspace_bytes", N, K, M)
     ws, _ = _tc_ws(dev, wsb)
-    L.call("dn4gl_lin_bwd_f32", ptr(G), ptr(None if Yout is None else _f32c(Yout)), N, M, ptr(bn), ptr(sums),
+    L.call("dn4gl_lin_bwd_f32", ptr(G), ptr(None if gseg is None else _f32c(gseg)), ptr(row2seg),
+           ptr(None if Yout is None else _f32c(Yout)), N, M, ptr(bn), ptr(sums),
            1 if g_masked else 0, ptr(_f32c(weight)), K, ptr(X), ptr(in_bn), int(in_act), float(in_slope), ptr(GX), ptr(sp),
            ptr(dW), ptr(db), ptr(ws), wsb, _stream())
     return GX, sp, dW, db
@@ -378,47 +381,43 @@ def bn_act(Y, rec, act=ACT_RELU, slope=0.0):
     return out
 
 
-def bn_bwd_sums(G, Y, rec, act=ACT_RELU, slope=0.0):
-    """{sum gm, sum gm * xhat} (2*M) with gm = G * act'(bn(Y))."""
-    G, Y = _f32c(G), _f32c(Y)
+def bn_act_pool(Y, rec, seg_ptr, mean=False, act=ACT_RELU, slope=0.0):
+    """(act(bn(Y)), per-graph sum / mean of it) in one pass over contiguous row segments."""
+    require_cuda(Y, "rows")
+    Y = _f32c(Y)
+    B = seg_ptr.numel() - 1
+    out = torch.empty_like(Y)
+    pooled = torch.empty((B, Y.size(1)), dtype=torch.float32, device=Y.device)
+    lib().call("dn4gl_bn_act_pool_f32", ptr(Y), Y.size(0), Y.size(1), ptr(rec), int(act), float(slope), ptr(out),
+               ptr(seg_ptr), B, 1 if mean else 0, ptr(pooled), _stream())
+    return out, pooled
+
+
+def segment_ids(seg_ptr, n_rows):
+    """int32 row -> segment index (PyG's ``batch`` vector) for contiguous segments."""
+    require_cuda(seg_ptr, "segment offsets")
+    out = torch.empty(int(n_rows), dtype=torch.int32, device=seg_ptr.device)
+    lib().call("dn4gl_segment_ids_i32", ptr(seg_ptr), seg_ptr.numel() - 1, int(n_rows), ptr(out), _stream())
+    return out
+
+
+def bn_bwd_sums(G, Y, rec, act=ACT_RELU, slope=0.0, gseg=None, row2seg=None):
+    """{sum gm, sum gm * xhat} (2*M) with gm = (G + gseg[row2seg]) * act'(bn(Y))."""
+    Y = _f32c(Y)
+    G = None if G is None else _f32c(G)
     N, M = Y.shape
     L = lib()
     sums = torch.empty(2 * M, dtype=torch.float32, device=Y.device)
     wsb = L.size("dn4gl_bn_bwd_sums_workspace_bytes", N, M)
     ws, _ = _tc_ws(Y.device, wsb)
-    L.call("dn4gl_bn_bwd_sums_f32", ptr(G), ptr(Y), N, M, ptr(rec), int(act), float(slope), ptr(sums), ptr(ws), wsb,
-           _stream())
+    L.call("dn4gl_bn_bwd_sums_f32", ptr(G), ptr(None if gseg is None else _f32c(gseg)), ptr(row2seg), ptr(Y), N, M,
+           ptr(rec), int(act), float(slope), ptr(sums), ptr(ws), wsb, _stream())
     return sums
 
 
 def _bn_dict(bn):
     return dict(gamma=bn.weight, beta=bn.bias, eps=bn.eps, momentum=bn.momentum, running_mean=bn.running_mean,
                 running_var=bn.running_var, num_batches_tracked=bn.num_batches_tracked)
-
-
-class _GinMlp(torch.autograd.Function):
-    """h = ReLU(BN2(Linear2(ReLU(BN1(Linear1(z))))))  in training mode (batch statistics), three launches forward
-    (two tensor-core stages + one elementwise), five backward; gconv.py:190-196."""
-
-    @staticmethod
-    def forward(ctx, z, W1, b1, g1, be1, W2, b2, g2, be2, bn1, bn2):
-        y1, rec1 = lin_fwd(z, W1, b1, bn=bn1)
-        y2, rec2 = lin_fwd(y1, W2, b2, in_bn=rec1, in_act=ACT_RELU, bn=bn2)
-        h = bn_act(y2, rec2, ACT_RELU)
-        ctx.save_for_backward(z, y1, y2, rec1, rec2, W1, W2)
-        return h
-
-    @staticmethod
-    def backward(ctx, gh):
-        z, y1, y2, rec1, rec2, W1, W2 = ctx.saved_tensors
-        D1, D2 = W1.size(0), W2.size(0)
-        gh = _f32c(gh)
-        sums2 = bn_bwd_sums(gh, y2, rec2, ACT_RELU)
-        ga1, sums1, dW2, db2 = lin_bwd(gh, W2, y1, Yout=y2, bn=rec2, sums=sums2, g_masked=False, in_bn=rec1,
-                                       in_act=ACT_RELU)
-        gz, _, dW1, db1 = lin_bwd(ga1, W1, z, Yout=y1, bn=rec1, sums=sums1, g_masked=True,
-                                  want_gx=ctx.needs_input_grad[0])
-        return (gz, dW1, db1, sums1[D1:], sums1[:D1], dW2, db2, sums2[D2:], sums2[:D2], None, None)
 
 
 def dot(a, b):
@@ -432,41 +431,76 @@ def dot(a, b):
     return out
 
 
-class _GinConv(torch.autograd.Function):
-    """one GIN layer as ONE autograd node: h = MLP((1 + eps) x + sum_{j->i} x_j)  (gconv.py:212 + :190-196).
-    eps is a device scalar (Parameter or buffer) read by the aggregation kernel; d eps = sum(g_z * x)."""
+class _GinLayer(torch.autograd.Function):
+    """one GIN layer as ONE autograd node (gconv.py:210-213 + :190-196):
+
+        z = (1 + eps) x + sum_{j->i} x_j          (skipped when csr_in is None: layer 0 applies the MLP to x itself)
+        h = ReLU(BN2(Linear2(ReLU(BN1(Linear1(z))))))      training-mode batch statistics
+        pooled = global_add_pool / global_mean_pool (h)    (when seg_ptr is given)
+
+    Forward: aggregation, two tensor-core stages (+ their statistics merges), one elementwise + readout pass.  Backward:
+    the readout gradient is added row-wise inside the stage prologues (never materialised), the BatchNorm sums of the
+    inner stage come out of the outer stage's epilogue; eps is read on the device, d eps = sum(g_z * x)."""
 
     @staticmethod
-    def forward(ctx, x, eps, W1, b1, g1, be1, W2, b2, g2, be2, bn1, bn2, csr_in, csr_out):
+    def forward(ctx, x, eps, W1, b1, g1, be1, W2, b2, g2, be2, bn1, bn2, csr_in, csr_out, seg_ptr, row2seg, mean):
+        ctx.set_materialize_grads(False)
         x = _f32c(x)
-        z = _spmm(csr_in, x, csr_in.n_rows, 1.0, eps)
+        z = _spmm(csr_in, x, csr_in.n_rows, 1.0, eps) if csr_in is not None else x
         y1, rec1 = lin_fwd(z, W1, b1, bn=bn1)
         y2, rec2 = lin_fwd(y1, W2, b2, in_bn=rec1, in_act=ACT_RELU, bn=bn2)
-        h = bn_act(y2, rec2, ACT_RELU)
+        if seg_ptr is not None:
+            h, pooled = bn_act_pool(y2, rec2, seg_ptr, mean, ACT_RELU)
+        else:
+            h, pooled = bn_act(y2, rec2, ACT_RELU), None
         ctx.save_for_backward(x, eps, z, y1, y2, rec1, rec2, W1, W2)
-        ctx.csr_out = csr_out
-        return h
+        ctx.csr_out, ctx.seg_ptr, ctx.row2seg, ctx.mean = csr_out, seg_ptr, row2seg, mean
+        return h, pooled
 
     @staticmethod
-    def backward(ctx, gh):
+    def backward(ctx, gh, gpooled):
         x, eps, z, y1, y2, rec1, rec2, W1, W2 = ctx.saved_tensors
         D1, D2 = W1.size(0), W2.size(0)
-        gh = _f32c(gh)
-        sums2 = bn_bwd_sums(gh, y2, rec2, ACT_RELU)
+        gh = None if gh is None else _f32c(gh)
+        gseg = row2seg = None
+        if gpooled is not None:
+            gseg, row2seg = _f32c(gpooled), ctx.row2seg
+            if ctx.mean:
+                cnt = (ctx.seg_ptr[1:] - ctx.seg_ptr[:-1]).clamp_min(1).to(gseg.dtype).unsqueeze(1)
+                gseg = gseg / cnt
+        if gh is None and gseg is None:
+            gh = torch.zeros_like(y2)
+        sums2 = bn_bwd_sums(gh, y2, rec2, ACT_RELU, gseg=gseg, row2seg=row2seg)
         ga1, sums1, dW2, db2 = lin_bwd(gh, W2, y1, Yout=y2, bn=rec2, sums=sums2, g_masked=False, in_bn=rec1,
-                                       in_act=ACT_RELU)
-        need_z = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+                                       in_act=ACT_RELU, gseg=gseg, row2seg=row2seg)
+        has_agg = ctx.csr_out is not None
+        need_eps = has_agg and eps is not None and ctx.needs_input_grad[1]
+        need_z = ctx.needs_input_grad[0] or need_eps
         gz, _, dW1, db1 = lin_bwd(ga1, W1, z, Yout=y1, bn=rec1, sums=sums1, g_masked=True, want_gx=need_z)
-        gx = _spmm(ctx.csr_out, gz, x.size(0), 1.0, eps) if ctx.needs_input_grad[0] else None
-        geps = dot(gz, x).view_as(eps) if ctx.needs_input_grad[1] else None
-        return (gx, geps, dW1, db1, sums1[D1:], sums1[:D1], dW2, db2, sums2[D2:], sums2[:D2], None, None, None, None)
+        gx = geps = None
+        if ctx.needs_input_grad[0]:
+            gx = _spmm(ctx.csr_out, gz, x.size(0), 1.0, eps) if has_agg else gz
+        if need_eps:
+            geps = dot(gz, x).view_as(eps)
+        return (gx, geps, dW1, db1, sums1[D1:], sums1[:D1], dW2, db2, sums2[D2:], sums2[:D2],
+                None, None, None, None, None, None, None)
+
+
+def gin_layer(seq, x, eps=None, csr_in=None, csr_out=None, seg_ptr=None, row2seg=None, mean=False):
+    """fused GIN layer -> (h, pooled | None); gin_mlp_fusable(seq) must hold.  csr_in None: no aggregation (layer 0)."""
+    l1, n1, _, l2, n2, _ = seq
+    return _GinLayer.apply(x, eps, l1.weight, l1.bias, n1.weight, n1.bias, l2.weight, l2.bias, n2.weight, n2.bias,
+                           _bn_dict(n1), _bn_dict(n2), csr_in, csr_out, seg_ptr, row2seg, mean)
 
 
 def gin_conv(seq, x, eps, csr_in, csr_out):
-    """fused GINConv (aggregation + MLP); gin_mlp_fusable(seq) must hold and x.size(1) must be a tiled width."""
-    l1, n1, _, l2, n2, _ = seq
-    return _GinConv.apply(x, eps, l1.weight, l1.bias, n1.weight, n1.bias, l2.weight, l2.bias, n2.weight, n2.bias,
-                          _bn_dict(n1), _bn_dict(n2), csr_in, csr_out)
+    """fused GINConv (aggregation + MLP)."""
+    return gin_layer(seq, x, eps, csr_in, csr_out)[0]
+
+
+def gin_mlp(seq, z):
+    """the GIN MLP `seq` applied to z through the fused tensor-core stages."""
+    return gin_layer(seq, z)[0]
 
 
 def gin_mlp_fusable(seq):
@@ -485,10 +519,3 @@ def gin_mlp_fusable(seq):
     if l1.bias is None or l2.bias is None:
         return False
     return lin_supported(l1.in_features, l1.out_features) and lin_supported(l2.in_features, l2.out_features)
-
-
-def gin_mlp(seq, z):
-    """apply the GIN MLP `seq` to z through the fused tensor-core stages (gin_mlp_fusable(seq) must hold)."""
-    l1, n1, _, l2, n2, _ = seq
-    return _GinMlp.apply(z, l1.weight, l1.bias, n1.weight, n1.bias, l2.weight, l2.bias, n2.weight, n2.bias,
-                         _bn_dict(n1), _bn_dict(n2))

@@ -50,7 +50,7 @@ def _structure_tensors(data):
     """every device tensor the GIN / RGIN train step reads from a compiled Batch, in a fixed order, plus the host
     scalars that are baked into kernel arguments (the CUDA-graph signature)."""
     s = data.structure
-    tensors = [data.x, data.y, s.node_ptr]
+    tensors = [data.x, data.y, s.node_ptr, s.row2seg]
     scalars = [s.num_nodes]
     for csr in (s.csr_in, s.csr_out):
         tensors += [csr.row_ptr, csr.col, csr.heavy_rows, csr.heavy_count]
@@ -75,6 +75,7 @@ def _static_clone(data):
     d = Batch(data.x.clone(), None, None, y=data.y.clone())
     s = copy.copy(s0)
     s.node_ptr = s0.node_ptr.clone()
+    s._row2seg = None if s0.row2seg is None else s0.row2seg.clone()
     s._rel = {}
     for name in ("csr_in", "csr_out"):
         c0 = getattr(s0, name)
@@ -156,6 +157,7 @@ class ClassificationPipeline:
         if hid in ops._TILED_D and s.node_ptr is not None:   # ... and the aggregation tiling for the model's width
             s.csr_in.tiles(hid)
             s.csr_out.tiles(hid)
+        s.row2seg
         return data
 
     def _train_body(self, data):

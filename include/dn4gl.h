@@ -308,8 +308,12 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
  *   dW (M x K) = gY^T X',  db (M) = colsum gY   (either may be NULL);
  *   GX (N x K) = (gY W) * act_in'(bn_in(X))     (NULL: not needed), and when in_bn != NULL also
  *   sums_prev[2*K] = {sum GX, sum GX * xhat_in}: the batch sums the previous stage's backward needs, so the chain
- *   needs no separate reduction pass.  dgamma = s2, dbeta = s1 of the stage's own sums.               */
-int dn4gl_lin_bwd_f32(const float *G, const float *Yout, int64_t N, int32_t M,
+ *   needs no separate reduction pass.  dgamma = s2, dbeta = s1 of the stage's own sums.
+ * The upstream gradient is G[r] + Gseg[row2seg[r]]: G (N x M, may be NULL) is the gradient arriving row-wise (the next
+ * layer's aggregation backward), Gseg (B x M, may be NULL, pre-scaled by 1/n_g for mean pooling) the gradient of the
+ * per-graph readout of this stage's output (global_add_pool / global_mean_pool backward, gconv.py:213) -- the broadcast
+ * row is added in the prologue instead of being materialised as an N x M tensor.                      */
+int dn4gl_lin_bwd_f32(const float *G, const float *Gseg, const int32_t *row2seg, const float *Yout, int64_t N, int32_t M,
                       const float *bn, const float *sums, int32_t g_masked,
                       const float *W, int32_t K,
                       const float *X, const float *in_bn, int32_t in_act, float in_slope,
@@ -321,8 +325,14 @@ int dn4gl_bn_act_f32(const float *Y, int64_t N, int32_t M, const float *bn, int3
 /* sums[2*M] = {sum_r gm, sum_r gm * xhat}, gm = G * act'(bn(Y)): the batch sums of a BatchNorm whose output
  * gradient G arrives from outside the MLP (aggregation / readout backward)                                        */
 size_t dn4gl_bn_bwd_sums_workspace_bytes(int64_t N, int32_t M);
-int dn4gl_bn_bwd_sums_f32(const float *G, const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope,
-                          float *sums, void *ws, size_t ws_bytes, void *stream);
+int dn4gl_bn_bwd_sums_f32(const float *G, const float *Gseg, const int32_t *row2seg, const float *Y, int64_t N, int32_t M,
+                          const float *bn, int32_t act, float slope, float *sums, void *ws, size_t ws_bytes, void *stream);
+/* out = act(bn(Y)) and pooled[b,:] = sum (mode 0) / mean (mode 1) of out over rows [seg_ptr[b], seg_ptr[b+1]) in one pass
+ * (the layer output handed to the next aggregation + its global_add_pool / global_mean_pool readout, gconv.py:213)   */
+int dn4gl_bn_act_pool_f32(const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope, float *out,
+                          const int32_t *seg_ptr, int32_t B, int32_t mode, float *pooled, void *stream);
+/* out[i] = index of the contiguous segment holding row i (PyG's `batch` vector as int32)                             */
+int dn4gl_segment_ids_i32(const int32_t *seg_ptr, int32_t B, int64_t N, int32_t *out, void *stream);
 
 /* out[0] = sum_i a[i] * b[i] over n floats, fixed-order (the gradient of GINConv's trainable eps: sum(g_z * x)).
  * ws: dn4gl_dot_workspace_bytes; counter: one int32 that is 0 on entry (left 0).                                  */

@@ -170,3 +170,53 @@ def test_gin_mlp_chain_against_torch_float64(din, d, N):
         for i in (1, 4):
             assert rel(getattr(mine.seq[i], k), getattr(ref.seq[i], k)) <= TOL
     assert int(mine.seq[1].num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("M", [32, 64, 24])
+@pytest.mark.parametrize("mean", [False, True])
+def test_bn_act_pool_and_segment_ids(M, mean):
+    from dummynode4graphlearning_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    sizes = torch.randint(1, 300, (57,), generator=g)
+    sizes[3] = 2500
+    N = int(sizes.sum())
+    seg = torch.zeros(58, dtype=torch.int32)
+    seg[1:] = torch.cumsum(sizes, 0)
+    Y = torch.randn(N, M, generator=g).to(dev())
+    rec = torch.cat([torch.randn(M, generator=g) * 0.1, torch.rand(M, generator=g) + 0.5, torch.rand(M, generator=g) + 0.5,
+                     torch.randn(M, generator=g) * 0.1]).to(dev())
+    h, pooled = ops.bn_act_pool(Y, rec, seg.to(dev()), mean=mean)
+    href = torch.relu((Y.double() - rec[:M].double()) * rec[2 * M:3 * M].double() + rec[3 * M:].double())
+    ids = torch.repeat_interleave(torch.arange(57), sizes)
+    assert torch.equal(ops.segment_ids(seg.to(dev()), N).cpu(), ids.to(torch.int32))
+    pref = torch.zeros(57, M, dtype=torch.float64).index_add_(0, ids, href.cpu())
+    if mean:
+        pref = pref / sizes.double().unsqueeze(1)
+    assert rel(h, href) <= 1e-6
+    assert rel(pooled, pref) <= TOL
+    assert torch.equal(h, ops.bn_act(Y, rec))
+
+
+@pytest.mark.parametrize("K,M", [(32, 32), (64, 64), (64, 32)])
+def test_lin_bwd_with_readout_gradient(K, M):
+    """G + gseg[row2seg] folded into the prologue == the materialised sum (and G = None == broadcast only)."""
+    from dummynode4graphlearning_b200 import ops
+    g = torch.Generator().manual_seed(K + M)
+    N, B = 9000, 40
+    ids = torch.sort(torch.randint(0, B, (N,), generator=g)).values.to(torch.int32).to(dev())
+    x = torch.randn(N, K, generator=g).to(dev())
+    W = (torch.randn(M, K, generator=g) / K ** 0.5).to(dev())
+    G = torch.randn(N, M, generator=g).to(dev())
+    gseg = torch.randn(B, M, generator=g).to(dev())
+    Y = torch.randn(N, M, generator=g).to(dev())
+    rec = torch.cat([torch.zeros(M), torch.ones(M), torch.rand(M, generator=g) + 0.5, torch.zeros(M)]).to(dev())
+    for Gin in (G, None):
+        tot = gseg[ids.long()] + (G if Gin is not None else 0)
+        s_a = ops.bn_bwd_sums(tot, Y, rec)
+        s_b = ops.bn_bwd_sums(Gin, Y, rec, gseg=gseg, row2seg=ids)
+        assert rel(s_b, s_a) <= 1e-6
+        ra = ops.lin_bwd(tot, W, x, Yout=Y, bn=rec, sums=s_a)
+        rb = ops.lin_bwd(Gin, W, x, Yout=Y, bn=rec, sums=s_a, gseg=gseg, row2seg=ids)
+        for a, b in zip(ra, rb):
+            if a is not None:
+                assert rel(b, a) <= 1e-6
