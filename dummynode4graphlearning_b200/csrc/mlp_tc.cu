@@ -26,6 +26,9 @@
 namespace {
 
 constexpr int TC_THREADS = 128;          // 4 warps <-> the 128 TMEM lanes
+#ifndef TC_SPLIT_ACC
+#define TC_SPLIT_ACC 1                   // accumulators per logical GEMM (1, 2; see lin_fwd_kernel)
+#endif
 constexpr uint32_t PANEL128 = 128u * 128u;   // bytes of one 128-row panel (32 floats per row)
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -85,6 +88,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// v = sum of NB column blocks (32 columns each, `stride` columns apart): the hi/lo halves and split accumulators of one
+// logical accumulator block, added smallest-index first with round-to-nearest fp32 adds
+template <int NB>
+__device__ __forceinline__ void tc_ld_sum(uint32_t taddr, uint32_t stride, float (&v)[32]) {
+    tc_ld32(taddr, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int b = 1; b < NB; ++b) {
+        float u[32];
+        tc_ld32(taddr + b * stride, u);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += u[i];
+    }
+}
 
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64))
@@ -279,7 +297,12 @@ __global__ void __launch_bounds__(NT) lin_fwd_kernel(const LinFwdArgs a) {
 
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     const uint32_t bar = s_u32(&bar_mem);
-    constexpr uint32_t TCOLS = 2 * MP;
+    // The tensor core adds every MMA into the fp32 accumulator with truncation (measured: the error grows linearly with
+    // the number of MMAs accumulated, ~2^-24 each: 4e-7 relative at 8 MMAs, 2e-7 when the k-steps are spread over
+    // accumulators of 4 MMAs that the epilogue adds in round-to-nearest).  Splitting costs tensor-memory read bandwidth
+    // (64 B/clk/SM: +57 % time at 1M x 32 with TC_SPLIT_ACC = 2), so the default is one accumulator.
+    constexpr int KSTEPS = KP / 8, NACC = (TC_SPLIT_ACC < KSTEPS / 2 ? TC_SPLIT_ACC : KSTEPS / 2), KPA = KSTEPS / NACC;
+    constexpr uint32_t TCOLS = NACC * 2 * MP;
     if (t == 0) {
         mbar_init(bar, 1);
         for (int s = 0; s < RING; ++s) mbar_init(s_u32(&full_mem[s]), 1);
@@ -350,14 +373,13 @@ __global__ void __launch_bounds__(NT) lin_fwd_kernel(const LinFwdArgs a) {
         __syncthreads();
         if (t == 0) {
             tc_fence_after();
-            uint32_t acc = 0;
 #pragma unroll
-            for (int jj = 0; jj < KP / 8; ++jj) {
+            for (int jj = 0; jj < KSTEPS; ++jj) {
                 const uint32_t aoff = (jj >> 2) * PANEL128 + (jj & 3) * 32u, boff = (jj >> 2) * (2 * MP * 128u) + (jj & 3) * 32u;
                 const uint64_t bd = make_desc(sB + boff, 16, 1024);
-                tc_mma_tf32(tmem, make_desc(sAh + aoff, 16, 1024), bd, IDESC, acc);
-                acc = 1;
-                tc_mma_tf32(tmem, make_desc(sAl + aoff, 16, 1024), bd, IDESC, 1);
+                const uint32_t d = tmem + (jj / KPA) * 2 * MP;
+                tc_mma_tf32(d, make_desc(sAh + aoff, 16, 1024), bd, IDESC, (jj % KPA) != 0 ? 1u : 0u);
+                tc_mma_tf32(d, make_desc(sAl + aoff, 16, 1024), bd, IDESC, 1);
             }
             tc_commit(bar);
         }
@@ -369,14 +391,11 @@ __global__ void __launch_bounds__(NT) lin_fwd_kernel(const LinFwdArgs a) {
         // MP + c are the [W_hi | W_lo] halves
 #pragma unroll
         for (int cb = 0; cb < (w < 4 ? PM : 0); ++cb) {
-            float v[32], u[32];
-            tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, v);
-            tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + MP + cb * 32, u);
-            tc_wait_ld();
+            float v[32];
+            tc_ld_sum<2 * NACC>(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, MP, v);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                sts128(sStage + tile_off(t, cb * 8 + q, 128),
-                       make_float4(v[4 * q] + u[4 * q], v[4 * q + 1] + u[4 * q + 1], v[4 * q + 2] + u[4 * q + 2], v[4 * q + 3] + u[4 * q + 3]));
+                sts128(sStage + tile_off(t, cb * 8 + q, 128), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
         }
         tc_fence_before();
         __syncthreads();
@@ -446,6 +465,8 @@ struct LinBwdArgs {
     int num_tiles;
 };
 
+// room for the shared-memory copy of the weight-gradient blocks (2 MP x 2 KP floats) next to the operand tiles and the ring
+__host__ __device__ constexpr bool bwd_accw_smem(int KP, int MP) { return KP * MP <= 32 * 64; }
 // per-CTA partial record: dW as the four hi/lo blocks the MMA produces ([2 MP] x [2 KP]), db (MP), previous sums (2 KP)
 __host__ __device__ constexpr int bwd_part_floats(int KP, int MP) { return 4 * MP * KP + MP + 2 * KP; }
 
@@ -461,6 +482,12 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
     const uint32_t sGmh = base, sGml = sGmh + G_BYTES, sGh = sGml + G_BYTES, sGl = sGh + G_BYTES;
     const uint32_t sXh = sGl + G_BYTES, sXl = sXh + X_BYTES, sWh = sXl + X_BYTES, sWl = sWh + W_BYTES, sRing = sWl + W_BYTES;
     const uint32_t sStage = sGh;        // the K-major gY copy is dead once the tile's MMAs have completed
+    // Weight-gradient accumulation across the tiles of this CTA.  Left in tensor memory it would see 16 truncating
+    // accumulations per tile (error ~ 16 T 2^-24 after T tiles, biased); instead every tile starts fresh accumulators and
+    // its result is added to a shared-memory copy with fp32 adds (ACCW_SMEM).  Only the 64 x 64 shape has no room for
+    // that copy and keeps accumulating in tensor memory.
+    constexpr bool ACCW_SMEM = bwd_accw_smem(KP, MP);
+    const uint32_t sAccW = sRing + RING * RAW_SLOT;     // [2 KP / 4 float4 columns][2 MP lanes] float4, lane fastest
     static_assert(2 * PM >= PK, "staging tile must fit the K-major gY copy");
     static_assert(2 * MP <= 128, "the weight-gradient MMA stacks gY hi and lo along M = 128");
     __shared__ __align__(8) uint64_t bar_mem;
@@ -470,7 +497,14 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
 
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     const uint32_t bar = s_u32(&bar_mem);
-    constexpr uint32_t TCOLS = 4 * KP;          // data accumulator [0, 2 KP), weight accumulator [2 KP, 4 KP)
+    // accumulators (see lin_fwd_kernel: at most a few MMAs per accumulator): data gradient NACC_D x [2 KP] columns, then
+    // weight gradient NACC_W x [2 KP] columns; the weight accumulators are re-started every tile and added to the CTA's
+    // partial in global memory with fp32 adds
+    constexpr int KS_D = MP / 8, NACC_D = TC_SPLIT_ACC, KPA_D = KS_D / NACC_D;
+    constexpr int NACC_W = TC_SPLIT_ACC, KPA_W = 16 / NACC_W;
+    constexpr uint32_t WBASE = NACC_D * 2 * KP;
+    constexpr uint32_t TCOLS = (WBASE + NACC_W * 2 * KP) <= 128 ? 128 : ((WBASE + NACC_W * 2 * KP) <= 256 ? 256 : 512);
+    static_assert(WBASE + NACC_W * 2 * KP <= 512, "tensor memory budget");
     if (t == 0) {
         mbar_init(bar, 1);
         for (int s = 0; s < RING; ++s) mbar_init(s_u32(&full_mem[s]), 1);
@@ -527,6 +561,7 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
     constexpr uint32_t IDESC_WGT = make_idesc(128, 2 * KP, 1, 1);    // [gY_hi ; gY_lo]^T (MN-major) x [X'_hi | X'_lo] (MN-major)
     uint32_t phase = 0;
     bool first = true;
+    float *part = a.part + static_cast<size_t>(blockIdx.x) * bwd_part_floats(KP, MP);
 
     int j = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
@@ -587,43 +622,56 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
             tc_fence_after();
             if (want_gx) {
                 // data gradient: (128 x MP) x (MP x [KP hi | KP lo]); k-steps of 8 output channels
-                uint32_t acc = 0;
 #pragma unroll
-                for (int jj = 0; jj < MP / 8; ++jj) {
+                for (int jj = 0; jj < KS_D; ++jj) {
                     const uint32_t aoff = (jj >> 2) * PANEL128 + (jj & 3) * 32u;
                     const uint64_t bd = make_desc_mn(sWh + jj * 1024u, MP * 128u);
-                    tc_mma_tf32(tmem, make_desc(sGh + aoff, 16, 1024), bd, IDESC_DATA, acc);
-                    acc = 1;
-                    tc_mma_tf32(tmem, make_desc(sGl + aoff, 16, 1024), bd, IDESC_DATA, 1);
+                    const uint32_t d = tmem + (jj / KPA_D) * 2 * KP;
+                    tc_mma_tf32(d, make_desc(sGh + aoff, 16, 1024), bd, IDESC_DATA, (jj % KPA_D) != 0 ? 1u : 0u);
+                    tc_mma_tf32(d, make_desc(sGl + aoff, 16, 1024), bd, IDESC_DATA, 1);
                 }
             }
             // weight gradient: ([MP hi ; MP lo ; ...] x 128 rows) x (128 rows x [KP hi | KP lo]); k-steps of 8 rows,
-            // accumulated over all tiles of this CTA
-            uint32_t accw = first ? 0u : 1u;
+            // per tile into fresh accumulators (ACCW_SMEM) or on top of the previous tiles
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-                tc_mma_tf32(tmem + 2 * KP, make_desc_mn(sGmh + jj * 1024u, PANEL128), make_desc_mn(sXh + jj * 1024u, PANEL128),
-                            IDESC_WGT, accw);
-                accw = 1;
-            }
+            for (int jj = 0; jj < 16; ++jj)
+                tc_mma_tf32(tmem + WBASE + (jj / KPA_W) * 2 * KP, make_desc_mn(sGmh + jj * 1024u, PANEL128),
+                            make_desc_mn(sXh + jj * 1024u, PANEL128), IDESC_WGT,
+                            ((jj % KPA_W) != 0 || (!ACCW_SMEM && !first)) ? 1u : 0u);
             tc_commit(bar);
         }
-        first = false;
         mbar_wait(bar, phase);
         phase ^= 1;
         __syncwarp();
         tc_fence_after();
+        // ---- this tile's weight-gradient blocks += the CTA's shared-memory copy (thread = accumulator lane, its own
+        // column of float4 slots: conflict-free, no race)
+        if (ACCW_SMEM && w * 32 < 2 * MP) {
+#pragma unroll
+            for (int cb = 0; cb < 2 * PK; ++cb) {
+                float v[32];
+                tc_ld_sum<NACC_W>(tmem + (static_cast<uint32_t>(w * 32) << 16) + WBASE + cb * 32, 2 * KP, v);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t slot = sAccW + static_cast<uint32_t>(((cb * 8 + q) * 2 * MP + t) * 16);
+                    float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    if (!first) {
+                        const float4 p = lds128s(slot);
+                        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                    }
+                    sts128(slot, o);
+                }
+            }
+        }
+        first = false;
         if (want_gx) {
 #pragma unroll
             for (int cb = 0; cb < (w < 4 ? PK : 0); ++cb) {
-                float v[32], u[32];
-                tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, v);
-                tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + KP + cb * 32, u);
-                tc_wait_ld();
+                float v[32];
+                tc_ld_sum<2 * NACC_D>(tmem + (static_cast<uint32_t>(w * 32) << 16) + cb * 32, KP, v);
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    sts128(sStage + tile_off(t, cb * 8 + q, 128),
-                           make_float4(v[4 * q] + u[4 * q], v[4 * q + 1] + u[4 * q + 1], v[4 * q + 2] + u[4 * q + 2], v[4 * q + 3] + u[4 * q + 3]));
+                    sts128(sStage + tile_off(t, cb * 8 + q, 128), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
             }
             tc_fence_before();
             __syncthreads();
@@ -657,17 +705,20 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
         __syncthreads();   // staging aliases the K-major gY copy; the ring slot of this tile is refilled next iteration
     }
 
-    // ---- per-CTA partials: dW blocks (2 MP x 2 KP, from tensor memory), db (MP), previous-stage sums (2 KP)
-    float *part = a.part + static_cast<size_t>(blockIdx.x) * bwd_part_floats(KP, MP);
+    // ---- per-CTA partials: dW blocks (2 MP x 2 KP), db (MP), previous-stage sums (2 KP)
     if (w * 32 < 2 * MP) {
 #pragma unroll
         for (int cb = 0; cb < 2 * PK; ++cb) {
-            float v[32];
-            tc_ld32(tmem + (static_cast<uint32_t>(w * 32) << 16) + 2 * KP + cb * 32, v);
-            tc_wait_ld();
             float4 *dst = reinterpret_cast<float4 *>(part + t * (2 * KP) + cb * 32);
+            if (ACCW_SMEM) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int q = 0; q < 8; ++q) dst[q] = lds128s(sAccW + static_cast<uint32_t>(((cb * 8 + q) * 2 * MP + t) * 16));
+            } else {
+                float v[32];
+                tc_ld_sum<NACC_W>(tmem + (static_cast<uint32_t>(w * 32) << 16) + WBASE + cb * 32, 2 * KP, v);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
         }
     }
     __syncthreads();
@@ -974,7 +1025,8 @@ constexpr size_t fwd_smem_c(int KP, int MP, int ring) {
     return 1024 + 2 * (KP / 32) * 16384 + 2 * (KP / 32) * MP * 128 + static_cast<size_t>(ring) * 128 * KP * 4;
 }
 constexpr size_t bwd_smem_c(int KP, int MP, int ring) {
-    return 1024 + 4 * (MP / 32) * 16384 + 2 * (KP / 32) * 16384 + 2 * (KP / 32) * MP * 128 + static_cast<size_t>(ring) * 128 * (2 * MP + KP) * 4;
+    return 1024 + 4 * (MP / 32) * 16384 + 2 * (KP / 32) * 16384 + 2 * (KP / 32) * MP * 128 + static_cast<size_t>(ring) * 128 * (2 * MP + KP) * 4 +
+           (KP * MP <= 32 * 64 ? 16u * MP * KP : 0u);
 }
 constexpr size_t SMEM_CAP = 227 * 1024 - 4096;     // dynamic shared memory a CTA may ask for (static part + slack kept back)
 size_t fwd_smem(int KP, int MP, int ring) {
@@ -982,7 +1034,7 @@ size_t fwd_smem(int KP, int MP, int ring) {
 }
 size_t bwd_smem(int KP, int MP, int ring) {
     return 1024 + 4 * (MP / 32) * PANEL128 + 2 * (KP / 32) * PANEL128 + 2 * (KP / 32) * MP * 128 +
-           static_cast<size_t>(ring) * 128 * (2 * MP + KP) * 4;
+           static_cast<size_t>(ring) * 128 * (2 * MP + KP) * 4 + (bwd_accw_smem(KP, MP) ? 16u * MP * KP : 0u);
 }
 int ctas_per_sm(size_t smem, int tmem_cols, int threads) {
     int n = static_cast<int>((227 * 1024) / (smem + 2048));
@@ -1001,7 +1053,7 @@ constexpr int NT_FWD = 256, NT_BWD = 512;
 template <int KP, int MP, int RING>
 int launch_fwd(const LinFwdArgs &a, int *grid_out, cudaStream_t s) {
     const size_t smem = fwd_smem(KP, MP, RING);
-    const int grid = tc_grid(a.N, smem, 2 * MP, NT_FWD);
+    const int grid = tc_grid(a.N, smem, (TC_SPLIT_ACC < KP / 16 ? TC_SPLIT_ACC : KP / 16) * 2 * MP, NT_FWD);
     DN_CUDA(cudaFuncSetAttribute(lin_fwd_kernel<KP, MP, RING, NT_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     lin_fwd_kernel<KP, MP, RING, NT_FWD><<<grid, NT_FWD, smem, s>>>(a);
     *grid_out = grid;
@@ -1010,7 +1062,7 @@ int launch_fwd(const LinFwdArgs &a, int *grid_out, cudaStream_t s) {
 template <int KP, int MP, int RING>
 int launch_bwd(const LinBwdArgs &a, int *grid_out, cudaStream_t s) {
     const size_t smem = bwd_smem(KP, MP, RING);
-    const int grid = tc_grid(a.N, smem, 4 * KP, NT_BWD);
+    const int grid = tc_grid(a.N, smem, 2 * TC_SPLIT_ACC * 2 * KP <= 128 ? 128 : (2 * TC_SPLIT_ACC * 2 * KP <= 256 ? 256 : 512), NT_BWD);
     DN_CUDA(cudaFuncSetAttribute(lin_bwd_kernel<KP, MP, RING, NT_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     lin_bwd_kernel<KP, MP, RING, NT_BWD><<<grid, NT_BWD, smem, s>>>(a);
     *grid_out = grid;

@@ -131,13 +131,15 @@ def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD):
     return csr
 
 
-_pending_err = []
+import collections
+
+_pending_err = collections.deque(maxlen=512)   # bounded: a long run that never checks must not pin flags forever
 
 
 def check_errors():
-    """Synchronising check of the asynchronous capacity flags raised by builder kernels."""
-    global _pending_err
-    flags, _pending_err = _pending_err, []
+    """Synchronising check of the asynchronous capacity flags raised by builder kernels (the most recent 512)."""
+    flags = list(_pending_err)
+    _pending_err.clear()
     for f in flags:
         code = int(f.item())
         if code != 0:

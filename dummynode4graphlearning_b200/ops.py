@@ -503,6 +503,69 @@ def gin_mlp(seq, z):
     return gin_layer(seq, z)[0]
 
 
+class _Mlp2(torch.autograd.Function):
+    """``Linear, act, Linear`` (rgin.py:52, dmpnn.py:47,55 with the default num_mlp_layers=2, no BatchNorm) as two
+    tensor-core stages: the activation is the second stage's prologue, its derivative the backward epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, act, slope):
+        x = _f32c(x)
+        y1, _ = lin_fwd(x, W1, b1)
+        y2, _ = lin_fwd(y1, W2, b2, in_act=act, in_slope=slope)
+        ctx.save_for_backward(x, y1, W1, W2)
+        ctx.act, ctx.slope, ctx.has_b = act, slope, (b1 is not None, b2 is not None)
+        return y2
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y1, W1, W2 = ctx.saved_tensors
+        ga1, _, dW2, db2 = lin_bwd(_f32c(g), W2, y1, in_act=ctx.act, in_slope=ctx.slope, want_db=ctx.has_b[1])
+        gx, _, dW1, db1 = lin_bwd(ga1, W1, x, want_gx=ctx.needs_input_grad[0], want_db=ctx.has_b[0])
+        return gx, dW1, db1, dW2, db2, None, None
+
+
+def _act_code(m):
+    import torch.nn as nn
+    if isinstance(m, nn.ReLU):
+        return ACT_RELU, 0.0
+    if isinstance(m, nn.LeakyReLU):
+        return ACT_LEAKY_RELU, float(m.negative_slope)
+    if type(m).__name__ == "Identity":
+        return ACT_NONE, 0.0
+    return None
+
+
+# The counting models chain ~12 of these GEMMs per forward with sum-aggregations over up to 512-node graphs and no
+# normalisation in between: the tensor core's truncating fp32 accumulation is a BIASED error (towards zero) that adds up
+# coherently and reaches 2-4e-5 on the DMPNN "large" loss (fp32 FMA: 2e-6; measured, DESIGN.md section 4 K6), above the
+# 1e-5 parity bar.  The classification GIN is immune (BatchNorm after every Linear removes per-channel bias).  So the
+# tensor-core path of `Linear, act, Linear` is opt-in for the counting models: DN4GL_MLP2_TC=1.
+MLP2_TENSOR_CORES = os.environ.get("DN4GL_MLP2_TC", "0") == "1"
+
+
+def mlp2_fusable(seq, force=False):
+    """True for ``Sequential(Linear, act, Linear)`` with act in {ReLU, LeakyReLU, Identity} and supported widths
+    (and the opt-in switch above, unless force)."""
+    import torch.nn as nn
+    if not (MLP2_TENSOR_CORES or force):
+        return False
+    if not (isinstance(seq, nn.Sequential) and len(seq) == 3):
+        return False
+    l1, a, l2 = seq
+    if not (isinstance(l1, nn.Linear) and isinstance(l2, nn.Linear) and _act_code(a) is not None):
+        return False
+    return lin_supported(l1.in_features, l1.out_features) and lin_supported(l2.in_features, l2.out_features)
+
+
+def mlp2(seq, x):
+    """apply ``Sequential(Linear, act, Linear)`` through the tensor-core stages (mlp2_fusable(seq) must hold)."""
+    l1, a, l2 = seq
+    act, slope = _act_code(a)
+    lead = x.shape[:-1]
+    y = _Mlp2.apply(x.reshape(-1, x.size(-1)), l1.weight, l1.bias, l2.weight, l2.bias, act, slope)
+    return y.view(lead + (l2.out_features,))
+
+
 def gin_mlp_fusable(seq):
     """True if `seq` is the reference's GIN MLP (Linear, BatchNorm1d, ReLU, Linear, BatchNorm1d, ReLU) in a state
     the fused stages reproduce: training-mode batch statistics with a fixed momentum, affine BN, supported widths."""

@@ -65,6 +65,13 @@ class DMPLayer(nn.Module):
             for n in ("src_weight", "dst_weight", "eloop_weight"):
                 getattr(self, n).div_(init_eeigenv)
 
+    def _apply_mlp(self, mlp, x):
+        if len(mlp) == 0:
+            return self.act(x)
+        if x.is_cuda and ops.mlp2_fusable(mlp):
+            return ops.mlp2(mlp, x)                # Linear, act, Linear on the tensor cores (csrc/mlp_tc.cu)
+        return mlp(x)
+
     def forward(self, graph, node_feat, edge_feat):
         # ---- node stream: update_all(message :111-127, fn.sum :92, update :129-140)
         S = ops.dmp_node_agg(edge_feat, graph)
@@ -72,13 +79,13 @@ class DMPLayer(nn.Module):
         n_out = ops.matmul_xw(node_feat, self.nloop_weight) + agg
         if self.nbias is not None:
             n_out = n_out + self.nbias
-        n_out = self.nmlp(n_out) if len(self.nmlp) > 0 else self.act(n_out)
+        n_out = self._apply_mlp(self.nmlp, n_out)
         n_out = self.drop(n_out)
         # ---- edge stream: EDGEAGG side effect (:126) + apply_edges(:142-156)
         PQ = ops.matmul_xw(node_feat, th.cat([self.dst_weight, self.src_weight], dim=1))
         T = ops.matmul_xw(edge_feat, th.cat([self.eloop_weight, self.src_weight - self.dst_weight], dim=1))
         e_out = ops.dmp_edge_update(PQ, T, self.ebias, graph)
-        e_out = self.emlp(e_out) if len(self.emlp) > 0 else self.act(e_out)
+        e_out = self._apply_mlp(self.emlp, e_out)
         e_out = self.drop(e_out)
         return n_out, e_out
 

@@ -114,7 +114,12 @@ class RGINLayer(nn.Module):
             out = out + ops.matmul_xw(node_feat, self.loop_weight)
         if self.bias is not None:
             out = out + self.bias
-        out = self.mlp(out) if len(self.mlp) > 0 else self.act(out)
+        if len(self.mlp) == 0:
+            out = self.act(out)
+        elif out.is_cuda and ops.mlp2_fusable(self.mlp):
+            out = ops.mlp2(self.mlp, out)          # Linear, act, Linear on the tensor cores (csrc/mlp_tc.cu)
+        else:
+            out = self.mlp(out)
         out = self.act(out)   # the reference applies the activation once more after the MLP (rgin.py:147-151)
         out = self.drop(out)
         return out, edge_type

@@ -122,8 +122,11 @@ def tu_add_dummy(b):
                ptr(b["vlabel"]), ptr(b["elabel"]), N, E,
                ptr(o["node_ptr"]), ptr(o["edge_ptr"]), ptr(o["src"]), ptr(o["dst"]),
                ptr(o["vlabel"]), ptr(o["v_is_dummy"]), ptr(o["elabel"]), ptr(o["e_is_dummy"]), _stream())
-    o.lazy("vid", lambda: _local_ids(o["node_ptr"], N + B, dev))
-    o.lazy("eid", lambda: _local_ids(o["edge_ptr"], E + 2 * N, dev))
+    # NB: the thunks must not capture `o` itself (o -> thunk -> o is a reference cycle: the batch's device tensors would
+    # live until the cyclic GC runs and the caching allocator would cudaMalloc fresh blocks meanwhile)
+    o_np, o_ep = o["node_ptr"], o["edge_ptr"]
+    o.lazy("vid", lambda: _local_ids(o_np, N + B, dev))
+    o.lazy("eid", lambda: _local_ids(o_ep, E + 2 * N, dev))
     if "vattr" in b:  # dummy node gets attribute 0 (line 191)
         va = torch.zeros(N + B, dtype=torch.float32, device=dev)
         va[o["v_is_dummy"] == 0] = b["vattr"]

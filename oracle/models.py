@@ -148,7 +148,7 @@ def dmp_layer(sd, p, h, ef, src, dst, is_rev, out_deg, cfg):
     agg = scatter_sum(node_msg, dst, h.size(0))
     n_out = h @ W["nloop"] + agg + sd[p + ".nbias"]                                      # :131-133
     n_out = mlp_seq(sd, p + ".nmlp", n_out, cfg["num_mlp_layers"], act, cfg.get("batch_norm", False))
-    d = (1 + out_deg[dst].unsqueeze(-1).float()).log2()                                  # :144-145
+    d = (1 + out_deg[dst].unsqueeze(-1).to(ef.dtype)).log2()                                 # :144-145
     add = 2 * (1 + d) * (ef @ (W["src"] - W["dst"]))                                     # :146
     e_out = ef @ W["eloop"] + add + edge_msg + sd[p + ".ebias"]                          # :147-149
     e_out = mlp_seq(sd, p + ".emlp", e_out, cfg["num_mlp_layers"], act, cfg.get("batch_norm", False))
@@ -195,8 +195,8 @@ def predict_net(sd, p, p_rep, p_mask, g_rep, g_mask, agg, act, with_weights):
     """PredictNet.forward, pred.py:87-156 (dropout 0).  agg pools over the WHOLE padded axis."""
     pool = {"sum": lambda t: t.sum(1), "mean": lambda t: t.mean(1), "max": lambda t: t.max(1)[0]}[agg]
     B, Lg = g_mask.shape
-    pl = p_mask.float().sum(1).view(B, 1)
-    gl = g_mask.float().sum(1).view(B, 1)
+    pl = p_mask.to(p_rep.dtype).sum(1).view(B, 1)     # dtype of the parameters: the oracle also runs in float64
+    gl = g_mask.to(p_rep.dtype).sum(1).view(B, 1)
     pli, gli = 1.0 / pl, 1.0 / gl
     pv = pool(linear(sd, p + ".p_fc", p_rep))
     g = linear(sd, p + ".g_fc", g_rep)
@@ -337,7 +337,7 @@ def counting_model(sd, pattern_b, graph_b, cfg):
     if cfg.get("edge_pred", True):
         ec, ew = predict_net(sd, "pred_net.e", peo, pem, geo, gem, agg, act_pred, "edge" in rw)
     if vc is not None and ec is not None:                                   # basemodel.py:1506-1512
-        gvl, gel = gm.float().sum(1).view(-1, 1), gem.float().sum(1).view(-1, 1)
+        gvl, gel = gm.to(vc.dtype).sum(1).view(-1, 1), gem.to(vc.dtype).sum(1).view(-1, 1)
         y = (gvl / (gvl + gel)) * vc + (gel / (gvl + gel)) * ec
     else:
         y = vc if vc is not None else ec
@@ -348,7 +348,7 @@ def counting_model(sd, pattern_b, graph_b, cfg):
 def counting_loss(out, counts, rep_reg_w=0.0, neg_slp=0.01):
     """bp_loss of train_epoch with bp_loss='MSE' (train.py:624-625, 776-813), match terms off."""
     crit = lambda pred, target, slp: F.mse_loss(F.leaky_relu(pred, slp), target)
-    loss = crit(out["pred_c"], counts.float().view(-1, 1), neg_slp)
+    loss = crit(out["pred_c"], counts.to(out["pred_c"].dtype).view(-1, 1), neg_slp)
     reg = 0.0
     for k in ("p_v_rep", "p_e_rep", "g_v_rep", "g_e_rep"):
         if out.get(k) is not None:

@@ -220,3 +220,39 @@ def test_lin_bwd_with_readout_gradient(K, M):
         for a, b in zip(ra, rb):
             if a is not None:
                 assert rel(b, a) <= 1e-6
+
+
+@pytest.mark.parametrize("act", ["relu", "leaky_relu", "none"])
+@pytest.mark.parametrize("d,N", [(64, 20000), (32, 333)])
+def test_mlp2_against_torch_float64(act, d, N):
+    """Linear, act, Linear of the counting models (rgin.py:52, dmpnn.py:47,55)."""
+    from dummynode4graphlearning_b200 import ops
+    from dummynode4graphlearning_b200.subgraph_isomorphism.utils import map_activation_str_to_layer
+    torch.manual_seed(d + N)
+    seq = nn.Sequential(nn.Linear(d, d), map_activation_str_to_layer(act), nn.Linear(d, d))
+    ref = nn.Sequential(nn.Linear(d, d), map_activation_str_to_layer(act), nn.Linear(d, d)).double()
+    ref.load_state_dict({k: v.double() for k, v in seq.state_dict().items()})
+    seq = seq.to(dev())
+    assert ops.mlp2_fusable(seq, force=True) and not ops.mlp2_fusable(seq)   # opt-in for the counting models
+    x = torch.randn(N, d)
+    g = torch.randn(N, d)
+    xm = x.to(dev()).requires_grad_(True)
+    ym = ops.mlp2(seq, xm)
+    ym.backward(g.to(dev()))
+    xr = x.double().requires_grad_(True)
+    # same side of the activation kink as the device took (see _ref_forward_with_masks)
+    with torch.no_grad():
+        y1 = ops.lin_fwd(xm.detach(), seq[0].weight, seq[0].bias)[0].cpu()
+    pre = ref[0](xr)
+    if act == "none":
+        a = pre
+    else:
+        slope = 0.0 if act == "relu" else 1 / 5.5
+        pos = (y1 > 0).double()
+        a = pre * (pos + (1 - pos) * slope)
+    yr = ref[2](a)
+    yr.backward(g.double())
+    assert rel(ym, yr) <= TOL
+    assert rel(xm.grad, xr.grad) <= TOL
+    for (k, pm), (_, pr) in zip(seq.named_parameters(), ref.named_parameters()):
+        assert rel(pm.grad, pr.grad) <= TOL, k
