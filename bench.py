@@ -316,8 +316,7 @@ def ours(a):
                 "traffic": None}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(pipe, world)
         return
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -341,8 +340,20 @@ def ours(a):
                                        for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1]["total_ms"])}},
     }
     print(json.dumps(line))
+    _finish(pipe, world)
+
+
+def _finish(pipe, world):
+    """multi-rank teardown: the captured train step holds NCCL work inside live CUDA graphs, and
+    destroy_process_group() blocks on that (observed: both ranks hang after the line is printed).  Drop the graphs,
+    drain the device and leave the process directly -- the measurement is complete and printed."""
+    import sys
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        pipe._graphs.clear()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":
