@@ -170,7 +170,9 @@ class ClassificationPipeline:
             gb = self.global_batch or data.num_graphs * torch.distributed.get_world_size()
             self.bucket.all_reduce(data.num_graphs / gb)
         self.opt.step()                                     # main.py:43
-        return loss
+        # detached: a caller holding the loss must not keep this step's autograd graph (and its AccumulateGrad nodes,
+        # bound to the stream they were created on) alive into the next step / a CUDA-graph capture
+        return loss.detach()
 
     def replayed_library_kernels(self):
         """libdn4gl kernels launched through CUDA-graph replays so far (they bypass the library's launch counter)."""
@@ -202,14 +204,83 @@ class ClassificationPipeline:
         return float(self.step_resident(dev).item())
 
 
+def _graph_tensors(g):
+    """device tensors a counting-model step reads from a BatchedGraph (fixed order) + the host scalars baked into kernel
+    arguments and tensor shapes (padded lengths come from the per-graph maxima)."""
+    tensors = [g.src, g.dst, g.node_ptr, g.edge_ptr]
+    scalars = [g.batch_size, g.number_of_nodes(), g.number_of_edges(), g.max_num_nodes(), g.max_num_edges()]
+    for frame in (g.ndata, g.edata):
+        for k in sorted(frame):
+            tensors.append(frame[k])
+            scalars.append(k)
+    for csr in (g._csr_in, g._csr_out):
+        if csr is None:
+            tensors += [None] * 5
+            scalars.append(None)
+        else:
+            tensors += [csr.row_ptr, csr.col, csr.eid, csr.heavy_rows, csr.heavy_count]
+            scalars += [csr.n_rows, csr.nnz, csr.heavy_thr, csr.max_seg]
+    return tensors, scalars
+
+
+def _static_graph(g):
+    """private copy of a BatchedGraph (the buffers a captured CUDA graph reads); caches that the model fills during its
+    forward (relation CSRs, int32 views, tilings) start empty so that the captured forward recomputes them."""
+    c = BatchedGraph(g.src.clone(), g.dst.clone(), g.node_ptr.clone(), g.edge_ptr.clone(),
+                     {k: v.clone() for k, v in g.ndata.items()}, {k: v.clone() for k, v in g.edata.items()})
+    c._n, c._host_sizes = g._n, g._host_sizes
+    for name in ("_csr_in", "_csr_out"):
+        c0 = getattr(g, name)
+        if c0 is not None:
+            n = CSR(c0.row_ptr.clone(), c0.col.clone(), c0.eid.clone(), c0.n_rows, c0.nnz)
+            n.heavy_rows = None if c0.heavy_rows is None else c0.heavy_rows.clone()
+            n.heavy_count = None if c0.heavy_count is None else c0.heavy_count.clone()
+            n.heavy_thr, n.seg_ptr, n.max_seg = c0.heavy_thr, c.node_ptr, c0.max_seg
+            setattr(c, name, n)
+    return c
+
+
+class _CapturedCountingStep:
+    """CUDA graph of one counting train step (forward, loss, backward, all-reduce, clipping, optimizer) for one
+    (pattern, graph) batch signature."""
+
+    def __init__(self, pipe, pattern, graph, counts):
+        from ._lib import lib
+        self.pattern, self.graph_batch, self.counts = _static_graph(pattern), _static_graph(graph), counts.clone()
+        self.static = _graph_tensors(self.pattern)[0] + _graph_tensors(self.graph_batch)[0] + [self.counts]
+        self.replays = 0
+        self.graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        k0 = lib().kernel_launches()
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        with torch.cuda.graph(self.graph):
+            self.loss = pipe._train_body(self.pattern, self.graph_batch, self.counts)
+        self.library_kernels = lib().kernel_launches() - k0
+
+    def run(self, pattern, graph, counts):
+        src = _graph_tensors(pattern)[0] + _graph_tensors(graph)[0] + [counts]
+        pairs = [(d, s) for d, s in zip(self.static, src) if d is not None]
+        torch._foreach_copy_([d for d, _ in pairs], [s for _, s in pairs])
+        self.graph.replay()
+        self.replays += 1
+        return self.loss
+
+
 class CountingPipeline:
-    def __init__(self, model, optimizer, config, add_dummy=True, rep_reg_w=0.0, neg_slp=0.01, max_grad_norm=8.0):
-        """config: the dataset maxima BEFORE augmentation (max_npv ... max_ngel)."""
+    def __init__(self, model, optimizer, config, add_dummy=True, rep_reg_w=0.0, neg_slp=0.01, max_grad_norm=8.0,
+                 cuda_graphs=None, max_graphs=8):
+        """config: the dataset maxima BEFORE augmentation (max_npv ... max_ngel).  cuda_graphs: as in
+        ClassificationPipeline (default: on exactly when the optimizer was built with capturable=True)."""
         self.model, self.opt, self.cfg, self.add_dummy = model, optimizer, config, add_dummy
         self.rep_reg_w, self.neg_slp, self.max_grad_norm = rep_reg_w, neg_slp, max_grad_norm
         self.bucket = GradientBucket(model.parameters())
         self.device = next(model.parameters()).device
         self.global_batch = None
+        capturable = all(g.get("capturable", False) for g in optimizer.param_groups)
+        self.cuda_graphs = capturable if cuda_graphs is None else bool(cuda_graphs)
+        if self.cuda_graphs and not capturable:
+            raise ValueError("cuda_graphs=True needs an optimizer built with capturable=True")
+        self._graphs, self._max_graphs = {}, max_graphs
 
     def transform(self, p_dev, g_dev):
         c = self.cfg
@@ -231,19 +302,39 @@ class CountingPipeline:
                     loss = loss + self.rep_reg_w * crit(out[k], torch.zeros_like(out[k]), 1) * out[k].size(1)
         return loss
 
-    def train_on(self, pattern, graph, counts):
-        self.model.train()
+    def _train_body(self, pattern, graph, counts):
         self.bucket.zero()
         out = self.model(pattern, graph)
         loss = self.loss_fn(out, counts)
         loss.backward()
+        self.bucket._ensure()
         if is_distributed():
             gb = self.global_batch or pattern.batch_size * torch.distributed.get_world_size()
             self.bucket.all_reduce(pattern.batch_size / gb)
         if self.max_grad_norm and self.max_grad_norm > 0:   # clip AFTER the reduction (train.py:833-834)
-            torch.nn.utils.clip_grad_norm_(self.bucket.params, self.max_grad_norm)
+            torch.nn.utils.clip_grad_norm_(self.bucket.active, self.max_grad_norm)
         self.opt.step()
-        return loss
+        return loss.detach()   # see ClassificationPipeline._train_body
+
+    def replayed_library_kernels(self):
+        return sum(e.replays * e.library_kernels for e in self._graphs.values() if isinstance(e, _CapturedCountingStep))
+
+    def train_on(self, pattern, graph, counts):
+        self.model.train()
+        if not self.cuda_graphs:
+            return self._train_body(pattern, graph, counts)
+        tp, sp = _graph_tensors(pattern)
+        tg, sg = _graph_tensors(graph)
+        sig = (tuple(None if t is None else (tuple(t.shape), t.dtype) for t in tp + tg), tuple(sp), tuple(sg),
+               tuple(counts.shape))
+        ent = self._graphs.get(sig)
+        if ent is None:
+            if len(self._graphs) < self._max_graphs:
+                self._graphs[sig] = "seen"
+            return self._train_body(pattern, graph, counts)
+        if ent == "seen":
+            ent = self._graphs[sig] = _CapturedCountingStep(self, pattern, graph, counts)
+        return ent.run(pattern, graph, counts)
 
     def step_resident(self, p_dev, g_dev, counts_dev):
         pattern, graph = self.transform(p_dev, g_dev)

@@ -51,3 +51,35 @@ def test_graphs_need_capturable_optimizer():
     assert ClassificationPipeline(model, opt).cuda_graphs is False
     with pytest.raises(ValueError):
         ClassificationPipeline(model, opt, cuda_graphs=True)
+
+
+@pytest.mark.parametrize("name,shape,bs,over", [("RGIN", "small", 24, dict(rep_rgin_regularizer="bdd", rep_rgin_num_bases=4)),
+                                                ("DMPNN", "small", 24, dict(node_pred=True, edge_pred=True))])
+def test_counting_graph_replay_equals_eager_steps(name, shape, bs, over):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from bench_counting import build
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.pipelines import CountingPipeline
+    dev = torch.device("cuda:0")
+
+    def run(graphs):
+        model, cfg, _ = build(name, shape, over, dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, amsgrad=True, capturable=True)
+        pipe = CountingPipeline(model, opt, cfg, add_dummy=True, rep_reg_w=1e-3, cuda_graphs=graphs)
+        batches = []
+        for seed in (1, 2):
+            p, g, c = synth.counting_batch(shape, bs, seed=seed)
+            batches.append((T.to_device(p, dev), T.to_device(g, dev), torch.from_numpy(c).to(dev)))
+        losses = [float(pipe.step_resident(*batches[i % 2 if i < 4 else 0]).item()) for i in range(8)]
+        return losses, {k: v.detach().clone() for k, v in model.state_dict().items()}, pipe
+
+    le, se, _ = run(False)
+    lg, sg, pipe = run(True)
+    assert pipe.replayed_library_kernels() > 0, "no CUDA graph was replayed"
+    for a, b in zip(le, lg):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (le, lg)
+    for k in se:
+        if se[k].is_floating_point():
+            denom = float(se[k].abs().max().clamp_min(1e-12))
+            assert float((se[k] - sg[k]).abs().max()) / denom <= 1e-4, k
