@@ -5,3 +5,4 @@ from .embed import (EquivariantEmbedding, MultihotEmbedding, NormalEmbedding, Or
 from .filter import ScalarFilter  # noqa: F401
 from .pred import MaxPredictNet, MeanPredictNet, PredictNet, SumPredictNet  # noqa: F401
 from .rgin import RGIN, RGINLayer  # noqa: F401
+from .rgcn import RGCN, RGCNLayer  # noqa: F401

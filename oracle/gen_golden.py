@@ -103,6 +103,41 @@ def gen_counting():
     print("counting_models.pt:", [k for k in out if not k.startswith("_")])
 
 
+def gen_counting_rgcn():
+    """the reference's RGCN class, added to counting_models.pt (same batch as gen_counting)."""
+    path = os.path.join(OUT, "counting_models.pt")
+    out = th.load(path, weights_only=False)
+    b = out["_batch"]
+    pd_, gd_, counts, mc = b["pattern"], b["graph"], b["counts"], b["model_cfg"]
+    variants = {
+        "RGCN/in_basis": dict(hid_dim=16, pred_hid_dim=16, rep_rgcn_edge_norm="in", rep_rgcn_regularizer="basis",
+                              rep_rgcn_num_bases=-1),
+        "RGCN/both_bdd4": dict(hid_dim=16, pred_hid_dim=16, rep_rgcn_edge_norm="both", rep_rgcn_regularizer="bdd",
+                               rep_rgcn_num_bases=4, pred_net="MeanPredictNet", pred_return_weights="none"),
+        "RGCN/none_basis4_bn_unshared": dict(hid_dim=16, pred_hid_dim=16, rep_rgcn_edge_norm="none",
+                                             rep_rgcn_regularizer="basis", rep_rgcn_num_bases=4, rep_rgcn_batch_norm=True,
+                                             share_rep_net=False, rep_act_func="relu"),
+    }
+    for tag, over in variants.items():
+        kw = rd.counting_kwargs({k: v for k, v in mc.items() if k.startswith("max_")}, **over)
+        model = rd.ref_counting_model("RGCN", kw, seed=zlib.crc32(tag.encode()) % 1000)
+        o = model(rd.dgl_batched(pd_), rd.dgl_batched(gd_))
+        c = th.from_numpy(counts).float().view(-1, 1)
+        crit = lambda pred, target, slp: F.mse_loss(F.leaky_relu(pred, slp), target)
+        loss = crit(o["pred_c"], c, 0.01)
+        reg = 0.0
+        for k in ("p_v_rep", "p_e_rep", "g_v_rep", "g_e_rep"):
+            if o[k] is not None:
+                reg = reg + crit(o[k], th.zeros_like(o[k]), 1) * o[k].size(1)
+        loss = loss + 1e-3 * reg
+        loss.backward()
+        out[tag] = dict(name="RGCN", kwargs=kw, state_dict={k: v.clone() for k, v in model.state_dict().items()},
+                        outputs={k: (v.detach().clone() if isinstance(v, th.Tensor) else None) for k, v in o.items()},
+                        loss=loss.detach().clone(), grads=_grads(model))
+    th.save(out, path)
+    print("counting_models.pt:", [k for k in out if not k.startswith("_")])
+
+
 def gen_classification():
     out = {}
     raw = synth.tu_batch("mutag", 10, seed=41)
@@ -144,4 +179,5 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_transforms()
     gen_counting()
+    gen_counting_rgcn()
     gen_classification()

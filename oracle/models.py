@@ -132,6 +132,39 @@ def rgin_layer(sd, p, h, src, dst, etype, cfg):
     return act(act(out)) if cfg["num_mlp_layers"] == 0 else act(out)                     # :147-151
 
 
+def rgcn_layer(sd, p, h, src, dst, etype, in_deg, out_deg, cfg):
+    """RGCNLayer, rgcn.py:102-197: per-edge weight gather + bmm, per-edge norm (in: 1/(indeg[dst]+1); both:
+    sqrt(outnorm[src] * innorm[dst]); :134-165), fn.sum, normalised self loop (:170-180), bias, [BatchNorm], act."""
+    N, D = h.shape
+    R, reg, nb, en = cfg["num_rels"], cfg["regularizer"], cfg["num_bases"], cfg["edge_norm"]
+    act = act_fn(cfg["act_func"])
+    if reg in ("none", "basis"):
+        w = sd[p + ".weight"]
+        if (p + ".w_comp") in sd and sd[p + ".w_comp"] is not None:
+            w = th.matmul(sd[p + ".w_comp"], w.view(w.size(0), -1)).view(R, D, -1)       # :104-107
+        msg = th.bmm(h[src].unsqueeze(1), w.index_select(0, etype)).squeeze(1)          # :110-111
+    else:
+        si = D // nb
+        w = sd[p + ".weight"].index_select(0, etype).view(-1, si, si)                    # :120
+        msg = th.bmm(h[src].reshape(-1, 1, si), w).view(-1, D)                           # :121
+    innorm = (1.0 / (in_deg.to(h.dtype) + 1)).view(-1, 1)                               # self_loop is always on (:222-239)
+    outnorm = (1.0 / (out_deg.to(h.dtype) + 1)).view(-1, 1)
+    if en == "in":
+        msg = msg * innorm[dst]
+    elif en == "both":
+        msg = msg * (outnorm[src] * innorm[dst]) ** 0.5
+    agg = scatter_sum(msg, dst, N)
+    loop = h @ sd[p + ".loop_weight"]
+    if en == "in":
+        loop = loop * innorm
+    elif en == "both":
+        loop = loop * (innorm * outnorm) ** 0.5
+    out = agg + loop + sd[p + ".bias"]
+    if cfg.get("batch_norm", False):
+        out = batch_norm_train(sd, p + ".bn", out)
+    return act(out)
+
+
 def dmp_layer(sd, p, h, ef, src, dst, is_rev, out_deg, cfg):
     """DMPLayer, dmpnn.py:111-166."""
     act = act_fn(cfg["act_func"])
@@ -266,8 +299,12 @@ def counting_model(sd, pattern_b, graph_b, cfg):
             e = e * eg
         for i in range(cfg["num_layers"]):
             if not v2:
-                p = "%s_rep_net.rgin.%s_rgin_(%d)" % (side, cfg["rep_name"][side], i)
-                o = rgin_layer(sd, p, v, S["src"], S["dst"], S["elabel"], cfg["layer"][side])
+                if cfg["model"] == "RGCN":
+                    p = "%s_rep_net.rgcn.%s_rgcn_(%d)" % (side, cfg["rep_name"][side], i)
+                    o = rgcn_layer(sd, p, v, S["src"], S["dst"], S["elabel"], S["in_deg"], S["out_deg"], cfg["layer"][side])
+                else:
+                    p = "%s_rep_net.rgin.%s_rgin_(%d)" % (side, cfg["rep_name"][side], i)
+                    o = rgin_layer(sd, p, v, S["src"], S["dst"], S["elabel"], cfg["layer"][side])
                 if vg is not None:
                     o = o * vg
                 v = v + o if residual and v.shape == o.shape else o

@@ -37,6 +37,9 @@ def _install_shims():
     dgl = types.ModuleType("dgl")
     fn = types.ModuleType("dgl.function")
     fn.sum = fake_dgl.function.sum
+    fn.TargetCode = fake_dgl.function.TargetCode                      # dgl 0.4 names used by models/rgcn.py:157-161
+    fn.CopyMessageFunction = fake_dgl.function.CopyMessageFunction
+    fn.copy_u = fake_dgl.function.copy_u
     dgl.function = fn
     dgl.DGLGraph = fake_dgl.DGLGraph
     dgl.batch = fake_dgl.batch
@@ -64,6 +67,7 @@ def subgraph():
     ns.models = importlib.import_module("models")
     ns.rgin = importlib.import_module("models.rgin")
     ns.dmpnn = importlib.import_module("models.dmpnn")
+    ns.rgcn = importlib.import_module("models.rgcn")
     ns.pred = importlib.import_module("models.pred")
     ns.embed = importlib.import_module("models.embed")
     ns.filter = importlib.import_module("models.filter")

@@ -21,10 +21,28 @@ class _SumReduce:
         self.msg, self.out = msg, out
 
 
+class _TargetCode:      # dgl 0.4 ``fn.TargetCode`` (rgcn.py:157)
+    SRC, DST, EDGE = 0, 1, 2
+
+
 class function:  # stands for the module ``dgl.function``
+    TargetCode = _TargetCode
+
     @staticmethod
     def sum(msg, out):
         return _SumReduce(msg, out)
+
+    @staticmethod
+    def CopyMessageFunction(target, in_field, out_field):
+        """dgl 0.4 builtin: copy a source / destination node field (or an edge field) onto the edges."""
+        def f(edges):
+            frame = {_TargetCode.SRC: edges.src, _TargetCode.DST: edges.dst, _TargetCode.EDGE: edges.data}[target]
+            return {out_field: frame[in_field]}
+        return f
+
+    @staticmethod
+    def copy_u(u, out):
+        return lambda edges: {out: edges.src[u]}
 
 
 class _EdgeBatch:

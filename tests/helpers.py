@@ -15,9 +15,11 @@ def oracle_cfg(name, kw):
     """oracle.models.counting_model config equivalent to the constructor kwargs `kw`."""
     shared = kw.get("share_rep_net", True)
 
+    pre = "rep_rgcn" if name == "RGCN" else "rep_rgin"
+
     def nb(n_rel):
-        b = kw.get("rep_rgin_num_bases", -1)
-        reg = kw.get("rep_rgin_regularizer", "basis")
+        b = kw.get(pre + "_num_bases", -1)
+        reg = kw.get(pre + "_regularizer", "basis")
         return n_rel if (reg == "none" or b is None or b > n_rel or b <= 0) else b
 
     n_layers = kw.get("rep_num_graph_layers", 1)
@@ -25,6 +27,11 @@ def oracle_cfg(name, kw):
         lay = dict(num_rels=kw["max_ngel"], regularizer=kw.get("rep_rgin_regularizer", "basis"), num_bases=nb(kw["max_ngel"]),
                    num_mlp_layers=kw.get("rep_rgin_num_mlp_layers", 2), act_func=kw.get("rep_act_func", "relu"),
                    batch_norm=kw.get("rep_rgin_batch_norm", False))
+        layp = dict(lay) if shared else dict(lay, num_rels=kw["max_npel"], num_bases=nb(kw["max_npel"]))
+    elif name == "RGCN":
+        lay = dict(num_rels=kw["max_ngel"], regularizer=kw.get("rep_rgcn_regularizer", "basis"), num_bases=nb(kw["max_ngel"]),
+                   edge_norm=kw.get("rep_rgcn_edge_norm", "in"), act_func=kw.get("rep_act_func", "relu"),
+                   batch_norm=kw.get("rep_rgcn_batch_norm", False))
         layp = dict(lay) if shared else dict(lay, num_rels=kw["max_npel"], num_bases=nb(kw["max_npel"]))
     else:
         lay = dict(num_mlp_layers=kw.get("rep_dmpnn_num_mlp_layers", 2), act_func=kw.get("rep_act_func", "relu"),

@@ -97,7 +97,8 @@ def test_closed_forms_on_random_graphs():
 
 
 @pytest.mark.parametrize("tag", ["RGIN/bdd4", "RGIN/basis_full", "RGIN/basis4_unshared", "DMPNN/node", "DMPNN/node_edge",
-                                 "DMPNN/edge_max_nofilter"])
+                                 "DMPNN/edge_max_nofilter", "RGCN/in_basis", "RGCN/both_bdd4",
+                                 "RGCN/none_basis4_bn_unshared"])
 def test_counting_oracle_matches_reference_golden(tag):
     gold = load_golden("counting_models.pt")
     g, b = gold[tag], gold["_batch"]
