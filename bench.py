@@ -123,54 +123,91 @@ def reference_arm(a):
 def workload_config(graphs, n_gpus):
     return {"workload": "c2: dummy + edge-to-vertex (CONJ) transform + GIN(hidden 32, 4 layers, train_eps, sum pool) "
                         "train step on synthetic PROTEINS-shaped graphs", "graphs_per_gpu": graphs,
-            "global_batch": graphs * n_gpus, "avg_nodes": 39, "optimizer": "Adam(lr=0.01, capturable)", "train_step": "CUDA graph replay per batch signature (transform eager)",
+            "global_batch": graphs * n_gpus, "avg_nodes": 39, "optimizer": "Adam(lr=0.01) as one flat-buffer kernel (dn4gl_adam_f32)", "train_step": "CUDA graph replay per batch signature (transform eager)",
             "parallelism": "dp%d" % n_gpus, "l2": "flushed between steps (256 MiB write inside the timed region)"}
 
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).
+
+    Sampled in-process through NVML every 10 ms by a daemon thread (the timed region of the default run is ~50-100 ms,
+    too short for a freshly spawned `nvidia-smi -lms` to report anything); falls back to one `nvidia-smi` query taken
+    while the GPU is still busy if NVML cannot be loaded."""
+
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, index):
-        self.path = "/tmp/dn4gl_clocks_%d_%d.csv" % (os.getpid(), index)
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        import threading
+        self.sm, self.reasons, self.mx, self.err = [], set(), None, None
+        self._stop = threading.Event()
+        self.nv = self.h = None
         try:
-            self.f = open(self.path, "w")
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            try:
+                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+        except Exception as e:   # noqa: BLE001
+            self.err = "nvml: %s" % e
+        self.index = index
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
         except Exception:
-            self.p = None
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, const in self.REASONS:
+            if mask & getattr(nv, const):
+                self.reasons.add(name)
+
+    def _run(self):
+        if self.nv is None:
+            return
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception as e:   # noqa: BLE001
+                self.err = "nvml: %s" % e
+                return
+            self._stop.wait(0.01)
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0]
+            c = [x.strip() for x in out.split(",")]
+            self.sm.append(float(c[0])); self.mx = float(c[1])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+        except Exception as e:   # noqa: BLE001
+            self.err = "nvidia-smi: %s" % e
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        for ln in open(self.path):
-            c = [x.strip() for x in ln.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.path)
-        except OSError:
-            pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        """call while the last timed work is still in flight or just done"""
+        if self.nv is None:
+            self._smi_once()
+        self._stop.set()
+        self.t.join(timeout=2)
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+               "samples": len(self.sm), "reasons": sorted(self.reasons), "how": "nvml thread, 10 ms period" if self.nv else "nvidia-smi"}
+        if self.err and not self.sm:
+            out["error"] = self.err
+        return out
 
 
 class EntryPointTimer:
@@ -225,7 +262,8 @@ def ours(a):
     args = Namespace(num_features=NUM_NODE_LABELS, hidden_dim=HID, num_classes=CLASSES, dropout_ratio=0.0,
                      additional={"train_eps": True, "num_layers": LAYERS, "aggregation": "sum"}, epochs=1, device=str(dev))
     model = GIN(args).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=LR, capturable=True)   # device-side step counter: the step can be captured
+    from dummynode4graphlearning_b200.optim import FlatAdam
+    opt = FlatAdam(model.parameters(), lr=LR)   # torch.optim.Adam's update rule as ONE kernel over flat buffers (capturable)
     pipe = ClassificationPipeline(model, opt, mode="conj", num_node_labels=NUM_NODE_LABELS, node_label_min=0)
     pipe.global_batch = a.graphs * world
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -252,7 +290,6 @@ def ours(a):
     barrier()
     launches = L.kernel_launches() + pipe.replayed_library_kernels() - k0
     ms = max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
-    clk = clocks.stop() if clocks else None
     value = a.graphs * world / (ms * 1e-3)
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------------------
@@ -266,6 +303,7 @@ def ours(a):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / a.steps
     e2e_value = a.graphs * world / (e2e_ms * 1e-3)
+    clk = clocks.stop() if clocks else None      # sampled over both timed regions (device-timed steps and e2e steps)
 
     # ---- per-entry-point device times + breakdown (instrumented pass, not part of `value`) -----------------
     timer = EntryPointTimer()

@@ -1,4 +1,6 @@
 // libdn4gl.so -- error plumbing, exclusive scan, stable CSR construction.
+#include <type_traits>
+
 #include "common.cuh"
 
 #include <string.h>
@@ -179,8 +181,28 @@ __device__ __forceinline__ unsigned long long sort_key(const int32_t *__restrict
 constexpr int LIGHT_SORT_MAX = 32;
 constexpr int HEAVY_SORT_MID = 4096;
 
-// one thread per row, rows with <= 32 items: insertion sort in local memory.  Longer rows are
-// appended to a work list for the CTA-per-row kernel.
+// compare-exchange of a sorting network
+template <typename K>
+__device__ __forceinline__ void cswap(K &a, K &b) {
+    const K lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo; b = hi;
+}
+
+// Batcher's odd-even merge sort of 8 keys held in registers (19 comparators)
+template <typename K>
+__device__ __forceinline__ void sort8(K (&a)[8]) {
+    cswap(a[0], a[1]); cswap(a[2], a[3]); cswap(a[4], a[5]); cswap(a[6], a[7]);
+    cswap(a[0], a[2]); cswap(a[1], a[3]); cswap(a[4], a[6]); cswap(a[5], a[7]);
+    cswap(a[1], a[2]); cswap(a[5], a[6]);
+    cswap(a[0], a[4]); cswap(a[1], a[5]); cswap(a[2], a[6]); cswap(a[3], a[7]);
+    cswap(a[2], a[4]); cswap(a[3], a[5]);
+    cswap(a[1], a[2]); cswap(a[3], a[4]); cswap(a[5], a[6]);
+}
+
+// one thread per row.  Rows with <= 8 items (almost every non-dummy row of the configs: mean degree 2-7) are sorted
+// by a register sorting network; rows with <= 32 items by an insertion sort in local memory.  Longer rows are appended
+// to a work list for the CTA-per-row kernels.
+template <bool HAS_PRIMARY>
 __global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, int32_t *__restrict__ items,
                                 const int32_t *__restrict__ primary, int32_t *__restrict__ worklist,
                                 int32_t *__restrict__ work_count) {
@@ -193,8 +215,28 @@ __global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, 
         if (d > HEAVY_SORT_MID) atomicAdd(work_count + 1, 1);
         return;
     }
+    if (d <= 8) {
+        if constexpr (HAS_PRIMARY) {
+            unsigned long long a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = (i < d) ? sort_key(primary, items[beg + i]) : ~0ull;
+            sort8(a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < d) items[beg + i] = static_cast<int32_t>(a[i] & 0xffffffffu);
+        } else {
+            int a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = (i < d) ? items[beg + i] : INT32_MAX;
+            sort8(a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < d) items[beg + i] = a[i];
+        }
+        return;
+    }
     unsigned long long a[LIGHT_SORT_MAX];
-    for (int i = 0; i < d; ++i) a[i] = sort_key(primary, items[beg + i]);
+    for (int i = 0; i < d; ++i) a[i] = sort_key(HAS_PRIMARY ? primary : nullptr, items[beg + i]);
     for (int i = 1; i < d; ++i) {
         unsigned long long k = a[i];
         int j = i - 1;
@@ -202,6 +244,52 @@ __global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, 
         a[j + 1] = k;
     }
     for (int i = 0; i < d; ++i) items[beg + i] = static_cast<int32_t>(a[i] & 0xffffffffu);
+}
+
+// one CTA per listed row with LIGHT_SORT_MAX < d <= HEAVY_SORT_MID items (the dummy rows: one per graph, as long as
+// the graph): bitonic sort of the keys (primary[item], item) in shared memory, O(d log^2 d) instead of the O(d^2)
+// rank sort that the 2 000-item dummy rows of the largest C2 graphs made the long pole of every CSR build (profiles/r1d:
+// 38-62 us per call).
+constexpr int BITONIC_THREADS = 512;
+template <bool HAS_PRIMARY>
+__global__ void __launch_bounds__(BITONIC_THREADS) sort_rows_bitonic(const int32_t *__restrict__ row_ptr,
+                                                                     int32_t *__restrict__ items,
+                                                                     const int32_t *__restrict__ primary,
+                                                                     const int32_t *__restrict__ worklist,
+                                                                     const int32_t *__restrict__ work_count) {
+    using K = typename std::conditional<HAS_PRIMARY, unsigned long long, unsigned int>::type;
+    __shared__ K keys[HEAVY_SORT_MID];
+    const int n_work = work_count[0];
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int r = worklist[w];
+        const int beg = row_ptr[r], d = row_ptr[r + 1] - beg;
+        if (d <= LIGHT_SORT_MAX || d > HEAVY_SORT_MID) continue;
+        int P = 64;
+        while (P < d) P <<= 1;
+        for (int i = threadIdx.x; i < P; i += BITONIC_THREADS) {
+            K k = static_cast<K>(~static_cast<K>(0));
+            if (i < d) {
+                const int it = items[beg + i];
+                if constexpr (HAS_PRIMARY) k = sort_key(primary, it); else k = static_cast<unsigned int>(it);
+            }
+            keys[i] = k;
+        }
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (P >> 1); t += BITONIC_THREADS) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j clear
+                    const int x = i | j;
+                    const bool asc = (i & k) == 0;
+                    const K a = keys[i], b = keys[x];
+                    if ((a > b) == asc) { keys[i] = b; keys[x] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < d; i += BITONIC_THREADS) items[beg + i] = static_cast<int32_t>(keys[i] & 0xffffffffu);
+        __syncthreads();
+    }
 }
 
 // one CTA per listed row: rank sort in shared memory on the unique key (primary[item], item).  Keys are kept as two
@@ -268,13 +356,16 @@ int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int
                     int32_t *worklist, int32_t *work_count, int32_t *err_flag, cudaStream_t st) {
     if (N == 0) return DN4GL_OK;
     DN_CUDA(cudaMemsetAsync(work_count, 0, 2 * sizeof(int32_t), st));
-    sort_rows_light<<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, N, items, primary, worklist,
-                                                                                work_count);
+    if (primary)
+        sort_rows_light<true><<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, N, items, primary, worklist,
+                                                                                          work_count);
+    else
+        sort_rows_light<false><<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, N, items, primary, worklist,
+                                                                                           work_count);
     DN_LAUNCHED();
     const int sms = dn4gl_num_sms();
-    const size_t mid = static_cast<size_t>(HEAVY_SORT_MID) * 2 * sizeof(int32_t);
-    // large instantiation: DN4GL_MAX_ROW_DEGREE keys x 2 int32 arrays = 196608 B of dynamic shared memory; it returns
-    // immediately unless the light pass flagged a row above the mid capacity
+    // rows above HEAVY_SORT_MID items (up to DN4GL_MAX_ROW_DEGREE keys x 2 int32 arrays = 196608 B of dynamic shared
+    // memory) keep the rank sort; that launch returns immediately unless the light pass flagged such a row
     const size_t big = static_cast<size_t>(DN4GL_MAX_ROW_DEGREE) * 2 * sizeof(int32_t);
     static bool attr_set = false;
     if (!attr_set) {
@@ -283,13 +374,11 @@ int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int
         attr_set = true;
     }
     if (primary) {
-        sort_rows_heavy<true><<<sms * 4, 256, mid, st>>>(row_ptr, items, primary, worklist, work_count, LIGHT_SORT_MAX,
-                                                         HEAVY_SORT_MID, 0, err_flag);
+        sort_rows_bitonic<true><<<sms * 2, BITONIC_THREADS, 0, st>>>(row_ptr, items, primary, worklist, work_count);
         sort_rows_heavy<true><<<sms, 256, big, st>>>(row_ptr, items, primary, worklist, work_count, HEAVY_SORT_MID,
                                                      DN4GL_MAX_ROW_DEGREE, 1, err_flag);
     } else {
-        sort_rows_heavy<false><<<sms * 4, 256, mid, st>>>(row_ptr, items, primary, worklist, work_count, LIGHT_SORT_MAX,
-                                                          HEAVY_SORT_MID, 0, err_flag);
+        sort_rows_bitonic<false><<<sms * 4, BITONIC_THREADS, 0, st>>>(row_ptr, items, primary, worklist, work_count);
         sort_rows_heavy<false><<<sms, 256, big, st>>>(row_ptr, items, primary, worklist, work_count, HEAVY_SORT_MID,
                                                       DN4GL_MAX_ROW_DEGREE, 1, err_flag);
     }
@@ -336,6 +425,37 @@ extern "C" int dn4gl_build_csr(const int32_t *key, const int32_t *val, int64_t N
         csr_fill_col<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(eid, val, E, col);
         DN_LAUNCHED();
     }
+    return DN4GL_OK;
+}
+
+// CSR of items whose keys are already non-decreasing (the (src, dst)-sorted edge list that coalesce / PyG hand over):
+// no histogram, scan, scatter or sort -- one pass marks the row boundaries.  Thread e writes row_ptr[r] = e for every
+// row r in (key[e-1], key[e]]; thread E closes the rows after the last key.
+__global__ void csr_from_sorted(const int32_t *__restrict__ key, const int32_t *__restrict__ val, int64_t N, int64_t E,
+                                int32_t *__restrict__ row_ptr, int32_t *__restrict__ col, int32_t *__restrict__ eid,
+                                int32_t *__restrict__ err_flag) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e > E) return;
+    const int64_t k = (e < E) ? key[e] : N;
+    const int64_t kp = (e > 0) ? key[e - 1] : -1;
+    if (e < E) {
+        if (col) col[e] = val ? val[e] : static_cast<int32_t>(e);
+        if (eid) eid[e] = static_cast<int32_t>(e);
+    }
+    if (k < kp || k < 0 || k > N || (e < E && k >= N)) {   // not sorted / out of range: reported, nothing written
+        if (err_flag) atomicExch(err_flag, DN4GL_EINVAL);
+        return;
+    }
+    for (int64_t r = kp + 1; r <= k; ++r) row_ptr[r] = static_cast<int32_t>(e);
+}
+
+extern "C" int dn4gl_build_csr_sorted(const int32_t *key, const int32_t *val, int64_t N, int64_t E, int32_t *row_ptr,
+                                      int32_t *col, int32_t *eid, int32_t *err_flag, void *stream) {
+    DN_ARG(N >= 0 && E >= 0 && N < INT32_MAX && E < INT32_MAX);
+    DN_ARG(row_ptr != nullptr && (E == 0 || key != nullptr));
+    csr_from_sorted<<<static_cast<unsigned>(ceil_div64(E + 1, 256)), 256, 0, as_stream(stream)>>>(key, val, N, E, row_ptr, col,
+                                                                                                 eid, err_flag);
+    DN_LAUNCHED();
     return DN4GL_OK;
 }
 

@@ -356,27 +356,34 @@ extern "C" int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const
 // repeated (src,dst) pairs are flagged out, survivors are compacted in (src, dst) order.
 // one thread per CSR position p (rows are already sorted by (dst, edge id)): keep[p] = not a self loop and not a
 // repeat of the previous destination in the same row
+// (the row of position p is src[items[p]]: no search over row_ptr)
 __global__ void coalesce_flags(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ items,
-                               const int32_t *__restrict__ dst, int64_t N, int64_t E, int32_t *__restrict__ keep) {
+                               const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int64_t N, int64_t E,
+                               int32_t *__restrict__ keep) {
     int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (p >= E) return;
-    int r = segment_of(row_ptr, static_cast<int>(N), p);
-    int d = dst[items[p]];
-    int prev = (p > row_ptr[r]) ? dst[items[p - 1]] : -1;
+    const int it = items[p];
+    const int r = src[it], d = dst[it];
+    int prev = -1;
+    if (p > 0) {
+        const int itp = items[p - 1];
+        if (src[itp] == r) prev = dst[itp];
+    }
     keep[p] = (d != r && d != prev) ? 1 : 0;
 }
 
 __global__ void coalesce_compact(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ items,
-                                 const int32_t *__restrict__ dst, int64_t N, int64_t E,
+                                 const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int64_t N, int64_t E,
                                  const int32_t *__restrict__ keep_scan, int32_t *__restrict__ o_src,
                                  int32_t *__restrict__ o_dst, int32_t *__restrict__ o_first) {
     int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (p >= E) return;
     int q = keep_scan[p];
     if (keep_scan[p + 1] != q) {
-        o_src[q] = segment_of(row_ptr, static_cast<int>(N), p);
-        o_dst[q] = dst[items[p]];
-        o_first[q] = items[p];
+        const int it = items[p];
+        o_src[q] = src[it];
+        o_dst[q] = dst[it];
+        o_first[q] = it;
     }
 }
 
@@ -385,7 +392,7 @@ extern "C" size_t dn4gl_coalesce_workspace_bytes(int64_t N, int64_t E) {
            dn4gl_scan_workspace_bytes(E + 1);
 }
 
-extern "C" int dn4gl_coalesce(const int32_t *dst, int64_t N, int64_t E, const int32_t *row_ptr, int32_t *items,
+extern "C" int dn4gl_coalesce(const int32_t *src, const int32_t *dst, int64_t N, int64_t E, const int32_t *row_ptr, int32_t *items,
                               int32_t *keep_scan, int32_t *o_src, int32_t *o_dst, int32_t *o_first, void *ws,
                               size_t ws_bytes, int32_t *err_flag, void *stream) {
     DN_ARG(N >= 0 && E >= 0 && row_ptr && keep_scan);
@@ -394,7 +401,7 @@ extern "C" int dn4gl_coalesce(const int32_t *dst, int64_t N, int64_t E, const in
         DN_CUDA(cudaMemsetAsync(keep_scan, 0, sizeof(int32_t), st));
         return DN4GL_OK;
     }
-    DN_ARG(dst && items && o_src && o_dst && o_first);
+    DN_ARG(src && dst && items && o_src && o_dst && o_first);
     WsCarver w(ws, ws_bytes);
     int32_t *worklist = w.take<int32_t>(N);
     int32_t *work_count = w.take<int32_t>(1);
@@ -406,11 +413,11 @@ extern "C" int dn4gl_coalesce(const int32_t *dst, int64_t N, int64_t E, const in
     }
     int rc = dn4gl_sort_rows(row_ptr, N, items, dst, worklist, work_count, err_flag, st);
     if (rc != DN4GL_OK) return rc;
-    coalesce_flags<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(row_ptr, items, dst, N, E, keep_scan);
+    coalesce_flags<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(row_ptr, items, src, dst, N, E, keep_scan);
     DN_LAUNCHED();
     rc = dn4gl_exclusive_scan_i32(keep_scan, keep_scan, E, scan_ws, scan_bytes, stream);
     if (rc != DN4GL_OK) return rc;
-    coalesce_compact<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(row_ptr, items, dst, N, E, keep_scan,
+    coalesce_compact<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(row_ptr, items, src, dst, N, E, keep_scan,
                                                                                  o_src, o_dst, o_first);
     DN_LAUNCHED();
     return DN4GL_OK;

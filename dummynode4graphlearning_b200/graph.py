@@ -95,7 +95,7 @@ class CSR:
         if not aligned and scratch <= ((smem_bytes // stages) & ~127):
             heavy_cap = self.nnz // 64 + 1
             heavy_list = torch.empty(heavy_cap, dtype=torch.int32, device=dev)
-            heavy_count = torch.zeros(1, dtype=torch.int32, device=dev)
+            heavy_count = torch.empty(1, dtype=torch.int32, device=dev)   # zeroed by dn4gl_make_row_tiles
         L.call("dn4gl_make_row_tiles", ptr(self.seg_ptr), int(self.seg_ptr.numel()) - 1, window, ptr(self.row_ptr),
                ptr(self.col), self.n_rows, ptr(desc), T, ptr(heavy_list), heavy_cap, ptr(heavy_count), _stream())
         cfg = dict(desc=desc, T=T, heavy_list=heavy_list, heavy_count=heavy_count, heavy_cap=heavy_cap,
@@ -104,8 +104,10 @@ class CSR:
         return cfg
 
 
-def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD):
-    """Stable CSR of the items 0..E-1 grouped by key (see dn4gl_build_csr)."""
+def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD, sorted_keys=False):
+    """Stable CSR of the items 0..E-1 grouped by key (see dn4gl_build_csr).  sorted_keys: the caller guarantees
+    non-decreasing keys (a coalesced edge list keyed by its row): one boundary-marking pass (dn4gl_build_csr_sorted);
+    a violation is reported through check_errors()."""
     require_cuda(key, "CSR key")
     L = lib()
     E = int(key.numel())
@@ -113,37 +115,46 @@ def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD):
     row_ptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
     col = torch.empty(E, dtype=torch.int32, device=dev)
     eid = torch.empty(E, dtype=torch.int32, device=dev)
-    ws_bytes = L.size("dn4gl_csr_workspace_bytes", n_rows, E)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    err = torch.zeros(1, dtype=torch.int32, device=dev)
-    L.call("dn4gl_build_csr", ptr(key), ptr(val), n_rows, E, ptr(row_ptr), ptr(col), ptr(eid),
-           ptr(ws), ws_bytes, ptr(err), _stream())
+    if sorted_keys:
+        L.call("dn4gl_build_csr_sorted", ptr(key), ptr(val), n_rows, E, ptr(row_ptr), ptr(col), ptr(eid),
+               ptr(error_flag(dev)), _stream())
+    else:
+        ws_bytes = L.size("dn4gl_csr_workspace_bytes", n_rows, E)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        L.call("dn4gl_build_csr", ptr(key), ptr(val), n_rows, E, ptr(row_ptr), ptr(col), ptr(eid),
+               ptr(ws), ws_bytes, ptr(error_flag(dev)), _stream())   # flag checked lazily by check_errors()
     csr = CSR(row_ptr, col, eid, n_rows, E)
-    csr_err = err  # checked lazily by check_errors()
     if heavy_threshold and heavy_threshold > 0 and E > 0:
         cap = E // heavy_threshold + 1
         csr.heavy_rows = torch.empty(cap, dtype=torch.int32, device=dev)
-        csr.heavy_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        csr.heavy_count = torch.empty(1, dtype=torch.int32, device=dev)   # zeroed by dn4gl_collect_heavy_rows
         csr.heavy_thr = heavy_threshold
         L.call("dn4gl_collect_heavy_rows", ptr(row_ptr), n_rows, heavy_threshold, ptr(csr.heavy_rows), cap,
                ptr(csr.heavy_count), _stream())
-    _pending_err.append(csr_err)
     return csr
 
 
-import collections
+_err_flags = {}   # device index -> persistent int32[1]; builder kernels only ever write a non-zero error code into it
 
-_pending_err = collections.deque(maxlen=512)   # bounded: a long run that never checks must not pin flags forever
+
+def error_flag(device):
+    """The device's sticky asynchronous error flag (one allocation per device instead of a zero-fill launch per
+    builder call; kernels raise it with atomicExch, check_errors() reads and clears it)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    f = _err_flags.get(idx)
+    if f is None:
+        f = _err_flags[idx] = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", idx))
+    return f
 
 
 def check_errors():
-    """Synchronising check of the asynchronous capacity flags raised by builder kernels (the most recent 512)."""
-    flags = list(_pending_err)
-    _pending_err.clear()
-    for f in flags:
+    """Synchronising check of the asynchronous capacity flags raised by builder kernels since the last check."""
+    for idx, f in list(_err_flags.items()):
         code = int(f.item())
         if code != 0:
-            raise RuntimeError("dn4gl builder kernel reported error %d (row degree above DN4GL_MAX_ROW_DEGREE)" % code)
+            f.zero_()
+            raise RuntimeError("dn4gl builder kernel reported error %d on cuda:%d (-3: row degree above "
+                               "DN4GL_MAX_ROW_DEGREE; -1: keys passed as sorted were not)" % (code, idx))
 
 
 def _i32(t, device):

@@ -308,12 +308,24 @@ def lin_supported(K, M):
     return bool(lib().raw("dn4gl_lin_supported")(int(K), int(M)))
 
 
+_tc_counter = {}   # device index -> persistent zeroed int32 counter shared by every captured launch on that device
+
+
 def _tc_ws(device, nbytes):
     """(workspace, zeroed int32 counter) per (device, stream): the kernels consume the workspace before the next
-    launch on the same stream starts, and leave the counter at zero."""
+    launch on the same stream starts, and leave the counter at zero.
+
+    Under CUDA-graph capture the workspace comes from the graph's pool, and the counter is ONE persistent per-device
+    tensor allocated outside any capture (captured launches of a device are serialised on the replaying stream, and
+    each kernel leaves the counter at zero) -- not a fresh torch.zeros per call, which put ~25 fill kernels into every
+    replayed train step."""
     if torch.cuda.is_current_stream_capturing():   # a CUDA graph owns its scratch (allocated from the graph's pool)
-        return (torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device),
-                torch.zeros(1, dtype=torch.int32, device=device))
+        cnt = _tc_counter.get(device.index)
+        if cnt is None:                            # no eager call came first: allocate inside the capture (one fill node)
+            cnt = torch.zeros(1, dtype=torch.int32, device=device)
+        return torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device), cnt
+    if device.index not in _tc_counter:
+        _tc_counter[device.index] = torch.zeros(1, dtype=torch.int32, device=device)
     key = (device.index, _stream())
     ent = _tc_scratch.get(key)
     if ent is None or ent[0].numel() < nbytes:

@@ -47,26 +47,47 @@ class GradientBucket:
             self.active = [p for p in self.params if p.grad is not None]
             if not self.active:
                 return
-            self.numel = sum(p.numel() for p in self.active)
+            self.numel = sum(((p.numel() + 3) // 4) * 4 for p in self.active)
             self.flat = torch.zeros(self.numel, dtype=torch.float32, device=self.active[0].device)
             off = 0
-            for p in self.active:  # gradients become views into the flat bucket: no pack/unpack copies afterwards
+            self.views = []
+            for p in self.active:  # gradients become views into the flat bucket
                 n = p.numel()
                 view = self.flat[off: off + n].view_as(p)
                 view.copy_(p.grad)
                 p.grad = view
-                off += n
+                self.views.append(view)
+                off += ((n + 3) // 4) * 4   # every view 16-byte aligned (vectorised optimizer / copies)
 
     def zero(self):
+        """start of a step.  Gradients are detached from the flat buffer (``p.grad = None``) so that autograd's
+        AccumulateGrad nodes adopt the incoming gradient tensors instead of launching one ``grad += new`` kernel per
+        parameter; ``gather()`` copies them into the flat buffer with one multi-tensor copy afterwards."""
+        for p in self.params:
+            p.grad = None
+
+    def gather(self):
+        """after backward: every active parameter's gradient ends up in (and ``p.grad`` points into) the flat buffer."""
+        self._ensure()
         if self.flat is None:
-            for p in self.params:
-                p.grad = None
-        else:
-            self.flat.zero_()
+            return
+        src, dst = [], []
+        for p, view in zip(self.active, self.views):
+            g = p.grad
+            if g is view:
+                continue
+            if g is None:
+                view.zero_()                      # did not take part in this step's loss
+            else:
+                src.append(g if g.dtype == view.dtype else g.to(view.dtype))
+                dst.append(view)
+            p.grad = view
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def all_reduce(self, local_weight=None):
         """sum over ranks of local_weight * grad (local_weight = B_r / B for mean-reduced losses)."""
-        self._ensure()
+        self.gather()
         if self.flat is None:
             return
         if local_weight is not None and local_weight != 1.0:

@@ -130,7 +130,7 @@ class ClassificationPipeline:
         self.model, self.opt, self.mode = model, optimizer, mode
         self.nvl, self.nel = num_node_labels, num_edge_labels
         self.node_label_min, self.with_edge_attr = node_label_min, with_edge_attr
-        self.bucket = GradientBucket(model.parameters())
+        self.bucket = getattr(optimizer, "bucket", None) or GradientBucket(model.parameters())
         self.device = next(model.parameters()).device
         self.global_batch = None
         capturable = all(g.get("capturable", False) for g in optimizer.param_groups)
@@ -165,7 +165,7 @@ class ClassificationPipeline:
         out = self.model(data)
         loss = F.nll_loss(out, data.y)                      # main.py:41
         loss.backward()
-        self.bucket._ensure()                               # gradients live in one flat buffer from the first step on
+        self.bucket.gather()                                # gradients live in one flat buffer (one multi-tensor copy)
         if is_distributed():
             gb = self.global_batch or data.num_graphs * torch.distributed.get_world_size()
             self.bucket.all_reduce(data.num_graphs / gb)
@@ -273,7 +273,7 @@ class CountingPipeline:
         ClassificationPipeline (default: on exactly when the optimizer was built with capturable=True)."""
         self.model, self.opt, self.cfg, self.add_dummy = model, optimizer, config, add_dummy
         self.rep_reg_w, self.neg_slp, self.max_grad_norm = rep_reg_w, neg_slp, max_grad_norm
-        self.bucket = GradientBucket(model.parameters())
+        self.bucket = getattr(optimizer, "bucket", None) or GradientBucket(model.parameters())
         self.device = next(model.parameters()).device
         self.global_batch = None
         capturable = all(g.get("capturable", False) for g in optimizer.param_groups)
@@ -307,12 +307,14 @@ class CountingPipeline:
         out = self.model(pattern, graph)
         loss = self.loss_fn(out, counts)
         loss.backward()
-        self.bucket._ensure()
+        self.bucket.gather()
         if is_distributed():
             gb = self.global_batch or pattern.batch_size * torch.distributed.get_world_size()
             self.bucket.all_reduce(pattern.batch_size / gb)
         if self.max_grad_norm and self.max_grad_norm > 0:   # clip AFTER the reduction (train.py:833-834)
-            torch.nn.utils.clip_grad_norm_(self.bucket.active, self.max_grad_norm)
+            flat = self.bucket.flat      # clip_grad_norm_ on the flat buffer: norm, coefficient, scale = 4 launches
+            coef = (self.max_grad_norm / (torch.linalg.vector_norm(flat) + 1e-6)).clamp(max=1.0)
+            flat.mul_(coef)
         self.opt.step()
         return loss.detach()   # see ClassificationPipeline._train_body
 

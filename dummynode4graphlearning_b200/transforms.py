@@ -23,7 +23,7 @@ from copy import deepcopy
 import torch
 
 from ._lib import lib, ptr
-from .graph import _pending_err, _stream, build_csr, require_cuda
+from .graph import _stream, build_csr, error_flag, require_cuda
 
 
 class LazyDict(dict):
@@ -267,10 +267,8 @@ def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_m
     o_src, o_dst, o_first = _empty_i32(E, dev), _empty_i32(E, dev), _empty_i32(E, dev)
     ws_bytes = L.size("dn4gl_coalesce_workspace_bytes", N, E)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    err = torch.zeros(1, dtype=torch.int32, device=dev)
-    L.call("dn4gl_coalesce", ptr(b["dst"]), N, E, ptr(csr_out.row_ptr), ptr(csr_out.eid), ptr(keep_scan),
-           ptr(o_src), ptr(o_dst), ptr(o_first), ptr(ws), ws_bytes, ptr(err), _stream())
-    _pending_err.append(err)
+    L.call("dn4gl_coalesce", ptr(b["src"]), ptr(b["dst"]), N, E, ptr(csr_out.row_ptr), ptr(csr_out.eid), ptr(keep_scan),
+           ptr(o_src), ptr(o_dst), ptr(o_first), ptr(ws), ws_bytes, ptr(error_flag(dev)), _stream())
     E2 = int(keep_scan[-1].item())
     o_src, o_dst, o_first = o_src[:E2], o_dst[:E2], o_first[:E2]
     # node features: [attr?, one_hot(label - min)]
@@ -285,7 +283,8 @@ def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_m
     if "vattr" in b:
         x = torch.cat([b["vattr"].view(N, -1), x], dim=1)
         n_attr = x.size(1) - nvl
-    out = LazyDict(num_graphs=B, x=x, node_ptr=b["node_ptr"], src=o_src, dst=o_dst, first_edge=o_first)
+    out = LazyDict(num_graphs=B, x=x, node_ptr=b["node_ptr"], src=o_src, dst=o_dst, first_edge=o_first,
+                   sorted_by_src=True)   # survivors are compacted in (src, dst) order: the by-src CSR needs no sort
     out.lazy("edge_index", lambda: torch.stack([o_src.long(), o_dst.long()]))
     out.lazy("batch", lambda: torch.repeat_interleave(torch.arange(B, device=dev),
                                                       (b["node_ptr"][1:] - b["node_ptr"][:-1]).long(), output_size=N))

@@ -62,6 +62,12 @@ size_t dn4gl_csr_workspace_bytes(int64_t N, int64_t E);
 int dn4gl_build_csr(const int32_t *key, const int32_t *val, int64_t N, int64_t E,
                     int32_t *row_ptr, int32_t *col, int32_t *eid,
                     void *ws, size_t ws_bytes, int32_t *err_flag, void *stream);
+/* Same result as dn4gl_build_csr for keys that are already NON-DECREASING (the (row, col)-sorted edge_index that PyG's
+ * coalesce -- and dn4gl_coalesce -- produce: graph_neural_networks/dataset.py:151): one boundary-marking pass, no
+ * workspace.  A key out of order or outside [0, N) raises DN4GL_EINVAL asynchronously through err_flag (may be NULL). */
+int dn4gl_build_csr_sorted(const int32_t *key, const int32_t *val, int64_t N, int64_t E, int32_t *row_ptr,
+                           int32_t *col, int32_t *eid, int32_t *err_flag, void *stream);
+
 
 /* list of rows with degree > threshold (for the heavy-row path of the aggregation kernels):
  * heavy_rows[cap], heavy_count[1]; cap >= E / threshold + 1; list order is unspecified.         */
@@ -156,14 +162,14 @@ int dn4gl_sub_conj_fill(int32_t B, const int32_t *src, int64_t E, int32_t id_bou
 
 /* ---- a3: PyG read_tu_data canonicalisation ------------------------------------------------- */
 /* remove_self_loops + coalesce [torch-geometric 2.0.2 read_tu_data, called from
- * graph_classification/graph_neural_networks/dataset.py:151]: given the edge list's destinations
- * dst[E] (edge-id order) and its by-src CSR (row_ptr[N+1], items[E] = edge ids, from
+ * graph_classification/graph_neural_networks/dataset.py:151]: given the edge list's endpoints
+ * src[E], dst[E] (edge-id order) and its by-src CSR (row_ptr[N+1], items[E] = edge ids, from
  * dn4gl_build_csr(key=src)), sorts every row in place by (dst, edge id), drops self loops, merges
  * repeated (src,dst) pairs.  keep_scan[E+1] = exclusive scan of survivor flags in sorted order;
  * survivors are written compacted in (src,dst) order: o_src/o_dst/o_first[<=E] (o_first = first
  * original edge of each merged group).  E' = keep_scan[E].                                    */
 size_t dn4gl_coalesce_workspace_bytes(int64_t N, int64_t E);
-int dn4gl_coalesce(const int32_t *dst, int64_t N, int64_t E, const int32_t *row_ptr, int32_t *items,
+int dn4gl_coalesce(const int32_t *src, const int32_t *dst, int64_t N, int64_t E, const int32_t *row_ptr, int32_t *items,
                    int32_t *keep_scan, int32_t *o_src, int32_t *o_dst, int32_t *o_first,
                    void *ws, size_t ws_bytes, int32_t *err_flag, void *stream);
 
@@ -333,6 +339,18 @@ int dn4gl_bn_act_pool_f32(const float *Y, int64_t N, int32_t M, const float *bn,
                           const int32_t *seg_ptr, int32_t B, int32_t mode, float *pooled, void *stream);
 /* out[i] = index of the contiguous segment holding row i (PyG's `batch` vector as int32)                             */
 int dn4gl_segment_ids_i32(const int32_t *seg_ptr, int32_t B, int64_t N, int32_t *out, void *stream);
+
+/* ---- optimizer step ---------------------------------------------------------------------------------------- */
+/* One Adam / AdamW (optionally amsgrad) update over FLAT fp32 buffers of n elements -- replaces the per-tensor kernels
+ * of torch.optim.Adam.step() (graph_neural_networks/main.py:43) and torch.optim.AdamW(amsgrad=True).step()
+ * (subgraph_isomorphism/train.py:831-838), same update rule and operation order as torch's single-tensor path:
+ *   [decoupled: p *= 1 - lr*wd | else g += wd*p];  m += (g - m)(1 - b1);  v = v*b2 + (1 - b2) g*g;
+ *   [amsgrad: vmax = max(vmax, v)];  p -= lr / (1 - b1^t) * m / (sqrt(v | vmax) / sqrt(1 - b2^t) + eps),  t = step + 1.
+ * hyper: 5 device floats {lr, beta1, beta2, eps, weight_decay}; step: 1 device float holding the number of updates done
+ * so far, advanced by the kernel (so a captured CUDA graph replays with the right bias correction and the current lr);
+ * max_exp_avg_sq NULL = no amsgrad; counter: one int32 that is 0 on entry (left 0).  All buffers 16-byte aligned.     */
+int dn4gl_adam_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq,
+                   int64_t n, const float *hyper, float *step, int32_t decoupled, int32_t *counter, void *stream);
 
 /* out[0] = sum_i a[i] * b[i] over n floats, fixed-order (the gradient of GINConv's trainable eps: sum(g_z * x)).
  * ws: dn4gl_dot_workspace_bytes; counter: one int32 that is 0 on entry (left 0).                                  */

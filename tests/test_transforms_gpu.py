@@ -211,6 +211,34 @@ def test_build_csr_stable(device, n, e):
     check_errors()
 
 
+@pytest.mark.parametrize("n,e", [(1, 0), (7, 0), (9, 3), (1000, 5000), (50000, 400000)])
+def test_build_csr_sorted_keys(device, n, e):
+    """dn4gl_build_csr_sorted (boundary marking) == the general stable build on non-decreasing keys; an unsorted key
+    raises the asynchronous error flag."""
+    from dummynode4graphlearning_b200.graph import build_csr, check_errors
+    from oracle import transforms as O
+
+    rng = np.random.default_rng(n * 3 + e)
+    dst = np.sort(rng.integers(0, n, e)).astype(np.int32)
+    if e > 100:
+        dst[dst < n // 3] = 0          # a heavy first row and a long run of empty rows behind it
+        dst[-50:] = n - 1
+    src = rng.integers(0, n, e).astype(np.int32)
+    csr = build_csr(torch.from_numpy(dst).to(device), torch.from_numpy(src).to(device), n, sorted_keys=True)
+    rp, col, eid = O.csr_by_dst(n, src, dst)
+    assert np.array_equal(csr.row_ptr.cpu().numpy(), rp)
+    assert np.array_equal(csr.eid.cpu().numpy(), eid)
+    assert np.array_equal(csr.col.cpu().numpy(), col)
+    check_errors()
+    if e > 100:
+        bad = dst.copy()
+        bad[e // 2] = n - 1            # out of order
+        build_csr(torch.from_numpy(bad).to(device), torch.from_numpy(src).to(device), n, sorted_keys=True)
+        with pytest.raises(RuntimeError):
+            check_errors()
+        check_errors()                 # the flag was cleared
+
+
 @pytest.mark.parametrize("n", [0, 1, 4095, 4096, 4097, 1 << 20, (1 << 22) + 3])
 def test_exclusive_scan(device, n):
     from dummynode4graphlearning_b200._lib import lib, ptr
