@@ -123,7 +123,7 @@ def reference_arm(a):
 def workload_config(graphs, n_gpus):
     return {"workload": "c2: dummy + edge-to-vertex (CONJ) transform + GIN(hidden 32, 4 layers, train_eps, sum pool) "
                         "train step on synthetic PROTEINS-shaped graphs", "graphs_per_gpu": graphs,
-            "global_batch": graphs * n_gpus, "avg_nodes": 39, "optimizer": "Adam(lr=0.01) as one flat-buffer kernel (dn4gl_adam_f32)", "train_step": "CUDA graph replay per batch signature (transform eager)",
+            "global_batch": graphs * n_gpus, "avg_nodes": 39, "optimizer": "Adam(lr=0.01) as one flat-buffer kernel (dn4gl_adam_f32)", "train_step": "CUDA graph replay per batch signature; transform eager on a second stream, overlapping the previous train step",
             "parallelism": "dp%d" % n_gpus, "l2": "flushed between steps (256 MiB write inside the timed region)"}
 
 
@@ -276,7 +276,7 @@ def ours(a):
     n_warm = max(a.warmup, 10)   # first step eager, second captures the CUDA graph, the rest settle the caching allocator
     for _ in range(n_warm):
         flush.fill_(1)
-        pipe.step_resident(dev_batch)
+        pipe.step_resident(dev_batch, assume_ready=True)   # the raw batch has been resident since before the warm-up
     # ---- timed region: EXACTLY K steps, device-timed ----------------------------------------------------
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
@@ -285,7 +285,7 @@ def ours(a):
     e0.record()
     for _ in range(a.steps):
         flush.fill_(1)
-        loss = pipe.step_resident(dev_batch)
+        loss = pipe.step_resident(dev_batch, assume_ready=True)
     e1.record()
     barrier()
     launches = L.kernel_launches() + pipe.replayed_library_kernels() - k0
@@ -297,9 +297,14 @@ def ours(a):
         pipe.step(host)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        flush.fill_(1)
-        last = pipe.step(host)
+    pending = None
+    for _ in range(a.steps):          # software-pipelined: submit step k (H2D, transform, train, D2H of its loss),
+        flush.fill_(1)                # then read the loss of step k-1 on the host -- every loss is read, in order
+        nxt = pipe.step_async(host)
+        if pending is not None:
+            last = pending.result()
+        pending = nxt
+    last = pending.result()
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / a.steps
     e2e_value = a.graphs * world / (e2e_ms * 1e-3)
@@ -308,6 +313,7 @@ def ours(a):
     # ---- per-entry-point device times + breakdown (instrumented pass, not part of `value`) -----------------
     timer = EntryPointTimer()
     pipe.cuda_graphs = False      # the instrumented pass brackets every C-ABI call with events: eager launches
+    pipe.overlap = False          # ... on one stream
     L.profiler = timer
     tr0, tr1, tn1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     tr_ms, tn_ms = [], []
@@ -369,7 +375,9 @@ def ours(a):
         "dtype": "f32", "data": "synthetic", "config": workload_config(a.graphs, world),
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": host_bytes(host), "d2h_bytes_per_step": 4 + 8 + 4},
+                "h2d_bytes_per_step": host_bytes(host), "d2h_bytes_per_step": 4 + 8 + 4,
+                "how": "ClassificationPipeline.step_async(host) per step, loss of step k-1 read on the host after step k "
+                       "is submitted (all losses read, last one before the clock stops)"},
         "roofline": roofline, "cpu_baseline": cpu,
         "breakdown": {"transform_ms": statistics.mean(tr_ms), "train_ms": statistics.mean(tn_ms),
                       "own_kernels_ms_per_step": own_ms, "conj_nodes": N, "conj_edges": E,

@@ -103,6 +103,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_of_sums(int32_t *__restrict
     }
 }
 
+// RAW_SUMS: tile_offsets holds the UNSCANNED tile sums and every CTA adds up the ones before it itself (at most
+// SCAN_RAW_MAX_TILES of them: a few loads per thread) -- saves the single-CTA scan_of_sums launch in between.
+constexpr int SCAN_RAW_MAX_TILES = 8192;
+template <bool RAW_SUMS>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep(const int32_t *in, int32_t *out, int64_t n,
                                                                const int32_t *__restrict__ tile_offsets) {
     __shared__ int sm[33];
@@ -114,8 +118,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep(const int32_t *in
         v[k] = (base + k < n) ? in[base + k] : 0;
         s += v[k];
     }
+    int tile_off = 0;
+    if (tile_offsets) {
+        if constexpr (RAW_SUMS) {
+            int part = 0;
+            for (int t = threadIdx.x; t < static_cast<int>(blockIdx.x); t += SCAN_THREADS) part += tile_offsets[t];
+            block_exclusive_scan(part, &tile_off, sm);
+        } else {
+            tile_off = tile_offsets[blockIdx.x];
+        }
+    }
     int total;
-    int ex = block_exclusive_scan(s, &total, sm) + (tile_offsets ? tile_offsets[blockIdx.x] : 0);
+    int ex = block_exclusive_scan(s, &total, sm) + tile_off;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
         if (base + k < n) out[base + k] = ex;
@@ -136,7 +150,7 @@ extern "C" int dn4gl_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t
     cudaStream_t st = as_stream(stream);
     int64_t tiles = ceil_div64(n > 0 ? n : 1, SCAN_TILE);
     if (tiles == 1) {
-        scan_downsweep<<<1, SCAN_THREADS, 0, st>>>(in, out, n, nullptr);
+        scan_downsweep<false><<<1, SCAN_THREADS, 0, st>>>(in, out, n, nullptr);
         DN_LAUNCHED();
         return DN4GL_OK;
     }
@@ -147,9 +161,14 @@ extern "C" int dn4gl_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t
     int32_t *sums = static_cast<int32_t *>(ws);
     scan_tile_sums<<<static_cast<unsigned>(tiles), SCAN_THREADS, 0, st>>>(in, n, sums);
     DN_LAUNCHED();
+    if (tiles <= SCAN_RAW_MAX_TILES) {
+        scan_downsweep<true><<<static_cast<unsigned>(tiles), SCAN_THREADS, 0, st>>>(in, out, n, sums);
+        DN_LAUNCHED();
+        return DN4GL_OK;
+    }
     scan_of_sums<<<1, SCAN_THREADS, 0, st>>>(sums, tiles);
     DN_LAUNCHED();
-    scan_downsweep<<<static_cast<unsigned>(tiles), SCAN_THREADS, 0, st>>>(in, out, n, sums);
+    scan_downsweep<false><<<static_cast<unsigned>(tiles), SCAN_THREADS, 0, st>>>(in, out, n, sums);
     DN_LAUNCHED();
     return DN4GL_OK;
 }
@@ -205,11 +224,16 @@ __device__ __forceinline__ void sort8(K (&a)[8]) {
 template <bool HAS_PRIMARY>
 __global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, int32_t *__restrict__ items,
                                 const int32_t *__restrict__ primary, int32_t *__restrict__ worklist,
-                                int32_t *__restrict__ work_count) {
+                                int32_t *__restrict__ work_count, const int32_t *__restrict__ val,
+                                int32_t *__restrict__ col) {
+    // col (optional): col[p] = val[items[p]] (or items[p]) of the SORTED row, written by whichever kernel sorts the row
     int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (r >= N) return;
     int beg = row_ptr[r], d = row_ptr[r + 1] - beg;
-    if (d <= 1) return;
+    if (d <= 1) {
+        if (d == 1 && col) { const int it = items[beg]; col[beg] = val ? val[it] : it; }
+        return;
+    }
     if (d > LIGHT_SORT_MAX) {
         worklist[atomicAdd(work_count, 1)] = static_cast<int32_t>(r);
         if (d > HEAVY_SORT_MID) atomicAdd(work_count + 1, 1);
@@ -223,7 +247,11 @@ __global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, 
             sort8(a);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                if (i < d) items[beg + i] = static_cast<int32_t>(a[i] & 0xffffffffu);
+                if (i < d) {
+                    const int it = static_cast<int32_t>(a[i] & 0xffffffffu);
+                    items[beg + i] = it;
+                    if (col) col[beg + i] = val ? val[it] : it;
+                }
         } else {
             int a[8];
 #pragma unroll
@@ -231,7 +259,10 @@ __global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, 
             sort8(a);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                if (i < d) items[beg + i] = a[i];
+                if (i < d) {
+                    items[beg + i] = a[i];
+                    if (col) col[beg + i] = val ? val[a[i]] : a[i];
+                }
         }
         return;
     }
@@ -243,7 +274,11 @@ __global__ void sort_rows_light(const int32_t *__restrict__ row_ptr, int64_t N, 
         while (j >= 0 && a[j] > k) { a[j + 1] = a[j]; --j; }
         a[j + 1] = k;
     }
-    for (int i = 0; i < d; ++i) items[beg + i] = static_cast<int32_t>(a[i] & 0xffffffffu);
+    for (int i = 0; i < d; ++i) {
+        const int it = static_cast<int32_t>(a[i] & 0xffffffffu);
+        items[beg + i] = it;
+        if (col) col[beg + i] = val ? val[it] : it;
+    }
 }
 
 // one CTA per listed row with LIGHT_SORT_MAX < d <= HEAVY_SORT_MID items (the dummy rows: one per graph, as long as
@@ -256,7 +291,9 @@ __global__ void __launch_bounds__(BITONIC_THREADS) sort_rows_bitonic(const int32
                                                                      int32_t *__restrict__ items,
                                                                      const int32_t *__restrict__ primary,
                                                                      const int32_t *__restrict__ worklist,
-                                                                     const int32_t *__restrict__ work_count) {
+                                                                     const int32_t *__restrict__ work_count,
+                                                                     const int32_t *__restrict__ val,
+                                                                     int32_t *__restrict__ col) {
     using K = typename std::conditional<HAS_PRIMARY, unsigned long long, unsigned int>::type;
     __shared__ K keys[HEAVY_SORT_MID];
     const int n_work = work_count[0];
@@ -287,7 +324,11 @@ __global__ void __launch_bounds__(BITONIC_THREADS) sort_rows_bitonic(const int32
                 __syncthreads();
             }
         }
-        for (int i = threadIdx.x; i < d; i += BITONIC_THREADS) items[beg + i] = static_cast<int32_t>(keys[i] & 0xffffffffu);
+        for (int i = threadIdx.x; i < d; i += BITONIC_THREADS) {
+            const int it = static_cast<int32_t>(keys[i] & 0xffffffffu);
+            items[beg + i] = it;
+            if (col) col[beg + i] = val ? val[it] : it;
+        }
         __syncthreads();
     }
 }
@@ -301,7 +342,8 @@ __global__ void __launch_bounds__(256) sort_rows_heavy(const int32_t *__restrict
                                                        const int32_t *__restrict__ primary,
                                                        const int32_t *__restrict__ worklist,
                                                        const int32_t *__restrict__ work_count, int lo, int cap,
-                                                       int only_if_flagged, int32_t *err_flag) {
+                                                       int only_if_flagged, int32_t *err_flag,
+                                                       const int32_t *__restrict__ val, int32_t *__restrict__ col) {
     extern __shared__ __align__(16) int32_t skeys[];
     int32_t *ki = skeys, *kp = skeys + cap;
     if (only_if_flagged && work_count[1] == 0) return;   // no row exceeded the mid capacity: nothing to do
@@ -340,28 +382,24 @@ __global__ void __launch_bounds__(256) sort_rows_heavy(const int32_t *__restrict
                 }
             }
             items[beg + rank] = k;
+            if (col) col[beg + rank] = val ? val[k] : k;
         }
         __syncthreads();
     }
 }
 
-__global__ void csr_fill_col(const int32_t *__restrict__ eid, const int32_t *__restrict__ val, int64_t E,
-                             int32_t *__restrict__ col) {
-    int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p < E) col[p] = val ? val[eid[p]] : eid[p];
-}
-
 // sorts the items of every row by (primary[item], item); shared by the CSR build and coalesce
 int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int32_t *primary,
-                    int32_t *worklist, int32_t *work_count, int32_t *err_flag, cudaStream_t st) {
+                    int32_t *worklist, int32_t *work_count, int32_t *err_flag, cudaStream_t st, const int32_t *val,
+                    int32_t *col, bool work_count_zeroed) {
     if (N == 0) return DN4GL_OK;
-    DN_CUDA(cudaMemsetAsync(work_count, 0, 2 * sizeof(int32_t), st));
+    if (!work_count_zeroed) DN_CUDA(cudaMemsetAsync(work_count, 0, 2 * sizeof(int32_t), st));
     if (primary)
         sort_rows_light<true><<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, N, items, primary, worklist,
-                                                                                          work_count);
+                                                                                          work_count, val, col);
     else
         sort_rows_light<false><<<static_cast<unsigned>(ceil_div64(N, 128)), 128, 0, st>>>(row_ptr, N, items, primary, worklist,
-                                                                                           work_count);
+                                                                                           work_count, val, col);
     DN_LAUNCHED();
     const int sms = dn4gl_num_sms();
     // rows above HEAVY_SORT_MID items (up to DN4GL_MAX_ROW_DEGREE keys x 2 int32 arrays = 196608 B of dynamic shared
@@ -374,13 +412,13 @@ int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int
         attr_set = true;
     }
     if (primary) {
-        sort_rows_bitonic<true><<<sms * 2, BITONIC_THREADS, 0, st>>>(row_ptr, items, primary, worklist, work_count);
+        sort_rows_bitonic<true><<<sms * 2, BITONIC_THREADS, 0, st>>>(row_ptr, items, primary, worklist, work_count, val, col);
         sort_rows_heavy<true><<<sms, 256, big, st>>>(row_ptr, items, primary, worklist, work_count, HEAVY_SORT_MID,
-                                                     DN4GL_MAX_ROW_DEGREE, 1, err_flag);
+                                                     DN4GL_MAX_ROW_DEGREE, 1, err_flag, val, col);
     } else {
-        sort_rows_bitonic<false><<<sms * 4, BITONIC_THREADS, 0, st>>>(row_ptr, items, primary, worklist, work_count);
+        sort_rows_bitonic<false><<<sms * 4, BITONIC_THREADS, 0, st>>>(row_ptr, items, primary, worklist, work_count, val, col);
         sort_rows_heavy<false><<<sms, 256, big, st>>>(row_ptr, items, primary, worklist, work_count, HEAVY_SORT_MID,
-                                                      DN4GL_MAX_ROW_DEGREE, 1, err_flag);
+                                                      DN4GL_MAX_ROW_DEGREE, 1, err_flag, val, col);
     }
     DN_LAUNCHED_N(2);
     return DN4GL_OK;
@@ -389,7 +427,7 @@ int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int
 extern "C" size_t dn4gl_csr_workspace_bytes(int64_t N, int64_t E) {
     (void)E;
     size_t n = static_cast<size_t>(N > 0 ? N : 1);
-    return align_up(n * sizeof(int32_t), 256) * 2 + 256 + dn4gl_scan_workspace_bytes(N + 1);
+    return align_up((n + 1) * sizeof(int32_t), 256) * 3 + 256 + dn4gl_scan_workspace_bytes(N + 1);
 }
 
 extern "C" int dn4gl_build_csr(const int32_t *key, const int32_t *val, int64_t N, int64_t E, int32_t *row_ptr,
@@ -399,33 +437,30 @@ extern "C" int dn4gl_build_csr(const int32_t *key, const int32_t *val, int64_t N
     DN_ARG(row_ptr != nullptr && (E == 0 || (key != nullptr && eid != nullptr)));
     cudaStream_t st = as_stream(stream);
     WsCarver wsc(ws, ws_bytes);
-    int32_t *cursor = wsc.take<int32_t>(N > 0 ? N : 1);
-    int32_t *worklist = wsc.take<int32_t>(N > 0 ? N : 1);
-    int32_t *work_count = wsc.take<int32_t>(1);
+    // counts | cursor | work_count are adjacent: ONE memset zeroes all three
+    int32_t *cnt = wsc.take<int32_t>(N + 1);
+    int32_t *cursor = wsc.take<int32_t>(N + 1);
+    int32_t *work_count = wsc.take<int32_t>(2);
+    int32_t *worklist = wsc.take<int32_t>(N + 1);
     size_t scan_bytes = dn4gl_scan_workspace_bytes(N + 1);
     char *scan_ws = wsc.take<char>(scan_bytes);
-    if (!cursor || !worklist || !work_count || !scan_ws) {
+    if (!cnt || !cursor || !worklist || !work_count || !scan_ws) {
         dn4gl_set_error("dn4gl_build_csr: workspace too small (%zu < %zu)", ws_bytes, dn4gl_csr_workspace_bytes(N, E));
         return DN4GL_EWORKSPACE;
     }
-    DN_CUDA(cudaMemsetAsync(row_ptr, 0, static_cast<size_t>(N + 1) * sizeof(int32_t), st));
+    const size_t zero_bytes = static_cast<size_t>(reinterpret_cast<char *>(work_count + 2) - reinterpret_cast<char *>(cnt));
+    DN_CUDA(cudaMemsetAsync(cnt, 0, zero_bytes, st));
     if (E > 0) {
-        csr_histogram<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(key, E, row_ptr);
+        csr_histogram<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(key, E, cnt);
         DN_LAUNCHED();
     }
-    int rc = dn4gl_exclusive_scan_i32(row_ptr, row_ptr, N, scan_ws, scan_bytes, stream);
+    int rc = dn4gl_exclusive_scan_i32(cnt, row_ptr, N, scan_ws, scan_bytes, stream);
     if (rc != DN4GL_OK) return rc;
     if (E == 0) return DN4GL_OK;
-    DN_CUDA(cudaMemsetAsync(cursor, 0, static_cast<size_t>(N) * sizeof(int32_t), st));
     csr_scatter<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(key, E, row_ptr, cursor, eid);
     DN_LAUNCHED();
-    rc = dn4gl_sort_rows(row_ptr, N, eid, nullptr, worklist, work_count, err_flag, st);
-    if (rc != DN4GL_OK) return rc;
-    if (col) {
-        csr_fill_col<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(eid, val, E, col);
-        DN_LAUNCHED();
-    }
-    return DN4GL_OK;
+    // the row sorts restore the stable order and write col = val[eid] (or eid) on the way out
+    return dn4gl_sort_rows(row_ptr, N, eid, nullptr, worklist, work_count, err_flag, st, val, col, true);
 }
 
 // CSR of items whose keys are already non-decreasing (the (src, dst)-sorted edge list that coalesce / PyG hand over):

@@ -747,25 +747,39 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
 }
 
 // Fixed-order sums of per-CTA partials.  A block is 32 output elements x 32 partial groups: thread (lane, g) adds
-// partials g, g+32, ... (independent coalesced loads, double accumulation), the groups are then added in index order.
-__device__ __forceinline__ double partial_column_sum(const float *__restrict__ part, int nparts, int stride, int e, int g) {
+// partials g, g+32, ... in double.  ALL loads of a thread (up to 8 partials x NCOL columns) are issued before the first
+// add: the r1d profile showed these few-CTA kernels spending 14-15 us on 5-10 dependent L2/DRAM round trips
+// (long_scoreboard 13-27 per issue) for 2.5 MB of data.  The add order stays fixed (p ascending, columns in order).
+template <int NCOL, int UNR = 8>
+__device__ __forceinline__ double partial_columns_sum(const float *__restrict__ part, int nparts, int stride,
+                                                      const int (&e)[NCOL], int g) {
     double s = 0.0;
-    int p = g;
-    for (; p + 96 < nparts; p += 128) {
-        const float v0 = __ldcg(part + static_cast<size_t>(p) * stride + e), v1 = __ldcg(part + static_cast<size_t>(p + 32) * stride + e);
-        const float v2 = __ldcg(part + static_cast<size_t>(p + 64) * stride + e), v3 = __ldcg(part + static_cast<size_t>(p + 96) * stride + e);
-        s += static_cast<double>(v0); s += static_cast<double>(v1); s += static_cast<double>(v2); s += static_cast<double>(v3);
+    for (int p0 = g; p0 < nparts; p0 += 32 * UNR) {
+        float v[UNR][NCOL];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int p = p0 + 32 * u;
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) v[u][c] = (p < nparts) ? __ldcg(part + static_cast<size_t>(p) * stride + e[c]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) s += static_cast<double>(v[u][c]);
+        }
     }
-    for (; p < nparts; p += 32) s += static_cast<double>(__ldcg(part + static_cast<size_t>(p) * stride + e));
     return s;
 }
+// sm[g][lane] = s for all 32 x 32 threads; warp w then owns element w: it reads the 32 group values of that element and
+// combines them with a fixed xor-butterfly.  Returns the total of element `g` (valid in every lane of warp g).
 __device__ __forceinline__ double group_sum(double (*sm)[33], int lane, int g, double s) {
     sm[g][lane] = s;
     __syncthreads();
-    double tot = 0.0;
-    if (g == 0)
-        for (int gg = 0; gg < 32; ++gg) tot += sm[gg][lane];
-    return tot;
+    double t = sm[lane][g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    return t;
 }
 
 // dW / db / previous-stage sums.  dW[m][k] is the sum of the four hi/lo blocks of the weight accumulator.
@@ -773,6 +787,7 @@ __global__ void __launch_bounds__(1024)
 lin_bwd_reduce_kernel(const float *__restrict__ part, int nparts, int MP, int KP, int M, int K,
                       float *__restrict__ dW, float *__restrict__ db, float *__restrict__ sums_prev) {
     __shared__ double sm[32][33];
+    __shared__ float *sm_dst[32];
     const int stride = bwd_part_floats(KP, MP);
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;                 // logical element: [MP*KP dW | MP db | 2 KP sums]
@@ -782,19 +797,27 @@ lin_bwd_reduce_kernel(const float *__restrict__ part, int nparts, int MP, int KP
         const int m = e / KP, k = e % KP;
         if (m < M && k < K && dW) {
             dst = dW + m * K + k;
-            s = partial_column_sum(part, nparts, stride, m * 2 * KP + k, g) + partial_column_sum(part, nparts, stride, m * 2 * KP + KP + k, g) +
-                partial_column_sum(part, nparts, stride, (MP + m) * 2 * KP + k, g) +
-                partial_column_sum(part, nparts, stride, (MP + m) * 2 * KP + KP + k, g);
+            const int cols[4] = {m * 2 * KP + k, m * 2 * KP + KP + k, (MP + m) * 2 * KP + k, (MP + m) * 2 * KP + KP + k};
+            s = partial_columns_sum<4, 5>(part, nparts, stride, cols, g);   // 148 partials: one pass of 5 x 4 loads
         }
     } else if (e < MP * KP + MP) {
         const int m = e - MP * KP;
-        if (m < M && db) { dst = db + m; s = partial_column_sum(part, nparts, stride, 4 * MP * KP + m, g); }
+        if (m < M && db) {
+            dst = db + m;
+            const int cols[1] = {4 * MP * KP + m};
+            s = partial_columns_sum<1>(part, nparts, stride, cols, g);
+        }
     } else if (e < MP * KP + MP + 2 * KP) {
         const int i = e - MP * KP - MP, which = i / KP, k = i % KP;
-        if (k < K && sums_prev) { dst = sums_prev + which * K + k; s = partial_column_sum(part, nparts, stride, 4 * MP * KP + MP + i, g); }
+        if (k < K && sums_prev) {
+            dst = sums_prev + which * K + k;
+            const int cols[1] = {4 * MP * KP + MP + i};
+            s = partial_columns_sum<1>(part, nparts, stride, cols, g);
+        }
     }
-    const double tot = group_sum(sm, lane, g, s);
-    if (g == 0 && dst != nullptr) *dst = static_cast<float>(tot);
+    if (g == 0) sm_dst[lane] = dst;
+    const double tot = group_sum(sm, lane, g, s);        // total of element blockIdx.x * 32 + g
+    if (lane == 0 && sm_dst[g] != nullptr) *sm_dst[g] = static_cast<float>(tot);
 }
 
 // BatchNorm record from the per-CTA (n, shift, S1, S2) partials of lin_fwd_kernel: every partial is re-centred on the
@@ -804,41 +827,60 @@ bn_finalize_kernel(const float4 *__restrict__ part, int nparts, int MP, int M, i
                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
                    float *__restrict__ bn_out, float *__restrict__ run_mean, float *__restrict__ run_var, long long *nbt) {
     __shared__ double sm[32][33];
+    __shared__ double sm_kstar[32];
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;     // < MP (MP is a multiple of 32)
     const float4 p0 = __ldcg(part + c);
-    const double kstar = static_cast<double>(p0.y) + static_cast<double>(p0.z) / static_cast<double>(p0.x);
     double A1 = 0.0, A2 = 0.0;
-    for (int p = g; p < nparts; p += 32) {
-        const float4 v = __ldcg(part + static_cast<size_t>(p) * MP + c);
-        const double n = v.x;
-        if (n > 0.0) {
-            const double s1 = v.z, s2 = v.w;
-            const double mean_i = static_cast<double>(v.y) + s1 / n, m2_i = s2 - s1 * s1 / n;
-            const double d = mean_i - kstar;
-            A1 += n * d;
-            A2 += (m2_i > 0.0 ? m2_i : 0.0) + n * d * d;
+    double kstar = 0.0;
+    bool have_k = false;
+    constexpr int UNR = 5;                                 // 296 partials: two passes of 5 loads
+    for (int q0 = g; q0 < nparts; q0 += 32 * UNR) {        // all loads of the chunk first, then the double arithmetic
+        float4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int p = q0 + 32 * u;
+            v[u] = (p < nparts) ? __ldcg(part + static_cast<size_t>(p) * MP + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (!have_k) {
+            kstar = static_cast<double>(p0.y) + static_cast<double>(p0.z) / static_cast<double>(p0.x);
+            have_k = true;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const double n = v[u].x;
+            if (n > 0.0) {
+                const double s1 = v[u].z, s2 = v[u].w;
+                const double r = s1 / n;
+                const double mean_i = static_cast<double>(v[u].y) + r, m2_i = s2 - s1 * r;
+                const double d = mean_i - kstar;
+                A1 += n * d;
+                A2 += (m2_i > 0.0 ? m2_i : 0.0) + n * d * d;
+            }
         }
     }
-    const double a1 = group_sum(sm, lane, g, A1);
-    __syncthreads();
+    if (!have_k) kstar = static_cast<double>(p0.y) + static_cast<double>(p0.z) / static_cast<double>(p0.x);
+    if (g == 0) sm_kstar[lane] = kstar;
+    const double a1 = group_sum(sm, lane, g, A1);          // totals of channel blockIdx.x * 32 + g
     const double a2 = group_sum(sm, lane, g, A2);
-    if (g == 0 && c < M) {
+    const int cc = blockIdx.x * 32 + g;
+    if (lane == 0 && cc < M) {
+        const double ks = sm_kstar[g];
         const double Nd = static_cast<double>(N);
-        const double mean = kstar + a1 / Nd;
+        const double mean = ks + a1 / Nd;
         double m2 = a2 - a1 * a1 / Nd;
         if (m2 < 0.0) m2 = 0.0;
         const double var = m2 / Nd;
         const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-        const float gam = gamma ? gamma[c] : 1.f, bet = beta ? beta[c] : 0.f;
-        bn_out[c] = static_cast<float>(mean);
-        bn_out[M + c] = rstd;
-        bn_out[2 * M + c] = gam * rstd;
-        bn_out[3 * M + c] = bet;
-        if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * static_cast<float>(mean);
+        const float gam = gamma ? gamma[cc] : 1.f, bet = beta ? beta[cc] : 0.f;
+        bn_out[cc] = static_cast<float>(mean);
+        bn_out[M + cc] = rstd;
+        bn_out[2 * M + cc] = gam * rstd;
+        bn_out[3 * M + cc] = bet;
+        if (run_mean) run_mean[cc] = (1.f - momentum) * run_mean[cc] + momentum * static_cast<float>(mean);
         if (run_var) {
             const double unb = N > 1 ? m2 / (Nd - 1.0) : var;
-            run_var[c] = (1.f - momentum) * run_var[c] + momentum * static_cast<float>(unb);
+            run_var[cc] = (1.f - momentum) * run_var[cc] + momentum * static_cast<float>(unb);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
@@ -964,9 +1006,12 @@ bn_bwd_sums_reduce_kernel(const float *__restrict__ part, int nparts, int CHP, i
     const int e = blockIdx.x * 32 + lane;
     const int which = e / (4 * CHP), ch = e % (4 * CHP);
     const bool ok = e < 8 * CHP && ch < M;
-    const double s = ok ? partial_column_sum(part, nparts, 8 * CHP, e, g) : 0.0;
-    const double tot = group_sum(sm, lane, g, s);
-    if (g == 0 && ok) sums[which * M + ch] = static_cast<float>(tot);
+    const int cols[1] = {e};
+    const double s = ok ? partial_columns_sum<1>(part, nparts, 8 * CHP, cols, g) : 0.0;
+    const double tot = group_sum(sm, lane, g, s);        // total of element blockIdx.x * 32 + g
+    const int eg = blockIdx.x * 32 + g, which_g = eg / (4 * CHP), ch_g = eg % (4 * CHP);
+    if (lane == 0 && eg < 8 * CHP && ch_g < M) sums[which_g * M + ch_g] = static_cast<float>(tot);
+    (void)which;
 }
 
 // fixed-order dot product: per-CTA partial (tree in shared memory), the last CTA adds the partials in index order

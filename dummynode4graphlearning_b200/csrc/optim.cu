@@ -30,10 +30,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const 
                                                    const float *__restrict__ hyper, float *step, int decoupled,
                                                    int32_t *counter) {
     const AdamHyper h = {hyper[0], hyper[1], hyper[2], hyper[3], hyper[4]};
-    const double t = static_cast<double>(*reinterpret_cast<volatile float *>(step)) + 1.0;
-    const double bc1 = 1.0 - pow(static_cast<double>(h.beta1), t), bc2 = 1.0 - pow(static_cast<double>(h.beta2), t);
-    const float step_size = static_cast<float>(static_cast<double>(h.lr) / bc1);
-    const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+    // bias corrections in double, once per CTA (pow is ~200 FP64 instructions)
+    __shared__ float sh_step_size, sh_inv_bc2_sqrt, sh_t;
+    if (threadIdx.x == 0) {
+        const double t = static_cast<double>(*reinterpret_cast<volatile float *>(step)) + 1.0;
+        const double bc1 = 1.0 - pow(static_cast<double>(h.beta1), t), bc2 = 1.0 - pow(static_cast<double>(h.beta2), t);
+        sh_step_size = static_cast<float>(static_cast<double>(h.lr) / bc1);
+        sh_inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+        sh_t = static_cast<float>(t);
+    }
+    __syncthreads();
+    const float step_size = sh_step_size, inv_bc2_sqrt = sh_inv_bc2_sqrt;
     const int64_t n4 = n >> 2;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     float4 *p4 = reinterpret_cast<float4 *>(p), *m4 = reinterpret_cast<float4 *>(m), *v4 = reinterpret_cast<float4 *>(v);
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, const 
     }
     __syncthreads();
     if (last && threadIdx.x == 0) {
-        *step = static_cast<float>(t);
+        *step = sh_t;
         *counter = 0;
     }
 }

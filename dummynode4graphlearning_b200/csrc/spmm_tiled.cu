@@ -306,7 +306,7 @@ __device__ __forceinline__ void process_heavy_row(const int32_t *__restrict__ ro
     constexpr int RPW = 32 / LANES;
     constexpr int DV = LANES * VEC;
     constexpr int SG = NCW * RPW;   // sub-groups in the CTA
-    constexpr int UH = (VEC == 4 || NCW > 15) ? 2 : 4;
+    constexpr int UH = (VEC == 4 || (NCW > 15 && VEC > 1)) ? 2 : 4;
     const int sub = lane / LANES, sl = lane % LANES;
     const int sg = cw * RPW + sub;
     const int beg = __ldg(row_ptr + row), end = __ldg(row_ptr + row + 1);

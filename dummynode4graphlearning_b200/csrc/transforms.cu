@@ -4,7 +4,8 @@
 #include "common.cuh"
 
 int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int32_t *primary, int32_t *worklist,
-                    int32_t *work_count, int32_t *err_flag, cudaStream_t st);
+                    int32_t *work_count, int32_t *err_flag, cudaStream_t st, const int32_t *val, int32_t *col,
+                    bool work_count_zeroed);
 
 // ===========================================================================================
 // a1: tu_data_processing.py:186-214.  One thread per output element; the graph of an element is
@@ -411,7 +412,7 @@ extern "C" int dn4gl_coalesce(const int32_t *src, const int32_t *dst, int64_t N,
         dn4gl_set_error("dn4gl_coalesce: workspace too small");
         return DN4GL_EWORKSPACE;
     }
-    int rc = dn4gl_sort_rows(row_ptr, N, items, dst, worklist, work_count, err_flag, st);
+    int rc = dn4gl_sort_rows(row_ptr, N, items, dst, worklist, work_count, err_flag, st, nullptr, nullptr, false);
     if (rc != DN4GL_OK) return rc;
     coalesce_flags<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(row_ptr, items, src, dst, N, E, keep_scan);
     DN_LAUNCHED();

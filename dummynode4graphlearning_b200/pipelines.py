@@ -90,6 +90,34 @@ def _static_clone(data):
     return d, _structure_tensors(d)[0]
 
 
+def _batch_tensors(data):
+    """every device tensor a compiled Batch holds (what the train step may read from it)."""
+    s = data.structure
+    out = [t for t in _structure_tensors(data)[0] if t is not None]
+    out += [t for t in (s.src, s.dst, s.csr_in.eid, s.csr_out.eid) if t is not None]
+    return out
+
+
+class PendingLoss:
+    """loss of a step that is still in flight: the device->host copy has been queued behind the step on its stream;
+    ``result()`` waits for that copy only (not for later work) and returns the python float."""
+
+    _ring = {}
+
+    def __init__(self, loss):
+        dev = loss.device.index
+        ring = PendingLoss._ring.setdefault(dev, {"bufs": [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(8)], "i": 0})
+        self.buf = ring["bufs"][ring["i"] % 8]
+        ring["i"] += 1
+        self.buf.copy_(loss.detach().reshape(1), non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def result(self):
+        self.event.synchronize()
+        return float(self.buf[0])
+
+
 class _CapturedStep:
     """one CUDA graph of (forward, loss, backward, gradient all-reduce, optimizer step) for ONE batch signature.
     Replaying it does all of that work again on the data currently held by the static buffers."""
@@ -119,8 +147,13 @@ class _CapturedStep:
 
 class ClassificationPipeline:
     def __init__(self, model, optimizer, mode="conj", num_node_labels=None, num_edge_labels=None,
-                 node_label_min=None, with_edge_attr=False, cuda_graphs=None, max_graphs=8):
+                 node_label_min=None, with_edge_attr=False, cuda_graphs=None, max_graphs=8, overlap=None):
         """mode: 'dummy' (DUMMY_ graphs), 'conj' (CONJ_: dummy + edge-to-vertex), 'line' (LINE_), 'raw'.
+
+        overlap: run the graph transforms on a second CUDA stream so that the transform of mini-batch k+1 (host-bound:
+        ~60 small launches and two size read-backs) overlaps the train step of mini-batch k on the main stream -- the
+        data-loader prefetch of the reference's DataLoader workers, done on the device.  Default: on when the train
+        step is replayed as a CUDA graph (the host is free as soon as the replay is queued).
 
         cuda_graphs: replay the train step (forward + loss + backward + all-reduce + optimizer) as a CUDA graph when a
         batch has the same signature (tensor shapes + tiling scalars) as an earlier one: the first occurrence of a
@@ -138,6 +171,13 @@ class ClassificationPipeline:
         if self.cuda_graphs and not capturable:
             raise ValueError("cuda_graphs=True needs an optimizer built with capturable=True")
         self._graphs, self._max_graphs = {}, max_graphs
+        self.overlap = bool(self.cuda_graphs if overlap is None else overlap) and self.device.type == "cuda"
+        self._tstream = None
+
+    def _transform_stream(self):
+        if self._tstream is None:
+            self._tstream = torch.cuda.Stream(self.device)
+        return self._tstream
 
     def transform(self, dev_batch):
         """raw TU-shaped device batch -> PyG-style Batch with compiled structure."""
@@ -192,16 +232,51 @@ class ClassificationPipeline:
             ent = self._graphs[sig] = _CapturedStep(self, data)
         return ent.run(data)
 
-    def step_resident(self, dev_batch):
-        """inputs already in HBM: transform + train step; returns the loss tensor (no host sync)."""
-        return self.train_on(self.transform(dev_batch))
+    def _hand_over(self, data, tstream):
+        """transform output (allocated and produced on `tstream`) -> consumable on the current (train) stream."""
+        main = torch.cuda.current_stream()
+        done = torch.cuda.Event()
+        done.record(tstream)
+        main.wait_event(done)
+        for t in _batch_tensors(data):       # the caching allocator must not recycle them before the train stream is done
+            t.record_stream(main)
+        return data
+
+    def step_resident(self, dev_batch, assume_ready=False):
+        """inputs already in HBM: transform + train step; returns the loss tensor (no host sync).
+
+        With ``overlap`` the transform runs on the pipeline's second stream.  ``assume_ready=True``: the caller
+        guarantees that ``dev_batch`` is complete (written before any still-running work was queued), so the transform
+        does not wait for the train stream and overlaps the previous step; otherwise it is ordered behind everything
+        queued on the current stream so far (always safe, no GPU-side overlap)."""
+        if not self.overlap:
+            return self.train_on(self.transform(dev_batch))
+        ts = self._transform_stream()
+        if not assume_ready:
+            ts.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(ts):
+            data = self.transform(dev_batch)
+        return self.train_on(self._hand_over(data, ts))
+
+    def _upload(self, host_batch):
+        dev = upload(host_batch, self.device)
+        return {k: (v.to(torch.int32) if isinstance(v, torch.Tensor) and v.dtype == torch.int64 and k != "y" else v)
+                for k, v in dev.items()}
+
+    def step_async(self, host_batch):
+        """host buffers in, ``PendingLoss`` out: H2D + transform (second stream when ``overlap``) + train step + queued D2H
+        of the loss.  The host returns as soon as everything is queued; ``PendingLoss.result()`` yields the float.  A
+        loop that reads the previous step's result after submitting the next one keeps both streams busy."""
+        if not self.overlap:
+            return PendingLoss(self.step_resident(self._upload(host_batch)))
+        ts = self._transform_stream()
+        with torch.cuda.stream(ts):          # the upload is ordered on the transform stream: no wait on the train stream
+            data = self.transform(self._upload(host_batch))
+        return PendingLoss(self.train_on(self._hand_over(data, ts)))
 
     def step(self, host_batch):
-        """host buffers in, python float out: H2D + transform + train step + D2H of the loss."""
-        dev = upload(host_batch, self.device)
-        dev = {k: (v.to(torch.int32) if isinstance(v, torch.Tensor) and v.dtype == torch.int64 and k != "y" else v)
-               for k, v in dev.items()}
-        return float(self.step_resident(dev).item())
+        """host buffers in, python float out: H2D + transform + train step + D2H of the loss (blocking)."""
+        return self.step_async(host_batch).result()
 
 
 def _graph_tensors(g):

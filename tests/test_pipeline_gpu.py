@@ -145,3 +145,52 @@ def test_flat_adam_pipeline_eager_vs_graph_vs_torch():
         if s_e[k].is_floating_point():
             denom = float(s_e[k].abs().max().clamp_min(1e-12))
             assert float((s_e[k] - s_g[k]).abs().max()) / denom <= 1e-5, k
+
+
+def test_overlapped_transform_stream_equals_serial():
+    """transform on the second stream (overlapping the previous train step) == everything on one stream, for both the
+    resident and the host-buffer entry points, with losses read through PendingLoss one step late."""
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+    from dummynode4graphlearning_b200.optim import FlatAdam
+    from dummynode4graphlearning_b200.pipelines import ClassificationPipeline, pin_batch
+    dev = torch.device("cuda:0")
+    args = Namespace(num_features=4, hidden_dim=32, num_classes=2, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": 3, "aggregation": "sum"}, epochs=1, device="cuda:0")
+    raws = [{k: v for k, v in synth.tu_batch("proteins", 48, seed=s).items() if k != "vattr"} for s in (1, 2)]
+    order = [0, 1, 0, 0, 1, 0, 1, 1, 0, 0]
+
+    def run(overlap, host_api):
+        torch.manual_seed(0)
+        model = GIN(args).to(dev)
+        pipe = ClassificationPipeline(model, FlatAdam(model.parameters(), lr=0.003), mode="conj", num_node_labels=4,
+                                      node_label_min=0, cuda_graphs=True, overlap=overlap)
+        losses = []
+        if host_api:
+            hosts = [pin_batch(r) for r in raws]
+            pending = None
+            for i in order:
+                nxt = pipe.step_async(hosts[i])
+                if pending is not None:
+                    losses.append(pending.result())
+                pending = nxt
+            losses.append(pending.result())
+        else:
+            devs = [T.to_device(r, dev) for r in raws]
+            torch.cuda.synchronize()
+            outs = [pipe.step_resident(devs[i], assume_ready=True).clone() for i in order]
+            losses = [float(o.item()) for o in outs]
+        torch.cuda.synchronize()
+        return losses, {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    for host_api in (False, True):
+        l0, s0 = run(False, host_api)
+        l1, s1 = run(True, host_api)
+        for a, b in zip(l0, l1):
+            assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (host_api, l0, l1)
+        for k in s0:
+            if s0[k].is_floating_point():
+                denom = float(s0[k].abs().max().clamp_min(1e-12))
+                assert float((s0[k] - s1[k]).abs().max()) / denom <= 1e-5, (host_api, k)
+            else:
+                assert torch.equal(s0[k], s1[k]), (host_api, k)

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""K1 (sum aggregation) alone on the C2 workload's CONJ structure (156 759 rows x D=32, 1.01 M edges): sweep of the
+tiled kernel's launch configuration, L2 flushed before every launch, algorithmic GB/s.
+  python tools/bench_k1_c2.py [--smem 64,100,150,200] [--warps 16,24,32] [--dims 32]"""
+import argparse
+import json
+import os
+import statistics
+import sys
+from argparse import Namespace
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--smem", default="64,100,150,200")
+    ap.add_argument("--warps", default="16,24,32")
+    ap.add_argument("--dims", default="32")
+    ap.add_argument("--iters", type=int, default=20)
+    a = ap.parse_args()
+    from dummynode4graphlearning_b200 import graph as G, ops, synth, transforms as T
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+    from dummynode4graphlearning_b200.pipelines import ClassificationPipeline
+    dev = torch.device("cuda:0")
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6550.0
+    raw = synth.tu_batch("proteins", 1113, seed=0)
+    args = Namespace(num_features=2, hidden_dim=32, num_classes=2, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": 2, "aggregation": "sum"}, epochs=1, device=str(dev))
+    model = GIN(args).to(dev)
+    pipe = ClassificationPipeline(model, torch.optim.Adam(model.parameters()), mode="conj", num_node_labels=2, node_label_min=0)
+    data = pipe.transform(T.to_device({k: v for k, v in raw.items() if k != "vattr"}, dev))
+    s = data.structure
+    N, E = s.num_nodes, int(s.csr_in.nnz)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    seg = (s.node_ptr[1:] - s.node_ptr[:-1])
+    print(json.dumps({"N": N, "E": E, "graphs": int(seg.numel()), "max_rows": int(seg.max()), "mean_rows": float(seg.float().mean()),
+                      "rows_in_graphs_over_300": int(seg[seg > 300].sum()), "rows_in_graphs_over_600": int(seg[seg > 600].sum())}))
+    for D in [int(x) for x in a.dims.split(",")]:
+        x = torch.rand((N, D), device=dev)
+        nbytes = 4 * D * N * 2 + 4 * E + 4 * (N + 1)
+        ref = None
+        for smem in [int(v) for v in a.smem.split(",")]:
+            for warps in [int(v) for v in a.warps.split(",")]:
+                G.TILE_SMEM, G.TILE_WARPS = smem * 1024, warps
+                for c in (s.csr_in, s.csr_out):
+                    c._tiles.clear()
+                try:
+                    t = s.csr_in.tiles(D)
+                    ts = []
+                    for _ in range(a.iters):
+                        flush.fill_(1)
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        out = ops.spmm_sum(x, s.csr_in, s.csr_out, 1.0)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        ts.append(e0.elapsed_time(e1) * 1e3)
+                    if ref is None:
+                        ref = out.clone()
+                    ok = bool(torch.equal(ref, out))
+                    us = statistics.median(ts)
+                    print(json.dumps({"D": D, "smem_kb": smem, "warps": warps, "stages": t["stages"], "window": t["window"],
+                                      "cap_rows": t["cap_rows"], "tiles": t["T"], "us": round(us, 2), "min_us": round(min(ts), 2),
+                                      "gbs": round(nbytes / us / 1e3, 1), "frac": round(nbytes / us / 1e3 / peak, 3), "same": ok}))
+                except Exception as ex:   # noqa: BLE001
+                    print(json.dumps({"D": D, "smem_kb": smem, "warps": warps, "error": str(ex)[:200]}))
+
+
+if __name__ == "__main__":
+    main()
