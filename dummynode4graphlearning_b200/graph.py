@@ -25,7 +25,14 @@ TILE_WARPS = int(os.environ.get("DN4GL_TILE_WARPS", "32"))             # warps p
 _dev_bound = {}
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device (raw handle: torch.cuda.current_stream() builds a
+    Python Stream object per call, ~15 us -- a fifth of the transform's host time in profiles/r1e)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

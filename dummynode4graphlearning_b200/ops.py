@@ -213,6 +213,47 @@ def dmp_edge_update(PQ, T, bias, graph):
     return _DmpEdgeUpdate.apply(PQ, T, bias, graph)
 
 
+class _CompEdge(torch.autograd.Function):
+    """C[e] = a[src e] * comp(h[src e], ef[e]) for comp in {sub, mult} (compgcn.py:214-240 without the weights)."""
+
+    @staticmethod
+    def forward(ctx, h, ef, graph, op, a):
+        require_cuda(ef, "edge features")
+        h, ef = _f32c(h), _f32c(ef)
+        E, D = ef.shape
+        a = None if a is None else _f32c(a).view(-1)
+        C = torch.empty((E, D), dtype=torch.float32, device=ef.device)
+        lib().call("dn4gl_comp_edge_f32", ptr(graph.src), ptr(a), ptr(h), ptr(ef), ptr(C), E, D, op, _stream())
+        ctx.save_for_backward(h, ef, a)
+        ctx.graph, ctx.op = graph, op
+        return C
+
+    @staticmethod
+    def backward(ctx, gC):
+        h, ef, a = ctx.saved_tensors
+        graph, op = ctx.graph, ctx.op
+        gC = _f32c(gC)
+        E, D = gC.shape
+        gh = gef = None
+        if ctx.needs_input_grad[1]:
+            gef = torch.empty_like(gC)
+            lib().call("dn4gl_comp_edge_bwd_ef_f32", ptr(graph.src), ptr(a), ptr(h), ptr(gC), ptr(gef), E, D, op, _stream())
+        if ctx.needs_input_grad[0]:
+            co = graph.csr_out
+            gh = torch.empty_like(h)
+            lib().call("dn4gl_comp_edge_bwd_h_f32", ptr(co.row_ptr), ptr(co.eid), ptr(a), ptr(ef), ptr(gC), ptr(gh),
+                       h.size(0), D, op, _stream())
+        return gh, gef, None, None, None
+
+
+COMP_SUB, COMP_MULT = 0, 1
+
+
+def comp_edge(h, ef, graph, op, src_scale=None):
+    """per-edge CompGCN composition with the source half of the edge normalisation folded in."""
+    return _CompEdge.apply(h, ef, graph, int(op), src_scale)
+
+
 def gather_rows(x, idx_i32):
     """out[i] = x[idx[i]] (no autograd; used for attribute plumbing of the transforms)."""
     require_cuda(x, "rows")

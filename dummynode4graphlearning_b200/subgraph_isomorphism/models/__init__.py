@@ -1,4 +1,5 @@
 from .basemodel import GraphAdjModel, GraphAdjModelV2  # noqa: F401
+from .compgcn import CompGCN, CompGCNLayer  # noqa: F401
 from .dmpnn import DMPNN, DMPLayer  # noqa: F401
 from .embed import (EquivariantEmbedding, MultihotEmbedding, NormalEmbedding, OrthogonalEmbedding,  # noqa: F401
                     UniformEmbedding)

@@ -97,6 +97,8 @@ class DMPLayer(nn.Module):
 
 
 class DMPNN(GraphAdjModelV2):
+    rep_key = "dmpnn"   # name of the layer list inside the rep-net ModuleDict (CompGCN reuses the wiring below)
+
     def create_rep_net(self, type, **kw):
         if type == "graph":
             num_layers = kw.get("rep_num_graph_layers", 1)
@@ -116,7 +118,7 @@ class DMPNN(GraphAdjModelV2):
         return nn.ModuleDict({"dmpnn": layers})
 
     def _run(self, net, g, v, e, v_gate, e_gate, v_zero=None, e_zero=None):
-        for layer in net["dmpnn"]:
+        for layer in net[self.rep_key]:
             nv, ne = layer(g, v, e)
             if v_gate is not None:
                 nv = nv * v_gate

@@ -273,6 +273,24 @@ int dn4gl_dmp_edge_update_bwd_PQ_f32(const int32_t *in_ptr, const int32_t *in_ei
                                      const uint8_t *is_rev, const float *g, float *gPQ,
                                      int64_t N, int32_t D, void *stream);
 
+/* ---- CompGCN composition ------------------------------------------------------------ */
+/* Replaces CompGCNLayer._comp_func + the edge normalisation inside _node_message_func
+ * (subgraph_isomorphism/models/compgcn.py:214-240, norms :190-209) for comp_opt "sub" (op 0) and "mult" (op 1):
+ *   C[e,:] = a[src e] * (h[src e,:] - ef[e,:])   |   a[src e] * h[src e,:] * ef[e,:]
+ * src_scale = a (N floats) or NULL for a = 1.  The reduce fn.sum(msg) (compgcn.py:163) is dn4gl_dmp_node_agg_f32 on C
+ * and the in/out weights are applied by one node-level GEMM on [S_rev | S_fwd] (linearity).  src[E]: source of every
+ * edge in edge-id order; h (N x D), ef / C (E x D) fp32 row-major, D % 4 == 0.                                          */
+int dn4gl_comp_edge_f32(const int32_t *src, const float *src_scale, const float *h, const float *ef, float *C,
+                        int64_t E, int32_t D, int32_t op, void *stream);
+/* gEF[e,:] = -a[src e] gC[e,:]  |  a[src e] gC[e,:] * h[src e,:]   (h may be NULL for op 0)                             */
+int dn4gl_comp_edge_bwd_ef_f32(const int32_t *src, const float *src_scale, const float *h, const float *gC,
+                               float *gEF, int64_t E, int32_t D, int32_t op, void *stream);
+/* gH[u,:] = a[u] * sum_{e in out(u)} gC[e,:] (* ef[e,:] for op 1), out-list = CSR by source (dn4gl_build_csr(key=src)),
+ * items in edge-id order: deterministic, no float atomics.  ef may be NULL for op 0.  D in {4,...,128,256}.              */
+int dn4gl_comp_edge_bwd_h_f32(const int32_t *out_ptr, const int32_t *out_eid, const float *src_scale,
+                              const float *ef, const float *gC, float *gH, int64_t N, int32_t D, int32_t op,
+                              void *stream);
+
 /* ---- dense helpers of the MLPs ----------------------------------------------------------------- */
 /* C (Ka x Kb) = A^T B, colsum_A (Ka, may be NULL) = column sums of A; A (N x Ka), B (N x Kb) row-major.
  * The weight gradient of every nn.Linear on the path (dW = G^T X, db = colsum G: gconv.py:190-196 MLPs,

@@ -138,6 +138,41 @@ def gen_counting_rgcn():
     print("counting_models.pt:", [k for k in out if not k.startswith("_")])
 
 
+def gen_counting_compgcn():
+    """the reference's CompGCN class, added to counting_models.pt (same batch as gen_counting)."""
+    path = os.path.join(OUT, "counting_models.pt")
+    out = th.load(path, weights_only=False)
+    b = out["_batch"]
+    pd_, gd_, counts, mc = b["pattern"], b["graph"], b["counts"], b["model_cfg"]
+    variants = {
+        "CompGCN/mult_none": dict(hid_dim=16, pred_hid_dim=16, rep_compgcn_comp_opt="mult", rep_compgcn_edge_norm="none"),
+        "CompGCN/sub_both_node_edge": dict(hid_dim=16, pred_hid_dim=16, rep_compgcn_comp_opt="sub",
+                                           rep_compgcn_edge_norm="both", node_pred=True, edge_pred=True,
+                                           pred_net="MeanPredictNet"),
+        "CompGCN/mult_in_bn_unshared": dict(hid_dim=16, pred_hid_dim=16, rep_compgcn_comp_opt="mult",
+                                            rep_compgcn_edge_norm="in", rep_compgcn_batch_norm=True, share_rep_net=False),
+        "CompGCN/corr_out": dict(hid_dim=16, pred_hid_dim=16, rep_compgcn_comp_opt="corr", rep_compgcn_edge_norm="out"),
+    }
+    for tag, over in variants.items():
+        kw = rd.counting_kwargs({k: v for k, v in mc.items() if k.startswith("max_")}, **over)
+        model = rd.ref_counting_model("CompGCN", kw, seed=zlib.crc32(tag.encode()) % 1000)
+        o = model(rd.dgl_batched(pd_), rd.dgl_batched(gd_))
+        c = th.from_numpy(counts).float().view(-1, 1)
+        crit = lambda pred, target, slp: F.mse_loss(F.leaky_relu(pred, slp), target)
+        loss = crit(o["pred_c"], c, 0.01)
+        reg = 0.0
+        for k in ("p_v_rep", "p_e_rep", "g_v_rep", "g_e_rep"):
+            if o[k] is not None:
+                reg = reg + crit(o[k], th.zeros_like(o[k]), 1) * o[k].size(1)
+        loss = loss + 1e-3 * reg
+        loss.backward()
+        out[tag] = dict(name="CompGCN", kwargs=kw, state_dict={k: v.clone() for k, v in model.state_dict().items()},
+                        outputs={k: (v.detach().clone() if isinstance(v, th.Tensor) else None) for k, v in o.items()},
+                        loss=loss.detach().clone(), grads=_grads(model))
+    th.save(out, path)
+    print("counting_models.pt:", [k for k in out if not k.startswith("_")])
+
+
 def gen_classification():
     out = {}
     raw = synth.tu_batch("mutag", 10, seed=41)
@@ -180,4 +215,5 @@ if __name__ == "__main__":
     gen_transforms()
     gen_counting()
     gen_counting_rgcn()
+    gen_counting_compgcn()
     gen_classification()

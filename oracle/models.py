@@ -188,6 +188,41 @@ def dmp_layer(sd, p, h, ef, src, dst, is_rev, out_deg, cfg):
     return n_out, e_out
 
 
+def compgcn_layer(sd, p, h, ef, src, dst, is_rev, in_deg, out_deg, cfg):
+    """CompGCNLayer, compgcn.py:169-279, in the reference's own per-edge formulation (self_loop is always on: the
+    model never passes it, compgcn.py:311-321)."""
+    act = act_fn(cfg["act_func"])
+    opt, en = cfg["comp_opt"], cfg["edge_norm"]
+
+    def comp(head, rel):                                                                 # :214-223
+        if opt == "sub":
+            return head - rel
+        if opt == "mult":
+            return head * rel
+        n = head.size(-1)
+        return th.fft.irfft(th.conj(th.fft.rfft(head, dim=-1)) * th.fft.rfft(rel.expand_as(head), dim=-1), n=n, dim=-1)
+
+    innorm = (1.0 / (in_deg.to(h.dtype) + 1)).view(-1, 1)                               # :181-184
+    outnorm = (1.0 / (out_deg.to(h.dtype) + 1)).view(-1, 1)                             # :191-194
+    c = comp(h[src], ef)                                                                 # :226
+    msg = c @ sd[p + ".in_weight"]
+    if is_rev is not None:                                                               # :229-232
+        r = is_rev.view(-1, 1)
+        msg = msg.masked_fill(r, 0.0) + (c @ sd[p + ".out_weight"]).masked_fill(~r, 0.0)
+    if en == "in":                                                                       # :203-208, :234-235
+        msg = msg * innorm[dst]
+    elif en == "out":
+        msg = msg * outnorm[src]
+    elif en == "both":
+        msg = msg * (outnorm[src] * innorm[dst]) ** 0.5
+    agg = scatter_sum(msg, dst, h.size(0))
+    loop = comp(h, sd[p + ".loop_rel"]) @ sd[p + ".loop_weight"]                         # :245-248
+    out = (agg + loop) * 0.3333333 + sd[p + ".bias"]
+    if cfg.get("batch_norm", False):
+        out = batch_norm_train(sd, p + ".bn", out)
+    return act(out), ef @ sd[p + ".rel_weight"]                                          # :263-266
+
+
 # ---------------------------------------------------------------------------------------------
 # ragged <-> left-padded plumbing (utils/dl.py:51-127)
 def pad_left(feats, sizes):
@@ -267,7 +302,7 @@ def counting_model(sd, pattern_b, graph_b, cfg):
     num_layers, act_func, pred_act_func, pred_net, pred_with_enc, pred_with_deg, return_weights, filter,
     residual, add_node_id, node_pred, edge_pred, layer={...})."""
     P, G = _side(pattern_b), _side(graph_b)
-    v2 = cfg["model"] == "DMPNN"
+    v2 = cfg["model"] in ("DMPNN", "CompGCN")
     act_pred = act_fn(cfg["pred_act_func"])
     agg = {"SumPredictNet": "sum", "MeanPredictNet": "mean", "MaxPredictNet": "max"}[cfg["pred_net"]]
     residual = cfg.get("residual", True)
@@ -309,8 +344,13 @@ def counting_model(sd, pattern_b, graph_b, cfg):
                     o = o * vg
                 v = v + o if residual and v.shape == o.shape else o
             else:
-                p = "%s_rep_net.dmpnn.%s_dmpnn_(%d)" % (side, cfg["rep_name"][side], i)
-                nv, ne = dmp_layer(sd, p, v, e, S["src"], S["dst"], S["e_is_reversed"], S["out_deg"], cfg["layer"][side])
+                if cfg["model"] == "CompGCN":
+                    p = "%s_rep_net.compgcn.%s_compgcn_(%d)" % (side, cfg["rep_name"][side], i)
+                    nv, ne = compgcn_layer(sd, p, v, e, S["src"], S["dst"], S["e_is_reversed"], S["in_deg"], S["out_deg"],
+                                           cfg["layer"][side])
+                else:
+                    p = "%s_rep_net.dmpnn.%s_dmpnn_(%d)" % (side, cfg["rep_name"][side], i)
+                    nv, ne = dmp_layer(sd, p, v, e, S["src"], S["dst"], S["e_is_reversed"], S["out_deg"], cfg["layer"][side])
                 if vg is not None:
                     nv = nv * vg
                 if eg is not None:

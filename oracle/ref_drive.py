@@ -197,7 +197,7 @@ def ref_counting_model(name, kw, seed=0):
     pred.py:50,53, which would make every output 0 -- SURVEY.md App. A-8)."""
     ns = refload.subgraph()
     th.manual_seed(seed)
-    model = {"RGIN": ns.rgin.RGIN, "DMPNN": ns.dmpnn.DMPNN, "RGCN": ns.rgcn.RGCN}[name](**kw)
+    model = {"RGIN": ns.rgin.RGIN, "DMPNN": ns.dmpnn.DMPNN, "RGCN": ns.rgcn.RGCN, "CompGCN": ns.compgcn.CompGCN}[name](**kw)
     with th.no_grad():
         for n, p in model.named_parameters():
             if "pred_fc2" in n or "weight_fc2" in n:

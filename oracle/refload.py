@@ -68,6 +68,7 @@ def subgraph():
     ns.rgin = importlib.import_module("models.rgin")
     ns.dmpnn = importlib.import_module("models.dmpnn")
     ns.rgcn = importlib.import_module("models.rgcn")
+    ns.compgcn = importlib.import_module("models.compgcn")
     ns.pred = importlib.import_module("models.pred")
     ns.embed = importlib.import_module("models.embed")
     ns.filter = importlib.import_module("models.filter")

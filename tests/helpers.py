@@ -33,6 +33,10 @@ def oracle_cfg(name, kw):
                    edge_norm=kw.get("rep_rgcn_edge_norm", "in"), act_func=kw.get("rep_act_func", "relu"),
                    batch_norm=kw.get("rep_rgcn_batch_norm", False))
         layp = dict(lay) if shared else dict(lay, num_rels=kw["max_npel"], num_bases=nb(kw["max_npel"]))
+    elif name == "CompGCN":
+        lay = dict(comp_opt=kw.get("rep_compgcn_comp_opt", "mult"), edge_norm=kw.get("rep_compgcn_edge_norm", "none"),
+                   act_func=kw.get("rep_act_func", "relu"), batch_norm=kw.get("rep_compgcn_batch_norm", False))
+        layp = dict(lay)
     else:
         lay = dict(num_mlp_layers=kw.get("rep_dmpnn_num_mlp_layers", 2), act_func=kw.get("rep_act_func", "relu"),
                    batch_norm=kw.get("rep_dmpnn_batch_norm", False))

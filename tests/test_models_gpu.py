@@ -18,8 +18,8 @@ TOL = 1e-5
 
 
 def _counting_model(name, kw, state_dict, device):
-    from dummynode4graphlearning_b200.subgraph_isomorphism.models import DMPNN, RGCN, RGIN
-    model = {"RGIN": RGIN, "DMPNN": DMPNN, "RGCN": RGCN}[name](**kw)
+    from dummynode4graphlearning_b200.subgraph_isomorphism.models import DMPNN, RGCN, RGIN, CompGCN
+    model = {"RGIN": RGIN, "DMPNN": DMPNN, "RGCN": RGCN, "CompGCN": CompGCN}[name](**kw)
     missing, unexpected = model.load_state_dict(state_dict, strict=True)   # key compatibility (App. A-12)
     assert not missing and not unexpected
     return model.to(device).train()
@@ -50,7 +50,8 @@ def _check_outputs(out, ref):
 
 @pytest.mark.parametrize("tag", ["RGIN/bdd4", "RGIN/basis_full", "RGIN/basis4_unshared", "DMPNN/node", "DMPNN/node_edge",
                                  "DMPNN/edge_max_nofilter", "RGCN/in_basis", "RGCN/both_bdd4",
-                                 "RGCN/none_basis4_bn_unshared"])
+                                 "RGCN/none_basis4_bn_unshared", "CompGCN/mult_none", "CompGCN/sub_both_node_edge",
+                                 "CompGCN/mult_in_bn_unshared", "CompGCN/corr_out"])
 def test_counting_models_match_reference_golden(device, tag):
     from dummynode4graphlearning_b200.graph import BatchedGraph
     gold = load_golden("counting_models.pt")
@@ -81,11 +82,13 @@ def test_counting_models_match_reference_golden(device, tag):
     ("DMPNN", "small", 64, dict(node_pred=True, edge_pred=True, pred_return_weights="node,edge")),
     ("DMPNN", "large", 8, dict(node_pred=True, edge_pred=False)),                        # BASELINE config C4 shapes
     ("RGCN", "small", 64, dict(rep_rgcn_edge_norm="both", rep_rgcn_regularizer="bdd", rep_rgcn_num_bases=4)),   # 8(f) rank 1
+    ("CompGCN", "small", 64, dict(rep_compgcn_comp_opt="mult", rep_compgcn_edge_norm="both", node_pred=True, edge_pred=True)),
+    ("CompGCN", "large", 8, dict(rep_compgcn_comp_opt="sub", rep_compgcn_edge_norm="in")),
 ])
 def test_counting_models_match_oracle_live(device, name, shape, bs, over):
     from dummynode4graphlearning_b200 import synth, transforms as T
     from dummynode4graphlearning_b200.graph import BatchedGraph
-    from dummynode4graphlearning_b200.subgraph_isomorphism.models import DMPNN, RGCN, RGIN
+    from dummynode4graphlearning_b200.subgraph_isomorphism.models import DMPNN, RGCN, RGIN, CompGCN
     from oracle import models as OM
 
     p, g, counts = synth.counting_batch(shape, bs, seed=5)
@@ -101,7 +104,7 @@ def test_counting_models_match_oracle_live(device, name, shape, bs, over):
               init_neigenv=4.0, init_eeigenv=4.0)
     kw.update(over)
     torch.manual_seed(1)
-    model = {"RGIN": RGIN, "DMPNN": DMPNN, "RGCN": RGCN}[name](**kw)
+    model = {"RGIN": RGIN, "DMPNN": DMPNN, "RGCN": RGCN, "CompGCN": CompGCN}[name](**kw)
     with torch.no_grad():
         for n, q in model.named_parameters():
             if "pred_fc2" in n or "weight_fc2" in n:

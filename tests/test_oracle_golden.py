@@ -98,7 +98,8 @@ def test_closed_forms_on_random_graphs():
 
 @pytest.mark.parametrize("tag", ["RGIN/bdd4", "RGIN/basis_full", "RGIN/basis4_unshared", "DMPNN/node", "DMPNN/node_edge",
                                  "DMPNN/edge_max_nofilter", "RGCN/in_basis", "RGCN/both_bdd4",
-                                 "RGCN/none_basis4_bn_unshared"])
+                                 "RGCN/none_basis4_bn_unshared", "CompGCN/mult_none", "CompGCN/sub_both_node_edge",
+                                 "CompGCN/mult_in_bn_unshared", "CompGCN/corr_out"])
 def test_counting_oracle_matches_reference_golden(tag):
     gold = load_golden("counting_models.pt")
     g, b = gold[tag], gold["_batch"]

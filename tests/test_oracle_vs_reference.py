@@ -53,6 +53,7 @@ def test_sub_transforms_live(shape, bs, seed):
 @pytest.mark.parametrize("tag,name,over", [
     ("live/RGIN", "RGIN", dict(hid_dim=16, pred_hid_dim=16)),
     ("live/RGCN", "RGCN", dict(hid_dim=16, pred_hid_dim=16, rep_rgcn_edge_norm="both")),
+    ("live/CompGCN", "CompGCN", dict(hid_dim=16, pred_hid_dim=16, rep_compgcn_comp_opt="sub", rep_compgcn_edge_norm="both")),
     ("live/DMPNN", "DMPNN", dict(hid_dim=16, pred_hid_dim=16, node_pred=True, edge_pred=True, pred_return_weights="node,edge")),
 ])
 def test_counting_models_live(tag, name, over):
