@@ -423,3 +423,118 @@ extern "C" int dn4gl_coalesce(const int32_t *src, const int32_t *dst, int64_t N,
     DN_LAUNCHED();
     return DN4GL_OK;
 }
+
+// ===========================================================================================
+// the remaining augmentation flags of subgraph_isomorphism/train.py on the same flat batch layout.
+//
+// add_reversed_edges (train.py:291-345, GraphAdj branch): every graph's m edges are followed by their m reversals
+// (v, u) with id = max_ne + position-in-graph, label + max_nel and is_reversed = 1; the original rows keep
+// is_reversed = 0 (DGL zero-fills the new column).  One thread per OUTPUT edge, closed-form offsets (2 * edge_ptr).
+__global__ void sub_add_reversed_kernel(int B, const int32_t *__restrict__ edge_ptr, const int32_t *__restrict__ src,
+                                        const int32_t *__restrict__ dst, const int32_t *__restrict__ eid,
+                                        const int32_t *__restrict__ elabel, int64_t E, int max_ne, int max_nel,
+                                        int32_t *__restrict__ o_edge_ptr, int32_t *__restrict__ o_src,
+                                        int32_t *__restrict__ o_dst, int32_t *__restrict__ o_eid,
+                                        int32_t *__restrict__ o_elabel, int32_t *__restrict__ o_erev) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i <= B) o_edge_ptr[i] = 2 * edge_ptr[i];
+    if (i >= 2 * E) return;
+    // graph g with 2 * edge_ptr[g] <= i < 2 * edge_ptr[g + 1]
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (2ll * __ldg(edge_ptr + mid) <= i) lo = mid; else hi = mid;
+    }
+    const int e0 = __ldg(edge_ptr + lo), m = __ldg(edge_ptr + lo + 1) - e0;
+    const int j = static_cast<int>(i - 2ll * e0);
+    if (j < m) {
+        const int e = e0 + j;
+        o_src[i] = src[e]; o_dst[i] = dst[e]; o_eid[i] = eid[e]; o_elabel[i] = elabel[e]; o_erev[i] = 0;
+    } else {
+        const int k = j - m, e = e0 + k;
+        o_src[i] = dst[e]; o_dst[i] = src[e]; o_eid[i] = max_ne + k; o_elabel[i] = elabel[e] + max_nel; o_erev[i] = 1;
+    }
+}
+
+extern "C" int dn4gl_sub_add_reversed(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                                      const int32_t *eid, const int32_t *elabel, int64_t E, int32_t max_ne, int32_t max_nel,
+                                      int32_t *o_edge_ptr, int32_t *o_src, int32_t *o_dst, int32_t *o_eid,
+                                      int32_t *o_elabel, int32_t *o_e_is_reversed, void *stream) {
+    DN_ARG(B >= 0 && E >= 0 && 2 * E < INT32_MAX && edge_ptr && o_edge_ptr);
+    DN_ARG(E == 0 || (src && dst && eid && elabel && o_src && o_dst && o_eid && o_elabel && o_e_is_reversed));
+    const int64_t threads = (2 * E > B + 1) ? 2 * E : B + 1;
+    sub_add_reversed_kernel<<<static_cast<unsigned>(ceil_div64(threads, 256)), 256, 0, as_stream(stream)>>>(
+        B, edge_ptr, src, dst, eid, elabel, E, max_ne, max_nel, o_edge_ptr, o_src, o_dst, o_eid, o_elabel, o_e_is_reversed);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+// remove_loops (train.py:270-288): drops every edge with u == v, order of the survivors preserved (DGL remove_edges).
+__global__ void loop_flags_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int64_t E,
+                                  int32_t *__restrict__ keep) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < E) keep[e] = (src[e] != dst[e]) ? 1 : 0;
+}
+__global__ void loop_compact_kernel(const int32_t *__restrict__ keep_scan, int64_t E, int B,
+                                    const int32_t *__restrict__ edge_ptr, int32_t *__restrict__ o_edge_ptr,
+                                    int32_t *__restrict__ survivors) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e <= B) o_edge_ptr[e] = keep_scan[edge_ptr[e]];
+    if (e < E) {
+        const int q = keep_scan[e];
+        if (keep_scan[e + 1] != q) survivors[q] = static_cast<int32_t>(e);
+    }
+}
+
+extern "C" int dn4gl_remove_loops_mark(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                                       int64_t E, int32_t *keep_scan, int32_t *o_edge_ptr, int32_t *survivors, void *ws,
+                                       size_t ws_bytes, void *stream) {
+    DN_ARG(B >= 0 && E >= 0 && edge_ptr && keep_scan && o_edge_ptr);
+    DN_ARG(E == 0 || (src && dst && survivors));
+    cudaStream_t st = as_stream(stream);
+    if (E > 0) {
+        loop_flags_kernel<<<static_cast<unsigned>(ceil_div64(E, 256)), 256, 0, st>>>(src, dst, E, keep_scan);
+        DN_LAUNCHED();
+    }
+    int rc = dn4gl_exclusive_scan_i32(keep_scan, keep_scan, E, ws, ws_bytes, stream);
+    if (rc != DN4GL_OK) return rc;
+    const int64_t threads = (E > B + 1) ? E : B + 1;
+    loop_compact_kernel<<<static_cast<unsigned>(ceil_div64(threads, 256)), 256, 0, st>>>(keep_scan, E, B, edge_ptr, o_edge_ptr,
+                                                                                        survivors);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+// compute_largest_eigenvalues (utils/graph.py:41-71): per graph  max_e (out_deg[u] + in_deg[v])  and
+// max_e (in_deg[u] + out_deg[v]).  One warp per graph, integer maxima (exact); a graph without edges reports 0.
+__global__ void eigen_bounds_kernel(int B, const int32_t *__restrict__ edge_ptr, const int32_t *__restrict__ src,
+                                    const int32_t *__restrict__ dst, const int32_t *__restrict__ in_deg,
+                                    const int32_t *__restrict__ out_deg, int32_t *__restrict__ node_eig,
+                                    int32_t *__restrict__ edge_eig) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= B) return;
+    int mn = 0, me = 0;
+    for (int e = edge_ptr[g] + lane; e < edge_ptr[g + 1]; e += 32) {
+        const int u = src[e], v = dst[e];
+        mn = max(mn, out_deg[u] + in_deg[v]);
+        me = max(me, in_deg[u] + out_deg[v]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = max(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        me = max(me, __shfl_xor_sync(0xffffffffu, me, o));
+    }
+    if (lane == 0) { node_eig[g] = mn; edge_eig[g] = me; }
+}
+
+extern "C" int dn4gl_sub_eigen_bounds(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                                      const int32_t *in_deg, const int32_t *out_deg, int32_t *node_eig, int32_t *edge_eig,
+                                      void *stream) {
+    DN_ARG(B >= 0);
+    if (B == 0) return DN4GL_OK;
+    DN_ARG(edge_ptr && in_deg && out_deg && node_eig && edge_eig);
+    eigen_bounds_kernel<<<static_cast<unsigned>(ceil_div64(static_cast<int64_t>(B) * 32, 256)), 256, 0, as_stream(stream)>>>(
+        B, edge_ptr, src, dst, in_deg, out_deg, node_eig, edge_eig);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}

@@ -201,6 +201,92 @@ def sub_add_dummy(b, max_nv, max_nvl, max_ne, max_nel):
     return o
 
 
+def sub_add_reversed(b, max_ne, max_nel):
+    """add_reversed_edges, GraphAdj branch (train.py:291-345): every graph's edges followed by their reversals with
+    id = max_ne + position, label + max_nel, is_reversed = 1.  A batch that already carries ``e_is_reversed`` is returned
+    unchanged (train.py:321,334).  max_* are the PRE-augmentation maxima passed at train.py:1315."""
+    if "e_is_reversed" in b:
+        return b
+    require_cuda(b["src"], "batch")
+    dev = b["src"].device
+    B, E = int(b["num_graphs"]), int(b["src"].numel())
+    o = dict(b)
+    o["edge_ptr"] = _empty_i32(B + 1, dev)
+    for k in ("src", "dst", "eid", "elabel", "e_is_reversed"):
+        o[k] = _empty_i32(2 * E, dev)
+    lib().call("dn4gl_sub_add_reversed", B, ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]), ptr(b["eid"]),
+               ptr(b["elabel"]), E, int(max_ne), int(max_nel), ptr(o["edge_ptr"]), ptr(o["src"]), ptr(o["dst"]),
+               ptr(o["eid"]), ptr(o["elabel"]), ptr(o["e_is_reversed"]), _stream())
+    return o
+
+
+_EDGE_COLUMNS = ("src", "dst", "eid", "elabel", "e_is_dummy", "e_is_reversed", "eattr")
+
+
+def sub_remove_loops(b):
+    """remove_loops, GraphAdj branch (train.py:270-288): edges with u == v dropped, survivors keep their order and
+    attribute rows (DGL ``remove_edges``).  One device->host read-back (the surviving edge count)."""
+    require_cuda(b["src"], "batch")
+    L = lib()
+    dev = b["src"].device
+    B, E = int(b["num_graphs"]), int(b["src"].numel())
+    keep_scan, surv, o_edge_ptr = _empty_i32(E + 1, dev), _empty_i32(max(E, 1), dev), _empty_i32(B + 1, dev)
+    wsb = L.size("dn4gl_scan_workspace_bytes", E + 1)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    L.call("dn4gl_remove_loops_mark", B, ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]), E, ptr(keep_scan),
+           ptr(o_edge_ptr), ptr(surv), ptr(ws), wsb, _stream())
+    E2 = int(keep_scan[-1].item())
+    surv = surv[:E2]
+    o = dict(b)
+    o["edge_ptr"] = o_edge_ptr
+    for k in _EDGE_COLUMNS:
+        if k in b:
+            o[k] = _take(b[k], surv)
+    return o
+
+
+def compute_norm(graph, self_loop=True):
+    """compute_norm (utils/graph.py:11-38) on a BatchedGraph -> (node_norm (N, 1), edge_norm (E, 1))."""
+    in_deg = graph.in_degrees().float()
+    if self_loop:
+        node_norm = (in_deg + 1).reciprocal().unsqueeze(-1)
+    else:
+        node_norm = in_deg.reciprocal().masked_fill_(in_deg == 0, 1.0).unsqueeze(-1)
+    return node_norm, torch.index_select(node_norm, 0, graph.dst)
+
+
+def compute_largest_eigenvalues(graph):
+    """compute_largest_eigenvalues (utils/graph.py:41-71) for every graph of a BatchedGraph -> (node_eigenv (B,),
+    edge_eigenv (B,)) as floats."""
+    B = graph.batch_size
+    dev = graph.src.device
+    ind = graph.cached("in_deg_i32", lambda: graph.in_degrees().to(torch.int32).contiguous())
+    outd = graph.cached("out_deg_i32", lambda: graph.out_degrees().to(torch.int32).contiguous())
+    ne, ee = _empty_i32(B, dev), _empty_i32(B, dev)
+    lib().call("dn4gl_sub_eigen_bounds", B, ptr(graph.edge_ptr), ptr(graph.src), ptr(graph.dst), ptr(ind), ptr(outd),
+               ptr(ne), ptr(ee), _stream())
+    return ne.float(), ee.float()
+
+
+def calculate_norms(graph, self_loop=True):
+    """calculate_norms (train.py:500-512): ``ndata['norm']`` / ``edata['norm']``."""
+    if "norm" not in graph.ndata or "norm" not in graph.edata:
+        graph.ndata["norm"], graph.edata["norm"] = compute_norm(graph, self_loop)
+    return graph
+
+
+def calculate_eigenvalues(graph):
+    """calculate_eigenvalues (train.py:515-527): per-graph bounds clamped at 1 and repeated over the graph's nodes /
+    edges as ``ndata['node_eigenv']`` (N, 1) / ``edata['edge_eigenv']`` (E, 1)."""
+    if "node_eigenv" not in graph.ndata or "edge_eigenv" not in graph.edata:
+        ne, ee = compute_largest_eigenvalues(graph)
+        graph.ndata["node_eigenv"] = torch.repeat_interleave(ne.clamp_min(1.0), graph.batch_num_nodes(),
+                                                             output_size=graph.number_of_nodes()).unsqueeze(-1)
+        graph.edata["edge_eigenv"] = torch.repeat_interleave(ee.clamp_min(1.0), graph.batch_num_edges(),
+                                                             output_size=graph.number_of_edges()).unsqueeze(-1)
+    return graph
+
+
 def sub_conjugate(b, id_bound=None):
     """edge-to-vertex transform of a subgraph-isomorphism batch (``convert_conjugate_graph``, utils/graph.py:77-175,
     as applied by ``convert_to_conjugate``, train.py:564-593): edges with equal ``eid`` merge into one vertex, duplicate

@@ -160,6 +160,26 @@ int dn4gl_sub_conj_fill(int32_t B, const int32_t *src, int64_t E, int32_t id_bou
                         const int32_t *keep_scan, int32_t *o_src, int32_t *o_dst, int32_t *o_v_origin,
                         int32_t *o_e_shared, void *ws, size_t ws_bytes, void *stream);
 
+/* ---- remaining augmentation flags of subgraph_isomorphism/train.py --------------------- */
+/* add_reversed_edges, GraphAdj branch (train.py:291-345): graph g's m edges are followed by their m reversals (v, u)
+ * with id = max_ne + position-in-graph, label + max_nel, is_reversed = 1 (originals: 0).  Outputs hold 2E edges;
+ * o_edge_ptr = 2 * edge_ptr.  Node arrays are unchanged.                                                            */
+int dn4gl_sub_add_reversed(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                           const int32_t *eid, const int32_t *elabel, int64_t E, int32_t max_ne, int32_t max_nel,
+                           int32_t *o_edge_ptr, int32_t *o_src, int32_t *o_dst, int32_t *o_eid,
+                           int32_t *o_elabel, int32_t *o_e_is_reversed, void *stream);
+/* remove_loops, GraphAdj branch (train.py:270-288): keep_scan[E+1] = exclusive scan of (src != dst); survivors[<=E] =
+ * surviving edge indices in order (gather every edge column through it); o_edge_ptr[B+1]; E' = keep_scan[E].
+ * ws: dn4gl_scan_workspace_bytes(E + 1).                                                                           */
+int dn4gl_remove_loops_mark(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                            int64_t E, int32_t *keep_scan, int32_t *o_edge_ptr, int32_t *survivors, void *ws,
+                            size_t ws_bytes, void *stream);
+/* compute_largest_eigenvalues (utils/graph.py:41-71) per graph of the batch: node_eig[g] = max_e (out_deg[u] + in_deg[v]),
+ * edge_eig[g] = max_e (in_deg[u] + out_deg[v]) over the graph's edges (0 for a graph without edges).                 */
+int dn4gl_sub_eigen_bounds(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                           const int32_t *in_deg, const int32_t *out_deg, int32_t *node_eig, int32_t *edge_eig,
+                           void *stream);
+
 /* ---- a3: PyG read_tu_data canonicalisation ------------------------------------------------- */
 /* remove_self_loops + coalesce [torch-geometric 2.0.2 read_tu_data, called from
  * graph_classification/graph_neural_networks/dataset.py:151]: given the edge list's endpoints

@@ -59,6 +59,31 @@ def gen_transforms():
     print("transforms.pt:", list(out))
 
 
+def gen_augment():
+    """the reference's remove_loops / add_reversed_edges / calculate_norms /
+    calculate_eigenvalues (train.py:270-345, 500-527) on seeded batches, added to transforms.pt."""
+    path = os.path.join(OUT, "transforms.pt")
+    out = th.load(path, weights_only=False)
+    for shape, bs, seed in (("small", 6, 23), ("large", 1, 24)):
+        p, g, _ = synth.counting_batch(shape, bs, seed=seed)
+        cfg = synth.counting_config(shape)
+        loops = {}
+        for name, b in (("pattern", p), ("graph", g)):      # plant self loops (the synthetic generator makes none)
+            b = dict(b)
+            b["dst"] = b["dst"].copy()
+            b["dst"][::5] = b["src"][::5]
+            loops[name] = b
+        lp, lg = rd.ref_sub_remove_loops(loops["pattern"], loops["graph"])
+        rp, rg = rd.ref_sub_add_reversed(p, g, cfg)
+        dp, dg = rd.ref_sub_add_dummy(rp, rg, process_model_config(dict(cfg, add_rev=True)))
+        out["aug/%s" % shape] = dict(
+            cfg=cfg, pattern=_np(p), graph=_np(g), pattern_loops=_np(loops["pattern"]), graph_loops=_np(loops["graph"]),
+            pattern_noloops=lp, graph_noloops=lg, pattern_rev=rp, graph_rev=rg, pattern_rev_dummy=dp, graph_rev_dummy=dg,
+            norms_self_loop=rd.ref_sub_norms_eigen(dg, True), norms_no_self_loop=rd.ref_sub_norms_eigen(dg, False))
+    th.save(out, path)
+    print("transforms.pt:", list(out))
+
+
 def _grads(model):
     return {n: (p.grad.clone() if p.grad is not None else None) for n, p in model.named_parameters()}
 
@@ -213,6 +238,7 @@ def gen_classification():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_transforms()
+    gen_augment()
     gen_counting()
     gen_counting_rgcn()
     gen_counting_compgcn()

@@ -156,6 +156,40 @@ def ref_sub_add_dummy(pattern_b, graph_b, cfg):
     return dgl_list_to_batch([x["pattern"] for x in ds]), dgl_list_to_batch([x["graph"] for x in ds])
 
 
+def _ref_dataset(pattern_b, graph_b):
+    tf = refload.subgraph().train_funcs
+    ps, gs = batch_to_dgl_list(pattern_b), batch_to_dgl_list(graph_b)
+    return tf, tf.GraphAdjDataset(
+        [{"pattern": p, "graph": g, "counts": 0, "subisomorphisms": th.zeros((0, 0), dtype=th.long)}
+         for p, g in zip(ps, gs)])
+
+
+def ref_sub_add_reversed(pattern_b, graph_b, cfg):
+    """reference add_reversed_edges, GraphAdj branch (train.py:291-345), called as train.py:1315 does."""
+    tf, ds = _ref_dataset(pattern_b, graph_b)
+    tf.add_reversed_edges(ds, cfg["max_npe"], cfg["max_npel"], cfg["max_nge"], cfg["max_ngel"])
+    return dgl_list_to_batch([x["pattern"] for x in ds]), dgl_list_to_batch([x["graph"] for x in ds])
+
+
+def ref_sub_remove_loops(pattern_b, graph_b):
+    """reference remove_loops, GraphAdj branch (train.py:270-288)."""
+    tf, ds = _ref_dataset(pattern_b, graph_b)
+    tf.remove_loops(ds)
+    return dgl_list_to_batch([x["pattern"] for x in ds]), dgl_list_to_batch([x["graph"] for x in ds])
+
+
+def ref_sub_norms_eigen(graph_b, self_loop=True):
+    """reference calculate_norms + calculate_eigenvalues (train.py:500-527) on every graph of the batch."""
+    C = refload.subgraph().constants
+    tf, ds = _ref_dataset(graph_b, graph_b)
+    tf.calculate_norms(ds, self_loop=self_loop)
+    tf.calculate_eigenvalues(ds)
+    gs = [x["graph"] for x in ds]
+    return dict(node_norm=th.cat([g.ndata[C.NORM] for g in gs]).numpy(), edge_norm=th.cat([g.edata[C.NORM] for g in gs]).numpy(),
+                node_eigenv=th.cat([g.ndata[C.NODEEIGENV] for g in gs]).numpy(),
+                edge_eigenv=th.cat([g.edata[C.EDGEEIGENV] for g in gs]).numpy())
+
+
 def ref_sub_conjugate(b):
     """reference convert_conjugate_graph, DGL branch (utils/graph.py:77-175)."""
     gu = refload.subgraph().graph_utils

@@ -77,13 +77,16 @@ def subgraph():
     ns.dl = importlib.import_module("utils.dl")
     ns.train_funcs = _extract_functions(
         os.path.join(_SUB, "train.py"),
-        ["process_model_config", "add_dummy_nodes_edges", "add_reversed_edges", "calculate_degrees"],
+        ["process_model_config", "add_dummy_nodes_edges", "add_reversed_edges", "calculate_degrees", "remove_loops",
+         "calculate_norms", "calculate_eigenvalues"],
+        extra={"compute_norm": ns.graph_utils.compute_norm,
+               "compute_largest_eigenvalues": ns.graph_utils.compute_largest_eigenvalues},
     )
     _state["sub"] = ns
     return ns
 
 
-def _extract_functions(path, names):
+def _extract_functions(path, names, extra=None):
     """exec selected top-level ``def``s of a reference file verbatim (train.py cannot be
     imported whole: it needs tensorboardX, sklearn metrics, the old-DGL ``dataset.Graph``)."""
     import math
@@ -105,6 +108,7 @@ def _extract_functions(path, names):
 
     glb["EdgeSeqDataset"] = EdgeSeqDataset
     glb["GraphAdjDataset"] = GraphAdjDataset
+    glb.update(extra or {})       # names train.py imports from utils.graph
     for node in tree.body:
         if isinstance(node, ast.FunctionDef) and node.name in names:
             code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")

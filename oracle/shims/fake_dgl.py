@@ -143,6 +143,15 @@ class DGLGraph:
         self._u = th.cat([self._u, u])
         self._v = th.cat([self._v, v])
 
+    def remove_edges(self, eids):
+        """DGL semantics: the listed edges disappear, the others keep their relative order and attribute rows."""
+        dead = th.zeros(self.number_of_edges(), dtype=th.bool)
+        dead[th.as_tensor(eids, dtype=th.long).view(-1)] = True
+        keep = (~dead).nonzero().view(-1)
+        self._u, self._v = self._u[keep], self._v[keep]
+        for k in self.edata:
+            self.edata[k] = self.edata[k][keep]
+
     def remove_nodes(self, nids):
         dead = th.zeros(self._n, dtype=th.bool)
         dead[th.as_tensor(nids, dtype=th.long)] = True

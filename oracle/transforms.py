@@ -132,6 +132,75 @@ def sub_add_dummy(b, max_nv, max_nvl, max_ne, max_nel):
     return o
 
 
+def sub_add_reversed(b, max_ne, max_nel):
+    """train.py:291-345 (GraphAdj branch), numpy restatement: per graph, the m edges then their m reversals with
+    id = arange(max_ne, max_ne + m), label + max_nel, is_reversed = 1 (originals zero-filled)."""
+    if "e_is_reversed" in b:
+        return b
+    B = int(b["num_graphs"])
+    cols = {k: [] for k in ("src", "dst", "eid", "elabel", "e_is_reversed")}
+    ep = np.zeros(B + 1, np.int32)
+    for g in range(B):
+        e0, e1 = int(b["edge_ptr"][g]), int(b["edge_ptr"][g + 1])
+        m = e1 - e0
+        u, v = _i32(b["src"])[e0:e1], _i32(b["dst"])[e0:e1]
+        cols["src"] += [u, v]
+        cols["dst"] += [v, u]
+        cols["eid"] += [_i32(b["eid"])[e0:e1], np.arange(max_ne, max_ne + m, dtype=np.int32)]
+        cols["elabel"] += [_i32(b["elabel"])[e0:e1], _i32(b["elabel"])[e0:e1] + np.int32(max_nel)]
+        cols["e_is_reversed"] += [np.zeros(m, np.int32), np.ones(m, np.int32)]
+        ep[g + 1] = ep[g] + 2 * m
+    o = dict(b)
+    o["edge_ptr"] = ep
+    for k, parts in cols.items():
+        o[k] = np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
+    return o
+
+
+def sub_remove_loops(b):
+    """train.py:270-288 (GraphAdj branch): ``remove_edges(e[u == v])`` per graph, order preserved."""
+    keep = _i32(b["src"]) != _i32(b["dst"])
+    o = dict(b)
+    csum = np.concatenate([[0], np.cumsum(keep)]).astype(np.int32)
+    o["edge_ptr"] = csum[_i32(b["edge_ptr"])]
+    for k in ("src", "dst", "eid", "elabel", "e_is_dummy", "e_is_reversed", "eattr"):
+        if k in b:
+            o[k] = np.asarray(b[k])[keep]
+    return o
+
+
+def _degrees(b):
+    N = len(b["vlabel"])
+    return np.bincount(_i32(b["dst"]), minlength=N), np.bincount(_i32(b["src"]), minlength=N)
+
+
+def compute_norm(b, self_loop=True):
+    """utils/graph.py:11-38 -> (node_norm (N,1) float32, edge_norm (E,1))."""
+    ind = _degrees(b)[0].astype(np.float32)
+    if self_loop:
+        nn_ = np.reciprocal(ind + 1)
+    else:
+        with np.errstate(divide="ignore"):
+            nn_ = np.where(ind == 0, np.float32(1.0), np.reciprocal(ind))
+    nn_ = nn_.astype(np.float32).reshape(-1, 1)
+    return nn_, nn_[_i32(b["dst"])]
+
+
+def compute_largest_eigenvalues(b):
+    """utils/graph.py:41-71 per graph -> (node_eigenv (B,), edge_eigenv (B,)) float32; 0 where a graph has no edge
+    (the reference's ``.max()`` of an empty tensor raises there)."""
+    ind, outd = _degrees(b)
+    B = int(b["num_graphs"])
+    ne, ee = np.zeros(B, np.float32), np.zeros(B, np.float32)
+    u, v = _i32(b["src"]), _i32(b["dst"])
+    for g in range(B):
+        e0, e1 = int(b["edge_ptr"][g]), int(b["edge_ptr"][g + 1])
+        if e1 > e0:
+            ne[g] = (outd[u[e0:e1]] + ind[v[e0:e1]]).max()
+            ee[g] = (ind[u[e0:e1]] + outd[v[e0:e1]]).max()
+    return ne, ee
+
+
 def sub_conjugate(b):
     """utils/graph.py:74-175.  Node/edge attribute names are swapped as at lines 155-165:
     the conjugate's vertices carry the edge columns, its edges the shared vertex's columns."""

@@ -42,6 +42,30 @@ def test_tu_transforms_match_reference_golden(gold_t, case):
     assert f["graph_indicator"] == [str(i + 1) for i in range(c["num_graphs"]) for _ in range(c["node_ptr"][i + 1] - c["node_ptr"][i])]
 
 
+@pytest.mark.parametrize("shape", ["small", "large"])
+def test_augmentation_flags_match_reference_golden(gold_t, shape):
+    """remove_loops / add_reversed_edges / add_dummy after add_rev / norms / eigenvalue bounds."""
+    g = gold_t["aug/" + shape]
+    cfg = g["cfg"]
+    E_KEYS = ("edge_ptr", "src", "dst", "eid", "elabel")
+    for side, mx in (("pattern", ("max_npv", "max_npvl", "max_npe", "max_npel")), ("graph", ("max_ngv", "max_ngvl", "max_nge", "max_ngel"))):
+        batches_equal(OT.sub_remove_loops(g[side + "_loops"]), g[side + "_noloops"], E_KEYS)
+        assert (g[side + "_noloops"]["src"] != g[side + "_noloops"]["dst"]).all()
+        rev = OT.sub_add_reversed(g[side], cfg[mx[2]], cfg[mx[3]])
+        batches_equal(rev, g[side + "_rev"], E_KEYS + ("e_is_reversed",))
+        # the dummy augmentation that follows sees the doubled maxima (process_model_config, train.py:38-47)
+        d = OT.sub_add_dummy(rev, cfg[mx[0]], cfg[mx[1]], 2 * cfg[mx[2]], 2 * cfg[mx[3]])
+        batches_equal(d, g[side + "_rev_dummy"], SUB_KEYS)
+    d = g["graph_rev_dummy"]
+    for sl, key in ((True, "norms_self_loop"), (False, "norms_no_self_loop")):
+        nn_, en = OT.compute_norm(d, sl)
+        np.testing.assert_array_equal(nn_, g[key]["node_norm"])
+        np.testing.assert_array_equal(en, g[key]["edge_norm"])
+    ne, ee = OT.compute_largest_eigenvalues(d)
+    np.testing.assert_array_equal(np.repeat(np.maximum(ne, 1), np.diff(d["node_ptr"])), g["norms_self_loop"]["node_eigenv"].ravel())
+    np.testing.assert_array_equal(np.repeat(np.maximum(ee, 1), np.diff(d["edge_ptr"])), g["norms_self_loop"]["edge_eigenv"].ravel())
+
+
 def test_appB_literal_vectors():
     """SURVEY.md App. B, typed in by hand (independent of the generated fixtures)."""
     b = dict(num_graphs=2, node_ptr=np.array([0, 3, 5], np.int32), edge_ptr=np.array([0, 4, 6], np.int32),

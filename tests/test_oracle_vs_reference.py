@@ -88,3 +88,28 @@ def test_counting_models_live(tag, name, over):
         if alias in sd and sd[alias].grad is not None:
             got = got + sd[alias].grad if got is not None else sd[alias].grad
         assert_close_rel(got, pp.grad, 1e-5, "grad " + n)
+
+
+@pytest.mark.parametrize("shape,bs,seed", [("small", 5, 301), ("large", 1, 302)])
+def test_augmentation_flags_live(shape, bs, seed):
+    """oracle vs the reference's remove_loops / add_reversed_edges / norms / eigenvalues, fresh seeds."""
+    from oracle import ref_drive as rd
+    p, g, _ = synth.counting_batch(shape, bs, seed=seed)
+    cfg = synth.counting_config(shape)
+    g2 = dict(g)
+    g2["dst"] = g["dst"].copy()
+    g2["dst"][::4] = g2["src"][::4]
+    _, rg = rd.ref_sub_remove_loops(p, g2)
+    batches_equal(OT.sub_remove_loops(g2), rg, ("edge_ptr", "src", "dst", "eid", "elabel"))
+    rp, rg = rd.ref_sub_add_reversed(p, g, cfg)
+    og = OT.sub_add_reversed(g, cfg["max_nge"], cfg["max_ngel"])
+    batches_equal(og, rg, ("edge_ptr", "src", "dst", "eid", "elabel", "e_is_reversed"))
+    batches_equal(OT.sub_add_reversed(p, cfg["max_npe"], cfg["max_npel"]), rp, ("edge_ptr", "src", "dst", "eid", "elabel", "e_is_reversed"))
+    for sl in (True, False):
+        r = rd.ref_sub_norms_eigen(og, sl)
+        nn_, en = OT.compute_norm(og, sl)
+        np.testing.assert_array_equal(nn_, r["node_norm"])
+        np.testing.assert_array_equal(en, r["edge_norm"])
+    ne, ee = OT.compute_largest_eigenvalues(og)
+    np.testing.assert_array_equal(np.repeat(np.maximum(ne, 1), np.diff(og["node_ptr"])), r["node_eigenv"].ravel())
+    np.testing.assert_array_equal(np.repeat(np.maximum(ee, 1), np.diff(og["edge_ptr"])), r["edge_eigenv"].ravel())

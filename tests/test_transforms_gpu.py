@@ -253,3 +253,64 @@ def test_exclusive_scan(device, n):
     L.call("dn4gl_exclusive_scan_i32", ptr(x), ptr(out), n, ptr(ws), wsb, torch.cuda.current_stream().cuda_stream)
     ref = np.concatenate([[0], np.cumsum(a, dtype=np.int64)]).astype(np.int32)
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("shape", ["small", "large"])
+def test_augmentation_flags_match_golden_and_oracle(device, shape):
+    """SURVEY.md 8(f) rank 3 on the GPU: remove_loops / add_reversed_edges (+ the dummy augmentation behind it) /
+    compute_norm / eigenvalue bounds, bit-exact with the reference-generated goldens."""
+    from dummynode4graphlearning_b200 import transforms as T
+    from dummynode4graphlearning_b200.graph import BatchedGraph
+    from helpers import batches_equal, load_golden
+
+    g = load_golden("transforms.pt")["aug/" + shape]
+    cfg = g["cfg"]
+    E_KEYS = ("edge_ptr", "src", "dst", "eid", "elabel")
+    SUB_KEYS = ("node_ptr", "edge_ptr", "src", "dst", "vid", "vlabel", "v_is_dummy", "eid", "elabel", "e_is_dummy", "e_is_reversed")
+    for side, mx in (("pattern", ("max_npv", "max_npvl", "max_npe", "max_npel")), ("graph", ("max_ngv", "max_ngvl", "max_nge", "max_ngel"))):
+        batches_equal(T.sub_remove_loops(T.to_device(g[side + "_loops"], device)), g[side + "_noloops"], E_KEYS)
+        rev = T.sub_add_reversed(T.to_device(g[side], device), cfg[mx[2]], cfg[mx[3]])
+        batches_equal(rev, g[side + "_rev"], E_KEYS + ("e_is_reversed",))
+        d = T.sub_add_dummy(rev, cfg[mx[0]], cfg[mx[1]], 2 * cfg[mx[2]], 2 * cfg[mx[3]])
+        batches_equal(d, g[side + "_rev_dummy"], SUB_KEYS)
+    gd = g["graph_rev_dummy"]
+    for sl, key in ((True, "norms_self_loop"), (False, "norms_no_self_loop")):
+        bg = BatchedGraph.from_batch(T.to_device(gd, device), device)
+        T.calculate_norms(bg, self_loop=sl)
+        T.calculate_eigenvalues(bg)
+        assert np.array_equal(bg.ndata["norm"].cpu().numpy(), g[key]["node_norm"])
+        assert np.array_equal(bg.edata["norm"].cpu().numpy(), g[key]["edge_norm"])
+        assert np.array_equal(bg.ndata["node_eigenv"].cpu().numpy(), g[key]["node_eigenv"])
+        assert np.array_equal(bg.edata["edge_eigenv"].cpu().numpy(), g[key]["edge_eigenv"])
+
+
+def test_augmentation_flags_random_against_oracle(device):
+    """larger seeded batches (C3 batch size) against the numpy oracle, incl. a graph with no edges left."""
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.graph import BatchedGraph
+    from helpers import batches_equal
+    from oracle import transforms as O
+
+    p, g, _ = synth.counting_batch("small", 256, seed=77)
+    cfg = synth.counting_config("small")
+    g = dict(g)
+    g["dst"] = g["dst"].copy()
+    g["dst"][::3] = g["src"][::3]
+    e0, e1 = int(g["edge_ptr"][5]), int(g["edge_ptr"][6])
+    g["dst"][e0:e1] = g["src"][e0:e1]                       # graph 5 loses every edge
+    ref = O.sub_remove_loops(g)
+    out = T.sub_remove_loops(T.to_device(g, device))
+    batches_equal(out, ref, ("edge_ptr", "src", "dst", "eid", "elabel"))
+    ref_r = O.sub_add_reversed(ref, cfg["max_nge"], cfg["max_ngel"])
+    out_r = T.sub_add_reversed(out, cfg["max_nge"], cfg["max_ngel"])
+    batches_equal(out_r, ref_r, ("edge_ptr", "src", "dst", "eid", "elabel", "e_is_reversed"))
+    assert T.sub_add_reversed(out_r, 1, 1) is out_r           # already reversed: untouched (train.py:321)
+    bg = BatchedGraph.from_batch(out_r, device)
+    ne, ee = T.compute_largest_eigenvalues(bg)
+    rne, ree = O.compute_largest_eigenvalues(ref_r)
+    assert np.array_equal(ne.cpu().numpy(), rne) and np.array_equal(ee.cpu().numpy(), ree)
+    assert rne[5] == 0
+    for sl in (True, False):
+        nn_, en = T.compute_norm(bg, sl)
+        rn, re = O.compute_norm(ref_r, sl)
+        assert np.array_equal(nn_.cpu().numpy(), rn) and np.array_equal(en.cpu().numpy(), re)
