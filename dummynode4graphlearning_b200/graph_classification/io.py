@@ -1,0 +1,123 @@
+"""On-disk TU layout <-> flat batch dicts.
+
+``load_tu_dir`` parses what ``load_graph_data_from_TUDatadir`` parses
+(graph_classification/data_processing/tu_data_processing.py:125-185: ``*_A.txt`` with 1-based global node ids,
+``*_graph_indicator.txt``, ``*_node_labels.txt``, ``*_edge_labels.txt``, ``*_node_attributes.txt``,
+``*_edge_attributes.txt``; labels shifted so the smallest is 1, missing label files -> all ones) into the flat
+block-diagonal batch the GPU transforms consume (``transforms.to_device`` -> ``tu_add_dummy`` -> ``tu_conjugate``).
+``save_tu_dir`` writes a (transformed) batch back exactly as ``save_graph_data`` / ``save_graph_labels`` do
+(tu_data_processing.py:341-414), so DUMMY_/LINE_/CONJ_ datasets produced on the GPU are byte-identical to the
+reference's offline files and can be read by its ``PYGDataset`` / PyG ``read_tu_data``.
+Host-side text I/O only -- no device work happens here.
+"""
+import os
+
+import numpy as np
+
+
+def _read_ints(path):
+    with open(path) as f:
+        return np.array([int(line.strip()) for line in f if line.strip() != ""], dtype=np.int64)
+
+
+def _read_floats(path):
+    with open(path) as f:
+        return [float(line.strip()) for line in f if line.strip() != ""]
+
+
+def _shift_min_to_one(labels):
+    """tu_data_processing.py:157-171"""
+    m = int(labels.min())
+    return labels - m + 1 if m != 1 else labels
+
+
+def load_tu_dir(data_dir):
+    """-> dict(num_graphs, node_ptr, edge_ptr, src, dst, vlabel, elabel[, vattr][, eattr][, y], has_edge_labels)
+    with graph-local structure flattened to global 0-based node ids (int32)."""
+    if os.path.exists(os.path.join(data_dir, "raw")):
+        data_dir = os.path.join(data_dir, "raw")
+    A, gi, nl, el, na, ea, y = [], [], [], [], [], [], None
+    for fn in sorted(os.listdir(data_dir)):
+        p = os.path.join(data_dir, fn)
+        if fn.endswith("_A.txt"):
+            with open(p) as f:
+                A.extend(tuple(map(int, line.strip().replace(" ", "").split(","))) for line in f if line.strip() != "")
+        elif fn.endswith("_graph_indicator.txt"):
+            gi.extend(_read_ints(p).tolist())
+        elif fn.endswith("_node_labels.txt"):
+            nl.extend(_read_ints(p).tolist())
+        elif fn.endswith("_edge_labels.txt"):
+            el.extend(_read_ints(p).tolist())
+        elif fn.endswith("_node_attributes.txt"):
+            na.extend(_read_floats(p))
+        elif fn.endswith("_edge_attributes.txt"):
+            ea.extend(_read_floats(p))
+        elif fn.endswith("_graph_labels.txt"):
+            y = _read_ints(p)
+    gi = np.asarray(gi, dtype=np.int64)
+    A = np.asarray(A, dtype=np.int64).reshape(-1, 2)
+    N, E = len(gi), len(A)
+    has_el = len(el) > 0
+    vlabel = _shift_min_to_one(np.asarray(nl, dtype=np.int64)) if len(nl) else np.ones(N, np.int64)
+    elabel = _shift_min_to_one(np.asarray(el, dtype=np.int64)) if has_el else np.ones(E, np.int64)
+    # graphs are numbered 1..B in file order; nodes of a graph are contiguous (the reference walks them that way, :173-185)
+    B = int(gi.max()) if N else 0
+    counts = np.bincount(gi - 1, minlength=B)
+    node_ptr = np.concatenate([[0], np.cumsum(counts)])
+    src, dst = A[:, 0] - 1, A[:, 1] - 1
+    eg = gi[src] - 1 if E else np.zeros(0, np.int64)
+    if E and (np.any(np.diff(eg) < 0) or np.any(gi[dst] - 1 != eg)):
+        raise ValueError("load_tu_dir: edges must be grouped by graph and stay inside their graph (TU layout)")
+    edge_ptr = np.concatenate([[0], np.cumsum(np.bincount(eg, minlength=B))])
+    out = dict(num_graphs=B, node_ptr=node_ptr.astype(np.int32), edge_ptr=edge_ptr.astype(np.int32),
+               src=src.astype(np.int32), dst=dst.astype(np.int32), vlabel=vlabel.astype(np.int32),
+               elabel=elabel.astype(np.int32), has_edge_labels=has_el)
+    if na:
+        out["vattr"] = np.asarray(na, dtype=np.float64)
+    if ea:
+        out["eattr"] = np.asarray(ea, dtype=np.float64)
+    if y is not None:
+        out["y"] = y
+    return out
+
+
+def _np(v):
+    return v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+
+
+def tu_file_lines(b):
+    """suffix -> list of text lines, exactly what save_graph_data / save_graph_labels write (tu_data_processing.py:341-414)."""
+    node_ptr, src, dst = _np(b["node_ptr"]).astype(np.int64), _np(b["src"]).astype(np.int64), _np(b["dst"]).astype(np.int64)
+    B = int(b["num_graphs"])
+    res = {
+        "graph_indicator": [str(g + 1) for g in range(B) for _ in range(int(node_ptr[g + 1] - node_ptr[g]))],
+        "A": ["%d,%d" % (s + 1, d + 1) for s, d in zip(src, dst)],            # global ids, 1-based (graph_nsum starts at 1)
+        "node_labels": [str(int(x)) for x in _np(b["vlabel"])],
+        "edge_labels": [str(int(x)) for x in _np(b["elabel"])],
+    }
+    if "vattr" in b:
+        res["node_attributes"] = [str(float(x)) for x in _np(b["vattr"])]
+    if "eattr" in b:
+        res["edge_attributes"] = [str(float(x)) for x in _np(b["eattr"])]
+    res["node_ids"] = [str(int(x)) for x in _np(b["vid"])]
+    res["edge_ids"] = [str(int(x)) for x in _np(b["eid"])]
+    if "y" in b:
+        res["graph_labels"] = [str(int(x)) for x in _np(b["y"])]
+    return res
+
+
+def save_tu_dir(b, data_dir, prefix=""):
+    """writes ``<prefix>{graph_indicator,A,node_labels,edge_labels,[node_attributes],[edge_attributes],node_ids,
+    edge_ids,[graph_labels]}.txt`` into data_dir; default prefix as in the reference (directory name + '_', or the
+    parent's name for a ``raw`` directory)."""
+    if prefix == "":
+        prefix = os.path.basename(data_dir) + "_"
+        if prefix == "raw_":
+            prefix = os.path.basename(os.path.dirname(data_dir)) + "_"
+    os.makedirs(data_dir, exist_ok=True)
+    for suffix, lines in tu_file_lines(b).items():
+        with open(os.path.join(data_dir, prefix + suffix + ".txt"), "w") as f:
+            for line in lines:
+                f.write(line)
+                f.write("\n")
+    return data_dir

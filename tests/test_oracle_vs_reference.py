@@ -113,3 +113,25 @@ def test_augmentation_flags_live(shape, bs, seed):
     ne, ee = OT.compute_largest_eigenvalues(og)
     np.testing.assert_array_equal(np.repeat(np.maximum(ne, 1), np.diff(og["node_ptr"])), r["node_eigenv"].ravel())
     np.testing.assert_array_equal(np.repeat(np.maximum(ee, 1), np.diff(og["edge_ptr"])), r["edge_eigenv"].ravel())
+
+
+@pytest.mark.parametrize("shape,nb,seed", [("mutag", 7, 401), ("proteins", 4, 402)])
+def test_tu_io_live(shape, nb, seed):
+    """load_tu_dir == the reference's load_graph_data_from_TUDatadir on the same files, and
+    save_tu_dir's text == the reference's save_graph_data text for the reference's own CONJ graphs."""
+    import tempfile
+    from dummynode4graphlearning_b200.graph_classification import io as tuio
+    from oracle import ref_drive as rd
+    b = synth.tu_batch(shape, nb, seed=seed)
+    with tempfile.TemporaryDirectory() as d:
+        raw = rd.write_tu_files(b, d)                 # 0-based labels on disk, "u, v" with a blank: what the parser must accept
+        mine = tuio.load_tu_dir(raw)
+    ref = rd.igraphs_to_batch(rd.ref_tu_load(b, False))
+    batches_equal(mine, ref, ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel"))
+    if "vattr" in ref:
+        np.testing.assert_array_equal(mine["vattr"], ref["vattr"])
+    conj_graphs = rd.ref_tu_conjugate(rd.ref_tu_load(b, True))
+    files = rd.ref_tu_save(conj_graphs)
+    lines = tuio.tu_file_lines(rd.igraphs_to_batch(conj_graphs))
+    for suffix, ref_lines in files.items():
+        assert lines[suffix] == ref_lines, suffix
