@@ -424,6 +424,25 @@ int dn4gl_sort_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int
     return DN4GL_OK;
 }
 
+extern "C" size_t dn4gl_sort_rows_workspace_bytes(int64_t N) {
+    return align_up(static_cast<size_t>(N > 0 ? N : 1) * sizeof(int32_t), 256) + 256;
+}
+
+extern "C" int dn4gl_sort_csr_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int32_t *primary, void *ws,
+                                   size_t ws_bytes, int32_t *err_flag, void *stream) {
+    DN_ARG(N >= 0 && row_ptr != nullptr && N < INT32_MAX);
+    if (N == 0) return DN4GL_OK;
+    DN_ARG(items != nullptr);
+    WsCarver w(ws, ws_bytes);
+    int32_t *worklist = w.take<int32_t>(N);
+    int32_t *work_count = w.take<int32_t>(2);
+    if (!worklist || !work_count) {
+        dn4gl_set_error("dn4gl_sort_csr_rows: workspace too small");
+        return DN4GL_EWORKSPACE;
+    }
+    return dn4gl_sort_rows(row_ptr, N, items, primary, worklist, work_count, err_flag, as_stream(stream), nullptr, nullptr, false);
+}
+
 extern "C" size_t dn4gl_csr_workspace_bytes(int64_t N, int64_t E) {
     (void)E;
     size_t n = static_cast<size_t>(N > 0 ? N : 1);

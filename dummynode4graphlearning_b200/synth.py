@@ -180,3 +180,29 @@ def counting_batch(shape="small", batch_size=512, seed=0):
         gras.append(_directed_multigraph(rng, gn, gm, n_l, n_l))
     counts = rng.poisson(5.0, batch_size).astype(np.int64)
     return _pack(pats), _pack(gras), counts
+
+
+def random_subisomorphisms(pattern_b, graph_b, seed=0, max_rows=5):
+    """per sample a (S_b, np_b) matrix of graph-local node ids (S_b in 0..max_rows): random maps whose first pattern edge
+    is planted on a real graph edge, so that the match-weight targets (dataset.py:54-108) are not all zero.  They are
+    inputs for the weight kernels, not true subisomorphisms (the kernels do not care)."""
+    rng = np.random.default_rng(seed)
+    mats = []
+    for b in range(int(pattern_b["num_graphs"])):
+        pn0, gn0 = int(pattern_b["node_ptr"][b]), int(graph_b["node_ptr"][b])
+        pn, gn = int(pattern_b["node_ptr"][b + 1]) - pn0, int(graph_b["node_ptr"][b + 1]) - gn0
+        pe0, pe1 = int(pattern_b["edge_ptr"][b]), int(pattern_b["edge_ptr"][b + 1])
+        ge0, ge1 = int(graph_b["edge_ptr"][b]), int(graph_b["edge_ptr"][b + 1])
+        S = int(rng.integers(0, max_rows + 1))
+        m = np.zeros((S, pn), np.int64)
+        for s in range(S):
+            m[s] = rng.choice(gn, size=pn, replace=gn < pn)
+            if ge1 > ge0 and pe1 > pe0:
+                k = int(rng.integers(ge0, ge1))
+                j = int(rng.integers(pe0, pe1))
+                pu, pv = int(pattern_b["src"][j]) - pn0, int(pattern_b["dst"][j]) - pn0
+                m[s, pu] = int(graph_b["src"][k]) - gn0
+                if pv != pu:
+                    m[s, pv] = int(graph_b["dst"][k]) - gn0
+        mats.append(m)
+    return mats

@@ -68,6 +68,13 @@ int dn4gl_build_csr(const int32_t *key, const int32_t *val, int64_t N, int64_t E
 int dn4gl_build_csr_sorted(const int32_t *key, const int32_t *val, int64_t N, int64_t E, int32_t *row_ptr,
                            int32_t *col, int32_t *eid, int32_t *err_flag, void *stream);
 
+/* Sorts the items of every CSR row in place by (primary[item], item) (primary NULL: by item).  With primary = dst on the
+ * by-source CSR this is DGL's all_edges(order="srcdst") order (dataset.py:1508), also the order dn4gl_coalesce works in.
+ * ws: dn4gl_sort_rows_workspace_bytes(N).  Rows above DN4GL_MAX_ROW_DEGREE items raise DN4GL_ELIMIT through err_flag. */
+size_t dn4gl_sort_rows_workspace_bytes(int64_t N);
+int dn4gl_sort_csr_rows(const int32_t *row_ptr, int64_t N, int32_t *items, const int32_t *primary, void *ws,
+                        size_t ws_bytes, int32_t *err_flag, void *stream);
+
 
 /* list of rows with degree > threshold (for the heavy-row path of the aggregation kernels):
  * heavy_rows[cap], heavy_count[1]; cap >= E / threshold + 1; list order is unspecified.         */
@@ -179,6 +186,25 @@ int dn4gl_remove_loops_mark(int32_t B, const int32_t *edge_ptr, const int32_t *s
 int dn4gl_sub_eigen_bounds(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
                            const int32_t *in_deg, const int32_t *out_deg, int32_t *node_eig, int32_t *edge_eig,
                            void *stream);
+
+/* ---- match-weight targets from ground-truth subisomorphisms ------------------------------ */
+/* Batched compute_nodeseq_subisoweights (subgraph_isomorphism/dataset.py:54-61, called at :1491-1500): sample b owns
+ * S_b subisomorphisms, each a row of np_b graph-LOCAL node ids, concatenated in values[total] with val_ptr[B+1] giving
+ * each sample's first element.  weights[Ng] (zeroed here) += 1 per occurrence of a graph node.                         */
+int dn4gl_subiso_node_weights(int32_t B, const int32_t *val_ptr, const int32_t *values, int64_t total,
+                              const int32_t *g_node_ptr, int64_t Ng, int32_t *weights, void *stream);
+/* Batched compute_edgeseq_subisoweights (dataset.py:64-108, called at :1502-1520): for every subisomorphism and every
+ * pattern edge (u, v, l) whose run of consecutive equal (u, v) is the last one with that key (the reference's dict
+ * semantics), every graph edge (map[u], map[v]) with label l gets +1.  work_ptr[B+1] = prefix sums of S_b * m_b
+ * (m_b = pattern edges of sample b), total_work = work_ptr[B].  The graph side is given as its CSR by source whose
+ * rows are sorted by (dst, edge id) (dn4gl_build_csr(key = src) then dn4gl_sort_csr_rows(primary = dst), i.e.
+ * all_edges(order="srcdst")) plus dst / label in edge-id order.  active_ws: Ep int32 of scratch.  weights[Eg] zeroed here. */
+int dn4gl_subiso_edge_weights(int32_t B, const int32_t *work_ptr, int64_t total_work, const int32_t *val_ptr,
+                              const int32_t *values, const int32_t *p_node_ptr, const int32_t *p_edge_ptr,
+                              const int32_t *p_src, const int32_t *p_dst, const int32_t *p_elabel, int64_t Ep,
+                              int32_t *active_ws, const int32_t *g_node_ptr, const int32_t *g_out_ptr,
+                              const int32_t *g_out_items, const int32_t *g_dst, const int32_t *g_elabel,
+                              int64_t Eg, int32_t *weights, void *stream);
 
 /* ---- a3: PyG read_tu_data canonicalisation ------------------------------------------------- */
 /* remove_self_loops + coalesce [torch-geometric 2.0.2 read_tu_data, called from

@@ -84,6 +84,32 @@ def gen_augment():
     print("transforms.pt:", list(out))
 
 
+def gen_match_weights():
+    """the reference's numba loops compute_nodeseq_subisoweights / compute_edgeseq_subisoweights
+    (dataset.py:54-108) driven as calculate_node_weights / calculate_edge_weights do (:1491-1520), added to transforms.pt."""
+    path = os.path.join(OUT, "transforms.pt")
+    out = th.load(path, weights_only=False)
+    for shape, bs, seed in (("small", 16, 61), ("large", 2, 62)):
+        p, g, _ = synth.counting_batch(shape, bs, seed=seed)
+        mats = synth.random_subisomorphisms(p, g, seed=seed)
+        nw, ew = rd.ref_match_weights(mats, p, g)
+        out["match/%s" % shape] = dict(pattern=_np(p), graph=_np(g), mats=mats, node_weights=nw, edge_weights=ew)
+    # hand-made: repeated pattern pairs, consecutive (0,1)x2 and NON-consecutive (1,2) ... (1,2): only the last run counts
+    p = dict(num_graphs=1, node_ptr=np.array([0, 3], np.int32), edge_ptr=np.array([0, 5], np.int32),
+             src=np.array([0, 0, 1, 2, 1], np.int32), dst=np.array([1, 1, 2, 0, 2], np.int32),
+             vid=np.arange(3, dtype=np.int32), vlabel=np.zeros(3, np.int32), eid=np.arange(5, dtype=np.int32),
+             elabel=np.array([0, 1, 0, 0, 1], np.int32))
+    g = dict(num_graphs=1, node_ptr=np.array([0, 4], np.int32), edge_ptr=np.array([0, 8], np.int32),
+             src=np.array([3, 0, 1, 0, 1, 2, 0, 1], np.int32), dst=np.array([0, 1, 2, 1, 2, 0, 1, 2], np.int32),
+             vid=np.arange(4, dtype=np.int32), vlabel=np.zeros(4, np.int32), eid=np.arange(8, dtype=np.int32),
+             elabel=np.array([0, 0, 0, 1, 1, 0, 1, 0], np.int32))
+    mats = [np.array([[0, 1, 2], [0, 1, 2], [3, 0, 1]], np.int64)]
+    nw, ew = rd.ref_match_weights(mats, p, g)
+    out["match/runs"] = dict(pattern=_np(p), graph=_np(g), mats=mats, node_weights=nw, edge_weights=ew)
+    th.save(out, path)
+    print("transforms.pt:", list(out), "runs case:", nw.tolist(), ew.tolist())
+
+
 def _grads(model):
     return {n: (p.grad.clone() if p.grad is not None else None) for n, p in model.named_parameters()}
 
@@ -239,6 +265,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_transforms()
     gen_augment()
+    gen_match_weights()
     gen_counting()
     gen_counting_rgcn()
     gen_counting_compgcn()

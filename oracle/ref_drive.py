@@ -190,6 +190,31 @@ def ref_sub_norms_eigen(graph_b, self_loop=True):
                 edge_eigenv=th.cat([g.edata[C.EDGEEIGENV] for g in gs]).numpy())
 
 
+def ref_match_weights(mats, pattern_b, graph_b):
+    """the reference's numba loops (dataset.py:54-108) driven per sample exactly as calculate_node_weights /
+    calculate_edge_weights do (dataset.py:1491-1520): pattern edges in eid order, graph edges in srcdst order, result
+    scattered back through g_eid."""
+    df = refload.subgraph().dataset_funcs
+    nw, ew = [], []
+    for b, (P, G) in enumerate(zip(batch_to_dgl_list(pattern_b), batch_to_dgl_list(graph_b))):
+        m = np.asarray(mats[b], dtype=np.int64)
+        if m.size == 0:
+            nw.append(np.zeros(G.number_of_nodes(), np.int64))
+            ew.append(np.zeros(G.number_of_edges(), np.int64))
+            continue
+        nw.append(df.compute_nodeseq_subisoweights(G.number_of_nodes(), m))
+        C = refload.subgraph().constants
+        p_u, p_v, p_e = P.all_edges(form="all", order="eid")
+        p_el = P.edata[C.EDGELABEL][p_e]
+        g_u, g_v, g_e = G.all_edges(form="all", order="srcdst")
+        g_el = G.edata[C.EDGELABEL][g_e]
+        w = th.zeros(g_e.size(0), dtype=th.long)
+        w[g_e] = th.from_numpy(df.compute_edgeseq_subisoweights(p_u.numpy(), p_v.numpy(), p_el.numpy(), g_u.numpy(),
+                                                                g_v.numpy(), g_el.numpy(), m))
+        ew.append(w.numpy())
+    return np.concatenate(nw), np.concatenate(ew)
+
+
 def ref_sub_conjugate(b):
     """reference convert_conjugate_graph, DGL branch (utils/graph.py:77-175)."""
     gu = refload.subgraph().graph_utils

@@ -13,6 +13,8 @@ import os
 import sys
 import types
 
+import numpy as np
+
 REF_ROOT = os.environ.get("DN4GL_REFERENCE_ROOT", "/root/reference")
 _SUB = os.path.join(REF_ROOT, "subgraph_isomorphism")
 _CLS = os.path.join(REF_ROOT, "graph_classification")
@@ -81,6 +83,12 @@ def subgraph():
          "calculate_norms", "calculate_eigenvalues"],
         extra={"compute_norm": ns.graph_utils.compute_norm,
                "compute_largest_eigenvalues": ns.graph_utils.compute_largest_eigenvalues},
+    )
+    import numba
+    ns.dataset_funcs = _extract_functions(
+        os.path.join(_SUB, "dataset.py"),
+        ["long_item_bisect_left", "compute_nodeseq_subisoweights", "compute_edgeseq_subisoweights"],
+        extra={"numba": numba, "np": np},
     )
     _state["sub"] = ns
     return ns

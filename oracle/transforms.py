@@ -250,3 +250,52 @@ def spmm_sum(N, src, dst, x, self_scale=0.0):
     lib().orc_spmm_sum_f32(ctypes.c_int64(N), ctypes.c_int64(len(src)), int(x.shape[1]), _p(src), _p(dst),
                            x.ctypes.data_as(_F), ctypes.c_float(self_scale), out.ctypes.data_as(_F))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# match-weight targets (subgraph_isomorphism/dataset.py:54-108, 1491-1520), plain Python/numpy
+def subiso_node_weights(mats, graph_b):
+    """per sample: histogram of the subisomorphism entries over the graph's nodes (dataset.py:55-61)."""
+    w = np.zeros(len(graph_b["vlabel"]), np.int64)
+    for b, m in enumerate(mats):
+        n0 = int(graph_b["node_ptr"][b])
+        for row in np.asarray(m).reshape(-1, np.asarray(m).shape[-1]) if np.asarray(m).size else []:
+            for gu in row:
+                w[n0 + int(gu)] += 1
+    return w
+
+
+def subiso_edge_weights(mats, pattern_b, graph_b):
+    """per sample: compute_edgeseq_subisoweights (dataset.py:64-108) on the pattern's edges in edge-id order and the
+    graph's edges in (src, dst)-sorted order, scattered back to edge-id order (dataset.py:1506-1518)."""
+    W = np.zeros(len(graph_b["src"]), np.int64)
+    for b, m in enumerate(mats):
+        m = np.asarray(m)
+        if m.size == 0:
+            continue
+        pn0, pe0, pe1 = int(pattern_b["node_ptr"][b]), int(pattern_b["edge_ptr"][b]), int(pattern_b["edge_ptr"][b + 1])
+        gn0, ge0, ge1 = int(graph_b["node_ptr"][b]), int(graph_b["edge_ptr"][b]), int(graph_b["edge_ptr"][b + 1])
+        p_u, p_v = _i32(pattern_b["src"])[pe0:pe1] - pn0, _i32(pattern_b["dst"])[pe0:pe1] - pn0
+        p_el = _i32(pattern_b["elabel"])[pe0:pe1]
+        g_u, g_v = _i32(graph_b["src"])[ge0:ge1].astype(np.int64) - gn0, _i32(graph_b["dst"])[ge0:ge1].astype(np.int64) - gn0
+        g_el = _i32(graph_b["elabel"])[ge0:ge1]
+        order = np.lexsort((np.arange(ge1 - ge0), g_v, g_u))          # stable (src, dst) order
+        su, sv, sl = g_u[order], g_v[order], g_el[order]
+        runs = {}                                                      # (u, v) -> labels of the LAST run with that key
+        i = 0
+        while i < len(p_el):
+            j = i + 1
+            while j < len(p_el) and p_u[j] == p_u[i] and p_v[j] == p_v[i]:
+                j += 1
+            runs[(int(p_u[i]), int(p_v[i]))] = p_el[i:j]
+            i = j
+        w = np.zeros(ge1 - ge0, np.int64)
+        for row in m:
+            for (u, v), els in runs.items():
+                gu, gv = int(row[u]), int(row[v])
+                for k in np.flatnonzero((su == gu) & (sv == gv)):
+                    for e in els:
+                        if e == sl[k]:
+                            w[k] += 1
+        W[ge0 + order] = w
+    return W

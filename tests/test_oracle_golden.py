@@ -66,6 +66,16 @@ def test_augmentation_flags_match_reference_golden(gold_t, shape):
     np.testing.assert_array_equal(np.repeat(np.maximum(ee, 1), np.diff(d["edge_ptr"])), g["norms_self_loop"]["edge_eigenv"].ravel())
 
 
+@pytest.mark.parametrize("case", ["small", "large", "runs"])
+def test_match_weights_match_reference_golden(gold_t, case):
+    """node / edge match weights == the reference's numba loops (dataset.py:54-108)."""
+    g = gold_t["match/" + case]
+    np.testing.assert_array_equal(OT.subiso_node_weights(g["mats"], g["graph"]), g["node_weights"])
+    np.testing.assert_array_equal(OT.subiso_edge_weights(g["mats"], g["pattern"], g["graph"]), g["edge_weights"])
+    if case == "runs":      # worked by hand in oracle/gen_golden.py: a later run of the same (u, v) replaces the earlier one
+        assert g["edge_weights"].tolist() == [1, 2, 0, 3, 2, 2, 3, 0] and g["node_weights"].tolist() == [3, 3, 2, 1]
+
+
 def test_appB_literal_vectors():
     """SURVEY.md App. B, typed in by hand (independent of the generated fixtures)."""
     b = dict(num_graphs=2, node_ptr=np.array([0, 3, 5], np.int32), edge_ptr=np.array([0, 4, 6], np.int32),

@@ -135,3 +135,15 @@ def test_tu_io_live(shape, nb, seed):
     lines = tuio.tu_file_lines(rd.igraphs_to_batch(conj_graphs))
     for suffix, ref_lines in files.items():
         assert lines[suffix] == ref_lines, suffix
+
+
+@pytest.mark.parametrize("shape,bs,seed", [("small", 10, 501), ("large", 2, 503)])
+def test_match_weights_live(shape, bs, seed):
+    """oracle vs the reference's numba loops on fresh seeds."""
+    from oracle import ref_drive as rd
+    p, g, _ = synth.counting_batch(shape, bs, seed=seed)
+    mats = synth.random_subisomorphisms(p, g, seed=seed)
+    rn, re = rd.ref_match_weights(mats, p, g)
+    np.testing.assert_array_equal(OT.subiso_node_weights(mats, g), rn)
+    np.testing.assert_array_equal(OT.subiso_edge_weights(mats, p, g), re)
+    assert rn.sum() > 0 and (shape != "small" or re.sum() > 0)

@@ -314,3 +314,35 @@ def test_augmentation_flags_random_against_oracle(device):
         nn_, en = T.compute_norm(bg, sl)
         rn, re = O.compute_norm(ref_r, sl)
         assert np.array_equal(nn_.cpu().numpy(), rn) and np.array_equal(en.cpu().numpy(), re)
+
+
+@pytest.mark.parametrize("case", ["small", "large", "runs"])
+def test_match_weights_golden(device, case):
+    """SURVEY.md 8(f) rank 2 on the GPU: batched node / edge match weights, bit-exact with the reference's numba loops."""
+    from dummynode4graphlearning_b200 import transforms as T
+    from dummynode4graphlearning_b200.subgraph_isomorphism import matching as M
+    from helpers import load_golden
+    g = load_golden("transforms.pt")["match/" + case]
+    sub = M.pack_subisomorphisms(g["mats"], device)
+    pb, gb = T.to_device(g["pattern"], device), T.to_device(g["graph"], device)
+    assert np.array_equal(M.node_weights(sub, gb).cpu().numpy(), g["node_weights"])
+    assert np.array_equal(M.edge_weights(sub, pb, gb).cpu().numpy(), g["edge_weights"])
+
+
+def test_match_weights_batch512_against_oracle(device):
+    """C3 batch size, up to 40 subisomorphisms per sample, against the Python oracle; empty samples give zeros."""
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.subgraph_isomorphism import matching as M
+    from oracle import transforms as O
+    p, g, _ = synth.counting_batch("small", 512, seed=88)
+    mats = synth.random_subisomorphisms(p, g, seed=9, max_rows=40)
+    mats[3] = np.zeros((0, mats[3].shape[1]), np.int64)
+    sub = M.pack_subisomorphisms(mats, device)
+    pb, gb = T.to_device(p, device), T.to_device(g, device)
+    nw, ew = M.node_weights(sub, gb), M.edge_weights(sub, pb, gb)
+    assert np.array_equal(nw.cpu().numpy(), O.subiso_node_weights(mats, g))
+    assert np.array_equal(ew.cpu().numpy(), O.subiso_edge_weights(mats, p, g))
+    n0, n1 = int(g["node_ptr"][3]), int(g["node_ptr"][4])
+    assert int(nw[n0:n1].sum()) == 0 and int(ew.sum()) > 0
+    empty = M.pack_subisomorphisms([np.zeros((0, m.shape[1]), np.int64) for m in mats], device)
+    assert int(M.node_weights(empty, gb).sum()) == 0 and int(M.edge_weights(empty, pb, gb).sum()) == 0
