@@ -135,6 +135,7 @@ class ClockSampler:
     too short for a freshly spawned `nvidia-smi -lms` to report anything); falls back to one `nvidia-smi` query taken
     while the GPU is still busy if NVML cannot be loaded."""
 
+    PERIOD = 0.05     # NVML queries take the driver's lock: at a 10 ms period they stalled single steps for 5-60 ms
     REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
                ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
                ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
@@ -155,6 +156,9 @@ class ClockSampler:
                 self.h = nv.nvmlDeviceGetHandleByIndex(index)
             self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
             self.nv = nv
+            self._sample()            # first calls (lazy initialisation inside NVML) happen before the timed region ...
+            self.sm.clear()           # ... and are not counted as a sample under load
+            self.reasons.clear()
         except Exception as e:   # noqa: BLE001
             self.err = "nvml: %s" % e
         self.index = index
@@ -181,7 +185,7 @@ class ClockSampler:
             except Exception as e:   # noqa: BLE001
                 self.err = "nvml: %s" % e
                 return
-            self._stop.wait(0.01)
+            self._stop.wait(self.PERIOD)
 
     def _smi_once(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -201,10 +205,15 @@ class ClockSampler:
         """call while the last timed work is still in flight or just done"""
         if self.nv is None:
             self._smi_once()
+        else:
+            try:
+                self._sample()        # one more while the last timed steps are still in flight
+            except Exception:   # noqa: BLE001
+                pass
         self._stop.set()
         self.t.join(timeout=2)
         out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
-               "samples": len(self.sm), "reasons": sorted(self.reasons), "how": "nvml thread, 10 ms period" if self.nv else "nvidia-smi"}
+               "samples": len(self.sm), "reasons": sorted(self.reasons), "how": "nvml thread, 50 ms period" if self.nv else "nvidia-smi"}
         if self.err and not self.sm:
             out["error"] = self.err
         return out
@@ -273,42 +282,71 @@ def ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n_warm = max(a.warmup, 10)   # first step eager, second captures the CUDA graph, the rest settle the caching allocator
+    n_warm = max(a.warmup, 30)   # first step eager, second captures the CUDA graph, the rest settle the caching allocator
+                                 # (two streams, up to two steps in flight: a cudaMalloc inside the timed loop costs 2-10 ms)
     for _ in range(n_warm):
         flush.fill_(1)
         pipe.step_resident(dev_batch, assume_ready=True)   # the raw batch has been resident since before the warm-up
+    # long-lived objects (modules, captured graphs, static buffers) leave the cyclic collector's working set: a
+    # generation-2 pass over them inside the timed loop showed up as 2-10 ms host stalls (steps are host-bound)
+    import gc
+    gc.collect()
+    gc.freeze()
     # ---- timed region: EXACTLY K steps, device-timed ----------------------------------------------------
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
+    clocks = ClockSampler(local) if (rank == 0 and not os.environ.get("DN4GL_NO_CLOCKS")) else None
     k0 = L.kernel_launches() + pipe.replayed_library_kernels()
+    nmalloc = lambda: int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))   # cudaMalloc calls so far
+    m0 = nmalloc()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    trace = [] if os.environ.get("DN4GL_BENCH_TRACE") else None
     for _ in range(a.steps):
         flush.fill_(1)
         loss = pipe.step_resident(dev_batch, assume_ready=True)
+        if trace is not None:
+            trace.append(time.perf_counter())
     e1.record()
     barrier()
     launches = L.kernel_launches() + pipe.replayed_library_kernels() - k0
+    m1 = nmalloc()
     ms = max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
     value = a.graphs * world / (ms * 1e-3)
+    if trace:
+        print("host ms per step:", " ".join("%.2f" % (1e3 * (b - a_)) for a_, b in zip(trace[:-1], trace[1:])), file=sys.stderr)
 
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------------------
-    for _ in range(5):
-        pipe.step(host)
+    pending = None
+    for _ in range(15):               # warm-up in the same software-pipelined pattern as the timed loop (two steps in flight)
+        nxt = pipe.step_async(host)
+        if pending is not None:
+            pending.result()
+        pending = nxt
+    pending.result()
     barrier()
     t0 = time.perf_counter()
     pending = None
+    etrace = [] if trace is not None else None
     for _ in range(a.steps):          # software-pipelined: submit step k (H2D, transform, train, D2H of its loss),
         flush.fill_(1)                # then read the loss of step k-1 on the host -- every loss is read, in order
+        ta = time.perf_counter()
         nxt = pipe.step_async(host)
+        tb = time.perf_counter()
         if pending is not None:
             last = pending.result()
         pending = nxt
+        if etrace is not None:
+            etrace.append((tb - ta, time.perf_counter() - tb))
     last = pending.result()
     torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev) / a.steps
+    t_end = time.perf_counter()
+    clk = clocks.stop() if clocks else None      # sampled over both timed regions (+ one sample right at their end)
+    e2e_ms = max_over_ranks((t_end - t0) * 1e3, dev) / a.steps
     e2e_value = a.graphs * world / (e2e_ms * 1e-3)
-    clk = clocks.stop() if clocks else None      # sampled over both timed regions (device-timed steps and e2e steps)
+    m2 = nmalloc()
+    if etrace:
+        print("e2e submit ms:", " ".join("%.2f" % (1e3 * x) for x, _ in etrace), file=sys.stderr)
+        print("e2e result ms:", " ".join("%.2f" % (1e3 * y) for _, y in etrace), file=sys.stderr)
 
     # ---- per-entry-point device times + breakdown (instrumented pass, not part of `value`) -----------------
     timer = EntryPointTimer()
@@ -329,10 +367,31 @@ def ours(a):
         tr_ms.append(tr0.elapsed_time(tr1)); tn_ms.append(tr1.elapsed_time(tn1))
     L.profiler = None
     per_entry = timer.summary()
-    # cold-cache duration of the dominant kernel: aggregation launches alone with an L2 flush before each
+    # ---- device duration of the dominant kernel (K1, sum aggregation) ---------------------------------------------
     from dummynode4graphlearning_b200 import ops
     s = data.structure
     N, E = s.num_nodes, int(s.csr_in.nnz)
+    peaks, which = measured_peaks()
+
+    def k1_back_to_back(csr_in, csr_out, n_rows, D, launches=64):
+        """average device time of one launch: `launches` aggregation launches queued back to back between two events
+        on the launching stream, each reading a different feature matrix and writing a different output out of a pool
+        larger than L2 (>= 320 MB), so every launch finds its operands in HBM, not in L2."""
+        per = 2 * 4 * D * n_rows
+        nbuf = max(3, -(-(320 << 20) // per))
+        xs = [torch.rand((n_rows, D), device=dev) for _ in range(nbuf)]
+        for i in range(min(nbuf, 4)):
+            ops.spmm_sum(xs[i], csr_in, csr_out, 1.0)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for i in range(launches):
+            ops.spmm_sum(xs[i % nbuf], csr_in, csr_out, 1.0)
+        b1.record()
+        torch.cuda.synchronize()
+        return 1e3 * b0.elapsed_time(b1) / launches      # us
+
+    # (a) one launch at a time behind an L2 flush (CUDA-event resolution ~2 us, includes the launch gap)
     xh = torch.rand((N, HID), device=dev)
     iso = []
     for _ in range(10):
@@ -343,21 +402,61 @@ def ours(a):
         a1.record()
         torch.cuda.synchronize()
         iso.append(a0.elapsed_time(a1))
-    peaks, which = measured_peaks()
+    del xh
+    # (b) back to back over operands larger than L2: the number `achieved` is computed from
+    b2b_us = k1_back_to_back(s.csr_in, s.csr_out, N, HID)
     agg_bytes = 4 * HID * N * 2 + 4 * E + 4 * (N + 1)        # compulsory traffic
     agg_name = "dn4gl_spmm_tiled_f32" if ("dn4gl_spmm_tiled_f32[D=%d]" % HID) in per_entry else "dn4gl_spmm_sum_f32"
     in_step = per_entry.get("%s[D=%d]" % (agg_name, HID), {"avg_us": float("nan"), "calls": 0})
-    achieved = agg_bytes / (in_step["avg_us"] * 1e-6) / 1e9
+    achieved = agg_bytes / (b2b_us * 1e-6) / 1e9
     kern = ("spmm_pipe_kernel<8,1>: producer/consumer ring of cp.async.bulk staged tiles" if agg_name.endswith("tiled_f32")
             else "spmm_rows_kernel<8,1> + spmm_heavy_kernel<8,1>")
+    traffic = traffic_src = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "k1_c2_ncu_traffic.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+    except Exception:   # noqa: BLE001
+        pass
     roofline = {"kernel": "%s (%s), D=32, N=%d, E=%d" % (agg_name, kern, N, E),
                 "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
-                "algorithmic_bytes_per_launch": agg_bytes, "avg_launch_us_in_step": in_step["avg_us"],
-                "launches_timed": in_step["calls"], "cold_l2_launch_us": 1e3 * statistics.median(iso),
-                "cold_l2_gbs": agg_bytes / (statistics.median(iso) * 1e-3) / 1e9,
-                "gather_effective_gbs": (4 * HID * (E + N) + 4 * E + 4 * (N + 1)) / (in_step["avg_us"] * 1e-6) / 1e9,
-                "traffic": None}
+                "algorithmic_bytes_per_launch": agg_bytes,
+                "how": "64 launches back to back between two CUDA events on the launching stream, operands rotated through a "
+                       ">= 320 MB pool (larger than L2)",
+                "avg_launch_us": b2b_us,
+                "in_step_eager_us": in_step["avg_us"], "in_step_eager_calls": in_step["calls"],
+                "in_step_eager_note": "event pair around each C-ABI call of an eager step: includes the host launch gap",
+                "cold_l2_single_launch_us": 1e3 * statistics.median(iso),
+                "gather_effective_gbs": (4 * HID * (E + N) + 4 * E + 4 * (N + 1)) / (b2b_us * 1e-6) / 1e9,
+                "traffic": traffic, "traffic_source": traffic_src}
+    # the same kernel at a C5 sweep point (BASELINE.json configs[4]): 16 384 MUTAG-shaped graphs + dummy, hidden 64
+    roofline_c5 = None
+    if rank == 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from agg_sweep import replicate
+            from dummynode4graphlearning_b200.graph import BatchedGraph
+            raw5 = replicate(synth.tu_batch("mutag", 1024, seed=0), 16)
+            d5 = T.tu_add_dummy(T.to_device({k: v for k, v in raw5.items() if k != "vattr"}, dev))
+            g5 = BatchedGraph(d5["src"], d5["dst"], d5["node_ptr"], d5["edge_ptr"])
+            g5.host_ptrs()
+            N5, E5, D5 = g5.number_of_nodes(), g5.number_of_edges(), 64
+            us5 = k1_back_to_back(g5.csr_in, g5.csr_out, N5, D5, launches=32)
+            b5 = 4 * D5 * N5 * 2 + 4 * E5 + 4 * (N5 + 1)
+            roofline_c5 = {"workload": "c5 point: 16384 MUTAG-shaped graphs + dummy, hidden 64", "N": N5, "E": E5,
+                           "algorithmic_bytes_per_launch": b5, "avg_launch_us": us5, "achieved": b5 / (us5 * 1e-6) / 1e9,
+                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": b5 / (us5 * 1e-6) / 1e9 / peaks["hbm_gbs"]}
+            del g5, d5
+        except Exception as ex:   # noqa: BLE001
+            roofline_c5 = {"error": str(ex)[:200]}
+    # the tensor-core MLP stages of the same step (HBM-bound too): algorithmic GB/s from the
+    # eager in-step event pairs (upper bound on the duration)
+    mlp = {}
+    for name, nbytes in (("dn4gl_lin_fwd_f32", 4 * N * (HID + HID)), ("dn4gl_lin_bwd_f32", 4 * N * (2 * HID + 2 * HID))):
+        if name in per_entry:
+            mlp[name] = {"in_step_eager_us": round(per_entry[name]["avg_us"], 2), "algorithmic_bytes": nbytes,
+                         "gbs": round(nbytes / (per_entry[name]["avg_us"] * 1e-6) / 1e9, 1)}
 
     if rank != 0:
         _finish(pipe, world)
@@ -378,9 +477,10 @@ def ours(a):
                 "h2d_bytes_per_step": host_bytes(host), "d2h_bytes_per_step": 4 + 8 + 4,
                 "how": "ClassificationPipeline.step_async(host) per step, loss of step k-1 read on the host after step k "
                        "is submitted (all losses read, last one before the clock stops)"},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_c5": roofline_c5, "mlp_stages": mlp, "cpu_baseline": cpu,
         "breakdown": {"transform_ms": statistics.mean(tr_ms), "train_ms": statistics.mean(tn_ms),
-                      "own_kernels_ms_per_step": own_ms, "conj_nodes": N, "conj_edges": E,
+                      "own_kernels_ms_per_step": own_ms,
+                      "cudaMalloc_calls_in_timed_region": m1 - m0, "cudaMalloc_calls_in_e2e_region": m2 - m1, "conj_nodes": N, "conj_edges": E,
                       "final_loss": float(loss.item()), "e2e_last_loss": last,
                       "entry_points": {k: {"calls_per_step": v["calls"] / max(len(tr_ms), 1), "avg_us": round(v["avg_us"], 2)}
                                        for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1]["total_ms"])}},

@@ -173,6 +173,7 @@ class ClassificationPipeline:
         self._graphs, self._max_graphs = {}, max_graphs
         self.overlap = bool(self.cuda_graphs if overlap is None else overlap) and self.device.type == "cuda"
         self._tstream = None
+        self._inflight = []      # completion events of the train steps queued so far (bounded lead, see _throttle)
 
     def _transform_stream(self):
         if self._tstream is None:
@@ -235,6 +236,20 @@ class ClassificationPipeline:
             ent = self._graphs[sig] = _CapturedStep(self, data)
         return ent.run(data)
 
+    def _throttle(self):
+        """bounds the host's lead over the train stream to ONE step: before the transform of step k+1 starts, the train
+        step k-1 must have finished (step k may still be running -- that is the overlap).  Without the bound the host
+        (whose transform only synchronises with its own stream) runs several steps ahead whenever the train stream is
+        the slower side; every step in flight pins a full set of transform outputs, the caching allocator answers with
+        cudaMalloc, and single steps stall for 5-50 ms (profiles/r1f)."""
+        while len(self._inflight) >= 2:
+            self._inflight.pop(0).synchronize()
+
+    def _mark_step(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self._inflight.append(ev)
+
     def _hand_over(self, data, tstream):
         """transform output (allocated and produced on `tstream`) -> consumable on the current (train) stream."""
         main = torch.cuda.current_stream()
@@ -255,11 +270,14 @@ class ClassificationPipeline:
         if not self.overlap:
             return self.train_on(self.transform(dev_batch))
         ts = self._transform_stream()
+        self._throttle()
         if not assume_ready:
             ts.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(ts):
             data = self.transform(dev_batch)
-        return self.train_on(self._hand_over(data, ts))
+        loss = self.train_on(self._hand_over(data, ts))
+        self._mark_step()
+        return loss
 
     def _upload(self, host_batch):
         dev = upload(host_batch, self.device)
@@ -273,9 +291,12 @@ class ClassificationPipeline:
         if not self.overlap:
             return PendingLoss(self.step_resident(self._upload(host_batch)))
         ts = self._transform_stream()
+        self._throttle()
         with torch.cuda.stream(ts):          # the upload is ordered on the transform stream: no wait on the train stream
             data = self.transform(self._upload(host_batch))
-        return PendingLoss(self.train_on(self._hand_over(data, ts)))
+        loss = self.train_on(self._hand_over(data, ts))
+        self._mark_step()
+        return PendingLoss(loss)
 
     def step(self, host_batch):
         """host buffers in, python float out: H2D + transform + train step + D2H of the loss (blocking)."""
