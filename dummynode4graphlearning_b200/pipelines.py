@@ -367,9 +367,10 @@ class _CapturedCountingStep:
 
 class CountingPipeline:
     def __init__(self, model, optimizer, config, add_dummy=True, rep_reg_w=0.0, neg_slp=0.01, max_grad_norm=8.0,
-                 cuda_graphs=None, max_graphs=8):
-        """config: the dataset maxima BEFORE augmentation (max_npv ... max_ngel).  cuda_graphs: as in
-        ClassificationPipeline (default: on exactly when the optimizer was built with capturable=True)."""
+                 cuda_graphs=None, max_graphs=8, overlap=None):
+        """config: the dataset maxima BEFORE augmentation (max_npv ... max_ngel).  cuda_graphs / overlap: as in
+        ClassificationPipeline (defaults: graphs on exactly when the optimizer was built with capturable=True, the
+        augmentation + CSR builds on a second stream exactly when graphs are on)."""
         self.model, self.opt, self.cfg, self.add_dummy = model, optimizer, config, add_dummy
         self.rep_reg_w, self.neg_slp, self.max_grad_norm = rep_reg_w, neg_slp, max_grad_norm
         self.bucket = getattr(optimizer, "bucket", None) or GradientBucket(model.parameters())
@@ -380,6 +381,12 @@ class CountingPipeline:
         if self.cuda_graphs and not capturable:
             raise ValueError("cuda_graphs=True needs an optimizer built with capturable=True")
         self._graphs, self._max_graphs = {}, max_graphs
+        self.overlap = bool(self.cuda_graphs if overlap is None else overlap) and self.device.type == "cuda"
+        self._tstream, self._inflight = None, []
+
+    _transform_stream = ClassificationPipeline._transform_stream
+    _throttle = ClassificationPipeline._throttle
+    _mark_step = ClassificationPipeline._mark_step
 
     def transform(self, p_dev, g_dev):
         c = self.cfg
@@ -438,9 +445,30 @@ class CountingPipeline:
             ent = self._graphs[sig] = _CapturedCountingStep(self, pattern, graph, counts)
         return ent.run(pattern, graph, counts)
 
-    def step_resident(self, p_dev, g_dev, counts_dev):
-        pattern, graph = self.transform(p_dev, g_dev)
-        return self.train_on(pattern, graph, counts_dev)
+    def step_resident(self, p_dev, g_dev, counts_dev, assume_ready=False):
+        """see ClassificationPipeline.step_resident: with ``overlap`` the augmentation + CSR builds of this mini-batch run
+        on the second stream while the previous train step is still executing."""
+        if not self.overlap:
+            pattern, graph = self.transform(p_dev, g_dev)
+            return self.train_on(pattern, graph, counts_dev)
+        main = torch.cuda.current_stream()
+        ts = self._transform_stream()
+        self._throttle()
+        if not assume_ready:
+            ts.wait_stream(main)
+        with torch.cuda.stream(ts):
+            pattern, graph = self.transform(p_dev, g_dev)
+            for g in (pattern, graph):       # everything the captured step copies out of the batch exists before the hand-over
+                g.csr_in, g.csr_out
+        done = torch.cuda.Event()
+        done.record(ts)
+        main.wait_event(done)
+        for t in _graph_tensors(pattern)[0] + _graph_tensors(graph)[0]:
+            if t is not None:
+                t.record_stream(main)
+        loss = self.train_on(pattern, graph, counts_dev)
+        self._mark_step()
+        return loss
 
     def step(self, p_host, g_host, counts_host):
         p_dev, g_dev = upload(p_host, self.device), upload(g_host, self.device)

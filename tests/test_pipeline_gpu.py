@@ -194,3 +194,37 @@ def test_overlapped_transform_stream_equals_serial():
                 assert float((s0[k] - s1[k]).abs().max()) / denom <= 1e-5, (host_api, k)
             else:
                 assert torch.equal(s0[k], s1[k]), (host_api, k)
+
+
+def test_counting_overlap_and_flat_adamw_equal_serial():
+    """CountingPipeline: augmentation on the second stream + FlatAdam(AdamW, amsgrad) under graph replay == the serial
+    eager pipeline with the same optimizer."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from bench_counting import build
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.optim import FlatAdam
+    from dummynode4graphlearning_b200.pipelines import CountingPipeline
+    dev = torch.device("cuda:0")
+
+    def run(graphs, overlap):
+        model, cfg, _ = build("DMPNN", "small", dict(node_pred=True, edge_pred=True), dev)
+        opt = FlatAdam(model.parameters(), lr=1e-3, weight_decay=1e-2, amsgrad=True, decoupled_weight_decay=True)
+        pipe = CountingPipeline(model, opt, cfg, add_dummy=True, rep_reg_w=1e-3, cuda_graphs=graphs, overlap=overlap)
+        batches = []
+        for seed in (1, 2):
+            p, g, c = synth.counting_batch("small", 24, seed=seed)
+            batches.append((T.to_device(p, dev), T.to_device(g, dev), torch.from_numpy(c).to(dev)))
+        torch.cuda.synchronize()
+        outs = [pipe.step_resident(*batches[i % 2 if i < 4 else 0], assume_ready=True).clone() for i in range(8)]
+        torch.cuda.synchronize()
+        return [float(o.item()) for o in outs], {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    l0, s0 = run(False, False)
+    l1, s1 = run(True, True)
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (l0, l1)
+    for k in s0:
+        if s0[k].is_floating_point():
+            denom = float(s0[k].abs().max().clamp_min(1e-12))
+            assert float((s0[k] - s1[k]).abs().max()) / denom <= 1e-4, k

@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--opt", default="flat", choices=["flat", "torch"], help="FlatAdam (dn4gl_adam_f32) or torch.optim.AdamW")
+    ap.add_argument("--no-overlap", action="store_true")
     a = ap.parse_args()
     import torch.distributed as dist
     from dummynode4graphlearning_b200 import synth, transforms as T
@@ -53,21 +55,26 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     name, shape, bs, over = CFG[a.config]
     model, cfg, kw = build(name, shape, over, dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, amsgrad=True, capturable=True)   # train.py:1408-1411 (AdamW, amsgrad)
-    pipe = CountingPipeline(model, opt, cfg, add_dummy=True, rep_reg_w=1e-3, cuda_graphs=not a.no_graphs)
+    if a.opt == "flat":     # train.py:1408-1411 (AdamW, amsgrad) as one flat-buffer kernel
+        from dummynode4graphlearning_b200.optim import FlatAdam
+        opt = FlatAdam(model.parameters(), lr=1e-3, weight_decay=1e-2, amsgrad=True, decoupled_weight_decay=True)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, amsgrad=True, capturable=True)
+    pipe = CountingPipeline(model, opt, cfg, add_dummy=True, rep_reg_w=1e-3, cuda_graphs=not a.no_graphs,
+                            overlap=False if a.no_overlap else None)
     pipe.global_batch = bs * world
     p, g, counts = synth.counting_batch(shape, bs, seed=rank)
     pd_, gd_ = T.to_device(p, dev), T.to_device(g, dev)
     cd = torch.from_numpy(counts).to(dev)
     for _ in range(a.warmup):
-        loss = pipe.step_resident(pd_, gd_, cd)
+        loss = pipe.step_resident(pd_, gd_, cd, assume_ready=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        loss = pipe.step_resident(pd_, gd_, cd)
+        loss = pipe.step_resident(pd_, gd_, cd, assume_ready=True)
     e1.record()
     if world > 1:
         dist.barrier()
@@ -75,7 +82,7 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
     if rank == 0:
         print(json.dumps({"config": a.config, "model": name, "shape": shape, "graphs_per_gpu": bs, "n_gpus": world,
-                          "cuda_graphs": not a.no_graphs, "ms_per_step": ms, "graphs_per_s": bs * world / (ms * 1e-3),
+                          "cuda_graphs": not a.no_graphs, "optimizer": a.opt, "overlap": pipe.overlap, "ms_per_step": ms, "graphs_per_s": bs * world / (ms * 1e-3),
                           "loss": float(loss.item()), "replayed_library_kernels": pipe.replayed_library_kernels()}), flush=True)
     if world > 1:
         pipe._graphs.clear()
