@@ -228,3 +228,31 @@ def test_counting_overlap_and_flat_adamw_equal_serial():
         if s0[k].is_floating_point():
             denom = float(s0[k].abs().max().clamp_min(1e-12))
             assert float((s0[k] - s1[k]).abs().max()) / denom <= 1e-4, k
+
+
+def test_flat_adam_parameter_without_gradient_and_lr_change():
+    """a parameter that never receives a gradient stays out of the flat buffers (as torch skips it); one that misses a
+    gradient in a later step is treated as zero gradient; a changed learning rate reaches the kernel."""
+    from dummynode4graphlearning_b200.optim import FlatAdam
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    a, b, c = (torch.nn.Parameter(torch.randn(5, 3, device=dev)) for _ in range(3))
+    ra, rb = (torch.nn.Parameter(p.detach().clone()) for p in (a, b))
+    ours = FlatAdam([a, b, c], lr=0.1)
+    ref = torch.optim.Adam([ra, rb], lr=0.1, foreach=False)
+    c0 = c.detach().clone()
+    for step in range(4):
+        if step == 2:
+            for o in (ours, ref):
+                o.param_groups[0]["lr"] = 0.01
+        ga, gb = torch.randn(5, 3, device=dev), torch.randn(5, 3, device=dev)
+        ours.zero_grad(); ref.zero_grad()
+        a.grad, ra.grad = ga.clone(), ga.clone()
+        if step != 1:
+            b.grad, rb.grad = gb.clone(), gb.clone()
+        else:
+            rb.grad = torch.zeros_like(rb)        # torch would skip a None gradient; FlatAdam treats it as zero
+        ours.step(); ref.step()
+    assert torch.equal(c.detach(), c0) and c.grad is None
+    for x, y in ((a, ra), (b, rb)):
+        assert float((x.detach() - y.detach()).abs().max()) <= 2e-6 * float(y.detach().abs().max())

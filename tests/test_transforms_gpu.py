@@ -346,3 +346,34 @@ def test_match_weights_batch512_against_oracle(device):
     assert int(nw[n0:n1].sum()) == 0 and int(ew.sum()) > 0
     empty = M.pack_subisomorphisms([np.zeros((0, m.shape[1]), np.int64) for m in mats], device)
     assert int(M.node_weights(empty, gb).sum()) == 0 and int(M.edge_weights(empty, pb, gb).sum()) == 0
+
+
+def test_augmentation_and_match_weights_empty_inputs(device):
+    """edge cases: graphs without edges inside a batch, a batch without any edge, no subisomorphisms at all."""
+    from dummynode4graphlearning_b200 import transforms as T
+    from dummynode4graphlearning_b200.graph import BatchedGraph
+    from dummynode4graphlearning_b200.subgraph_isomorphism import matching as M
+    from helpers import batches_equal
+    from oracle import transforms as O
+
+    b = dict(num_graphs=3, node_ptr=np.array([0, 2, 5, 6], np.int32), edge_ptr=np.array([0, 0, 3, 3], np.int32),
+             src=np.array([2, 3, 4], np.int32), dst=np.array([3, 3, 2], np.int32), vid=np.array([0, 1, 0, 1, 2, 0], np.int32),
+             vlabel=np.zeros(6, np.int32), eid=np.arange(3, dtype=np.int32), elabel=np.array([1, 0, 1], np.int32))
+    rev = T.sub_add_reversed(T.to_device(b, device), 7, 3)
+    batches_equal(rev, O.sub_add_reversed(b, 7, 3), ("edge_ptr", "src", "dst", "eid", "elabel", "e_is_reversed"))
+    batches_equal(T.sub_remove_loops(T.to_device(b, device)), O.sub_remove_loops(b), ("edge_ptr", "src", "dst", "eid", "elabel"))
+    empty = dict(b, edge_ptr=np.zeros(4, np.int32), src=np.zeros(0, np.int32), dst=np.zeros(0, np.int32),
+                 eid=np.zeros(0, np.int32), elabel=np.zeros(0, np.int32))
+    r0 = T.sub_add_reversed(T.to_device(empty, device), 7, 3)
+    assert r0["src"].numel() == 0 and r0["edge_ptr"].cpu().tolist() == [0, 0, 0, 0]
+    l0 = T.sub_remove_loops(T.to_device(empty, device))
+    assert l0["src"].numel() == 0 and l0["edge_ptr"].cpu().tolist() == [0, 0, 0, 0]
+    bg = BatchedGraph.from_batch(T.to_device(b, device), device)
+    ne, ee = T.compute_largest_eigenvalues(bg)
+    rne, ree = O.compute_largest_eigenvalues(b)
+    assert np.array_equal(ne.cpu().numpy(), rne) and np.array_equal(ee.cpu().numpy(), ree) and rne[0] == 0 and rne[2] == 0
+    sub = M.pack_subisomorphisms([np.zeros((0, 2), np.int64), np.array([[0, 1, 2]], np.int64), np.zeros((0, 1), np.int64)], device)
+    gb = T.to_device(b, device)
+    assert M.node_weights(sub, gb).cpu().tolist() == [0, 0, 1, 1, 1, 0]
+    ew = M.edge_weights(sub, gb, gb)          # the batch as its own pattern: the identity map matches every edge once
+    assert ew.cpu().tolist() == O.subiso_edge_weights([np.zeros((0, 2)), np.array([[0, 1, 2]]), np.zeros((0, 1))], b, b).tolist() == [1, 1, 1]
