@@ -12,7 +12,7 @@ import re
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 HEADER = os.path.join(_ROOT, "include", "dn4gl.h")
-SO_PATH = os.path.join(_PKG, "csrc", "libdn4gl.so")
+SO_PATH = os.environ.get("DN4GL_LIB") or os.path.join(_PKG, "csrc", "libdn4gl.so")   # DN4GL_LIB: debug builds (tools/)
 
 
 class Dn4glError(RuntimeError):

@@ -60,6 +60,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// ---- optional per-CTA timeline (debug build -DDN4GL_TIMELINE = libdn4gl_tl.so, tools/k1_timeline.py): %globaltimer
+// stamps of the first consumer warp's lane 0 and of the producer, 32 slots per CTA: [0] entry, [1] after the prologue,
+// then per work item two stamps (full barrier passed, item done); producer stamps in slots 16.. (stage free).
+// Compiled out of the product build.
+#ifdef DN4GL_TIMELINE
+__device__ unsigned long long g_timeline[148 * 32];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_STAMP(slot) do { if ((slot) < 32 && blockIdx.x < 148) g_timeline[blockIdx.x * 32 + (slot)] = gtime(); } while (0)
+#define TL_STAMP_LO(slot) do { if ((slot) < 16) TL_STAMP(slot); } while (0)
+extern "C" int dn4gl_debug_read_timeline(unsigned long long *host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(unsigned long long) * 148 * 32) == cudaSuccess ? 0 : -2;
+}
+extern "C" int dn4gl_debug_clear_timeline(void) {
+    static unsigned long long zeros[148 * 32];
+    return cudaMemcpyToSymbol(g_timeline, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -2;
+}
+#else
+#define TL_STAMP(slot) do { } while (0)
+#define TL_STAMP_LO(slot) do { } while (0)
+#endif
+
 template <int NCW>
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
 
@@ -372,6 +397,7 @@ spmm_pipe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict_
                  const float *__restrict__ eps_dev, int smem_bytes, int stages, int nnz_per_row) {
     constexpr int DV = LANES * VEC;
     if (eps_dev != nullptr) self_scale = 1.f + __ldg(eps_dev);   // trainable GIN eps lives on the device
+    if (threadIdx.x == 32) TL_STAMP(0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[TP_MAX_STAGES], empty_bar[TP_MAX_STAGES];
     const TileCfg L = tile_cfg(smem_bytes, stages, DV, nnz_per_row);
@@ -386,14 +412,17 @@ spmm_pipe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict_
     __syncthreads();
     const int H = (heavy_list != nullptr && heavy_count != nullptr) ? __ldg(heavy_count) : 0;
     const int total = H + num_tiles;
+    if (threadIdx.x == 32) TL_STAMP(1);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ producer (one lane)
         if (lane != 0) return;
         int s = 0;
         uint32_t use = 0;   // how many times stage s has been filled before
+        [[maybe_unused]] int tl_p = 16;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1u);
+            TL_STAMP(tl_p); ++tl_p;
             bool issued = false;
             if (t >= H) {
                 const int4 td = __ldg(tiles + (t - H));
@@ -428,16 +457,19 @@ spmm_pipe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict_
     const int cw = warp - 1;
     int s = 0;
     uint32_t use = 0;
+    [[maybe_unused]] int tl_c = 2;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
         unsigned char *base = smem_raw + static_cast<size_t>(s) * L.stage_bytes;
         if (t < H) {
             const int row = __ldg(heavy_list + t);
             mbar_wait(&full_bar[s], use & 1u);
+            if (threadIdx.x == 32) TL_STAMP_LO(tl_c);
             process_heavy_row<LANES, VEC, NCW>(row_ptr, col, x, out, row, self_scale, reinterpret_cast<float4 *>(base), cw, lane);
         } else {
             const int4 td = __ldg(tiles + (t - H));
             const int rows = td.y - td.x;
             mbar_wait(&full_bar[s], use & 1u);
+            if (threadIdx.x == 32) TL_STAMP_LO(tl_c);
             if (rows > 0) {
                 const bool open = td.w < 0;                          // cut inside a graph or not verified self-contained
                 const bool cut = heavy_list != nullptr && open;      // its long rows are on the heavy list
@@ -462,6 +494,8 @@ spmm_pipe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict_
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (threadIdx.x == 32) TL_STAMP_LO(tl_c + 1);
+        tl_c += 2;
         if (++s == stages) { s = 0; ++use; }
     }
 }

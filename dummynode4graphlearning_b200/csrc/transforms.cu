@@ -424,6 +424,26 @@ extern "C" int dn4gl_coalesce(const int32_t *src, const int32_t *dst, int64_t N,
     return DN4GL_OK;
 }
 
+// Tail padding for a compacted edge list whose length only the device knows: entries [count[0], cap) of a and b are
+// set to `fill` (the index of a trash row behind the last real row), so that every consumer can run with the host-known
+// capacity `cap` instead of waiting for a device->host read of the count (transforms.pyg_canonicalize, deferred count).
+__global__ void pad_tail_kernel(const int32_t *__restrict__ count, int64_t cap, int32_t *__restrict__ a, int32_t *__restrict__ b,
+                                int32_t fill) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < cap && i >= count[0]) {
+        a[i] = fill;
+        if (b) b[i] = fill;
+    }
+}
+
+extern "C" int dn4gl_pad_tail_i32(const int32_t *count, int64_t cap, int32_t *a, int32_t *b, int32_t fill, void *stream) {
+    DN_ARG(cap >= 0 && count != nullptr && (cap == 0 || a != nullptr));
+    if (cap == 0) return DN4GL_OK;
+    pad_tail_kernel<<<static_cast<unsigned>(ceil_div64(cap, 256)), 256, 0, as_stream(stream)>>>(count, cap, a, b, fill);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
 // ===========================================================================================
 // the remaining augmentation flags of subgraph_isomorphism/train.py on the same flat batch layout.
 //

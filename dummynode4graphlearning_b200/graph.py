@@ -111,14 +111,19 @@ class CSR:
         return cfg
 
 
-def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD, sorted_keys=False):
+def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD, sorted_keys=False, trash_row=False):
     """Stable CSR of the items 0..E-1 grouped by key (see dn4gl_build_csr).  sorted_keys: the caller guarantees
     non-decreasing keys (a coalesced edge list keyed by its row): one boundary-marking pass (dn4gl_build_csr_sorted);
-    a violation is reported through check_errors()."""
+    a violation is reported through check_errors().  trash_row: keys / values may also be n_rows (padding of a list
+    whose true length only the device knows, transforms.pyg_canonicalize): the CSR is built over n_rows + 1 rows and handed
+    out with n_rows logical rows -- kernels never visit the last row, `nnz` is the capacity."""
     require_cuda(key, "CSR key")
     L = lib()
     E = int(key.numel())
     dev = key.device
+    logical_rows = n_rows
+    if trash_row:
+        n_rows = n_rows + 1
     row_ptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
     col = torch.empty(E, dtype=torch.int32, device=dev)
     eid = torch.empty(E, dtype=torch.int32, device=dev)
@@ -130,13 +135,13 @@ def build_csr(key, val, n_rows, heavy_threshold=HEAVY_THRESHOLD, sorted_keys=Fal
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         L.call("dn4gl_build_csr", ptr(key), ptr(val), n_rows, E, ptr(row_ptr), ptr(col), ptr(eid),
                ptr(ws), ws_bytes, ptr(error_flag(dev)), _stream())   # flag checked lazily by check_errors()
-    csr = CSR(row_ptr, col, eid, n_rows, E)
+    csr = CSR(row_ptr, col, eid, logical_rows, E)
     if heavy_threshold and heavy_threshold > 0 and E > 0:
         cap = E // heavy_threshold + 1
         csr.heavy_rows = torch.empty(cap, dtype=torch.int32, device=dev)
         csr.heavy_count = torch.empty(1, dtype=torch.int32, device=dev)   # zeroed by dn4gl_collect_heavy_rows
         csr.heavy_thr = heavy_threshold
-        L.call("dn4gl_collect_heavy_rows", ptr(row_ptr), n_rows, heavy_threshold, ptr(csr.heavy_rows), cap,
+        L.call("dn4gl_collect_heavy_rows", ptr(row_ptr), logical_rows, heavy_threshold, ptr(csr.heavy_rows), cap,
                ptr(csr.heavy_count), _stream())
     return csr
 

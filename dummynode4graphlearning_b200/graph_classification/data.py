@@ -13,14 +13,15 @@ class GraphStructure:
     """CSR by destination / by source + per-graph node offsets of a PyG-style batch."""
 
     def __init__(self, edge_index, num_nodes, batch=None, node_ptr=None, max_seg=None, src=None, dst=None,
-                 sorted_by_src=False):
+                 sorted_by_src=False, trash_row=False):
         """edge_index (2, E) int64 as PyG carries it, or the int32 endpoint arrays src / dst directly."""
         if src is None:
             src = edge_index[0].to(torch.int32).contiguous()
             dst = edge_index[1].to(torch.int32).contiguous()
         self.src, self.dst, self.num_nodes = src, dst, int(num_nodes)
-        self.csr_in = build_csr(dst, src, self.num_nodes)
-        self.csr_out = build_csr(src, dst, self.num_nodes, sorted_keys=sorted_by_src)   # coalesced lists are (src, dst)-sorted
+        self.trash_row = bool(trash_row)   # src / dst are padded with (N, N) entries up to their capacity (deferred count)
+        self.csr_in = build_csr(dst, src, self.num_nodes, trash_row=trash_row)
+        self.csr_out = build_csr(src, dst, self.num_nodes, sorted_keys=sorted_by_src, trash_row=trash_row)   # coalesced lists are (src, dst)-sorted
         if node_ptr is None and batch is not None:
             nb = int(batch[-1].item()) + 1 if batch.numel() else 0   # batch is sorted (PyG collate)
             counts = torch.bincount(batch, minlength=nb)
@@ -60,9 +61,9 @@ class Batch:
     first access (the GIN train step never reads them -- it uses the compiled structure)."""
 
     def __init__(self, x, edge_index, batch, edge_attr=None, y=None, is_dummy_node=None, is_dummy_edge=None,
-                 node_ptr=None, max_graph_nodes=None, src=None, dst=None, sorted_by_src=False):
+                 node_ptr=None, max_graph_nodes=None, src=None, dst=None, sorted_by_src=False, trash_row=False):
         self.x, self.edge_attr, self.y = x, edge_attr, y
-        self._sorted_by_src = sorted_by_src
+        self._sorted_by_src, self._trash_row = sorted_by_src, trash_row
         self._lazy = dict(edge_index=edge_index, batch=batch, is_dummy_node=is_dummy_node)
         self.is_dummy_edge = is_dummy_edge
         self._node_ptr, self._max_seg = node_ptr, max_graph_nodes
@@ -89,7 +90,7 @@ class Batch:
             if self._src is not None:
                 self._structure = GraphStructure(None, self.x.size(0), None if self._node_ptr is not None else self.batch,
                                                  self._node_ptr, self._max_seg, src=self._src, dst=self._dst,
-                                                 sorted_by_src=self._sorted_by_src)
+                                                 sorted_by_src=self._sorted_by_src, trash_row=self._trash_row)
             else:
                 self._structure = GraphStructure(self.edge_index, self.x.size(0), self.batch, self._node_ptr, self._max_seg)
         return self._structure
@@ -101,7 +102,7 @@ class Batch:
         return Batch(d["x"], lazy("edge_index"), lazy("batch"), d.get("edge_attr"), d.get("y"),
                      lazy("is_dummy_node"), d.get("is_dummy_edge"), node_ptr=d["node_ptr"],
                      max_graph_nodes=d.get("max_graph_nodes"), src=d.get("src"), dst=d.get("dst"),
-                     sorted_by_src=bool(d.get("sorted_by_src", False)))
+                     sorted_by_src=bool(d.get("sorted_by_src", False)), trash_row=bool(d.get("trash_row", False)))
 
 
 def structure_of(data):

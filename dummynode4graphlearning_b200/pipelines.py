@@ -193,7 +193,7 @@ class ClassificationPipeline:
         b["has_edge_labels"] = True
         # GIN never reads edge_attr (gconv.py:204); RGIN does (rgconv.py:109-111)
         can = T.pyg_canonicalize(b, self.nvl, self.nel, node_label_min=self.node_label_min,
-                                 with_edge_attr=self.with_edge_attr)
+                                 with_edge_attr=self.with_edge_attr, defer_count=not self.with_edge_attr)
         data = Batch.from_canonical(can)
         s = data.structure  # compile the CSR pair now (part of the transform cost)
         hid = getattr(self.model, "hidden_dim", None)

@@ -338,7 +338,8 @@ def sub_conjugate(b, id_bound=None):
     return o
 
 
-def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_min=None, with_edge_attr=True):
+def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_min=None, with_edge_attr=True,
+                     defer_count=False):
     """What PyG ``read_tu_data`` + ``PYGDataset.set_dummy_flags`` turn the saved TU files into
     (graph_neural_networks/dataset.py:118-151): one-hot ``x`` (attribute column first, then labels
     shifted to start at 0), ``edge_index`` int64 with self loops removed and coalesced = sorted by
@@ -355,8 +356,22 @@ def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_m
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     L.call("dn4gl_coalesce", ptr(b["src"]), ptr(b["dst"]), N, E, ptr(csr_out.row_ptr), ptr(csr_out.eid), ptr(keep_scan),
            ptr(o_src), ptr(o_dst), ptr(o_first), ptr(ws), ws_bytes, ptr(error_flag(dev)), _stream())
-    E2 = int(keep_scan[-1].item())
-    o_src, o_dst, o_first = o_src[:E2], o_dst[:E2], o_first[:E2]
+    defer = bool(defer_count) and not (with_edge_attr and b.get("has_edge_labels", True)) and E > 0
+    if defer:
+        # the surviving edge count stays on the device: the arrays keep their capacity E, the tail [E'', E) points at a
+        # trash row N (dn4gl_pad_tail_i32), and the CSRs are built over N + 1 rows -- no second device->host read-back on
+        # the GIN path.  Whoever needs the exact lists (edge_index, first_edge) pays for the read-back lazily.
+        L.call("dn4gl_pad_tail_i32", ptr(keep_scan[E:]), E, ptr(o_src), ptr(o_dst), N, _stream())
+        count = {}
+
+        def exact():
+            if "E2" not in count:
+                count["E2"] = int(keep_scan[-1].item())
+            return count["E2"]
+        E2 = None
+    else:
+        E2 = int(keep_scan[-1].item())
+        o_src, o_dst, o_first = o_src[:E2], o_dst[:E2], o_first[:E2]
     # node features: [attr?, one_hot(label - min)]
     vl = b["vlabel"]
     if node_label_min is not None and num_node_labels is not None:
@@ -369,9 +384,16 @@ def pyg_canonicalize(b, num_node_labels=None, num_edge_labels=None, node_label_m
     if "vattr" in b:
         x = torch.cat([b["vattr"].view(N, -1), x], dim=1)
         n_attr = x.size(1) - nvl
-    out = LazyDict(num_graphs=B, x=x, node_ptr=b["node_ptr"], src=o_src, dst=o_dst, first_edge=o_first,
+    out = LazyDict(num_graphs=B, x=x, node_ptr=b["node_ptr"], src=o_src, dst=o_dst,
                    sorted_by_src=True)   # survivors are compacted in (src, dst) order: the by-src CSR needs no sort
-    out.lazy("edge_index", lambda: torch.stack([o_src.long(), o_dst.long()]))
+    if defer:
+        out["trash_row"] = True          # src / dst hold E entries, the last E - E'' of them (N, N)
+        out.lazy("first_edge", lambda: o_first[:exact()])
+        out.lazy("edge_index", lambda: torch.stack([o_src[:exact()].long(), o_dst[:exact()].long()]))
+        out.lazy("num_edges", exact)
+    else:
+        out["first_edge"] = o_first
+        out.lazy("edge_index", lambda: torch.stack([o_src.long(), o_dst.long()]))
     out.lazy("batch", lambda: torch.repeat_interleave(torch.arange(B, device=dev),
                                                       (b["node_ptr"][1:] - b["node_ptr"][:-1]).long(), output_size=N))
     if with_edge_attr and b.get("has_edge_labels", True) and E > 0:

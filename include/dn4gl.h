@@ -219,6 +219,11 @@ int dn4gl_coalesce(const int32_t *src, const int32_t *dst, int64_t N, int64_t E,
                    int32_t *keep_scan, int32_t *o_src, int32_t *o_dst, int32_t *o_first,
                    void *ws, size_t ws_bytes, int32_t *err_flag, void *stream);
 
+/* a[i] = b[i] = fill for i in [count[0], cap): pads a compacted list whose length only the device knows (dn4gl_coalesce's
+ * keep_scan[E]) up to its host-known capacity with the index of a trash row, so that the CSR builds behind it need no
+ * device->host read of the count.  b may be NULL.                                                                    */
+int dn4gl_pad_tail_i32(const int32_t *count, int64_t cap, int32_t *a, int32_t *b, int32_t fill, void *stream);
+
 /* ---- K1: sum aggregation -------------------------------------------------------------------- */
 /* out[v,:] = self_scale * x[v,:] + sum_{p in [row_ptr[v], row_ptr[v+1])} x[col[p],:]
  * replaces torch_scatter.scatter(reduce='sum') under PyG GINConv.propagate (gconv.py:212) and

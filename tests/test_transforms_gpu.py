@@ -377,3 +377,49 @@ def test_augmentation_and_match_weights_empty_inputs(device):
     assert M.node_weights(sub, gb).cpu().tolist() == [0, 0, 1, 1, 1, 0]
     ew = M.edge_weights(sub, gb, gb)          # the batch as its own pattern: the identity map matches every edge once
     assert ew.cpu().tolist() == O.subiso_edge_weights([np.zeros((0, 2)), np.array([[0, 1, 2]]), np.zeros((0, 1))], b, b).tolist() == [1, 1, 1]
+
+
+def test_pyg_canonicalize_deferred_count_equals_exact(device):
+    """deferred edge count (tail padded with a trash row, no second read-back) == the exact path: same CSRs on the logical
+    rows, same lazily materialised edge_index, same GIN output -- on a batch with planted self loops and repeated edges so
+    that the padding is really exercised."""
+    from argparse import Namespace
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.graph_classification.data import Batch
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+
+    raw = {k: v for k, v in synth.tu_batch("mutag", 40, seed=3).items() if k != "vattr"}
+    raw["dst"] = raw["dst"].copy()
+    raw["dst"][::9] = raw["src"][::9]                  # self loops
+    raw["src"] = raw["src"].copy()
+    for g in range(0, 40, 3):                           # a repeated edge per third graph
+        e0 = int(raw["edge_ptr"][g])
+        if raw["edge_ptr"][g + 1] - e0 >= 2:
+            raw["src"][e0 + 1], raw["dst"][e0 + 1] = raw["src"][e0], raw["dst"][e0]
+    b = T.tu_add_dummy(T.to_device(raw, device))
+    b["has_edge_labels"] = True
+    exact = T.pyg_canonicalize(b, 8, None, node_label_min=0, with_edge_attr=False)
+    lazy = T.pyg_canonicalize(b, 8, None, node_label_min=0, with_edge_attr=False, defer_count=True)
+    E2 = int(exact["src"].numel())
+    assert lazy.get("trash_row") and int(lazy["src"].numel()) > E2, "the test batch must lose edges in coalesce"
+    assert torch.equal(lazy["edge_index"], exact["edge_index"]) and torch.equal(lazy["first_edge"], exact["first_edge"])
+    N = int(b["vlabel"].numel())
+    assert bool((lazy["src"][E2:] == N).all()) and bool((lazy["dst"][E2:] == N).all())
+    de, dl = Batch.from_canonical(exact), Batch.from_canonical(lazy)
+    for name in ("csr_in", "csr_out"):
+        ce, cl = getattr(de.structure, name), getattr(dl.structure, name)
+        assert cl.n_rows == ce.n_rows == N
+        assert torch.equal(cl.row_ptr[: N + 1], ce.row_ptr) and torch.equal(cl.col[:E2], ce.col)
+    args = Namespace(num_features=8, hidden_dim=32, num_classes=2, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": 3, "aggregation": "sum"}, epochs=1, device=str(device))
+    torch.manual_seed(0)
+    model = GIN(args).to(device).train()
+    oe = model(de)
+    ol = model(dl)
+    assert torch.equal(oe, ol)
+    oe.sum().backward()
+    ge = [p.grad.clone() for p in model.parameters()]
+    model.zero_grad()
+    ol.sum().backward()
+    for a, c in zip(ge, [p.grad for p in model.parameters()]):
+        assert torch.equal(a, c)
