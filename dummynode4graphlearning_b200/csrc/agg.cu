@@ -415,3 +415,50 @@ extern "C" int dn4gl_label_filter_gate(const int32_t *g_ptr, const int32_t *g_la
     DN_LAUNCHED();
     return DN4GL_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Classification loss of the train step: F.nll_loss(log_probs, y) with the default mean reduction
+// (graph_classification/graph_neural_networks/main.py:41).  The library kernels behind torch's nll_loss take 20 + 12 us
+// for a 1113 x 2 input (profiles/r1f launch list); this is one CTA with a fixed reduction tree, and one elementwise kernel
+// for the gradient  g_logp[b, c] = (c == y_b) ? -g / B : 0.
+__global__ void __launch_bounds__(1024) nll_mean_fwd_kernel(const float *__restrict__ logp, const int64_t *__restrict__ y,
+                                                           int B, int C, float *__restrict__ loss) {
+    __shared__ float red[1024];
+    float s = 0.f;
+    for (int b = threadIdx.x; b < B; b += 1024) {
+        const int64_t c = y[b];
+        if (c >= 0 && c < C) s -= logp[static_cast<int64_t>(b) * C + c];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = red[0] / static_cast<float>(B > 0 ? B : 1);
+}
+
+__global__ void nll_mean_bwd_kernel(const float *__restrict__ g, const int64_t *__restrict__ y, int B, int C,
+                                    float *__restrict__ g_logp) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<int64_t>(B) * C) return;
+    const int b = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<int64_t>(b) * C);
+    g_logp[i] = (y[b] == c) ? -g[0] / static_cast<float>(B) : 0.f;
+}
+
+extern "C" int dn4gl_nll_mean_f32(const float *logp, const int64_t *y, int32_t B, int32_t C, float *loss, void *stream) {
+    DN_ARG(B >= 0 && C > 0 && loss != nullptr && (B == 0 || (logp != nullptr && y != nullptr)));
+    nll_mean_fwd_kernel<<<1, 1024, 0, as_stream(stream)>>>(logp, y, B, C, loss);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+extern "C" int dn4gl_nll_mean_bwd_f32(const float *g, const int64_t *y, int32_t B, int32_t C, float *g_logp, void *stream) {
+    DN_ARG(B >= 0 && C > 0);
+    if (B == 0) return DN4GL_OK;
+    DN_ARG(g != nullptr && y != nullptr && g_logp != nullptr);
+    nll_mean_bwd_kernel<<<static_cast<unsigned>(ceil_div64(static_cast<int64_t>(B) * C, 256)), 256, 0, as_stream(stream)>>>(
+        g, y, B, C, g_logp);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}

@@ -922,7 +922,23 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const float *__restric
         const int beg = __ldg(seg_ptr + g), end = __ldg(seg_ptr + g + 1);
         float4 acc = zero4();
         if (4 * c < M) {
-            for (int r = beg + r0; r < end; r += RP) {
+            // four rows per thread in flight: with one load per iteration the 1 000-row graphs of the C2 batch made their
+            // CTA walk 34 dependent DRAM round trips (23 us for a 6 us traffic problem, profiles/r1d); same add order
+            int r = beg + r0;
+            for (; r + 3 * RP < end; r += 4 * RP) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = load_chunk(Y, r + u * RP, M, c, vec);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (bn) v[u] = bn_apply(v[u], b);
+                    v[u].x = act_f(v[u].x, act, slope); v[u].y = act_f(v[u].y, act, slope);
+                    v[u].z = act_f(v[u].z, act, slope); v[u].w = act_f(v[u].w, act, slope);
+                    store_chunk(out, r + u * RP, M, c, v[u], vec);
+                    acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+                }
+            }
+            for (; r < end; r += RP) {
                 float4 v = load_chunk(Y, r, M, c, vec);
                 if (bn) v = bn_apply(v, b);
                 v.x = act_f(v.x, act, slope); v.y = act_f(v.y, act, slope); v.z = act_f(v.z, act, slope); v.w = act_f(v.w, act, slope);
@@ -969,19 +985,44 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restric
     const Bn4 b = load_bn4(bn, M, c);
     float4 s1 = zero4(), s2 = zero4();
     if (4 * c < M) {
-        for (int64_t r = static_cast<int64_t>(blockIdx.x) * RP + r0; r < N; r += static_cast<int64_t>(gridDim.x) * RP) {
-            float4 g = G != nullptr ? load_chunk(G, r, M, c, vec) : zero4();
-            if (Gseg != nullptr) {
-                const float4 gs = load_chunk(Gseg, __ldg(row2seg + r), M, c, vec);
-                g.x += gs.x; g.y += gs.y; g.z += gs.z; g.w += gs.w;
-            }
-            const float4 y = load_chunk(Y, r, M, c, vec);
+        // several rows per thread in flight (all loads first, then the arithmetic in row order: same sums as one at a time)
+        const int64_t stride = static_cast<int64_t>(gridDim.x) * RP;
+        auto accumulate = [&](float4 g, const float4 &y) {
             const float4 xc = make_float4(y.x - b.mean.x, y.y - b.mean.y, y.z - b.mean.z, y.w - b.mean.w);
             g.x *= dact_f(fmaf(xc.x, b.k.x, b.beta.x), act, slope); g.y *= dact_f(fmaf(xc.y, b.k.y, b.beta.y), act, slope);
             g.z *= dact_f(fmaf(xc.z, b.k.z, b.beta.z), act, slope); g.w *= dact_f(fmaf(xc.w, b.k.w, b.beta.w), act, slope);
             s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
             s2.x = fmaf(g.x, xc.x * b.rstd.x, s2.x); s2.y = fmaf(g.y, xc.y * b.rstd.y, s2.y);
             s2.z = fmaf(g.z, xc.z * b.rstd.z, s2.z); s2.w = fmaf(g.w, xc.w * b.rstd.w, s2.w);
+        };
+        int64_t r = static_cast<int64_t>(blockIdx.x) * RP + r0;
+        constexpr int UR = 2;   // rows in flight per thread (4 needed 90 registers and halved the occupancy)
+        for (; r + (UR - 1) * stride < N; r += UR * stride) {
+            float4 g[UR], y[UR];
+            int seg[UR];
+#pragma unroll
+            for (int u = 0; u < UR; ++u) {
+                g[u] = G != nullptr ? load_chunk(G, r + u * stride, M, c, vec) : zero4();
+                seg[u] = Gseg != nullptr ? __ldg(row2seg + r + u * stride) : 0;
+                y[u] = load_chunk(Y, r + u * stride, M, c, vec);
+            }
+            if (Gseg != nullptr) {
+#pragma unroll
+                for (int u = 0; u < UR; ++u) {
+                    const float4 gs = load_chunk(Gseg, seg[u], M, c, vec);
+                    g[u].x += gs.x; g[u].y += gs.y; g[u].z += gs.z; g[u].w += gs.w;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UR; ++u) accumulate(g[u], y[u]);
+        }
+        for (; r < N; r += stride) {
+            float4 g = G != nullptr ? load_chunk(G, r, M, c, vec) : zero4();
+            if (Gseg != nullptr) {
+                const float4 gs = load_chunk(Gseg, __ldg(row2seg + r), M, c, vec);
+                g.x += gs.x; g.y += gs.y; g.z += gs.z; g.w += gs.w;
+            }
+            accumulate(g, load_chunk(Y, r, M, c, vec));
         }
     }
     chunk_allreduce<CHP>(s1);
@@ -1025,7 +1066,18 @@ __global__ void __launch_bounds__(256) dot_kernel(const float *__restrict__ a, c
     if (vec) {
         const int64_t n4 = n / 4;
         const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b);
-        for (int64_t i = blockIdx.x * 256ll + t; i < n4; i += gridDim.x * 256ll) {
+        const int64_t stride = gridDim.x * 256ll;
+        int64_t i = blockIdx.x * 256ll + t;
+        for (; i + 3 * stride < n4; i += 4 * stride) {      // eight independent 128-bit loads in flight, same add order
+            float4 u[4], v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { u[k] = __ldg(a4 + i + k * stride); v[k] = __ldg(b4 + i + k * stride); }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s = fmaf(u[k].x, v[k].x, s); s = fmaf(u[k].y, v[k].y, s); s = fmaf(u[k].z, v[k].z, s); s = fmaf(u[k].w, v[k].w, s);
+            }
+        }
+        for (; i < n4; i += stride) {
             const float4 u = __ldg(a4 + i), v = __ldg(b4 + i);
             s = fmaf(u.x, v.x, s); s = fmaf(u.y, v.y, s); s = fmaf(u.z, v.z, s); s = fmaf(u.w, v.w, s);
         }

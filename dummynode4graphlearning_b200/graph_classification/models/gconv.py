@@ -110,6 +110,27 @@ class GIN(torch.nn.Module):
         B rows instead of N."""
         mean = self.pooling is global_mean_pool
         x, out = data.x, 0
+        if self.dropout == 0:
+            # jumping-knowledge head as ONE GEMM: sum_l Linear_l(pooled_l) = [pooled_0 | ... | pooled_L] @ [W_0 | ... | W_L]^T
+            # + biases (dropout with p = 0 is the identity).  Five (B x D) @ (D x C) GEMMs with their bias / dropout / add
+            # kernels and their backward were ~40 launches of 2-3 us in a train step that is bound by launch count.
+            pooled_all = []
+            for layer in range(self.no_layers):
+                if layer == 0:
+                    x, pooled = ops.gin_layer(self.first_h, x, seg_ptr=s.node_ptr, row2seg=s.row2seg, mean=mean)
+                else:
+                    conv = self.convs[layer - 1]
+                    x, pooled = ops.gin_layer(conv.nn, x, conv.eps, s.csr_in, s.csr_out, s.node_ptr, s.row2seg, mean)
+                pooled_all.append(pooled)
+            w_all = torch.cat([lin.weight for lin in self.linears], dim=1)
+            score = ops.linear(torch.cat(pooled_all, dim=1), w_all, None)
+            bias_rest = torch.stack([lin.bias for lin in self.linears[1:]]).sum(0) if self.no_layers > 1 else 0
+            if mean:
+                score = score + (self.linears[0].bias + bias_rest)
+            else:   # layer 0 pools Linear(h): its bias is counted once per pooled row (gconv.py:210)
+                cnt = (s.node_ptr[1:] - s.node_ptr[:-1]).to(score.dtype).unsqueeze(1)
+                score = score + (cnt * self.linears[0].bias + bias_rest)
+            return F.log_softmax(score, dim=-1)
         for layer in range(self.no_layers):
             if layer == 0:
                 x, pooled = ops.gin_layer(self.first_h, x, seg_ptr=s.node_ptr, row2seg=s.row2seg, mean=mean)

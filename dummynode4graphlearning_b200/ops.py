@@ -141,6 +141,38 @@ def label_filter_gate(graph, pattern, Lp_max, kind="node"):
     return gate
 
 
+class _NllMean(torch.autograd.Function):
+    """F.nll_loss(log_probs, y) (mean reduction, main.py:41) as one small kernel each way."""
+
+    @staticmethod
+    def forward(ctx, logp, y):
+        require_cuda(logp, "log-probabilities")
+        logp = _f32c(logp)
+        y = y.contiguous()
+        B, C = logp.shape
+        loss = torch.empty((), dtype=torch.float32, device=logp.device)
+        lib().call("dn4gl_nll_mean_f32", ptr(logp), ptr(y), B, C, ptr(loss), _stream())
+        ctx.save_for_backward(y)
+        ctx.shape = (B, C)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        B, C = ctx.shape
+        g = _f32c(g).reshape(1)
+        out = torch.empty((B, C), dtype=torch.float32, device=g.device)
+        lib().call("dn4gl_nll_mean_bwd_f32", ptr(g), ptr(y), B, C, ptr(out), _stream())
+        return out, None
+
+
+def nll_loss(logp, y):
+    """mean negative log-likelihood of int64 targets y under row-wise log-probabilities logp (B, C)."""
+    if y.dtype != torch.int64:
+        y = y.long()
+    return _NllMean.apply(logp, y)
+
+
 # ---------------------------------------------------------------------------------------------
 def _rev_u8(graph):
     if "is_reversed" not in graph.edata:

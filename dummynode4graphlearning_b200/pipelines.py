@@ -206,7 +206,7 @@ class ClassificationPipeline:
     def _train_body(self, data):
         self.bucket.zero()
         out = self.model(data)
-        loss = F.nll_loss(out, data.y)                      # main.py:41
+        loss = ops.nll_loss(out, data.y) if out.is_cuda else F.nll_loss(out, data.y)    # main.py:41
         loss.backward()
         self.bucket.gather()                                # gradients live in one flat buffer (one multi-tensor copy)
         if is_distributed():

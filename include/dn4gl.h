@@ -41,6 +41,9 @@ int dn4gl_version(void);
 const char *dn4gl_last_error(void);
 /* binds the calling thread to `device` (cudaSetDevice); one process per GPU is the intended use */
 int dn4gl_set_device(int device);
+/* caps the SM count the library sizes its (persistent) grids with; 0 = all SMs.  Process-wide; set it before the first
+ * workspace query / launch and leave it (workspace sizes depend on it).  Used to leave SMs to a concurrent stream.     */
+int dn4gl_set_sm_limit(int n);
 /* number of CUDA kernels this library has launched in this process so far (monotonic counter) */
 int64_t dn4gl_launch_count(void);
 
@@ -276,6 +279,12 @@ int dn4gl_segment_sum_f32(const int32_t *seg_ptr, const uint8_t *mask, const flo
 /* backward of the above: gx[v,:] = mask[v] ? 0 : scale_b * g[b(v),:]                            */
 int dn4gl_segment_bcast_f32(const int32_t *seg_ptr, const uint8_t *mask, const float *g, float *gx,
                             int32_t B, int64_t N, int32_t D, int32_t mode, void *stream);
+
+/* loss[0] = -(1/B) sum_b logp[b, y[b]]: F.nll_loss(log_probs, y) with mean reduction, the classification criterion of
+ * graph_neural_networks/main.py:41 (y: int64 class indices as torch carries them; no class weights, no ignore_index --
+ * the reference uses neither).  One CTA, fixed reduction tree.  _bwd: g_logp[b, c] = (c == y[b]) ? -g[0] / B : 0.        */
+int dn4gl_nll_mean_f32(const float *logp, const int64_t *y, int32_t B, int32_t C, float *loss, void *stream);
+int dn4gl_nll_mean_bwd_f32(const float *g, const int64_t *y, int32_t B, int32_t C, float *g_logp, void *stream);
 
 /* left-padded dense batchify, replaces split_and_batchify_graph_feats(pre_pad=True)
  * (subgraph_isomorphism/utils/dl.py:51-81): out[b, Lmax-len_b+i, :] = x[seg_ptr[b]+i, :] (0 on

@@ -204,3 +204,19 @@ def test_spmm_variants_agree_with_oracle(device, monkeypatch, mode, smem, known,
     assert np.array_equal(out.detach().cpu().numpy()[light], ref[light])     # CSR-order accumulation: bit-exact
     np.testing.assert_allclose(out.detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-4)
     np.testing.assert_allclose(xt.grad.cpu().numpy(), ref_grad, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,C", [(1, 2), (1113, 2), (5000, 7)])
+def test_nll_mean_matches_torch(device, B, C):
+    """dn4gl_nll_mean_f32 (+ backward) == F.nll_loss(log_softmax(.), y) (mean), main.py:41."""
+    import torch.nn.functional as F
+    from dummynode4graphlearning_b200 import ops
+    torch.manual_seed(B)
+    z = torch.randn(B, C, device=device, requires_grad=True)
+    y = torch.randint(0, C, (B,), device=device)
+    ref = F.nll_loss(F.log_softmax(z, dim=-1), y)
+    (gr,) = torch.autograd.grad(ref * 1.7, z)
+    out = ops.nll_loss(F.log_softmax(z, dim=-1), y)
+    (go,) = torch.autograd.grad(out * 1.7, z)
+    assert abs(float(out) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
+    assert float((go - gr).abs().max()) <= 1e-6 * float(gr.abs().max())
