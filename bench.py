@@ -30,7 +30,7 @@ import torch.nn.functional as F  # noqa: E402
 
 HID, LAYERS, CLASSES, LR = 32, 4, 2, 0.01   # hyper_params.py:15 (GIN / PROTEINS)
 NUM_NODE_LABELS = 2                          # CONJ graphs: vertex label = original edge label (1) or dummy (0)
-L2_FLUSH_BYTES = 256 << 20
+L2_FLUSH_BYTES = 192 << 20     # > the 126 MB L2
 
 
 def parse():
@@ -124,98 +124,92 @@ def workload_config(graphs, n_gpus):
     return {"workload": "c2: dummy + edge-to-vertex (CONJ) transform + GIN(hidden 32, 4 layers, train_eps, sum pool) "
                         "train step on synthetic PROTEINS-shaped graphs", "graphs_per_gpu": graphs,
             "global_batch": graphs * n_gpus, "avg_nodes": 39, "optimizer": "Adam(lr=0.01) as one flat-buffer kernel (dn4gl_adam_f32)", "train_step": "CUDA graph replay per batch signature; transform eager on a second stream, overlapping the previous train step",
-            "parallelism": "dp%d" % n_gpus, "l2": "flushed between steps (256 MiB write inside the timed region)"}
+            "parallelism": "dp%d" % n_gpus, "l2": "flushed between steps (192 MiB write, larger than the 126 MB L2, inside the timed region)"}
 
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).
+    """SM clock / throttle reasons DURING the timed regions (B200_PROFILING.md clocks line).
 
-    Sampled in-process through NVML every 10 ms by a daemon thread (the timed region of the default run is ~50-100 ms,
-    too short for a freshly spawned `nvidia-smi -lms` to report anything); falls back to one `nvidia-smi` query taken
-    while the GPU is still busy if NVML cannot be loaded."""
+    A separate `nvidia-smi -lms 50` process is started before the warm-up (its start-up takes a few hundred ms) and
+    its time-stamped rows are filtered to the window between mark_start() and stop().  In-process NVML sampling from a
+    thread was tried first: its queries take the driver's lock and stalled single steps of this (host-bound, 1.2 ms)
+    loop for 5-130 ms in one run out of four (profiles/README.md, r1f/r1g); the loop without a sampler shows no step
+    above 3.1 ms in 4000 (tools/e2e_stall.py).  Falls back to one NVML sample at the end if nvidia-smi is missing."""
 
-    PERIOD = 0.05     # NVML queries take the driver's lock: at a 10 ms period they stalled single steps for 5-60 ms
-    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
-               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
-               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
-               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        import threading
-        self.sm, self.reasons, self.mx, self.err = [], set(), None, None
-        self._stop = threading.Event()
-        self.nv = self.h = None
+        self.index, self.p, self.t0 = index, None, None
+        self.path = "/tmp/dn4gl_clocks_%d_%d.csv" % (os.getpid(), index)
         try:
-            import pynvml as nv
-            nv.nvmlInit()
             uuid = str(torch.cuda.get_device_properties(index).uuid)
-            try:
-                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
-            except Exception:
-                self.h = nv.nvmlDeviceGetHandleByIndex(index)
-            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
-            self.nv = nv
-            self._sample()            # first calls (lazy initialisation inside NVML) happen before the timed region ...
-            self.sm.clear()           # ... and are not counted as a sample under load
-            self.reasons.clear()
-        except Exception as e:   # noqa: BLE001
-            self.err = "nvml: %s" % e
-        self.index = index
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
-
-    def _sample(self):
-        nv = self.nv
-        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            sel = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        except Exception:   # noqa: BLE001
+            sel = str(index)
         try:
-            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-        except Exception:
-            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-        for name, const in self.REASONS:
-            if mask & getattr(nv, const):
-                self.reasons.add(name)
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", sel, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:   # noqa: BLE001
+            self.p = None
 
-    def _run(self):
-        if self.nv is None:
-            return
-        while not self._stop.is_set():
-            try:
-                self._sample()
-            except Exception as e:   # noqa: BLE001
-                self.err = "nvml: %s" % e
-                return
-            self._stop.wait(self.PERIOD)
+    def mark_start(self):
+        self.t0 = time.time()
 
-    def _smi_once(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                 capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0]
-            c = [x.strip() for x in out.split(",")]
-            self.sm.append(float(c[0])); self.mx = float(c[1])
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
-                if v.lower().startswith("active"):
-                    self.reasons.add(name)
-        except Exception as e:   # noqa: BLE001
-            self.err = "nvidia-smi: %s" % e
+    def _nvml_once(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        return {"sm_mhz": float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                "sm_max_mhz": float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)), "samples": 1, "reasons": [],
+                "how": "one NVML sample right after the timed regions (nvidia-smi unavailable)"}
 
     def stop(self):
-        """call while the last timed work is still in flight or just done"""
-        if self.nv is None:
-            self._smi_once()
-        else:
+        import datetime
+        t1 = time.time()
+        if self.p is None:
             try:
-                self._sample()        # one more while the last timed steps are still in flight
+                return self._nvml_once()
+            except Exception as e:   # noqa: BLE001
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [], "error": str(e)[:100]}
+        time.sleep(0.06)              # let the row that covers the end of the window arrive
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:   # noqa: BLE001
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons, total = [], [], set(), 0
+        for ln in open(self.path):
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 7:
+                continue
+            total += 1
+            try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(c[1]), float(c[2])
+            except ValueError:
+                continue
+            if self.t0 is not None and not (self.t0 - 0.05 <= ts <= t1 + 0.05):
+                continue
+            sm.append(clk); mx.append(cmax)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+               "reasons": sorted(reasons), "how": "nvidia-smi -lms 50 in a separate process, rows inside the timed window",
+               "rows_total": total}
+        if not sm:
+            try:
+                out.update(self._nvml_once())
             except Exception:   # noqa: BLE001
                 pass
-        self._stop.set()
-        self.t.join(timeout=2)
-        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
-               "samples": len(self.sm), "reasons": sorted(self.reasons), "how": "nvml thread, 50 ms period" if self.nv else "nvidia-smi"}
-        if self.err and not self.sm:
-            out["error"] = self.err
         return out
 
 
@@ -282,6 +276,7 @@ def ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local) if (rank == 0 and not os.environ.get("DN4GL_NO_CLOCKS")) else None
     n_warm = max(a.warmup, 30)   # first step eager, second captures the CUDA graph, the rest settle the caching allocator
                                  # (two streams, up to two steps in flight: a cudaMalloc inside the timed loop costs 2-10 ms)
     for _ in range(n_warm):
@@ -294,7 +289,8 @@ def ours(a):
     gc.freeze()
     # ---- timed region: EXACTLY K steps, device-timed ----------------------------------------------------
     barrier()
-    clocks = ClockSampler(local) if (rank == 0 and not os.environ.get("DN4GL_NO_CLOCKS")) else None
+    if clocks:
+        clocks.mark_start()
     k0 = L.kernel_launches() + pipe.replayed_library_kernels()
     nmalloc = lambda: int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))   # cudaMalloc calls so far
     m0 = nmalloc()

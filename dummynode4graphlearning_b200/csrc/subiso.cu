@@ -98,3 +98,79 @@ extern "C" int dn4gl_subiso_edge_weights(int32_t B, const int32_t *work_ptr, int
     DN_LAUNCHED_N(2);
     return DN4GL_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// get_conjugate_subisomorphisms (subgraph_isomorphism/utils/graph.py:294-330) followed by the g_eid gather of
+// convert_to_conjugate (train.py:546-556 / 577-587): every subisomorphism (a map of pattern NODES to graph nodes) becomes
+// a map of pattern EDGE slots to graph EDGE ids -- the vertices of the conjugate graphs.  Slot q stands for the q-th
+// distinct (u, v) pair of the pattern in order of first appearance; its label set is the LAST run of consecutive pattern
+// edges with that pair (dict semantics, as in the edge weights above); the slot's value is the last edge, in
+// (src, dst, id) order, between the mapped endpoints whose label is in the set, else -- and for the slots beyond the
+// number of distinct pairs -- position 0 of that order (the reference's zero-initialised matrix), mapped to its edge id.
+// One thread per (subisomorphism, slot).  Output ids are graph-LOCAL edge ids, laid out like the work items
+// (work_ptr[b] + s * m_b + q).
+__global__ void subiso_conjugate_kernel(int B, const int32_t *__restrict__ work_ptr, const int32_t *__restrict__ val_ptr,
+                                        const int32_t *__restrict__ values, const int32_t *__restrict__ p_node_ptr,
+                                        const int32_t *__restrict__ p_edge_ptr, const int32_t *__restrict__ p_src,
+                                        const int32_t *__restrict__ p_dst, const int32_t *__restrict__ p_elabel,
+                                        const int32_t *__restrict__ active, const int32_t *__restrict__ g_node_ptr,
+                                        const int32_t *__restrict__ g_edge_ptr, const int32_t *__restrict__ out_ptr,
+                                        const int32_t *__restrict__ out_items, const int32_t *__restrict__ g_dst,
+                                        const int32_t *__restrict__ g_elabel, int32_t *__restrict__ conj, int64_t total) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int b = segment_of(work_ptr, B, t);
+    const int pe0 = p_edge_ptr[b], m = p_edge_ptr[b + 1] - pe0;
+    const int local = static_cast<int>(t - work_ptr[b]);
+    const int s = local / m, q = local % m;
+    const int gn0 = g_node_ptr[b], ge0 = g_edge_ptr[b];
+    const int first_pos = out_ptr[gn0];                      // position 0 of the graph's (src, dst, id) order
+    int result_pos = first_pos;
+    // the q-th distinct pair in order of first appearance
+    int f = -1, seen = 0;
+    for (int e = pe0; e < pe0 + m && f < 0; ++e) {
+        bool is_first = true;
+        for (int e2 = pe0; e2 < e; ++e2)
+            if (p_src[e2] == p_src[e] && p_dst[e2] == p_dst[e]) { is_first = false; break; }
+        if (is_first) {
+            if (seen == q) f = e;
+            ++seen;
+        }
+    }
+    if (f >= 0) {
+        const int pn0 = p_node_ptr[b], np_ = p_node_ptr[b + 1] - pn0;
+        const int32_t *row = values + val_ptr[b] + static_cast<int64_t>(s) * np_;
+        const int pu = p_src[f], pv = p_dst[f];
+        const int u = gn0 + row[pu - pn0], v = gn0 + row[pv - pn0];
+        for (int p = out_ptr[u]; p < out_ptr[u + 1]; ++p) {
+            const int it = out_items[p];
+            const int d = g_dst[it];
+            if (d > v) break;
+            if (d != v) continue;
+            const int lab = g_elabel[it];
+            for (int e = f; e < pe0 + m; ++e)               // labels of the pair's last run
+                if (active[e] && p_src[e] == pu && p_dst[e] == pv && p_elabel[e] == lab) { result_pos = p; break; }
+        }
+    }
+    conj[t] = out_items[result_pos] - ge0;
+}
+
+extern "C" int dn4gl_subiso_conjugate(int32_t B, const int32_t *work_ptr, int64_t total_work, const int32_t *val_ptr,
+                                      const int32_t *values, const int32_t *p_node_ptr, const int32_t *p_edge_ptr,
+                                      const int32_t *p_src, const int32_t *p_dst, const int32_t *p_elabel, int64_t Ep,
+                                      int32_t *active_ws, const int32_t *g_node_ptr, const int32_t *g_edge_ptr,
+                                      const int32_t *g_out_ptr, const int32_t *g_out_items, const int32_t *g_dst,
+                                      const int32_t *g_elabel, int32_t *conj, void *stream) {
+    DN_ARG(B >= 0 && total_work >= 0 && Ep >= 0);
+    if (total_work == 0) return DN4GL_OK;
+    DN_ARG(work_ptr && val_ptr && values && p_node_ptr && p_edge_ptr && p_src && p_dst && p_elabel && active_ws &&
+           g_node_ptr && g_edge_ptr && g_out_ptr && g_out_items && g_dst && g_elabel && conj && Ep > 0);
+    cudaStream_t st = as_stream(stream);
+    pattern_active_edges_kernel<<<static_cast<unsigned>(ceil_div64(Ep, 256)), 256, 0, st>>>(B, p_edge_ptr, p_src, p_dst,
+                                                                                          active_ws, Ep);
+    subiso_conjugate_kernel<<<static_cast<unsigned>(ceil_div64(total_work, 256)), 256, 0, st>>>(
+        B, work_ptr, val_ptr, values, p_node_ptr, p_edge_ptr, p_src, p_dst, p_elabel, active_ws, g_node_ptr, g_edge_ptr,
+        g_out_ptr, g_out_items, g_dst, g_elabel, conj, total_work);
+    DN_LAUNCHED_N(2);
+    return DN4GL_OK;
+}

@@ -39,6 +39,50 @@ def node_weights(subiso, graph_b):
     return w.long()
 
 
+def _sorted_out_lists(graph_b):
+    """CSR by source with rows sorted by (dst, edge id): all_edges(order="srcdst"), dataset.py:1508 / train.py:573."""
+    L = lib()
+    dev = graph_b["src"].device
+    Ng = int(graph_b["vlabel"].numel())
+    csr = build_csr(graph_b["src"], graph_b["dst"], Ng, heavy_threshold=0)
+    wsb = L.size("dn4gl_sort_rows_workspace_bytes", Ng)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    L.call("dn4gl_sort_csr_rows", ptr(csr.row_ptr), Ng, ptr(csr.eid), ptr(graph_b["dst"]), ptr(ws), wsb, ptr(error_flag(dev)),
+           _stream())
+    return csr
+
+
+def _work_ptr(subiso, pattern_b, dev):
+    B = int(pattern_b["num_graphs"])
+    m = (pattern_b["edge_ptr"][1:] - pattern_b["edge_ptr"][:-1]).long()
+    work = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+    work[1:] = torch.cumsum(subiso["rows"].long() * m, 0)
+    total = int(work[-1].item())
+    if total >= 2 ** 31:
+        raise ValueError("more than 2^31 (subisomorphism, pattern edge) pairs in one batch")
+    return work.to(torch.int32), total
+
+
+def conjugate_subisomorphisms(subiso, pattern_b, graph_b):
+    """node maps -> edge maps for the conjugate (edge-to-vertex) graphs: ``get_conjugate_subisomorphisms``
+    (utils/graph.py:294-330) + the ``g_eid[...]`` gather of ``convert_to_conjugate`` (train.py:577-587), batched.
+    Returns (work_ptr int32[B+1], conj int64[total]): sample b's (S_b, m_b) matrix of graph-local edge ids is
+    ``conj[work_ptr[b]:work_ptr[b+1]].view(S_b, m_b)``."""
+    require_cuda(graph_b["src"], "graph batch")
+    dev = graph_b["src"].device
+    B, Ep = int(graph_b["num_graphs"]), int(pattern_b["src"].numel())
+    work, total = _work_ptr(subiso, pattern_b, dev)
+    conj = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    if total > 0:
+        csr = _sorted_out_lists(graph_b)
+        active = torch.empty(max(Ep, 1), dtype=torch.int32, device=dev)
+        lib().call("dn4gl_subiso_conjugate", B, ptr(work), total, ptr(subiso["val_ptr"]), ptr(subiso["values"]),
+                   ptr(pattern_b["node_ptr"]), ptr(pattern_b["edge_ptr"]), ptr(pattern_b["src"]), ptr(pattern_b["dst"]),
+                   ptr(pattern_b["elabel"]), Ep, ptr(active), ptr(graph_b["node_ptr"]), ptr(graph_b["edge_ptr"]),
+                   ptr(csr.row_ptr), ptr(csr.eid), ptr(graph_b["dst"]), ptr(graph_b["elabel"]), ptr(conj), _stream())
+    return work, conj[:total].long()
+
+
 def edge_weights(subiso, pattern_b, graph_b):
     """(E_g,) int64 in edge-id order: for every subisomorphism and pattern edge (u, v, l), +1 on every graph edge
     (map[u], map[v]) with label l -- with the reference's run/dict semantics for repeated pattern pairs."""

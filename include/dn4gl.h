@@ -209,6 +209,19 @@ int dn4gl_subiso_edge_weights(int32_t B, const int32_t *work_ptr, int64_t total_
                               const int32_t *g_out_items, const int32_t *g_dst, const int32_t *g_elabel,
                               int64_t Eg, int32_t *weights, void *stream);
 
+/* Batched get_conjugate_subisomorphisms (utils/graph.py:294-330) + the g_eid gather of convert_to_conjugate
+ * (train.py:546-556, 577-587): conj[work_ptr[b] + s * m_b + q] = graph-local id of the edge that pattern edge slot q of
+ * subisomorphism s maps to (slot q = q-th distinct (u, v) pair of the pattern in order of first appearance, label set =
+ * last run with that pair; the last matching edge in (src, dst, id) order wins; unmatched slots and slots beyond the
+ * number of distinct pairs give the first edge of that order, as the reference's zero-initialised matrix does).
+ * Arguments as for dn4gl_subiso_edge_weights, plus g_edge_ptr[B+1]; needs at least one edge per graph with matches.     */
+int dn4gl_subiso_conjugate(int32_t B, const int32_t *work_ptr, int64_t total_work, const int32_t *val_ptr,
+                           const int32_t *values, const int32_t *p_node_ptr, const int32_t *p_edge_ptr,
+                           const int32_t *p_src, const int32_t *p_dst, const int32_t *p_elabel, int64_t Ep,
+                           int32_t *active_ws, const int32_t *g_node_ptr, const int32_t *g_edge_ptr,
+                           const int32_t *g_out_ptr, const int32_t *g_out_items, const int32_t *g_dst,
+                           const int32_t *g_elabel, int32_t *conj, void *stream);
+
 /* ---- a3: PyG read_tu_data canonicalisation ------------------------------------------------- */
 /* remove_self_loops + coalesce [torch-geometric 2.0.2 read_tu_data, called from
  * graph_classification/graph_neural_networks/dataset.py:151]: given the edge list's endpoints

@@ -93,7 +93,8 @@ def gen_match_weights():
         p, g, _ = synth.counting_batch(shape, bs, seed=seed)
         mats = synth.random_subisomorphisms(p, g, seed=seed)
         nw, ew = rd.ref_match_weights(mats, p, g)
-        out["match/%s" % shape] = dict(pattern=_np(p), graph=_np(g), mats=mats, node_weights=nw, edge_weights=ew)
+        out["match/%s" % shape] = dict(pattern=_np(p), graph=_np(g), mats=mats, node_weights=nw, edge_weights=ew,
+                                       conj=rd.ref_conjugate_subisomorphisms(mats, p, g))
     # hand-made: repeated pattern pairs, consecutive (0,1)x2 and NON-consecutive (1,2) ... (1,2): only the last run counts
     p = dict(num_graphs=1, node_ptr=np.array([0, 3], np.int32), edge_ptr=np.array([0, 5], np.int32),
              src=np.array([0, 0, 1, 2, 1], np.int32), dst=np.array([1, 1, 2, 0, 2], np.int32),
@@ -105,7 +106,8 @@ def gen_match_weights():
              elabel=np.array([0, 0, 0, 1, 1, 0, 1, 0], np.int32))
     mats = [np.array([[0, 1, 2], [0, 1, 2], [3, 0, 1]], np.int64)]
     nw, ew = rd.ref_match_weights(mats, p, g)
-    out["match/runs"] = dict(pattern=_np(p), graph=_np(g), mats=mats, node_weights=nw, edge_weights=ew)
+    out["match/runs"] = dict(pattern=_np(p), graph=_np(g), mats=mats, node_weights=nw, edge_weights=ew,
+                             conj=rd.ref_conjugate_subisomorphisms(mats, p, g))
     th.save(out, path)
     print("transforms.pt:", list(out), "runs case:", nw.tolist(), ew.tolist())
 

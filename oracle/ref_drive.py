@@ -215,6 +215,27 @@ def ref_match_weights(mats, pattern_b, graph_b):
     return np.concatenate(nw), np.concatenate(ew)
 
 
+def ref_conjugate_subisomorphisms(mats, pattern_b, graph_b):
+    """the reference's get_conjugate_subisomorphisms (utils/graph.py:294-330, numba) driven per sample exactly as
+    convert_to_conjugate's GraphAdj branch does (train.py:569-587, without its final ``mask``, which is a no-op for the
+    non-negative ids it produces)."""
+    gu_ = refload.subgraph().graph_utils
+    C = refload.subgraph().constants
+    out = []
+    for b, (P, G) in enumerate(zip(batch_to_dgl_list(pattern_b), batch_to_dgl_list(graph_b))):
+        m = np.asarray(mats[b], dtype=np.int64)
+        if m.size == 0 or P.number_of_edges() == 0:
+            out.append(np.zeros((0, P.number_of_edges()), np.int64))
+            continue
+        p_u, p_v, p_e = P.all_edges(form="all", order="eid")
+        p_el = P.edata[C.EDGELABEL][p_e]
+        g_u, g_v, g_e = G.all_edges(form="all", order="srcdst")
+        g_el = G.edata[C.EDGELABEL][g_e]
+        cs = gu_.get_conjugate_subisomorphisms(p_u.numpy(), p_v.numpy(), p_el.numpy(), g_u.numpy(), g_v.numpy(), g_el.numpy(), m)
+        out.append(np.vstack([g_e.numpy()[cs[i]] for i in range(len(cs))]))
+    return out
+
+
 def ref_sub_conjugate(b):
     """reference convert_conjugate_graph, DGL branch (utils/graph.py:77-175)."""
     gu = refload.subgraph().graph_utils

@@ -299,3 +299,41 @@ def subiso_edge_weights(mats, pattern_b, graph_b):
                             w[k] += 1
         W[ge0 + order] = w
     return W
+
+
+def subiso_conjugate(mats, pattern_b, graph_b):
+    """per sample: get_conjugate_subisomorphisms (utils/graph.py:294-330) then ``g_eid[...]`` (train.py:577-587); returns a
+    list of (S_b, m_b) int64 matrices of graph-local edge ids (empty (0, m_b) where there is nothing to map)."""
+    out = []
+    for b, m in enumerate(mats):
+        m = np.asarray(m)
+        pn0, pe0, pe1 = int(pattern_b["node_ptr"][b]), int(pattern_b["edge_ptr"][b]), int(pattern_b["edge_ptr"][b + 1])
+        gn0, ge0, ge1 = int(graph_b["node_ptr"][b]), int(graph_b["edge_ptr"][b]), int(graph_b["edge_ptr"][b + 1])
+        p_len = pe1 - pe0
+        if m.size == 0 or p_len == 0:
+            out.append(np.zeros((0, p_len), np.int64))
+            continue
+        p_u, p_v = _i32(pattern_b["src"])[pe0:pe1] - pn0, _i32(pattern_b["dst"])[pe0:pe1] - pn0
+        p_el = _i32(pattern_b["elabel"])[pe0:pe1]
+        g_u, g_v = _i32(graph_b["src"])[ge0:ge1].astype(np.int64) - gn0, _i32(graph_b["dst"])[ge0:ge1].astype(np.int64) - gn0
+        g_el = _i32(graph_b["elabel"])[ge0:ge1]
+        order = np.lexsort((np.arange(ge1 - ge0), g_v, g_u))
+        su, sv, sl = g_u[order], g_v[order], g_el[order]
+        runs = {}                                 # insertion order = first appearance; value = labels of the last run
+        i = 0
+        while i < p_len:
+            j = i + 1
+            while j < p_len and p_u[j] == p_u[i] and p_v[j] == p_v[i]:
+                j += 1
+            runs[(int(p_u[i]), int(p_v[i]))] = p_el[i:j]
+            i = j
+        conj = np.zeros((len(m), p_len), np.int64)
+        for r, row in enumerate(m):
+            for q, ((u, v), els) in enumerate(runs.items()):
+                gu, gv = int(row[u]), int(row[v])
+                for k in np.flatnonzero((su == gu) & (sv == gv)):
+                    for e in els:
+                        if e == sl[k]:
+                            conj[r, q] = k
+        out.append(order[conj])                   # g_eid[conj_subisomorphisms[i]]
+    return out

@@ -72,8 +72,12 @@ def test_match_weights_match_reference_golden(gold_t, case):
     g = gold_t["match/" + case]
     np.testing.assert_array_equal(OT.subiso_node_weights(g["mats"], g["graph"]), g["node_weights"])
     np.testing.assert_array_equal(OT.subiso_edge_weights(g["mats"], g["pattern"], g["graph"]), g["edge_weights"])
+    for a, r in zip(OT.subiso_conjugate(g["mats"], g["pattern"], g["graph"]), g["conj"]):
+        assert a.shape == r.shape
+        np.testing.assert_array_equal(a, r)
     if case == "runs":      # worked by hand in oracle/gen_golden.py: a later run of the same (u, v) replaces the earlier one
         assert g["edge_weights"].tolist() == [1, 2, 0, 3, 2, 2, 3, 0] and g["node_weights"].tolist() == [3, 3, 2, 1]
+        assert g["conj"][0].tolist() == [[6, 4, 5, 1, 1], [6, 4, 5, 1, 1], [0, 6, 1, 1, 1]]
 
 
 def test_appB_literal_vectors():

@@ -146,4 +146,7 @@ def test_match_weights_live(shape, bs, seed):
     rn, re = rd.ref_match_weights(mats, p, g)
     np.testing.assert_array_equal(OT.subiso_node_weights(mats, g), rn)
     np.testing.assert_array_equal(OT.subiso_edge_weights(mats, p, g), re)
+    for a, r in zip(OT.subiso_conjugate(mats, p, g), rd.ref_conjugate_subisomorphisms(mats, p, g)):
+        assert a.shape == r.shape
+        np.testing.assert_array_equal(a, r)
     assert rn.sum() > 0 and (shape != "small" or re.sum() > 0)

@@ -327,6 +327,10 @@ def test_match_weights_golden(device, case):
     pb, gb = T.to_device(g["pattern"], device), T.to_device(g["graph"], device)
     assert np.array_equal(M.node_weights(sub, gb).cpu().numpy(), g["node_weights"])
     assert np.array_equal(M.edge_weights(sub, pb, gb).cpu().numpy(), g["edge_weights"])
+    work, conj = M.conjugate_subisomorphisms(sub, pb, gb)
+    work, conj = work.cpu().numpy(), conj.cpu().numpy()
+    for b, ref in enumerate(g["conj"]):
+        assert np.array_equal(conj[work[b]: work[b + 1]].reshape(ref.shape), ref), b
 
 
 def test_match_weights_batch512_against_oracle(device):
@@ -342,6 +346,10 @@ def test_match_weights_batch512_against_oracle(device):
     nw, ew = M.node_weights(sub, gb), M.edge_weights(sub, pb, gb)
     assert np.array_equal(nw.cpu().numpy(), O.subiso_node_weights(mats, g))
     assert np.array_equal(ew.cpu().numpy(), O.subiso_edge_weights(mats, p, g))
+    work, conj = M.conjugate_subisomorphisms(sub, pb, gb)
+    work, conj = work.cpu().numpy(), conj.cpu().numpy()
+    for b, ref in enumerate(O.subiso_conjugate(mats, p, g)):
+        assert np.array_equal(conj[work[b]: work[b + 1]].reshape(ref.shape), ref), b
     n0, n1 = int(g["node_ptr"][3]), int(g["node_ptr"][4])
     assert int(nw[n0:n1].sum()) == 0 and int(ew.sum()) > 0
     empty = M.pack_subisomorphisms([np.zeros((0, m.shape[1]), np.int64) for m in mats], device)
