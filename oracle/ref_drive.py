@@ -236,6 +236,64 @@ def ref_conjugate_subisomorphisms(mats, pattern_b, graph_b):
     return out
 
 
+def write_counting_dirs(root, pattern_b, graph_b, counts, mats, layout="own", creator="igraph version 0.9.11"):
+    """dump a synthetic counting batch in the directory layout utils/io.py:145-220 reads.  layout "own": every pattern
+    has its own graphs (graphs/P_i/G_i_k.gml, split by suffix % 10); "shared": all patterns share graphs/G_k.gml
+    (split by suffix % 3).  GML text in python-igraph's writer layout (brackets on their own lines).  Returns the three
+    directory paths."""
+    from dummynode4graphlearning_b200.subgraph_isomorphism import io as sio
+
+    def one(b, i):
+        n0, n1, e0, e1 = int(b["node_ptr"][i]), int(b["node_ptr"][i + 1]), int(b["edge_ptr"][i]), int(b["edge_ptr"][i + 1])
+        return dict(num_nodes=n1 - n0, src=b["src"][e0:e1].astype(np.int64) - n0, dst=b["dst"][e0:e1].astype(np.int64) - n0,
+                    vid=b["vid"][n0:n1], vlabel=b["vlabel"][n0:n1], elabel=b["elabel"][e0:e1],
+                    ekey=np.zeros(e1 - e0, np.int64))
+
+    pd, gd, md = (os.path.join(root, x) for x in ("patterns", "graphs", "metadata"))
+    for d in (pd, gd, md):
+        os.makedirs(d, exist_ok=True)
+    B = int(pattern_b["num_graphs"])
+    if layout == "own":
+        for i in range(B):
+            p = "P_%d" % i
+            sio.write_gml_graph(os.path.join(pd, p + ".gml"), one(pattern_b, i), creator)
+            os.makedirs(os.path.join(gd, p), exist_ok=True)
+            g = "G_%d_%d" % (i, i)
+            sio.write_gml_graph(os.path.join(gd, p, g + ".gml"), one(graph_b, i), creator)
+            sio.write_metadata_csv(os.path.join(md, p + ".csv"), [(g, counts[i], mats[i])])
+    else:
+        for i in range(B):
+            sio.write_gml_graph(os.path.join(gd, "G_%d.gml" % i), one(graph_b, i), creator)
+        for i in range(min(B, 3)):
+            p = "P_%d" % i
+            sio.write_gml_graph(os.path.join(pd, p + ".gml"), one(pattern_b, i), creator)
+            # ground truth is per (pattern, graph): reuse sample i's matrix shape with zero rows where it does not fit
+            rows = [("G_%d" % k, counts[k], mats[i] if k == i else np.zeros((0, mats[i].shape[1]), np.int64))
+                    for k in range(B)]
+            sio.write_metadata_csv(os.path.join(md, p + ".csv"), rows)
+    return pd, gd, md
+
+
+def ref_load_data(pattern_dir, graph_dir, metadata_dir):
+    """the reference's utils/io.py:load_data (igraph.read = the shim's GML reader), graphs flattened to dicts of arrays."""
+    io = refload.subgraph().io
+
+    def flat(g):
+        el = g.get_edgelist()
+        return dict(num_nodes=g.vcount(), src=np.asarray([e[0] for e in el], np.int64),
+                    dst=np.asarray([e[1] for e in el], np.int64),
+                    vid=np.asarray(g.vs["id"], np.int64), vlabel=np.asarray(g.vs["label"], np.int64),
+                    elabel=np.asarray(g.es["label"] if el else [], np.int64),
+                    ekey=np.asarray(g.es["key"] if el else [], np.int64))
+
+    data, shared = io.load_data(pattern_dir, graph_dir, metadata_dir, num_workers=1)
+    out = {}
+    for split, xs in data.items():
+        out[split] = [dict(id=x["id"], pattern=flat(x["pattern"]), graph=flat(x["graph"]), counts=x["counts"],
+                           subisomorphisms=np.asarray(x["subisomorphisms"])) for x in xs]
+    return out, shared
+
+
 def ref_sub_conjugate(b):
     """reference convert_conjugate_graph, DGL branch (utils/graph.py:77-175)."""
     gu = refload.subgraph().graph_utils

@@ -77,6 +77,7 @@ def subgraph():
     ns.basemodel = importlib.import_module("models.basemodel")
     ns.graph_utils = importlib.import_module("utils.graph")
     ns.dl = importlib.import_module("utils.dl")
+    ns.io = importlib.import_module("utils.io")
     ns.train_funcs = _extract_functions(
         os.path.join(_SUB, "train.py"),
         ["process_model_config", "add_dummy_nodes_edges", "add_reversed_edges", "calculate_degrees", "remove_loops",

@@ -146,5 +146,50 @@ class Graph:
 Graph.__module__ = "igraph"
 
 
-def read(*a, **k):  # utils/io.py:51 (GML loader) -- out of scope, never called by the oracle
-    raise NotImplementedError("fake igraph: ig.read is not available")
+def read(path, *a, **k):
+    """``igraph.read`` for the GML files of the counting data sets (utils/io.py:51).  Line-oriented restatement of the
+    python-igraph 0.9 GML reader for the layout igraph itself writes (one ``key value`` per line, ``[`` / ``]`` on their own
+    line or after the key): vertices numbered in file order, ``source`` / ``target`` resolved through the nodes' ``id``,
+    numeric attributes returned as floats (igraph's numeric attribute type is double)."""
+    directed, nodes, edges, cur, kind = False, [], [], None, None
+    pending = None
+    with open(path) as f:
+        for raw in f:
+            line = raw.strip()
+            if not line or line.startswith("#"):
+                continue
+            parts = line.split(None, 1)
+            key = parts[0]
+            val = parts[1].strip() if len(parts) > 1 else None
+            if key == "[":
+                if pending in ("node", "edge"):
+                    kind, cur = pending, {}
+                pending = None
+                continue
+            if key == "]":
+                if kind == "node":
+                    nodes.append(cur)
+                elif kind == "edge":
+                    edges.append(cur)
+                kind, cur = None, None
+                continue
+            if key in ("graph", "node", "edge") and val in (None, "["):
+                if val == "[" and key in ("node", "edge"):
+                    kind, cur = key, {}
+                else:
+                    pending = key
+                continue
+            if kind is None:
+                if key == "directed":
+                    directed = bool(int(val))
+                continue                       # Creator / Version / graph attributes
+            cur[key] = val[1:-1] if val.startswith('"') else float(val)
+    g = Graph(directed=directed)
+    g.add_vertices(len(nodes))
+    index = {nd["id"]: i for i, nd in enumerate(nodes)}
+    for key in dict.fromkeys(k2 for nd in nodes for k2 in nd):
+        g.vs[key] = [nd.get(key) for nd in nodes]
+    g.add_edges([(index[e["source"]], index[e["target"]]) for e in edges])
+    for key in dict.fromkeys(k2 for e in edges for k2 in e if k2 not in ("source", "target")):
+        g.es[key] = [e.get(key) for e in edges]
+    return g
