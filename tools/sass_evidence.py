@@ -53,7 +53,7 @@ def main():
     print("# columns: instructions | registers | static shared bytes | watched mnemonics (count)")
     tot = collections.Counter()
     for k, c in sorted(counts.items(), key=lambda kv: names[kv[0]]):
-        short = re.sub(r"\(.*", "", names[k])
+        short = re.sub(r"\(.*", "", names[k].replace("(anonymous namespace)::", ""))
         short = re.sub(r"^void ", "", short)
         reg, sh = usage.get(k, (-1, -1))
         marks = ", ".join("%s x%d" % (label, c[label]) for label, _ in WATCH if c[label])
