@@ -70,3 +70,46 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "SO_PATH", str(tmp_path / "libdn4gl.so"))
     with pytest.raises(_lib.Dn4glError):
         _lib._Lib()
+
+
+def test_argument_validation_needs_no_device():
+    """shape / null / range violations return DN4GL_EINVAL with a message naming the entry point and the violated
+    condition (include/dn4gl.h: "return value ... text via dn4gl_last_error()") -- checked before any device work, so
+    this runs without a GPU; empty inputs are a successful no-op."""
+    lib = _lib.lib()
+    EINVAL = -1
+    rc = lib.raw("dn4gl_spmm_tiled_f32")(None, None, None, None, 10, 32, 0.0, None, None, 1, None, None, 0,
+                                         200 * 1024, 2, 8, 7, None)                      # warps must be 16 | 24 | 32
+    assert rc == EINVAL
+    msg = lib.raw("dn4gl_last_error")().decode()
+    assert "dn4gl_spmm_tiled_f32" in msg and "warps" in msg
+    rc = lib.raw("dn4gl_spmm_tiled_f32")(None, None, None, None, 10, 30, 0.0, None, None, 1, None, None, 0,
+                                         200 * 1024, 2, 8, 32, None)                     # D % 4 != 0
+    assert rc == EINVAL and "D % 4" in lib.raw("dn4gl_last_error")().decode()
+    rc = lib.raw("dn4gl_spmm_tiled_f32")(None, None, None, None, 10, 32, 0.0, None, None, 1, None, None, 0,
+                                         200 * 1024, 2, 8, 32, None)                     # null operands with work to do
+    assert rc == EINVAL
+    assert lib.raw("dn4gl_spmm_tiled_f32")(None, None, None, None, 0, 32, 0.0, None, None, 0, None, None, 0,
+                                           200 * 1024, 2, 8, 32, None) == 0              # N == 0: nothing to do
+    assert lib.raw("dn4gl_segment_sum_f32")(None, None, None, None, 4, 32, 5, None) == EINVAL      # mode must be 0 | 1
+    assert "dn4gl_segment_sum_f32" in lib.raw("dn4gl_last_error")().decode()
+    assert lib.raw("dn4gl_segment_sum_f32")(None, None, None, None, 0, 32, 0, None) == 0           # B == 0
+    assert lib.raw("dn4gl_make_row_tiles")(None, 0, 0, None, None, 0, None, 0, None, 0, None, None) == EINVAL
+    with pytest.raises(_lib.Dn4glError, match="dn4gl_segment_sum_f32"):
+        lib.call("dn4gl_segment_sum_f32", None, None, None, None, 4, 32, 5, None)
+
+
+def test_tile_capacity_query():
+    """dn4gl_spmm_tiled_cap_rows is the host-side arithmetic the Python tiling uses: monotone in shared memory, inverse
+    in stages and width, 0 for unsupported shapes."""
+    lib = _lib.lib()
+    cap = lambda D, smem, st, npr: lib.size("dn4gl_spmm_tiled_cap_rows", D, smem, st, npr)   # noqa: E731
+    assert cap(32, 200 * 1024, 2, 8) == 623                     # the C2 configuration (profiles/r1g_k1_timeline_c2_static.txt)
+    assert cap(32, 200 * 1024, 2, 8) > cap(32, 200 * 1024, 3, 8) > cap(32, 200 * 1024, 4, 8) > 0
+    assert cap(32, 200 * 1024, 2, 8) > cap(64, 200 * 1024, 2, 8) > cap(512, 200 * 1024, 2, 8) > 0
+    assert cap(32, 100 * 1024, 2, 8) < cap(32, 200 * 1024, 2, 8)
+    assert cap(30, 200 * 1024, 2, 8) == 0 and cap(32, 200 * 1024, 9, 8) == 0 and cap(32, 200 * 1024, 2, 0) == 0
+    # one stage must hold cap rows of features + their index slices
+    for D, st, npr in [(32, 2, 8), (64, 3, 4), (128, 2, 16)]:
+        c = cap(D, 200 * 1024, st, npr)
+        assert c * (D * 4 + npr * 4 + 4) + 96 <= (200 * 1024 // st)
