@@ -113,3 +113,30 @@ def test_tile_capacity_query():
     for D, st, npr in [(32, 2, 8), (64, 3, 4), (128, 2, 16)]:
         c = cap(D, 200 * 1024, st, npr)
         assert c * (D * 4 + npr * 4 + 4) + 96 <= (200 * 1024 // st)
+
+
+def test_every_entry_point_survives_all_zero_arguments():
+    """robustness audit: each status-returning entry point called with NULL pointers and zero sizes either validates
+    (DN4GL_EINVAL + message) or treats the call as an empty no-op (0) -- never a crash, never a device call that could
+    fault.  Runs in a child process so that a segfault would be reported as a failure, not kill the test session."""
+    code = r'''
+import ctypes, json, sys
+sys.path.insert(0, %r)
+from dummynode4graphlearning_b200 import _lib
+protos = _lib.parse_header()
+dll = ctypes.CDLL(_lib.SO_PATH)
+out = {}
+for name, (restype, argtypes) in sorted(protos.items()):
+    if restype is not ctypes.c_int or name in ("dn4gl_version", "dn4gl_set_device", "dn4gl_set_sm_limit"):
+        continue
+    fn = getattr(dll, name); fn.restype = restype; fn.argtypes = argtypes
+    out[name] = fn(*[None if t is ctypes.c_void_p else (0.0 if t is ctypes.c_float else 0) for t in argtypes])
+print(json.dumps(out))
+''' % ROOT
+    p = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
+    assert p.returncode == 0, "child crashed (rc %d): %s" % (p.returncode, p.stderr[-500:])
+    import json
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert len(res) >= 45
+    bad = {k: v for k, v in res.items() if v not in (0, -1)}
+    assert not bad, bad
