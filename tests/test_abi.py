@@ -140,3 +140,28 @@ print(json.dumps(out))
     assert len(res) >= 45
     bad = {k: v for k, v in res.items() if v not in (0, -1)}
     assert not bad, bad
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may import, call or load it (no CPU fallback)."""
+    import ast
+    pkg = os.path.join(ROOT, "dummynode4graphlearning_b200")
+    offenders = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(d, f)
+            tree = ast.parse(open(path).read(), path)
+            for n in ast.walk(tree):
+                mods = []
+                if isinstance(n, ast.Import):
+                    mods = [a.name for a in n.names]
+                elif isinstance(n, ast.ImportFrom) and n.level == 0:
+                    mods = [n.module or ""]
+                if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+                    offenders.append("%s:%d" % (os.path.relpath(path, ROOT), n.lineno))
+            src = open(path).read()
+            if "liborc" in src:
+                offenders.append(os.path.relpath(path, ROOT) + ": mentions liborc")
+    assert not offenders, offenders
