@@ -189,6 +189,7 @@ class BatchedGraph:
         self._csr_in = self._csr_out = None
         self._cache = {}
         self._host_sizes = None
+        self._pad_lengths = (None, None)   # (nodes, edges) overrides of the padded lengths, see set_padded_lengths
 
     # ---- construction -----------------------------------------------------------------------
     @staticmethod
@@ -248,6 +249,25 @@ class BatchedGraph:
     def max_num_edges(self):
         p = self.host_ptrs()[1]
         return int((p[1:] - p[:-1]).max().item()) if p.numel() > 1 else 0
+
+    def set_padded_lengths(self, nodes=None, edges=None):
+        """pad the (B, L, .) readout tensors of this batch to `nodes` / `edges` rows instead of this batch's own maxima.
+        Under data-parallel sharding the counting head and the label filter depend on the padded length of the WHOLE
+        mini-batch (padded rows contribute the head's bias, pattern padding leaks label 0
+        into the gate); a rank that holds a shard passes the batch-wide maxima (``parallel.sync_padded_lengths``) to
+        reproduce the single-process numbers exactly.  None keeps the shard's own maximum."""
+        for name, v, own in (("nodes", nodes, self.max_num_nodes()), ("edges", edges, self.max_num_edges())):
+            if v is not None and int(v) < own:
+                raise ValueError("padded %s length %d is smaller than this batch's longest graph (%d)" % (name, v, own))
+        self._pad_lengths = (None if nodes is None else int(nodes), None if edges is None else int(edges))
+        return self
+
+    def padded_num_nodes(self):
+        """L of the left-padded (B, L, .) node tensors (split_and_batchify_graph_feats, utils/dl.py:51-81)."""
+        return self._pad_lengths[0] if self._pad_lengths[0] is not None else self.max_num_nodes()
+
+    def padded_num_edges(self):
+        return self._pad_lengths[1] if self._pad_lengths[1] is not None else self.max_num_edges()
 
     def all_edges(self, form="uv", order="eid"):
         if order != "eid":

@@ -18,7 +18,7 @@ from . import ops
 from . import transforms as T
 from .graph import CSR, BatchedGraph
 from .graph_classification.data import Batch
-from .parallel import GradientBucket, is_distributed
+from .parallel import GradientBucket, is_distributed, sync_padded_lengths
 
 _HOST_KEYS = ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel", "vid", "eid", "y", "vattr", "e_is_reversed")
 
@@ -307,7 +307,8 @@ def _graph_tensors(g):
     """device tensors a counting-model step reads from a BatchedGraph (fixed order) + the host scalars baked into kernel
     arguments and tensor shapes (padded lengths come from the per-graph maxima)."""
     tensors = [g.src, g.dst, g.node_ptr, g.edge_ptr]
-    scalars = [g.batch_size, g.number_of_nodes(), g.number_of_edges(), g.max_num_nodes(), g.max_num_edges()]
+    scalars = [g.batch_size, g.number_of_nodes(), g.number_of_edges(), g.max_num_nodes(), g.max_num_edges(),
+               g.padded_num_nodes(), g.padded_num_edges()]
     for frame in (g.ndata, g.edata):
         for k in sorted(frame):
             tensors.append(frame[k])
@@ -327,7 +328,7 @@ def _static_graph(g):
     forward (relation CSRs, int32 views, tilings) start empty so that the captured forward recomputes them."""
     c = BatchedGraph(g.src.clone(), g.dst.clone(), g.node_ptr.clone(), g.edge_ptr.clone(),
                      {k: v.clone() for k, v in g.ndata.items()}, {k: v.clone() for k, v in g.edata.items()})
-    c._n, c._host_sizes = g._n, g._host_sizes
+    c._n, c._host_sizes, c._pad_lengths = g._n, g._host_sizes, g._pad_lengths
     for name in ("_csr_in", "_csr_out"):
         c0 = getattr(g, name)
         if c0 is not None:
@@ -367,10 +368,13 @@ class _CapturedCountingStep:
 
 class CountingPipeline:
     def __init__(self, model, optimizer, config, add_dummy=True, rep_reg_w=0.0, neg_slp=0.01, max_grad_norm=8.0,
-                 cuda_graphs=None, max_graphs=8, overlap=None):
+                 cuda_graphs=None, max_graphs=8, overlap=None, exact_sharding=False):
         """config: the dataset maxima BEFORE augmentation (max_npv ... max_ngel).  cuda_graphs / overlap: as in
         ClassificationPipeline (defaults: graphs on exactly when the optimizer was built with capturable=True, the
-        augmentation + CSR builds on a second stream exactly when graphs are on)."""
+        augmentation + CSR builds on a second stream exactly when graphs are on).  exact_sharding: under
+        torch.distributed, all-reduce(max) the four padded lengths of every mini-batch (one 4-int collective and one
+        host read per step) so that a sharded batch gives exactly the single-process head / filter numbers
+        (SURVEY.md 8(e) i, v); off by default -- each rank then pads to its own shard's maxima."""
         self.model, self.opt, self.cfg, self.add_dummy = model, optimizer, config, add_dummy
         self.rep_reg_w, self.neg_slp, self.max_grad_norm = rep_reg_w, neg_slp, max_grad_norm
         self.bucket = getattr(optimizer, "bucket", None) or GradientBucket(model.parameters())
@@ -383,6 +387,7 @@ class CountingPipeline:
         self._graphs, self._max_graphs = {}, max_graphs
         self.overlap = bool(self.cuda_graphs if overlap is None else overlap) and self.device.type == "cuda"
         self._tstream, self._inflight = None, []
+        self.exact_sharding = bool(exact_sharding)
 
     _transform_stream = ClassificationPipeline._transform_stream
     _throttle = ClassificationPipeline._throttle
@@ -397,6 +402,11 @@ class CountingPipeline:
         for g in (pattern, graph):   # compile both CSRs + degrees now (calculate_degrees, train.py:1355-1356)
             g.in_degrees()
             g.out_degrees()
+        if self.exact_sharding and is_distributed():
+            gv, ge, pv, pe = sync_padded_lengths(graph.max_num_nodes(), graph.max_num_edges(),
+                                                 pattern.max_num_nodes(), pattern.max_num_edges())
+            graph.set_padded_lengths(gv, ge)
+            pattern.set_padded_lengths(pv, pe)
         return pattern, graph
 
     def loss_fn(self, out, counts):

@@ -30,8 +30,8 @@ _PRED = {"MeanPredictNet": MeanPredictNet, "SumPredictNet": SumPredictNet, "MaxP
 def _padded_mask(g, kind, dummy=True, reversed_=False):
     """(B, Lmax) bool: True on real (non-padded) rows, minus dummy rows (basemodel.py:905-912) and, for
     edges, minus reversed edges (:1562-1571).  One pad kernel on a ones column."""
-    frame, ptr, L = (g.ndata, g.node_ptr, g.max_num_nodes()) if kind == "node" else \
-                    (g.edata, g.edge_ptr, g.max_num_edges())
+    frame, ptr, L = (g.ndata, g.node_ptr, g.padded_num_nodes()) if kind == "node" else \
+                    (g.edata, g.edge_ptr, g.padded_num_edges())
     n = g.number_of_nodes() if kind == "node" else g.number_of_edges()
     drop = None
     if dummy and "is_dummy" in frame:
@@ -162,7 +162,7 @@ class _CountingBase(nn.Module):
         if self.pred_with_deg:
             feats += [g.out_degrees().float().view(-1, 1), g.in_degrees().float().view(-1, 1)]
         out = th.cat(feats + [rep], dim=-1) if feats else rep
-        return ops.pad_segments(out, g.node_ptr, g.max_num_nodes(), drop)
+        return ops.pad_segments(out, g.node_ptr, g.padded_num_nodes(), drop)
 
     def _edge_readout(self, g, enc, rep, drop):
         u, v = g.all_edges(form="uv", order="eid")
@@ -172,7 +172,7 @@ class _CountingBase(nn.Module):
         if self.pred_with_deg:
             feats += [g.out_degrees().float().view(-1, 1)[u], g.in_degrees().float().view(-1, 1)[v]]
         out = th.cat(feats + [rep], dim=-1) if feats else rep
-        return ops.pad_segments(out, g.edge_ptr, g.max_num_edges(), drop)
+        return ops.pad_segments(out, g.edge_ptr, g.padded_num_edges(), drop)
 
 
 class GraphAdjModel(_CountingBase):

@@ -16,5 +16,5 @@ class ScalarFilter(nn.Module):
         return ((g_x.unsqueeze(2) - p_x.unsqueeze(1)) == 0).any(dim=2)
 
     def gate_from_graphs(self, pattern, graph, kind="node"):
-        Lp_max = pattern.max_num_nodes() if kind == "node" else pattern.max_num_edges()
+        Lp_max = pattern.padded_num_nodes() if kind == "node" else pattern.padded_num_edges()
         return ops.label_filter_gate(graph, pattern, Lp_max, kind)
