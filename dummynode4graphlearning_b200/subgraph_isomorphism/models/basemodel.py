@@ -18,7 +18,7 @@ import torch.nn as nn
 from ... import ops
 from ..utils import OutputDict
 from .embed import (EquivariantEmbedding, MultihotEmbedding, NormalEmbedding, OrthogonalEmbedding,
-                    UniformEmbedding, get_enc_len)
+                    PositionEmbedding, UniformEmbedding, get_enc_len)
 from .filter import ScalarFilter
 from .pred import MaxPredictNet, MeanPredictNet, SumPredictNet
 
@@ -83,11 +83,16 @@ class _CountingBase(nn.Module):
         return getattr(self, {"v": "max_n%sv", "vl": "max_n%svl", "el": "max_n%sel"}[key] % side)
 
     def create_enc_net(self, type, **kw):
-        if kw.get("enc_net", "Multihot") != "Multihot":
-            raise NotImplementedError("only the Multihot encoder is on the hot path")
+        kind = kw.get("enc_net", "Multihot")
+        if kind not in ("Multihot", "Position"):
+            raise NotImplementedError(kind)            # basemodel.py:649-650
         if type == "pattern" and self.share_enc_net:
             return self.g_enc_net
-        enc = OrderedDict((k, MultihotEmbedding(self._max_of(type, k), self.base)) for k in self._enc_keys())
+        if kind == "Multihot":
+            enc = OrderedDict((k, MultihotEmbedding(self._max_of(type, k), self.base)) for k in self._enc_keys())
+        else:                                          # sinusoid tables of the same width (basemodel.py:642-646)
+            enc = OrderedDict((k, PositionEmbedding(get_enc_len(self._max_of(type, k) - 1, self.base) * self.base,
+                                                    self._max_of(type, k))) for k in self._enc_keys())
         for net in enc.values():
             net.weight.requires_grad = False
         return nn.ModuleDict(enc)

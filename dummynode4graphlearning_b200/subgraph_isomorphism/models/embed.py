@@ -83,3 +83,20 @@ class MultihotEmbedding(Embedding):
 
     def extra_repr(self):
         return "base=%d, max_n=%d, enc_dim=%d" % (self.base, self.max_n, self.weight.shape[1])
+
+
+class PositionEmbedding(Embedding):
+    """frozen sinusoid table of ``--enc_net Position`` (embed.py:211-222): row i = [sin(i * f_k) ..., cos(i * f_k) ...]
+    with f_k = 10000^(-2k / embedding_dim).  Same width as the multi-hot table it replaces
+    (``get_enc_len(max_n - 1, base) * base`` columns, basemodel.py:642-646), so every downstream shape is unchanged."""
+
+    def __init__(self, embedding_dim, max_len=512, scale=1):
+        freq_seq = th.arange(0, embedding_dim, 2.0, dtype=th.float)
+        inv_freq = th.pow(10000, (freq_seq / embedding_dim)).reciprocal()
+        sinusoid_inp = th.ger(th.arange(0, max_len, 1.0), inv_freq)
+        super().__init__(max_len, embedding_dim)
+        with th.no_grad():
+            self.weight.copy_(th.cat([th.sin(sinusoid_inp), th.cos(sinusoid_inp)], dim=-1) * scale)
+
+    def extra_repr(self):
+        return "embedding_dim=%d, max_len=%d" % (self.weight.shape[1], self.weight.shape[0])

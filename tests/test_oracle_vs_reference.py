@@ -55,6 +55,8 @@ def test_sub_transforms_live(shape, bs, seed):
     ("live/RGCN", "RGCN", dict(hid_dim=16, pred_hid_dim=16, rep_rgcn_edge_norm="both")),
     ("live/CompGCN", "CompGCN", dict(hid_dim=16, pred_hid_dim=16, rep_compgcn_comp_opt="sub", rep_compgcn_edge_norm="both")),
     ("live/DMPNN", "DMPNN", dict(hid_dim=16, pred_hid_dim=16, node_pred=True, edge_pred=True, pred_return_weights="node,edge")),
+    ("live/RGIN_position", "RGIN", dict(hid_dim=16, pred_hid_dim=16, enc_net="Position")),            # --enc_net Position
+    ("live/DMPNN_position", "DMPNN", dict(hid_dim=16, pred_hid_dim=16, enc_net="Position", node_pred=True, edge_pred=True)),
 ])
 def test_counting_models_live(tag, name, over):
     """the reference's own RGIN / DMPNN classes (fake-DGL graph drives their message / update UDFs) vs the functional
@@ -150,3 +152,24 @@ def test_match_weights_live(shape, bs, seed):
         assert a.shape == r.shape
         np.testing.assert_array_equal(a, r)
     assert rn.sum() > 0 and (shape != "small" or re.sum() > 0)
+
+
+@pytest.mark.parametrize("name", ["RGIN", "DMPNN"])
+def test_position_encoder_matches_reference_class(name):
+    """--enc_net Position (basemodel.py:642-646, embed.py:211-222): the product's sinusoid tables are bit-identical to
+    the reference class's and its models expose the same state_dict keys and shapes."""
+    from dummynode4graphlearning_b200.subgraph_isomorphism import models as PM
+    from oracle import refload
+    ns = refload.subgraph()
+    for d, n in ((14, 65), (10, 17), (10, 18), (2, 2)):
+        assert torch.equal(PM.PositionEmbedding(d, n).weight, ns.embed.PositionEmbedding(d, n).weight)
+    mc = process_model_config(dict(synth.counting_config("small"), add_dummy=True))
+    kw = dict({k: v for k, v in mc.items() if k.startswith("max_")}, hid_dim=16, enc_net="Position", emb_net="Equivariant",
+              filter_net="ScalarFilter", rep_num_graph_layers=2, rep_num_pattern_layers=2, share_enc_net=False)
+    mine = getattr(PM, name)(**kw).state_dict()
+    ref = {"RGIN": ns.rgin.RGIN, "DMPNN": ns.dmpnn.DMPNN}[name](**kw).state_dict()
+    assert sorted(mine) == sorted(ref)
+    for k in mine:
+        assert mine[k].shape == ref[k].shape, k
+        if "enc_net" in k:
+            assert torch.equal(mine[k], ref[k]) and not mine[k].requires_grad, k
