@@ -19,9 +19,86 @@ class Identity(nn.Module):
         return x
 
 
+class Sparsemax(nn.Module):
+    """Euclidean projection of every slice along `dim` onto the probability simplex (Martins & Astudillo 2016;
+    utils/act.py:210-331).  Same operation sequence as the reference -- shift by the maximum, descending sort, support
+    size k = max{j : 1 + j z_(j) > sum_{i<=j} z_(i)}, threshold tau = (sum of the supported z - 1) / k -- so values and
+    autograd gradients agree with it."""
+
+    def __init__(self, dim=-1):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, x):
+        z = x.movedim(self.dim, -1)
+        z = z - z.max(dim=-1, keepdim=True)[0]
+        zs = th.sort(z, dim=-1, descending=True)[0]
+        j = th.arange(1, z.size(-1) + 1, device=z.device, dtype=z.dtype)
+        in_support = (1 + j * zs > th.cumsum(zs, dim=-1)).to(z.dtype)
+        k = (in_support * j).max(dim=-1, keepdim=True)[0]
+        tau = ((in_support * zs).sum(dim=-1, keepdim=True) - 1) / k
+        # maximum(0, .) rather than clamp: an entry that lands exactly on the threshold gets half the gradient, as in
+        # the reference's th.max(zeros, x - taus)
+        return th.maximum(th.zeros_like(z), z - tau).movedim(-1, self.dim)
+
+    def extra_repr(self):
+        return "dim={}".format(self.dim)
+
+
+class GumbelSoftmax(nn.Module):
+    """utils/act.py:357-371: torch's gumbel_softmax (random).  The reference passes `dim` in the position of torch's
+    deprecated `eps` argument, so it always normalises over the last axis; so does this module."""
+
+    def __init__(self, tau=1.0, hard=False, dim=-1):
+        super().__init__()
+        self.tau, self.hard, self.dim = tau, hard, dim
+
+    def forward(self, x):
+        return th.nn.functional.gumbel_softmax(x, tau=self.tau, hard=self.hard, dim=-1)
+
+    def extra_repr(self):
+        return "tau={}, hard={}, dim={}".format(self.tau, self.hard, self.dim)
+
+
+class _Extreme(nn.Module):
+    """keep the extreme entries of every slice along `dim` (all of them on ties), zero the rest; with scale_up the kept
+    entries are rescaled so that the slice keeps its sum (0 where that ratio is undefined)   (utils/act.py:374-455)."""
+
+    pick = None
+
+    def __init__(self, dim=-1, scale_up=False, inplace=False):
+        super().__init__()
+        self.dim, self.scale_up, self.inplace = dim, scale_up, inplace
+
+    def forward(self, x):
+        ext = type(self).pick(x, dim=self.dim, keepdim=True)[0]
+        kept = x * (x == ext).to(x.dtype)
+        if self.scale_up:
+            scale = x.sum(dim=self.dim, keepdim=True) / kept.sum(dim=self.dim, keepdim=True)
+            kept = kept * scale.masked_fill(scale.isnan(), 0.0)
+        if self.inplace:
+            return x.copy_(kept)
+        return kept
+
+    def extra_repr(self):
+        return "dim={}, scale_up={}{}".format(self.dim, self.scale_up, ", inplace=True" if self.inplace else "")
+
+
+class Maximum(_Extreme):
+    pick = staticmethod(th.max)
+
+
+class Minimum(_Extreme):
+    pick = staticmethod(th.min)
+
+
 supported_act_funcs = {
     "none": Identity(),
     "softmax": nn.Softmax(dim=-1),
+    "sparsemax": Sparsemax(dim=-1),
+    "gumbel_softmax": GumbelSoftmax(dim=-1),
+    "maximum": Maximum(dim=-1),
+    "minimum": Minimum(dim=-1),
     "sigmoid": nn.Sigmoid(),
     "tanh": nn.Tanh(),
     "relu": nn.ReLU(),

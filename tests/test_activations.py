@@ -1,0 +1,43 @@
+"""CPU: known answers for the row-wise activation choices of --rep_act_func / --pred_act_func that torch does not ship
+(subgraph_isomorphism/utils/act.py:210-455); the comparison with the reference's own functions is the live test
+tests/test_oracle_vs_reference.py::test_activation_registry_matches_reference."""
+import torch
+
+from dummynode4graphlearning_b200.subgraph_isomorphism.utils import (Maximum, Minimum, Sparsemax, map_activation_str_to_layer,
+                                                                     supported_act_funcs)
+
+
+def test_sparsemax_known_answers():
+    sp = Sparsemax(dim=-1)
+    x = torch.tensor([[0.1, 1.1, 0.2], [5.0, 0.0, 0.0], [0.5, 0.5, 0.5], [1.0, 1.0, 0.5]])
+    y = sp(x)
+    # (0.1, 1.1, 0.2): support {1.1, 0.2}, tau = 0.15 -> (0, 0.95, 0.05); a dominant logit takes everything; ties split
+    assert torch.allclose(y, torch.tensor([[0.0, 0.95, 0.05], [1.0, 0.0, 0.0], [1 / 3, 1 / 3, 1 / 3], [0.5, 0.5, 0.0]]), atol=1e-6)
+    assert torch.allclose(y.sum(-1), torch.ones(4), atol=1e-6) and bool((y >= 0).all())
+    # shift invariance, and other axes / ranks
+    assert torch.allclose(sp(x + 3.0), y, atol=1e-6)
+    z = torch.randn(3, 4, 5, generator=torch.Generator().manual_seed(0))
+    for dim in (0, 1, 2):
+        out = Sparsemax(dim=dim)(z)
+        assert out.shape == z.shape and torch.allclose(out.sum(dim), torch.ones_like(out.sum(dim)), atol=1e-5)
+
+
+def test_maximum_minimum_known_answers():
+    x = torch.tensor([[1.0, 3.0, 3.0, -2.0], [-1.0, -4.0, 0.5, -4.0]])
+    assert Maximum()(x).tolist() == [[0.0, 3.0, 3.0, 0.0], [0.0, 0.0, 0.5, 0.0]]
+    assert Minimum()(x).tolist() == [[0.0, 0.0, 0.0, -2.0], [0.0, -4.0, 0.0, -4.0]]
+    up = Maximum(scale_up=True)(x)                      # kept entries rescaled to the row's sum: 5 / 6 and -8.5 / 0.5
+    assert torch.allclose(up, torch.tensor([[0.0, 2.5, 2.5, 0.0], [0.0, 0.0, -8.5, 0.0]]))
+    assert Maximum(scale_up=True)(torch.zeros(1, 3)).tolist() == [[0.0, 0.0, 0.0]]      # 0 / 0 -> 0, not nan
+    y = x.clone()
+    assert Minimum(inplace=True)(y) is y and y.tolist() == Minimum()(x).tolist()
+
+
+def test_registry_is_complete_and_shared():
+    names = {"none", "softmax", "sparsemax", "gumbel_softmax", "sigmoid", "tanh", "relu", "relu6", "leaky_relu", "prelu", "elu",
+             "celu", "selu", "gelu", "maximum", "minimum"}
+    assert set(supported_act_funcs) == names                                             # utils/act.py:457-473
+    assert map_activation_str_to_layer("relu") is map_activation_str_to_layer("relu")   # shared singletons (App. A-3)
+    assert abs(map_activation_str_to_layer("leaky_relu").negative_slope - 1 / 5.5) < 1e-12
+    g = map_activation_str_to_layer("gumbel_softmax")(torch.zeros(5, 7))
+    assert torch.allclose(g.sum(-1), torch.ones(5), atol=1e-6)

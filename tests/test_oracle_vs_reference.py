@@ -173,3 +173,44 @@ def test_position_encoder_matches_reference_class(name):
         assert mine[k].shape == ref[k].shape, k
         if "enc_net" in k:
             assert torch.equal(mine[k], ref[k]) and not mine[k].requires_grad, k
+
+
+def test_activation_registry_matches_reference():
+    """every --rep_act_func / --pred_act_func choice (utils/act.py:457-473) exists with the reference's values and
+    gradients, including the row-wise ones (sparsemax, maximum, minimum) on ties, 3-D inputs and other dims."""
+    from dummynode4graphlearning_b200.subgraph_isomorphism import utils as PU
+    from oracle import refload
+    import importlib
+    refload.subgraph()                       # installs the shims and puts the reference's package root on sys.path
+    ref = importlib.import_module("utils.act")
+    assert sorted(PU.supported_act_funcs) == sorted(ref.supported_act_funcs)
+    g = torch.Generator().manual_seed(11)
+    xs = [torch.randn(7, 16, generator=g), torch.randn(3, 5, 8, generator=g) * 4,
+          torch.tensor([[1.0, 1.0, 0.5, -2.0], [0.0, 0.0, 0.0, 0.0], [-1.0, -3.0, -1.0, -3.0]])]
+    for name in sorted(ref.supported_act_funcs):
+        if name in ("gumbel_softmax", "prelu"):
+            continue
+        for x in xs:
+            a = x.clone().requires_grad_(True)
+            b = x.clone().requires_grad_(True)
+            ya, yb = PU.map_activation_str_to_layer(name)(a), ref.map_activation_str_to_layer(name)(b)
+            assert torch.equal(ya, yb), name
+            w = torch.arange(ya.numel(), dtype=ya.dtype).view(ya.shape).cos()
+            (ya * w).sum().backward()
+            (yb * w).sum().backward()
+            assert torch.allclose(a.grad, b.grad, rtol=0, atol=1e-7), name
+    for cls in ("Sparsemax", "Maximum", "Minimum"):
+        x = torch.randn(4, 6, 5, generator=g)
+        for dim in (0, 1, -1):
+            kw = [dict(dim=dim)] if cls == "Sparsemax" else [dict(dim=dim), dict(dim=dim, scale_up=True)]
+            for k in kw:
+                assert torch.allclose(getattr(PU, cls)(**k)(x), getattr(ref, cls)(**k)(x), rtol=0, atol=1e-7), (cls, k)
+    y = PU.Maximum(inplace=True, scale_up=True)
+    z1, z2 = x.clone(), x.clone()
+    assert torch.equal(y(z1), ref.Maximum(inplace=True, scale_up=True)(z2)) and torch.equal(z1, z2)
+    torch.manual_seed(5)
+    ya = PU.map_activation_str_to_layer("gumbel_softmax")(xs[0])
+    torch.manual_seed(5)
+    yb = ref.map_activation_str_to_layer("gumbel_softmax")(xs[0])
+    assert torch.equal(ya, yb)
+    assert abs(PU.supported_act_funcs["prelu"].weight.item() - ref.supported_act_funcs["prelu"].weight.item()) < 1e-7
