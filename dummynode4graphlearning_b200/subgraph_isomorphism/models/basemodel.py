@@ -16,7 +16,7 @@ import torch as th
 import torch.nn as nn
 
 from ... import ops
-from ..utils import OutputDict
+from ..utils import OutputDict, expand_dimensions
 from .embed import (EquivariantEmbedding, MultihotEmbedding, NormalEmbedding, OrthogonalEmbedding,
                     PositionEmbedding, UniformEmbedding, get_enc_len)
 from .filter import ScalarFilter
@@ -138,6 +138,45 @@ class _CountingBase(nn.Module):
 
     def refine_edge_weights(self, weights, use_max=False):
         return weights
+
+    # ---- growing a trained model to larger data-set maxima (BaseModel.expand, basemodel.py:167-219) ------------
+    def expand(self, **kw):
+        """what ``train.py:1399`` calls on every loaded checkpoint: the maxima become max(old, new); encoder tables are
+        rebuilt; embedding nets and (with pred_with_enc) the head are rebuilt for the wider encodings and inherit the
+        trained values in their trailing corner (``expand_dimensions(pre_pad=True)``), zeros elsewhere.  The
+        representation nets are left untouched, as in the reference.  Two reference behaviours kept on purpose: with
+        ``share_emb_net`` (default) the pattern embedding net BECOMES the graph's after an expand although the two are
+        independent at construction; on failure the maxima are rolled back and the exception re-raised."""
+        if "base" in kw and kw["base"] != self.base:
+            raise ValueError
+        kw = dict(kw)
+        names = ("max_npv", "max_npvl", "max_npe", "max_npel", "max_ngv", "max_ngvl", "max_nge", "max_ngel")
+        bak = {k: getattr(self, k) for k in names}
+        for k in names:
+            setattr(self, k, max(kw.get(k, -1), bak[k]))
+        try:
+            self.g_enc_net = self.create_enc_net(type="graph", **kw)
+            self.p_enc_net = self.g_enc_net if self.share_enc_net else self.create_enc_net(type="pattern", **kw)
+            new_filter = self.create_filter_net(**kw)
+            expand_dimensions(self.filter_net, new_filter, pre_pad=True)   # raises for filter_net "None", as upstream
+            self.filter_net = new_filter
+            new_g_emb = self.create_emb_net(type="graph", **kw)
+            expand_dimensions(self.g_emb_net, new_g_emb, pre_pad=True)
+            self.g_emb_net = new_g_emb
+            if self.share_emb_net:
+                self.p_emb_net = self.g_emb_net
+            else:
+                new_p_emb = self.create_emb_net(type="pattern", **kw)
+                expand_dimensions(self.p_emb_net, new_p_emb, pre_pad=True)
+                self.p_emb_net = new_p_emb
+            if self.pred_with_enc:
+                new_pred = self.create_pred_net(**kw)
+                expand_dimensions(self.pred_net, new_pred, pre_pad=True)
+                self.pred_net = new_pred
+        except Exception:
+            for k, v in bak.items():
+                setattr(self, k, v)
+            raise
 
     # ---- shared forward pieces ---------------------------------------------------------------------
     def _encode(self, net, g):

@@ -187,6 +187,25 @@ def init_module(x, activation="none", init="uniform"):
         nn.init.zeros_(x.bias)
 
 
+def expand_dimensions(old_module, new_module, pre_pad=True):
+    """grow a trained module into a freshly built larger one (utils/dl.py:157-195): every parameter of `new_module`
+    that also exists (by name) in `old_module` is zeroed and receives the old values in its trailing corner (pre_pad,
+    the layout of the left-padded encodings) or leading corner; parameters without an old counterpart keep their
+    fresh initialisation.  Also accepts two tensors."""
+    with th.no_grad():
+        if isinstance(old_module, th.Tensor):
+            if old_module.dim() < 1 or old_module.dim() > 4:
+                raise NotImplementedError
+            new_module.zero_()
+            corner = tuple(slice(-n, None) if pre_pad else slice(0, n) for n in old_module.shape)
+            new_module[corner].copy_(old_module)
+            return
+        old = dict(old_module.named_parameters())
+        for name, param in new_module.named_parameters():
+            if name in old:
+                expand_dimensions(old[name], param, pre_pad)
+
+
 class OutputDict(dict):
     """Model output: the reference's key set (models/container.py:14-101, basemodel.py:964-980);
     readable both as ``out["pred_c"]`` and ``out.pred_c``; ``None`` entries are kept so that

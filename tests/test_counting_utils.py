@@ -41,3 +41,21 @@ def test_registry_is_complete_and_shared():
     assert abs(map_activation_str_to_layer("leaky_relu").negative_slope - 1 / 5.5) < 1e-12
     g = map_activation_str_to_layer("gumbel_softmax")(torch.zeros(5, 7))
     assert torch.allclose(g.sum(-1), torch.ones(5), atol=1e-6)
+
+
+def test_expand_dimensions_known_answer():
+    """utils/dl.py:157-195: old values land in the trailing corner (pre_pad) or the leading one, zeros elsewhere;
+    parameters that only the new module has keep their initialisation."""
+    import torch.nn as nn
+    from dummynode4graphlearning_b200.subgraph_isomorphism.utils import expand_dimensions
+    old, new = torch.arange(1.0, 7.0).view(2, 3), torch.full((3, 5), 9.0)
+    expand_dimensions(old, new, pre_pad=True)
+    assert new.tolist() == [[0, 0, 0, 0, 0], [0, 0, 1, 2, 3], [0, 0, 4, 5, 6]]
+    new = torch.full((3, 5), 9.0)
+    expand_dimensions(old, new, pre_pad=False)
+    assert new.tolist() == [[1, 2, 3, 0, 0], [4, 5, 6, 0, 0], [0, 0, 0, 0, 0]]
+    a, b = nn.ModuleDict({"x": nn.Linear(2, 2)}), nn.ModuleDict({"x": nn.Linear(4, 2), "y": nn.Linear(3, 1)})
+    keep = b["y"].weight.clone()
+    expand_dimensions(a, b)
+    assert torch.equal(b["x"].weight[:, 2:], a["x"].weight) and float(b["x"].weight.detach()[:, :2].abs().sum()) == 0.0
+    assert torch.equal(b["x"].bias, a["x"].bias) and torch.equal(b["y"].weight, keep)

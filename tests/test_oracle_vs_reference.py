@@ -214,3 +214,38 @@ def test_activation_registry_matches_reference():
     yb = ref.map_activation_str_to_layer("gumbel_softmax")(xs[0])
     assert torch.equal(ya, yb)
     assert abs(PU.supported_act_funcs["prelu"].weight.item() - ref.supported_act_funcs["prelu"].weight.item()) < 1e-7
+
+
+@pytest.mark.parametrize("name,extra", [("RGIN", {}), ("DMPNN", {}), ("CompGCN", {}),
+                                        ("RGIN", dict(share_emb_net=False, share_enc_net=False, pred_with_enc=False))])
+def test_model_expand_matches_reference(name, extra):
+    """BaseModel.expand (basemodel.py:167-219, called by train.py:1399 on every loaded checkpoint): after loading the
+    reference's weights and expanding both models to larger maxima with the same RNG state, the state_dicts are
+    identical (trailing-corner copies, zeros elsewhere, fresh layers for new heads, aliasing quirk included)."""
+    from dummynode4graphlearning_b200.subgraph_isomorphism import models as PM
+    from oracle import refload
+    ns = refload.subgraph()
+    small = dict(max_ngv=33, max_ngvl=9, max_nge=200, max_ngel=10, max_npv=9, max_npvl=9, max_npe=24, max_npel=10)
+    big = dict(max_ngv=65, max_ngvl=17, max_nge=384, max_ngel=10, max_npv=17, max_npvl=17, max_npe=48, max_npel=10)
+    common = dict(hid_dim=16, emb_net="Equivariant", filter_net="ScalarFilter", rep_num_graph_layers=2,
+                  rep_num_pattern_layers=2, pred_with_enc=True, pred_with_deg=True, pred_hid_dim=16)
+    kw = dict(small, **common)
+    kw.update(extra)
+    torch.manual_seed(0)
+    ref = getattr(ns.models, name)(**kw)
+    mine = getattr(PM, name)(**kw)
+    mine.load_state_dict(ref.state_dict())
+    kw2 = dict(big, **common)
+    kw2.update(extra, pred_return_weights="node")
+    torch.manual_seed(1)
+    ref.expand(**kw2)
+    torch.manual_seed(1)
+    mine.expand(**kw2)
+    sa, sb = mine.state_dict(), ref.state_dict()
+    assert sorted(sa) == sorted(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert (mine.p_emb_net is mine.g_emb_net) == (ref.p_emb_net is ref.g_emb_net)
+    assert all(getattr(mine, k) == getattr(ref, k) for k in big)
+    with pytest.raises(ValueError):
+        mine.expand(base=3)
