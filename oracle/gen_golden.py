@@ -226,6 +226,44 @@ def gen_counting_compgcn():
     print("counting_models.pt:", [k for k in out if not k.startswith("_")])
 
 
+def gen_counting_loss():
+    """the full back-propagated loss incl. match terms, produced by the reference's OWN train_epoch
+    (train.py:596-1000, executed verbatim on one mini-batch) for the three criteria -> counting_loss.pt."""
+    base = th.load(os.path.join(OUT, "counting_models.pt"), weights_only=False)
+    b = base["_batch"]
+    Lg = int(np.diff(b["graph"]["node_ptr"]).max())
+    Le = int(np.diff(b["graph"]["edge_ptr"]).max())
+    B = len(b["counts"])
+    gen = th.Generator().manual_seed(77)
+    nw, ew = th.randint(0, 4, (B, Lg), generator=gen), th.randint(0, 4, (B, Le), generator=gen)
+    out = {"_node_weights": nw, "_edge_weights": ew}
+    cases = {
+        "DMPNN/node_edge|MSE": dict(bp_loss="MSE", neg_pred_slp=0.01, match_loss_w=0.5, match_reg_w=0.25, rep_reg_w=1e-3),
+        "DMPNN/node_edge|MAE": dict(bp_loss="MAE", neg_pred_slp=0.1, match_loss_w=1.0, match_reg_w=1.0, rep_reg_w=0.0),
+        "DMPNN/node_edge|SMSE": dict(bp_loss="SMSE", neg_pred_slp=0.05, match_loss_w=0.3, match_reg_w=0.2, rep_reg_w=1e-3,
+                                     max_grad_norm=8.0),
+        "RGIN/bdd4|MSE": dict(bp_loss="MSE", neg_pred_slp=0.01, match_loss_w=0.7, match_reg_w=0.4, rep_reg_w=1e-3),
+    }
+    for tag, conf in cases.items():
+        mtag = tag.split("|")[0]
+        g = base[mtag]
+        model = rd.ref_counting_model(g["name"], g["kwargs"], seed=0)
+        model.load_state_dict(g["state_dict"])
+        th.manual_seed(zlib.crc32(tag.encode()) % 1000)
+        with th.no_grad():   # pred_fc2 / weight_fc2 are zero-initialised (App. A-8): make every term of the loss live;
+            for n, q in model.named_parameters():   # small pred_c so that relu(pred_v - pred_c) is not identically zero
+                if "weight_fc2" in n:
+                    q.normal_(0.0, 0.05)
+                elif "pred_fc2" in n:
+                    q.normal_(0.0, 0.02)
+        metric, loss, grads = rd.ref_train_epoch(model, rd.dgl_batched(b["pattern"]), rd.dgl_batched(b["graph"]), b["counts"],
+                                                 nw.clone(), ew.clone(), conf)
+        out[tag] = dict(model=mtag, conf=conf, state_dict={k: v.clone() for k, v in model.state_dict().items()},
+                        loss=float(loss), eval_metric=float(metric), grads=grads)
+    th.save(out, os.path.join(OUT, "counting_loss.pt"))
+    print("counting_loss.pt:", {k: round(v["loss"], 4) for k, v in out.items() if not k.startswith("_")})
+
+
 def gen_classification():
     out = {}
     raw = synth.tu_batch("mutag", 10, seed=41)
@@ -271,4 +309,5 @@ if __name__ == "__main__":
     gen_counting()
     gen_counting_rgcn()
     gen_counting_compgcn()
+    gen_counting_loss()
     gen_classification()

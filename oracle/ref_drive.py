@@ -294,6 +294,54 @@ def ref_load_data(pattern_dir, graph_dir, metadata_dir):
     return out, shared
 
 
+class _OneBatchLoader:
+    """the only things train_epoch asks of its DataLoader: len(), iteration, and a .dataset that is not an EdgeSeqDataset."""
+
+    def __init__(self, batch):
+        self.batch, self.dataset = batch, object()
+
+    def __len__(self):
+        return 1
+
+    def __iter__(self):
+        return iter([self.batch])
+
+
+class _SnapshotOptimizer:
+    """records the parameter gradients train_epoch has accumulated when it calls step() (it zeroes them right after)."""
+
+    def __init__(self, model):
+        self.model, self.grads = model, None
+
+    def step(self):
+        self.grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in self.model.named_parameters()}
+
+    def zero_grad(self):
+        for p in self.model.parameters():
+            p.grad = None
+
+
+def ref_train_epoch(model, pattern_g, graph_g, counts, node_weights, edge_weights, config):
+    """one mini-batch through the reference's own train_epoch (train.py:596-1000, executed verbatim): returns
+    (eval metric, bp_loss, {parameter name: gradient after clipping}).  config: bp_loss, eval_metric, neg_pred_slp,
+    match_loss_w, match_reg_w, rep_reg_w, max_grad_norm (numbers, not schedules)."""
+    import gc
+    import torch.nn as nn
+    import torch.nn.functional as F
+    sub = refload.subgraph()
+    te = refload._extract_functions(os.path.join(refload._SUB, "train.py"), ["train_epoch"],
+                                    extra={"np": np, "F": F, "nn": nn, "gc": gc}).train_epoch
+    cfg = dict(train_epochs=1, lr=1e-3, train_grad_steps=1, train_log_steps=1, eval_metric="MAE", bp_loss="MSE",
+               neg_pred_slp=0.01, match_loss_w=0.0, match_reg_w=0.0, rep_reg_w=0.0, max_grad_norm=0.0)
+    cfg.update(config)
+    opt = _SnapshotOptimizer(model)
+    opt.zero_grad()
+    batch = (["x"] * len(counts), pattern_g, graph_g, th.as_tensor(counts), (node_weights, edge_weights))
+    metric, loss = te(model, opt, None, "train", _OneBatchLoader(batch), th.device("cpu"), cfg, 0, None, None)
+    assert sub is not None
+    return metric, loss, opt.grads
+
+
 def ref_sub_conjugate(b):
     """reference convert_conjugate_graph, DGL branch (utils/graph.py:77-175)."""
     gu = refload.subgraph().graph_utils

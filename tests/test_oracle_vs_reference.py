@@ -249,3 +249,46 @@ def test_model_expand_matches_reference(name, extra):
     assert all(getattr(mine, k) == getattr(ref, k) for k in big)
     with pytest.raises(ValueError):
         mine.expand(base=3)
+
+
+@pytest.mark.parametrize("name,kind,seed", [("DMPNN", "SMSE", 7), ("RGIN", "MAE", 8), ("CompGCN", "MSE", 9)])
+def test_bp_loss_live_against_reference_train_epoch(name, kind, seed):
+    """one mini-batch through the reference's own train_epoch (verbatim, with its match terms, criteria
+    and clipping) vs the product's losses.counting_bp_loss applied to the same reference model's outputs: loss and every
+    parameter gradient."""
+    from dummynode4graphlearning_b200.subgraph_isomorphism.losses import counting_bp_loss
+    from oracle import ref_drive as rd
+    p, g, counts = synth.counting_batch("small", 5, seed=seed)
+    cfg = dict(synth.counting_config("small"), add_dummy=True)
+    mc = process_model_config(cfg)
+    pd_ = OT.sub_add_dummy(p, cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])
+    gd_ = OT.sub_add_dummy(g, cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"])
+    over = dict(hid_dim=16, pred_hid_dim=16, pred_return_weights="node,edge" if name != "RGIN" else "node")
+    if name != "RGIN":
+        over.update(node_pred=True, edge_pred=True)
+    kw = rd.counting_kwargs({k: v for k, v in mc.items() if k.startswith("max_")}, **over)
+    model = rd.ref_counting_model(name, kw, seed=seed)
+    with torch.no_grad():
+        for n, q in model.named_parameters():
+            if "weight_fc2" in n:
+                q.normal_(0.0, 0.05)
+            elif "pred_fc2" in n:
+                q.normal_(0.0, 0.02)
+    gen = torch.Generator().manual_seed(seed)
+    nw = torch.randint(0, 4, (5, int(np.diff(gd_["node_ptr"]).max())), generator=gen)
+    ew = torch.randint(0, 4, (5, int(np.diff(gd_["edge_ptr"]).max())), generator=gen)
+    conf = dict(bp_loss=kind, neg_pred_slp=0.05, match_loss_w=0.3, match_reg_w=0.2, rep_reg_w=1e-3, max_grad_norm=0.0)
+    _, ref_loss, ref_grads = rd.ref_train_epoch(model, rd.dgl_batched(pd_), rd.dgl_batched(gd_), counts, nw.clone(),
+                                                ew.clone(), conf)
+    model.zero_grad()
+    out = model(rd.dgl_batched(pd_), rd.dgl_batched(gd_))
+    loss, terms = counting_bp_loss(out, torch.from_numpy(counts), nw, ew, model=model, bp_loss=kind, neg_slp=0.05,
+                                   rep_reg_w=1e-3, match_loss_w=0.3, match_reg_w=0.2)
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-6 * abs(ref_loss)
+    assert float(terms["match_v_loss"]) > 0 and float(terms["rep_reg"]) > 0
+    loss.backward()
+    for n, q in model.named_parameters():
+        if ref_grads[n] is None:
+            assert q.grad is None, n
+        else:
+            assert_close_rel(q.grad, ref_grads[n], 1e-6, "grad " + n)
