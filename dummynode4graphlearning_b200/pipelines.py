@@ -368,13 +368,17 @@ class _CapturedCountingStep:
 
 class CountingPipeline:
     def __init__(self, model, optimizer, config, add_dummy=True, rep_reg_w=0.0, neg_slp=0.01, max_grad_norm=8.0,
-                 cuda_graphs=None, max_graphs=8, overlap=None, exact_sharding=False):
+                 cuda_graphs=None, max_graphs=8, overlap=None, exact_sharding=False, bp_loss="MSE", match_loss_w=0.0,
+                 match_reg_w=0.0):
         """config: the dataset maxima BEFORE augmentation (max_npv ... max_ngel).  cuda_graphs / overlap: as in
         ClassificationPipeline (defaults: graphs on exactly when the optimizer was built with capturable=True, the
         augmentation + CSR builds on a second stream exactly when graphs are on).  exact_sharding: under
         torch.distributed, all-reduce(max) the four padded lengths of every mini-batch (one 4-int collective and one
         host read per step) so that a sharded batch gives exactly the single-process head / filter numbers
-        (SURVEY.md 8(e) i, v); off by default -- each rank then pads to its own shard's maxima."""
+        (SURVEY.md 8(e) i, v); off by default -- each rank then pads to its own shard's maxima.  bp_loss / match_loss_w /
+        match_reg_w: criterion and weights of the match terms (train.py:620-627, 776-813); they only enter steps that
+        are given per-node / per-edge match weights (``train_on(..., node_weights=, edge_weights=)``), which run
+        eagerly (the targets change with every mini-batch)."""
         self.model, self.opt, self.cfg, self.add_dummy = model, optimizer, config, add_dummy
         self.rep_reg_w, self.neg_slp, self.max_grad_norm = rep_reg_w, neg_slp, max_grad_norm
         self.bucket = getattr(optimizer, "bucket", None) or GradientBucket(model.parameters())
@@ -388,6 +392,7 @@ class CountingPipeline:
         self.overlap = bool(self.cuda_graphs if overlap is None else overlap) and self.device.type == "cuda"
         self._tstream, self._inflight = None, []
         self.exact_sharding = bool(exact_sharding)
+        self.bp_loss, self.match_loss_w, self.match_reg_w = bp_loss, match_loss_w, match_reg_w
 
     _transform_stream = ClassificationPipeline._transform_stream
     _throttle = ClassificationPipeline._throttle
@@ -418,10 +423,22 @@ class CountingPipeline:
                     loss = loss + self.rep_reg_w * crit(out[k], torch.zeros_like(out[k]), 1) * out[k].size(1)
         return loss
 
-    def _train_body(self, pattern, graph, counts):
+    def match_loss_fn(self, out, counts, graph, node_weights, edge_weights):
+        """the reference's full bp_loss (losses.counting_bp_loss) with flat per-node / per-edge match weights of the
+        augmented graph batch (matching.node_weights / edge_weights), left-padded here like the model's outputs."""
+        from .subgraph_isomorphism.losses import counting_bp_loss, pad_match_weights
+        nw = None if node_weights is None else pad_match_weights(node_weights, graph.node_ptr, graph.padded_num_nodes())
+        ew = None if edge_weights is None else pad_match_weights(edge_weights, graph.edge_ptr, graph.padded_num_edges())
+        return counting_bp_loss(out, counts, nw, ew, model=self.model, bp_loss=self.bp_loss, neg_slp=self.neg_slp,
+                                rep_reg_w=self.rep_reg_w, match_loss_w=self.match_loss_w, match_reg_w=self.match_reg_w)[0]
+
+    def _train_body(self, pattern, graph, counts, node_weights=None, edge_weights=None):
         self.bucket.zero()
         out = self.model(pattern, graph)
-        loss = self.loss_fn(out, counts)
+        if node_weights is None and edge_weights is None:
+            loss = self.loss_fn(out, counts)
+        else:
+            loss = self.match_loss_fn(out, counts, graph, node_weights, edge_weights)
         loss.backward()
         self.bucket.gather()
         if is_distributed():
@@ -437,9 +454,11 @@ class CountingPipeline:
     def replayed_library_kernels(self):
         return sum(e.replays * e.library_kernels for e in self._graphs.values() if isinstance(e, _CapturedCountingStep))
 
-    def train_on(self, pattern, graph, counts):
+    def train_on(self, pattern, graph, counts, node_weights=None, edge_weights=None):
         if not self.model.training:      # Module.train() walks every submodule (~0.2 ms of host time per step)
             self.model.train()
+        if node_weights is not None or edge_weights is not None:
+            return self._train_body(pattern, graph, counts, node_weights, edge_weights)
         if not self.cuda_graphs:
             return self._train_body(pattern, graph, counts)
         tp, sp = _graph_tensors(pattern)

@@ -28,6 +28,20 @@ def pack_subisomorphisms(mats, device=None):
     return out
 
 
+def add_dummy_to_subisomorphisms(mats, graph_b):
+    """what ``add_dummy_nodes_edges`` does to a sample's ground truth (train.py:467-472): every subisomorphism also maps
+    the pattern's dummy node to the graph's dummy node, whose graph-local id is the graph's ORIGINAL node count.
+    mats: per-sample (S_b, np_b) arrays; graph_b: the batch BEFORE augmentation (host numpy)."""
+    n = np.diff(np.asarray(graph_b["node_ptr"]))
+    out = []
+    for b, m in enumerate(mats):
+        m = np.asarray(m, dtype=np.int64)
+        if m.ndim != 2:
+            m = m.reshape(0, 0)
+        out.append(np.concatenate([m, np.full((m.shape[0], 1), int(n[b]), dtype=np.int64)], axis=1))
+    return out
+
+
 def node_weights(subiso, graph_b):
     """(N_g,) int64: number of subisomorphism entries that hit each graph node (zeros for samples without matches)."""
     require_cuda(graph_b["src"], "graph batch")

@@ -59,3 +59,15 @@ def test_expand_dimensions_known_answer():
     expand_dimensions(a, b)
     assert torch.equal(b["x"].weight[:, 2:], a["x"].weight) and float(b["x"].weight.detach()[:, :2].abs().sum()) == 0.0
     assert torch.equal(b["x"].bias, a["x"].bias) and torch.equal(b["y"].weight, keep)
+
+
+def test_add_dummy_to_subisomorphisms():
+    """train.py:437-443: the dummy column is the graph's ORIGINAL node count; samples without matches stay empty."""
+    import numpy as np
+    from dummynode4graphlearning_b200.subgraph_isomorphism.matching import add_dummy_to_subisomorphisms, pack_subisomorphisms
+    g = dict(node_ptr=np.array([0, 5, 12, 15], dtype=np.int32))
+    mats = [np.array([[0, 1], [3, 4]]), np.zeros((0, 3), dtype=np.int64), np.array([[2, 1, 0]])]
+    out = add_dummy_to_subisomorphisms(mats, g)
+    assert out[0].tolist() == [[0, 1, 5], [3, 4, 5]] and out[1].shape == (0, 4) and out[2].tolist() == [[2, 1, 0, 3]]
+    packed = pack_subisomorphisms(out)
+    assert packed["val_ptr"].tolist() == [0, 6, 6, 10] and packed["rows"].tolist() == [2, 0, 1]
