@@ -277,12 +277,35 @@ __device__ __forceinline__ void process_tile_fast(const TileAddr<LANES, VEC> &ta
                     add4(acc[k], v0); add4(acc[k], v1); add4(acc[k], v2); add4(acc[k], v3);
                 }
             }
+#ifdef DN4GL_K1_TAIL_ILP
+            // EXPERIMENT (off in the product build, `make libdn4gl_exp.so`): the 1..3 neighbours left after the
+            // four-wide batches are fetched together -- all index loads, then all row loads, then the adds in CSR
+            // order (bit-identical result) -- instead of one dependent col -> x -> add chain per neighbour.  Absent
+            // neighbours re-read the first one (a valid address) and are not added.
+            {
+                const int rem = static_cast<int>(ce - ca) >> 2;   // 0..3
+                if (rem > 0) {
+                    const uint32_t c0 = static_cast<uint32_t>(lds32(ca));
+                    const uint32_t c1 = rem > 1 ? static_cast<uint32_t>(lds32(ca + 4u)) : c0;
+                    const uint32_t c2 = rem > 2 ? static_cast<uint32_t>(lds32(ca + 8u)) : c0;
+                    const uint32_t a0 = xa + c0 * ROWB, a1 = xa + c1 * ROWB, a2 = xa + c2 * ROWB;
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        const float4 v0 = lds128(a0 + k * KB), v1 = lds128(a1 + k * KB), v2 = lds128(a2 + k * KB);
+                        add4(acc[k], v0);
+                        if (rem > 1) add4(acc[k], v1);
+                        if (rem > 2) add4(acc[k], v2);
+                    }
+                }
+            }
+#else
 #pragma unroll 1
             for (; ca < ce; ca += 4u) {
                 const uint32_t a0 = xa + static_cast<uint32_t>(lds32(ca)) * ROWB;
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) add4(acc[k], lds128(a0 + k * KB));
             }
+#endif
             if (self_scale != 0.f) {
                 const uint32_t a0 = xa + static_cast<uint32_t>(row) * ROWB;
 #pragma unroll
