@@ -18,3 +18,8 @@ for V in base exp; do
   timeout 400 python tools/agg_sweep.py > gpurun_out/${TAG}_ab_sweep_$V.jsonl 2> gpurun_out/${TAG}_ab_sweep_$V.err
   echo "$V sweep rc=$?"; tail -3 gpurun_out/${TAG}_ab_sweep_$V.jsonl | cut -c1-300
 done
+unset DN4GL_LIB
+for S in 3 4; do   # three / four smaller stages instead of the automatic choice (2 at C2), product build
+  DN4GL_TILE_STAGES=$S timeout 300 python tools/bench_k1_c2.py > gpurun_out/${TAG}_ab_k1_c2_stages$S.jsonl 2> gpurun_out/${TAG}_ab_k1_c2_stages$S.err
+  echo "stages=$S rc=$?"; tail -3 gpurun_out/${TAG}_ab_k1_c2_stages$S.jsonl | cut -c1-300
+done
