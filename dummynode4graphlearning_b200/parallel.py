@@ -25,6 +25,36 @@ def shard_range(num_items, rank, world_size):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def balanced_shard_ranges(work, world_size):
+    """contiguous slices [lo, hi) of a mini-batch, one per rank, balanced by per-sample work instead of by count
+    (work = nodes + edges of a sample; the reference's BucketSampler, utils/sampler.py:59-64, already
+    puts samples of similar size next to each other, so contiguous cuts suffice).  Cut k is placed where the running sum
+    of work crosses k / world_size of the total, at the nearer sample boundary; every rank gets at least one sample when
+    there are enough samples.  Returns a list of world_size (lo, hi) pairs covering [0, len(work))."""
+    n = len(work)
+    w = [max(float(x), 0.0) for x in work]
+    total = sum(w)
+    if world_size <= 1 or n == 0:
+        return [(0, n)] + [(n, n)] * (max(world_size, 1) - 1)
+    prefix = [0.0]
+    for x in w:
+        prefix.append(prefix[-1] + x)
+    cuts, lo = [0], 0
+    for k in range(1, world_size):
+        target = total * k / world_size
+        i = lo
+        while i < n and prefix[i + 1] <= target:
+            i += 1
+        if i < n and (target - prefix[i]) > (prefix[i + 1] - target):   # the boundary after sample i is nearer
+            i += 1
+        i = max(i, min(lo + 1, n))                 # at least one sample for the previous rank ...
+        i = min(i, max(n - (world_size - k), lo))  # ... and leave one for each rank still to come, when possible
+        cuts.append(i)
+        lo = i
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
+
+
 class GradientBucket:
     """Flat fp32 view over all trainable parameters' gradients: one collective per step."""
 

@@ -12,7 +12,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dummynode4graphlearning_b200.parallel import GradientBucket, max_over_ranks, shard_range, sync_padded_lengths
+from dummynode4graphlearning_b200.parallel import (GradientBucket, balanced_shard_ranges, max_over_ranks, shard_range,
+                                                   sync_padded_lengths)
 
 
 def _free_port():
@@ -106,6 +107,29 @@ def test_shard_range_partitions():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             lens = [b - a for a, b in spans]
             assert max(lens) - min(lens) <= 1
+
+
+def test_balanced_shard_ranges():
+    """contiguous cuts by work: cover the batch, never empty while samples remain, and no rank carries more than the ideal
+    share plus one sample; with size-sorted batches (BucketSampler) they beat the by-count split."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 64, 512):
+        for w in (1, 2, 3, 8):
+            work = rng.integers(10, 600, n).astype(float)
+            spans = balanced_shard_ranges(work, w)
+            assert len(spans) == w and spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            if n >= w:
+                assert all(b > a for a, b in spans)
+                loads = [work[a:b].sum() for a, b in spans]
+                assert max(loads) <= work.sum() / w + work.max() + 1e-9
+    work = np.sort(rng.integers(10, 2000, 512)).astype(float)          # one size-sorted batch of 512 samples
+    by_work = max(work[a:b].sum() for a, b in balanced_shard_ranges(work, 8))
+    by_count = max(work[a:b].sum() for a, b in (shard_range(512, r, 8) for r in range(8)))
+    assert by_work < 0.65 * by_count
+    assert balanced_shard_ranges([], 4) == [(0, 0)] * 4 and balanced_shard_ranges([5.0, 1.0], 1) == [(0, 2)]
+    assert balanced_shard_ranges([0.0, 0.0, 0.0], 3) == [(0, 1), (1, 2), (2, 3)]
 
 
 def test_bucket_single_process_is_identity():
