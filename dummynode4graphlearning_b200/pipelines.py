@@ -369,7 +369,7 @@ class _CapturedCountingStep:
 class CountingPipeline:
     def __init__(self, model, optimizer, config, add_dummy=True, rep_reg_w=0.0, neg_slp=0.01, max_grad_norm=8.0,
                  cuda_graphs=None, max_graphs=8, overlap=None, exact_sharding=False, bp_loss="MSE", match_loss_w=0.0,
-                 match_reg_w=0.0):
+                 match_reg_w=0.0, remove_loops=False, add_rev=False, convert_conj=False):
         """config: the dataset maxima BEFORE augmentation (max_npv ... max_ngel).  cuda_graphs / overlap: as in
         ClassificationPipeline (defaults: graphs on exactly when the optimizer was built with capturable=True, the
         augmentation + CSR builds on a second stream exactly when graphs are on).  exact_sharding: under
@@ -378,7 +378,10 @@ class CountingPipeline:
         (SURVEY.md 8(e) i, v); off by default -- each rank then pads to its own shard's maxima.  bp_loss / match_loss_w /
         match_reg_w: criterion and weights of the match terms (train.py:620-627, 776-813); they only enter steps that
         are given per-node / per-edge match weights (``train_on(..., node_weights=, edge_weights=)``), which run
-        eagerly (the targets change with every mini-batch)."""
+        eagerly (the targets change with every mini-batch).  remove_loops / add_rev / convert_conj: the reference's other
+        data-set level preprocessing switches, applied per mini-batch on the GPU in the reference's order
+        (train.py:1271-1340: loops, reversed edges, dummy, edge-to-vertex), each with the maxima the previous steps
+        leave behind; build the model with ``transforms.process_model_config`` of the same switches."""
         self.model, self.opt, self.cfg, self.add_dummy = model, optimizer, config, add_dummy
         self.rep_reg_w, self.neg_slp, self.max_grad_norm = rep_reg_w, neg_slp, max_grad_norm
         self.bucket = getattr(optimizer, "bucket", None) or GradientBucket(model.parameters())
@@ -393,16 +396,30 @@ class CountingPipeline:
         self._tstream, self._inflight = None, []
         self.exact_sharding = bool(exact_sharding)
         self.bp_loss, self.match_loss_w, self.match_reg_w = bp_loss, match_loss_w, match_reg_w
+        self.remove_loops, self.add_rev, self.convert_conj = bool(remove_loops), bool(add_rev), bool(convert_conj)
 
     _transform_stream = ClassificationPipeline._transform_stream
     _throttle = ClassificationPipeline._throttle
     _mark_step = ClassificationPipeline._mark_step
 
-    def transform(self, p_dev, g_dev):
+    def augment(self, p_dev, g_dev):
+        """flat device batches -> flat device batches after the configured preprocessing switches (no CSR yet)."""
         c = self.cfg
-        if self.add_dummy:
-            p_dev = T.sub_add_dummy(p_dev, c["max_npv"], c["max_npvl"], c["max_npe"], c["max_npel"])
-            g_dev = T.sub_add_dummy(g_dev, c["max_ngv"], c["max_ngvl"], c["max_nge"], c["max_ngel"])
+        npe, npel, nge, ngel = c["max_npe"], c["max_npel"], c["max_nge"], c["max_ngel"]
+        if self.remove_loops:                                   # train.py:1271-1274
+            p_dev, g_dev = T.sub_remove_loops(p_dev), T.sub_remove_loops(g_dev)
+        if self.add_rev:                                        # train.py:1310-1319: maxima double afterwards
+            p_dev, g_dev = T.sub_add_reversed(p_dev, npe, npel), T.sub_add_reversed(g_dev, nge, ngel)
+            npe, npel, nge, ngel = 2 * npe, 2 * npel, 2 * nge, 2 * ngel
+        if self.add_dummy:                                      # train.py:1322-1334
+            p_dev = T.sub_add_dummy(p_dev, c["max_npv"], c["max_npvl"], npe, npel)
+            g_dev = T.sub_add_dummy(g_dev, c["max_ngv"], c["max_ngvl"], nge, ngel)
+        if self.convert_conj:                                   # train.py:1337-1340 -> convert_to_conjugate :564-593
+            p_dev, g_dev = T.sub_conjugate(p_dev), T.sub_conjugate(g_dev)
+        return p_dev, g_dev
+
+    def transform(self, p_dev, g_dev):
+        p_dev, g_dev = self.augment(p_dev, g_dev)
         pattern, graph = BatchedGraph.from_batch(p_dev, self.device), BatchedGraph.from_batch(g_dev, self.device)
         for g in (pattern, graph):   # compile both CSRs + degrees now (calculate_degrees, train.py:1355-1356)
             g.in_degrees()

@@ -74,3 +74,24 @@ def batches_equal(a, b, keys):
         y = b[k].cpu().numpy() if isinstance(b[k], torch.Tensor) else np.asarray(b[k])
         assert x.shape == y.shape, (k, x.shape, y.shape)
         assert np.array_equal(x, y), (k, np.flatnonzero(x != y)[:8])
+
+
+def oracle_preprocess_chain(p, g, cfg, remove_loops, add_rev, add_dummy, convert_conj):
+    """the data-set level switches in the order of train.py:1271-1340, each with the maxima its predecessors leave."""
+    npe, npel, nge, ngel = cfg["max_npe"], cfg["max_npel"], cfg["max_nge"], cfg["max_ngel"]
+    if remove_loops:
+        p, g = _OT().sub_remove_loops(p), _OT().sub_remove_loops(g)
+    if add_rev:
+        p, g = _OT().sub_add_reversed(p, npe, npel), _OT().sub_add_reversed(g, nge, ngel)
+        npe, npel, nge, ngel = 2 * npe, 2 * npel, 2 * nge, 2 * ngel
+    if add_dummy:
+        p = _OT().sub_add_dummy(p, cfg["max_npv"], cfg["max_npvl"], npe, npel)
+        g = _OT().sub_add_dummy(g, cfg["max_ngv"], cfg["max_ngvl"], nge, ngel)
+    if convert_conj:
+        p, g = _OT().sub_conjugate(p), _OT().sub_conjugate(g)
+    return p, g
+
+
+def _OT():
+    from oracle import transforms
+    return transforms

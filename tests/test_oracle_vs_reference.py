@@ -9,7 +9,7 @@ import torch
 
 from dummynode4graphlearning_b200 import synth
 from dummynode4graphlearning_b200.transforms import process_model_config
-from helpers import assert_close_rel, batches_equal, oracle_cfg
+from helpers import assert_close_rel, batches_equal, oracle_cfg, oracle_preprocess_chain
 from oracle import models as OM
 from oracle import transforms as OT
 
@@ -292,3 +292,34 @@ def test_bp_loss_live_against_reference_train_epoch(name, kind, seed):
             assert q.grad is None, n
         else:
             assert_close_rel(q.grad, ref_grads[n], 1e-6, "grad " + n)
+
+
+@pytest.mark.parametrize("flags", [(True, True, True, True), (False, True, True, False), (True, False, True, True),
+                                   (False, True, False, True)])
+def test_preprocessing_chain_live(flags):
+    """remove_loops -> add_reversed_edges -> add_dummy_nodes_edges -> convert_to_conjugate chained as train.py's main
+    does (:1271-1340), reference functions vs the oracle chain that CountingPipeline.augment mirrors on the GPU."""
+    from oracle import ref_drive as rd
+    remove_loops, add_rev, add_dummy, convert_conj = flags
+    p, g, _ = synth.counting_batch("small", 7, seed=sum(flags) * 31 + 5)
+    g = dict(g)
+    g["dst"] = g["dst"].copy()
+    g["dst"][::5] = g["src"][::5]                     # plant loops
+    cfg = synth.counting_config("small")
+    rp, rg = p, g
+    npe, npel, nge, ngel = cfg["max_npe"], cfg["max_npel"], cfg["max_nge"], cfg["max_ngel"]
+    if remove_loops:
+        rp, rg = rd.ref_sub_remove_loops(rp, rg)
+    if add_rev:
+        rp, rg = rd.ref_sub_add_reversed(rp, rg, cfg)
+        npe, npel, nge, ngel = 2 * npe, 2 * npel, 2 * nge, 2 * ngel
+    if add_dummy:
+        rp, rg = rd.ref_sub_add_dummy(rp, rg, dict(cfg, max_npe=npe, max_npel=npel, max_nge=nge, max_ngel=ngel))
+    if convert_conj:
+        rp, rg = rd.ref_sub_conjugate(rp), rd.ref_sub_conjugate(rg)
+    op, og = oracle_preprocess_chain(p, g, cfg, *flags)
+    keys = [k for k in ("node_ptr", "edge_ptr", "src", "dst", "vid", "vlabel", "eid", "elabel", "v_is_dummy", "e_is_dummy",
+                        "e_is_reversed", "v_is_reversed") if k in rg and k in og]
+    assert {"node_ptr", "edge_ptr", "src", "dst", "vid", "vlabel", "eid", "elabel"} <= set(keys)
+    batches_equal(op, rp, keys)
+    batches_equal(og, rg, keys)
