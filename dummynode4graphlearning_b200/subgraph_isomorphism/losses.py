@@ -12,10 +12,47 @@ the model (``refine_node_weights``), and -- exactly as the reference does -- zer
 on masked rows (padding, dummy nodes, reversed edges) in place and outside autograd before the criteria are applied.
 Pure tensor code: it runs wherever the model's outputs live.
 """
+import math
+
 import torch as th
 import torch.nn.functional as F
 
 _CRITERIA = {"MAE": F.l1_loss, "MSE": F.mse_loss, "SMSE": F.smooth_l1_loss}
+
+
+NUM_CYCLES = 2        # constants.py:39
+_PI = 3.141592653589793
+
+
+def scheduled_value(spec, step, total_steps, num_cycles=NUM_CYCLES):
+    """value of a loss-weight / slope option at training step `step` (train.py:648-740).  `spec` is a number, or the
+    CLI form ``anneal_<shape>$a$b`` / ``cyclical_<shape>$a$b`` with shape in {linear, cosine, constant, none}
+    (config.py defaults: neg_pred_slp ``anneal_cosine$1.0$0.01``, match_reg_w ``anneal_cosine$0.01$0.0``): within each
+    of `num_cycles` cycles over `total_steps` the value moves from a to b during the first half; an annealed value then
+    stays at b, a cyclical one returns to a (linear) or follows the full cosine period (utils/anneal.py:12-49,
+    utils/cyclical.py:12-46, always called with num_init_steps = 0)."""
+    if isinstance(spec, (int, float)):
+        return float(spec)
+    if spec.startswith("anneal_"):
+        kind, cyclical = spec[7:], False
+    elif spec.startswith("cyclical_"):
+        kind, cyclical = spec[9:], True
+    else:
+        raise ValueError(spec)
+    kind, a, b = kind.rsplit("$", 3)
+    a, b = float(a), float(b)
+    if step > total_steps or not kind or kind in ("none", "constant"):
+        return b
+    progress = float(num_cycles * step) / max(1, total_steps) % 1
+    if kind == "linear":
+        if progress < 0.5:
+            return float(a + (b - a) * (progress * 2))
+        return float(b + (a - b) * (progress * 2 - 1)) if cyclical else b
+    if kind == "cosine":
+        if progress < 0.5 or cyclical:
+            return float(a + (b - a) * (1 - math.cos(_PI * progress * 2)) / 2)
+        return b
+    raise NotImplementedError(kind)
 
 
 def bp_criterion(kind):

@@ -62,3 +62,16 @@ def test_criteria_and_missing_heads():
                g_e_rep=None, g_v_mask=None, g_e_mask=None)
     loss, terms = counting_bp_loss(out, torch.tensor([1, 1]), node_weights=torch.ones(2, 3), match_loss_w=1.0)
     assert float(loss.detach()) == pytest.approx(float(bp_criterion("MSE")(x, t, 0.01))) and float(terms["match_v_loss"]) == 0.0
+
+
+def test_scheduled_value_known_answers():
+    """config.py defaults: the negative slope anneals 1.0 -> 0.01 over the first half of each of two cycles."""
+    from dummynode4graphlearning_b200.subgraph_isomorphism.losses import scheduled_value
+    spec = "anneal_cosine$1.0$0.01"
+    assert scheduled_value(spec, 0, 1000) == 1.0
+    assert scheduled_value(spec, 125, 1000) == pytest.approx(1.0 + (0.01 - 1.0) * 0.5)        # quarter of a cycle: midpoint
+    assert scheduled_value(spec, 250, 1000) == 0.01 and scheduled_value(spec, 400, 1000) == 0.01
+    assert scheduled_value(spec, 500, 1000) == 1.0                                          # second cycle restarts
+    assert scheduled_value(spec, 2000, 1000) == 0.01
+    assert scheduled_value("cyclical_linear$0.0$1.0", 375, 1000) == pytest.approx(0.5)        # on the way back
+    assert scheduled_value(0.3, 5, 10) == 0.3

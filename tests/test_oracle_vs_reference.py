@@ -323,3 +323,29 @@ def test_preprocessing_chain_live(flags):
     assert {"node_ptr", "edge_ptr", "src", "dst", "vid", "vlabel", "eid", "elabel"} <= set(keys)
     batches_equal(op, rp, keys)
     batches_equal(og, rg, keys)
+
+
+def test_loss_weight_schedules_match_reference():
+    """neg_pred_slp / match_loss_w / match_reg_w / rep_reg_w option strings resolved per step exactly as train_epoch does
+    (train.py:648-740 -> utils/anneal.py, utils/cyclical.py with num_init_steps = 0)."""
+    import importlib
+    from dummynode4graphlearning_b200.subgraph_isomorphism.losses import scheduled_value
+    from oracle import refload
+    refload.subgraph()
+    anneal_fn = importlib.import_module("utils.anneal").anneal_fn
+    cyclical_fn = importlib.import_module("utils.cyclical").cyclical_fn
+    total = 1000
+    for spec in ("anneal_cosine$1.0$0.01", "anneal_cosine$0.01$0.0", "anneal_linear$0.5$2.0", "cyclical_cosine$0.0$1.0",
+                 "cyclical_linear$1.0$0.25", "anneal_constant$3.0$4.0", "cyclical_none$3.0$4.0"):
+        head, a, b = spec.rsplit("$", 3)
+        for step in list(range(0, 1003, 7)) + [249, 250, 251, 499, 500, 501, 999, 1000, 1001, 5000]:
+            if head.startswith("anneal_"):
+                ref = anneal_fn(head[7:], step, num_init_steps=0, num_anneal_steps=total, num_cycles=2, value1=float(a),
+                                value2=float(b))
+            else:
+                ref = cyclical_fn(head[9:], step, num_init_steps=0, num_cyclical_steps=total, num_cycles=2,
+                                  value1=float(a), value2=float(b))
+            assert scheduled_value(spec, step, total) == ref, (spec, step)
+    assert scheduled_value(0.25, 3, 10) == 0.25 and scheduled_value(1, 3, 10) == 1.0
+    with pytest.raises(ValueError):
+        scheduled_value("cosine$1$2", 0, 10)
