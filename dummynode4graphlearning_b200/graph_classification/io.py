@@ -121,3 +121,47 @@ def save_tu_dir(b, data_dir, prefix=""):
                 f.write(line)
                 f.write("\n")
     return data_dir
+
+
+def convert_tu_dataset(raw_path, dataset, device="cuda:0"):
+    """what running ``tu_data_processing.py`` does after its download step (:431-456): read ``<...>/<dataset>/raw``,
+    build the DUMMY_ (dummy-augmented), LINE_ (edge-to-vertex) and CONJ_ (dummy + edge-to-vertex) variants and write
+    them next to it as ``.../DUMMY_<dataset>/raw`` etc., graph labels included -- with the graph construction done by
+    the GPU kernels on the whole data set at once instead of igraph calls per graph.  Scalar node / edge attributes
+    never leave the host: they are carried in float64 through the index maps the kernels return (dummy items get 0,
+    :191,:197; conjugate vertices take their original edge's attributes and conjugate edges their shared vertex's,
+    :238-242,:322-326), so the text written equals the reference's digit for digit.  Returns {variant: directory}."""
+    from .. import transforms as T
+    raw = load_tu_dir(raw_path)
+    dev = T.to_device({k: v for k, v in raw.items() if k not in ("y", "vattr", "eattr")}, device)
+    dummy = T.tu_add_dummy(dev)
+    line, conj = T.tu_conjugate(dev), T.tu_conjugate(dummy)
+
+    def with_dummy_zeros(values, flags):
+        out = np.zeros(len(flags), dtype=np.float64)
+        out[flags == 0] = values
+        return out
+
+    attrs = {"DUMMY_": {}, "LINE_": {}, "CONJ_": {}}
+    va, ea = raw.get("vattr"), raw.get("eattr")
+    va_d = None if va is None else with_dummy_zeros(va, _np(dummy["v_is_dummy"]))
+    ea_d = None if ea is None else with_dummy_zeros(ea, _np(dummy["e_is_dummy"]))
+    for key, val in (("vattr", va_d), ("eattr", ea_d)):
+        if val is not None:
+            attrs["DUMMY_"][key] = val
+    for prefix, b, v_src, e_src in (("LINE_", line, va, ea), ("CONJ_", conj, va_d, ea_d)):
+        if e_src is not None:
+            attrs[prefix]["vattr"] = e_src[_np(b["v_origin"]).astype(np.int64)]
+        if v_src is not None:
+            attrs[prefix]["eattr"] = v_src[_np(b["e_shared"]).astype(np.int64)]
+    out = {}
+    for prefix, b in (("DUMMY_", dummy), ("LINE_", line), ("CONJ_", conj)):
+        target = raw_path.replace(dataset, prefix + dataset)       # tu_data_processing.py:438-440
+        if target == raw_path:
+            raise ValueError("convert_tu_dataset: %r does not occur in %r" % (dataset, raw_path))
+        b = {k: b[k] for k in ("num_graphs", "node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel", "vid", "eid")}
+        b.update(attrs[prefix])
+        if "y" in raw:
+            b["y"] = raw["y"]
+        out[prefix] = save_tu_dir(b, target)
+    return out

@@ -56,3 +56,45 @@ def test_label_shift_and_defaults():
     assert b["vlabel"].tolist() == [1, 4, 1, 2] and b["elabel"].tolist() == [1, 1, 1, 1] and not b["has_edge_labels"]
     assert b["node_ptr"].tolist() == [0, 2, 4] and b["edge_ptr"].tolist() == [0, 2, 4] and b["y"].tolist() == [-1, 1]
     assert b["src"].tolist() == [0, 1, 2, 3] and b["dst"].tolist() == [1, 0, 3, 2]
+
+
+def _tu_dir_with_decimal_attributes(d, shape="proteins", nb=6, seed=3):
+    from dummynode4graphlearning_b200 import synth
+    b = synth.tu_batch(shape, nb, seed=seed)
+    b["vattr"] = np.round(np.random.default_rng(seed).normal(size=len(b["vlabel"])), 3)   # text that float32 would not keep
+    b["vid"] = np.concatenate([np.arange(n) for n in np.diff(b["node_ptr"])]).astype(np.int32)
+    b["eid"] = np.concatenate([np.arange(n) for n in np.diff(b["edge_ptr"])]).astype(np.int32)
+    raw = os.path.join(d, "PROTEINS", "raw")
+    tuio.save_tu_dir(b, raw)
+    return raw
+
+
+@pytest.mark.reference_live
+def test_convert_tu_dataset_host_logic_equals_reference_main(monkeypatch):
+    """convert_tu_dataset == the body of tu_data_processing.py's __main__ (:431-456) on the same raw directory, file by
+    file and byte by byte, attributes included.  The GPU graph construction is replaced by the oracle's here (CPU
+    test of the host logic: attribute passthrough, directory naming, labels); tests/test_zz_convert_gpu.py runs the real
+    thing."""
+    import dummynode4graphlearning_b200.transforms as T
+    from oracle import refload
+    monkeypatch.setattr(T, "to_device", lambda b, device: b)
+    monkeypatch.setattr(T, "tu_add_dummy", OT.tu_add_dummy)
+    monkeypatch.setattr(T, "tu_conjugate", OT.tu_conjugate)
+    tu = refload.classification().tu
+    with tempfile.TemporaryDirectory() as d:
+        raw = _tu_dir_with_decimal_attributes(d)
+        out = tuio.convert_tu_dataset(raw, "PROTEINS", "cpu")
+        assert sorted(out) == ["CONJ_", "DUMMY_", "LINE_"]
+        for prefix, with_dummy, conj in (("DUMMY_", True, False), ("LINE_", False, True), ("CONJ_", True, True)):
+            assert out[prefix] == os.path.join(d, prefix + "PROTEINS", "raw")
+            graphs = tu.load_graph_data_from_TUDatadir(raw, with_dummy=with_dummy)
+            if conj:
+                graphs = [tu.convert_conjugate_graph_forward(g) for g in graphs]
+            ref_dir = os.path.join(d, "ref", prefix + "PROTEINS", "raw")
+            os.makedirs(ref_dir)
+            tu.save_graph_data(graphs, ref_dir)
+            tu.save_graph_labels(tu.load_graph_labels_from_TUDatadir(raw), ref_dir)
+            assert sorted(os.listdir(ref_dir)) == sorted(os.listdir(out[prefix])), prefix
+            for name in os.listdir(ref_dir):
+                assert open(os.path.join(ref_dir, name)).read() == open(os.path.join(out[prefix], name)).read(), (prefix, name)
+            assert any(n.endswith("_attributes.txt") for n in os.listdir(ref_dir))
