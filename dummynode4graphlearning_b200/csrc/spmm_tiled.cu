@@ -346,6 +346,145 @@ __device__ __forceinline__ void process_tile_fast(const TileAddr<LANES, VEC> &ta
     }
 }
 
+#ifdef DN4GL_K1_TWO_ROWS
+// EXPERIMENT (off in the product build; `make libdn4gl_exp.so EXP_FLAGS=-DDN4GL_K1_TWO_ROWS`): process_tile_fast with
+// TWO rows per sub-group in flight -- the row_ptr pairs of both rows are fetched together and the four-wide batches of
+// both rows are issued together (8 index loads, 8 row loads before the first add), so that the dependent
+// row_ptr -> col -> x chain at the start of a row overlaps with the other row's.  Per-row accumulation order is
+// unchanged (CSR order), i.e. the result is bit-identical; what is left of the longer row runs through the single-row
+// loops.  Long rows (> TP_SPLIT) are split over the warp's sub-groups exactly as in process_tile_fast.
+template <int LANES, int VEC, int NCW>
+__device__ __forceinline__ void process_tile_fast2(const TileAddr<LANES, VEC> &ta, float4 *__restrict__ out,
+                                                   float self_scale, int cw, int lane) {
+    constexpr int RPW = 32 / LANES;
+    constexpr int DV = LANES * VEC;
+    constexpr uint32_t ROWB = DV * 16u;
+    constexpr uint32_t KB = LANES * 16u;
+    constexpr int STEP = NCW * RPW;
+    const int sub = lane / LANES, sl = lane % LANES;
+    const uint32_t xa = ta.x_a, ca_base = ta.col_a;
+    float4 *outl = out + sl;
+#pragma unroll 1
+    for (int rb = ta.r0 + cw * RPW; rb < ta.r1; rb += 2 * STEP) {
+        int row[2], beg[2], end[2];
+        bool valid[2], big[2], run[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            row[h] = rb + h * STEP + sub;
+            valid[h] = row[h] < ta.r1;
+            beg[h] = 0;
+            end[h] = 0;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (valid[h]) {
+                const uint32_t ra = ta.rp_a + 4u * static_cast<uint32_t>(row[h]);
+                beg[h] = lds32(ra);
+                end[h] = lds32(ra + 4u);
+            }
+        float4 acc[2][VEC];
+        uint32_t ca[2], ce[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            big[h] = (LANES < 32) && (end[h] - beg[h] > TP_SPLIT);
+            run[h] = valid[h] && !big[h];
+            ca[h] = ca_base + 4u * static_cast<uint32_t>(beg[h]);
+            ce[h] = run[h] ? ca_base + 4u * static_cast<uint32_t>(end[h]) : ca[h];   // empty range when not run here
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[h][k] = zero4();
+        }
+#pragma unroll 1
+        while (ca[0] + 16u <= ce[0] && ca[1] + 16u <= ce[1]) {   // both rows: 4 + 4 neighbours in flight
+            uint32_t a[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a[h][j] = xa + static_cast<uint32_t>(lds32(ca[h] + 4u * j)) * ROWB;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float4 v[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[h][j] = lds128(a[h][j] + k * KB);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) add4(acc[h][k], v[h][j]);
+            }
+            ca[0] += 16u;
+            ca[1] += 16u;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {   // what is left of either row
+#pragma unroll 1
+            for (; ca[h] + 16u <= ce[h]; ca[h] += 16u) {
+                const uint32_t a0 = xa + static_cast<uint32_t>(lds32(ca[h])) * ROWB;
+                const uint32_t a1 = xa + static_cast<uint32_t>(lds32(ca[h] + 4u)) * ROWB;
+                const uint32_t a2 = xa + static_cast<uint32_t>(lds32(ca[h] + 8u)) * ROWB;
+                const uint32_t a3 = xa + static_cast<uint32_t>(lds32(ca[h] + 12u)) * ROWB;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const float4 v0 = lds128(a0 + k * KB), v1 = lds128(a1 + k * KB);
+                    const float4 v2 = lds128(a2 + k * KB), v3 = lds128(a3 + k * KB);
+                    add4(acc[h][k], v0); add4(acc[h][k], v1); add4(acc[h][k], v2); add4(acc[h][k], v3);
+                }
+            }
+#pragma unroll 1
+            for (; ca[h] < ce[h]; ca[h] += 4u) {
+                const uint32_t a0 = xa + static_cast<uint32_t>(lds32(ca[h])) * ROWB;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) add4(acc[h][k], lds128(a0 + k * KB));
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (run[h]) {
+                if (self_scale != 0.f) {
+                    const uint32_t a0 = xa + static_cast<uint32_t>(row[h]) * ROWB;
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) axpy4_rn(acc[h][k], self_scale, lds128(a0 + k * KB));
+                }
+                float4 *o = outl + static_cast<int64_t>(row[h]) * DV;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) o[k * LANES] = acc[h][k];
+            }
+        if constexpr (LANES < 32) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                unsigned m = __ballot_sync(0xffffffffu, valid[h] && big[h]);
+                while (m) {   // long rows of this half-iteration, split over the RPW sub-groups of the warp
+                    const int src_lane = __ffs(m) - 1;
+                    m &= ~(((1u << LANES) - 1u) << src_lane);
+                    const int brow = rb + h * STEP + src_lane / LANES;
+                    const int bbeg = __shfl_sync(0xffffffffu, beg[h], src_lane);
+                    const int bend = __shfl_sync(0xffffffffu, end[h], src_lane);
+                    float4 bacc = zero4();
+                    uint32_t cb = ca_base + 4u * static_cast<uint32_t>(bbeg + sub);
+                    const uint32_t cbe = ca_base + 4u * static_cast<uint32_t>(bend);
+#pragma unroll 1
+                    for (; cb + 12u * RPW < cbe; cb += 16u * RPW) {
+                        const uint32_t a0 = xa + static_cast<uint32_t>(lds32(cb)) * ROWB;
+                        const uint32_t a1 = xa + static_cast<uint32_t>(lds32(cb + 4u * RPW)) * ROWB;
+                        const uint32_t a2 = xa + static_cast<uint32_t>(lds32(cb + 8u * RPW)) * ROWB;
+                        const uint32_t a3 = xa + static_cast<uint32_t>(lds32(cb + 12u * RPW)) * ROWB;
+                        const float4 v0 = lds128(a0), v1 = lds128(a1), v2 = lds128(a2), v3 = lds128(a3);
+                        add4(bacc, v0); add4(bacc, v1); add4(bacc, v2); add4(bacc, v3);
+                    }
+#pragma unroll 1
+                    for (; cb < cbe; cb += 4u * RPW) add4(bacc, lds128(xa + static_cast<uint32_t>(lds32(cb)) * ROWB));
+                    subgroup_allreduce<LANES>(bacc);
+                    if (sub == 0) {
+                        if (self_scale != 0.f) axpy4_rn(bacc, self_scale, lds128(xa + static_cast<uint32_t>(brow) * ROWB));
+                        outl[static_cast<int64_t>(brow) * DV] = bacc;
+                    }
+                }
+            }
+        }
+    }
+}
+#endif
+
 // one listed long row of a cut tile, reduced by all consumer warps of the CTA through `scratch` (an idle stage)
 template <int LANES, int VEC, int NCW>
 __device__ __forceinline__ void process_heavy_row(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
@@ -508,7 +647,11 @@ spmm_pipe_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict_
                     ta.r0 = td.x; ta.r1 = td.y; ta.e0 = td.z; ta.nst = min(nnz, L.cap_nnz);
                 }
                 if (rows <= L.cap_rows && !open && nnz <= L.cap_nnz)
+#ifdef DN4GL_K1_TWO_ROWS
+                    process_tile_fast2<LANES, VEC, NCW>(ta, out, self_scale, cw, lane);
+#else
                     process_tile_fast<LANES, VEC, NCW>(ta, out, self_scale, cw, lane);
+#endif
                 else if (rows <= L.cap_rows)
                     process_tile<LANES, VEC, NCW, true>(ta, row_ptr, col, x, out, self_scale, cut, cw, lane);
                 else

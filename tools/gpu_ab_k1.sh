@@ -1,6 +1,7 @@
 #!/bin/bash
 # A/B of the experimental aggregation-kernel build against the product build, one gpurun call:
-#   make -C dummynode4graphlearning_b200/csrc libdn4gl_exp.so        (here, before the call: the .so travels)
+#   make -C dummynode4graphlearning_b200/csrc libdn4gl_exp.so [EXP_FLAGS=-DDN4GL_K1_TWO_ROWS]   (here, before the call: the
+#   .so travels; default EXP_FLAGS = -DDN4GL_K1_TAIL_ILP, measured in round 1: no gain)
 #   gpurun --timeout 900 -- 'bash tools/gpu_ab_k1.sh r2a'
 # 1. parity of the experimental build (the aggregation tests through DN4GL_LIB), 2. K1 alone on the C2 structure and
 # the C5 sweep with both builds.  Outputs under gpurun_out/<tag>_ab_*.
