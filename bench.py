@@ -514,7 +514,10 @@ def ours(a):
                 "how": "ClassificationPipeline.step_async(host) per step, loss of step k-1 read on the host after step k "
                        "is submitted (all losses read, last one before the clock stops)"},
         "roofline": roofline, "roofline_c5": roofline_c5, "mlp_stages": mlp, "cpu_baseline": cpu,
-        "breakdown": {"transform_ms": statistics.mean(tr_ms), "train_ms": statistics.mean(tn_ms),
+        "breakdown": {"how": "instrumented pass AFTER the timed regions: eager launches on one stream with a CUDA-event pair "
+                             "around every C-ABI call (medians over %d steps); slower than the measured step by "
+                             "construction -- use it for shares, not for totals" % len(tr_ms),
+                      "transform_ms": statistics.median(tr_ms), "train_ms": statistics.median(tn_ms),
                       "own_kernels_ms_per_step": own_ms,
                       "cudaMalloc_calls_in_timed_region": m1 - m0, "cudaMalloc_calls_in_e2e_region": m2 - m1, "conj_nodes": N, "conj_edges": E,
                       "final_loss": float(loss.item()), "e2e_last_loss": last,
