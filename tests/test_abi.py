@@ -165,3 +165,31 @@ def test_product_never_imports_the_oracle():
             if "liborc" in src:
                 offenders.append(os.path.relpath(path, ROOT) + ": mentions liborc")
     assert not offenders, offenders
+
+
+def test_integration_md_binding_matches_the_header():
+    """the ctypes stub shown to reference maintainers in INTEGRATION.md declares as many arguments as include/dn4gl.h
+    does for every entry point it binds, and its example calls pass that many."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    protos = _lib.parse_header()
+    bound = re.findall(r"_L\.(dn4gl_\w+)\.argtypes = \[(.*?)\]", text, flags=re.S)
+    assert len(bound) >= 3
+    for name, args in bound:
+        n = len([a for a in args.replace("\n", " ").split(",") if a.strip()])
+        assert n == len(protos[name][1]), "%s: INTEGRATION.md binds %d arguments, the header declares %d" % (
+            name, n, len(protos[name][1]))
+    for name, args in re.findall(r"_chk\(_L\.(dn4gl_\w+)\((.*?)\)\)\s*(?:#[^\n]*)?\n", text, flags=re.S):
+        depth, n, cur = 0, 0, ""
+        for ch in args:
+            if ch in "([":
+                depth += 1
+            elif ch in ")]":
+                depth -= 1
+            if ch == "," and depth == 0:
+                n += 1
+                cur = ""
+            else:
+                cur += ch
+        n += 1 if cur.strip() else 0
+        assert n == len(protos[name][1]), "%s: example call passes %d arguments, the header declares %d" % (
+            name, n, len(protos[name][1]))
