@@ -53,7 +53,7 @@ def _slice(sizes, x, y, lo, hi):
     return xs, seg, y[lo:hi]
 
 
-def _worker(rank, world, port, num_graphs, out_dir):
+def _worker(rank, world, port, num_graphs, out_dir, by_work=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -63,6 +63,8 @@ def _worker(rank, world, port, num_graphs, out_dir):
         bucket = GradientBucket(model.parameters())
         sizes, x, y = _make_batch(num_graphs)
         lo, hi = shard_range(num_graphs, rank, world)
+        if by_work:   # contiguous cuts balanced by graph size instead of by count
+            lo, hi = balanced_shard_ranges(sizes.tolist(), world)[rank]
         for step in range(2):   # second step exercises the flat-bucket path (zero() on views)
             bucket.zero()
             xs, seg, ys = _slice(sizes, x, y, lo, hi)
@@ -80,10 +82,10 @@ def _worker(rank, world, port, num_graphs, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("num_graphs", [8, 7])   # even and ragged shards
-def test_sharded_gradient_equals_single_process(tmp_path, num_graphs):
+@pytest.mark.parametrize("num_graphs,by_work", [(8, False), (7, False), (9, True)])   # even, ragged, work-balanced shards
+def test_sharded_gradient_equals_single_process(tmp_path, num_graphs, by_work):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), num_graphs, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), num_graphs, str(tmp_path), by_work), nprocs=world, join=True)
     got = torch.load(os.path.join(str(tmp_path), "dp.pt"))
     torch.manual_seed(0)
     model = _Toy()
