@@ -1,6 +1,8 @@
-"""CPU: known answers for the row-wise activation choices of --rep_act_func / --pred_act_func that torch does not ship
-(subgraph_isomorphism/utils/act.py:210-455); the comparison with the reference's own functions is the live test
-tests/test_oracle_vs_reference.py::test_activation_registry_matches_reference."""
+"""CPU: known answers for host-side helpers of the counting path -- the row-wise activation choices of --rep_act_func /
+--pred_act_func that torch does not ship (subgraph_isomorphism/utils/act.py:210-455), expand_dimensions, the dummy column
+of subisomorphisms, the lazy batch dict.  The comparisons with the reference's own functions are the live tests in
+tests/test_oracle_vs_reference.py."""
+import pytest
 import torch
 
 from dummynode4graphlearning_b200.subgraph_isomorphism.utils import (Maximum, Minimum, Sparsemax, map_activation_str_to_layer,
@@ -71,3 +73,31 @@ def test_add_dummy_to_subisomorphisms():
     assert out[0].tolist() == [[0, 1, 5], [3, 4, 5]] and out[1].shape == (0, 4) and out[2].tolist() == [[2, 1, 0, 3]]
     packed = pack_subisomorphisms(out)
     assert packed["val_ptr"].tolist() == [0, 6, 6, 10] and packed["rows"].tolist() == [2, 0, 1]
+
+
+def test_lazy_batch_dict_semantics():
+    """transforms.LazyDict: derived columns are computed once, on first access; membership sees them before that;
+    pop() discards a pending column WITHOUT computing it (the pipeline drops columns the model does not read);
+    iteration / dict(...) materialise everything."""
+    from dummynode4graphlearning_b200.transforms import LazyDict
+    calls = []
+
+    def make(name, value):
+        def fn():
+            calls.append(name)
+            return value
+        return fn
+
+    d = LazyDict(a=1)
+    d.lazy("b", make("b", 2))
+    d.lazy("c", make("c", 3))
+    d.lazy("e", make("e", 5))
+    assert "b" in d and "zzz" not in d and calls == []
+    assert d["b"] == 2 and d["b"] == 2 and calls == ["b"]            # computed once, then stored
+    assert d.get("c") == 3 and d.get("zzz", 7) == 7 and calls == ["b", "c"]
+    assert d.pop("e", None) is None and "e" not in d and calls == ["b", "c"]   # discarded, never computed
+    with pytest.raises(KeyError):
+        d["e"]
+    d.lazy("f", make("f", 6))
+    assert dict(d) == {"a": 1, "b": 2, "c": 3, "f": 6} and calls == ["b", "c", "f"]
+    assert sorted(d.keys()) == ["a", "b", "c", "f"] and len(list(d.items())) == 4
