@@ -31,9 +31,14 @@ def _shift_min_to_one(labels):
     return labels - m + 1 if m != 1 else labels
 
 
-def load_tu_dir(data_dir):
+def load_tu_dir(data_dir, keep_trailing_edgeless=False):
     """-> dict(num_graphs, node_ptr, edge_ptr, src, dst, vlabel, elabel[, vattr][, eattr][, y], has_edge_labels)
-    with graph-local structure flattened to global 0-based node ids (int32)."""
+    with graph-local structure flattened to global 0-based node ids (int32).
+
+    Like the reference's walk over the edge list (``while j < k``, tu_data_processing.py:179), graphs that come AFTER
+    the graph of the last edge are not produced (trailing graphs without edges are dropped; a data
+    set without any edge yields no graph).  ``y`` is cut to the graphs produced, all labels of the file stay available
+    as ``y_all`` (the reference saves them unchanged, :341-350).  keep_trailing_edgeless=True keeps every graph."""
     if os.path.exists(os.path.join(data_dir, "raw")):
         data_dir = os.path.join(data_dir, "raw")
     A, gi, nl, el, na, ea, y = [], [], [], [], [], [], None
@@ -78,6 +83,16 @@ def load_tu_dir(data_dir):
         out["eattr"] = np.asarray(ea, dtype=np.float64)
     if y is not None:
         out["y"] = y
+    if not keep_trailing_edgeless:
+        B_eff = int(eg[-1]) + 1 if E else 0
+        if B_eff < B:
+            n_eff = int(node_ptr[B_eff])
+            out.update(num_graphs=B_eff, node_ptr=out["node_ptr"][:B_eff + 1], edge_ptr=out["edge_ptr"][:B_eff + 1],
+                       vlabel=out["vlabel"][:n_eff])
+            if "vattr" in out:
+                out["vattr"] = out["vattr"][:n_eff]
+            if y is not None:
+                out["y_all"], out["y"] = y, y[:B_eff]
     return out
 
 
@@ -162,6 +177,6 @@ def convert_tu_dataset(raw_path, dataset, device="cuda:0"):
         b = {k: b[k] for k in ("num_graphs", "node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel", "vid", "eid")}
         b.update(attrs[prefix])
         if "y" in raw:
-            b["y"] = raw["y"]
+            b["y"] = raw.get("y_all", raw["y"])                    # save_graph_labels writes the label file unchanged
         out[prefix] = save_tu_dir(b, target)
     return out

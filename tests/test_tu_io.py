@@ -98,3 +98,42 @@ def test_convert_tu_dataset_host_logic_equals_reference_main(monkeypatch):
             for name in os.listdir(ref_dir):
                 assert open(os.path.join(ref_dir, name)).read() == open(os.path.join(out[prefix], name)).read(), (prefix, name)
             assert any(n.endswith("_attributes.txt") for n in os.listdir(ref_dir))
+
+
+def _write_tiny(d, A, gi, y):
+    for name, lines in (("A", A), ("graph_indicator", gi), ("node_labels", ["1"] * len(gi)), ("graph_labels", y)):
+        with open(os.path.join(d, "X_" + name + ".txt"), "w") as f:
+            f.write("\n".join(lines) + "\n")
+
+
+def test_graphs_without_edges():
+    """App. A-2: the reference's edge walk never reaches graphs after the last edge's graph (they are dropped, labels kept
+    in y_all); graphs without edges before that are produced with m = 0."""
+    with tempfile.TemporaryDirectory() as d:
+        _write_tiny(d, ["1, 2", "2, 1"], ["1", "1", "2", "2"], ["1", "-1"])
+        b = tuio.load_tu_dir(d)
+        assert b["num_graphs"] == 1 and b["node_ptr"].tolist() == [0, 2] and b["edge_ptr"].tolist() == [0, 2]
+        assert b["vlabel"].tolist() == [1, 1] and b["y"].tolist() == [1] and b["y_all"].tolist() == [1, -1]
+        keep = tuio.load_tu_dir(d, keep_trailing_edgeless=True)
+        assert keep["num_graphs"] == 2 and keep["node_ptr"].tolist() == [0, 2, 4] and keep["edge_ptr"].tolist() == [0, 2, 2]
+    with tempfile.TemporaryDirectory() as d:
+        _write_tiny(d, ["1, 2", "2, 1", "5, 6", "6, 5"], ["1", "1", "2", "2", "3", "3"], ["1", "1", "1"])
+        b = tuio.load_tu_dir(d)
+        assert b["num_graphs"] == 3 and b["edge_ptr"].tolist() == [0, 2, 2, 4] and "y_all" not in b
+
+
+@pytest.mark.reference_live
+@pytest.mark.parametrize("A,gi", [(["1, 2", "2, 1"], ["1", "1", "2", "2"]),
+                                  (["1, 2", "2, 1", "5, 6", "6, 5"], ["1", "1", "2", "2", "3", "3"]),
+                                  (["3, 4", "4, 3"], ["1", "1", "2", "2"]),
+                                  (["1, 2", "2, 1"], ["1", "1", "2", "3", "3", "3"])])
+def test_graphs_without_edges_live(A, gi):
+    from oracle import ref_drive as rd, refload
+    tu = refload.classification().tu
+    with tempfile.TemporaryDirectory() as d:
+        _write_tiny(d, A, gi, ["1"] * int(gi[-1]))
+        ref = rd.igraphs_to_batch(tu.load_graph_data_from_TUDatadir(d, with_dummy=False))
+        mine = tuio.load_tu_dir(d)
+    assert mine["num_graphs"] == ref["num_graphs"]
+    for k in ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel"):
+        assert np.array_equal(mine[k], ref[k]), k
