@@ -9,7 +9,8 @@ import torch
 
 from dummynode4graphlearning_b200 import synth
 from dummynode4graphlearning_b200.transforms import process_model_config
-from helpers import assert_close_rel, batches_equal, oracle_cfg, oracle_preprocess_chain
+from helpers import (NASTY_CFG, assert_close_rel, batches_equal, nasty_sub_batch, nasty_tu_batch, oracle_cfg,
+                     oracle_preprocess_chain)
 from oracle import models as OM
 from oracle import transforms as OT
 
@@ -349,3 +350,48 @@ def test_loss_weight_schedules_match_reference():
     assert scheduled_value(0.25, 3, 10) == 0.25 and scheduled_value(1, 3, 10) == 1.0
     with pytest.raises(ValueError):
         scheduled_value("cosine$1$2", 0, 10)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_tu_transforms_fuzz_live(seed):
+    """dummy augmentation, CONJ and LINE transforms on graphs with self loops, duplicate edges, isolated and single nodes and
+    edgeless graphs: oracle == reference."""
+    from oracle import ref_drive as rd
+    rng = np.random.default_rng(seed)
+    b = nasty_tu_batch(rng, int(rng.integers(1, 6)))
+    ref_dummy = rd.ref_tu_load(b, True)
+    batches_equal(OT.tu_add_dummy(b), rd.igraphs_to_batch(ref_dummy),
+                  ["node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel", "v_is_dummy", "e_is_dummy"])
+    ref_conj = rd.igraphs_to_batch(rd.ref_tu_conjugate(ref_dummy))
+    got = OT.tu_conjugate(OT.tu_add_dummy(b))
+    batches_equal(got, ref_conj, [k for k in TU_KEYS if k in ref_conj and k in got])
+    ref_line = rd.igraphs_to_batch(rd.ref_tu_conjugate(rd.ref_tu_load(b, False)))
+    batches_equal(OT.tu_conjugate(b), ref_line, [k for k in ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel") if k in ref_line])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_sub_preprocessing_fuzz_live(seed):
+    """random subsets of remove_loops / add_reversed_edges / add_dummy_nodes_edges / convert_to_conjugate chained in
+    train.py's order on multigraphs with loops, isolated nodes and edgeless graphs: oracle == reference."""
+    from oracle import ref_drive as rd
+    rng = np.random.default_rng(1000 + seed)
+    B = int(rng.integers(1, 5))
+    p, g = nasty_sub_batch(rng, B, 5, 4), nasty_sub_batch(rng, B, 8, 6)
+    flags = tuple(bool(x) for x in rng.integers(0, 2, 4))
+    cfg = NASTY_CFG
+    rp, rg = p, g
+    npe, npel, nge, ngel = cfg["max_npe"], cfg["max_npel"], cfg["max_nge"], cfg["max_ngel"]
+    if flags[0]:
+        rp, rg = rd.ref_sub_remove_loops(rp, rg)
+    if flags[1]:
+        rp, rg = rd.ref_sub_add_reversed(rp, rg, cfg)
+        npe, npel, nge, ngel = 2 * npe, 2 * npel, 2 * nge, 2 * ngel
+    if flags[2]:
+        rp, rg = rd.ref_sub_add_dummy(rp, rg, dict(cfg, max_npe=npe, max_npel=npel, max_nge=nge, max_ngel=ngel))
+    if flags[3]:
+        rp, rg = rd.ref_sub_conjugate(rp), rd.ref_sub_conjugate(rg)
+    op, og = oracle_preprocess_chain(p, g, cfg, *flags)
+    keys = [k for k in ("node_ptr", "edge_ptr", "src", "dst", "vid", "vlabel", "eid", "elabel", "v_is_dummy", "e_is_dummy",
+                        "e_is_reversed", "v_is_reversed") if k in rg and k in og]
+    batches_equal(op, rp, keys)
+    batches_equal(og, rg, keys)
