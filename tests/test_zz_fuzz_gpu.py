@@ -23,6 +23,12 @@ def _same(mine, ref, keys, what):
             assert np.array_equal(got.astype(np.int64), np.asarray(ref[k]).astype(np.int64)), (what, k)
 
 
+def _no_async_errors():
+    from dummynode4graphlearning_b200.graph import check_errors
+    torch.cuda.synchronize()
+    check_errors()            # capacity / ordering violations the builder kernels report through the device flag
+
+
 @pytest.mark.parametrize("seed", range(16))
 def test_tu_transforms_fuzz(device, seed):
     from dummynode4graphlearning_b200 import transforms as T
@@ -38,6 +44,7 @@ def test_tu_transforms_fuzz(device, seed):
     es, ed, _, _ = OT.pyg_coalesce(oc["src"], oc["dst"])
     can = T.pyg_canonicalize(T.tu_conjugate(T.tu_add_dummy(T.to_device(b, device))), with_edge_attr=False)
     assert np.array_equal(can["edge_index"].cpu().numpy(), np.stack([es, ed]).astype(np.int64))
+    _no_async_errors()
 
 
 @pytest.mark.parametrize("seed", range(16))
@@ -55,3 +62,4 @@ def test_sub_preprocessing_fuzz(device, seed):
     op, og = oracle_preprocess_chain(p, g, NASTY_CFG, *flags)
     _same(mp, op, SUB, ("pattern", flags))
     _same(mg, og, SUB, ("graph", flags))
+    _no_async_errors()
