@@ -395,3 +395,50 @@ def test_sub_preprocessing_fuzz_live(seed):
                         "e_is_reversed", "v_is_reversed") if k in rg and k in og]
     batches_equal(op, rp, keys)
     batches_equal(og, rg, keys)
+
+
+@pytest.mark.parametrize("name,over", [("RGIN", {}), ("DMPNN", dict(node_pred=True, edge_pred=True)),
+                                       ("RGCN", dict(rep_rgcn_edge_norm="both")),
+                                       ("CompGCN", dict(rep_compgcn_comp_opt="sub", rep_compgcn_edge_norm="both"))])
+def test_counting_models_fuzz_live(name, over):
+    """the four counting models on dummy-augmented multigraphs with self loops, repeated edges and isolated nodes
+    (every graph keeps at least one non-loop edge: with none, the reference's own 1 / (number of real edges) is inf):
+    oracle == reference for pred_c and every parameter gradient."""
+    import torch.nn.functional as F
+    from oracle import ref_drive as rd
+    cfg = dict(NASTY_CFG, add_dummy=True)
+    mc = process_model_config(cfg)
+    done = 0
+    for seed in range(2000, 2120):
+        rng = np.random.default_rng(seed)
+        B = int(rng.integers(1, 5))
+        p, g = nasty_sub_batch(rng, B, 5, 4), nasty_sub_batch(rng, B, 8, 6)
+        if any((b["src"][a:z] == b["dst"][a:z]).all() for b in (p, g) for a, z in zip(b["edge_ptr"][:-1], b["edge_ptr"][1:])):
+            continue                                   # an edgeless (or loops-only) graph: degenerate for the reference itself
+        counts = rng.poisson(3.0, B).astype(np.int64)
+        pd_ = OT.sub_add_dummy(p, cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])
+        gd_ = OT.sub_add_dummy(g, cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"])
+        kw = rd.counting_kwargs({k: v for k, v in mc.items() if k.startswith("max_")}, hid_dim=16, pred_hid_dim=16, **over)
+        model = rd.ref_counting_model(name, kw, seed=seed)
+        with torch.no_grad():
+            for n, q in model.named_parameters():
+                if "fc2" in n:
+                    q.normal_(0.0, 0.1)
+        o = model(rd.dgl_batched(pd_), rd.dgl_batched(gd_))
+        F.mse_loss(F.leaky_relu(o["pred_c"], 0.01), torch.from_numpy(counts).float().view(-1, 1)).backward()
+        sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+        out = OM.counting_model(sd, pd_, gd_, oracle_cfg(name, kw))
+        assert_close_rel(out["pred_c"], o["pred_c"].detach(), 1e-5, "pred_c seed %d" % seed)
+        OM.counting_loss(out, torch.from_numpy(counts), rep_reg_w=0.0).backward()
+        for n, pp in model.named_parameters():
+            if pp.grad is None:
+                continue
+            got = sd[n].grad
+            alias = n.replace("g_rep_net", "p_rep_net", 1) if n.startswith("g_rep_net") else None
+            if alias in sd and sd[alias].grad is not None:
+                got = got + sd[alias].grad if got is not None else sd[alias].grad
+            assert_close_rel(got, pp.grad, 1e-4, "grad %s seed %d" % (n, seed))
+        done += 1
+        if done == 5:
+            break
+    assert done == 5
