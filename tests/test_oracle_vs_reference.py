@@ -442,3 +442,27 @@ def test_counting_models_fuzz_live(name, over):
         if done == 5:
             break
     assert done == 5
+
+
+def test_match_weights_fuzz_live():
+    """match weights and the conjugate subisomorphism map on multigraphs with self loops and repeated (u, v, label)
+    edges (every pattern / graph keeps at least one edge: the reference's numba loops take max() of the edge arrays)."""
+    from oracle import ref_drive as rd
+    done = 0
+    for seed in range(3000, 3200):
+        rng = np.random.default_rng(seed)
+        B = int(rng.integers(1, 5))
+        p, g = nasty_sub_batch(rng, B, 5, 4), nasty_sub_batch(rng, B, 8, 6)
+        if (np.diff(p["edge_ptr"]) == 0).any() or (np.diff(g["edge_ptr"]) == 0).any():
+            continue
+        mats = synth.random_subisomorphisms(p, g, seed=seed, max_rows=6)
+        rn, re = rd.ref_match_weights(mats, p, g)
+        np.testing.assert_array_equal(OT.subiso_node_weights(mats, g), rn)
+        np.testing.assert_array_equal(OT.subiso_edge_weights(mats, p, g), re)
+        for a, r in zip(OT.subiso_conjugate(mats, p, g), rd.ref_conjugate_subisomorphisms(mats, p, g)):
+            assert a.shape == r.shape
+            np.testing.assert_array_equal(a, r)
+        done += 1
+        if done == 15:
+            break
+    assert done == 15

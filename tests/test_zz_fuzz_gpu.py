@@ -63,3 +63,30 @@ def test_sub_preprocessing_fuzz(device, seed):
     _same(mp, op, SUB, ("pattern", flags))
     _same(mg, og, SUB, ("graph", flags))
     _no_async_errors()
+
+
+def test_match_weights_fuzz(device):
+    """batched match-weight / conjugate-map kernels on multigraphs with self loops and repeated (u, v, label) edges."""
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.subgraph_isomorphism import matching as M
+    done = 0
+    for seed in range(3000, 3200):
+        rng = np.random.default_rng(seed)
+        B = int(rng.integers(1, 5))
+        p, g = nasty_sub_batch(rng, B, 5, 4), nasty_sub_batch(rng, B, 8, 6)
+        if (np.diff(p["edge_ptr"]) == 0).any() or (np.diff(g["edge_ptr"]) == 0).any():
+            continue
+        mats = synth.random_subisomorphisms(p, g, seed=seed, max_rows=6)
+        sub = M.pack_subisomorphisms(mats, device)
+        pb, gb = T.to_device(p, device), T.to_device(g, device)
+        assert np.array_equal(M.node_weights(sub, gb).cpu().numpy(), OT.subiso_node_weights(mats, g)), seed
+        assert np.array_equal(M.edge_weights(sub, pb, gb).cpu().numpy(), OT.subiso_edge_weights(mats, p, g)), seed
+        work, conj = M.conjugate_subisomorphisms(sub, pb, gb)
+        work, conj = work.cpu().numpy(), conj.cpu().numpy()
+        for b, ref in enumerate(OT.subiso_conjugate(mats, p, g)):
+            assert np.array_equal(conj[work[b]: work[b + 1]].reshape(ref.shape), ref), (seed, b)
+        done += 1
+        if done == 15:
+            break
+    assert done == 15
+    _no_async_errors()
