@@ -466,3 +466,24 @@ def test_match_weights_fuzz_live():
         if done == 15:
             break
     assert done == 15
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_tu_io_fuzz_live(seed):
+    """reader and writer on the nasty TU batches: load_tu_dir == the reference's loader, and the text written for the
+    reference's own DUMMY_ / CONJ_ graphs == save_graph_data's."""
+    import tempfile
+    from dummynode4graphlearning_b200.graph_classification import io as tuio
+    from oracle import ref_drive as rd
+    rng = np.random.default_rng(500 + seed)
+    b = nasty_tu_batch(rng, int(rng.integers(1, 6)))
+    with tempfile.TemporaryDirectory() as d:
+        mine = tuio.load_tu_dir(rd.write_tu_files(b, d))
+    ref = rd.igraphs_to_batch(rd.ref_tu_load(b, False))
+    batches_equal(mine, ref, ("node_ptr", "edge_ptr", "src", "dst", "vlabel", "elabel"))
+    dummy_graphs = rd.ref_tu_load(b, True)
+    for graphs in (dummy_graphs, rd.ref_tu_conjugate(dummy_graphs)):
+        files = rd.ref_tu_save(graphs)
+        lines = tuio.tu_file_lines(rd.igraphs_to_batch(graphs))
+        for suffix, ref_lines in files.items():
+            assert lines[suffix] == ref_lines, suffix
