@@ -73,7 +73,7 @@ def _tu_dir_with_decimal_attributes(d, shape="proteins", nb=6, seed=3):
 def test_convert_tu_dataset_host_logic_equals_reference_main(monkeypatch):
     """convert_tu_dataset == the body of tu_data_processing.py's __main__ (:431-456) on the same raw directory, file by
     file and byte by byte, attributes included.  The GPU graph construction is replaced by the oracle's here (CPU
-    test of the host logic: attribute passthrough, directory naming, labels); tests/test_zz_convert_gpu.py runs the real
+    test of the host logic: attribute passthrough, directory naming, labels); tests/test_zzz_convert_gpu.py runs the real
     thing."""
     import dummynode4graphlearning_b200.transforms as T
     from oracle import refload
