@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(NT) lin_fwd_kernel(const LinFwdArgs a) {
     }
     if (w == 0) tc_alloc(s_u32(&tmem_ptr), TCOLS);
     __syncthreads();
+    DN_PDL_WAIT();   // (experiment) everything above is on-chip; global memory is first touched below
     // raw ring: tile j of this CTA lives in slot j % RING
     auto issue = [&](int j) {
         const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(j) * gridDim.x;
@@ -512,6 +513,7 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
     }
     if (w == 0) tc_alloc(s_u32(&tmem_ptr), TCOLS);
     __syncthreads();
+    DN_PDL_WAIT();   // (experiment) everything above is on-chip; global memory is first touched below
     const bool want_gx = a.GX != nullptr, has_bn = a.bn != nullptr, has_bn_in = a.in_bn != nullptr;
     auto issue = [&](int j) {
         const int64_t tile = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(j) * gridDim.x;
@@ -786,6 +788,7 @@ __device__ __forceinline__ double group_sum(double (*sm)[33], int lane, int g, d
 __global__ void __launch_bounds__(1024)
 lin_bwd_reduce_kernel(const float *__restrict__ part, int nparts, int MP, int KP, int M, int K,
                       float *__restrict__ dW, float *__restrict__ db, float *__restrict__ sums_prev) {
+    DN_PDL_WAIT();
     __shared__ double sm[32][33];
     __shared__ float *sm_dst[32];
     const int stride = bwd_part_floats(KP, MP);
@@ -826,6 +829,7 @@ __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float4 *__restrict__ part, int nparts, int MP, int M, int64_t N,
                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
                    float *__restrict__ bn_out, float *__restrict__ run_mean, float *__restrict__ run_var, long long *nbt) {
+    DN_PDL_WAIT();
     __shared__ double sm[32][33];
     __shared__ double sm_kstar[32];
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
@@ -892,6 +896,7 @@ bn_finalize_kernel(const float4 *__restrict__ part, int nparts, int MP, int M, i
 // out = act(bn(Y))  (the activation a stage hands to a non-MLP consumer: aggregation, readout)
 __global__ void bn_act_kernel(const float *__restrict__ Y, int64_t N, int M, const float *__restrict__ bn, int act, float slope,
                               float *__restrict__ out) {
+    DN_PDL_WAIT();
     const int CH = (M + 3) / 4;
     const bool vec = (M % 4 == 0) && aligned16_dev(Y) && aligned16_dev(out);
     const int64_t total = N * CH;
@@ -913,6 +918,7 @@ template <int CHP>
 __global__ void __launch_bounds__(256) bn_act_pool_kernel(const float *__restrict__ Y, int M, const float *__restrict__ bn, int act,
                                                           float slope, float *__restrict__ out, const int32_t *__restrict__ seg_ptr,
                                                           int B, int mode, float *__restrict__ pooled) {
+    DN_PDL_WAIT();
     constexpr int RP = 256 / CHP;
     __shared__ float red[8][4 * CHP];
     const int t = threadIdx.x, w = t >> 5, lane = t & 31, c = t % CHP, r0 = t / CHP;
@@ -967,6 +973,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const float *__restric
 
 // row -> segment index for contiguous segments (the `batch` vector of a PyG batch, as int32)
 __global__ void segment_ids_kernel(const int32_t *__restrict__ seg_ptr, int B, int64_t N, int32_t *__restrict__ out) {
+    DN_PDL_WAIT();
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < N) out[i] = segment_of(seg_ptr, B, i);
 }
@@ -978,6 +985,7 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restric
                                                           const int32_t *__restrict__ row2seg, const float *__restrict__ Y,
                                                           int64_t N, int M, const float *__restrict__ bn, int act, float slope,
                                                           float *__restrict__ part /* [grid][2*4*CHP] */) {
+    DN_PDL_WAIT();
     constexpr int RP = 256 / CHP;
     __shared__ float red[8][8 * CHP];
     const int t = threadIdx.x, w = t >> 5, lane = t & 31, c = t % CHP, r0 = t / CHP;
@@ -1042,6 +1050,7 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restric
 }
 __global__ void __launch_bounds__(1024)
 bn_bwd_sums_reduce_kernel(const float *__restrict__ part, int nparts, int CHP, int M, float *__restrict__ sums) {
+    DN_PDL_WAIT();
     __shared__ double sm[32][33];
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
@@ -1058,6 +1067,7 @@ bn_bwd_sums_reduce_kernel(const float *__restrict__ part, int nparts, int CHP, i
 // fixed-order dot product: per-CTA partial (tree in shared memory), the last CTA adds the partials in index order
 __global__ void __launch_bounds__(256) dot_kernel(const float *__restrict__ a, const float *__restrict__ b, int64_t n,
                                                   float *__restrict__ out, float *__restrict__ part, int *counter) {
+    DN_PDL_WAIT();
     __shared__ float red[256];
     __shared__ int is_last;
     const int t = threadIdx.x;
@@ -1152,7 +1162,7 @@ int launch_fwd(const LinFwdArgs &a, int *grid_out, cudaStream_t s) {
     const size_t smem = fwd_smem(KP, MP, RING);
     const int grid = tc_grid(a.N, smem, (TC_SPLIT_ACC < KP / 16 ? TC_SPLIT_ACC : KP / 16) * 2 * MP, NT_FWD);
     DN_CUDA(cudaFuncSetAttribute(lin_fwd_kernel<KP, MP, RING, NT_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    lin_fwd_kernel<KP, MP, RING, NT_FWD><<<grid, NT_FWD, smem, s>>>(a);
+    DN_LAUNCH((lin_fwd_kernel<KP, MP, RING, NT_FWD>), grid, NT_FWD, smem, s, a);
     *grid_out = grid;
     return 0;
 }
@@ -1161,7 +1171,7 @@ int launch_bwd(const LinBwdArgs &a, int *grid_out, cudaStream_t s) {
     const size_t smem = bwd_smem(KP, MP, RING);
     const int grid = tc_grid(a.N, smem, 2 * TC_SPLIT_ACC * 2 * KP <= 128 ? 128 : (2 * TC_SPLIT_ACC * 2 * KP <= 256 ? 256 : 512), NT_BWD);
     DN_CUDA(cudaFuncSetAttribute(lin_bwd_kernel<KP, MP, RING, NT_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    lin_bwd_kernel<KP, MP, RING, NT_BWD><<<grid, NT_BWD, smem, s>>>(a);
+    DN_LAUNCH((lin_bwd_kernel<KP, MP, RING, NT_BWD>), grid, NT_BWD, smem, s, a);
     *grid_out = grid;
     return 0;
 }
@@ -1224,7 +1234,7 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
 #undef DN_FWD_CASE
     if (rc) return rc;
     if (bn_out != nullptr) {
-        bn_finalize_kernel<<<MP / 32, 1024, 0, s>>>(reinterpret_cast<const float4 *>(a.part), grid, MP, M, N, gamma, beta, eps,
+        DN_LAUNCH(bn_finalize_kernel, MP / 32, 1024, 0, s, reinterpret_cast<const float4 *>(a.part), grid, MP, M, N, gamma, beta, eps,
                                                     momentum, bn_out, running_mean, running_var,
                                                     reinterpret_cast<long long *>(num_batches_tracked));
         DN_LAUNCHED_N(2);
@@ -1269,7 +1279,7 @@ int dn4gl_lin_bwd_f32(const float *G, const float *Gseg, const int32_t *row2seg,
 #undef DN_BWD_CASE
     if (rc) return rc;
     const int elems = MP * KP + MP + 2 * KP;
-    lin_bwd_reduce_kernel<<<(elems + 31) / 32, 1024, 0, s>>>(a.part, grid, MP, KP, M, K, dW, db, sums_prev);
+    DN_LAUNCH(lin_bwd_reduce_kernel, (elems + 31) / 32, 1024, 0, s, a.part, grid, MP, KP, M, K, dW, db, sums_prev);
     DN_LAUNCHED_N(2);
     return DN4GL_OK;
 }
@@ -1282,7 +1292,7 @@ int dn4gl_bn_act_f32(const float *Y, int64_t N, int32_t M, const float *bn, int3
     const int64_t total = N * ((M + 3) / 4);
     const int64_t want = ceil_div64(total, 256 * 4);
     const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 8;
-    bn_act_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(Y, N, M, bn, act, slope, out);
+    DN_LAUNCH(bn_act_kernel, static_cast<int>(want < cap ? want : cap), 256, 0, as_stream(stream), Y, N, M, bn, act, slope, out);
     DN_LAUNCHED();
     return DN4GL_OK;
 }
@@ -1300,12 +1310,12 @@ int dn4gl_bn_act_pool_f32(const float *Y, int64_t N, int32_t M, const float *bn,
     const int grid = B < cap ? B : cap;
     cudaStream_t s = as_stream(stream);
     switch (CHP) {
-    case 1: bn_act_pool_kernel<1><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
-    case 2: bn_act_pool_kernel<2><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
-    case 4: bn_act_pool_kernel<4><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
-    case 8: bn_act_pool_kernel<8><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
-    case 16: bn_act_pool_kernel<16><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
-    default: bn_act_pool_kernel<32><<<grid, 256, 0, s>>>(Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    case 1: DN_LAUNCH(bn_act_pool_kernel<1>, grid, 256, 0, s, Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    case 2: DN_LAUNCH(bn_act_pool_kernel<2>, grid, 256, 0, s, Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    case 4: DN_LAUNCH(bn_act_pool_kernel<4>, grid, 256, 0, s, Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    case 8: DN_LAUNCH(bn_act_pool_kernel<8>, grid, 256, 0, s, Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    case 16: DN_LAUNCH(bn_act_pool_kernel<16>, grid, 256, 0, s, Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
+    default: DN_LAUNCH(bn_act_pool_kernel<32>, grid, 256, 0, s, Y, M, bn, act, slope, out, seg_ptr, B, mode, pooled); break;
     }
     DN_LAUNCHED();
     return DN4GL_OK;
@@ -1315,7 +1325,7 @@ int dn4gl_segment_ids_i32(const int32_t *seg_ptr, int32_t B, int64_t N, int32_t 
     DN_ARG(B >= 0 && N >= 0);
     if (N == 0) return DN4GL_OK;
     DN_ARG(seg_ptr != nullptr && out != nullptr && B >= 1);
-    segment_ids_kernel<<<static_cast<unsigned>(ceil_div64(N, 256)), 256, 0, as_stream(stream)>>>(seg_ptr, B, N, out);
+    DN_LAUNCH(segment_ids_kernel, static_cast<unsigned>(ceil_div64(N, 256)), 256, 0, as_stream(stream), seg_ptr, B, N, out);
     DN_LAUNCHED();
     return DN4GL_OK;
 }
@@ -1331,7 +1341,7 @@ int dn4gl_dot_f32(const float *a, const float *b, int64_t n, float *out, void *w
     DN_ARG(ws_bytes >= dn4gl_dot_workspace_bytes(n));
     const int64_t want = ceil_div64(n > 0 ? n : 1, 256 * 16);
     const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 4;
-    dot_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(a, b, n, out, static_cast<float *>(ws), counter);
+    DN_LAUNCH(dot_kernel, static_cast<int>(want < cap ? want : cap), 256, 0, as_stream(stream), a, b, n, out, static_cast<float *>(ws), counter);
     DN_LAUNCHED();
     return DN4GL_OK;
 }
@@ -1358,14 +1368,14 @@ int dn4gl_bn_bwd_sums_f32(const float *G, const float *Gseg, const int32_t *row2
     const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
     float *part = static_cast<float *>(ws);
     switch (CHP) {
-    case 1: bn_bwd_sums_kernel<1><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    case 2: bn_bwd_sums_kernel<2><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    case 4: bn_bwd_sums_kernel<4><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    case 8: bn_bwd_sums_kernel<8><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    case 16: bn_bwd_sums_kernel<16><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    default: bn_bwd_sums_kernel<32><<<grid, 256, 0, s>>>(G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 1: DN_LAUNCH(bn_bwd_sums_kernel<1>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 2: DN_LAUNCH(bn_bwd_sums_kernel<2>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 4: DN_LAUNCH(bn_bwd_sums_kernel<4>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 8: DN_LAUNCH(bn_bwd_sums_kernel<8>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 16: DN_LAUNCH(bn_bwd_sums_kernel<16>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    default: DN_LAUNCH(bn_bwd_sums_kernel<32>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
     }
-    bn_bwd_sums_reduce_kernel<<<(8 * CHP + 31) / 32, 1024, 0, s>>>(part, grid, CHP, M, sums);
+    DN_LAUNCH(bn_bwd_sums_reduce_kernel, (8 * CHP + 31) / 32, 1024, 0, s, part, grid, CHP, M, sums);
     DN_LAUNCHED_N(2);
     return DN4GL_OK;
 }
