@@ -193,3 +193,44 @@ def test_integration_md_binding_matches_the_header():
         n += 1 if cur.strip() else 0
         assert n == len(protos[name][1]), "%s: example call passes %d arguments, the header declares %d" % (
             name, n, len(protos[name][1]))
+
+
+def test_every_kernel_launched_through_dn_launch_waits_for_its_predecessor():
+    """source-level guard of the programmatic-dependent-launch contract (csrc/common.cuh): a kernel that may be launched
+    with the PDL attribute (DN_LAUNCH) must execute DN_PDL_WAIT() before it touches global memory; the product build
+    compiles both macros away, so only this check keeps the experiment build (-DDN4GL_PDL) honest."""
+    csrc = os.path.join(ROOT, "dummynode4graphlearning_b200", "csrc")
+    launched, bodies = set(), {}
+    for fn in sorted(os.listdir(csrc)):
+        if not fn.endswith(".cu"):
+            continue
+        src = open(os.path.join(csrc, fn)).read()
+        while "__launch_bounds__" in src:          # drop the attribute (its argument list may nest parentheses)
+            a = src.index("__launch_bounds__")
+            b, depth = src.index("(", a), 0
+            while True:
+                depth += {"(": 1, ")": -1}.get(src[b], 0)
+                b += 1
+                if depth == 0:
+                    break
+            src = src[:a] + src[b:]
+        launched |= set(re.findall(r"DN_LAUNCH\(\(?([A-Za-z_]\w*)", src))
+        for m in re.finditer(r"__global__[^;{]*?\b([A-Za-z_]\w*)\s*\(", src):
+            i = src.index("{", m.end())
+            depth, j = 0, i
+            while True:
+                depth += {"{": 1, "}": -1}.get(src[j], 0)
+                if depth == 0:
+                    break
+                j += 1
+            bodies[m.group(1)] = src[i:j]
+    assert len(launched) >= 20
+    for k in sorted(launched):
+        assert k in bodies, k
+        body = bodies[k]
+        assert "DN_PDL_WAIT()" in body, "%s is launched through DN_LAUNCH but never waits" % k
+        head = body[: body.index("DN_PDL_WAIT()")]
+        # nothing before the wait may read or write global memory (under DN4GL_PDL; an #ifndef DN4GL_PDL block is fine)
+        head = re.sub(r"#ifndef DN4GL_PDL.*?#endif", "", head, flags=re.S)
+        for bad in ("__ldg", "__ldcg", "ldg4(", "load_chunk", "load_vec4", "load_bn4", "bulk_g2s", "issue("):
+            assert bad not in head.replace("auto issue", ""), "%s: %s before DN_PDL_WAIT()" % (k, bad)
