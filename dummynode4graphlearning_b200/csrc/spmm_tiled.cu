@@ -686,6 +686,18 @@ __device__ __forceinline__ int tile_boundary(const int32_t *__restrict__ seg_ptr
     }
     const int gs = seg_ptr[lo];
     if (gs < target + C) { *aligned = true; return gs; }
+#ifdef DN4GL_TILE_WHOLE_GRAPHS
+    // EXPERIMENT (off in the product build; `make libdn4gl_exp.so EXP_FLAGS=-DDN4GL_TILE_WHOLE_GRAPHS`, host model and
+    // invariants: tools/k1_tiles_model.py).  Window k lies inside graph lo - 1 = [s, e).  If that graph fits one stage
+    // (rows <= 2 C <= cap_rows) it is not cut: the spanned window's slot -- otherwise an arbitrary cut -- starts at the
+    // graph's first row, so tile k - 1 ends there and tile k = [s, e) is the whole graph (closed, unchecked fast path).
+    // C2: rows in cut tiles 15.2 % -> 5.8 %.  Boundaries stay non-decreasing and every tile still lies within one
+    // window of its slot; anything this gets wrong is caught as before (verify_tiles_kernel, capacity checks).
+    if (lo >= 1) {
+        const int s = seg_ptr[lo - 1];
+        if (gs - s <= 2 * C) { *aligned = true; return (k == s / C + 1) ? s : gs; }
+    }
+#endif
     *aligned = false;
     return static_cast<int>(target);
 }
@@ -726,6 +738,9 @@ __global__ void collect_cut_heavy_kernel(const int32_t *__restrict__ row_ptr, in
     int k = r / C;
     if (k >= T) k = T - 1;
     if (r < tiles[k].x) --k;
+#ifdef DN4GL_TILE_WHOLE_GRAPHS
+    else if (r >= tiles[k].y && k + 1 < T) ++k;   // the next slot's tile may start inside this window
+#endif
     if (tiles[k].w < 0) {
         const int i = atomicAdd(heavy_count, 1);
         if (i < cap) heavy_list[i] = r;

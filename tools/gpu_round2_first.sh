@@ -1,13 +1,13 @@
 #!/bin/bash
 # First GPU call of a round, everything the prepared experiments need in ONE box (≈ 25-30 min):
 #   make -C dummynode4graphlearning_b200/csrc libdn4gl_pdl1.so libdn4gl_pdl2.so
-#   make -C dummynode4graphlearning_b200/csrc libdn4gl_exp.so EXP_FLAGS=-DDN4GL_K1_TWO_ROWS      (here; the .so travel)
+#   make -C dummynode4graphlearning_b200/csrc libdn4gl_exp_whole.so libdn4gl_exp_tworows.so libdn4gl_exp_both.so   (here; the .so travel)
 #   gpurun --timeout 2400 -- 'bash tools/gpu_round2_first.sh r2a'
 # 1. tools/gpu_suite.sh   : pytest -m gpu (incl. the never-run test_zzz_* cases), bench line, ncu launch list, ncu --set
 #                           full of the aggregation kernel
 # 2. ncu --set full of lin_bwd_kernel (17.5 % of the step's GPU time)
 # 3. tools/gpu_ab_pdl.sh  : programmatic dependent launch, parity + bench for both variants
-# 4. tools/gpu_ab_k1.sh   : the K1 experiment the exp library was built with + 3 / 4 stages
+# 4. tools/gpu_ab_k1.sh   : every K1 experiment library present (whole-graph tiles, two rows in flight, both) + 3 / 4 stages
 TAG=${1:-rX}
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
@@ -17,5 +17,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:lin_
     > gpurun_out/${TAG}_ncu_lin_bwd.log 2>&1
 echo "ncu lin_bwd rc=$?"
 bash tools/gpu_ab_pdl.sh "$TAG"
-test -f dummynode4graphlearning_b200/csrc/libdn4gl_exp.so && bash tools/gpu_ab_k1.sh "$TAG"
+bash tools/gpu_ab_k1.sh "$TAG"
 ls -la gpurun_out | tail -40
