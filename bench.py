@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graphs", type=int, default=1113, help="graphs per GPU (C2: 1113)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--size-hints", action="store_true",
+                    help="EXPERIMENT (off by default): put transforms.tu_conjugate_sizes(raw) into the batches so that the "
+                         "transform allocates its outputs without its device->host size read-back")
     return ap.parse_args()
 
 
@@ -301,6 +304,8 @@ def ours(a):
     raw = synth.tu_batch("proteins", a.graphs, seed=rank)      # weak scaling: every rank owns its own 1113 graphs
     host = pin_batch({k: v for k, v in raw.items() if k != "vattr"})
     dev_batch = T.to_device({k: v for k, v in raw.items() if k != "vattr"}, dev)
+    if a.size_hints:      # what a loader that sees its batch on the host would attach (computed once here: the batch is fixed)
+        host["conj_sizes"] = dev_batch["conj_sizes"] = T.tu_conjugate_sizes(raw, with_dummy=True)
     torch.manual_seed(0)
     args = Namespace(num_features=NUM_NODE_LABELS, hidden_dim=HID, num_classes=CLASSES, dropout_ratio=0.0,
                      additional={"train_eps": True, "num_layers": LAYERS, "aggregation": "sum"}, epochs=1, device=str(dev))
@@ -529,7 +534,9 @@ def ours(a):
     line = {
         "metric": "train graphs/sec", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": a.steps,
         "warmup": n_warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(a.graphs, world),
+        "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(a.graphs, world), **({"size_hints": "experiment: transform output sizes computed on "
+                       "the host (tu_conjugate_sizes), no size read-back"} if a.size_hints else {})),
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": host_bytes(host), "d2h_bytes_per_step": 4 + 8 + 4,

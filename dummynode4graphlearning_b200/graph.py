@@ -169,7 +169,8 @@ def check_errors():
         if code != 0:
             f.zero_()
             raise RuntimeError("dn4gl builder kernel reported error %d on cuda:%d (-3: row degree above "
-                               "DN4GL_MAX_ROW_DEGREE; -1: keys passed as sorted were not)" % (code, idx))
+                               "DN4GL_MAX_ROW_DEGREE; -1: keys passed as sorted were not; -5: a conj_sizes hint did not match "
+                               "the sizes the device counted)" % (code, idx))
 
 
 def _i32(t, device):

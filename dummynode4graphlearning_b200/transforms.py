@@ -20,6 +20,7 @@ bit-exact with the reference (tests/test_transforms_gpu.py).
 import math
 from copy import deepcopy
 
+import numpy as np
 import torch
 
 from ._lib import lib, ptr
@@ -87,7 +88,7 @@ def to_device(b, device):
     dev = torch.device(device)
     out = {}
     for k, v in b.items():
-        if k in ("num_graphs", "has_edge_labels", "max_graph_nodes"):
+        if k in ("num_graphs", "has_edge_labels", "max_graph_nodes", "conj_sizes"):
             out[k] = v
         elif k.endswith("attr"):
             out[k] = torch.as_tensor(v).to(dev, torch.float32).contiguous()
@@ -135,7 +136,29 @@ def tu_add_dummy(b):
         o["y"] = b["y"]
     if b.get("max_graph_nodes") is not None:
         o["max_graph_nodes"] = int(b["max_graph_nodes"]) + 1
+    if b.get("conj_sizes") is not None:      # host-side size hint for the tu_conjugate that follows (tu_conjugate_sizes)
+        o["conj_sizes"] = b["conj_sizes"]
     return o
+
+
+def tu_conjugate_sizes(raw, with_dummy):
+    """Sizes of the edge-to-vertex transform of a RAW TU-flavoured host batch (numpy arrays), computed on the host without
+    building it: ``(V', E', nodes of the largest output graph)`` of ``tu_conjugate(tu_add_dummy(raw))`` (with_dummy) or
+    ``tu_conjugate(raw)`` (LINE_).  V' = m [+ 1 per graph], E' = sum_v in(v) out(v) [+ 2 m] (tu_data_processing.py:223-338;
+    multi-edges count with their multiplicity, a self loop is both an in- and an out-edge of its node).  Put the result
+    into the batch as ``conj_sizes`` (a loader knows its batch on the host anyway): ``tu_conjugate`` then allocates its
+    outputs from it instead of reading the sizes back from the device, which removes the transform's only host
+    synchronisation.  The hint MUST come from this function applied to the same batch: the fill kernel writes E' edges."""
+    node_ptr, edge_ptr = np.asarray(raw["node_ptr"], np.int64), np.asarray(raw["edge_ptr"], np.int64)
+    src, dst = np.asarray(raw["src"], np.int64), np.asarray(raw["dst"], np.int64)
+    B, N, m = len(node_ptr) - 1, int(node_ptr[-1]), int(edge_ptr[-1])
+    ind, outd = np.bincount(dst, minlength=N), np.bincount(src, minlength=N)
+    pairs = int((ind * outd).sum())
+    per_graph = np.diff(edge_ptr)
+    if with_dummy:
+        has_nodes = np.diff(node_ptr) > 0          # a graph without nodes gets no dummy edges, hence no dummy vertex
+        return m + int(has_nodes.sum()), pairs + 2 * m, int((per_graph + has_nodes).max()) if B else 0
+    return m, pairs, int(per_graph.max()) if B else 0
 
 
 def tu_conjugate(b):
@@ -153,10 +176,17 @@ def tu_conjugate(b):
     L.call("dn4gl_tu_conjugate_count", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
            ptr(isd), N, E, ptr(csr_in.row_ptr), ptr(csr_in.eid), ptr(cand_off), ptr(newid),
            ptr(o_node_ptr), ptr(o_edge_ptr), ptr(ws), ws_bytes, _stream())
-    max_nodes = (o_node_ptr[1:] - o_node_ptr[:-1]).max() if B > 0 else o_node_ptr[-1]
-    sizes = torch.stack([o_node_ptr[-1], o_edge_ptr[-1], max_nodes]).cpu()  # the one D2H sync: output sizes
-    V2, E2 = int(sizes[0]), int(sizes[1])
-    o = LazyDict(num_graphs=B, max_graph_nodes=int(sizes[2]), node_ptr=o_node_ptr, edge_ptr=o_edge_ptr,
+    hint = b.get("conj_sizes")
+    if hint is not None:                      # sizes known on the host (tu_conjugate_sizes): no read-back, no sync
+        V2, E2, max_nodes = (int(v) for v in hint)
+        flag = error_flag(dev)                # a hint that does not match the device's counts raises the async flag
+        wrong = (o_node_ptr[-1:] != V2) | (o_edge_ptr[-1:] != E2)
+        flag.copy_(torch.where(wrong, torch.full_like(flag, -5), flag))
+    else:
+        max_nodes = (o_node_ptr[1:] - o_node_ptr[:-1]).max() if B > 0 else o_node_ptr[-1]
+        sizes = torch.stack([o_node_ptr[-1], o_edge_ptr[-1], max_nodes]).cpu()  # the one D2H sync: output sizes
+        V2, E2, max_nodes = int(sizes[0]), int(sizes[1]), int(sizes[2])
+    o = LazyDict(num_graphs=B, max_graph_nodes=max_nodes, node_ptr=o_node_ptr, edge_ptr=o_edge_ptr,
                  src=_empty_i32(E2, dev), dst=_empty_i32(E2, dev),
                  v_origin=_empty_i32(V2, dev), e_shared=_empty_i32(E2, dev))
     L.call("dn4gl_tu_conjugate_fill", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),

@@ -44,3 +44,24 @@ def test_reference_arm_other_ranks_do_no_work():
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                                   text=True, cwd=ROOT, env=env)
     assert out.strip() == ""
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_tu_conjugate_sizes_match_the_oracle(seed):
+    """transforms.tu_conjugate_sizes (host-side size hint that removes the transform's read-back) == the sizes of the
+    oracle's edge-to-vertex transform, on the synthetic shapes and on multigraphs with loops / isolated nodes / edgeless
+    graphs, with and without the dummy augmentation."""
+    import numpy as np
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from helpers import nasty_tu_batch
+    from oracle import transforms as OT
+    rng = np.random.default_rng(seed)
+    if seed < 4:
+        raw = synth.tu_batch("proteins" if seed % 2 else "mutag", 7 + seed, seed=seed)
+    else:
+        raw = nasty_tu_batch(rng, int(rng.integers(1, 6)))
+    for with_dummy in (True, False):
+        ref = OT.tu_conjugate(OT.tu_add_dummy(raw)) if with_dummy else OT.tu_conjugate(raw)
+        nodes = np.diff(np.asarray(ref["node_ptr"], np.int64))
+        want = (int(ref["node_ptr"][-1]), int(ref["edge_ptr"][-1]), int(nodes.max()))
+        assert T.tu_conjugate_sizes(raw, with_dummy) == want, (seed, with_dummy)

@@ -17,5 +17,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:lin_
     > gpurun_out/${TAG}_ncu_lin_bwd.log 2>&1
 echo "ncu lin_bwd rc=$?"
 bash tools/gpu_ab_pdl.sh "$TAG"
+# 3b. host-side size hints (no size read-back in the transform), product library
+timeout 300 python bench.py --no-cpu-baseline --size-hints > gpurun_out/${TAG}_bench_size_hints.json 2> gpurun_out/${TAG}_bench_size_hints.err
+echo "size-hints bench rc=$?"; cut -c1-260 gpurun_out/${TAG}_bench_size_hints.json
 bash tools/gpu_ab_k1.sh "$TAG"
 ls -la gpurun_out | tail -40
