@@ -234,3 +234,14 @@ def test_every_kernel_launched_through_dn_launch_waits_for_its_predecessor():
         head = re.sub(r"#ifndef DN4GL_PDL.*?#endif", "", head, flags=re.S)
         for bad in ("__ldg", "__ldcg", "ldg4(", "load_chunk", "load_vec4", "load_bn4", "bulk_g2s", "issue("):
             assert bad not in head.replace("auto issue", ""), "%s: %s before DN_PDL_WAIT()" % (k, bad)
+
+
+def test_product_library_contains_no_experiment_code():
+    """the prepared experiments (-DDN4GL_PDL, see csrc/Makefile) must stay out of libdn4gl.so: no programmatic-dependent-
+    launch instructions (griddepcontrol.wait / launch_dependents = SASS ACQBULK / PREEXIT) in the product SASS."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.SO_PATH], capture_output=True, text=True, check=True).stdout
+    assert "ACQBULK" not in sass and "PREEXIT" not in sass
+    assert sass.count("Function :") >= 100          # the scan really saw the kernels
