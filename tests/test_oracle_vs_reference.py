@@ -487,3 +487,68 @@ def test_tu_io_fuzz_live(seed):
         lines = tuio.tu_file_lines(rd.igraphs_to_batch(graphs))
         for suffix, ref_lines in files.items():
             assert lines[suffix] == ref_lines, suffix
+
+
+@pytest.mark.parametrize("name,add,variant,seed", [
+    ("GIN", {"train_eps": True, "num_layers": 3, "aggregation": "sum"}, "conj", 0),
+    ("GIN", {"train_eps": False, "num_layers": 2, "aggregation": "mean"}, "dummy", 1),
+    ("GIN", {"train_eps": True, "num_layers": 2, "aggregation": "sum"}, "line", 2),
+    ("RGIN", {"num_layers": 2}, "dummy", 3),
+    ("RGIN", {"num_layers": 3}, "conj", 4),
+])
+def test_classification_models_fuzz_live(name, add, variant, seed):
+    """the reference's own GIN / classification RGIN classes (gconv.py, rgconv.py, run under oracle/shims) on the PyG view
+    of DUMMY_ / CONJ_ / LINE_ multigraphs with self loops, repeated edges, isolated nodes and edgeless graphs (the view
+    removes loops and merges repeats, so nodes without any edge and graphs of a single vertex reach the layers):
+    log-softmax outputs, loss and every gradient of the oracle restatement == the reference."""
+    import torch.nn.functional as F
+    from argparse import Namespace
+    from oracle import ref_drive as rd
+    for attempt in range(50):     # LINE_ of an edgeless graph has no vertices (nothing a loader would keep): draw again
+        rng = np.random.default_rng(7000 + seed + 100 * attempt)
+        raw = nasty_tu_batch(rng, int(rng.integers(3, 7)))
+        b = {"dummy": lambda: OT.tu_add_dummy(raw), "conj": lambda: OT.tu_conjugate(OT.tu_add_dummy(raw)),
+             "line": lambda: OT.tu_conjugate(raw)}[variant]()
+        if int(np.diff(b["node_ptr"]).min()) > 0:
+            break
+    else:
+        raise AssertionError("no usable batch")
+    vl, el = np.asarray(b["vlabel"], np.int64), np.asarray(b["elabel"], np.int64)
+    vmin, emin = int(vl.min()), int(el.min()) if len(el) else 0
+    R = (int(el.max()) - emin + 1) if len(el) else 1
+    s, d, first, mult = OT.pyg_coalesce(b["src"], b["dst"], el - emin, R)
+    x = torch.from_numpy(np.eye(int(vl.max()) - vmin + 1, dtype=np.float32)[vl - vmin])
+    edge_index = torch.from_numpy(np.stack([s, d]).astype(np.int64))
+    edge_attr = torch.from_numpy(mult.astype(np.float32))
+    B = int(b["num_graphs"])
+    batch = torch.from_numpy(np.repeat(np.arange(B), np.diff(b["node_ptr"])).astype(np.int64))
+    y = torch.from_numpy(np.asarray(raw["y"], np.int64))
+    args = Namespace(num_features=x.size(1), hidden_dim=8, nhid=8, num_classes=2, dropout_ratio=0.0, additional=add,
+                     epochs=1, device="cpu", num_relations=R)
+    model = rd.ref_classifier(name, args, seed=seed)
+    with torch.no_grad():
+        for n, p_ in model.named_parameters():
+            if n.endswith("eps"):
+                p_.fill_(0.2)
+    model.train()
+    out_ref = model(Namespace(x=x, edge_index=edge_index, edge_attr=edge_attr, batch=batch, y=y))
+    loss_ref = F.nll_loss(out_ref, y)
+    loss_ref.backward()
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    nl = add["num_layers"]
+    if name == "GIN":
+        out = OM.gin_classifier(sd, x, edge_index, batch, B, nl, add["aggregation"])
+    else:
+        et = edge_attr.max(1)[1] if edge_attr.numel() else torch.zeros(0, dtype=torch.int64)
+        out = OM.rgin_classifier(sd, x, edge_index, et, batch, B, nl, R)
+    assert_close_rel(out, out_ref.detach(), 1e-6, "log_softmax")
+    loss = F.nll_loss(out, y)
+    assert_close_rel(loss, loss_ref.detach(), 1e-6, "loss")
+    loss.backward()
+    for n, p_ in model.named_parameters():
+        if p_.grad is None:
+            continue
+        got = sd[n].grad
+        if got is None and n.startswith("convs.") and ".nn." in n:     # aliases of nns.* (gconv.py:195-197)
+            got = sd[n.replace("convs.", "nns.").replace(".nn.", ".")].grad
+        assert_close_rel(got, p_.grad, 2e-5, "grad " + n, atol=2e-5)
