@@ -78,10 +78,40 @@ def main():
     from oracle import transforms as OT   # dev tool: the oracle builds the C2 structure on the host
     conj = OT.tu_conjugate(OT.tu_add_dummy(synth.tu_batch("proteins", 1113, seed=0)))
     seg = conj["node_ptr"].astype(np.int64)
+    s_, d_, _, _ = OT.pyg_coalesce(conj["src"], conj["dst"])
+    deg = np.bincount(d_, minlength=int(seg[-1]))
+    row_cost = deg // 4 + deg % 4 + 1                     # four-neighbour batches + remainders + row overhead
     for whole in (False, True):
         share, biggest = check(seg, C, whole)
         print("C2, window %d, %s: %.1f %% of the rows in cut tiles (checked slow path), largest closed tile %d rows"
               % (C, "whole graphs up to 2 windows" if whole else "shipped rule", 100 * share, biggest))
+        # round-robin deal of the work items over 148 persistent CTAs (long rows of cut tiles first, as the kernel does);
+        # rows on the checked path are charged SLOW x the unchecked cost (an assumption -- the timeline only says "slower")
+        for slow in (1.5, 2.5):
+            items = []
+            tiles = make_tiles(seg, C, whole)
+            for r0, r1, cut in tiles:
+                if cut:
+                    items += [float(np.ceil(deg[r] / 31.0 / 4.0) + 8) for r in range(r0, r1) if deg[r] > 64]
+            for r0, r1, cut in tiles:
+                c = row_cost[r0:r1]
+                if cut:
+                    c = np.where(deg[r0:r1] > 64, 0, c)
+                items.append(float(c.sum()) * (slow if cut else 1.0) / 31.0)
+            def deal(seq, serpentine=False):
+                load = np.zeros(148)
+                for i, w in enumerate(seq):
+                    r, c = divmod(i, 148)
+                    load[147 - c if (serpentine and r % 2) else c] += w
+                return load.max() / load.mean()
+            H = len(items) - len(tiles)
+            by_cost = items[:H] + sorted(items[H:], reverse=True)       # long rows first as today, then tiles by cost
+            lpt = np.zeros(148)
+            for w in sorted(items, reverse=True):
+                lpt[lpt.argmin()] += w
+            print("    checked path %.1fx: %d items, max / mean CTA load: as dealt today %.2f, tiles sorted by cost %.2f, "
+                  "sorted + serpentine %.2f, greedy longest-first %.2f"
+                  % (slow, len(items), deal(items), deal(by_cost), deal(by_cost, True), lpt.max() / lpt.mean()))
 
 
 if __name__ == "__main__":
