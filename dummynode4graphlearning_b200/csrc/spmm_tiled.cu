@@ -747,6 +747,98 @@ __global__ void collect_cut_heavy_kernel(const int32_t *__restrict__ row_ptr, in
     }
 }
 
+#ifdef DN4GL_TILE_BALANCE
+// EXPERIMENT (off in the product build; `make libdn4gl_exp_balance.so`, host model: tools/k1_tiles_model.py).  The pipe
+// kernel deals its work items round-robin: CTA b takes the items t with t % G == b, the H listed long rows first, then the
+// tiles in row order -- at C2 the estimated spread of the CTA loads is 1.7-2.2x the mean and the slowest CTA is the
+// kernel's duration.  This kernel PERMUTES the tile descriptors in place (the pipe kernel does not care about their
+// order) so that the same deal hands every CTA about the same work: tiles sorted by estimated cost, longest first, each
+// given to the least-loaded CTA that still has a free slot (CTA b owns the slots i with (H + i) % G == b); model:
+// 1.12-1.25x.  One CTA, T <= TB_MAX descriptors held in shared memory; runs once per tiling, after the long-row list has
+// been collected (that step looks tiles up by window).
+constexpr int TB_MAX = 1024;
+__device__ __forceinline__ int tb_tile_cost(const int4 td) {
+    const int rows = td.y - td.x, nnz = (td.w & 0x7fffffff) - td.z;
+    const int c = (nnz >> 2) + rows;                 // four-neighbour batches + per-row overhead
+    return td.w < 0 ? 2 * c : c;                     // rows of cut tiles take the checked path
+}
+__global__ void __launch_bounds__(1024)
+balance_tiles_kernel(int4 *__restrict__ tiles, int T, const int32_t *__restrict__ row_ptr,
+                     const int32_t *__restrict__ heavy_list, const int32_t *__restrict__ heavy_count, int G) {
+    __shared__ int4 desc[TB_MAX];
+    __shared__ unsigned long long key[TB_MAX];       // (cost << 32) | (0xffffffff - index): descending sort, stable
+    __shared__ int dest[TB_MAX];
+    __shared__ int load[256], freec[256], used[256];
+    const int tid = threadIdx.x;
+    int P = 1;
+    while (P < T) P <<= 1;
+    for (int i = tid; i < P; i += blockDim.x) {
+        unsigned long long k = 0ull;
+        if (i < T) {
+            const int4 td = tiles[i];
+            desc[i] = td;
+            k = (static_cast<unsigned long long>(static_cast<unsigned>(tb_tile_cost(td))) << 32) |
+                static_cast<unsigned long long>(0xffffffffu - static_cast<unsigned>(i));
+        }
+        key[i] = k;
+    }
+    const int H = (heavy_list != nullptr && heavy_count != nullptr) ? *heavy_count : 0;
+    for (int b = tid; b < G; b += blockDim.x) {
+        const int first = ((b - H % G) % G + G) % G;          // first tile slot i with (H + i) % G == b
+        load[b] = 0;
+        used[b] = 0;
+        freec[b] = first < T ? (T - 1 - first) / G + 1 : 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < H; i += blockDim.x) {                // the listed long rows keep their places
+        const int r = heavy_list[i];
+        atomicAdd(&load[i % G], ((row_ptr[r + 1] - row_ptr[r]) >> 2) + 256);
+    }
+    for (int k2 = 2; k2 <= P; k2 <<= 1) {                      // bitonic sort, descending
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < P; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = key[i], c = key[l];
+                    const bool desc_run = (i & k2) == 0;
+                    if (desc_run ? (a < c) : (a > c)) { key[i] = c; key[l] = a; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {                                            // greedy longest-first, one warp, items in sorted order
+        for (int k = 0; k < T; ++k) {
+            unsigned long long best = ~0ull;                   // (load << 32) | b of the least-loaded CTA with a free slot
+            for (int b = tid; b < G; b += 32)
+                if (freec[b] > 0) {
+                    const unsigned long long v = (static_cast<unsigned long long>(static_cast<unsigned>(load[b])) << 32) |
+                                                 static_cast<unsigned>(b);
+                    best = v < best ? v : best;
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o);
+                best = v < best ? v : best;
+            }
+            if (tid == 0) {
+                const int b = static_cast<int>(best & 0xffffffffu);
+                const int first = ((b - H % G) % G + G) % G;
+                dest[k] = first + used[b] * G;
+                used[b] += 1;
+                freec[b] -= 1;
+                load[b] += static_cast<int>(key[k] >> 32);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < T; k += blockDim.x)
+        tiles[dest[k]] = desc[0xffffffffu - static_cast<unsigned>(key[k] & 0xffffffffu)];
+}
+#endif
+
 extern "C" int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t window_rows, const int32_t *row_ptr,
                                     const int32_t *col, int64_t N, int32_t *tile_desc, int32_t num_tiles,
                                     int32_t *heavy_list, int32_t heavy_cap, int32_t *heavy_count, void *stream) {
@@ -767,6 +859,16 @@ extern "C" int dn4gl_make_row_tiles(const int32_t *seg_ptr, int32_t B, int32_t w
                 heavy_cap, heavy_count);
             ++launched;
         }
+#ifdef DN4GL_TILE_BALANCE
+        {
+            const int G = dn4gl_num_sms();
+            if (num_tiles > G && num_tiles <= TB_MAX && G <= 256) {
+                balance_tiles_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<int4 *>(tile_desc), num_tiles, row_ptr, heavy_list,
+                                                         heavy_count, G);
+                ++launched;
+            }
+        }
+#endif
     }
     if (launched) DN_LAUNCHED_N(launched);
     return DN4GL_OK;

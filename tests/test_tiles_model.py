@@ -37,3 +37,36 @@ def test_whole_graph_rule_keeps_a_spanning_graph_in_one_tile():
     # a graph longer than two windows is still cut
     seg = np.array([0, 4, 29, 33])
     assert any(cut for _, _, cut in model.make_tiles(seg, 10, whole=True))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_balanced_deal_is_a_permutation_and_flattens_the_loads(seed):
+    """the greedy longest-first slot assignment of the prepared -DDN4GL_TILE_BALANCE experiment (restated in
+    tools/k1_tiles_model.py::device_balance): every tile lands in exactly one slot, every CTA keeps its slot count, and
+    the estimated load spread of the round-robin deal shrinks on heavy-tailed tile costs."""
+    rng = np.random.default_rng(seed)
+    G, T, H = 16, int(rng.integers(40, 200)), int(rng.integers(0, 10))
+    desc, e = [], 0
+    for k in range(T):
+        rows = int(rng.integers(0, 600))
+        nnz = int(rows * rng.integers(2, 9) + (rng.integers(0, 5) == 0) * rng.integers(0, 20000))
+        desc.append((1000 * k, 1000 * k + rows, e, e + nnz, bool(rng.integers(0, 6) == 0)))
+        e += nnz
+    heavy = [int(rng.integers(256, 600)) for _ in range(H)]
+    order, dest, load = model.device_balance(desc, H, heavy, G)
+    assert sorted(order) == list(range(T)) and sorted(dest) == list(range(T))
+    cost = {i: (((d[3] - d[2]) >> 2) + (d[1] - d[0])) * (2 if d[4] else 1) for i, d in enumerate(desc)}
+    # loads recomputed from the final layout under the kernel's deal: item t -> CTA t % G, long rows first
+    after = [0] * G
+    for i in range(H):
+        after[i % G] += heavy[i]
+    for k, slot in zip(order, dest):
+        after[(H + slot) % G] += cost[k]
+    assert after == load
+    before = [0] * G
+    for i in range(H):
+        before[i % G] += heavy[i]
+    for i in range(T):
+        before[(H + i) % G] += cost[i]
+    assert max(after) <= max(before)
+    assert max(after) <= 1.35 * (sum(after) / G) or max(after) == max(cost.values())

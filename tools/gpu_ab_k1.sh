@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of the experimental aggregation-kernel builds against the product build, one gpurun call:
-#   make -C dummynode4graphlearning_b200/csrc libdn4gl_exp_whole.so libdn4gl_exp_tworows.so libdn4gl_exp_both.so
+#   make -C dummynode4graphlearning_b200/csrc libdn4gl_exp_whole.so libdn4gl_exp_tworows.so libdn4gl_exp_balance.so libdn4gl_exp_wholebal.so
 #   (here, before the call: the .so travel; `make libdn4gl_exp.so EXP_FLAGS=...` for anything else)
 #   gpurun --timeout 1500 -- 'bash tools/gpu_ab_k1.sh r2a'
 # For every libdn4gl_exp*.so present: 1. parity (the aggregation tests through DN4GL_LIB), 2. K1 alone on the C2
@@ -9,6 +9,8 @@
 #   whole   = -DDN4GL_TILE_WHOLE_GRAPHS  graphs that span a window but fit a stage become their own closed tile
 #             (tools/k1_tiles_model.py: rows on the checked slow path at C2 15.2 % -> 5.8 %)
 #   tworows = -DDN4GL_K1_TWO_ROWS        two rows per sub-group in flight (process_tile_fast2)
+#   balance = -DDN4GL_TILE_BALANCE       tile descriptors permuted so that the round-robin deal gives every CTA about the
+#             same estimated work (model: max / mean CTA load 1.7-2.2 -> 1.12-1.25); wholebal = whole + balance
 #   (measured in round 1, no gain: -DDN4GL_K1_TAIL_ILP)
 TAG=${1:-rX}
 cd "${GRAFT_REPO_ROOT:-.}"

@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of a round, everything the prepared experiments need in ONE box (≈ 25-30 min):
 #   make -C dummynode4graphlearning_b200/csrc libdn4gl_pdl1.so libdn4gl_pdl2.so
-#   make -C dummynode4graphlearning_b200/csrc libdn4gl_exp_whole.so libdn4gl_exp_tworows.so libdn4gl_exp_both.so   (here; the .so travel)
+#   make -C dummynode4graphlearning_b200/csrc libdn4gl_exp_whole.so libdn4gl_exp_tworows.so libdn4gl_exp_balance.so libdn4gl_exp_wholebal.so   (here; the .so travel)
 #   gpurun --timeout 2400 -- 'bash tools/gpu_round2_first.sh r2a'
 # 1. tools/gpu_suite.sh   : pytest -m gpu (incl. the never-run test_zzz_* cases), bench line, ncu launch list, ncu --set
 #                           full of the aggregation kernel

@@ -64,6 +64,30 @@ def check(seg_ptr, C, whole):
     return cut_rows / max(N, 1), max((r1 - r0 for r0, r1, cut in tiles if not cut), default=0)
 
 
+def device_balance(desc, H, heavy_cost, G):
+    """the slot permutation balance_tiles_kernel (-DDN4GL_TILE_BALANCE) computes, restated: desc = [(r0, r1, e0, e1, cut)],
+    H listed long rows with costs heavy_cost dealt to CTAs i % G first; returns (dest, load): dest[k] = slot of the k-th
+    tile in cost order (ties: lower index first), load = estimated CTA loads afterwards."""
+    T = len(desc)
+    cost = [((e1 - e0) >> 2) + (r1 - r0) for r0, r1, e0, e1, _ in desc]
+    cost = [2 * c if d[4] else c for c, d in zip(cost, desc)]
+    order = sorted(range(T), key=lambda i: (-cost[i], i))
+    load = [0] * G
+    for i in range(H):
+        load[i % G] += heavy_cost[i]
+    first = [((b - H % G) % G + G) % G for b in range(G)]
+    free = [((T - 1 - f) // G + 1) if f < T else 0 for f in first]
+    used = [0] * G
+    dest = []
+    for i in order:
+        b = min((load[b], b) for b in range(G) if free[b] > 0)[1]
+        dest.append(first[b] + used[b] * G)
+        used[b] += 1
+        free[b] -= 1
+        load[b] += cost[i]
+    return order, dest, load
+
+
 def main():
     C = int(sys.argv[1]) if len(sys.argv) > 1 else 311
     rng = np.random.default_rng(0)
@@ -109,9 +133,21 @@ def main():
             lpt = np.zeros(148)
             for w in sorted(items, reverse=True):
                 lpt[lpt.argmin()] += w
+            # greedy longest-first under the round-robin deal's fixed slot counts (a pure permutation of the tile slots:
+            # CTA b owns the slots i with (H + i) % 148 == b; the long rows stay where they are)
+            T = len(tiles)
+            load = np.zeros(148)
+            for i in range(H):
+                load[i % 148] += items[i]
+            free = np.bincount((H + np.arange(T)) % 148, minlength=148)
+            for w in sorted(items[H:], reverse=True):
+                b = int(np.where(free > 0, load, np.inf).argmin())
+                load[b] += w
+                free[b] -= 1
             print("    checked path %.1fx: %d items, max / mean CTA load: as dealt today %.2f, tiles sorted by cost %.2f, "
-                  "sorted + serpentine %.2f, greedy longest-first %.2f"
-                  % (slow, len(items), deal(items), deal(by_cost), deal(by_cost, True), lpt.max() / lpt.mean()))
+                  "sorted + serpentine %.2f, greedy longest-first %.2f, the same as a permutation of the tile slots %.2f"
+                  % (slow, len(items), deal(items), deal(by_cost), deal(by_cost, True), lpt.max() / lpt.mean(),
+                     load.max() / load.mean()))
 
 
 if __name__ == "__main__":
