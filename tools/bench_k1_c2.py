@@ -41,7 +41,7 @@ def main():
     for D in [int(x) for x in a.dims.split(",")]:
         x = torch.rand((N, D), device=dev)
         nbytes = 4 * D * N * 2 + 4 * E + 4 * (N + 1)
-        ref = None
+        ref = ref64 = None
         for smem in [int(v) for v in a.smem.split(",")]:
             for warps in [int(v) for v in a.warps.split(",")]:
                 G.TILE_SMEM, G.TILE_WARPS = smem * 1024, warps
@@ -61,10 +61,21 @@ def main():
                     if ref is None:
                         ref = out.clone()
                     ok = bool(torch.equal(ref, out))
+                    err = None
+                    try:    # independent check (float64 scatter-add over the CSR): an experiment build must stay <= 1e-5
+                        if ref64 is None:
+                            rp = s.csr_in.row_ptr[: N + 1].long()
+                            rows = torch.repeat_interleave(torch.arange(N, device=dev), rp[1:] - rp[:-1])
+                            cols = s.csr_in.col[: int(rp[-1])].long()
+                            ref64 = x.double().index_add(0, rows, x.double()[cols])
+                        err = float((out.double() - ref64).abs().max() / ref64.abs().max())
+                    except Exception as ex:   # noqa: BLE001 -- the timing line must survive a failing check
+                        err = "check failed: " + str(ex)[:120]
                     us = statistics.median(ts)
                     print(json.dumps({"D": D, "smem_kb": smem, "warps": warps, "stages": t["stages"], "window": t["window"],
                                       "cap_rows": t["cap_rows"], "tiles": t["T"], "us": round(us, 2), "min_us": round(min(ts), 2),
-                                      "gbs": round(nbytes / us / 1e3, 1), "frac": round(nbytes / us / 1e3 / peak, 3), "same": ok}))
+                                      "gbs": round(nbytes / us / 1e3, 1), "frac": round(nbytes / us / 1e3 / peak, 3), "same": ok,
+                                      "max_rel_err_vs_fp64": err}))
                 except Exception as ex:   # noqa: BLE001
                     print(json.dumps({"D": D, "smem_kb": smem, "warps": warps, "error": str(ex)[:200]}))
 
