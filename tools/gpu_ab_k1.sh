@@ -2,7 +2,7 @@
 # A/B of the experimental aggregation-kernel builds against the product build, one gpurun call:
 #   make -C dummynode4graphlearning_b200/csrc libdn4gl_exp_whole.so libdn4gl_exp_tworows.so libdn4gl_exp_balance.so libdn4gl_exp_wholebal.so
 #   (here, before the call: the .so travel; `make libdn4gl_exp.so EXP_FLAGS=...` for anything else)
-#   gpurun --timeout 1500 -- 'bash tools/gpu_ab_k1.sh r2a'
+#   gpurun --timeout 2400 -- 'bash tools/gpu_ab_k1.sh r2a'      (≈ 5 min per library: parity 2, C2 1, sweep 2-3)
 # For every libdn4gl_exp*.so present: 1. parity (the aggregation tests through DN4GL_LIB), 2. K1 alone on the C2
 # structure and the C5 sweep; the same two measurements for the product build first.  Then 3 / 4 smaller stages with the
 # product build.  Outputs under gpurun_out/<tag>_ab_*.
@@ -17,7 +17,7 @@ cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 CS=$PWD/dummynode4graphlearning_b200/csrc
 run_pair() {   # $1 = label; DN4GL_LIB set by the caller (or unset for the product build)
-  timeout 300 python tools/bench_k1_c2.py > gpurun_out/${TAG}_ab_k1_c2_$1.jsonl 2> gpurun_out/${TAG}_ab_k1_c2_$1.err
+  timeout 300 python tools/bench_k1_c2.py --smem 200 --warps 16,32 > gpurun_out/${TAG}_ab_k1_c2_$1.jsonl 2> gpurun_out/${TAG}_ab_k1_c2_$1.err
   echo "$1 k1_c2 rc=$?"; tail -3 gpurun_out/${TAG}_ab_k1_c2_$1.jsonl | cut -c1-300
   timeout 400 python tools/agg_sweep.py > gpurun_out/${TAG}_ab_sweep_$1.jsonl 2> gpurun_out/${TAG}_ab_sweep_$1.err
   echo "$1 sweep rc=$?"; tail -3 gpurun_out/${TAG}_ab_sweep_$1.jsonl | cut -c1-300
@@ -34,6 +34,6 @@ for EXP in $CS/libdn4gl_exp*.so; do
 done
 unset DN4GL_LIB
 for S in 3 4; do   # three / four smaller stages instead of the automatic choice (2 at C2), product build
-  DN4GL_TILE_STAGES=$S timeout 300 python tools/bench_k1_c2.py > gpurun_out/${TAG}_ab_k1_c2_stages$S.jsonl 2> gpurun_out/${TAG}_ab_k1_c2_stages$S.err
+  DN4GL_TILE_STAGES=$S timeout 300 python tools/bench_k1_c2.py --smem 200 --warps 16,32 > gpurun_out/${TAG}_ab_k1_c2_stages$S.jsonl 2> gpurun_out/${TAG}_ab_k1_c2_stages$S.err
   echo "stages=$S rc=$?"; tail -3 gpurun_out/${TAG}_ab_k1_c2_stages$S.jsonl | cut -c1-300
 done
