@@ -32,8 +32,13 @@ for EXP in $CS/libdn4gl_exp*.so; do
   echo "$V parity rc=$?"; tail -2 gpurun_out/${TAG}_ab_pytest_$V.log | cut -c1-200
   run_pair $V
 done
-unset DN4GL_LIB
-for S in 3 4; do   # three / four smaller stages instead of the automatic choice (2 at C2), product build
-  DN4GL_TILE_STAGES=$S timeout 300 python tools/bench_k1_c2.py --smem 200 --warps 16,32 > gpurun_out/${TAG}_ab_k1_c2_stages$S.jsonl 2> gpurun_out/${TAG}_ab_k1_c2_stages$S.err
-  echo "stages=$S rc=$?"; tail -3 gpurun_out/${TAG}_ab_k1_c2_stages$S.jsonl | cut -c1-300
+# three / four smaller stages instead of the automatic choice (2 at C2): product build and, if present, whole + balance
+# (the host model predicts that smaller stages need the tile experiments: DESIGN.md section 9 item 1)
+for LIBV in base wholebal; do
+  if [ $LIBV = base ]; then unset DN4GL_LIB; else test -f $CS/libdn4gl_exp_wholebal.so || continue; export DN4GL_LIB=$CS/libdn4gl_exp_wholebal.so; fi
+  for S in 3 4; do
+    DN4GL_TILE_STAGES=$S timeout 300 python tools/bench_k1_c2.py --smem 200 --warps 16,32 > gpurun_out/${TAG}_ab_k1_c2_${LIBV}_stages$S.jsonl 2> gpurun_out/${TAG}_ab_k1_c2_${LIBV}_stages$S.err
+    echo "$LIBV stages=$S rc=$?"; tail -3 gpurun_out/${TAG}_ab_k1_c2_${LIBV}_stages$S.jsonl | cut -c1-300
+  done
 done
+unset DN4GL_LIB
