@@ -179,28 +179,35 @@ def write_gml_graph(path, g, creator="dn4gl"):
 # ----------------------------------------------------------------------------------------------------------------------
 # directory conventions (utils/io.py:19-142)
 def get_subdirs(dirpath, leaf_only=True):
-    """utils/io.py:19-29 (post-order, the directory itself last)."""
-    subdirs, is_leaf = [], True
-    for filename in os.listdir(dirpath):
-        filename = os.path.join(dirpath, filename)
-        if os.path.isdir(filename):
-            is_leaf = False
-            subdirs.extend(get_subdirs(filename, leaf_only=leaf_only))
-    if not leaf_only or is_leaf:
-        subdirs.append(dirpath)
-    return subdirs
+    """directories below (and including) dirpath, children before their parent, siblings in directory-listing order;
+    leaf_only keeps the directories without sub-directories (same list as utils/io.py:19-29)."""
+    out, stack = [], [[dirpath, os.scandir(dirpath), True]]
+    while stack:
+        frame = stack[-1]
+        entry = next(frame[1], None)
+        if entry is None:
+            stack.pop()
+            if frame[2] or not leaf_only:
+                out.append(frame[0])
+        elif entry.is_dir():
+            frame[2] = False
+            stack.append([entry.path, os.scandir(entry.path), True])
+    return out
 
 
 def get_files(dirpath):
-    """utils/io.py:32-40"""
-    files = []
-    for filename in os.listdir(dirpath):
-        filename = os.path.join(dirpath, filename)
-        if os.path.isdir(filename):
-            files.extend(get_files(filename))
+    """every file below dirpath; a sub-directory's files take the place of the sub-directory in its parent's listing
+    (same list as utils/io.py:32-40)."""
+    out, stack = [], [os.scandir(dirpath)]
+    while stack:
+        entry = next(stack[-1], None)
+        if entry is None:
+            stack.pop()
+        elif entry.is_dir():
+            stack.append(os.scandir(entry.path))
         else:
-            files.append(filename)
-    return files
+            out.append(entry.path)
+    return out
 
 
 def _read_graphs_from_dir(dirpath):

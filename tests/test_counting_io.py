@@ -188,3 +188,35 @@ def test_load_data_equals_reference_live(layout, seed):
                 assert a[side]["num_nodes"] == b[side]["num_nodes"]
                 for k in ("src", "dst", "vid", "vlabel", "elabel", "ekey"):
                     assert np.array_equal(a[side][k], b[side][k]), (split, a["id"], side, k)
+
+
+def _make_tree(root):
+    for rel in ("a/x/1.gml", "a/x/2.gml", "a/y.gml", "b/3.gml", "c/d/e/4.gml", "top.gml"):
+        p = os.path.join(root, rel)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        open(p, "w").close()
+    os.makedirs(os.path.join(root, "empty"))
+
+
+def test_directory_walks_known_answer():
+    """get_subdirs: children before their parent, leaves only by default; get_files: every file exactly once."""
+    with tempfile.TemporaryDirectory() as d:
+        _make_tree(d)
+        rel = lambda ps: [os.path.relpath(p, d) for p in ps]
+        leaves, every, files = rel(sio.get_subdirs(d)), rel(sio.get_subdirs(d, leaf_only=False)), rel(sio.get_files(d))
+    assert sorted(leaves) == ["a/x", "b", "c/d/e", "empty"]
+    assert sorted(every) == [".", "a", "a/x", "b", "c", "c/d", "c/d/e", "empty"] and every[-1] == "."
+    for child, parent in (("a/x", "a"), ("c/d/e", "c/d"), ("c/d", "c")):
+        assert every.index(child) < every.index(parent)
+    assert sorted(files) == ["a/x/1.gml", "a/x/2.gml", "a/y.gml", "b/3.gml", "c/d/e/4.gml", "top.gml"]
+
+
+@pytest.mark.reference_live
+def test_directory_walks_equal_reference_live():
+    from oracle import refload
+    rio = refload.subgraph().io
+    with tempfile.TemporaryDirectory() as d:
+        _make_tree(d)
+        assert sio.get_subdirs(d) == rio.get_subdirs(d)
+        assert sio.get_subdirs(d, leaf_only=False) == rio.get_subdirs(d, leaf_only=False)
+        assert sio.get_files(d) == rio.get_files(d)

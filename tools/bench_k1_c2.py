@@ -42,6 +42,22 @@ def main():
         x = torch.rand((N, D), device=dev)
         nbytes = 4 * D * N * 2 + 4 * E + 4 * (N + 1)
         ref = ref64 = None
+        # what a plain device copy of the same two matrices achieves at this size (x -> out, L2 flushed): the size-bound
+        # reference for the roofline fraction (a 40 MB problem does not reach the 1 GiB copy peak either)
+        cp = torch.empty_like(x)
+        tc = []
+        for _ in range(a.iters):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cp.copy_(x)
+            e1.record()
+            torch.cuda.synchronize()
+            tc.append(e0.elapsed_time(e1) * 1e3)
+        cus = statistics.median(tc)
+        print(json.dumps({"D": D, "copy_same_size_us": round(cus, 2), "copy_min_us": round(min(tc), 2),
+                          "copy_gbs": round(8 * D * N / cus / 1e3, 1), "copy_frac": round(8 * D * N / cus / 1e3 / peak, 3)}))
+        del cp
         for smem in [int(v) for v in a.smem.split(",")]:
             for warps in [int(v) for v in a.warps.split(",")]:
                 G.TILE_SMEM, G.TILE_WARPS = smem * 1024, warps
