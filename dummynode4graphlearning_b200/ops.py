@@ -395,15 +395,15 @@ def _tc_ws(device, nbytes):
     if torch.cuda.is_current_stream_capturing():   # a CUDA graph owns its scratch (allocated from the graph's pool)
         cnt = _tc_counter.get(device.index)
         if cnt is None:                            # no eager call came first: allocate inside the capture (one fill node)
-            cnt = torch.zeros(1, dtype=torch.int32, device=device)
+            cnt = torch.zeros(64, dtype=torch.int32, device=device)
         return torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device), cnt
     if device.index not in _tc_counter:
-        _tc_counter[device.index] = torch.zeros(1, dtype=torch.int32, device=device)
+        _tc_counter[device.index] = torch.zeros(64, dtype=torch.int32, device=device)
     key = (device.index, _stream())
     ent = _tc_scratch.get(key)
     if ent is None or ent[0].numel() < nbytes:
         ent = (torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device),
-               ent[1] if ent is not None else torch.zeros(1, dtype=torch.int32, device=device))
+               ent[1] if ent is not None else torch.zeros(64, dtype=torch.int32, device=device))
         _tc_scratch[key] = ent
     return ent
 
@@ -420,7 +420,7 @@ def lin_fwd(x, weight, bias=None, in_bn=None, in_act=ACT_NONE, in_slope=0.0, bn=
     Y = torch.empty((N, M), dtype=torch.float32, device=x.device)
     rec = None
     wsb = L.size("dn4gl_lin_workspace_bytes", N, K, M)
-    ws, _ = _tc_ws(x.device, wsb)
+    ws, counters = _tc_ws(x.device, wsb)
     g = b = rm = rv = nbt = None
     eps = mom = 0.0
     if bn is not None:
@@ -429,7 +429,7 @@ def lin_fwd(x, weight, bias=None, in_bn=None, in_act=ACT_NONE, in_slope=0.0, bn=
         rm, rv, nbt = bn.get("running_mean"), bn.get("running_var"), bn.get("num_batches_tracked")
     L.call("dn4gl_lin_fwd_f32", ptr(x), N, K, ptr(in_bn), int(in_act), float(in_slope), ptr(_f32c(weight)),
            ptr(None if bias is None else _f32c(bias)), M, ptr(Y), ptr(g), ptr(b), eps, mom, ptr(rec), ptr(rm), ptr(rv),
-           ptr(nbt), ptr(ws), wsb, _stream())
+           ptr(nbt), ptr(ws), wsb, ptr(counters), _stream())
     return Y, rec
 
 
@@ -449,11 +449,11 @@ def lin_bwd(G, weight, X, Yout=None, bn=None, sums=None, g_masked=False, in_bn=N
     dW = torch.empty((M, K), dtype=torch.float32, device=dev) if want_dw else None
     db = torch.empty(M, dtype=torch.float32, device=dev) if want_db else None
     wsb = L.size("dn4gl_lin_workspace_bytes", N, K, M)
-    ws, _ = _tc_ws(dev, wsb)
+    ws, counters = _tc_ws(dev, wsb)
     L.call("dn4gl_lin_bwd_f32", ptr(G), ptr(None if gseg is None else _f32c(gseg)), ptr(row2seg),
            ptr(None if Yout is None else _f32c(Yout)), N, M, ptr(bn), ptr(sums),
            1 if g_masked else 0, ptr(_f32c(weight)), K, ptr(X), ptr(in_bn), int(in_act), float(in_slope), ptr(GX), ptr(sp),
-           ptr(dW), ptr(db), ptr(ws), wsb, _stream())
+           ptr(dW), ptr(db), ptr(ws), wsb, ptr(counters), _stream())
     return GX, sp, dW, db
 
 

@@ -387,17 +387,19 @@ int dn4gl_atb_f32(const float *A, const float *B, float *C, float *colsum_A, int
 /* 1 if (K inputs, M outputs) is inside the kernels' tile limits (currently K, M <= 64)               */
 int32_t dn4gl_lin_supported(int32_t K, int32_t M);
 size_t dn4gl_lin_workspace_bytes(int64_t N, int32_t K, int32_t M);
+#define DN4GL_LIN_COUNTERS 64
 /* Y (N x M) = act_in(bn_in(X)) W^T + bias.   X (N x K) row-major; in_bn NULL or the record (over K) of the previous
  * stage's BatchNorm; W (M x K) as nn.Linear stores it; bias NULL or (M).
  * If bn_out != NULL the per-channel batch statistics of Y (biased variance, eps) are reduced in a fixed order and
  * the record {mean, rstd, gamma*rstd, beta} (gamma / beta NULL = 1 / 0) is written to bn_out[4*M]; running_mean /
  * running_var (momentum, unbiased variance) and num_batches_tracked are updated in place when non-NULL -- the
- * training-mode semantics of nn.BatchNorm1d.  ws: dn4gl_lin_workspace_bytes.                          */
+ * training-mode semantics of nn.BatchNorm1d.  ws: dn4gl_lin_workspace_bytes.  counters: DN4GL_LIN_COUNTERS int32 that are
+ * 0 on entry and left 0 (tickets of the last-CTA merges; one array per stream that runs these stages concurrently).    */
 int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, int32_t in_act, float in_slope,
                       const float *W, const float *bias, int32_t M, float *Y,
                       const float *gamma, const float *beta, float eps, float momentum, float *bn_out,
                       float *running_mean, float *running_var, int64_t *num_batches_tracked,
-                      void *ws, size_t ws_bytes, void *stream);
+                      void *ws, size_t ws_bytes, int32_t *counters, void *stream);
 /* Backward of one stage  Y = X' W^T + b,  X' = act_in(bn_in(X)):
  *   gY = G                                  (bn == NULL), or the BatchNorm(+ReLU) backward of the stage OUTPUT:
  *        gm = G * [bn(Y) > 0] (skipped when g_masked), gY = k * (gm - s1/N - xhat * s2/N), xhat = (Y - mean) * rstd,
@@ -409,13 +411,13 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
  * The upstream gradient is G[r] + Gseg[row2seg[r]]: G (N x M, may be NULL) is the gradient arriving row-wise (the next
  * layer's aggregation backward), Gseg (B x M, may be NULL, pre-scaled by 1/n_g for mean pooling) the gradient of the
  * per-graph readout of this stage's output (global_add_pool / global_mean_pool backward, gconv.py:213) -- the broadcast
- * row is added in the prologue instead of being materialised as an N x M tensor.                      */
+ * row is added in the prologue instead of being materialised as an N x M tensor.  counters: as for dn4gl_lin_fwd_f32. */
 int dn4gl_lin_bwd_f32(const float *G, const float *Gseg, const int32_t *row2seg, const float *Yout, int64_t N, int32_t M,
                       const float *bn, const float *sums, int32_t g_masked,
                       const float *W, int32_t K,
                       const float *X, const float *in_bn, int32_t in_act, float in_slope,
                       float *GX, float *sums_prev, float *dW, float *db,
-                      void *ws, size_t ws_bytes, void *stream);
+                      void *ws, size_t ws_bytes, int32_t *counters, void *stream);
 /* out = act(bn(Y))  (bn NULL = identity): the activation a stage hands to the aggregation / readout kernels      */
 int dn4gl_bn_act_f32(const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope, float *out,
                      void *stream);

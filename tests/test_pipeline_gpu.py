@@ -139,8 +139,8 @@ def test_flat_adam_pipeline_eager_vs_graph_vs_torch():
     # grow by an order of magnitude per step -- the optimizer itself is pinned by test_flat_adam_matches_torch
     for b, c in zip(l_e, l_g):
         assert abs(b - c) <= 1e-6 * max(1.0, abs(b)), (l_e, l_g)
-    for a, b in list(zip(l_t, l_e))[:2]:
-        assert abs(a - b) <= 2e-5 * max(1.0, abs(a)), (l_t, l_e)
+    for (a, b), tol in zip(list(zip(l_t, l_e))[:2], (2e-6, 2e-4)):   # step 1: same weights; step 2: one update apart
+        assert abs(a - b) <= tol * max(1.0, abs(a)), (l_t, l_e)
     for k in s_e:
         if s_e[k].is_floating_point():
             denom = float(s_e[k].abs().max().clamp_min(1e-12))

@@ -1,0 +1,8 @@
+#!/bin/bash
+TAG=${1:-r2f}
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+CS=$PWD/dummynode4graphlearning_b200/csrc
+DN4GL_LIB=$CS/libdn4gl_pipetl.so timeout 300 python tools/pipe_timeline.py --rows 156759 > gpurun_out/${TAG}_pipe_tl.jsonl 2> gpurun_out/${TAG}_pipe_tl.err
+echo "pipe tl rc=$?"; tail -3 gpurun_out/${TAG}_pipe_tl.err
+bash tools/gpu_ncu_list.sh $TAG
