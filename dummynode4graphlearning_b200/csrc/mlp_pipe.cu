@@ -20,6 +20,7 @@
 // measures: (1) all A_lo MMAs are issued FIRST (their sum is 2^-11 of the result, truncation at that magnitude is
 // harmless) and only then the A_hi MMAs; (2) the A_hi k-steps are spread over NACC accumulators that the epilogue
 // adds in round-to-nearest fp32.  The double-buffered accumulators hide the extra tensor-memory reads.
+#include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -100,6 +101,9 @@ __device__ __forceinline__ float lds32f(uint32_t a) {
 // shared -> global bulk asynchronous store (TMA engine), tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -541,18 +545,19 @@ int launch_fwd_pipe(const LinFwdArgs &a, const BnFinalArgs &f, int *counter, cud
 constexpr int BWD_GROUP = 12;
 __host__ __device__ constexpr int bwd_pipe_part_floats(int KP, int MP) { return MP * KP + MP + 2 * KP; }
 
-template <int KP, int MP, int RING, int NCV>
+template <int KP, int MP, int RING, int NCV, int NEPI_>
 struct BwdCfg {
     static constexpr int PK = KP / 32, PM = MP / 32;
-    static constexpr int NT = (6 + NCV) * 32;
-    static constexpr int W_CONV0 = 4, W_PROD = 4 + NCV, W_MMA = 5 + NCV;
+    static constexpr int NEPI = NEPI_, NWE = 4 * NEPI;                                     // epilogue groups (tiles j % NEPI) of 4 warps
+    static constexpr int NT = (NWE + 2 + NCV) * 32;
+    static constexpr int W_CONV0 = NWE, W_PROD = NWE + NCV, W_MMA = NWE + 1 + NCV;
     static constexpr uint32_t G_BYTES = PM * PANEL128, X_BYTES = PK * PANEL128, W_BYTES = PK * MP * 128u;
     static constexpr uint32_t RAW_X = 128u * KP * 4u, RAW_SLOT = RAW_X + 512u;          // X rows + 128 row -> graph ids
     static constexpr uint32_t STAGE_BYTES = PK * PANEL128;
     static constexpr uint32_t ACCW_BYTES = 2u * MP * KP * 4u;                           // [KP/4 chunks][2 MP lanes] float4
     static constexpr uint32_t OFF_GM = 0, OFF_GK = OFF_GM + 2 * G_BYTES, OFF_X = OFF_GK + 2 * G_BYTES, OFF_W = OFF_X + 2 * X_BYTES,
-                              OFF_RAW = OFF_W + 2 * W_BYTES, OFF_STAGE = OFF_RAW + RING * RAW_SLOT, OFF_ACCW = OFF_STAGE + STAGE_BYTES,
-                              SMEM = OFF_ACCW + ACCW_BYTES + 1024;
+                              OFF_RAW = OFF_W + 2 * W_BYTES, OFF_STAGE = OFF_RAW + RING * RAW_SLOT, OFF_ACCW = OFF_STAGE + NEPI * STAGE_BYTES,
+                              SMEM = OFF_ACCW + NEPI * ACCW_BYTES + 1024;
     static constexpr int KS_D = MP / 8;
     static constexpr uint32_t ACC_COLS = 4 * KP;                                        // data accumulator 2 KP + weight accumulator 2 KP
     static constexpr uint32_t TCOLS = 2 * ACC_COLS <= 256 ? 256 : 512;
@@ -561,11 +566,11 @@ struct BwdCfg {
     static_assert(SMEM <= 227 * 1024 - 3072, "shared memory budget");
 };
 
-template <int KP, int MP, int RING, int NCV>
-__global__ void __launch_bounds__((6 + NCV) * 32, 1)
+template <int KP, int MP, int RING, int NCV, int NEPI_>
+__global__ void __launch_bounds__((4 * NEPI_ + 2 + NCV) * 32, 1)
 lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restrict__ db, float *__restrict__ sums_prev,
-                    double *__restrict__ gpart, int *__restrict__ counters) {
-    using C = BwdCfg<KP, MP, RING, NCV>;
+                    float *__restrict__ gpart, int *__restrict__ counters) {
+    using C = BwdCfg<KP, MP, RING, NCV, NEPI_>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (s_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sGm = base + C::OFF_GM, sGk = base + C::OFF_GK, sX = base + C::OFF_X, sW = base + C::OFF_W,
@@ -573,7 +578,7 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
     __shared__ __align__(8) uint64_t bars[2 * RING + 2 + 4];
     __shared__ uint32_t tmem_ptr;
     __shared__ float red_db[NCV][MP];
-    __shared__ float red_sp[4][2 * KP];
+    __shared__ float red_sp[4 * C::NEPI][2 * KP];
     __shared__ int flag_s;
     const uint32_t bar0 = s_u32(bars);
     auto raw_full = [&](int s) { return bar0 + 8u * s; };
@@ -585,7 +590,7 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     TL_SPAN(0);
     if (t == 0) {
-        for (int s = 0; s < RING; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NCV + 4); }
+        for (int s = 0; s < RING; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NCV + 4); }   // converter warps + the 4 warps of the tile's epilogue group
         mbar_init(a_full, NCV); mbar_init(a_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
         fence_barrier_init();
@@ -603,7 +608,7 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
             store_split(sW, sW + C::W_BYTES, tile_off_mn(m, c, MP), v, 0, 0);
         }
     }
-    for (uint32_t i = t * 16u; i < C::ACCW_BYTES; i += C::NT * 16u) sts128(sAccW + i, zero4());
+    for (uint32_t i = t * 16u; i < C::NEPI * C::ACCW_BYTES; i += C::NT * 16u) sts128(sAccW + i, zero4());
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -619,6 +624,12 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
         // ---------------------------------------------------------------- producer: raw X slabs (+ row -> graph ids)
         if (lane == 0) {
             TL_DECL;
+            if (my_tiles > 1) {                                  // tile 1's G / Yout slabs (tile 0 is loaded right away)
+                const int64_t prow = tile_row0(1), pleft = a.N - prow;
+                const uint32_t pb = static_cast<uint32_t>(pleft < 128 ? pleft : 128) * a.M * 4u;
+                if (a.G != nullptr) bulk_prefetch_l2(a.G + prow * a.M, pb);
+                if (has_bn) bulk_prefetch_l2(a.Yo + prow * a.M, pb);
+            }
             for (int j = 0; j < my_tiles; ++j) {
                 const int s = j % RING, use = j / RING;
                 TL_WAIT(0, mbar_wait(raw_empty(s), (use & 1) ^ 1));
@@ -628,6 +639,14 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
                 mbar_expect_tx(raw_full(s), xb + sb);
                 bulk_g2s(sRaw + s * C::RAW_SLOT, a.X + row0 * a.K, xb, raw_full(s));
                 if (has_seg) bulk_g2s(sRaw + s * C::RAW_SLOT + C::RAW_X, a.row2seg + row0, sb, raw_full(s));
+                // G and Yout are read by the converters with plain loads one tile ahead: pull their slabs into L2 early
+                // (TMA L2 prefetch), so that those loads see L2 latency instead of a loaded HBM queue
+                if (j + 2 < my_tiles) {
+                    const int64_t prow = tile_row0(j + 2), pleft = a.N - prow;
+                    const uint32_t pb = static_cast<uint32_t>(pleft < 128 ? pleft : 128) * a.M * 4u;
+                    if (a.G != nullptr) bulk_prefetch_l2(a.G + prow * a.M, pb);
+                    if (has_bn) bulk_prefetch_l2(a.Yo + prow * a.M, pb);
+                }
             }
             TL_DONE(0);
         }
@@ -710,7 +729,7 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
                 const int r = r_m + RPm * i;
                 float4 g = gw[i % PF];
                 const float4 y = yw[i % PF];
-                if (i + PF < NPm) issue(j, i + PF, gw[i % PF], yw[i % PF]); else issue(j + 1, i + PF - NPm, gw[i % PF], yw[i % PF]);
+                if (i + PF < NPm) issue(j, i + PF, gw[i % PF], yw[i % PF]);      // later passes of THIS tile
                 if (r < valid && colm_ok) {
                     if (has_seg) {
                         const int seg = static_cast<int>(lds32f_i(slab + C::RAW_X + r * 4));
@@ -756,6 +775,11 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
             fence_async_smem();
             __syncwarp();
             if (lane == 0) { mbar_arrive(a_full); mbar_arrive(raw_empty(s)); }
+            // the first passes of the NEXT tile, issued only now: the proxy fence above is a full memory barrier and would
+            // wait for them (one HBM round trip per tile, measured); they fly while this warp waits for the MMAs, and the
+            // producer has pulled their slabs into L2 a tile earlier
+#pragma unroll
+            for (int i = 0; i < PF; ++i) issue(j + 1, i, gw[i], yw[i]);
         }
         if (ct == 0) TL_DONE(2);
         // db: lanes sharing a chunk (fixed butterfly), then the converter warps through shared memory
@@ -764,7 +788,7 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
             float *p = &red_db[w - C::W_CONV0][4 * c_m];
             p[0] = db4.x; p[1] = db4.y; p[2] = db4.z; p[3] = db4.w;
         }
-        asm volatile("bar.sync 2, %0;" ::"n"(NCV * 32) : "memory");
+        asm volatile("bar.sync 4, %0;" ::"n"(NCV * 32) : "memory");   // ids 1, 2: epilogue groups, 3: both groups
         if (ct < MP) {
             float sum = 0.f;
 #pragma unroll
@@ -774,7 +798,9 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
     } else {
         // ---------------------------------------------------------------- epilogue warps 0..3 (TMEM lane quadrant = w)
         constexpr int CHk = KP / 4, RPe = 128 / CHk, NPe = 128 / RPe;
-        const int c_k = t % CHk, r_k = t / CHk;
+        const int eg = w >> 2, wq = w & 3, tg = t & 127;   // epilogue group (tiles j = eg, eg + NEPI, ...), lane quadrant, thread in group
+        const int c_k = tg % CHk, r_k = tg / CHk;
+        const uint32_t sSt = sStage + eg * C::STAGE_BYTES, sAw = sAccW + eg * C::ACCW_BYTES;
         const bool colk_ok = 4 * c_k < a.K;
         const Bn4 bi = load_bn4(a.in_bn, a.K, c_k);
         const int in_act = a.in_act;
@@ -782,18 +808,18 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
         const uint32_t pitch = static_cast<uint32_t>(a.K) * 4u;
         float4 sp1 = zero4(), sp2 = zero4();
         TL_DECL;
-        for (int j = 0; j < my_tiles; ++j) {
+        for (int j = eg; j < my_tiles; j += C::NEPI) {
             const int ab = j & 1, ua = j >> 1, s = j % RING;
             const int64_t row0 = tile_row0(j);
             const int valid = static_cast<int>((a.N - row0) < 128 ? (a.N - row0) : 128);
             TL_WAIT(0, mbar_wait(acc_full(ab), ua & 1));
             tc_fence_after();
             [[maybe_unused]] const long long tl_p0 = clock64();
-            const uint32_t tacc = tmem + ab * C::ACC_COLS + (static_cast<uint32_t>(w * 32) << 16);
+            const uint32_t tacc = tmem + ab * C::ACC_COLS + (static_cast<uint32_t>(wq * 32) << 16);
             // ---- this tile's weight-gradient blocks += the CTA's shared-memory copy.  Accumulator row = lane: rows
             // [0, MP) are gY_hi^T [X'_hi | X'_lo], rows [MP, 2 MP) gY_lo^T [X'_hi | (X'_lo: 2^-22, dropped)]
-            if (w * 32 < 2 * MP) {
-                const bool lo_row = t >= MP;
+            if (wq * 32 < 2 * MP) {
+                const bool lo_row = tg >= MP;
 #pragma unroll
                 for (int cb = 0; cb < C::PK; ++cb) {
                     float v[32];
@@ -809,7 +835,7 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
                     }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const uint32_t slot = sAccW + static_cast<uint32_t>(((cb * 8 + q) * 2 * MP + t) * 16);
+                        const uint32_t slot = sAw + static_cast<uint32_t>(((cb * 8 + q) * 2 * MP + tg) * 16);
                         const float4 p = lds128s(slot);
                         sts128(slot, make_float4(p.x + v[4 * q], p.y + v[4 * q + 1], p.z + v[4 * q + 2], p.w + v[4 * q + 3]));
                     }
@@ -821,8 +847,8 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
                 if (lane == 0) { mbar_arrive(acc_empty(ab)); mbar_arrive(raw_empty(s)); }
                 continue;
             }
-            if (t == 0) bulk_wait_read0();
-            named_bar_sync<128>(1);
+            if (tg == 0) bulk_wait_read0();
+            named_bar_sync<128>(1 + eg);
 #pragma unroll
             for (int cb = 0; cb < C::PK; ++cb) {
                 float v[32];
@@ -837,19 +863,19 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
                 for (int p = 0; p < 8; ++p) {
                     const int chunk = cb * 8 + (p ^ (lane & 7));
                     if (4 * chunk < a.K)
-                        sts128(sStage + static_cast<uint32_t>(t) * pitch + chunk * 16, make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]));
+                        sts128(sSt + static_cast<uint32_t>(tg) * pitch + chunk * 16, make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]));
                 }
             }
             if (need_mask) {
                 // ---- activation mask of the previous stage + its BatchNorm-backward sums, in place on the staged tile
-                named_bar_sync<128>(1);
+                named_bar_sync<128>(1 + eg);
                 const uint32_t slab = sRaw + s * C::RAW_SLOT;
                 if (colk_ok) {
 #pragma unroll 4
                     for (int i = 0; i < NPe; ++i) {
                         const int r = r_k + RPe * i;
                         if (r < valid) {
-                            const uint32_t ga = sStage + static_cast<uint32_t>(r) * pitch + c_k * 16;
+                            const uint32_t ga = sSt + static_cast<uint32_t>(r) * pitch + c_k * 16;
                             float4 g = lds128s(ga);
                             const float4 x = lds128s(slab + static_cast<uint32_t>(r) * pitch + c_k * 16);
                             if (has_bn_in) {
@@ -873,16 +899,17 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(raw_empty(s));
-            named_bar_sync<128>(1);
+            named_bar_sync<128>(1 + eg);
 #ifdef DN4GL_PIPE_TL
             tl_w[1] += clock64() - tl_p0;
 #endif
-            if (t == 0) {
-                bulk_s2g(a.GX + row0 * a.K, sStage, static_cast<uint32_t>(valid) * pitch);
+            if (tg == 0) {
+                bulk_s2g(a.GX + row0 * a.K, sSt, static_cast<uint32_t>(valid) * pitch);
                 bulk_commit();
             }
         }
-        if (t == 0) { bulk_wait_all0(); TL_DONE(3); }
+        if (tg == 0) bulk_wait_all0();
+        if (t == 0) TL_DONE(3);
         // previous-stage sums: lanes sharing a chunk, then the 4 warps
         chunk_allreduce<CHk>(sp1);
         chunk_allreduce<CHk>(sp2);
@@ -891,14 +918,24 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
             p[0] = sp1.x; p[1] = sp1.y; p[2] = sp1.z; p[3] = sp1.w;
             p[KP] = sp2.x; p[KP + 1] = sp2.y; p[KP + 2] = sp2.z; p[KP + 3] = sp2.w;
         }
-        named_bar_sync<128>(1);
-        for (int i = t; i < 2 * KP; i += 128) part[MP * KP + MP + i] = (red_sp[0][i] + red_sp[1][i]) + (red_sp[2][i] + red_sp[3][i]);
-        // the CTA's weight gradient: dW[m][k] = (hi row m: hh + hl) + (lo row MP + m: lh), from the shared-memory copy
-        for (int e = t; e < MP * (KP / 4); e += 128) {
+        asm volatile("bar.sync 3, %0;" ::"n"(128 * C::NEPI) : "memory");
+        for (int i = t; i < 2 * KP; i += 128 * C::NEPI) {
+            float sum = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 4 * C::NEPI; ++ww) sum += red_sp[ww][i];
+            part[MP * KP + MP + i] = sum;
+        }
+        // the CTA's weight gradient: dW[m][k] = sum over the epilogue groups of (hi row m: hh + hl) + (lo row MP + m: lh)
+        for (int e = t; e < MP * (KP / 4); e += 128 * C::NEPI) {
             const int m = e % MP, q = e / MP;
-            const float4 hi = lds128s(sAccW + static_cast<uint32_t>((q * 2 * MP + m) * 16));
-            const float4 lo = lds128s(sAccW + static_cast<uint32_t>((q * 2 * MP + MP + m) * 16));
-            *reinterpret_cast<float4 *>(part + m * KP + 4 * q) = make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
+            float4 acc = zero4();
+#pragma unroll
+            for (int g = 0; g < C::NEPI; ++g) {
+                const float4 hi = lds128s(sAccW + g * C::ACCW_BYTES + static_cast<uint32_t>((q * 2 * MP + m) * 16));
+                const float4 lo = lds128s(sAccW + g * C::ACCW_BYTES + static_cast<uint32_t>((q * 2 * MP + MP + m) * 16));
+                acc.x += hi.x + lo.x; acc.y += hi.y + lo.y; acc.z += hi.z + lo.z; acc.w += hi.w + lo.w;
+            }
+            *reinterpret_cast<float4 *>(part + m * KP + 4 * q) = acc;
         }
     }
     // ---- teardown + two-level last-finisher merge of the per-CTA partials (additions in CTA-index order, double)
@@ -918,17 +955,25 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
     if (t == 0) __threadfence();
     __syncthreads();
     {
+        // level 1: this group's partials, CTA-index order, double accumulation; ALL loads of a thread are issued before the
+        // first add (one L2 round trip instead of one per element and pair of partials)
+        constexpr int EPT = (P + C::NT - 1) / C::NT;
         const float *pbase = reinterpret_cast<const float *>(a.part);
-        for (int e = t; e < P; e += C::NT) {
+        float v[EPT][BWD_GROUP];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int e = t + i * C::NT;
+#pragma unroll
+            for (int u = 0; u < BWD_GROUP; ++u)
+                v[i][u] = (e < P && g0 + u < g1) ? __ldcg(pbase + static_cast<size_t>(g0 + u) * P + e) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int e = t + i * C::NT;
             double acc = 0.0;
-            for (int c0 = g0; c0 < g1; c0 += 6) {
-                float v[6];
 #pragma unroll
-                for (int u = 0; u < 6; ++u) v[u] = (c0 + u < g1) ? __ldcg(pbase + static_cast<size_t>(c0 + u) * P + e) : 0.f;
-#pragma unroll
-                for (int u = 0; u < 6; ++u) acc += static_cast<double>(v[u]);
-            }
-            gpart[static_cast<size_t>(grp) * P + e] = acc;
+            for (int u = 0; u < BWD_GROUP; ++u) acc += static_cast<double>(v[i][u]);
+            if (e < P) gpart[static_cast<size_t>(grp) * P + e] = static_cast<float>(acc);
         }
     }
     __syncthreads();
@@ -941,44 +986,52 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
     if (!flag_s) { TL_SPAN(3); return; }
     if (t == 0) __threadfence();
     __syncthreads();
-    for (int e = t; e < P; e += C::NT) {
-        double acc = 0.0;
-        for (int q0 = 0; q0 < ngrp; q0 += 7) {
-            double v[7];
+    {
+        constexpr int EPT = (P + C::NT - 1) / C::NT, MAXG = 16;      // level 2: up to 16 groups (grid <= 192 CTAs)
+        float v[EPT][MAXG];
 #pragma unroll
-            for (int u = 0; u < 7; ++u) v[u] = (q0 + u < ngrp) ? __ldcg(gpart + static_cast<size_t>(q0 + u) * P + e) : 0.0;
+        for (int i = 0; i < EPT; ++i) {
+            const int e = t + i * C::NT;
 #pragma unroll
-            for (int u = 0; u < 7; ++u) acc += v[u];
+            for (int u = 0; u < MAXG; ++u) v[i][u] = (e < P && u < ngrp) ? __ldcg(gpart + static_cast<size_t>(u) * P + e) : 0.f;
         }
-        const float r = static_cast<float>(acc);
-        if (e < MP * KP) {
-            const int m = e / KP, k = e % KP;
-            if (dW != nullptr && m < a.M && k < a.K) dW[m * a.K + k] = r;
-        } else if (e < MP * KP + MP) {
-            const int m = e - MP * KP;
-            if (db != nullptr && m < a.M) db[m] = r;
-        } else {
-            const int i = e - MP * KP - MP, which = i / KP, k = i % KP;
-            if (sums_prev != nullptr && k < a.K) sums_prev[which * a.K + k] = r;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int e = t + i * C::NT;
+            if (e >= P) continue;
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < MAXG; ++u) acc += static_cast<double>(v[i][u]);
+            const float r = static_cast<float>(acc);
+            if (e < MP * KP) {
+                const int m = e / KP, kk = e % KP;
+                if (dW != nullptr && m < a.M && kk < a.K) dW[m * a.K + kk] = r;
+            } else if (e < MP * KP + MP) {
+                const int m = e - MP * KP;
+                if (db != nullptr && m < a.M) db[m] = r;
+            } else {
+                const int i2 = e - MP * KP - MP, which = i2 / KP, kk = i2 % KP;
+                if (sums_prev != nullptr && kk < a.K) sums_prev[which * a.K + kk] = r;
+            }
         }
     }
     if (t == 0) counters[1 + 16] = 0;
     TL_SPAN(3);
 }
 
-template <int KP, int MP, int RING, int NCV>
-int launch_bwd_pipe(const LinBwdArgs &a, float *dW, float *db, float *sums_prev, double *gpart, int *counters, cudaStream_t s) {
-    using C = BwdCfg<KP, MP, RING, NCV>;
+template <int KP, int MP, int RING, int NCV, int NEPI_>
+int launch_bwd_pipe(const LinBwdArgs &a, float *dW, float *db, float *sums_prev, float *gpart, int *counters, cudaStream_t s) {
+    using C = BwdCfg<KP, MP, RING, NCV, NEPI_>;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(lin_bwd_pipe_kernel<KP, MP, RING, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(lin_bwd_pipe_kernel<KP, MP, RING, NCV, NEPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(C::SMEM)) != cudaSuccess)
             return -1;
         attr_done = true;
     }
     const int sms = dn4gl_num_sms();
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    DN_LAUNCH((lin_bwd_pipe_kernel<KP, MP, RING, NCV>), grid, C::NT, C::SMEM, s, a, dW, db, sums_prev, gpart, counters);
+    DN_LAUNCH((lin_bwd_pipe_kernel<KP, MP, RING, NCV, NEPI_>), grid, C::NT, C::SMEM, s, a, dW, db, sums_prev, gpart, counters);
     return grid;
 }
 
@@ -1010,7 +1063,7 @@ size_t dn4gl_pipe_lin_bwd_ws_bytes(int K, int M) {
     const int KP = K <= 32 ? 32 : 64, MP = M <= 32 ? 32 : 64;
     const size_t P = static_cast<size_t>(bwd_pipe_part_floats(KP, MP));
     const size_t ctas = static_cast<size_t>(dn4gl_num_sms());
-    return align_up(ctas * P * sizeof(float), 256) + align_up(((ctas + BWD_GROUP - 1) / BWD_GROUP) * P * sizeof(double), 256);
+    return align_up(ctas * P * sizeof(float), 256) + align_up(((ctas + BWD_GROUP - 1) / BWD_GROUP) * P * sizeof(float), 256);
 }
 // -> CTAs launched (> 0), 0 if the shape has no pipelined instantiation, -1 on a CUDA error.  Preconditions (caller):
 // K % 4 == 0, M % 4 == 0, all matrices 16-byte aligned, counters zero on entry (left zero), ws >= the size above.
@@ -1020,6 +1073,8 @@ int dn4gl_pipe_lin_bwd(LinBwdArgs a, float *dW, float *db, float *sums_prev, voi
     if (KP == 64 || MP == 64) return 0;          // 64-wide shapes: operand tiles alone exceed one CTA's shared memory (mlp_tc.cu path)
     const size_t P = static_cast<size_t>(bwd_pipe_part_floats(KP, MP));
     a.part = static_cast<float *>(ws);
-    double *gpart = reinterpret_cast<double *>(static_cast<char *>(ws) + align_up(static_cast<size_t>(dn4gl_num_sms()) * P * sizeof(float), 256));
-    return launch_bwd_pipe<32, 32, 3, 8>(a, dW, db, sums_prev, gpart, counters, s);
+    float *gpart = reinterpret_cast<float *>(static_cast<char *>(ws) + align_up(static_cast<size_t>(dn4gl_num_sms()) * P * sizeof(float), 256));
+    static const int nepi = getenv("DN4GL_BWD_NEPI") ? atoi(getenv("DN4GL_BWD_NEPI")) : 1;     // experiment switch
+    if (nepi == 2) return launch_bwd_pipe<32, 32, 3, 8, 2>(a, dW, db, sums_prev, gpart, counters, s);
+    return launch_bwd_pipe<32, 32, 3, 8, 1>(a, dW, db, sums_prev, gpart, counters, s);
 }

@@ -8,7 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dummynode4graphlearning_b200 import ops, _lib
 
-ROLES = {"fwd": [("producer", ["raw_empty"]), ("mma", ["acc_empty", "a_full"]), ("convert", ["raw_full", "a_empty"]),
+ROLES = {"bwd": [("producer", ["raw_empty"]), ("mma", ["acc_empty", "a_full"]), ("convert", ["raw_full", "a_empty"]),
+                 ("epilogue", ["acc_full", "PHASE_work"])],
+         "fwd": [("producer", ["raw_empty"]), ("mma", ["acc_empty", "a_full"]), ("convert", ["raw_full", "a_empty"]),
                  ("epilogue", ["acc_full", "PHASE_tmem_to_staging", "PHASE_store"])]}
 
 
@@ -37,14 +39,22 @@ def main():
             W = torch.randn(D, D, device=dev) / D ** 0.5
             b = torch.randn(D, device=dev)
             bn = dict(gamma=torch.ones(D, device=dev), beta=torch.zeros(D, device=dev), eps=1e-5, momentum=0.1)
-            for op in ("fwd", "fwd_bn"):
+            G = torch.randn(N, D, device=dev)
+            Y, rec = ops.lin_fwd(X, W, b, bn=bn)
+            sums = ops.bn_bwd_sums(G, Y, rec)
+            for op in ("fwd", "fwd_bn", "bwd", "bwd_bn"):
                 for _ in range(3):
-                    ops.lin_fwd(X, W, b, bn=bn if op == "fwd_bn" else None)
+                    if op.startswith("fwd"):
+                        ops.lin_fwd(X, W, b, bn=bn if op == "fwd_bn" else None)
+                    elif op == "bwd":
+                        ops.lin_bwd(G, W, X)
+                    else:
+                        ops.lin_bwd(G, W, X, Yout=Y, bn=rec, sums=sums, in_bn=rec, in_act=1)
                 torch.cuda.synchronize()
                 tl = read()
                 ctas = min(148, (N + 127) // 128)
                 out = {"N": N, "D": D, "op": op, "tiles_per_cta": round((N + 127) // 128 / ctas, 2)}
-                for r, (name, waits) in enumerate(ROLES["fwd"]):
+                for r, (name, waits) in enumerate(ROLES["fwd" if op.startswith("fwd") else "bwd"]):
                     tot = tl[:ctas, r, 0]
                     out[name] = {"loop_cycles_mean": round(float(tot.mean())), "loop_cycles_max": round(float(tot.max()))}
                     for k, wn in enumerate(waits):
