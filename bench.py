@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--graphs", type=int, default=1113, help="graphs per GPU (C2: 1113)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the C2 line (skip the C1 / C3 / C4 / C5 measurements)")
     ap.add_argument("--size-hints", action="store_true",
                     help="EXPERIMENT (off by default): put transforms.tu_conjugate_sizes(raw) into the batches so that the "
                          "transform allocates its outputs without its device->host size read-back")
@@ -95,7 +96,23 @@ def cpu_transform(raw, pool, threads):
             np.concatenate([r[2] + off[i] for i, r in enumerate(res)]), np.concatenate([r[3] for r in res]))
 
 
-def cpu_reference_run(raw, steps, warmup):
+def cpu_transform_dummy(raw, pool, threads):
+    """C1: dummy augmentation + PyG canonicalisation on the host (same sharding as cpu_transform)."""
+    from oracle import transforms as OT
+
+    def one(c):
+        d = OT.tu_add_dummy(c)
+        s, dd, _, _ = OT.pyg_coalesce(d["src"], d["dst"])
+        return d["vlabel"], s, dd, np.diff(d["node_ptr"])
+
+    chunks = split_tu_batch(raw, threads)
+    res = list(pool.map(one, chunks)) if pool is not None and len(chunks) > 1 else [one(c) for c in chunks]
+    off = np.cumsum([0] + [int(r[3].sum()) for r in res])
+    return (np.concatenate([r[0] for r in res]), np.concatenate([r[1] + off[i] for i, r in enumerate(res)]),
+            np.concatenate([r[2] + off[i] for i, r in enumerate(res)]), np.concatenate([r[3] for r in res]))
+
+
+def cpu_reference_run(raw, steps, warmup, mode="conj", hid=HID, layers=LAYERS, num_labels=NUM_NODE_LABELS):
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import models as OM
@@ -103,12 +120,11 @@ def cpu_reference_run(raw, steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
     from dummynode4graphlearning_b200.graph_classification.models import GIN
     torch.manual_seed(0)
-    args = Namespace(num_features=NUM_NODE_LABELS, hidden_dim=HID, num_classes=CLASSES, dropout_ratio=0.0,
-                     additional={"train_eps": True, "num_layers": LAYERS, "aggregation": "sum"}, epochs=1, device="cpu")
+    args = Namespace(num_features=num_labels, hidden_dim=hid, num_classes=CLASSES, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": layers, "aggregation": "sum"}, epochs=1, device="cpu")
     sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "num_batches" not in k)
           for k, v in GIN(args).state_dict().items()}
     params = []
-    seen = set()
     for k, v in sd.items():   # nns.* / convs.*.nn.* alias: optimise each tensor once
         if v.requires_grad and not (k.startswith("convs.") and ".nn." in k):
             params.append(v)
@@ -118,15 +134,16 @@ def cpu_reference_run(raw, steps, warmup):
     t_tr, t_md = [], []
     threads = os.cpu_count() or 1
     pool = ThreadPoolExecutor(threads) if threads > 1 else None
+    tf = cpu_transform if mode == "conj" else cpu_transform_dummy
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        vlabel, s, d, nodes_per_graph = cpu_transform(raw, pool, threads)
-        x = torch.from_numpy(np.eye(NUM_NODE_LABELS, dtype=np.float32)[vlabel])
+        vlabel, s, d, nodes_per_graph = tf(raw, pool, threads)
+        x = torch.from_numpy(np.eye(num_labels, dtype=np.float32)[vlabel])
         ei = torch.from_numpy(np.stack([s, d]).astype(np.int64))
         batch = torch.from_numpy(np.repeat(np.arange(B), nodes_per_graph).astype(np.int64))
         t1 = time.perf_counter()
         opt.zero_grad()
-        out = OM.gin_classifier(sd, x, ei, batch, B, LAYERS, "sum")
+        out = OM.gin_classifier(sd, x, ei, batch, B, layers, "sum")
         loss = F.nll_loss(out, y)
         loss.backward()
         opt.step()
@@ -138,6 +155,131 @@ def cpu_reference_run(raw, steps, warmup):
     return dict(graphs_per_s=B * steps / total, ms_per_step=1e3 * total / steps,
                 transform_ms=1e3 * statistics.mean(t_tr), train_ms=1e3 * statistics.mean(t_md),
                 cores=torch.get_num_threads())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (C1, C3, C4): same metric (train graphs/s, full step), own CPU leg
+COUNTING = {"c3": ("RGIN", "small", 512, dict(rep_rgin_regularizer="bdd", rep_rgin_num_bases=4)),
+            "c4": ("DMPNN", "large", 64, dict(node_pred=True, edge_pred=False))}
+
+
+def counting_kwargs(shape, over):
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    cfg = dict(synth.counting_config(shape), add_dummy=True)
+    mc = T.process_model_config(cfg)
+    kw = dict({k: v for k, v in mc.items() if k.startswith("max_")}, hid_dim=64, rep_num_graph_layers=3,
+              rep_num_pattern_layers=3, rep_act_func="relu", pred_act_func="relu", pred_net="SumPredictNet",
+              pred_hid_dim=64, emb_net="Equivariant", enc_net="Multihot", filter_net="ScalarFilter", pred_with_enc=True,
+              pred_with_deg=True, init_neigenv=4.0, init_eeigenv=4.0)
+    kw.update(over)
+    return cfg, kw
+
+
+def build_counting_model(name, kw, device):
+    from dummynode4graphlearning_b200.subgraph_isomorphism.models import DMPNN, RGIN
+    torch.manual_seed(0)
+    model = {"RGIN": RGIN, "DMPNN": DMPNN}[name](**kw)
+    with torch.no_grad():      # pred_fc2 / weight_fc2 are zero-initialised in the reference (pred.py:50,53): outputs would be 0
+        for n, q in model.named_parameters():
+            if "pred_fc2" in n or "weight_fc2" in n:
+                q.normal_(0.0, 0.1)
+    return model.to(device)
+
+
+def gpu_counting_run(key, dev, world, rank, steps, warmup=8):
+    """C3 / C4: augmentation (dummy) + CSR builds + model forward + loss + backward (+ all-reduce) + clip + AdamW(amsgrad)
+    per step, inputs resident in HBM, device-timed, max over ranks."""
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.optim import FlatAdam
+    from dummynode4graphlearning_b200.parallel import max_over_ranks
+    from dummynode4graphlearning_b200.pipelines import CountingPipeline
+    name, shape, bs, over = COUNTING[key]
+    cfg, kw = counting_kwargs(shape, over)
+    model = build_counting_model(name, kw, dev)
+    opt = FlatAdam(model.parameters(), lr=1e-3, weight_decay=1e-2, amsgrad=True, decoupled_weight_decay=True)   # train.py:1408-1411
+    pipe = CountingPipeline(model, opt, cfg, add_dummy=True, rep_reg_w=1e-3)
+    pipe.global_batch = bs * world
+    p, g, counts = synth.counting_batch(shape, bs, seed=rank)
+    pd_, gd_ = T.to_device(p, dev), T.to_device(g, dev)
+    cd = torch.from_numpy(counts).to(dev)
+    for _ in range(warmup):
+        loss = pipe.step_resident(pd_, gd_, cd, assume_ready=True)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = pipe.step_resident(pd_, gd_, cd, assume_ready=True)
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    out = {"workload": "%s: %s + dummy, synthetic '%s' shape, batch %d per GPU, hid 64, 3 layers, SumPredictNet; augmentation + "
+                       "CSR builds + forward + loss + backward + clip + AdamW(amsgrad) per step" % (key, name, shape, bs),
+           "metric": "train graphs/sec", "value": bs * world / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms, "steps": steps,
+           "n_gpus": world, "graphs_per_gpu": bs, "graph_nodes": int(g["node_ptr"][-1]), "graph_edges": int(g["edge_ptr"][-1]),
+           "loss": float(loss.item())}
+    pipe._graphs.clear()
+    return out, (p, g, counts, cfg, kw, name)
+
+
+def cpu_counting_run(p, g, counts, cfg, kw, name, steps=2, warmup=1):
+    """CPU leg of C3 / C4: oracle port (C augmentation + torch-CPU restatement of the reference's per-edge formulation)."""
+    from oracle import models as OM, transforms as OT
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = build_counting_model(name, kw, "cpu")
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "enc_net" not in k) for k, v in model.state_dict().items()}
+    params = [v for k, v in sd.items() if v.requires_grad and not k.startswith("p_")]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-2, amsgrad=True)
+    ocfg = OM.counting_cfg_from_kwargs(name, kw)
+    ts = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        pa = OT.sub_add_dummy(p, cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])
+        ga = OT.sub_add_dummy(g, cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"])
+        opt.zero_grad()
+        out = OM.counting_model(sd, pa, ga, ocfg)
+        loss = OM.counting_loss(out, torch.from_numpy(counts), rep_reg_w=1e-3)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 8.0)
+        opt.step()
+        if it >= warmup:
+            ts.append(time.perf_counter() - t0)
+    B = len(counts)
+    return {"value": B / statistics.mean(ts), "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "ms_per_step": 1e3 * statistics.mean(ts),
+            "sample": "full batch (%d samples), %d timed steps after %d warm-up: oracle/c augmentation + oracle/models.py "
+                      "(the reference's per-edge formulation on torch-CPU) + AdamW(amsgrad)" % (B, steps, warmup)}
+
+
+def gpu_classification_run(shape, graphs, mode, hid, layers, num_labels, dev, steps, warmup=30):
+    """C1-style classification step through ClassificationPipeline (inputs resident in HBM, device-timed)."""
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+    from dummynode4graphlearning_b200.optim import FlatAdam
+    from dummynode4graphlearning_b200.pipelines import ClassificationPipeline
+    raw = synth.tu_batch(shape, graphs, seed=0)
+    dev_batch = T.to_device({k: v for k, v in raw.items() if k != "vattr"}, dev)
+    torch.manual_seed(0)
+    args = Namespace(num_features=num_labels, hidden_dim=hid, num_classes=CLASSES, dropout_ratio=0.0,
+                     additional={"train_eps": True, "num_layers": layers, "aggregation": "sum"}, epochs=1, device=str(dev))
+    model = GIN(args).to(dev)
+    pipe = ClassificationPipeline(model, FlatAdam(model.parameters(), lr=LR), mode=mode, num_node_labels=num_labels, node_label_min=0)
+    for _ in range(warmup):
+        pipe.step_resident(dev_batch, assume_ready=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = pipe.step_resident(dev_batch, assume_ready=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    pipe._graphs.clear()
+    return {"metric": "train graphs/sec", "value": graphs / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms, "steps": steps,
+            "loss": float(loss.item())}, raw
 
 
 def reference_arm(a):
@@ -454,6 +596,24 @@ def ours(a):
         torch.cuda.synchronize()
         return 1e3 * b0.elapsed_time(b1) / launches      # us
 
+    def copy_back_to_back(n_rows, D, launches=64):
+        """the same measurement for a plain device copy of one (n_rows, D) matrix into another (read N D 4 + write N D 4
+        bytes = the two feature streams of the aggregation): what a kernel with no index work reaches AT THIS SIZE."""
+        per = 2 * 4 * D * n_rows
+        nbuf = max(3, -(-(320 << 20) // per))
+        xs = [torch.rand((n_rows, D), device=dev) for _ in range(nbuf)]
+        ys = [torch.empty((n_rows, D), device=dev) for _ in range(3)]
+        for i in range(3):
+            ys[i].copy_(xs[i])
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for i in range(launches):
+            ys[i % 3].copy_(xs[i % nbuf])
+        b1.record()
+        torch.cuda.synchronize()
+        return 1e3 * b0.elapsed_time(b1) / launches      # us
+
     # (a) one launch at a time behind an L2 flush (CUDA-event resolution ~2 us, includes the launch gap)
     xh = torch.rand((N, HID), device=dev)
     iso = []
@@ -493,6 +653,15 @@ def ours(a):
                 "cold_l2_single_launch_us": 1e3 * statistics.median(iso),
                 "gather_effective_gbs": (4 * HID * (E + N) + 4 * E + 4 * (N + 1)) / (b2b_us * 1e-6) / 1e9,
                 "traffic": traffic, "traffic_source": traffic_src}
+    try:   # size-bound reference: a plain copy of the same two matrices, same method
+        cus = copy_back_to_back(N, HID)
+        roofline["copy_same_size"] = {"avg_launch_us": cus, "gbs": 8 * HID * N / (cus * 1e-6) / 1e9,
+                                      "frac_of_peak": 8 * HID * N / (cus * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                                      "note": "torch copy_ of one (N, D) fp32 matrix into another, 64 launches back to back over "
+                                              "a pool larger than L2: what a kernel without index work reaches at this size"}
+        roofline["frac_of_copy_at_same_size"] = achieved / roofline["copy_same_size"]["gbs"]
+    except Exception as ex:   # noqa: BLE001
+        roofline["copy_same_size"] = {"error": str(ex)[:200]}
     # the same kernel at a C5 sweep point (BASELINE.json configs[4]): 16 384 MUTAG-shaped graphs + dummy, hidden 64
     roofline_c5 = None
     if rank == 0:
@@ -513,6 +682,34 @@ def ours(a):
             del g5, d5
         except Exception as ex:   # noqa: BLE001
             roofline_c5 = {"error": str(ex)[:200]}
+    # ---- C5 sweep (BASELINE.json configs[4]): batches of 1k-64k MUTAG-shaped graphs + dummy, hidden 64-512 ------------
+    c5_sweep = None
+    if rank == 0 and world == 1 and not a.no_extras:
+        c5_sweep = []
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from agg_sweep import replicate
+            from dummynode4graphlearning_b200.graph import BatchedGraph
+            base5 = synth.tu_batch("mutag", 1024, seed=0)
+            for B5, dims in ((1024, (64, 512)), (4096, (64, 128, 256)), (16384, (64, 128, 256)), (65536, (64, 128))):
+                raw5 = replicate(base5, B5 // 1024)
+                d5 = T.tu_add_dummy(T.to_device({k: v for k, v in raw5.items() if k != "vattr"}, dev))
+                g5 = BatchedGraph(d5["src"], d5["dst"], d5["node_ptr"], d5["edge_ptr"])
+                g5.host_ptrs()
+                N5, E5 = g5.number_of_nodes(), g5.number_of_edges()
+                for D5 in dims:
+                    us5 = k1_back_to_back(g5.csr_in, g5.csr_out, N5, D5, launches=24)
+                    cu5 = copy_back_to_back(N5, D5, launches=24)
+                    b5 = 4 * D5 * N5 * 2 + 4 * E5 + 4 * (N5 + 1)
+                    c5_sweep.append({"graphs": B5, "D": D5, "N": N5, "E": E5, "algorithmic_bytes": b5, "avg_launch_us": round(us5, 2),
+                                     "gbs": round(b5 / (us5 * 1e-6) / 1e9, 1), "frac": round(b5 / (us5 * 1e-6) / 1e9 / peaks["hbm_gbs"], 3),
+                                     "frac_of_nominal_8tbs": round(b5 / (us5 * 1e-6) / 1e9 / 8000.0, 3),
+                                     "graphs_per_s": round(B5 / (us5 * 1e-6)),
+                                     "copy_same_size_us": round(cu5, 2), "copy_frac": round(8 * D5 * N5 / (cu5 * 1e-6) / 1e9 / peaks["hbm_gbs"], 3)})
+                del g5, d5
+                torch.cuda.empty_cache()
+        except Exception as ex:   # noqa: BLE001
+            c5_sweep.append({"error": str(ex)[:200]})
     # the tensor-core MLP stages of the same step (HBM-bound too): algorithmic GB/s from the
     # eager in-step event pairs (upper bound on the duration)
     mlp = {}
@@ -521,6 +718,39 @@ def ours(a):
             mlp[name] = {"in_step_eager_us": round(per_entry[name]["avg_us"], 2), "algorithmic_bytes": nbytes,
                          "gbs": round(nbytes / (per_entry[name]["avg_us"] * 1e-6) / 1e9, 1)}
 
+    # ---- the other BASELINE configurations -------------------------------------------------------------------------
+    configs = {}
+    if not a.no_extras:
+        pipe._graphs.clear()                      # free the C2 graphs' static buffers before the other pipelines capture theirs
+        torch.cuda.empty_cache()
+        want_cpu = world == 1 and not a.no_cpu_baseline
+        try:   # C4 (DMPNN 'large', per-GPU batch 64) runs data-parallel on every rank: the 8-GPU configuration of BASELINE.json
+            r4, ctx4 = gpu_counting_run("c4", dev, world, rank, steps=20)
+            if want_cpu and rank == 0:
+                r4["cpu_baseline"] = cpu_counting_run(*ctx4, steps=2, warmup=1)
+            configs["c4_dmpnn_large"] = r4
+        except Exception as ex:   # noqa: BLE001
+            configs["c4_dmpnn_large"] = {"error": str(ex)[:300]}
+        if world == 1:
+            try:
+                r3, ctx3 = gpu_counting_run("c3", dev, 1, 0, steps=20)
+                if want_cpu:
+                    r3["cpu_baseline"] = cpu_counting_run(*ctx3, steps=2, warmup=1)
+                configs["c3_rgin_small"] = r3
+            except Exception as ex:   # noqa: BLE001
+                configs["c3_rgin_small"] = {"error": str(ex)[:300]}
+            for key, hid1, lay1, note in (("c1_gin_mutag_hid128", 128, 2, "main.py:174 defaults (hidden 128, 2 layers)"),
+                                          ("c1_gin_mutag_hid32", 32, 4, "hyper_params.py:15 (hidden 32, 4 layers)")):
+                try:
+                    r1, raw1 = gpu_classification_run("mutag", 188, "dummy", hid1, lay1, 8, dev, steps=50)
+                    r1["workload"] = "c1: dummy augmentation + GIN(%s) train step, 188 MUTAG-shaped graphs" % note
+                    if want_cpu:
+                        c1 = cpu_reference_run(raw1, 10, 2, mode="dummy", hid=hid1, layers=lay1, num_labels=8)
+                        r1["cpu_baseline"] = {"value": c1["graphs_per_s"], "unit": "graphs/s", "cores": c1["cores"], "kind": "port",
+                                              "ms_per_step": c1["ms_per_step"], "sample": "full batch (188 graphs) per step, 10 timed steps"}
+                    configs[key] = r1
+                except Exception as ex:   # noqa: BLE001
+                    configs[key] = {"error": str(ex)[:300]}
     if rank != 0:
         _finish(pipe, world)
         return
@@ -542,7 +772,8 @@ def ours(a):
                 "h2d_bytes_per_step": host_bytes(host), "d2h_bytes_per_step": 4 + 8 + 4,
                 "how": "ClassificationPipeline.step_async(host) per step, loss of step k-1 read on the host after step k "
                        "is submitted (all losses read, last one before the clock stops)"},
-        "roofline": roofline, "roofline_c5": roofline_c5, "mlp_stages": mlp, "transform": transform_only, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_c5": roofline_c5, "c5_sweep": c5_sweep, "configs": configs, "mlp_stages": mlp,
+        "transform": transform_only, "cpu_baseline": cpu,
         "breakdown": {"how": "instrumented pass AFTER the timed regions: eager launches on one stream with a CUDA-event pair "
                              "around every C-ABI call (medians over %d steps); slower than the measured step by "
                              "construction -- use it for shares, not for totals" % len(tr_ms),

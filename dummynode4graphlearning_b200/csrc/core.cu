@@ -365,7 +365,17 @@ __global__ void __launch_bounds__(256) sort_rows_heavy(const int32_t *__restrict
         int beg = row_ptr[r], d = row_ptr[r + 1] - beg;
         if (d <= lo) continue;
         if (d > cap) {
-            if (cap >= DN4GL_MAX_ROW_DEGREE && err_flag && threadIdx.x == 0) atomicExch(err_flag, DN4GL_ELIMIT);
+            if (cap >= DN4GL_MAX_ROW_DEGREE) {
+                // above the documented limit: the row is reported through err_flag and left UNSORTED, but `col` still gets
+                // valid indices (the scatter's order), so that an aggregation launched before the flag is read gathers
+                // real rows in a wrong order instead of reading uninitialised memory
+                if (err_flag && threadIdx.x == 0) atomicExch(err_flag, DN4GL_ELIMIT);
+                if (col)
+                    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+                        const int it = items[beg + i];
+                        col[beg + i] = val ? val[it] : it;
+                    }
+            }
             continue;
         }
         const int dpad = (d + 3) & ~3;

@@ -304,14 +304,22 @@ __global__ void conj_fill_kernel(const int32_t *__restrict__ src, const int32_t 
                                  const int32_t *__restrict__ in_ptr, const int32_t *__restrict__ in_eid,
                                  const int32_t *__restrict__ cand_off, const int32_t *__restrict__ newid, ConjWs c,
                                  int32_t *__restrict__ o_src, int32_t *__restrict__ o_dst,
-                                 int32_t *__restrict__ o_v_origin, int32_t *__restrict__ o_e_shared) {
+                                 int32_t *__restrict__ o_v_origin, int32_t *__restrict__ o_e_shared,
+                                 int64_t cap_v, int64_t cap_e, int32_t *__restrict__ err_flag) {
     int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (e >= E) return;
     bool d = isd && isd[e];
     // conjugate vertex <- original edge (survivors only; kept[] is the scan, so compare neighbours)
-    if (c.kept[e + 1] != c.kept[e]) o_v_origin[c.kept[e]] = static_cast<int32_t>(e);
+    if (c.kept[e + 1] != c.kept[e]) {
+        if (c.kept[e] < cap_v) o_v_origin[c.kept[e]] = static_cast<int32_t>(e);
+        else if (err_flag) atomicExch(err_flag, DN4GL_ECAPACITY);
+    }
     int pos = cand_off[e];
     if (cand_off[e + 1] == pos) return;
+    if (cand_off[e + 1] > cap_e) {          // the caller's buffers (sized from a host-side hint) are too small: write nothing
+        if (err_flag) atomicExch(err_flag, DN4GL_ECAPACITY);
+        return;
+    }
     int s = src[e];
     int me = newid[e];
     int fd_in = c.fd_in[s];
@@ -333,10 +341,10 @@ extern "C" int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const
                                        int64_t E, const int32_t *in_ptr, const int32_t *in_eid,
                                        const int32_t *cand_off, const int32_t *newid, const int32_t *o_node_ptr,
                                        const int32_t *o_edge_ptr, int32_t *o_src, int32_t *o_dst,
-                                       int32_t *o_v_origin, int32_t *o_e_shared, void *ws, size_t ws_bytes,
-                                       void *stream) {
+                                       int32_t *o_v_origin, int32_t *o_e_shared, int64_t cap_v, int64_t cap_e,
+                                       int32_t *err_flag, void *ws, size_t ws_bytes, void *stream) {
     (void)node_ptr; (void)edge_ptr; (void)dst; (void)o_node_ptr; (void)o_edge_ptr;
-    DN_ARG(B >= 0 && N >= 0 && E >= 0);
+    DN_ARG(B >= 0 && N >= 0 && E >= 0 && cap_v >= 0 && cap_e >= 0);
     if (E == 0) return DN4GL_OK;
     DN_ARG(src && in_ptr && in_eid && cand_off && newid && o_v_origin);
     ConjWs c;
@@ -345,7 +353,7 @@ extern "C" int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const
         return DN4GL_EWORKSPACE;
     }
     conj_fill_kernel<<<static_cast<unsigned>(ceil_div64(E, 128)), 128, 0, as_stream(stream)>>>(
-        src, e_isdummy, E, in_ptr, in_eid, cand_off, newid, c, o_src, o_dst, o_v_origin, o_e_shared);
+        src, e_isdummy, E, in_ptr, in_eid, cand_off, newid, c, o_src, o_dst, o_v_origin, o_e_shared, cap_v, cap_e, err_flag);
     DN_LAUNCHED();
     return DN4GL_OK;
 }

@@ -173,6 +173,19 @@ def check_errors():
                                "the sizes the device counted)" % (code, idx))
 
 
+def cached_for_tensor(cache, name, tensor, extra, make):
+    """value derived from `tensor` (e.g. a CSR compiled from an edge list), cached in the dict `cache` under `name`.
+    The entry is valid only for the SAME tensor object at the SAME version with the same `extra`; it holds a reference
+    to the tensor, so neither its id nor its storage address can be handed to another batch while the entry lives
+    (a key built from data_ptr() silently matched a later batch that the caching allocator placed at the same address)."""
+    ent = cache.get(name)
+    if ent is not None and ent[0] is tensor and ent[1] == tensor._version and ent[2] == extra:
+        return ent[3]
+    value = make()
+    cache[name] = (tensor, tensor._version, extra, value)
+    return value
+
+
 def _i32(t, device):
     return torch.as_tensor(t).to(device=device, dtype=torch.int32).contiguous()
 

@@ -43,17 +43,18 @@ class GraphStructure:
 
     def relation_csr(self, edge_type, num_rels):
         """CSR pair addressing the (N*R, D) per-relation table (see subgraph_isomorphism/models/rgin.py)."""
-        key = (edge_type.data_ptr(), int(num_rels))
-        if key not in self._rel:
-            from ..graph import CSR
+        from ..graph import CSR, cached_for_tensor
+
+        def make():
             base = self.csr_in
             et = edge_type.long()
             col = (base.col.long() * num_rels + et[base.eid.long()]).to(torch.int32)
             fwd = CSR(base.row_ptr, col, base.eid, base.n_rows, base.nnz)
             fwd.heavy_rows, fwd.heavy_count, fwd.heavy_thr = base.heavy_rows, base.heavy_count, base.heavy_thr
             bwd = build_csr((self.src.long() * num_rels + et).to(torch.int32), self.dst, self.num_nodes * num_rels)
-            self._rel[key] = (fwd, bwd)
-        return self._rel[key]
+            return fwd, bwd
+
+        return cached_for_tensor(self._rel, ("rel_csr", int(num_rels)), edge_type, int(num_rels), make)
 
 
 class Batch:

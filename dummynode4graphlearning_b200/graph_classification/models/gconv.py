@@ -32,12 +32,9 @@ class GINConv(nn.Module):
         self._cache = {}
 
     def _structure(self, x, edge_index):
+        from ...graph import cached_for_tensor
         from ..data import GraphStructure
-        key = (edge_index.data_ptr(), edge_index.size(1), x.size(0))
-        if key not in self._cache:
-            self._cache.clear()
-            self._cache[key] = GraphStructure(edge_index, x.size(0))
-        return self._cache[key]
+        return cached_for_tensor(self._cache, "structure", edge_index, x.size(0), lambda: GraphStructure(edge_index, x.size(0)))
 
     def forward(self, x, edge_index, structure=None):
         s = structure if structure is not None else self._structure(x, edge_index)

@@ -102,20 +102,34 @@ class PendingLoss:
     """loss of a step that is still in flight: the device->host copy has been queued behind the step on its stream;
     ``result()`` waits for that copy only (not for later work) and returns the python float."""
 
-    _ring = {}
+    _free = {}      # device index -> pinned (loss, error code) buffers that no unresolved PendingLoss owns
 
     def __init__(self, loss):
-        dev = loss.device.index
-        ring = PendingLoss._ring.setdefault(dev, {"bufs": [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(8)], "i": 0})
-        self.buf = ring["bufs"][ring["i"] % 8]
-        ring["i"] += 1
+        from .graph import error_flag
+        self.dev = loss.device.index
+        pool = PendingLoss._free.setdefault(self.dev, [])
+        # one private pinned pair per unresolved result (handed back by result()): any number of steps may be in flight
+        self.buf, self.err = pool.pop() if pool else (torch.empty(1, dtype=torch.float32).pin_memory(),
+                                                     torch.empty(1, dtype=torch.int32).pin_memory())
         self.buf.copy_(loss.detach().reshape(1), non_blocking=True)
+        # the builder kernels' sticky asynchronous error flag travels with the loss: result() raises instead of returning
+        # a number computed from a malformed CSR (row above DN4GL_MAX_ROW_DEGREE, unsorted keys, wrong size hint)
+        self.flag = error_flag(loss.device)
+        self.err.copy_(self.flag, non_blocking=True)
         self.event = torch.cuda.Event()
         self.event.record()
+        self.value = None
 
     def result(self):
-        self.event.synchronize()
-        return float(self.buf[0])
+        if self.value is None:
+            self.event.synchronize()
+            self.value, code = float(self.buf[0]), int(self.err[0])
+            PendingLoss._free[self.dev].append((self.buf, self.err))
+            self.buf = self.err = None
+            if code != 0:
+                from .graph import check_errors
+                check_errors()          # reads, clears and raises with the code table
+        return self.value
 
 
 class _CapturedStep:
@@ -369,7 +383,7 @@ class _CapturedCountingStep:
 class CountingPipeline:
     def __init__(self, model, optimizer, config, add_dummy=True, rep_reg_w=0.0, neg_slp=0.01, max_grad_norm=8.0,
                  cuda_graphs=None, max_graphs=8, overlap=None, exact_sharding=False, bp_loss="MSE", match_loss_w=0.0,
-                 match_reg_w=0.0, remove_loops=False, add_rev=False, convert_conj=False):
+                 match_reg_w=0.0, remove_loops=False, add_rev=False, convert_conj=False, share_emb_net=True):
         """config: the dataset maxima BEFORE augmentation (max_npv ... max_ngel).  cuda_graphs / overlap: as in
         ClassificationPipeline (defaults: graphs on exactly when the optimizer was built with capturable=True, the
         augmentation + CSR builds on a second stream exactly when graphs are on).  exact_sharding: under
@@ -383,9 +397,16 @@ class CountingPipeline:
         (train.py:1271-1340: loops, reversed edges, dummy, edge-to-vertex), each with the maxima the previous steps
         leave behind; build the model with ``transforms.process_model_config`` of the same switches."""
         self.model, self.opt, self.cfg, self.add_dummy = model, optimizer, config, add_dummy
-        self.rep_reg_w, self.neg_slp, self.max_grad_norm = rep_reg_w, neg_slp, max_grad_norm
-        self.bucket = getattr(optimizer, "bucket", None) or GradientBucket(model.parameters())
         self.device = next(model.parameters()).device
+        # neg_slp and rep_reg_w change every step in the reference (train.py:648-740 recomputes them from their
+        # schedules): they live in device scalars that the (possibly captured) train step READS, so an update through the
+        # properties below is seen by the next step / CUDA-graph replay
+        self._neg_slp_t = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._rep_reg_w_t = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._neg_slp = self._rep_reg_w = None
+        self.neg_slp, self.rep_reg_w, self.max_grad_norm = neg_slp, rep_reg_w, max_grad_norm
+        self.share_emb_net = bool(share_emb_net)
+        self.bucket = getattr(optimizer, "bucket", None) or GradientBucket(model.parameters())
         self.global_batch = None
         capturable = all(g.get("capturable", False) for g in optimizer.param_groups)
         self.cuda_graphs = capturable if cuda_graphs is None else bool(cuda_graphs)
@@ -402,18 +423,41 @@ class CountingPipeline:
     _throttle = ClassificationPipeline._throttle
     _mark_step = ClassificationPipeline._mark_step
 
+    @property
+    def neg_slp(self):
+        return self._neg_slp
+
+    @neg_slp.setter
+    def neg_slp(self, v):
+        if v != self._neg_slp:
+            self._neg_slp = float(v)
+            self._neg_slp_t.fill_(self._neg_slp)
+
+    @property
+    def rep_reg_w(self):
+        return self._rep_reg_w
+
+    @rep_reg_w.setter
+    def rep_reg_w(self, v):
+        if v != self._rep_reg_w:
+            self._rep_reg_w = float(v)
+            self._rep_reg_w_t.fill_(self._rep_reg_w)
+
     def augment(self, p_dev, g_dev):
         """flat device batches -> flat device batches after the configured preprocessing switches (no CSR yet)."""
         c = self.cfg
-        npe, npel, nge, ngel = c["max_npe"], c["max_npel"], c["max_nge"], c["max_ngel"]
+        npv, npvl, npe, npel = c["max_npv"], c["max_npvl"], c["max_npe"], c["max_npel"]
+        ngv, ngvl, nge, ngel = c["max_ngv"], c["max_ngvl"], c["max_nge"], c["max_ngel"]
+        if self.share_emb_net:      # train.py:1276-1289: pattern and graph share the embedding tables, so the pattern side is
+            npv, npvl, npe, npel = ngv, ngvl, nge, ngel      # augmented with the GRAPH maxima (same dummy / reversed ids and labels)
         if self.remove_loops:                                   # train.py:1271-1274
             p_dev, g_dev = T.sub_remove_loops(p_dev), T.sub_remove_loops(g_dev)
         if self.add_rev:                                        # train.py:1310-1319: maxima double afterwards
             p_dev, g_dev = T.sub_add_reversed(p_dev, npe, npel), T.sub_add_reversed(g_dev, nge, ngel)
             npe, npel, nge, ngel = 2 * npe, 2 * npel, 2 * nge, 2 * ngel
         if self.add_dummy:                                      # train.py:1322-1334
-            p_dev = T.sub_add_dummy(p_dev, c["max_npv"], c["max_npvl"], npe, npel)
-            g_dev = T.sub_add_dummy(g_dev, c["max_ngv"], c["max_ngvl"], nge, ngel)
+            p_dev = T.sub_add_dummy(p_dev, npv, npvl, npe, npel)
+            g_dev = T.sub_add_dummy(g_dev, ngv, ngvl, nge, ngel)
         if self.convert_conj:                                   # train.py:1337-1340 -> convert_to_conjugate :564-593
             p_dev, g_dev = T.sub_conjugate(p_dev), T.sub_conjugate(g_dev)
         return p_dev, g_dev
@@ -432,12 +476,18 @@ class CountingPipeline:
         return pattern, graph
 
     def loss_fn(self, out, counts):
-        crit = lambda pred, target, slp: F.mse_loss(F.leaky_relu(pred, slp), target)   # train.py:624-625
-        loss = crit(out["pred_c"], counts.float().view(-1, 1), self.neg_slp)
-        if self.rep_reg_w:
-            for k in ("p_v_rep", "p_e_rep", "g_v_rep", "g_e_rep"):                      # train.py:801-811
+        """train.py:620-627 + :801-811 with the configured criterion; the negative slope and the regulariser weight are
+        read from device scalars (leaky_relu(x, s) = where(x > 0, x, x * s): same values as F.leaky_relu)."""
+        from .subgraph_isomorphism.losses import _CRITERIA
+        if self.bp_loss not in _CRITERIA:
+            raise NotImplementedError(self.bp_loss)
+        fn = _CRITERIA[self.bp_loss]
+        pred = out["pred_c"]
+        loss = fn(torch.where(pred > 0, pred, pred * self._neg_slp_t), counts.float().view(-1, 1))
+        if self._rep_reg_w != 0.0 or self.cuda_graphs:      # a captured step keeps the term: the weight may change later
+            for k in ("p_v_rep", "p_e_rep", "g_v_rep", "g_e_rep"):                      # train.py:801-811 (slope 1: identity)
                 if out[k] is not None:
-                    loss = loss + self.rep_reg_w * crit(out[k], torch.zeros_like(out[k]), 1) * out[k].size(1)
+                    loss = loss + self._rep_reg_w_t * fn(out[k], torch.zeros_like(out[k])) * out[k].size(1)
         return loss
 
     def match_loss_fn(self, out, counts, graph, node_weights, edge_weights):
@@ -519,4 +569,4 @@ class CountingPipeline:
     def step(self, p_host, g_host, counts_host):
         p_dev, g_dev = upload(p_host, self.device), upload(g_host, self.device)
         counts = counts_host.to(self.device, non_blocking=True)
-        return float(self.step_resident(p_dev, g_dev, counts).item())
+        return PendingLoss(self.step_resident(p_dev, g_dev, counts)).result()    # also raises on a builder-kernel error

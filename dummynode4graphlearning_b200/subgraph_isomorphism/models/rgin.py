@@ -22,7 +22,6 @@ from .basemodel import GraphAdjModel
 
 def relation_csr(g, edge_type, num_rels):
     """forward / transposed CSR pair whose columns address the (N*R, D) per-relation table."""
-    key = ("rel_csr", edge_type.data_ptr(), int(num_rels))
 
     def make():
         base = g.csr_in
@@ -34,7 +33,8 @@ def relation_csr(g, edge_type, num_rels):
         bwd = build_csr(tkey, g.dst, g.number_of_nodes() * num_rels)
         return fwd, bwd
 
-    return g.cached(key, make)
+    from ...graph import cached_for_tensor
+    return cached_for_tensor(g._cache, ("rel_csr", int(num_rels)), edge_type, int(num_rels), make)
 
 
 class RGINLayer(nn.Module):

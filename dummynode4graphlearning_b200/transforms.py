@@ -192,7 +192,7 @@ def tu_conjugate(b):
     L.call("dn4gl_tu_conjugate_fill", B, ptr(b["node_ptr"]), ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]),
            ptr(isd), N, E, ptr(csr_in.row_ptr), ptr(csr_in.eid), ptr(cand_off), ptr(newid),
            ptr(o_node_ptr), ptr(o_edge_ptr), ptr(o["src"]), ptr(o["dst"]), ptr(o["v_origin"]), ptr(o["e_shared"]),
-           ptr(ws), ws_bytes, _stream())
+           V2, E2, ptr(error_flag(dev)), ptr(ws), ws_bytes, _stream())
     vo, es = o["v_origin"], o["e_shared"]
     # vertex attributes <- original edge attributes (lines 238-242), edge attributes <- shared vertex (322-326);
     # derived lazily: a consumer that only needs the structure and the vertex labels pays for nothing else

@@ -34,6 +34,7 @@ extern "C" {
 #define DN4GL_ECUDA (-2)    /* a CUDA runtime call or launch failed                         */
 #define DN4GL_ELIMIT (-3)   /* a documented capacity limit was exceeded                     */
 #define DN4GL_EWORKSPACE (-4) /* workspace too small                                        */
+#define DN4GL_ECAPACITY (-5)  /* caller-sized output buffer too small / size hint mismatch (asynchronous flag) */
 
 #define DN4GL_ABI_VERSION 1
 
@@ -125,7 +126,10 @@ int dn4gl_sub_add_dummy(int32_t B, const int32_t *node_ptr, const int32_t *edge_
  *   _fill:  writes o_src/o_dst (global conjugate vertex ids), o_v_origin[V'] (original edge
  *           of each conjugate vertex) and o_e_shared[E'] (shared original vertex of each
  *           conjugate edge) in exactly the reference's order.
- * e_isdummy may be NULL (LINE_ graphs).  ws from dn4gl_conj_workspace_bytes.                 */
+ * e_isdummy may be NULL (LINE_ graphs).  ws from dn4gl_conj_workspace_bytes.
+ * cap_v / cap_e: rows the caller allocated for o_v_origin / o_src, o_dst, o_e_shared (normally the totals _count wrote;
+ * a caller that sized them from a host-side hint passes the hint): nothing is written beyond them, an overflow raises
+ * DN4GL_ECAPACITY through err_flag (may be NULL).                                                                  */
 size_t dn4gl_conj_workspace_bytes(int32_t B, int64_t N, int64_t E);
 int dn4gl_tu_conjugate_count(int32_t B, const int32_t *node_ptr, const int32_t *edge_ptr,
                              const int32_t *src, const int32_t *dst, const int32_t *e_isdummy,
@@ -141,6 +145,7 @@ int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const int32_t *e
                             const int32_t *cand_off, const int32_t *newid,
                             const int32_t *o_node_ptr, const int32_t *o_edge_ptr,
                             int32_t *o_src, int32_t *o_dst, int32_t *o_v_origin, int32_t *o_e_shared,
+                            int64_t cap_v, int64_t cap_e, int32_t *err_flag,
                             void *ws, size_t ws_bytes, void *stream);
 
 /* subgraph-isomorphism flavour, replaces convert_conjugate_graph, DGL branch (subgraph_isomorphism/utils/graph.py:

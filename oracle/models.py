@@ -431,3 +431,42 @@ def counting_loss(out, counts, rep_reg_w=0.0, neg_slp=0.01):
         if out.get(k) is not None:
             reg = reg + crit(out[k], th.zeros_like(out[k]), 1) * out[k].size(1)
     return loss + rep_reg_w * reg
+
+
+def counting_cfg_from_kwargs(name, kw):
+    """oracle.models.counting_model config equivalent to the constructor kwargs `kw`."""
+    shared = kw.get("share_rep_net", True)
+
+    pre = "rep_rgcn" if name == "RGCN" else "rep_rgin"
+
+    def nb(n_rel):
+        b = kw.get(pre + "_num_bases", -1)
+        reg = kw.get(pre + "_regularizer", "basis")
+        return n_rel if (reg == "none" or b is None or b > n_rel or b <= 0) else b
+
+    n_layers = kw.get("rep_num_graph_layers", 1)
+    if name == "RGIN":
+        lay = dict(num_rels=kw["max_ngel"], regularizer=kw.get("rep_rgin_regularizer", "basis"), num_bases=nb(kw["max_ngel"]),
+                   num_mlp_layers=kw.get("rep_rgin_num_mlp_layers", 2), act_func=kw.get("rep_act_func", "relu"),
+                   batch_norm=kw.get("rep_rgin_batch_norm", False))
+        layp = dict(lay) if shared else dict(lay, num_rels=kw["max_npel"], num_bases=nb(kw["max_npel"]))
+    elif name == "RGCN":
+        lay = dict(num_rels=kw["max_ngel"], regularizer=kw.get("rep_rgcn_regularizer", "basis"), num_bases=nb(kw["max_ngel"]),
+                   edge_norm=kw.get("rep_rgcn_edge_norm", "in"), act_func=kw.get("rep_act_func", "relu"),
+                   batch_norm=kw.get("rep_rgcn_batch_norm", False))
+        layp = dict(lay) if shared else dict(lay, num_rels=kw["max_npel"], num_bases=nb(kw["max_npel"]))
+    elif name == "CompGCN":
+        lay = dict(comp_opt=kw.get("rep_compgcn_comp_opt", "mult"), edge_norm=kw.get("rep_compgcn_edge_norm", "none"),
+                   act_func=kw.get("rep_act_func", "relu"), batch_norm=kw.get("rep_compgcn_batch_norm", False))
+        layp = dict(lay)
+    else:
+        lay = dict(num_mlp_layers=kw.get("rep_dmpnn_num_mlp_layers", 2), act_func=kw.get("rep_act_func", "relu"),
+                   batch_norm=kw.get("rep_dmpnn_batch_norm", False))
+        layp = dict(lay)
+    return dict(model=name, num_layers=n_layers, pred_act_func=kw.get("pred_act_func", "relu"),
+                pred_net=kw.get("pred_net", "SumPredictNet"), pred_with_enc=kw.get("pred_with_enc", False),
+                pred_with_deg=kw.get("pred_with_deg", False), return_weights=kw.get("pred_return_weights", "none"),
+                filter=kw.get("filter_net", "None") == "ScalarFilter", residual=kw.get("rep_residual", True),
+                add_node_id=kw.get("add_node_id", False), node_pred=kw.get("node_pred", True),
+                edge_pred=kw.get("edge_pred", True), rep_name={"g": "graph", "p": "graph" if shared else "pattern"},
+                layer={"g": lay, "p": layp})

@@ -75,7 +75,7 @@ def test_pipeline_step_with_match_weights(device):
         model = model.to(device)
         opt = torch.optim.SGD(model.parameters(), lr=0.0)
         return model, CountingPipeline(model, opt, cfg, rep_reg_w=1e-3, max_grad_norm=0.0, cuda_graphs=False,
-                                       match_loss_w=0.5, match_reg_w=0.25)
+                                       match_loss_w=0.5, match_reg_w=0.25, share_emb_net=False)   # goldens: per-side maxima
 
     model, pipe = fresh()
     pattern, graph = pipe.transform(T.to_device(p, device), T.to_device(g, device))

@@ -23,9 +23,13 @@ def _batch(seed, B=9):
     return p, g, counts
 
 
+@pytest.mark.parametrize("share_emb_net", [False, True])
 @pytest.mark.parametrize("flags", [(True, True, True, True), (False, True, True, False), (True, False, True, True),
                                    (False, True, False, True), (False, False, True, False)])
-def test_augment_chain_matches_oracle(device, flags):
+def test_augment_chain_matches_oracle(device, flags, share_emb_net):
+    """share_emb_net (the reference's default, train.py:1276-1289): the pattern side is augmented with the GRAPH maxima --
+    the 'small' config has different pattern / graph maxima (8 / 8 / 8 / 8 vs 64 / 256 / 16 / 16), so the pattern's dummy
+    and reversed ids / labels differ between the two settings."""
     from dummynode4graphlearning_b200 import synth, transforms as T
     from dummynode4graphlearning_b200.pipelines import CountingPipeline
     remove_loops, add_rev, add_dummy, convert_conj = flags
@@ -33,9 +37,11 @@ def test_augment_chain_matches_oracle(device, flags):
     cfg = synth.counting_config("small")
     lin = torch.nn.Linear(2, 2).to(device)            # augment() needs no model; the constructor wants parameters
     pipe = CountingPipeline(lin, torch.optim.SGD(lin.parameters(), lr=0.0), cfg, add_dummy=add_dummy, cuda_graphs=False,
-                            remove_loops=remove_loops, add_rev=add_rev, convert_conj=convert_conj)
+                            remove_loops=remove_loops, add_rev=add_rev, convert_conj=convert_conj, share_emb_net=share_emb_net)
     mp, mg = pipe.augment(T.to_device(p, device), T.to_device(g, device))
-    op, og = oracle_preprocess_chain(p, g, cfg, *flags)
+    ocfg = dict(cfg, max_npv=cfg["max_ngv"], max_npvl=cfg["max_ngvl"], max_npe=cfg["max_nge"], max_npel=cfg["max_ngel"]) \
+        if share_emb_net else cfg
+    op, og = oracle_preprocess_chain(p, g, ocfg, *flags)
     for mine, ref, side in ((mp, op, "pattern"), (mg, og, "graph")):
         for k in KEYS:
             if k in ref:

@@ -57,7 +57,7 @@ def test_sub_preprocessing_fuzz(device, seed):
     flags = tuple(bool(x) for x in rng.integers(0, 2, 4))
     lin = torch.nn.Linear(2, 2).to(device)
     pipe = CountingPipeline(lin, torch.optim.SGD(lin.parameters(), lr=0.0), NASTY_CFG, add_dummy=flags[2], cuda_graphs=False,
-                            remove_loops=flags[0], add_rev=flags[1], convert_conj=flags[3])
+                            remove_loops=flags[0], add_rev=flags[1], convert_conj=flags[3], share_emb_net=False)
     mp, mg = pipe.augment(T.to_device(p, device), T.to_device(g, device))
     op, og = oracle_preprocess_chain(p, g, NASTY_CFG, *flags)
     _same(mp, op, SUB, ("pattern", flags))
