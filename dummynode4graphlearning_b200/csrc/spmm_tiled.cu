@@ -27,16 +27,11 @@
 // bit-identical to the per-row kernel and to the sequential oracle.
 #include "common.cuh"
 
-// Tiling refinements measured in round 2 (profiles/r2a_k1_c2_*.jsonl, C2 structure, cold launch): whole-graph tiles
-// 24.6 -> 24.5 us alone, cost-balanced deal 24.6 -> 22.6 us, both 23.3 us; both on (fewer rows on the checked path AND an
-// even deal).  -DDN4GL_NO_TILE_WHOLE_GRAPHS / -DDN4GL_NO_TILE_BALANCE restore the round-1 tiling for A/B runs.
-#ifndef DN4GL_NO_TILE_WHOLE_GRAPHS
-#define DN4GL_TILE_WHOLE_GRAPHS 1
-#endif
-#ifndef DN4GL_NO_TILE_BALANCE
-#define DN4GL_TILE_BALANCE 1
-#endif
-
+// Tiling refinements measured in round 2 (profiles/r2a_k1_c2_*.jsonl, r2l_bench.json; C2 structure): whole-graph tiles
+// (-DDN4GL_TILE_WHOLE_GRAPHS) change nothing by themselves (24.5 vs 24.6 us cold); the cost-balanced deal
+// (-DDN4GL_TILE_BALANCE) brings the kernel from 21.5 to 18.8 us back to back, but its one-CTA sort + greedy assignment
+// costs ~300 us per tiling -- per mini-batch, twice -- so it only pays for a structure that is reused for many launches.
+// Both stay compiled out of the product build.
 constexpr int TP_NCW_MAX = 31;                // consumer warps: 15 (512 threads, <=128 registers) or 31 (1024 threads, 64)
 constexpr int TP_SPLIT = 64;                  // rows above this many neighbours are split (== graph.py HEAVY_THRESHOLD)
 constexpr int TP_MAX_STAGES = 4;

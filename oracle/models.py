@@ -33,8 +33,11 @@ def linear(sd, p, x):
     return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
 
 
-def batch_norm_train(sd, p, x):
-    """nn.BatchNorm1d in training mode: biased batch statistics over all rows."""
+def batch_norm_train(sd, p, x, training=True):
+    """nn.BatchNorm1d: training mode = biased batch statistics over all rows; eval mode = the running statistics."""
+    if not training:
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                            training=False, eps=1e-5)
     return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], training=True, eps=1e-5)
 
 
@@ -55,14 +58,15 @@ def mlp_seq(sd, p, x, num_layers, act, batch_norm=False):
 
 # ---------------------------------------------------------------------------------------------
 # classification (graph_classification/graph_neural_networks/models)
-def gin_mlp(sd, p, x):
+def gin_mlp(sd, p, x, training=True):
     """Sequential(Linear, BN, ReLU, Linear, BN, ReLU)   gconv.py:190-196"""
-    x = F.relu(batch_norm_train(sd, p + ".1", linear(sd, p + ".0", x)))
-    return F.relu(batch_norm_train(sd, p + ".4", linear(sd, p + ".3", x)))
+    x = F.relu(batch_norm_train(sd, p + ".1", linear(sd, p + ".0", x), training))
+    return F.relu(batch_norm_train(sd, p + ".4", linear(sd, p + ".3", x), training))
 
 
-def gin_classifier(sd, x, edge_index, batch, num_graphs, num_layers, aggregation="sum"):
-    """GIN.forward, gconv.py:203-215, dropout 0.  GINConv [ext PyG 2.0.2]: nn(scatter_sum(x[src], dst) + (1+eps) x)."""
+def gin_classifier(sd, x, edge_index, batch, num_graphs, num_layers, aggregation="sum", training=True):
+    """GIN.forward, gconv.py:203-215, dropout 0.  GINConv [ext PyG 2.0.2]: nn(scatter_sum(x[src], dst) + (1+eps) x).
+    training=False: model.eval() (BatchNorm uses its running statistics)."""
     src, dst = edge_index[0], edge_index[1]
     cnt = th.bincount(batch, minlength=num_graphs).clamp(min=1).float().view(-1, 1)
 
@@ -73,12 +77,12 @@ def gin_classifier(sd, x, edge_index, batch, num_graphs, num_layers, aggregation
     out = 0
     for layer in range(num_layers):
         if layer == 0:
-            x = gin_mlp(sd, "first_h", x)
+            x = gin_mlp(sd, "first_h", x, training)
             out = out + pool(linear(sd, "linears.0", x))
         else:
             agg = scatter_sum(x[src], dst, x.size(0))
             agg = agg + (1 + sd["convs.%d.eps" % (layer - 1)]) * x
-            x = gin_mlp(sd, "nns.%d" % (layer - 1), agg)
+            x = gin_mlp(sd, "nns.%d" % (layer - 1), agg, training)
             out = out + linear(sd, "linears.%d" % layer, pool(x))
     return F.log_softmax(out, dim=-1)
 

@@ -10,6 +10,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from conftest import record_error
 from helpers import assert_close_rel, load_golden, oracle_cfg, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -62,6 +63,8 @@ def test_counting_models_match_reference_golden(device, tag):
     out = model(pattern, graph)
     _check_outputs(out, g["outputs"])
     loss = _loss(out, torch.from_numpy(b["counts"]).to(device))
+    record_error("counting_golden[%s]" % tag, "loss", err=rel_err(loss, g["loss"]))
+    record_error("counting_golden[%s]" % tag, "pred_c", err=rel_err(out["pred_c"], g["outputs"]["pred_c"]))
     assert_close_rel(loss, g["loss"], TOL, "loss")
     loss.backward()
     grads = dict(model.named_parameters())
@@ -73,6 +76,7 @@ def test_counting_models_match_reference_golden(device, tag):
         if ref is None:
             assert grads[n].grad is None, n     # frozen tables / row_vec stay gradient-free
         else:
+            record_error("counting_golden[%s]" % tag, "grad " + n, err=rel_err(grads[n].grad, ref) if float(ref.abs().max()) > 1e-6 * gmax else 0.0)
             assert_close_rel(grads[n].grad, ref, TOL, "grad " + n, atol=1e-6 * gmax if n.endswith(".bias") else 0.0)
 
 
@@ -131,8 +135,11 @@ def test_counting_models_match_oracle_live(device, name, shape, bs, over):
     ref64_loss = OM.counting_loss(ref64, torch.from_numpy(counts), rep_reg_w=1e-3)
     ref64_loss.backward()
 
+    tname = "counting_live[%s-%s-%d]" % (name, shape, bs)
+
     def close(mine, r32, r64, what):
         e32 = rel_err(mine, r32)
+        record_error(tname, what, err=e32, err_vs_fp64=rel_err(mine, r64), fp32_oracle_vs_fp64=rel_err(r32, r64))
         if e32 <= TOL:
             return
         e_mine, e_ref = rel_err(mine, r64), rel_err(r32, r64)
@@ -170,9 +177,17 @@ def test_classifiers_match_reference_golden(device, tag):
     loss.backward()
     params = dict(model.named_parameters())
     assert set(params) == set(g["grads"])
+    # a bias in front of a BatchNorm has a mathematically zero gradient (only rounding noise on both sides): those are
+    # compared against an absolute floor tied to the LARGEST gradient of the model, everything else relatively at 1e-5
+    gmax = max(float(r.abs().max()) for r in g["grads"].values() if r is not None)
+    record_error("classifier_golden[%s]" % tag, "log_softmax", err=rel_err(out, g["out"]))
+    record_error("classifier_golden[%s]" % tag, "loss", err=rel_err(loss, g["loss"]))
     for n, ref in g["grads"].items():
         if ref is not None:
-            assert_close_rel(params[n].grad, ref, 2e-5, "grad " + n, atol=2e-5)   # BN: pre-BN biases have zero gradient
+            pre_bn_bias = float(ref.abs().max()) <= 1e-6 * gmax
+            if not pre_bn_bias:
+                record_error("classifier_golden[%s]" % tag, "grad " + n, err=rel_err(params[n].grad, ref))
+            assert_close_rel(params[n].grad, ref, TOL, "grad " + n, atol=1e-6 * gmax if pre_bn_bias else 0.0)
 
 
 def test_gin_full_size_c2_against_oracle(device):
@@ -226,3 +241,100 @@ def test_gin_full_size_c2_against_oracle(device):
         e_gpu = float((q.grad.double().cpu() - g64).abs().max())
         e_cpu = float((g32.double() - g64).abs().max())
         assert e_gpu <= 4 * e_cpu + 1e-5 * max(scale, 1e-3), (n, e_gpu, e_cpu, scale)
+
+
+def _full_size_classification(device, mode, hid, layers, train=True, dropout=0.0, seed=0, graphs=None):
+    """PROTEINS-shaped batch -> GPU transform -> (model on the GPU, canonical batch, oracle runner)."""
+    from dummynode4graphlearning_b200 import synth, transforms as T
+    from dummynode4graphlearning_b200.graph_classification.data import Batch
+    from dummynode4graphlearning_b200.graph_classification.models import GIN
+    from oracle import models as OM
+    raw = synth.tu_batch("proteins", graphs, seed=seed)
+    b = T.tu_add_dummy(T.to_device(raw, device))
+    if mode == "conj":
+        b = T.tu_conjugate(b)
+        b.pop("eattr", None)
+    b["has_edge_labels"] = True
+    can = T.pyg_canonicalize(b)
+    data = Batch.from_canonical(can)
+    args = Namespace(num_features=can["x"].size(1), hidden_dim=hid, num_classes=2, dropout_ratio=dropout,
+                     additional={"train_eps": True, "num_layers": layers, "aggregation": "sum"}, epochs=3, device=str(device))
+    torch.manual_seed(0)
+    model = GIN(args)
+    base = model.state_dict()
+
+    def oracle_run(dtype, training=True):
+        sd = {k: (v.clone().to(dtype).requires_grad_("running" not in k) if v.is_floating_point() else v.clone())
+              for k, v in base.items()}
+        ref = OM.gin_classifier(sd, can["x"].cpu().to(dtype), can["edge_index"].cpu(), can["batch"].cpu(),
+                                can["num_graphs"], layers, "sum", training=training)
+        loss = F.nll_loss(ref, can["y"].cpu())
+        if training:
+            loss.backward()
+        return ref.detach(), loss.detach(), sd
+
+    return model.to(device), data, can, oracle_run
+
+
+@pytest.mark.parametrize("hid,layers", [(32, 4), (128, 2)])
+def test_gin_full_size_dummy_proteins_meets_1e5(device, hid, layers):
+    """The full-size C2-sized batch on NON-degenerate inputs (DUMMY_PROTEINS features: scalar attribute + 3 labels + dummy
+    flag; the CONJ features of test_gin_full_size_c2_against_oracle are two one-hot rows): here no BatchNorm channel has
+    ~zero variance and the CUDA path is held to the north star's 1e-5 directly against the fp32 CPU oracle, for the
+    log-probabilities, the loss and every gradient.  hid 128 = main.py:174's default width (library-GEMM MLP branch)."""
+    model, data, can, oracle_run = _full_size_classification(device, "dummy", hid, layers)
+    r32, l32, sd32 = oracle_run(torch.float32)
+    r64, l64, sd64 = oracle_run(torch.float64)
+    model.train()
+    out = model(data)
+    loss = F.nll_loss(out, can["y"])
+    loss.backward()
+    tname = "gin_full_size_dummy_proteins[hid%d]" % hid
+    record_error(tname, "log_softmax", err=rel_err(out, r32), err_vs_fp64=rel_err(out, r64), fp32_oracle_vs_fp64=rel_err(r32, r64))
+    record_error(tname, "loss", err=rel_err(loss, l32), err_vs_fp64=rel_err(loss, l64), fp32_oracle_vs_fp64=rel_err(l32, l64))
+    assert_close_rel(out, r32, TOL, "log_softmax")
+    assert_close_rel(loss, l32, TOL, "loss")
+    gmax = max(float(v.grad.abs().max()) for v in sd32.values() if getattr(v, "grad", None) is not None)
+    for n, q in model.named_parameters():
+        key = n if sd32[n].grad is not None else n.replace("convs.", "nns.").replace(".nn.", ".")
+        ref, ref64 = sd32[key].grad, sd64[key].grad
+        pre_bn_bias = float(ref64.abs().max()) <= 1e-6 * gmax          # zero by construction: rounding noise on both sides
+        if not pre_bn_bias:
+            record_error(tname, "grad " + n, err=rel_err(q.grad, ref), err_vs_fp64=rel_err(q.grad, ref64),
+                         fp32_oracle_vs_fp64=rel_err(ref, ref64))
+        # fp32 sums over 1e5 rows: the CPU oracle itself sits up to a few 1e-6 from float64; the bar applies to the distance
+        # from the oracle OR, where the oracle's own rounding dominates, from the exact (float64) value
+        e32, e64, eref = rel_err(q.grad, ref), rel_err(q.grad, ref64), rel_err(ref, ref64)
+        if pre_bn_bias:
+            assert float((q.grad.cpu() - ref).abs().max()) <= 1e-6 * gmax, n
+        else:
+            assert e32 <= TOL or e64 <= max(TOL, 2 * eref), (n, e32, e64, eref)
+
+
+def test_gin_eval_mode_and_dropout_paths(device):
+    """eval mode (running statistics, no batch statistics: the unfused branch) against the oracle, and dropout > 0 in
+    training mode: same mask stream as torch's F.dropout on this device is not required by the reference -- the check is
+    that the fused-path switch is taken off and the result is finite, deterministic under a fixed seed and different from
+    the dropout-free result."""
+    model, data, can, oracle_run = _full_size_classification(device, "dummy", 32, 3, graphs=64, seed=3)
+    model.train()
+    for _ in range(2):                      # move the running statistics away from their initial values
+        model(data)
+    sd_after = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    model.eval()
+    with torch.no_grad():
+        out_eval = model(data)
+    from oracle import models as OM
+    ref = OM.gin_classifier(sd_after, can["x"].cpu(), can["edge_index"].cpu(), can["batch"].cpu(), can["num_graphs"], 3, "sum",
+                            training=False)
+    record_error("gin_eval_mode", "log_softmax", err=rel_err(out_eval, ref))
+    assert_close_rel(out_eval, ref, TOL, "eval-mode log_softmax")
+    model_d, data_d, _, _ = _full_size_classification(device, "dummy", 32, 3, dropout=0.5, graphs=64, seed=3)
+    model_d.train()
+    torch.manual_seed(7)
+    a = model_d(data_d)
+    torch.manual_seed(7)
+    b = model_d(data_d)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    model.train()
+    assert not torch.allclose(a, model(data), atol=1e-3)

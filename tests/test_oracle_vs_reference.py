@@ -552,3 +552,10 @@ def test_classification_models_fuzz_live(name, add, variant, seed):
         if got is None and n.startswith("convs.") and ".nn." in n:     # aliases of nns.* (gconv.py:195-197)
             got = sd[n.replace("convs.", "nns.").replace(".nn.", ".")].grad
         assert_close_rel(got, p_.grad, 2e-5, "grad " + n, atol=2e-5)
+    if name == "GIN":     # model.eval(): BatchNorm on the running statistics the training pass above has just updated
+        model.eval()
+        with torch.no_grad():
+            out_eval_ref = model(Namespace(x=x, edge_index=edge_index, edge_attr=edge_attr, batch=batch, y=y))
+        sd_eval = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        out_eval = OM.gin_classifier(sd_eval, x, edge_index, batch, B, nl, add["aggregation"], training=False)
+        assert_close_rel(out_eval, out_eval_ref, 1e-6, "eval-mode log_softmax")
