@@ -42,9 +42,9 @@ def parse():
     ap.add_argument("--graphs", type=int, default=1113, help="graphs per GPU (C2: 1113)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="only the C2 line (skip the C1 / C3 / C4 / C5 measurements)")
-    ap.add_argument("--size-hints", action="store_true",
-                    help="EXPERIMENT (off by default): put transforms.tu_conjugate_sizes(raw) into the batches so that the "
-                         "transform allocates its outputs without its device->host size read-back")
+    ap.add_argument("--no-size-hints", dest="size_hints", action="store_false",
+                    help="let the transform read its output sizes back from the device (one device->host sync per step) "
+                         "instead of taking transforms.tu_conjugate_sizes(raw) from the host batch")
     return ap.parse_args()
 
 
@@ -765,8 +765,9 @@ def ours(a):
         "metric": "train graphs/sec", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": a.steps,
         "warmup": n_warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(a.graphs, world), **({"size_hints": "experiment: transform output sizes computed on "
-                       "the host (tu_conjugate_sizes), no size read-back"} if a.size_hints else {})),
+        "config": dict(workload_config(a.graphs, world), **({"size_hints": "the loader attaches the closed-form output sizes of the edge-to-vertex transform "
+                       "(transforms.tu_conjugate_sizes of the raw host batch): no device->host read inside a step; a wrong "
+                       "hint raises DN4GL_ECAPACITY"} if a.size_hints else {})),
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": host_bytes(host), "d2h_bytes_per_step": 4 + 8 + 4,

@@ -620,12 +620,13 @@ def _act_code(m):
     return None
 
 
-# The counting models chain ~12 of these GEMMs per forward with sum-aggregations over up to 512-node graphs and no
-# normalisation in between: the tensor core's truncating fp32 accumulation is a BIASED error (towards zero) that adds up
-# coherently and reaches 2-4e-5 on the DMPNN "large" loss (fp32 FMA: 2e-6; measured), above the
-# 1e-5 parity bar.  The classification GIN is immune (BatchNorm after every Linear removes per-channel bias).  So the
-# tensor-core path of `Linear, act, Linear` is opt-in for the counting models: DN4GL_MLP2_TC=1.
-MLP2_TENSOR_CORES = os.environ.get("DN4GL_MLP2_TC", "0") == "1"
+# `Linear, act, Linear` of the counting models on the tensor cores.  Round 1 kept this opt-in: the truncating fp32
+# accumulation of the tensor core is a BIASED error that the counting models (12 such GEMMs per forward, 512-node sum
+# aggregations, no normalisation) add up coherently -- 2-4e-5 on the DMPNN "large" loss, above the 1e-5 bar.  Round 2's stage
+# kernels issue the A_lo products first and spread the A_hi k-steps over four accumulators added in round-to-nearest
+# (csrc/mlp_pipe.cu): 8.5e-6 on that loss, every other recorded quantity <= 5.4e-6 (profiles/r2n_parity_errors_mlp2tc.json),
+# so the tensor-core path is the default; DN4GL_MLP2_TC=0 restores the library GEMMs.
+MLP2_TENSOR_CORES = os.environ.get("DN4GL_MLP2_TC", "1") == "1"
 
 
 def mlp2_fusable(seq, force=False):

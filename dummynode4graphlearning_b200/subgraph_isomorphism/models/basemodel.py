@@ -205,8 +205,7 @@ class _CountingBase(nn.Module):
             feats += [enc["v"], enc["vl"]]
         if self.pred_with_deg:
             feats += [g.out_degrees().float().view(-1, 1), g.in_degrees().float().view(-1, 1)]
-        out = th.cat(feats + [rep], dim=-1) if feats else rep
-        return ops.pad_segments(out, g.node_ptr, g.padded_num_nodes(), drop)
+        return th.cat(feats + [rep], dim=-1) if feats else rep
 
     def _edge_readout(self, g, enc, rep, drop):
         u, v = g.all_edges(form="uv", order="eid")
@@ -215,8 +214,17 @@ class _CountingBase(nn.Module):
             feats += [enc["v"][u], enc["v"][v], enc["vl"][u], enc["el"], enc["vl"][v]]
         if self.pred_with_deg:
             feats += [g.out_degrees().float().view(-1, 1)[u], g.in_degrees().float().view(-1, 1)[v]]
-        out = th.cat(feats + [rep], dim=-1) if feats else rep
-        return ops.pad_segments(out, g.edge_ptr, g.padded_num_edges(), drop)
+        return th.cat(feats + [rep], dim=-1) if feats else rep
+
+    @staticmethod
+    def _head(net, kind, pattern, p_x, p_drop, p_mask, graph, g_x, g_drop, g_mask):
+        """one PredictNet on the flat readout rows: unpadded when the head supports it (pred.py docstring), else through the
+        reference's left-padded (B, L, rep) tensors."""
+        p_ptr, Lp = (pattern.node_ptr, pattern.padded_num_nodes()) if kind == "node" else (pattern.edge_ptr, pattern.padded_num_edges())
+        g_ptr, Lg = (graph.node_ptr, graph.padded_num_nodes()) if kind == "node" else (graph.edge_ptr, graph.padded_num_edges())
+        if net.supports_ragged() and p_x.is_cuda:
+            return net.forward_ragged(p_x, p_ptr, p_drop, p_mask, Lp, g_x, g_ptr, g_drop, g_mask, Lg)
+        return net(ops.pad_segments(p_x, p_ptr, Lp, p_drop), p_mask, ops.pad_segments(g_x, g_ptr, Lg, g_drop), g_mask)
 
 
 class GraphAdjModel(_CountingBase):
@@ -252,6 +260,7 @@ class GraphAdjModel(_CountingBase):
         return self._embed(self.g_emb_net, g_enc)
 
     def get_subiso_pred(self, p_v_rep, p_v_mask, g_v_rep, g_v_mask):
+        """the reference's signature: LEFT-PADDED (B, L, rep) tensors (basemodel.py:958-964)"""
         v_pred_c, v_pred_w = self.pred_net(p_v_rep, p_v_mask, g_v_rep, g_v_mask)
         return v_pred_c, (v_pred_w, None)
 
@@ -268,7 +277,8 @@ class GraphAdjModel(_CountingBase):
         g_v_mask, g_drop = _padded_mask(graph, "node")
         p_v_output = self._node_readout(pattern, p_enc, p_v_rep, p_drop)
         g_v_output = self._node_readout(graph, g_enc, g_v_rep, g_drop)
-        pred_c, (pred_v, pred_e) = self.get_subiso_pred(p_v_output, p_v_mask, g_v_output, g_v_mask)
+        pred_c, pred_v = self._head(self.pred_net, "node", pattern, p_v_output, p_drop, p_v_mask, graph, g_v_output, g_drop, g_v_mask)
+        pred_e = None
         return OutputDict(
             p_v_emb=p_v_emb, p_e_emb=None, g_v_emb=g_v_emb, g_e_emb=None,
             p_v_rep=p_v_rep, p_e_rep=None, g_v_rep=g_v_rep, g_e_rep=None,
@@ -322,22 +332,26 @@ class GraphAdjModelV2(_CountingBase):
     def get_graph_emb(self, g_enc):
         return self._embed(self.g_emb_net, g_enc)
 
+    def _mix(self, v_c, e_c, g_v_mask, g_e_mask):
+        if self.node_pred and self.edge_pred:   # length-weighted mix (basemodel.py:1506-1512)
+            g_v_len = g_v_mask.float().sum(dim=1).view(-1, 1)
+            g_e_len = g_e_mask.float().sum(dim=1).view(-1, 1)
+            g_len = g_v_len + g_e_len
+            return (g_v_len / g_len) * v_c + (g_e_len / g_len) * e_c
+        if self.node_pred:
+            return v_c
+        if self.edge_pred:
+            return e_c
+        raise ValueError
+
     def get_subiso_pred(self, p_v_rep, p_v_mask, p_e_rep, p_e_mask, g_v_rep, g_v_mask, g_e_rep, g_e_mask):
+        """the reference's signature: LEFT-PADDED (B, L, rep) tensors (basemodel.py:1497-1518)"""
         v_c = v_w = e_c = e_w = None
         if self.node_pred:
             v_c, v_w = self.pred_net["v"](p_v_rep, p_v_mask, g_v_rep, g_v_mask)
         if self.edge_pred:
             e_c, e_w = self.pred_net["e"](p_e_rep, p_e_mask, g_e_rep, g_e_mask)
-        if self.node_pred and self.edge_pred:   # length-weighted mix (basemodel.py:1506-1512)
-            g_v_len = g_v_mask.float().sum(dim=1).view(-1, 1)
-            g_e_len = g_e_mask.float().sum(dim=1).view(-1, 1)
-            g_len = g_v_len + g_e_len
-            return (g_v_len / g_len) * v_c + (g_e_len / g_len) * e_c, (v_w, e_w)
-        if self.node_pred:
-            return v_c, (v_w, e_w)
-        if self.edge_pred:
-            return e_c, (v_w, e_w)
-        raise ValueError
+        return self._mix(v_c, e_c, g_v_mask, g_e_mask), (v_w, e_w)
 
     def forward(self, pattern, graph):
         vl_gate, el_gate = self.get_filter_gate(pattern, graph)
@@ -353,15 +367,14 @@ class GraphAdjModelV2(_CountingBase):
         p_e_mask, p_e_drop = _padded_mask(pattern, "edge", reversed_=True)
         g_e_mask, g_e_drop = _padded_mask(graph, "edge", reversed_=True)
 
-        p_v_out = g_v_out = p_e_out = g_e_out = None
+        v_c = pred_v = e_c = pred_e = None
         if self.node_pred:
-            p_v_out = self._node_readout(pattern, p_enc, p_v_rep, p_v_drop)
-            g_v_out = self._node_readout(graph, g_enc, g_v_rep, g_v_drop)
+            v_c, pred_v = self._head(self.pred_net["v"], "node", pattern, self._node_readout(pattern, p_enc, p_v_rep, p_v_drop),
+                                     p_v_drop, p_v_mask, graph, self._node_readout(graph, g_enc, g_v_rep, g_v_drop), g_v_drop, g_v_mask)
         if self.edge_pred:
-            p_e_out = self._edge_readout(pattern, p_enc, p_e_rep, p_e_drop)
-            g_e_out = self._edge_readout(graph, g_enc, g_e_rep, g_e_drop)
-        pred_c, (pred_v, pred_e) = self.get_subiso_pred(p_v_out, p_v_mask, p_e_out, p_e_mask,
-                                                        g_v_out, g_v_mask, g_e_out, g_e_mask)
+            e_c, pred_e = self._head(self.pred_net["e"], "edge", pattern, self._edge_readout(pattern, p_enc, p_e_rep, p_e_drop),
+                                     p_e_drop, p_e_mask, graph, self._edge_readout(graph, g_enc, g_e_rep, g_e_drop), g_e_drop, g_e_mask)
+        pred_c = self._mix(v_c, e_c, g_v_mask, g_e_mask)
         return OutputDict(
             p_v_emb=p_v_emb, p_e_emb=p_e_emb, g_v_emb=g_v_emb, g_e_emb=g_e_emb,
             p_v_rep=p_v_rep, p_e_rep=p_e_rep, g_v_rep=g_v_rep, g_e_rep=g_e_rep,

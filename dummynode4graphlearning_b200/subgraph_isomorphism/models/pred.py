@@ -3,9 +3,14 @@
 Same modules, parameters (``p_fc, g_fc, pred_fc1, pred_fc2[, weight_fc1, weight_fc2]``) and padded
 semantics as the reference: the head sees LEFT-PADDED (B, L, rep) tensors whose padded and masked rows
 are zero, projects every row (so padded rows contribute the projection's bias) and pools over the whole
-padded axis.  The padded tensors are produced by one CUDA kernel
-(``ops.pad_segments``) instead of the reference's per-graph Python loop; the dense projections are
-library GEMMs.
+padded axis.
+
+``forward`` takes those padded tensors (``ops.pad_segments`` builds them in one kernel).  The models call
+``forward_ragged`` instead whenever the pooling is a sum or a mean and dropout is inactive: every padded or masked row of
+the reference's tensor is a zero row whose projection is exactly the bias, so  sum_rows (W x_r + b)  over the padded axis
+=  sum over the graph's unmasked rows of W x_r  +  L b  -- the projection of the N real rows and a masked segment sum (K3)
+replace the (B, L, rep) tensor and the projection of every padded row (pred.py:111,142,215-216; ``L`` is the batch-wide
+padded length, so the batch-composition dependence of App. A-7 is kept).
 """
 import torch as th
 import torch.nn as nn
@@ -66,12 +71,58 @@ class PredictNet(nn.Module):
         return y, w
 
 
+    # ---- unpadded evaluation ------------------------------------------------------------------------------------
+    ragged_pool = None      # "sum" | "mean" for heads whose pooling commutes with the projection
+
+    def supports_ragged(self):
+        return self.ragged_pool is not None and not (self.training and self.drop.p > 0)
+
+    def _pooled(self, fc, x, seg_ptr, drop, L):
+        """agg_graph(fc(padded rows)) without the padded tensor.  The projection stays BEFORE the sum, as in the reference:
+        summing the raw rows first is algebraically the same but puts degree / multi-hot columns of magnitude ~1e5 through
+        the projection's cancellations (measured: 2e-5 on the DMPNN 'large' loss instead of < 1e-6).  So: project the
+        N real rows (not B * L padded ones), masked segment sum of the projections, + L biases (every padded or masked
+        row of the reference's tensor is a zero row and contributes exactly the bias)."""
+        h = ops.linear(x, fc.weight, None)                    # (N, H)
+        v = ops.segment_sum(h, seg_ptr, drop) + float(L) * fc.bias
+        return v / float(L) if self.ragged_pool == "mean" else v
+
+    def forward_ragged(self, p_x, p_ptr, p_drop, p_mask, Lp, g_x, g_ptr, g_drop, g_mask, Lg):
+        """p_x (Np, rep) / g_x (Ng, rep): flat readout rows; *_ptr int32 (B + 1) row offsets; *_drop (N,) bool rows the
+        padded path zeroes (dummy nodes, reversed edges) or None; *_mask (B, L) bool as handed to ``forward``; Lp / Lg the
+        padded lengths.  Same values as ``forward`` on the padded tensors (up to fp32 summation order); ``w`` is defined on
+        the unpadded positions (the padded ones are don't-care: the loss masks them, train.py:783-784)."""
+        bsz = p_mask.size(0)
+        pl = p_mask.float().sum(dim=1).view(bsz, 1)
+        gl = g_mask.float().sum(dim=1).view(bsz, 1)
+        pl_inv, gl_inv = 1.0 / pl, 1.0 / gl
+        p_vec = self._pooled(self.p_fc, p_x, p_ptr, p_drop, Lp)
+        gv = self._pooled(self.g_fc, g_x, g_ptr, g_drop, Lg)
+        w = None
+        if self.weight_fc1 is not None:
+            gx = g_x if g_drop is None else g_x.masked_fill(g_drop.view(-1, 1), 0.0)
+            g = ops.linear(gx, self.g_fc.weight, self.g_fc.bias)                      # (Ng, H), per node
+            seg = ops.segment_ids(g_ptr, g_x.size(0)).long()
+            p, plx, plix = p_vec[seg], pl[seg], pl_inv[seg]
+            wr = self.act(self.weight_fc1(th.cat([p, g, g - p, g * p, plx, plix], dim=1)))
+            wr = self.weight_fc2(th.cat([wr, plx, plix], dim=1))                      # (Ng, 1)
+            w = ops.pad_segments(wr, g_ptr, int(Lg)).view(bsz, int(Lg))
+        y = th.cat([p_vec, gv, gv - p_vec, gv * p_vec, pl, gl, pl_inv, gl_inv], dim=1)
+        y = self.act(self.pred_fc1(y))
+        y = self.pred_fc2(th.cat([y, pl, gl, pl_inv, gl_inv], dim=1))
+        return y, w
+
+
 class MeanPredictNet(PredictNet):
+    ragged_pool = "mean"
+
     def agg_graph(self, g_rep, g_mask=None):
         return th.mean(g_rep, dim=1)
 
 
 class SumPredictNet(PredictNet):
+    ragged_pool = "sum"
+
     def agg_graph(self, g_rep, g_mask=None):
         return th.sum(g_rep, dim=1)
 

@@ -233,7 +233,7 @@ def test_mlp2_against_torch_float64(act, d, N):
     ref = nn.Sequential(nn.Linear(d, d), map_activation_str_to_layer(act), nn.Linear(d, d)).double()
     ref.load_state_dict({k: v.double() for k, v in seq.state_dict().items()})
     seq = seq.to(dev())
-    assert ops.mlp2_fusable(seq, force=True) and not ops.mlp2_fusable(seq)   # opt-in for the counting models
+    assert ops.mlp2_fusable(seq, force=True) and ops.mlp2_fusable(seq) == ops.MLP2_TENSOR_CORES   # default on since round 2
     x = torch.randn(N, d)
     g = torch.randn(N, d)
     xm = x.to(dev()).requires_grad_(True)

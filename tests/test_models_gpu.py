@@ -305,8 +305,8 @@ def test_gin_full_size_dummy_proteins_meets_1e5(device, hid, layers):
         # fp32 sums over 1e5 rows: the CPU oracle itself sits up to a few 1e-6 from float64; the bar applies to the distance
         # from the oracle OR, where the oracle's own rounding dominates, from the exact (float64) value
         e32, e64, eref = rel_err(q.grad, ref), rel_err(q.grad, ref64), rel_err(ref, ref64)
-        if pre_bn_bias:
-            assert float((q.grad.cpu() - ref).abs().max()) <= 1e-6 * gmax, n
+        if pre_bn_bias:      # both sides are rounding noise around an exact zero (the fp32 CPU oracle's is ~1e-6 * gmax itself)
+            assert float(q.grad.abs().max()) <= 1e-5 * gmax and float(ref.abs().max()) <= 1e-5 * gmax, n
         else:
             assert e32 <= TOL or e64 <= max(TOL, 2 * eref), (n, e32, e64, eref)
 
