@@ -154,9 +154,48 @@ class _CapturedStep:
         src = _structure_tensors(data)[0]
         pairs = [(d, s) for d, s in zip(self.static, src) if d is not None]
         torch._foreach_copy_([d for d, _ in pairs], [s for _, s in pairs])
+        self.copied = torch.cuda.Event()     # from here on the batch's own tensors may be overwritten (captured transform)
+        self.copied.record()
         self.graph.replay()
         self.replays += 1
         return self.loss
+
+
+class _CapturedTransform:
+    """CUDA graph of the whole transform (dummy augmentation, edge-to-vertex transform, canonicalisation, both CSR builds,
+    tilings) for ONE raw-batch signature.  Only possible when the transform has no device->host read, i.e. when the
+    loader attached ``conj_sizes`` (transforms.tu_conjugate_sizes).  The ~60 small launches that the eager transform paces
+    from the host (0.6 ms of host time per C2 batch) become one graph launch; the outputs are static tensors, so a replay
+    must not start before the train step that consumes the previous outputs has copied them (``wait`` event)."""
+
+    def __init__(self, pipe, dev_batch):
+        self.static_in = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in dev_batch.items()}
+        self.graph = torch.cuda.CUDAGraph()
+        from ._lib import lib
+        k0 = lib().kernel_launches()
+        cur = torch.cuda.current_stream()
+        on_side = cur != torch.cuda.default_stream(cur.device)      # capture must not run on the legacy default stream
+        with torch.cuda.graph(self.graph, **({"stream": cur} if on_side else {})):
+            self.out = pipe._transform_eager(self.static_in)
+        self.library_kernels = lib().kernel_launches() - k0
+        self.replays = 0
+
+    def run(self, batch, wait=None):
+        """batch: device OR pinned-host tensors of the captured signature (copied into the graph's input buffers)."""
+        if wait is not None:
+            torch.cuda.current_stream().wait_event(wait)
+        for k, v in batch.items():
+            if isinstance(v, torch.Tensor):
+                d = self.static_in[k]
+                d.copy_(v if v.dtype == d.dtype else v.to(d.dtype), non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        return self.out
+
+
+def _raw_signature(b):
+    return tuple(sorted((k, (tuple(v.shape), str(v.dtype)) if isinstance(v, torch.Tensor) else
+                         (tuple(v) if isinstance(v, (tuple, list)) else v)) for k, v in b.items()))
 
 
 class ClassificationPipeline:
@@ -185,6 +224,8 @@ class ClassificationPipeline:
         if self.cuda_graphs and not capturable:
             raise ValueError("cuda_graphs=True needs an optimizer built with capturable=True")
         self._graphs, self._max_graphs = {}, max_graphs
+        self._tgraphs = {}       # captured transforms by raw-batch signature
+        self._consumed = None    # event: the latest train step no longer reads its batch's own tensors
         self.overlap = bool(self.cuda_graphs if overlap is None else overlap) and self.device.type == "cuda"
         self._tstream = None
         self._inflight = []      # completion events of the train steps queued so far (bounded lead, see _throttle)
@@ -196,8 +237,33 @@ class ClassificationPipeline:
             self._tstream = torch.cuda.Stream(self.device, priority=-1)
         return self._tstream
 
-    def transform(self, dev_batch):
-        """raw TU-shaped device batch -> PyG-style Batch with compiled structure."""
+    def transform(self, batch):
+        """raw TU-shaped batch (device tensors, or pinned host tensors of an int32 / float32 / int64-y batch) -> PyG-style
+        Batch with compiled structure.  A batch that carries the loader's ``conj_sizes`` hint and whose signature has been
+        seen before is transformed by replaying a captured CUDA graph (see _CapturedTransform); everything else runs the
+        kernels eagerly."""
+        on_host = any(isinstance(v, torch.Tensor) and not v.is_cuda for v in batch.values())
+        capturable = (self.cuda_graphs and self.mode == "conj" and batch.get("conj_sizes") is not None and
+                      not self.with_edge_attr and not torch.cuda.is_current_stream_capturing())
+        if capturable:
+            norm = {k: (v.to(torch.int32) if isinstance(v, torch.Tensor) and v.dtype == torch.int64 and k != "y" else v)
+                    for k, v in batch.items()} if on_host else batch
+            sig = _raw_signature(norm)
+            ent = self._tgraphs.get(sig)
+            if ent is None:
+                if len(self._tgraphs) < self._max_graphs:
+                    self._tgraphs[sig] = "seen"
+            else:
+                if ent == "seen":
+                    dev_b = self._upload(batch) if on_host else batch
+                    torch.cuda.current_stream().synchronize()
+                    ent = self._tgraphs[sig] = _CapturedTransform(self, dev_b)
+                # the outputs are static tensors: the consumer of the previous replay must be done with them -- a replayed
+                # train step right after its copy into its own buffers, an eager one at its end (train_on sets the event)
+                return ent.run(norm, wait=self._consumed)
+        return self._transform_eager(self._upload(batch) if on_host else batch)
+
+    def _transform_eager(self, dev_batch):
         b = dev_batch
         if self.mode in ("dummy", "conj"):
             b = T.tu_add_dummy(b)
@@ -233,7 +299,8 @@ class ClassificationPipeline:
 
     def replayed_library_kernels(self):
         """libdn4gl kernels launched through CUDA-graph replays so far (they bypass the library's launch counter)."""
-        return sum(e.replays * e.library_kernels for e in self._graphs.values() if isinstance(e, _CapturedStep))
+        return (sum(e.replays * e.library_kernels for e in self._graphs.values() if isinstance(e, _CapturedStep)) +
+                sum(e.replays * e.library_kernels for e in self._tgraphs.values() if isinstance(e, _CapturedTransform)))
 
     def train_on(self, data):
         if not self.model.training:      # Module.train() walks every submodule (~0.2 ms of host time per step)
@@ -245,10 +312,15 @@ class ClassificationPipeline:
         if ent is None:                                     # first time this signature is seen: a normal eager step
             if len(self._graphs) < self._max_graphs:
                 self._graphs[sig] = "seen"
-            return self._train_body(data)
+            loss = self._train_body(data)
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+            return loss
         if ent == "seen":
             ent = self._graphs[sig] = _CapturedStep(self, data)
-        return ent.run(data)
+        loss = ent.run(data)
+        self._consumed = ent.copied
+        return loss
 
     def _throttle(self):
         """bounds the host's lead over the train stream to ONE step: before the transform of step k+1 starts, the train
@@ -307,7 +379,7 @@ class ClassificationPipeline:
         ts = self._transform_stream()
         self._throttle()
         with torch.cuda.stream(ts):          # the upload is ordered on the transform stream: no wait on the train stream
-            data = self.transform(self._upload(host_batch))
+            data = self.transform(host_batch)
         loss = self.train_on(self._hand_over(data, ts))
         self._mark_step()
         return PendingLoss(loss)
