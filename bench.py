@@ -447,7 +447,7 @@ def ours(a):
     host = pin_batch({k: v for k, v in raw.items() if k != "vattr"})
     dev_batch = T.to_device({k: v for k, v in raw.items() if k != "vattr"}, dev)
     if a.size_hints:      # what a loader that sees its batch on the host would attach (computed once here: the batch is fixed)
-        host["conj_sizes"] = dev_batch["conj_sizes"] = T.tu_conjugate_sizes(raw, with_dummy=True)
+        host["conj_sizes"] = dev_batch["conj_sizes"] = T.tu_conjugate_sizes_ex(raw, with_dummy=True)
     torch.manual_seed(0)
     args = Namespace(num_features=NUM_NODE_LABELS, hidden_dim=HID, num_classes=CLASSES, dropout_ratio=0.0,
                      additional={"train_eps": True, "num_layers": LAYERS, "aggregation": "sum"}, epochs=1, device=str(dev))
@@ -785,8 +785,9 @@ def ours(a):
         "warmup": n_warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": dict(workload_config(a.graphs, world), **({"size_hints": "the loader attaches the closed-form output sizes of the edge-to-vertex transform "
-                       "(transforms.tu_conjugate_sizes of the raw host batch): no device->host read inside a step; a wrong "
-                       "hint raises DN4GL_ECAPACITY"} if a.size_hints else {})),
+                       "(transforms.tu_conjugate_sizes_ex of the raw host batch: V', E', largest graph, 'every graph has a node', "
+                       "'edges sorted by source'): no device->host read inside a step, the CONJ_ CSR pair is written in closed "
+                       "form (dn4gl_tu_conj_direct_*) and the whole transform replays as a CUDA graph"} if a.size_hints else {})),
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": host_bytes(host), "d2h_bytes_per_step": 4 + 8 + 4,

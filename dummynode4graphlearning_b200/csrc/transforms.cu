@@ -359,6 +359,133 @@ extern "C" int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const
 }
 
 // ===========================================================================================
+// a2 + a3 in closed form for CONJ_ graphs (dummy + edge-to-vertex + PyG canonicalisation), round 2.
+//
+// After tu_add_dummy every node t has exactly one dummy out-edge (t -> n) and one dummy in-edge (n -> t), all dummy
+// edges merge into ONE conjugate vertex D (tu_data_processing.py:289-318), and PyG's read_tu_data then removes self
+// loops and sorts / merges the edge list (graph_neural_networks/dataset.py:151).  For a graph with m real edges the
+// canonical CONJ_ structure is therefore known row by row without generating, sorting and compacting candidates:
+//   vertices   real edge e  -> conjugate vertex e (its position among the graph's edges), D = vertex m
+//   out(e)     = { e2 real : src(e2) = dst(e), e2 != e } ascending, then D        (e2 = e only for a self loop)
+//   in(e)      = { e2 real : dst(e2) = src(e), e2 != e } ascending, then D
+//   out(D) = in(D) = all real edges 0 .. m-1                                     ((D, D) is dropped, :311-318)
+// No pair occurs twice (one dummy edge per node and direction; parallel real edges are distinct vertices), so the rows
+// are exactly the rows of the (row, col)-sorted, coalesced edge_index, and the in-rows the rows of its transpose in
+// ascending source order -- the same CSR pair dn4gl_tu_conjugate_* + dn4gl_coalesce + two dn4gl_build_csr produce
+// (tests/test_zzz_conj_direct_gpu.py compares them bit for bit), with 3 launches instead of ~35 and no sort.
+// Needs: every graph has at least one node (else it has no D), the real graph's CSR by source and by destination
+// (items in ascending edge id).  Global conjugate vertex id of real edge e of graph g: e + g;  D_g = edge_ptr[g+1] + g.
+__global__ void conj_direct_lens_kernel(int B, const int32_t *__restrict__ edge_ptr, const int32_t *__restrict__ src,
+                                        const int32_t *__restrict__ dst, const int32_t *__restrict__ out_ptr,
+                                        const int32_t *__restrict__ in_ptr, int64_t E, int32_t *__restrict__ len_out,
+                                        int32_t *__restrict__ len_in, int32_t *__restrict__ o_node_ptr) {
+    const int64_t u = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // conjugate vertex
+    if (u <= B) o_node_ptr[u] = edge_ptr[u] + static_cast<int32_t>(u);
+    if (u >= E + B) return;
+    // graph of u: largest g with edge_ptr[g] + g <= u
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (static_cast<int64_t>(edge_ptr[mid]) + mid <= u) lo = mid; else hi = mid;
+    }
+    const int g = lo;
+    const int64_t e = u - g;
+    if (e == edge_ptr[g + 1]) {                 // D_g
+        const int m = edge_ptr[g + 1] - edge_ptr[g];
+        len_out[u] = m;
+        len_in[u] = m;
+        return;
+    }
+    const int s = src[e], t = dst[e], self = (s == t) ? 1 : 0;
+    len_out[u] = out_ptr[t + 1] - out_ptr[t] + 1 - self;
+    len_in[u] = in_ptr[s + 1] - in_ptr[s] + 1 - self;
+}
+
+// one warp per conjugate vertex: both rows + the vertex label (label of the original edge; D: 0)
+__global__ void __launch_bounds__(256)
+conj_direct_fill_kernel(int B, const int32_t *__restrict__ edge_ptr, const int32_t *__restrict__ src,
+                        const int32_t *__restrict__ dst, const int32_t *__restrict__ elabel,
+                        const int32_t *__restrict__ out_ptr, const int32_t *__restrict__ out_eid,
+                        const int32_t *__restrict__ in_ptr, const int32_t *__restrict__ in_eid, int64_t E,
+                        const int32_t *__restrict__ rp_out, const int32_t *__restrict__ rp_in,
+                        int32_t *__restrict__ col_out, int32_t *__restrict__ col_in, int32_t *__restrict__ o_vlabel) {
+    const int64_t u = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (u >= E + B) return;
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (static_cast<int64_t>(edge_ptr[mid]) + mid <= u) lo = mid; else hi = mid;
+    }
+    const int g = lo;
+    const int64_t e = u - g;
+    const int32_t Dg = edge_ptr[g + 1] + g;
+    if (e == edge_ptr[g + 1]) {                 // D_g: all real edges of the graph, both directions
+        const int m = edge_ptr[g + 1] - edge_ptr[g];
+        const int32_t first = edge_ptr[g] + g;
+        for (int i = lane; i < m; i += 32) {
+            col_out[rp_out[u] + i] = first + i;
+            col_in[rp_in[u] + i] = first + i;
+        }
+        if (lane == 0) o_vlabel[u] = 0;
+        return;
+    }
+    const int s = src[e], t = dst[e];
+    if (lane == 0) o_vlabel[u] = elabel ? elabel[e] : 1;
+    {   // out-row: real out-edges of t except e itself (ascending edge id), then D
+        const int b0 = out_ptr[t], n = out_ptr[t + 1] - b0;
+        int w = rp_out[u];
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const int e2 = i < n ? out_eid[b0 + i] : -1;
+            const bool keep = i < n && e2 != e;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) col_out[w + __popc(m & ((1u << lane) - 1u))] = e2 + g;
+            w += __popc(m);
+        }
+        if (lane == 0) col_out[w] = Dg;
+    }
+    {   // in-row: real in-edges of s except e itself, then D
+        const int b0 = in_ptr[s], n = in_ptr[s + 1] - b0;
+        int w = rp_in[u];
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const int e2 = i < n ? in_eid[b0 + i] : -1;
+            const bool keep = i < n && e2 != e;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) col_in[w + __popc(m & ((1u << lane) - 1u))] = e2 + g;
+            w += __popc(m);
+        }
+        if (lane == 0) col_in[w] = Dg;
+    }
+}
+
+extern "C" int dn4gl_tu_conj_direct_lens(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                                         const int32_t *out_ptr, const int32_t *in_ptr, int64_t E, int32_t *len_out,
+                                         int32_t *len_in, int32_t *o_node_ptr, void *stream) {
+    DN_ARG(B >= 1 && E >= 0 && edge_ptr && out_ptr && in_ptr && len_out && len_in && o_node_ptr && (E == 0 || (src && dst)));
+    const int64_t V = E + B;
+    conj_direct_lens_kernel<<<static_cast<unsigned>(ceil_div64(V + 1, 256)), 256, 0, as_stream(stream)>>>(
+        B, edge_ptr, src, dst, out_ptr, in_ptr, E, len_out, len_in, o_node_ptr);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+extern "C" int dn4gl_tu_conj_direct_fill(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                                         const int32_t *elabel, const int32_t *out_ptr, const int32_t *out_eid,
+                                         const int32_t *in_ptr, const int32_t *in_eid, int64_t E, const int32_t *rp_out,
+                                         const int32_t *rp_in, int32_t *col_out, int32_t *col_in, int32_t *o_vlabel,
+                                         void *stream) {
+    DN_ARG(B >= 1 && E >= 0 && edge_ptr && out_ptr && in_ptr && rp_out && rp_in && o_vlabel);
+    DN_ARG(E == 0 || (src && dst && out_eid && in_eid && col_out && col_in));
+    const int64_t V = E + B;
+    conj_direct_fill_kernel<<<static_cast<unsigned>(ceil_div64(V * 32, 256)), 256, 0, as_stream(stream)>>>(
+        B, edge_ptr, src, dst, elabel, out_ptr, out_eid, in_ptr, in_eid, E, rp_out, rp_in, col_out, col_in, o_vlabel);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+// ===========================================================================================
 // a3: PyG read_tu_data [ext, torch-geometric 2.0.2]: remove_self_loops + coalesce.
 // Input: the edge list (src, dst in edge-id order) and its by-src CSR (row_ptr, items = edge ids
 // from dn4gl_build_csr(key=src)).  Rows are sorted in place by (dst, edge id), self loops and

@@ -33,6 +33,19 @@ class GraphStructure:
         self._rel = {}
         self._row2seg = None
 
+    @classmethod
+    def from_csr(cls, csr_in, csr_out, num_nodes, node_ptr, max_seg=None):
+        """from an already compiled CSR pair (transforms.tu_conj_structure): no edge list is kept (src / dst are None)."""
+        s = cls.__new__(cls)
+        s.src = s.dst = None
+        s.num_nodes, s.trash_row = int(num_nodes), False
+        s.csr_in, s.csr_out = csr_in, csr_out
+        s.node_ptr = node_ptr.to(torch.int32).contiguous()
+        s.csr_in.seg_ptr = s.csr_out.seg_ptr = s.node_ptr
+        s.csr_in.max_seg = s.csr_out.max_seg = max_seg
+        s._rel, s._row2seg = {}, None
+        return s
+
     @property
     def row2seg(self):
         """int32 row -> graph index (``batch`` as the kernels read it); built once per batch."""

@@ -265,6 +265,19 @@ class ClassificationPipeline:
 
     def _transform_eager(self, dev_batch):
         b = dev_batch
+        hint = b.get("conj_sizes")
+        if (self.mode == "conj" and not self.with_edge_attr and hint is not None and len(hint) >= 5 and hint[3]
+                and self.nvl is not None and self.node_label_min is not None and "vattr" not in b):
+            # CONJ_ structure in closed form from the raw graphs' CSRs (transforms.tu_conj_structure): the loader's extended
+            # hint (tu_conjugate_sizes_ex) says every graph has a node, and the model reads x, y and the structure only
+            data = T.tu_conj_structure(b, self.nvl, self.node_label_min)
+            s = data.structure
+            hid = getattr(self.model, "hidden_dim", None)
+            if hid in ops._TILED_D:
+                s.csr_in.tiles(hid)
+                s.csr_out.tiles(hid)
+            s.row2seg
+            return data
         if self.mode in ("dummy", "conj"):
             b = T.tu_add_dummy(b)
         if self.mode in ("conj", "line"):

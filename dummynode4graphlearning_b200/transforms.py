@@ -161,6 +161,74 @@ def tu_conjugate_sizes(raw, with_dummy):
     return m, pairs, int(per_graph.max()) if B else 0
 
 
+def exclusive_scan_(lens_plus_one):
+    """in place: x[i] <- sum_{j<i} x[j] over the first n = len - 1 entries, x[n] <- total (dn4gl_exclusive_scan_i32)."""
+    L = lib()
+    n = int(lens_plus_one.numel()) - 1
+    wsb = L.size("dn4gl_scan_workspace_bytes", n)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=lens_plus_one.device)
+    L.call("dn4gl_exclusive_scan_i32", ptr(lens_plus_one), ptr(lens_plus_one), n, ptr(ws), wsb, _stream())
+    return lens_plus_one
+
+
+def tu_conjugate_sizes_ex(raw, with_dummy=True):
+    """``tu_conjugate_sizes`` plus what the closed-form CONJ_ builder (``tu_conj_structure``) needs to know on the host:
+    (V', E', max nodes, every graph has a node, edges are sorted by source)."""
+    v, e, mx = tu_conjugate_sizes(raw, with_dummy)
+    node_ptr, src = np.asarray(raw["node_ptr"], np.int64), np.asarray(raw["src"], np.int64)
+    return (v, e, mx, bool((np.diff(node_ptr) > 0).all()), bool((np.diff(src) >= 0).all()) if len(src) > 1 else True)
+
+
+def tu_conj_structure(b, num_node_labels, node_label_min=0):
+    """RAW TU-shaped device batch -> the canonical CONJ_ mini-batch (what ``pyg_canonicalize(tu_conjugate(tu_add_dummy(b)))``
+    yields for a model that reads x, y and the graph structure: GIN), written in closed form by
+    dn4gl_tu_conj_direct_lens / _fill from the raw graphs' two CSRs: no dummy-augmented graph, no candidate list, no
+    sort, no compaction (csrc/transforms.cu; tu_data_processing.py:125-338 + dataset.py:151).  Needs the loader's hint
+    ``b["conj_sizes"]`` from ``tu_conjugate_sizes_ex`` with "every graph has a node" true.  -> graph_classification.data.Batch"""
+    from .graph import CSR, HEAVY_THRESHOLD
+    from .graph_classification.data import Batch, GraphStructure
+    require_cuda(b["src"], "batch")
+    L = lib()
+    dev = b["src"].device
+    B, N, E = int(b["num_graphs"]), int(b["vlabel"].numel()), int(b["src"].numel())
+    V2, E2cap, max_nodes, all_nodes, sorted_src = b["conj_sizes"]
+    if not all_nodes or V2 != E + B:
+        raise ValueError("tu_conj_structure needs graphs with at least one node each")
+    out = build_csr(b["src"], b["dst"], N, heavy_threshold=0, sorted_keys=bool(sorted_src))
+    inn = build_csr(b["dst"], b["src"], N, heavy_threshold=0)
+    V = E + B
+    rp_out, rp_in, node_ptr = _empty_i32(V + 1, dev), _empty_i32(V + 1, dev), _empty_i32(B + 1, dev)
+    L.call("dn4gl_tu_conj_direct_lens", B, ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]), ptr(out.row_ptr), ptr(inn.row_ptr),
+           E, ptr(rp_out), ptr(rp_in), ptr(node_ptr), _stream())
+    exclusive_scan_(rp_out)
+    exclusive_scan_(rp_in)
+    cap = max(int(E2cap), 1)      # E' counts the (e, e) pairs of self-loop edges, which the rows leave out: an upper bound
+    col_out, col_in, vlabel = _empty_i32(cap, dev), _empty_i32(cap, dev), _empty_i32(V, dev)
+    el = b.get("elabel") if b.get("has_edge_labels", True) else None
+    L.call("dn4gl_tu_conj_direct_fill", B, ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]), ptr(el), ptr(out.row_ptr), ptr(out.eid),
+           ptr(inn.row_ptr), ptr(inn.eid), E, ptr(rp_out), ptr(rp_in), ptr(col_out), ptr(col_in), ptr(vlabel), _stream())
+    csrs = []
+    for rp, col in ((rp_in, col_in), (rp_out, col_out)):
+        c = CSR(rp, col, None, V, cap)
+        hcap = cap // HEAVY_THRESHOLD + 1
+        c.heavy_rows, c.heavy_count, c.heavy_thr = _empty_i32(hcap, dev), _empty_i32(1, dev), HEAVY_THRESHOLD
+        L.call("dn4gl_collect_heavy_rows", ptr(rp), V, HEAVY_THRESHOLD, ptr(c.heavy_rows), hcap, ptr(c.heavy_count), _stream())
+        c.seg_ptr, c.max_seg = node_ptr, int(max_nodes)
+        csrs.append(c)
+    x = (vlabel.view(-1, 1) == torch.arange(int(node_label_min), int(node_label_min) + int(num_node_labels),
+                                            dtype=vlabel.dtype, device=dev)).to(torch.float32)
+    def edge_index():      # only a consumer outside the GIN train step asks for it: one device->host read of the edge count
+        nnz = int(rp_out[-1].item())
+        rows = torch.repeat_interleave(torch.arange(V, device=dev), (rp_out[1:] - rp_out[:-1]).long(), output_size=nnz)
+        return torch.stack([rows, col_out[:nnz].long()])
+
+    batch = lambda: torch.repeat_interleave(torch.arange(B, device=dev), (node_ptr[1:] - node_ptr[:-1]).long(), output_size=V)
+    data = Batch(x, edge_index, batch, y=b.get("y"), is_dummy_node=lambda: vlabel == 0, node_ptr=node_ptr,
+                 max_graph_nodes=int(max_nodes))
+    data._structure = GraphStructure.from_csr(csrs[0], csrs[1], V, node_ptr, int(max_nodes))
+    return data
+
+
 def tu_conjugate(b):
     """edge-to-vertex transform of a TU-flavoured batch (raw -> LINE_, dummy-augmented -> CONJ_)."""
     require_cuda(b["src"], "batch")
@@ -178,7 +246,7 @@ def tu_conjugate(b):
            ptr(o_node_ptr), ptr(o_edge_ptr), ptr(ws), ws_bytes, _stream())
     hint = b.get("conj_sizes")
     if hint is not None:                      # sizes known on the host (tu_conjugate_sizes): no read-back, no sync
-        V2, E2, max_nodes = (int(v) for v in hint)
+        V2, E2, max_nodes = (int(v) for v in tuple(hint)[:3])      # tu_conjugate_sizes or the first fields of ..._sizes_ex
         flag = error_flag(dev)                # a hint that does not match the device's counts raises the async flag
         wrong = (o_node_ptr[-1:] != V2) | (o_edge_ptr[-1:] != E2)
         flag.copy_(torch.where(wrong, torch.full_like(flag, -5), flag))

@@ -148,6 +148,25 @@ int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const int32_t *e
                             int64_t cap_v, int64_t cap_e, int32_t *err_flag,
                             void *ws, size_t ws_bytes, void *stream);
 
+/* CONJ_ structure in closed form (round 2): the CSR pair of load_graph_data_from_TUDatadir(with_dummy=True) ->
+ * convert_conjugate_graph_forward (tu_data_processing.py:125-338) -> PyG read_tu_data's remove_self_loops + coalesce
+ * (graph_neural_networks/dataset.py:151), written row by row from the RAW graphs' CSRs without building the
+ * dummy-augmented graph, the candidate list, or sorting anything: every node has exactly one dummy out- and in-edge and
+ * all dummy edges merge into one conjugate vertex D, so  out(e) = {real out-edges of dst(e)} \ {e} + {D},
+ * in(e) = {real in-edges of src(e)} \ {e} + {D},  out(D) = in(D) = all real edges.  Requires every graph to have >= 1 node.
+ *   out_ptr / out_eid, in_ptr / in_eid: the raw graphs' CSR by source / by destination (dn4gl_build_csr[_sorted], items in
+ *   ascending edge id).   _lens: row lengths len_out / len_in [E + B] (scan them into rp_out / rp_in [E + B + 1]) and
+ *   o_node_ptr[B + 1] (= edge_ptr[g] + g).   _fill: col_out / col_in (global conjugate vertex ids, rows ascending) and
+ *   o_vlabel[E + B] (label of the original edge, 1 if elabel == NULL; D: 0).                                          */
+int dn4gl_tu_conj_direct_lens(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                              const int32_t *out_ptr, const int32_t *in_ptr, int64_t E, int32_t *len_out,
+                              int32_t *len_in, int32_t *o_node_ptr, void *stream);
+int dn4gl_tu_conj_direct_fill(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
+                              const int32_t *elabel, const int32_t *out_ptr, const int32_t *out_eid,
+                              const int32_t *in_ptr, const int32_t *in_eid, int64_t E, const int32_t *rp_out,
+                              const int32_t *rp_in, int32_t *col_out, int32_t *col_in, int32_t *o_vlabel,
+                              void *stream);
+
 /* subgraph-isomorphism flavour, replaces convert_conjugate_graph, DGL branch (subgraph_isomorphism/utils/graph.py:
  * 77-175; igraph branch :177-267 is the same rule), called per graph by convert_to_conjugate (train.py:564-593).
  * Edges with equal eid merge into one conjugate vertex (numbered by ascending id, attributes of the first such edge);
