@@ -401,63 +401,52 @@ __global__ void conj_direct_lens_kernel(int B, const int32_t *__restrict__ edge_
     len_in[u] = in_ptr[s + 1] - in_ptr[s] + 1 - self;
 }
 
-// one warp per conjugate vertex: both rows + the vertex label (label of the original edge; D: 0)
+// rows of the real vertices: one THREAD per (vertex, direction) -- rows hold ~5 entries, the loads of a row are independent
+// of each other, and 3e5 threads are resident at once, so the kernel takes a few dependent-load latencies in total (the
+// first version, a warp per vertex with a binary search over the graph offsets each, took 73 us at C2).  The vertex's graph
+// comes from the edge -> graph map (dn4gl_segment_ids_i32 over edge_ptr).
 __global__ void __launch_bounds__(256)
-conj_direct_fill_kernel(int B, const int32_t *__restrict__ edge_ptr, const int32_t *__restrict__ src,
-                        const int32_t *__restrict__ dst, const int32_t *__restrict__ elabel,
+conj_direct_rows_kernel(const int32_t *__restrict__ edge2graph, const int32_t *__restrict__ edge_ptr,
+                        const int32_t *__restrict__ src, const int32_t *__restrict__ dst, const int32_t *__restrict__ elabel,
                         const int32_t *__restrict__ out_ptr, const int32_t *__restrict__ out_eid,
                         const int32_t *__restrict__ in_ptr, const int32_t *__restrict__ in_eid, int64_t E,
                         const int32_t *__restrict__ rp_out, const int32_t *__restrict__ rp_in,
                         int32_t *__restrict__ col_out, int32_t *__restrict__ col_in, int32_t *__restrict__ o_vlabel) {
-    const int64_t u = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (u >= E + B) return;
-    int lo = 0, hi = B;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (static_cast<int64_t>(edge_ptr[mid]) + mid <= u) lo = mid; else hi = mid;
-    }
-    const int g = lo;
-    const int64_t e = u - g;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= 2 * E) return;
+    const int64_t e = i >> 1;
+    const bool inward = i & 1;
+    const int g = edge2graph[e];
+    const int64_t u = e + g;
     const int32_t Dg = edge_ptr[g + 1] + g;
-    if (e == edge_ptr[g + 1]) {                 // D_g: all real edges of the graph, both directions
-        const int m = edge_ptr[g + 1] - edge_ptr[g];
-        const int32_t first = edge_ptr[g] + g;
-        for (int i = lane; i < m; i += 32) {
-            col_out[rp_out[u] + i] = first + i;
-            col_in[rp_in[u] + i] = first + i;
-        }
-        if (lane == 0) o_vlabel[u] = 0;
-        return;
+    const int node = inward ? src[e] : dst[e];                    // in-row: in-edges of src(e); out-row: out-edges of dst(e)
+    const int32_t *ptr = inward ? in_ptr : out_ptr, *items = inward ? in_eid : out_eid;
+    int32_t *col = inward ? col_in : col_out;
+    const int b0 = ptr[node], n = ptr[node + 1] - b0;
+    int w = (inward ? rp_in : rp_out)[u];
+    for (int k = 0; k < n; ++k) {
+        const int e2 = items[b0 + k];
+        if (e2 != e) col[w++] = e2 + g;                           // e itself appears only for a self loop
     }
-    const int s = src[e], t = dst[e];
-    if (lane == 0) o_vlabel[u] = elabel ? elabel[e] : 1;
-    {   // out-row: real out-edges of t except e itself (ascending edge id), then D
-        const int b0 = out_ptr[t], n = out_ptr[t + 1] - b0;
-        int w = rp_out[u];
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            const int e2 = i < n ? out_eid[b0 + i] : -1;
-            const bool keep = i < n && e2 != e;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) col_out[w + __popc(m & ((1u << lane) - 1u))] = e2 + g;
-            w += __popc(m);
-        }
-        if (lane == 0) col_out[w] = Dg;
+    col[w] = Dg;
+    if (!inward) o_vlabel[u] = elabel ? elabel[e] : 1;
+}
+
+// rows of the merged dummy vertices D_g: all real edges of the graph, both directions; one warp per graph
+__global__ void __launch_bounds__(256)
+conj_direct_dummy_rows_kernel(int B, const int32_t *__restrict__ edge_ptr, const int32_t *__restrict__ rp_out,
+                              const int32_t *__restrict__ rp_in, int32_t *__restrict__ col_out,
+                              int32_t *__restrict__ col_in, int32_t *__restrict__ o_vlabel) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= B) return;
+    const int m = edge_ptr[g + 1] - edge_ptr[g];
+    const int32_t first = edge_ptr[g] + g, u = edge_ptr[g + 1] + g;
+    const int wo = rp_out[u], wi = rp_in[u];
+    for (int k = lane; k < m; k += 32) {
+        col_out[wo + k] = first + k;
+        col_in[wi + k] = first + k;
     }
-    {   // in-row: real in-edges of s except e itself, then D
-        const int b0 = in_ptr[s], n = in_ptr[s + 1] - b0;
-        int w = rp_in[u];
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            const int e2 = i < n ? in_eid[b0 + i] : -1;
-            const bool keep = i < n && e2 != e;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) col_in[w + __popc(m & ((1u << lane) - 1u))] = e2 + g;
-            w += __popc(m);
-        }
-        if (lane == 0) col_in[w] = Dg;
-    }
+    if (lane == 0) o_vlabel[u] = 0;
 }
 
 extern "C" int dn4gl_tu_conj_direct_lens(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
@@ -471,17 +460,20 @@ extern "C" int dn4gl_tu_conj_direct_lens(int32_t B, const int32_t *edge_ptr, con
     return DN4GL_OK;
 }
 
-extern "C" int dn4gl_tu_conj_direct_fill(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
-                                         const int32_t *elabel, const int32_t *out_ptr, const int32_t *out_eid,
-                                         const int32_t *in_ptr, const int32_t *in_eid, int64_t E, const int32_t *rp_out,
-                                         const int32_t *rp_in, int32_t *col_out, int32_t *col_in, int32_t *o_vlabel,
-                                         void *stream) {
+extern "C" int dn4gl_tu_conj_direct_fill(int32_t B, const int32_t *edge_ptr, const int32_t *edge2graph, const int32_t *src,
+                                         const int32_t *dst, const int32_t *elabel, const int32_t *out_ptr,
+                                         const int32_t *out_eid, const int32_t *in_ptr, const int32_t *in_eid, int64_t E,
+                                         const int32_t *rp_out, const int32_t *rp_in, int32_t *col_out, int32_t *col_in,
+                                         int32_t *o_vlabel, void *stream) {
     DN_ARG(B >= 1 && E >= 0 && edge_ptr && out_ptr && in_ptr && rp_out && rp_in && o_vlabel);
-    DN_ARG(E == 0 || (src && dst && out_eid && in_eid && col_out && col_in));
-    const int64_t V = E + B;
-    conj_direct_fill_kernel<<<static_cast<unsigned>(ceil_div64(V * 32, 256)), 256, 0, as_stream(stream)>>>(
-        B, edge_ptr, src, dst, elabel, out_ptr, out_eid, in_ptr, in_eid, E, rp_out, rp_in, col_out, col_in, o_vlabel);
-    DN_LAUNCHED();
+    DN_ARG(E == 0 || (edge2graph && src && dst && out_eid && in_eid && col_out && col_in));
+    cudaStream_t st = as_stream(stream);
+    if (E > 0)
+        conj_direct_rows_kernel<<<static_cast<unsigned>(ceil_div64(2 * E, 256)), 256, 0, st>>>(
+            edge2graph, edge_ptr, src, dst, elabel, out_ptr, out_eid, in_ptr, in_eid, E, rp_out, rp_in, col_out, col_in, o_vlabel);
+    conj_direct_dummy_rows_kernel<<<static_cast<unsigned>(ceil_div64(static_cast<int64_t>(B) * 32, 256)), 256, 0, st>>>(
+        B, edge_ptr, rp_out, rp_in, col_out, col_in, o_vlabel);
+    DN_LAUNCHED_N(E > 0 ? 2 : 1);
     return DN4GL_OK;
 }
 

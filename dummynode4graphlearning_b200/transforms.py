@@ -205,7 +205,10 @@ def tu_conj_structure(b, num_node_labels, node_label_min=0):
     cap = max(int(E2cap), 1)      # E' counts the (e, e) pairs of self-loop edges, which the rows leave out: an upper bound
     col_out, col_in, vlabel = _empty_i32(cap, dev), _empty_i32(cap, dev), _empty_i32(V, dev)
     el = b.get("elabel") if b.get("has_edge_labels", True) else None
-    L.call("dn4gl_tu_conj_direct_fill", B, ptr(b["edge_ptr"]), ptr(b["src"]), ptr(b["dst"]), ptr(el), ptr(out.row_ptr), ptr(out.eid),
+    e2g = _empty_i32(max(E, 1), dev)
+    if E > 0:
+        L.call("dn4gl_segment_ids_i32", ptr(b["edge_ptr"]), B, E, ptr(e2g), _stream())
+    L.call("dn4gl_tu_conj_direct_fill", B, ptr(b["edge_ptr"]), ptr(e2g), ptr(b["src"]), ptr(b["dst"]), ptr(el), ptr(out.row_ptr), ptr(out.eid),
            ptr(inn.row_ptr), ptr(inn.eid), E, ptr(rp_out), ptr(rp_in), ptr(col_out), ptr(col_in), ptr(vlabel), _stream())
     csrs = []
     for rp, col in ((rp_in, col_in), (rp_out, col_out)):

@@ -157,12 +157,13 @@ int dn4gl_tu_conjugate_fill(int32_t B, const int32_t *node_ptr, const int32_t *e
  *   out_ptr / out_eid, in_ptr / in_eid: the raw graphs' CSR by source / by destination (dn4gl_build_csr[_sorted], items in
  *   ascending edge id).   _lens: row lengths len_out / len_in [E + B] (scan them into rp_out / rp_in [E + B + 1]) and
  *   o_node_ptr[B + 1] (= edge_ptr[g] + g).   _fill: col_out / col_in (global conjugate vertex ids, rows ascending) and
- *   o_vlabel[E + B] (label of the original edge, 1 if elabel == NULL; D: 0).                                          */
+ *   o_vlabel[E + B] (label of the original edge, 1 if elabel == NULL; D: 0); edge2graph[E] = graph of every raw edge
+ *   (dn4gl_segment_ids_i32 over edge_ptr).                                                                            */
 int dn4gl_tu_conj_direct_lens(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
                               const int32_t *out_ptr, const int32_t *in_ptr, int64_t E, int32_t *len_out,
                               int32_t *len_in, int32_t *o_node_ptr, void *stream);
-int dn4gl_tu_conj_direct_fill(int32_t B, const int32_t *edge_ptr, const int32_t *src, const int32_t *dst,
-                              const int32_t *elabel, const int32_t *out_ptr, const int32_t *out_eid,
+int dn4gl_tu_conj_direct_fill(int32_t B, const int32_t *edge_ptr, const int32_t *edge2graph, const int32_t *src,
+                              const int32_t *dst, const int32_t *elabel, const int32_t *out_ptr, const int32_t *out_eid,
                               const int32_t *in_ptr, const int32_t *in_eid, int64_t E, const int32_t *rp_out,
                               const int32_t *rp_in, int32_t *col_out, int32_t *col_in, int32_t *o_vlabel,
                               void *stream);
