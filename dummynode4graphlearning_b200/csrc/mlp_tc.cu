@@ -252,7 +252,10 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
     // accumulators (see lin_fwd_kernel: at most a few MMAs per accumulator): data gradient NACC_D x [2 KP] columns, then
     // weight gradient NACC_W x [2 KP] columns; the weight accumulators are re-started every tile and added to the CTA's
     // partial in global memory with fp32 adds
-    constexpr int KS_D = MP / 8, NACC_D = TC_SPLIT_ACC, KPA_D = KS_D / NACC_D;
+    // data gradient: all gY_lo products first (2^-11 of the result: their truncation is harmless), then the gY_hi k-steps
+    // spread over NACC_D accumulators (2 at MP = 64: four full-magnitude accumulations each) -- the same measures as the
+    // pipelined forward stage (mlp_pipe.cu header); this kernel serves the 64-wide backward of the counting models
+    constexpr int KS_D = MP / 8, NACC_D = (MP >= 64 && TC_SPLIT_ACC < 2) ? 2 : TC_SPLIT_ACC, KPA_D = KS_D / NACC_D;
     constexpr int NACC_W = TC_SPLIT_ACC, KPA_W = 16 / NACC_W;
     constexpr uint32_t WBASE = NACC_D * 2 * KP;
     constexpr uint32_t TCOLS = (WBASE + NACC_W * 2 * KP) <= 128 ? 128 : ((WBASE + NACC_W * 2 * KP) <= 256 ? 256 : 512);
@@ -378,10 +381,14 @@ __global__ void __launch_bounds__(NT) lin_bwd_kernel(const LinBwdArgs a) {
 #pragma unroll
                 for (int jj = 0; jj < KS_D; ++jj) {
                     const uint32_t aoff = (jj >> 2) * PANEL128 + (jj & 3) * 32u;
-                    const uint64_t bd = make_desc_mn(sWh + jj * 1024u, MP * 128u);
-                    const uint32_t d = tmem + (jj / KPA_D) * 2 * KP;
-                    tc_mma_tf32(d, make_desc(sGh + aoff, 16, 1024), bd, IDESC_DATA, (jj % KPA_D) != 0 ? 1u : 0u);
-                    tc_mma_tf32(d, make_desc(sGl + aoff, 16, 1024), bd, IDESC_DATA, 1);
+                    tc_mma_tf32(tmem, make_desc(sGl + aoff, 16, 1024), make_desc_mn(sWh + jj * 1024u, MP * 128u), IDESC_DATA, jj != 0 ? 1u : 0u);
+                }
+#pragma unroll
+                for (int jj = 0; jj < KS_D; ++jj) {
+                    const uint32_t aoff = (jj >> 2) * PANEL128 + (jj & 3) * 32u;
+                    const int acc = jj / KPA_D;
+                    tc_mma_tf32(tmem + acc * 2 * KP, make_desc(sGh + aoff, 16, 1024), make_desc_mn(sWh + jj * 1024u, MP * 128u), IDESC_DATA,
+                                (acc == 0 || (jj % KPA_D) != 0) ? 1u : 0u);
                 }
             }
             // weight gradient: ([MP hi ; MP lo ; ...] x 128 rows) x (128 rows x [KP hi | KP lo]); k-steps of 8 rows,
@@ -920,7 +927,9 @@ int launch_fwd(const LinFwdArgs &a, int *grid_out, cudaStream_t s) {
 template <int KP, int MP, int RING>
 int launch_bwd(const LinBwdArgs &a, int *grid_out, cudaStream_t s) {
     const size_t smem = bwd_smem(KP, MP, RING);
-    const int grid = tc_grid(a.N, smem, 2 * TC_SPLIT_ACC * 2 * KP <= 128 ? 128 : (2 * TC_SPLIT_ACC * 2 * KP <= 256 ? 256 : 512), NT_BWD);
+    constexpr int nacc_d = (MP >= 64 && TC_SPLIT_ACC < 2) ? 2 : TC_SPLIT_ACC;
+    constexpr int cols = (nacc_d + TC_SPLIT_ACC) * 2 * KP;
+    const int grid = tc_grid(a.N, smem, cols <= 128 ? 128 : (cols <= 256 ? 256 : 512), NT_BWD);
     DN_CUDA(cudaFuncSetAttribute(lin_bwd_kernel<KP, MP, RING, NT_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     DN_LAUNCH((lin_bwd_kernel<KP, MP, RING, NT_BWD>), grid, NT_BWD, smem, s, a);
     *grid_out = grid;

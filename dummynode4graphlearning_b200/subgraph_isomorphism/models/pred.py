@@ -106,7 +106,15 @@ class PredictNet(nn.Module):
             p, plx, plix = p_vec[seg], pl[seg], pl_inv[seg]
             wr = self.act(self.weight_fc1(th.cat([p, g, g - p, g * p, plx, plix], dim=1)))
             wr = self.weight_fc2(th.cat([wr, plx, plix], dim=1))                      # (Ng, 1)
-            w = ops.pad_segments(wr, g_ptr, int(Lg)).view(bsz, int(Lg))
+            # padded positions: the reference evaluates the same formula on zero rows (g = bias), one value per graph.
+            # The loss zeroes those positions IN PLACE outside autograd (train.py:783-784) but keeps their gradient path
+            # (the match regulariser relu(pred_v - pred_c) sees 0 - pred_c there), so they must exist with their producer.
+            gb = self.g_fc.bias.view(1, -1).expand(bsz, -1)
+            wp = self.act(self.weight_fc1(th.cat([p_vec, gb, gb - p_vec, gb * p_vec, pl, pl_inv], dim=1)))
+            wp = self.weight_fc2(th.cat([wp, pl, pl_inv], dim=1))                     # (B, 1)
+            ones = th.ones((g_x.size(0), 1), dtype=wr.dtype, device=wr.device)
+            is_pad = 1.0 - ops.pad_segments(ones, g_ptr, int(Lg)).view(bsz, int(Lg))
+            w = ops.pad_segments(wr, g_ptr, int(Lg)).view(bsz, int(Lg)) + is_pad * wp
         y = th.cat([p_vec, gv, gv - p_vec, gv * p_vec, pl, gl, pl_inv, gl_inv], dim=1)
         y = self.act(self.pred_fc1(y))
         y = self.pred_fc2(th.cat([y, pl, gl, pl_inv, gl_inv], dim=1))
