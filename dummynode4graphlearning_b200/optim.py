@@ -75,8 +75,10 @@ class FlatAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        if self.flat_param is None and not self._build():
-            return loss
+        if self.flat_param is None:
+            if not self._build():
+                return loss
+            self._apply_pending_state()      # a checkpoint loaded before the first backward
         if self._hyper_host is None or not torch.cuda.is_current_stream_capturing():
             self.sync_hyper()
         b = self.bucket
@@ -89,3 +91,52 @@ class FlatAdam(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none=True):
         self.bucket.zero()
+
+    # ---- checkpointing (train.py:1450-1470 / main.py:95-100 save and restore optimizer.state_dict()) ------------------
+    def state_dict(self):
+        """torch-format state: per parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` [/ ``max_exp_avg_sq``] sliced out of
+        the flat buffers (parameters that never received a gradient have no entry, as with torch.optim.Adam), so a
+        checkpoint resumes with the moments and the bias-correction step instead of restarting Adam."""
+        if self.flat_param is not None:
+            b = self.bucket
+            base = self.flat_param.data_ptr()
+            step = self._step.detach().clone().view(())
+            for p in b.active:
+                off = (p.data_ptr() - base) // 4
+                sl = slice(off, off + p.numel())
+                st = {"step": step.clone(), "exp_avg": self.exp_avg[sl].view_as(p).clone(),
+                      "exp_avg_sq": self.exp_avg_sq[sl].view_as(p).clone()}
+                if self.max_exp_avg_sq is not None:
+                    st["max_exp_avg_sq"] = self.max_exp_avg_sq[sl].view_as(p).clone()
+                self.state[p] = st
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """accepts what ``state_dict()`` (or a torch.optim.Adam / AdamW over the same parameters) produced.  The flat
+        buffers are filled at the first step after the load (they need the gradient bucket's layout)."""
+        super().load_state_dict(state_dict)
+        self._pending_state = {p: dict(st) for p, st in self.state.items() if st}
+        if self.flat_param is not None:
+            self._apply_pending_state()
+
+    def _apply_pending_state(self):
+        pend = getattr(self, "_pending_state", None)
+        if not pend:
+            return
+        b = self.bucket
+        base = self.flat_param.data_ptr()
+        steps = []
+        for p in b.active:
+            st = pend.get(p)
+            if st is None:
+                continue
+            off = (p.data_ptr() - base) // 4
+            sl = slice(off, off + p.numel())
+            self.exp_avg[sl].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[sl].copy_(st["exp_avg_sq"].reshape(-1))
+            if self.max_exp_avg_sq is not None and "max_exp_avg_sq" in st:
+                self.max_exp_avg_sq[sl].copy_(st["max_exp_avg_sq"].reshape(-1))
+            steps.append(float(st["step"]))
+        if steps:
+            self._step.fill_(max(steps))
+        self._pending_state = None

@@ -112,6 +112,47 @@ def test_flat_adam_matches_torch(kw):
         assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max().clamp_min(1.0)), (a - b).abs().max()
 
 
+def test_flat_adam_checkpoint_resume():
+    """state_dict() / load_state_dict(): 3 steps, checkpoint, 3 more steps == 6 uninterrupted steps, both when the
+    checkpoint is loaded into a fresh FlatAdam (before its first backward) and into torch.optim.AdamW's format."""
+    from dummynode4graphlearning_b200.optim import FlatAdam
+    dev = torch.device("cuda:0")
+    shapes = [(16, 5), (16,), (7, 9)]
+    torch.manual_seed(11)
+    init = [torch.randn(s, device=dev) for s in shapes]
+    grads = [[torch.randn(s, device=dev) for s in shapes] for _ in range(6)]
+    kw = dict(lr=0.01, weight_decay=0.01, amsgrad=True, decoupled_weight_decay=True)
+
+    def run(params, opt, steps):
+        for gs in steps:
+            opt.zero_grad()
+            for p, g in zip(params, gs):
+                p.grad = g.clone()
+            opt.step()
+
+    full = [torch.nn.Parameter(t.clone()) for t in init]
+    run(full, FlatAdam(full, **kw), grads)
+    a = [torch.nn.Parameter(t.clone()) for t in init]
+    oa = FlatAdam(a, **kw)
+    run(a, oa, grads[:3])
+    sd = oa.state_dict()
+    assert len(sd["state"]) == 3 and all(float(st["step"]) == 3.0 for st in sd["state"].values())
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    ob = FlatAdam(b, **kw)
+    ob.load_state_dict(sd)
+    run(b, ob, grads[3:])
+    assert ob.num_steps == 6
+    for x, y in zip(full, b):
+        assert torch.equal(x.detach(), y.detach())
+    # the same checkpoint drives torch's own AdamW (format compatibility)
+    c = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    oc = torch.optim.AdamW(c, lr=0.01, weight_decay=0.01, amsgrad=True, foreach=False)
+    oc.load_state_dict(sd)
+    run(c, oc, grads[3:])
+    for x, y in zip(full, c):
+        assert float((x.detach() - y.detach()).abs().max()) <= 2e-6 * float(x.detach().abs().max().clamp_min(1.0))
+
+
 def test_flat_adam_pipeline_eager_vs_graph_vs_torch():
     """the C2-style train step with FlatAdam: CUDA-graph replay == eager, and both track torch.optim.Adam."""
     from dummynode4graphlearning_b200 import synth, transforms as T
