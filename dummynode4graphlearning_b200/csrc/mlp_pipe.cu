@@ -213,7 +213,8 @@ lin_fwd_pipe_kernel(const LinFwdArgs a, const BnFinalArgs f, int *__restrict__ c
     for (int i = t; i < MP * (KP / 4); i += C::NT) {
         const int m = i / (KP / 4), c = i % (KP / 4);
         float4 v = zero4();
-        if (m < a.M && 4 * c < a.K) v = __ldg(reinterpret_cast<const float4 *>(a.W + static_cast<size_t>(m) * a.K + 4 * c));
+        if (m < a.M && 4 * c < a.K)
+            v = a.x_direct ? load_chunk(a.W, m, a.K, c, false) : __ldg(reinterpret_cast<const float4 *>(a.W + static_cast<size_t>(m) * a.K + 4 * c));
         store_split(sB, sB, 0, v, tile_off(m, c, 2 * MP), tile_off(MP + m, c, 2 * MP));
     }
     for (int i = t; i < MP; i += C::NT) bias_sm[i] = (a.bias != nullptr && i < a.M) ? __ldg(a.bias + i) : 0.f;
@@ -235,8 +236,12 @@ lin_fwd_pipe_kernel(const LinFwdArgs a, const BnFinalArgs f, int *__restrict__ c
                 const int64_t row0 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(j) * gridDim.x) * 128;
                 const int64_t left = a.N - row0;
                 const uint32_t bytes = static_cast<uint32_t>((left < 128 ? left : 128) * a.K * 4);
-                mbar_expect_tx(raw_full(s), bytes);
-                bulk_g2s(sRaw + s * C::RAW_BYTES, a.X + row0 * a.K, bytes, raw_full(s));
+                if (a.x_direct) {                      // the converters load X themselves: just hand the slot over
+                    mbar_arrive(raw_full(s));
+                } else {
+                    mbar_expect_tx(raw_full(s), bytes);
+                    bulk_g2s(sRaw + s * C::RAW_BYTES, a.X + row0 * a.K, bytes, raw_full(s));
+                }
             }
             TL_DONE(0);
         }
@@ -290,8 +295,17 @@ lin_fwd_pipe_kernel(const LinFwdArgs a, const BnFinalArgs f, int *__restrict__ c
                 const uint32_t src = sRaw + s * C::RAW_BYTES + static_cast<uint32_t>(r_in) * rpitch + c_in * 16;
                 const uint32_t sAh = sA + b * 2 * C::A_BYTES;
                 float4 v[128 / RP];
+                if (a.x_direct) {                          // K % 4 != 0 or unaligned X: bounds-checked global loads
+                    const int64_t row0 = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(j) * gridDim.x) * 128;
 #pragma unroll
-                for (int i = 0; i < 128 / RP; ++i) v[i] = col_ok ? lds128s(src + static_cast<uint32_t>(RP * i) * rpitch) : zero4();
+                    for (int i = 0; i < 128 / RP; ++i) {
+                        const int64_t gr = row0 + r_in + RP * i;
+                        v[i] = (col_ok && gr < a.N) ? load_chunk(a.X, gr, a.K, c_in, false) : zero4();
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128 / RP; ++i) v[i] = col_ok ? lds128s(src + static_cast<uint32_t>(RP * i) * rpitch) : zero4();
+                }
 #pragma unroll
                 for (int i = 0; i < 128 / RP; ++i) {
                     if (BN) v[i] = bn_apply(v[i], bi);
@@ -637,9 +651,13 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
                 const int64_t row0 = tile_row0(j), left = a.N - row0;
                 const uint32_t rows = static_cast<uint32_t>(left < 128 ? left : 128);
                 const uint32_t xb = rows * a.K * 4u, sb = has_seg ? ((rows * 4u + 15u) & ~15u) : 0u;
-                mbar_expect_tx(raw_full(s), xb + sb);
-                bulk_g2s(sRaw + s * C::RAW_SLOT, a.X + row0 * a.K, xb, raw_full(s));
-                if (has_seg) bulk_g2s(sRaw + s * C::RAW_SLOT + C::RAW_X, a.row2seg + row0, sb, raw_full(s));
+                if (a.x_direct && !has_seg) {
+                    mbar_arrive(raw_full(s));              // nothing to stage: the converters load X themselves
+                } else {
+                    mbar_expect_tx(raw_full(s), (a.x_direct ? 0u : xb) + sb);
+                    if (!a.x_direct) bulk_g2s(sRaw + s * C::RAW_SLOT, a.X + row0 * a.K, xb, raw_full(s));
+                    if (has_seg) bulk_g2s(sRaw + s * C::RAW_SLOT + C::RAW_X, a.row2seg + row0, sb, raw_full(s));
+                }
                 // G and Yout are read by the converters with plain loads one tile ahead: pull their slabs into L2 early
                 // (TMA L2 prefetch), so that those loads see L2 latency instead of a loaded HBM queue
                 if (j + 2 < my_tiles) {
@@ -766,7 +784,7 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
                 const int r = r_k + RPk * i;
                 float4 v = zero4();
                 if (r < valid && colk_ok) {
-                    v = lds128s(slab + static_cast<uint32_t>(r) * rpitch + c_k * 16);
+                    v = a.x_direct ? load_chunk(a.X, row0 + r, a.K, c_k, false) : lds128s(slab + static_cast<uint32_t>(r) * rpitch + c_k * 16);
                     if (has_bn_in) v = bn_apply(v, bi);
                     v.x = act_f(v.x, in_act, in_slope); v.y = act_f(v.y, in_act, in_slope);
                     v.z = act_f(v.z, in_act, in_slope); v.w = act_f(v.w, in_act, in_slope);
@@ -1072,6 +1090,7 @@ size_t dn4gl_pipe_lin_bwd_ws_bytes(int K, int M) {
 // K % 4 == 0, M % 4 == 0, all matrices 16-byte aligned, counters zero on entry (left zero), ws >= the size above.
 int dn4gl_pipe_lin_bwd(LinBwdArgs a, float *dW, float *db, float *sums_prev, void *ws, int *counters, cudaStream_t s) {
     if (a.K > 64 || a.M > 64) return 0;
+    if (a.x_direct && a.GX != nullptr) return 0;      // the mask pass of the data gradient reads the staged X slab
     const int KP = a.K <= 32 ? 32 : 64, MP = a.M <= 32 ? 32 : 64;
     if (KP == 64 || MP == 64) return 0;          // 64-wide shapes: operand tiles alone exceed one CTA's shared memory (mlp_tc.cu path)
     const size_t P = static_cast<size_t>(bwd_pipe_part_floats(KP, MP));

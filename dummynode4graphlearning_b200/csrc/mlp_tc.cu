@@ -993,7 +993,8 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
     // warp-specialised pipeline (mlp_pipe.cu) whenever the slabs are 16-byte granular; it also merges the batch statistics
     // in its last CTA (no bn_finalize launch).  DN4GL_LIN_SERIAL=1 keeps the phase-serial kernels (A/B, debugging).
     static const bool serial_only = getenv("DN4GL_LIN_SERIAL") != nullptr;
-    if (!serial_only && ring_ok && (M % 4 == 0) && aligned16(Y) && aligned16(W) && (bn_out == nullptr || counters != nullptr)) {
+    if (!serial_only && (M % 4 == 0) && aligned16(Y) && (bn_out == nullptr || counters != nullptr)) {
+        a.x_direct = (ring_ok && aligned16(W)) ? 0 : 1;     // e.g. the 2-feature first layer: X / W through bounds-checked loads
         BnFinalArgs f;
         f.gamma = gamma; f.beta = beta; f.eps = eps; f.momentum = momentum; f.bn_out = bn_out;
         f.run_mean = running_mean; f.run_var = running_var; f.nbt = reinterpret_cast<long long *>(num_batches_tracked);
@@ -1048,8 +1049,11 @@ int dn4gl_lin_bwd_f32(const float *G, const float *Gseg, const int32_t *row2seg,
     int rc = 0, grid = 0;
     // warp-specialised pipeline with last-finisher merges (mlp_pipe.cu): no lin_bwd_reduce launch
     static const bool serial_only = getenv("DN4GL_LIN_SERIAL") != nullptr;
-    if (!serial_only && ring_ok && counters != nullptr && aligned16(W) && (GX == nullptr || aligned16(GX)) &&
+    const bool gy_ok = (M % 4 == 0) && (G == nullptr || aligned16(G)) && (Yout == nullptr || aligned16(Yout));
+    const bool x_ok = (K % 4 == 0) && aligned16(X) && aligned16(W);
+    if (!serial_only && gy_ok && counters != nullptr && (x_ok || GX == nullptr) && (GX == nullptr || aligned16(GX)) &&
         (Gseg == nullptr || (aligned16(Gseg) && aligned16(row2seg)))) {
+        a.x_direct = x_ok ? 0 : 1;
         const int g = dn4gl_pipe_lin_bwd(a, dW, db, sums_prev, ws, counters, s);
         if (g < 0) { dn4gl_set_error("dn4gl_lin_bwd_f32: launch configuration of the pipelined kernel failed"); return DN4GL_ECUDA; }
         if (g > 0) { DN_LAUNCHED(); return DN4GL_OK; }

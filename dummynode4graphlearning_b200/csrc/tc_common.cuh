@@ -13,6 +13,7 @@ struct LinFwdArgs {
     int stats;
     float *part;
     int num_tiles;
+    int x_direct = 0;      // pipelined kernels: read X with plain (bounds-checked) global loads instead of bulk slabs (K % 4 != 0 or unaligned)
 };
 struct LinBwdArgs {
     const float *G; const float *Gseg; const int32_t *row2seg; const float *Yo; int64_t N; int M;
@@ -22,6 +23,7 @@ struct LinBwdArgs {
     float *GX;
     float *part;
     int num_tiles;
+    int x_direct = 0;      // as in LinFwdArgs (only without a data gradient: the epilogue's mask pass reads the staged X slab)
 };
 
 // BatchNorm finalisation parameters of a forward stage (training-mode nn.BatchNorm1d semantics)

@@ -56,7 +56,7 @@ class CSR:
     """row_ptr[n_rows+1], col[nnz], eid[nnz] (all int32, device) + the heavy-row list."""
 
     __slots__ = ("row_ptr", "col", "eid", "n_rows", "nnz", "heavy_rows", "heavy_count", "heavy_thr", "seg_ptr",
-                 "max_seg", "_tiles")
+                 "max_seg", "_tiles", "block_diagonal")
 
     def __init__(self, row_ptr, col, eid, n_rows, nnz):
         self.row_ptr, self.col, self.eid, self.n_rows, self.nnz = row_ptr, col, eid, n_rows, nnz
@@ -64,6 +64,7 @@ class CSR:
         self.heavy_thr = 0
         self.seg_ptr = None   # per-graph row offsets when rows AND columns are block-diagonal over the same graphs
         self.max_seg = None   # rows of the largest graph if the host knows it (lets every tile be graph-aligned)
+        self.block_diagonal = False   # True: built graph by graph over seg_ptr (the tiling skips its column verification)
         self._tiles = {}
 
     def tiles(self, D, smem_bytes=None):
@@ -107,7 +108,7 @@ class CSR:
             heavy_list = torch.empty(heavy_cap, dtype=torch.int32, device=dev)
             heavy_count = torch.empty(1, dtype=torch.int32, device=dev)   # zeroed by dn4gl_make_row_tiles
         L.call("dn4gl_make_row_tiles", ptr(self.seg_ptr), int(self.seg_ptr.numel()) - 1, window, ptr(self.row_ptr),
-               ptr(self.col), self.n_rows, ptr(desc), T, ptr(heavy_list), heavy_cap, ptr(heavy_count), _stream())
+               None if self.block_diagonal else ptr(self.col), self.n_rows, ptr(desc), T, ptr(heavy_list), heavy_cap, ptr(heavy_count), _stream())
         cfg = dict(desc=desc, T=T, heavy_list=heavy_list, heavy_count=heavy_count, heavy_cap=heavy_cap,
                    smem=smem_bytes, stages=stages, npr=npr, window=window, cap_rows=cap, warps=warps)
         self._tiles[key] = cfg

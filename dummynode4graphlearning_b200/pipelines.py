@@ -82,7 +82,7 @@ def _static_clone(data):
         c = CSR(c0.row_ptr.clone(), c0.col.clone(), None, c0.n_rows, c0.nnz)
         c.heavy_rows = None if c0.heavy_rows is None else c0.heavy_rows.clone()
         c.heavy_count = None if c0.heavy_count is None else c0.heavy_count.clone()
-        c.heavy_thr, c.seg_ptr, c.max_seg = c0.heavy_thr, s.node_ptr, c0.max_seg
+        c.heavy_thr, c.seg_ptr, c.max_seg, c.block_diagonal = c0.heavy_thr, s.node_ptr, c0.max_seg, c0.block_diagonal
         for key, t in c0._tiles.items():
             c._tiles[key] = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in t.items()}
         setattr(s, name, c)

@@ -216,7 +216,7 @@ def tu_conj_structure(b, num_node_labels, node_label_min=0):
         hcap = cap // HEAVY_THRESHOLD + 1
         c.heavy_rows, c.heavy_count, c.heavy_thr = _empty_i32(hcap, dev), _empty_i32(1, dev), HEAVY_THRESHOLD
         L.call("dn4gl_collect_heavy_rows", ptr(rp), V, HEAVY_THRESHOLD, ptr(c.heavy_rows), hcap, ptr(c.heavy_count), _stream())
-        c.seg_ptr, c.max_seg = node_ptr, int(max_nodes)
+        c.seg_ptr, c.max_seg, c.block_diagonal = node_ptr, int(max_nodes), True
         csrs.append(c)
     x = (vlabel.view(-1, 1) == torch.arange(int(node_label_min), int(node_label_min) + int(num_node_labels),
                                             dtype=vlabel.dtype, device=dev)).to(torch.float32)

@@ -291,7 +291,9 @@ int dn4gl_spmm_sum_f32(const int32_t *row_ptr, const int32_t *col, const float *
  *   ceil(N / window_rows); window_rows <= cap_rows - (largest graph) keeps every tile inside one stage (cap_rows / 2
  *   is always safe).  heavy_list[heavy_cap] / heavy_count[1] (optional, both or neither): rows with more than 64
  *   neighbours inside tiles that had to cut a graph longer than the window; the kernel reduces them CTA-wide.
- *   heavy_cap >= E / 64 + 1.  The tiling must be rebuilt when row_ptr / col change.
+ *   heavy_cap >= E / 64 + 1.  The tiling must be rebuilt when row_ptr / col change.  col may be NULL: the caller vouches
+ *   that every column of a graph's rows lies inside that graph (block-diagonal by construction, e.g. the output of
+ *   dn4gl_tu_conj_direct_fill) and the per-tile verification pass is skipped.
  * dn4gl_spmm_tiled_f32: smem_bytes = dynamic shared memory per CTA (16 KiB .. 220 KiB; <= 110 KiB lets two CTAs share
  *   an SM for D <= 128), stages in 1..4, nnz_per_row = col slots staged per row (about ceil(E/N) + 1), warps = 16, 24
  *   or 32 per CTA (one producer + 15 / 23 / 31 consumers; more than 16 only applies to D <= 128).  Tiles whose columns were verified to
