@@ -497,6 +497,22 @@ def ours(a):
     final_loss = float(loss.item())      # read NOW: `loss` is the captured step's static buffer, later steps overwrite it
     m1 = nmalloc()
     ms = max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
+    # what the in-loop L2 flush costs: the same K steps without it, and K flushes alone (informational -- `value` and
+    # `ms_per_step` above are the flushed loop, flush included)
+    ex0, ex1, ex2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    barrier()
+    ex0.record()
+    for _ in range(a.steps):
+        pipe.step_resident(dev_batch, assume_ready=True)
+    ex1.record()
+    for _ in range(a.steps):
+        flush.fill_(1)
+    ex2.record()
+    barrier()
+    l2_flush = {"flush_alone_ms_per_step": ex1.elapsed_time(ex2) / a.steps,
+                "ms_per_step_without_flush": max_over_ranks(ex0.elapsed_time(ex1), dev) / a.steps,
+                "note": "ms_per_step / value are measured WITH the 192 MiB flush write inside the timed loop on the train "
+                        "stream; these two figures say how much of the step it is"}
     value = a.graphs * world / (ms * 1e-3)
     if trace:
         print("host ms per step:", " ".join("%.2f" % (1e3 * (b - a_)) for a_, b in zip(trace[:-1], trace[1:])), file=sys.stderr)
@@ -861,7 +877,7 @@ def ours(a):
                        "(transforms.tu_conjugate_sizes_ex of the raw host batch: V', E', largest graph, 'every graph has a node', "
                        "'edges sorted by source'): no device->host read inside a step, the CONJ_ CSR pair is written in closed "
                        "form (dn4gl_tu_conj_direct_*) and the whole transform replays as a CUDA graph"} if a.size_hints else {})),
-        "clocks": clk, "gpu_launches": launches,
+        "clocks": clk, "gpu_launches": launches, "l2_flush": l2_flush,
         "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": host_bytes(host), "d2h_bytes_per_step": 4 + 8 + 4,
                 "how": "ClassificationPipeline.step_async(host) per step, loss of step k-1 read on the host after step k "

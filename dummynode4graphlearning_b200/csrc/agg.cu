@@ -473,3 +473,192 @@ extern "C" int dn4gl_nll_mean_bwd_f32(const float *g, const int64_t *y, int32_t 
     DN_LAUNCHED();
     return DN4GL_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Jumping-knowledge class head of the GIN classifier (gconv.py:205-214): the scores are the sum over layers of
+// Linear_l(pooled_l) followed by log_softmax.  As torch ops this was two concatenations, a stack, a small GEMM, five
+// elementwise kernels and log_softmax forward, and the mirror image backward (slices of the concatenation gradient
+// copied out one by one): ~25 launches of 2-3 us in a train step bound by launch count.  Here: one kernel each way.
+//   score[b, c] = sum_l sum_d pooled_l[b, d] W_l[c, d] + n_b bias_0[c] + sum_{l >= 1} bias_l[c]
+// n_b = rows of graph b when seg_ptr is given (sum pooling: the reference pools Linear_0(h), so bias_0 is counted once
+// per pooled row), 1 otherwise.
+constexpr int JK_MAX_LAYERS = 16;
+struct JkHeadPtrs {
+    const float *pooled[JK_MAX_LAYERS];
+    const float *W[JK_MAX_LAYERS];
+    const float *bias[JK_MAX_LAYERS];
+    float *g_pooled[JK_MAX_LAYERS];
+    float *dW[JK_MAX_LAYERS];
+    float *db[JK_MAX_LAYERS];
+};
+
+// one warp per graph; lane c ends up with score[b, c] (C <= 32)
+__global__ void __launch_bounds__(256) jk_head_fwd_kernel(JkHeadPtrs p, int L, int B, int D, int C,
+                                                         const int32_t *__restrict__ seg_ptr, float *__restrict__ logp) {
+    DN_PDL_WAIT();
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    float mine = 0.f;
+    for (int c = 0; c < C; ++c) {
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) {
+            const float *x = p.pooled[l] + static_cast<int64_t>(b) * D, *w = p.W[l] + static_cast<int64_t>(c) * D;
+            for (int d = lane; d < D; d += 32) s = fmaf(__ldg(x + d), __ldg(w + d), s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == c) mine = s;
+    }
+    if (lane < C) {
+        float rest = 0.f;
+        for (int l = 1; l < L; ++l) rest += __ldg(p.bias[l] + lane);
+        const float n = seg_ptr ? static_cast<float>(seg_ptr[b + 1] - seg_ptr[b]) : 1.f;
+        mine += n * __ldg(p.bias[0] + lane) + rest;
+    }
+    float m = lane < C ? mine : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float e = lane < C ? expf(mine - m) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if (lane < C) logp[static_cast<int64_t>(b) * C + lane] = mine - m - logf(e);
+}
+
+// Backward.  Each CTA owns a contiguous range of graphs and walks it JK_ROWS graphs at a time: the pooled rows and the
+// score gradient gs = g - exp(logp) * rowsum(g) of those graphs are staged in shared memory (one round of independent
+// loads), g_pooled_l = gs W_l is written, and the weight / bias gradients accumulate in shared memory (entry q of acc is
+// owned by thread q mod 256: no atomics, fixed order).  The last CTA to finish (ticket) merges the per-CTA partials:
+// one warp per entry, lanes over CTAs, butterfly sum -- a fixed tree.
+constexpr int JK_ROWS = 8;
+__global__ void __launch_bounds__(256) jk_head_bwd_kernel(JkHeadPtrs p, int L, int B, int D, int C,
+                                                         const int32_t *__restrict__ seg_ptr, const float *__restrict__ g_logp,
+                                                         const float *__restrict__ logp, float *__restrict__ part,
+                                                         int *counter) {
+    DN_PDL_WAIT();
+    extern __shared__ float jk_smem[];
+    __shared__ int is_last;
+    const int LD = L * D, NW = C * LD, NACC = NW + 2 * C;      // acc: dW (l, c, d) | sum_b gs[b, c] | sum_b n_b gs[b, c]
+    float *acc = jk_smem, *gs = jk_smem + NACC, *cnt = gs + JK_ROWS * C, *xs = cnt + JK_ROWS;   // xs: JK_ROWS x LD
+    const int t = threadIdx.x;
+    for (int q = t; q < NACC; q += 256) acc[q] = 0.f;
+    const int per = (B + gridDim.x - 1) / gridDim.x;
+    const int r_begin = blockIdx.x * per, r_end = min(B, r_begin + per);
+    for (int r0 = r_begin; r0 < r_end; r0 += JK_ROWS) {
+        const int rows = min(JK_ROWS, r_end - r0);
+        __syncthreads();
+        for (int q = t; q < rows * LD; q += 256) {
+            const int r = q / LD, j = q - r * LD, l = j / D, d = j - l * D;
+            xs[q] = __ldg(p.pooled[l] + static_cast<int64_t>(r0 + r) * D + d);
+        }
+        if (t < rows) {
+            const float *g = g_logp + static_cast<int64_t>(r0 + t) * C, *lp = logp + static_cast<int64_t>(r0 + t) * C;
+            float tot = 0.f;
+            for (int c = 0; c < C; ++c) tot += g[c];
+            for (int c = 0; c < C; ++c) gs[t * C + c] = g[c] - expf(lp[c]) * tot;
+            cnt[t] = seg_ptr ? static_cast<float>(seg_ptr[r0 + t + 1] - seg_ptr[r0 + t]) : 1.f;
+        }
+        __syncthreads();
+        for (int q = t; q < rows * LD; q += 256) {             // g_pooled_l[b, d] = sum_c gs[b, c] W_l[c, d]
+            const int r = q / LD, j = q - r * LD, l = j / D, d = j - l * D;
+            float s = 0.f;
+            for (int c = 0; c < C; ++c) s = fmaf(gs[r * C + c], __ldg(p.W[l] + static_cast<int64_t>(c) * D + d), s);
+            p.g_pooled[l][static_cast<int64_t>(r0 + r) * D + d] = s;
+        }
+        for (int q = t; q < NW; q += 256) {                    // dW_l[c, d] += sum_b gs[b, c] pooled_l[b, d]
+            const int l = q / (C * D), rem = q - l * C * D, c = rem / D, d = rem - c * D;
+            const float *x = xs + l * D + d;
+            float s = acc[q];
+            for (int r = 0; r < rows; ++r) s = fmaf(gs[r * C + c], x[r * LD], s);
+            acc[q] = s;
+        }
+        if (t < 2 * C) {
+            const int c = t < C ? t : t - C;
+            float s = acc[NW + t];
+            for (int r = 0; r < rows; ++r) s += (t < C ? 1.f : cnt[r]) * gs[r * C + c];
+            acc[NW + t] = s;
+        }
+    }
+    __syncthreads();
+    float *mine = part + static_cast<int64_t>(blockIdx.x) * NACC;
+    for (int q = t; q < NACC; q += 256) mine[q] = acc[q];
+    __threadfence();
+    __syncthreads();
+    if (t == 0) is_last = (atomicAdd(counter, 1) == static_cast<int>(gridDim.x) - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int G = gridDim.x, lane = t & 31;
+    for (int q = t >> 5; q < NACC; q += 8) {
+        float s = 0.f;
+        for (int k = lane; k < G; k += 32) s += __ldcg(part + static_cast<int64_t>(k) * NACC + q);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane != 0) continue;
+        if (q < NW) {
+            const int l = q / (C * D);
+            p.dW[l][q - l * C * D] = s;
+        } else {
+            const int u = q - NW, c = u < C ? u : u - C;
+            if (u < C) {                                       // plain sum: every layer but the first
+                for (int l = 1; l < L; ++l) p.db[l][c] = s;
+                if (!seg_ptr) p.db[0][c] = s;
+            } else if (seg_ptr) {
+                p.db[0][c] = s;
+            }
+        }
+    }
+    if (t == 0) *counter = 0;
+}
+
+static inline int jk_grid(int B) {
+    const int want = (B + JK_ROWS - 1) / JK_ROWS;
+    const int cap = dn4gl_num_sms();
+    return want < 1 ? 1 : (want > cap ? cap : want);
+}
+
+static inline size_t jk_bwd_smem(int L, int D, int C) {
+    return (static_cast<size_t>(C) * L * D + 2 * C + JK_ROWS * C + JK_ROWS + static_cast<size_t>(JK_ROWS) * L * D) * sizeof(float);
+}
+
+extern "C" size_t dn4gl_jk_head_workspace_bytes(int32_t L, int32_t B, int32_t D, int32_t C) {
+    return static_cast<size_t>(jk_grid(B)) * (static_cast<size_t>(C) * L * D + 2 * C) * sizeof(float);
+}
+
+static bool jk_fill(JkHeadPtrs &p, int L, const float *const *pooled, const float *const *W, const float *const *bias) {
+    for (int l = 0; l < L; ++l) {
+        if (!pooled[l] || !W[l] || !bias[l]) return false;
+        p.pooled[l] = pooled[l]; p.W[l] = W[l]; p.bias[l] = bias[l];
+    }
+    return true;
+}
+
+extern "C" int dn4gl_jk_head_fwd_f32(const float *const *pooled, const float *const *W, const float *const *bias, int32_t L,
+                                     int32_t B, int32_t D, int32_t C, const int32_t *seg_ptr, float *logp, void *stream) {
+    DN_ARG(L >= 1 && L <= JK_MAX_LAYERS && B >= 0 && D >= 1 && C >= 1 && C <= 32 && pooled && W && bias);
+    if (B == 0) return DN4GL_OK;
+    JkHeadPtrs p = {};
+    DN_ARG(jk_fill(p, L, pooled, W, bias) && logp != nullptr);
+    DN_LAUNCH(jk_head_fwd_kernel, (B + 7) / 8, 256, 0, as_stream(stream), p, L, B, D, C, seg_ptr, logp);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+extern "C" int dn4gl_jk_head_bwd_f32(const float *g_logp, const float *logp, const float *const *pooled, const float *const *W,
+                                     int32_t L, int32_t B, int32_t D, int32_t C, const int32_t *seg_ptr,
+                                     float *const *g_pooled, float *const *dW, float *const *db, void *ws, size_t ws_bytes,
+                                     int32_t *counter, void *stream) {
+    DN_ARG(L >= 1 && L <= JK_MAX_LAYERS && B >= 1 && D >= 1 && C >= 1 && C <= 32 && pooled && W && g_pooled && dW && db);
+    DN_ARG(g_logp && logp && ws && counter && ws_bytes >= dn4gl_jk_head_workspace_bytes(L, B, D, C));
+    const size_t smem = jk_bwd_smem(L, D, C);
+    DN_ARG(smem <= 48 * 1024);
+    JkHeadPtrs p = {};
+    for (int l = 0; l < L; ++l) {
+        DN_ARG(pooled[l] && W[l] && g_pooled[l] && dW[l] && db[l]);
+        p.pooled[l] = pooled[l]; p.W[l] = W[l]; p.g_pooled[l] = g_pooled[l]; p.dW[l] = dW[l]; p.db[l] = db[l];
+    }
+    DN_LAUNCH(jk_head_bwd_kernel, jk_grid(B), 256, smem, as_stream(stream), p, L, B, D, C, seg_ptr, g_logp, logp,
+              static_cast<float *>(ws), counter);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}

@@ -88,6 +88,48 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 #define TL_DONE(role) do { } while (0)
 #endif
 
+// ---- grid rendezvous of the persistent stage kernels (grid <= number of SMs, one CTA per SM, launched COOPERATIVELY so
+// that every CTA is resident: launch_coop below).  The merges of the per-CTA partials used to be done by the last CTA to
+// finish (one ticket level forward, two backward): 4.1 us / 7.4 us between the last CTA leaving its tile loop and the
+// kernel's end (profiles/r2z_pipe_timeline.txt), a fifth of the backward stage.  Now every CTA arrives once its
+// partials are written, and the merge is SPREAD over the CTAs -- each takes a few output entries, a warp per entry, the
+// lanes over the partials: one round of loads per entry instead of two serial merge levels.
+//   grid_arrive: all threads' earlier global stores are published, the CTA is counted; merging CTAs wait for all G.
+//   grid_depart: the last merging CTA to leave puts both counters back to zero for the next launch.
+// The wait is bounded: a grid that never completes (a launch that was not cooperative after all) traps instead of
+// hanging the device.
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void grid_arrive(int *arrive, int G, bool wait) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(arrive, 1);
+        if (wait) {
+            unsigned spins = 0;
+            while (ld_acquire_gpu(arrive) < G)
+                if (++spins > (1u << 25)) __trap();
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void grid_depart(int *arrive, int *depart, int mergers) {
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(depart, 1) == mergers - 1) {
+        *depart = 0;
+        *arrive = 0;
+    }
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {      // fixed butterfly
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 __device__ __forceinline__ int lds32f_i(uint32_t a) {
     int v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -188,7 +230,6 @@ lin_fwd_pipe_kernel(const LinFwdArgs a, const BnFinalArgs f, int *__restrict__ c
     __shared__ float shift_s[NEPI][MP];
     __shared__ float ncta_s[NEPI];
     __shared__ __align__(16) float bias_sm[MP];
-    __shared__ int is_last;
     const uint32_t bar0 = s_u32(bars);
     auto raw_full = [&](int s) { return bar0 + 8u * s; };
     auto raw_empty = [&](int s) { return bar0 + 8u * (RING + s); };
@@ -447,41 +488,35 @@ lin_fwd_pipe_kernel(const LinFwdArgs a, const BnFinalArgs f, int *__restrict__ c
             }
         }
     }
-    // ---- teardown; with statistics: the last CTA merges the per-CTA partials into the BatchNorm record
+    // ---- teardown; with statistics: grid rendezvous, then CTA b merges channels b, b + G, ... into the BatchNorm record
     tc_fence_before();
-    if (a.stats) __threadfence();
     __syncthreads();
     TL_SPAN(2);
     if (w == C::W_MMA) tc_dealloc(tmem, C::TCOLS);
     if (!a.stats) { TL_SPAN(3); return; }
-    if (t == 0) is_last = (atomicAdd(counter, 1) == static_cast<int>(gridDim.x) - 1) ? 1 : 0;
-    __syncthreads();
-    if (!is_last) { TL_SPAN(3); return; }
-    __threadfence();
+    const int G = static_cast<int>(gridDim.x);
+    const bool merger = static_cast<int>(blockIdx.x) < a.M;
+    grid_arrive(counter, G, merger);
+    if (!merger) { TL_SPAN(3); return; }
     {
-        // thread (c, g): channel c, partial group g; every partial is re-centred on the mean of CTA 0 (exact in double),
-        // so the merge is a plain fixed-order sum and cancellation-free (same arithmetic as round 1's bn_finalize_kernel)
-        constexpr int G = C::NT / MP;
-        double *dsm = reinterpret_cast<double *>(smem_raw + (((base - s_u32(smem_raw)) + C::OFF_RAW + 15u) & ~15u));   // ring is idle now
-        const int nparts = static_cast<int>(gridDim.x);
-        const int c = t % MP, g = t / MP;
+        // one warp per channel, lanes over the per-CTA partials {n, a, S1 = sum (y - a), S2 = sum (y - a)^2}.  Every partial
+        // is re-centred on K* = the mean of CTA 0's rows (exact in double): with d = a - K*,
+        //   sum (y - K*) = S1 + n d,   sum (y - K*)^2 = S2 + d (2 S1 + n d),
+        // so T2 - T1^2 / N has no cancellation to speak of.  Lane l adds partials l, l + 32, ... in that order, then a
+        // fixed butterfly over the lanes: a fixed summation tree, double arithmetic, no divisions in the loop.
         const float4 *part = reinterpret_cast<const float4 *>(a.part);
-        // T1 = sum (y - K*), T2 = sum (y - K*)^2 over all rows, from the per-CTA shifted sums {n, a, S1 = sum (y - a),
-        // S2 = sum (y - a)^2}: with d = a - K*,  sum (y - K*) = S1 + n d  and  sum (y - K*)^2 = S2 + d (2 S1 + n d).
-        // K* = mean of CTA 0's rows, so T2 - T1^2 / N has no cancellation to speak of; double arithmetic, no divisions
-        // in the loop (the per-partial double divisions of the first version cost 3-5 us of tail).
-        double A1 = 0.0, A2 = 0.0;
-        if (g < G) {
+        for (int c = static_cast<int>(blockIdx.x) + G * w; c < a.M; c += G * (C::NT / 32)) {
             const float4 p0 = __ldcg(part + c);
-            const double kstar = static_cast<double>(p0.y) + static_cast<double>(p0.z) / static_cast<double>(p0.x);
-            constexpr int UNR = 8;
-            for (int q0 = g; q0 < nparts; q0 += G * UNR) {
+            double A1 = 0.0, A2 = 0.0, kstar = 0.0;
+            constexpr int UNR = 5;      // 5 x 32 lanes >= 148 CTAs: one round of loads
+            for (int q0 = 0; q0 < G; q0 += 32 * UNR) {
                 float4 v[UNR];
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) {
-                    const int p = q0 + G * u;
-                    v[u] = (p < nparts) ? __ldcg(part + static_cast<size_t>(p) * MP + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int q = q0 + lane + 32 * u;
+                    v[u] = (q < G) ? __ldcg(part + static_cast<size_t>(q) * MP + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                if (q0 == 0) kstar = static_cast<double>(p0.y) + static_cast<double>(p0.z) / static_cast<double>(p0.x);
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) {
                     const double n = v[u].x, s1 = v[u].z, s2 = v[u].w;
@@ -492,39 +527,49 @@ lin_fwd_pipe_kernel(const LinFwdArgs a, const BnFinalArgs f, int *__restrict__ c
                     }
                 }
             }
-            dsm[(2 * g) * MP + c] = A1;
-            dsm[(2 * g + 1) * MP + c] = A2;
-        }
-        __syncthreads();
-        if (t < MP && t < a.M) {
-            double a1 = 0.0, a2 = 0.0;
-            for (int gg = 0; gg < G; ++gg) { a1 += dsm[(2 * gg) * MP + t]; a2 += dsm[(2 * gg + 1) * MP + t]; }
-            const float4 p0 = __ldcg(part + t);
-            const double ks = static_cast<double>(p0.y) + static_cast<double>(p0.z) / static_cast<double>(p0.x);
-            const double Nd = static_cast<double>(a.N);
-            const double mean = ks + a1 / Nd;
-            double m2 = a2 - a1 * a1 / Nd;
-            if (m2 < 0.0) m2 = 0.0;
-            const double var = m2 / Nd;
-            const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(f.eps)));
-            const float gam = f.gamma ? f.gamma[t] : 1.f, bet = f.beta ? f.beta[t] : 0.f;
-            const int M = a.M;
-            f.bn_out[t] = static_cast<float>(mean);
-            f.bn_out[M + t] = rstd;
-            f.bn_out[2 * M + t] = gam * rstd;
-            f.bn_out[3 * M + t] = bet;
-            if (f.run_mean) f.run_mean[t] = (1.f - f.momentum) * f.run_mean[t] + f.momentum * static_cast<float>(mean);
-            if (f.run_var) {
-                const double unb = a.N > 1 ? m2 / (Nd - 1.0) : var;
-                f.run_var[t] = (1.f - f.momentum) * f.run_var[t] + f.momentum * static_cast<float>(unb);
+            const double a1 = warp_sum_f64(A1), a2 = warp_sum_f64(A2);
+            if (lane == 0) {
+                const double Nd = static_cast<double>(a.N);
+                const double mean = kstar + a1 / Nd;
+                double m2 = a2 - a1 * a1 / Nd;
+                if (m2 < 0.0) m2 = 0.0;
+                const double var = m2 / Nd;
+                const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(f.eps)));
+                const float gam = f.gamma ? f.gamma[c] : 1.f, bet = f.beta ? f.beta[c] : 0.f;
+                const int M = a.M;
+                f.bn_out[c] = static_cast<float>(mean);
+                f.bn_out[M + c] = rstd;
+                f.bn_out[2 * M + c] = gam * rstd;
+                f.bn_out[3 * M + c] = bet;
+                if (f.run_mean) f.run_mean[c] = (1.f - f.momentum) * f.run_mean[c] + f.momentum * static_cast<float>(mean);
+                if (f.run_var) {
+                    const double unb = a.N > 1 ? m2 / (Nd - 1.0) : var;
+                    f.run_var[c] = (1.f - f.momentum) * f.run_var[c] + f.momentum * static_cast<float>(unb);
+                }
             }
         }
-        if (t == 0) {
-            if (f.nbt) *f.nbt += 1;
-            *counter = 0;          // left at zero for the next launch
-        }
+        if (blockIdx.x == 0 && t == 0 && f.nbt) *f.nbt += 1;
+        grid_depart(counter, counter + 1, G < a.M ? G : a.M);
         TL_SPAN(3);
     }
+}
+
+// cooperative launch: the driver places the grid only when ALL its CTAs fit on the device at once (and refuses a grid
+// that never could), which is what the grid rendezvous in the kernels' tails relies on.  Captured into CUDA graphs like
+// any other launch.
+template <typename... P, typename... A>
+static inline cudaError_t launch_coop(void (*kernel)(P...), int grid, int block, size_t smem, cudaStream_t stream, A &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(block));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 
 template <int KP, int MP, int NACC, int NBUF_A, int RING, int NCV, int NEPI, int NACCBUF>
@@ -539,7 +584,12 @@ int launch_fwd_pipe(const LinFwdArgs &a, const BnFinalArgs &f, int *counter, cud
     }
     const int sms = dn4gl_num_sms();
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    DN_LAUNCH((lin_fwd_pipe_kernel<KP, MP, NACC, NBUF_A, RING, NCV, NEPI, NACCBUF>), grid, C::NT, C::SMEM, s, a, f, counter);
+    if (a.stats) {      // the statistics merge rendezvouses the grid: every CTA must be resident
+        if (launch_coop(lin_fwd_pipe_kernel<KP, MP, NACC, NBUF_A, RING, NCV, NEPI, NACCBUF>, grid, C::NT, C::SMEM, s, a, f, counter) != cudaSuccess)
+            return -1;
+    } else {
+        DN_LAUNCH((lin_fwd_pipe_kernel<KP, MP, NACC, NBUF_A, RING, NCV, NEPI, NACCBUF>), grid, C::NT, C::SMEM, s, a, f, counter);
+    }
     return grid;
 }
 
@@ -594,7 +644,6 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
     __shared__ uint32_t tmem_ptr;
     __shared__ float red_db[NCV][MP];
     __shared__ float red_sp[4 * C::NEPI][2 * KP];
-    __shared__ int flag_s;
     const uint32_t bar0 = s_u32(bars);
     auto raw_full = [&](int s) { return bar0 + 8u * s; };
     auto raw_empty = [&](int s) { return bar0 + 8u * (RING + s); };
@@ -957,84 +1006,62 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
             *reinterpret_cast<float4 *>(part + m * KP + 4 * q) = acc;
         }
     }
-    // ---- teardown + two-level last-finisher merge of the per-CTA partials (additions in CTA-index order, double)
+    // ---- teardown + merge of the per-CTA partials {dW, db, sums}: grid rendezvous, then CTA b merges entries
+    // [b per, (b + 1) per) -- a warp per entry, lane l adds partials l, l + 32, ... in that order (double), then a fixed
+    // butterfly over the lanes; small grids (<= 16 CTAs): a thread per entry, partials in CTA order
     tc_fence_before();
     __syncthreads();
     TL_SPAN(2);
     if (w == C::W_MMA) tc_dealloc(tmem, C::TCOLS);
     constexpr int P = bwd_pipe_part_floats(KP, MP);
-    const int G = static_cast<int>(gridDim.x), grp = static_cast<int>(blockIdx.x) / BWD_GROUP, ngrp = (G + BWD_GROUP - 1) / BWD_GROUP;
-    const int g0 = grp * BWD_GROUP, g1 = (g0 + BWD_GROUP < G) ? g0 + BWD_GROUP : G;
-    if (t == 0) {
-        __threadfence();
-        flag_s = (atomicAdd(counters + 1 + grp, 1) == (g1 - g0) - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!flag_s) { TL_SPAN(3); return; }
-    if (t == 0) __threadfence();
-    __syncthreads();
-    {
-        // level 1: this group's partials, CTA-index order, double accumulation; ALL loads of a thread are issued before the
-        // first add (one L2 round trip instead of one per element and pair of partials)
-        constexpr int EPT = (P + C::NT - 1) / C::NT;
-        const float *pbase = reinterpret_cast<const float *>(a.part);
-        float v[EPT][BWD_GROUP];
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const int e = t + i * C::NT;
-#pragma unroll
-            for (int u = 0; u < BWD_GROUP; ++u)
-                v[i][u] = (e < P && g0 + u < g1) ? __ldcg(pbase + static_cast<size_t>(g0 + u) * P + e) : 0.f;
+    const int G = static_cast<int>(gridDim.x);
+    const int per = (P + G - 1) / G, e_begin = static_cast<int>(blockIdx.x) * per, e_end = (e_begin + per < P) ? e_begin + per : P;
+    const bool merger = e_begin < P;
+    grid_arrive(counters, G, merger);
+    if (!merger) { TL_SPAN(3); return; }
+    const float *pbase = reinterpret_cast<const float *>(a.part);
+    auto emit = [&](int e, float r) {
+        if (e < MP * KP) {
+            const int m = e / KP, kk = e % KP;
+            if (dW != nullptr && m < a.M && kk < a.K) dW[m * a.K + kk] = r;
+        } else if (e < MP * KP + MP) {
+            const int m = e - MP * KP;
+            if (db != nullptr && m < a.M) db[m] = r;
+        } else {
+            const int i2 = e - MP * KP - MP, which = i2 / KP, kk = i2 % KP;
+            if (sums_prev != nullptr && kk < a.K) sums_prev[which * a.K + kk] = r;
         }
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const int e = t + i * C::NT;
+    };
+    if (G > 16) {
+        const int lane_ = t & 31;
+        for (int e = e_begin + w; e < e_end; e += C::NT / 32) {
             double acc = 0.0;
+            constexpr int UNR = 5;
+            for (int q0 = 0; q0 < G; q0 += 32 * UNR) {
+                float v[UNR];
 #pragma unroll
-            for (int u = 0; u < BWD_GROUP; ++u) acc += static_cast<double>(v[i][u]);
-            if (e < P) gpart[static_cast<size_t>(grp) * P + e] = static_cast<float>(acc);
-        }
-    }
-    __syncthreads();
-    if (t == 0) {
-        counters[1 + grp] = 0;
-        __threadfence();
-        flag_s = (atomicAdd(counters + 1 + 16, 1) == ngrp - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!flag_s) { TL_SPAN(3); return; }
-    if (t == 0) __threadfence();
-    __syncthreads();
-    {
-        constexpr int EPT = (P + C::NT - 1) / C::NT, MAXG = 16;      // level 2: up to 16 groups (grid <= 192 CTAs)
-        float v[EPT][MAXG];
+                for (int u = 0; u < UNR; ++u) {
+                    const int q = q0 + lane_ + 32 * u;
+                    v[u] = (q < G) ? __ldcg(pbase + static_cast<size_t>(q) * P + e) : 0.f;
+                }
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const int e = t + i * C::NT;
-#pragma unroll
-            for (int u = 0; u < MAXG; ++u) v[i][u] = (e < P && u < ngrp) ? __ldcg(gpart + static_cast<size_t>(u) * P + e) : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const int e = t + i * C::NT;
-            if (e >= P) continue;
-            double acc = 0.0;
-#pragma unroll
-            for (int u = 0; u < MAXG; ++u) acc += static_cast<double>(v[i][u]);
-            const float r = static_cast<float>(acc);
-            if (e < MP * KP) {
-                const int m = e / KP, kk = e % KP;
-                if (dW != nullptr && m < a.M && kk < a.K) dW[m * a.K + kk] = r;
-            } else if (e < MP * KP + MP) {
-                const int m = e - MP * KP;
-                if (db != nullptr && m < a.M) db[m] = r;
-            } else {
-                const int i2 = e - MP * KP - MP, which = i2 / KP, kk = i2 % KP;
-                if (sums_prev != nullptr && kk < a.K) sums_prev[which * a.K + kk] = r;
+                for (int u = 0; u < UNR; ++u) acc += static_cast<double>(v[u]);
             }
+            acc = warp_sum_f64(acc);
+            if (lane_ == 0) emit(e, static_cast<float>(acc));
+        }
+    } else {
+        for (int e = e_begin + t; e < e_end; e += C::NT) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (u < G) ? __ldcg(pbase + static_cast<size_t>(u) * P + e) : 0.f;
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc += static_cast<double>(v[u]);
+            emit(e, static_cast<float>(acc));
         }
     }
-    if (t == 0) counters[1 + 16] = 0;
+    grid_depart(counters, counters + 1, (P + per - 1) / per);
     TL_SPAN(3);
 }
 
@@ -1050,7 +1077,8 @@ int launch_bwd_pipe(const LinBwdArgs &a, float *dW, float *db, float *sums_prev,
     }
     const int sms = dn4gl_num_sms();
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    DN_LAUNCH((lin_bwd_pipe_kernel<KP, MP, RING, NCV, NEPI_>), grid, C::NT, C::SMEM, s, a, dW, db, sums_prev, gpart, counters);
+    if (launch_coop(lin_bwd_pipe_kernel<KP, MP, RING, NCV, NEPI_>, grid, C::NT, C::SMEM, s, a, dW, db, sums_prev, gpart, counters) != cudaSuccess)
+        return -1;
     return grid;
 }
 

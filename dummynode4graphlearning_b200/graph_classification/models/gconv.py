@@ -119,6 +119,11 @@ class GIN(torch.nn.Module):
                     conv = self.convs[layer - 1]
                     x, pooled = ops.gin_layer(conv.nn, x, conv.eps, s.csr_in, s.csr_out, s.node_ptr, s.row2seg, mean)
                 pooled_all.append(pooled)
+            if ops.jk_head_supported(self.no_layers, self.hidden_dim, self.num_classes):
+                # ... and with its log_softmax as one kernel each way (csrc/agg.cu jk_head_*): the concatenations, the GEMM,
+                # the bias arithmetic and -- backward -- the slice copies of the concatenation gradient were ~25 launches
+                return ops.jk_head(pooled_all, [lin.weight for lin in self.linears], [lin.bias for lin in self.linears],
+                                   None if mean else s.node_ptr)
             w_all = torch.cat([lin.weight for lin in self.linears], dim=1)
             score = ops.linear(torch.cat(pooled_all, dim=1), w_all, None)
             bias_rest = torch.stack([lin.bias for lin in self.linears[1:]]).sum(0) if self.no_layers > 1 else 0

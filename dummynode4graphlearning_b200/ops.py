@@ -166,6 +166,65 @@ class _NllMean(torch.autograd.Function):
         return out, None
 
 
+JK_HEAD_MAX_LAYERS, JK_HEAD_MAX_CLASSES = 16, 32
+
+
+def jk_head_supported(L, D, C):
+    """shapes dn4gl_jk_head_{fwd,bwd}_f32 take (include/dn4gl.h)."""
+    return 1 <= L <= JK_HEAD_MAX_LAYERS and 1 <= C <= JK_HEAD_MAX_CLASSES and ((C + 8) * L * D + 10 * C + 8) * 4 <= 48 * 1024
+
+
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class _JkHead(torch.autograd.Function):
+    """log_softmax(sum_l Linear_l(pooled_l)) of the GIN classifier (gconv.py:205-214, dropout 0) as one kernel each way;
+    seg_ptr: sum pooling, layer 0's bias is counted once per pooled row (gconv.py:210)."""
+
+    @staticmethod
+    def forward(ctx, seg_ptr, L, *tensors):
+        pooled = [_f32c(t) for t in tensors[:L]]
+        W = [_f32c(t) for t in tensors[L:2 * L]]
+        bias = [_f32c(t) for t in tensors[2 * L:3 * L]]
+        require_cuda(pooled[0], "pooled rows")
+        B, D = pooled[0].shape
+        C = W[0].size(0)
+        logp = torch.empty((B, C), dtype=torch.float32, device=pooled[0].device)
+        lib().call("dn4gl_jk_head_fwd_f32", _ptr_array(pooled), _ptr_array(W), _ptr_array(bias), L, B, D, C, ptr(seg_ptr),
+                   ptr(logp), _stream())
+        ctx.save_for_backward(logp, *pooled, *W)
+        ctx.seg_ptr, ctx.dims = seg_ptr, (L, B, D, C)
+        return logp
+
+    @staticmethod
+    def backward(ctx, g):
+        L, B, D, C = ctx.dims
+        logp, pooled, W = ctx.saved_tensors[0], ctx.saved_tensors[1:1 + L], ctx.saved_tensors[1 + L:]
+        dev = logp.device
+        g_pooled = torch.empty((L, B, D), dtype=torch.float32, device=dev)
+        dW = torch.empty((L, C, D), dtype=torch.float32, device=dev)
+        db = torch.empty((L, C), dtype=torch.float32, device=dev)
+        if B == 0:
+            g_pooled.zero_(), dW.zero_(), db.zero_()
+        else:
+            lb = lib()
+            wsb = lb.size("dn4gl_jk_head_workspace_bytes", L, B, D, C)
+            ws, counter = _tc_ws(dev, wsb)
+            lb.call("dn4gl_jk_head_bwd_f32", ptr(_f32c(g)), ptr(logp), _ptr_array(pooled), _ptr_array(W), L, B, D, C,
+                    ptr(ctx.seg_ptr), _ptr_array(list(g_pooled)), _ptr_array(list(dW)), _ptr_array(list(db)), ptr(ws), wsb,
+                    ptr(counter), _stream())
+        return (None, None) + tuple(g_pooled) + tuple(dW) + tuple(db)
+
+
+def jk_head(pooled, weights, biases, seg_ptr=None):
+    """log_softmax(sum_l pooled[l] @ weights[l].T + n_b * biases[0] + sum_{l >= 1} biases[l]); n_b = rows of graph b when
+    seg_ptr is given, else 1.  jk_head_supported(L, D, C) must hold."""
+    L = len(pooled)
+    return _JkHead.apply(seg_ptr, L, *pooled, *weights, *biases)
+
+
 def nll_loss(logp, y):
     """mean negative log-likelihood of int64 targets y under row-wise log-probabilities logp (B, C)."""
     if y.dtype != torch.int64:

@@ -326,6 +326,23 @@ int dn4gl_segment_bcast_f32(const int32_t *seg_ptr, const uint8_t *mask, const f
 int dn4gl_nll_mean_f32(const float *logp, const int64_t *y, int32_t B, int32_t C, float *loss, void *stream);
 int dn4gl_nll_mean_bwd_f32(const float *g, const int64_t *y, int32_t B, int32_t C, float *g_logp, void *stream);
 
+/* Jumping-knowledge class head of the GIN classifier, graph_neural_networks/models/gconv.py:205-214 (out += dropout(
+ * Linear_l(pool(h_l))), then log_softmax; dropout p = 0):
+ *   logp = log_softmax_c( sum_l pooled_l W_l^T + n_b bias_0 + sum_{l>=1} bias_l )
+ * pooled / W / bias / g_pooled / dW / db are HOST arrays of L device pointers (pooled_l: B x D, W_l: C x D row-major,
+ * bias_l: C).  seg_ptr (B + 1, the graphs' row ranges) selects the reference's sum-pooling form, where layer 0 pools
+ * Linear_0(h) and its bias is therefore counted n_b = rows-of-graph-b times (gconv.py:210); NULL counts it once (mean
+ * pooling).  L <= 16, C <= 32; _bwd additionally needs ((C + 8) L D + 10 C + 8) * 4 <= 48 KiB of shared memory
+ * (DN4GL_EINVAL otherwise: the host composes the head from library GEMMs instead).  _bwd writes every g_pooled_l,
+ * dW_l, db_l; partial sums are merged in a fixed order by the last CTA (counter: one zeroed int32, left at zero).        */
+size_t dn4gl_jk_head_workspace_bytes(int32_t L, int32_t B, int32_t D, int32_t C);
+int dn4gl_jk_head_fwd_f32(const float *const *pooled, const float *const *W, const float *const *bias, int32_t L,
+                          int32_t B, int32_t D, int32_t C, const int32_t *seg_ptr, float *logp, void *stream);
+int dn4gl_jk_head_bwd_f32(const float *g_logp, const float *logp, const float *const *pooled, const float *const *W,
+                          int32_t L, int32_t B, int32_t D, int32_t C, const int32_t *seg_ptr,
+                          float *const *g_pooled, float *const *dW, float *const *db, void *ws, size_t ws_bytes,
+                          int32_t *counter, void *stream);
+
 /* left-padded dense batchify, replaces split_and_batchify_graph_feats(pre_pad=True)
  * (subgraph_isomorphism/utils/dl.py:51-81): out[b, Lmax-len_b+i, :] = x[seg_ptr[b]+i, :] (0 on
  * pads and on rows with mask[v]=1); inverse gather for the backward.                          */

@@ -220,3 +220,39 @@ def test_nll_mean_matches_torch(device, B, C):
     (go,) = torch.autograd.grad(out * 1.7, z)
     assert abs(float(out) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
     assert float((go - gr).abs().max()) <= 1e-6 * float(gr.abs().max())
+
+
+@pytest.mark.parametrize("B,D,C,L,pool_sum", [(1113, 32, 2, 4, True), (1, 32, 2, 4, True), (37, 64, 6, 2, False),
+                                              (2500, 17, 32, 3, True), (33, 128, 3, 5, False)])
+def test_jk_head_matches_float64_composition(device, B, D, C, L, pool_sum):
+    """dn4gl_jk_head_{fwd,bwd}_f32 == log_softmax(sum_l Linear_l(pooled_l)) with layer 0's bias counted once per pooled row
+    under sum pooling (gconv.py:205-214), evaluated in float64 from the same inputs: log-probabilities, and the gradients
+    of every pooled matrix, weight and bias, within 1e-5 of the largest entry."""
+    from dummynode4graphlearning_b200 import ops
+    assert ops.jk_head_supported(L, D, C)
+    g = torch.Generator().manual_seed(B * 7 + D)
+    mk = lambda *s: torch.randn(*s, generator=g)
+    pooled, Ws, bs = [mk(B, D) * 3 for _ in range(L)], [mk(C, D) * 0.2 for _ in range(L)], [mk(C) for _ in range(L)]
+    lens = torch.randint(1, 60, (B,), generator=g)
+    seg = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]).to(torch.int32)
+    wgt, y = mk(B, C), torch.randint(0, C, (B,), generator=g)
+
+    def run(dtype, dev, head):
+        ps = [t.to(dev, dtype).requires_grad_() for t in pooled]
+        ws = [t.to(dev, dtype).requires_grad_() for t in Ws]
+        bb = [t.to(dev, dtype).requires_grad_() for t in bs]
+        out = head(ps, ws, bb)
+        (out * wgt.to(dev, dtype)).sum().backward()
+        return out.detach().double().cpu(), [t.grad.double().cpu() for t in ps + ws + bb]
+
+    def composed(ps, ws, bb):
+        n = lens.to(ps[0].dtype).unsqueeze(1) if pool_sum else 1.0
+        score = sum(p @ w.t() for p, w in zip(ps, ws)) + n * bb[0] + sum(bb[1:])
+        return torch.log_softmax(score, dim=-1)
+
+    ref, ref_g = run(torch.float64, "cpu", composed)
+    out, out_g = run(torch.float32, device, lambda ps, ws, bb: ops.jk_head(ps, ws, bb, seg.to(device) if pool_sum else None))
+    assert float((out - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+    for a, r in zip(out_g, ref_g):
+        assert a.shape == r.shape
+        assert float((a - r).abs().max()) <= 1e-5 * max(1e-3, float(r.abs().max()))
