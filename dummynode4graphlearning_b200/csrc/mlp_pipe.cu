@@ -88,48 +88,6 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 #define TL_DONE(role) do { } while (0)
 #endif
 
-// ---- grid rendezvous of the persistent stage kernels (grid <= number of SMs, one CTA per SM, launched COOPERATIVELY so
-// that every CTA is resident: launch_coop below).  The merges of the per-CTA partials used to be done by the last CTA to
-// finish (one ticket level forward, two backward): 4.1 us / 7.4 us between the last CTA leaving its tile loop and the
-// kernel's end (profiles/r2z_pipe_timeline.txt), a fifth of the backward stage.  Now every CTA arrives once its
-// partials are written, and the merge is SPREAD over the CTAs -- each takes a few output entries, a warp per entry, the
-// lanes over the partials: one round of loads per entry instead of two serial merge levels.
-//   grid_arrive: all threads' earlier global stores are published, the CTA is counted; merging CTAs wait for all G.
-//   grid_depart: the last merging CTA to leave puts both counters back to zero for the next launch.
-// The wait is bounded: a grid that never completes (a launch that was not cooperative after all) traps instead of
-// hanging the device.
-__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void grid_arrive(int *arrive, int G, bool wait) {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(arrive, 1);
-        if (wait) {
-            unsigned spins = 0;
-            while (ld_acquire_gpu(arrive) < G)
-                if (++spins > (1u << 25)) __trap();
-        }
-    }
-    __syncthreads();
-}
-__device__ __forceinline__ void grid_depart(int *arrive, int *depart, int mergers) {
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(depart, 1) == mergers - 1) {
-        *depart = 0;
-        *arrive = 0;
-    }
-}
-__device__ __forceinline__ double warp_sum_f64(double v) {      // fixed butterfly
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 __device__ __forceinline__ int lds32f_i(uint32_t a) {
     int v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -496,7 +454,8 @@ lin_fwd_pipe_kernel(const LinFwdArgs a, const BnFinalArgs f, int *__restrict__ c
     if (!a.stats) { TL_SPAN(3); return; }
     const int G = static_cast<int>(gridDim.x);
     const bool merger = static_cast<int>(blockIdx.x) < a.M;
-    grid_arrive(counter, G, merger);
+    const int n_mergers = G < a.M ? G : a.M;
+    const int passed = grid_arrive(counter, counter + 1, G, merger);
     if (!merger) { TL_SPAN(3); return; }
     {
         // one warp per channel, lanes over the per-CTA partials {n, a, S1 = sum (y - a), S2 = sum (y - a)^2}.  Every partial
@@ -549,27 +508,9 @@ lin_fwd_pipe_kernel(const LinFwdArgs a, const BnFinalArgs f, int *__restrict__ c
             }
         }
         if (blockIdx.x == 0 && t == 0 && f.nbt) *f.nbt += 1;
-        grid_depart(counter, counter + 1, G < a.M ? G : a.M);
+        grid_depart(counter, counter + 1, passed, n_mergers);
         TL_SPAN(3);
     }
-}
-
-// cooperative launch: the driver places the grid only when ALL its CTAs fit on the device at once (and refuses a grid
-// that never could), which is what the grid rendezvous in the kernels' tails relies on.  Captured into CUDA graphs like
-// any other launch.
-template <typename... P, typename... A>
-static inline cudaError_t launch_coop(void (*kernel)(P...), int grid, int block, size_t smem, cudaStream_t stream, A &&...args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(static_cast<unsigned>(block));
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 
 template <int KP, int MP, int NACC, int NBUF_A, int RING, int NCV, int NEPI, int NACCBUF>
@@ -1017,7 +958,7 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
     const int G = static_cast<int>(gridDim.x);
     const int per = (P + G - 1) / G, e_begin = static_cast<int>(blockIdx.x) * per, e_end = (e_begin + per < P) ? e_begin + per : P;
     const bool merger = e_begin < P;
-    grid_arrive(counters, G, merger);
+    const int passed = grid_arrive(counters, counters + 1, G, merger);
     if (!merger) { TL_SPAN(3); return; }
     const float *pbase = reinterpret_cast<const float *>(a.part);
     auto emit = [&](int e, float r) {
@@ -1061,7 +1002,7 @@ lin_bwd_pipe_kernel(const LinBwdArgs a, float *__restrict__ dW, float *__restric
             emit(e, static_cast<float>(acc));
         }
     }
-    grid_depart(counters, counters + 1, (P + per - 1) / per);
+    grid_depart(counters, counters + 1, passed, (P + per - 1) / per);
     TL_SPAN(3);
 }
 

@@ -742,10 +742,12 @@ template <int CHP>   // chunks per row rounded up to a power of two (<= 32)
 __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restrict__ G, const float *__restrict__ Gseg,
                                                           const int32_t *__restrict__ row2seg, const float *__restrict__ Y,
                                                           int64_t N, int M, const float *__restrict__ bn, int act, float slope,
-                                                          float *__restrict__ part /* [grid][2*4*CHP] */) {
+                                                          float *__restrict__ part /* [grid][2*4*CHP] */, float *__restrict__ sums,
+                                                          int *__restrict__ counters) {
     DN_PDL_WAIT();
     constexpr int RP = 256 / CHP;
     __shared__ float red[8][8 * CHP];
+    __shared__ double dred[256];
     const int t = threadIdx.x, w = t >> 5, lane = t & 31, c = t % CHP, r0 = t / CHP;
     const bool vec = (M % 4 == 0) && aligned16_dev(G) && aligned16_dev(Y) && aligned16_dev(Gseg);
     const Bn4 b = load_bn4(bn, M, c);
@@ -805,21 +807,39 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restric
         for (int ww = 0; ww < 8; ++ww) s += red[ww][i];
         part[static_cast<size_t>(blockIdx.x) * 8 * CHP + i] = s;
     }
-}
-__global__ void __launch_bounds__(1024)
-bn_bwd_sums_reduce_kernel(const float *__restrict__ part, int nparts, int CHP, int M, float *__restrict__ sums) {
-    DN_PDL_WAIT();
-    __shared__ double sm[32][33];
-    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int e = blockIdx.x * 32 + lane;
-    const int which = e / (4 * CHP), ch = e % (4 * CHP);
-    const bool ok = e < 8 * CHP && ch < M;
-    const int cols[1] = {e};
-    const double s = ok ? partial_columns_sum<1>(part, nparts, 8 * CHP, cols, g) : 0.0;
-    const double tot = group_sum(sm, lane, g, s);        // total of element blockIdx.x * 32 + g
-    const int eg = blockIdx.x * 32 + g, which_g = eg / (4 * CHP), ch_g = eg % (4 * CHP);
-    if (lane == 0 && eg < 8 * CHP && ch_g < M) sums[which_g * M + ch_g] = static_cast<float>(tot);
-    (void)which;
+    // grid rendezvous (tc_common.cuh), then CTA e merges entry e of the per-CTA partials: thread q adds partials q,
+    // q + 256, ... in that order (double), then a fixed tree over the threads.  This replaces the follow-up reduce kernel.
+    constexpr int NE = 8 * CHP;
+    const int Gc = static_cast<int>(gridDim.x);
+    const bool merger = static_cast<int>(blockIdx.x) < NE;
+    const int passed = grid_arrive(counters, counters + 1, Gc, merger);
+    if (!merger) return;
+    for (int e = static_cast<int>(blockIdx.x); e < NE; e += Gc) {
+        double acc = 0.0;
+        constexpr int UNR = 3;      // 3 x 256 threads >= 4 x 148 CTAs: one round of loads
+        for (int q0 = 0; q0 < Gc; q0 += 256 * UNR) {
+            float v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int q = q0 + t + 256 * u;
+                v[u] = (q < Gc) ? __ldcg(part + static_cast<size_t>(q) * NE + e) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) acc += static_cast<double>(v[u]);
+        }
+        acc = warp_sum_f64(acc);
+        if (lane == 0) dred[w] = acc;
+        __syncthreads();
+        if (t == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) tot += dred[ww];
+            const int which = e / (4 * CHP), ch = e % (4 * CHP);
+            if (ch < M) sums[which * M + ch] = static_cast<float>(tot);
+        }
+        __syncthreads();
+    }
+    grid_depart(counters, counters + 1, passed, Gc < NE ? Gc : NE);
 }
 
 // fixed-order dot product: per-CTA partial (tree in shared memory), the last CTA adds the partials in index order
@@ -1138,9 +1158,10 @@ size_t dn4gl_bn_bwd_sums_workspace_bytes(int64_t N, int32_t M) {
 }
 
 int dn4gl_bn_bwd_sums_f32(const float *G, const float *Gseg, const int32_t *row2seg, const float *Y, int64_t N, int32_t M,
-                          const float *bn, int32_t act, float slope, float *sums, void *ws, size_t ws_bytes, void *stream) {
+                          const float *bn, int32_t act, float slope, float *sums, void *ws, size_t ws_bytes, int32_t *counters,
+                          void *stream) {
     DN_ARG(N >= 0 && M >= 1 && M <= 128 && (G != nullptr || Gseg != nullptr) && Y != nullptr && bn != nullptr && sums != nullptr && ws != nullptr);
-    DN_ARG((Gseg == nullptr) == (row2seg == nullptr));
+    DN_ARG((Gseg == nullptr) == (row2seg == nullptr) && counters != nullptr);
     DN_ARG(ws_bytes >= dn4gl_bn_bwd_sums_workspace_bytes(N, M));
     cudaStream_t s = as_stream(stream);
     if (N == 0) { DN_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * M, s)); return DN4GL_OK; }
@@ -1149,19 +1170,30 @@ int dn4gl_bn_bwd_sums_f32(const float *G, const float *Gseg, const int32_t *row2
     while (CHP < CH) CHP <<= 1;
     const int RP = 256 / CHP;
     const int64_t want = ceil_div64(N, static_cast<int64_t>(RP) * 8);
-    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * 4;
+    int occ = 0;        // resident CTAs per SM of this instantiation (the cooperative launch refuses a larger grid)
+    switch (CHP) {
+    case 1: DN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_sums_kernel<1>, 256, 0)); break;
+    case 2: DN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_sums_kernel<2>, 256, 0)); break;
+    case 4: DN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_sums_kernel<4>, 256, 0)); break;
+    case 8: DN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_sums_kernel<8>, 256, 0)); break;
+    case 16: DN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_sums_kernel<16>, 256, 0)); break;
+    default: DN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_sums_kernel<32>, 256, 0)); break;
+    }
+    const int64_t cap = static_cast<int64_t>(dn4gl_num_sms()) * (occ < 1 ? 1 : (occ > 4 ? 4 : occ));
     const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
     float *part = static_cast<float *>(ws);
+    // cooperative: the merge of the per-CTA partials rendezvouses the grid (4 CTAs of 256 threads per SM are resident)
+    cudaError_t rc;
     switch (CHP) {
-    case 1: DN_LAUNCH(bn_bwd_sums_kernel<1>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    case 2: DN_LAUNCH(bn_bwd_sums_kernel<2>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    case 4: DN_LAUNCH(bn_bwd_sums_kernel<4>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    case 8: DN_LAUNCH(bn_bwd_sums_kernel<8>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    case 16: DN_LAUNCH(bn_bwd_sums_kernel<16>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
-    default: DN_LAUNCH(bn_bwd_sums_kernel<32>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part); break;
+    case 1: rc = launch_coop(bn_bwd_sums_kernel<1>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part, sums, counters); break;
+    case 2: rc = launch_coop(bn_bwd_sums_kernel<2>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part, sums, counters); break;
+    case 4: rc = launch_coop(bn_bwd_sums_kernel<4>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part, sums, counters); break;
+    case 8: rc = launch_coop(bn_bwd_sums_kernel<8>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part, sums, counters); break;
+    case 16: rc = launch_coop(bn_bwd_sums_kernel<16>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part, sums, counters); break;
+    default: rc = launch_coop(bn_bwd_sums_kernel<32>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part, sums, counters); break;
     }
-    DN_LAUNCH(bn_bwd_sums_reduce_kernel, (8 * CHP + 31) / 32, 1024, 0, s, part, grid, CHP, M, sums);
-    DN_LAUNCHED_N(2);
+    DN_CUDA(rc);
+    DN_LAUNCHED();
     return DN4GL_OK;
 }
 

@@ -272,5 +272,67 @@ __device__ __forceinline__ float4 raw_chunk(uint32_t slab, int r, int ncols, int
     return lds128s(slab + static_cast<uint32_t>(r * ncols * 4 + c * 16));
 }
 
+// ---- grid rendezvous (kernels whose CTAs are all resident: launched COOPERATIVELY, launch_coop below).  The merges of
+// per-CTA partials used to be done by the last CTA to finish (one ticket level in the forward stage, two in the backward
+// stage) or by a follow-up kernel: 4.1 us / 7.4 us between the last CTA leaving its tile loop and the end of the stage
+// kernels (profiles/r2z_pipe_timeline.txt), a fifth of the backward stage.  Now every CTA arrives once its partials are
+// written, and the merge is SPREAD over the CTAs -- each takes a few output entries, the lanes / threads over the
+// partials: one round of loads per entry instead of serial merge levels.
+//   grid_arrive: the CTA's earlier global stores are published (bar.sync, then a gpu-scope fence by thread 0 -- the
+//                cooperative-groups pattern) and the CTA is counted; merging CTAs wait until all G have arrived and take
+//                a ticket saying so (issued before the merge, read after it: its round trip hides behind the loads).
+//   grid_depart: the merging CTA holding the last ticket -- every other merger is past its wait by then -- puts both
+//                counters back to zero for the next launch.
+// The wait is bounded: a grid that never completes (a launch that was not cooperative after all) traps instead of
+// hanging the device.
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int grid_arrive(int *arrive, int *passed, int G, bool wait) {
+    int ticket = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(arrive, 1);
+        if (wait) {
+            unsigned spins = 0;
+            while (ld_acquire_gpu(arrive) < G)
+                if (++spins > (1u << 25)) __trap();
+            ticket = atomicAdd(passed, 1);
+        }
+    }
+    __syncthreads();
+    return ticket;      // meaningful in thread 0 of a merging CTA
+}
+__device__ __forceinline__ void grid_depart(int *arrive, int *passed, int ticket, int mergers) {
+    if (threadIdx.x == 0 && ticket == mergers - 1) {
+        *passed = 0;
+        *arrive = 0;
+    }
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {      // fixed butterfly
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// cooperative launch: the driver places the grid only when ALL its CTAs fit on the device at once (and refuses a grid
+// that never could), which is what the grid rendezvous relies on.  Captured into CUDA graphs like any other launch.
+template <typename... P, typename... A>
+static inline cudaError_t launch_coop(void (*kernel)(P...), int grid, int block, size_t smem, cudaStream_t stream, A &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(block));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
 
 }  // namespace

@@ -553,9 +553,9 @@ def bn_bwd_sums(G, Y, rec, act=ACT_RELU, slope=0.0, gseg=None, row2seg=None):
     L = lib()
     sums = torch.empty(2 * M, dtype=torch.float32, device=Y.device)
     wsb = L.size("dn4gl_bn_bwd_sums_workspace_bytes", N, M)
-    ws, _ = _tc_ws(Y.device, wsb)
+    ws, counters = _tc_ws(Y.device, wsb)
     L.call("dn4gl_bn_bwd_sums_f32", ptr(G), ptr(None if gseg is None else _f32c(gseg)), ptr(row2seg), ptr(Y), N, M,
-           ptr(rec), int(act), float(slope), ptr(sums), ptr(ws), wsb, _stream())
+           ptr(rec), int(act), float(slope), ptr(sums), ptr(ws), wsb, ptr(counters), _stream())
     return sums
 
 
@@ -564,15 +564,42 @@ def _bn_dict(bn):
                 running_var=bn.running_var, num_batches_tracked=bn.num_batches_tracked)
 
 
-def dot(a, b):
-    """sum(a * b) as a 1-element tensor, fixed-order."""
+def dot(a, b, out=None, counter_slot=0):
+    """sum(a * b) as a 1-element tensor, fixed-order.  counter_slot: which of the device's ticket counters the launch
+    uses (a launch that may run next to the stage kernels must not share theirs)."""
     a, b = _f32c(a), _f32c(b)
     L = lib()
-    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=a.device)
     wsb = L.size("dn4gl_dot_workspace_bytes", a.numel())
     ws, counter = _tc_ws(a.device, wsb)
-    L.call("dn4gl_dot_f32", ptr(a), ptr(b), a.numel(), ptr(out), ptr(ws), wsb, ptr(counter), _stream())
+    L.call("dn4gl_dot_f32", ptr(a), ptr(b), a.numel(), ptr(out), ptr(ws), wsb, counter.data_ptr() + 4 * counter_slot, _stream())
     return out
+
+
+_side_streams = {}
+SIDE_STREAM_DOT = os.environ.get("DN4GL_SIDE_DOT", "1") == "1"
+
+
+def _side_stream(device):
+    s = _side_streams.get(device.index)
+    if s is None:
+        s = _side_streams[device.index] = torch.cuda.Stream(device=device)
+    return s
+
+
+def dot_beside(a, b):
+    """dot(a, b) launched on a second stream, forked from and joined back into the current one by the caller:
+    ``out, join = dot_beside(a, b); <launch independent work on the current stream>; join()``.  The bandwidth-bound
+    reduction then runs next to a latency-bound kernel (the backward aggregation) instead of after it; inside a CUDA-graph
+    capture the two become parallel branches."""
+    a, b = _f32c(a), _f32c(b)
+    out = torch.empty(1, dtype=torch.float32, device=a.device)     # allocated on the current stream, which consumes it
+    cur, side = torch.cuda.current_stream(a.device), _side_stream(a.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        dot(a, b, out=out, counter_slot=32)
+    return out, lambda: cur.wait_stream(side)
 
 
 class _GinLayer(torch.autograd.Function):
@@ -622,9 +649,15 @@ class _GinLayer(torch.autograd.Function):
         need_z = ctx.needs_input_grad[0] or need_eps
         gz, _, dW1, db1 = lin_bwd(ga1, W1, z, Yout=y1, bn=rec1, sums=sums1, g_masked=True, want_gx=need_z)
         gx = geps = None
+        join = None
+        if need_eps and SIDE_STREAM_DOT and ctx.needs_input_grad[0]:
+            geps, join = dot_beside(gz, x)          # d eps next to the backward aggregation (both only read gz)
+            geps = geps.view_as(eps)
         if ctx.needs_input_grad[0]:
             gx = _spmm(ctx.csr_out, gz, x.size(0), 1.0, eps) if has_agg else gz
-        if need_eps:
+        if join is not None:
+            join()
+        elif need_eps:
             geps = dot(gz, x).view_as(eps)
         return (gx, geps, dW1, db1, sums1[D1:], sums1[:D1], dW2, db2, sums2[D2:], sums2[:D2],
                 None, None, None, None, None, None, None)

@@ -466,10 +466,12 @@ int dn4gl_lin_bwd_f32(const float *G, const float *Gseg, const int32_t *row2seg,
 int dn4gl_bn_act_f32(const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope, float *out,
                      void *stream);
 /* sums[2*M] = {sum_r gm, sum_r gm * xhat}, gm = G * act'(bn(Y)): the batch sums of a BatchNorm whose output
- * gradient G arrives from outside the MLP (aggregation / readout backward)                                        */
+ * gradient G arrives from outside the MLP (aggregation / readout backward).  counters: DN4GL_LIN_COUNTERS zeroed int32,
+ * left at zero (the per-CTA partials are merged inside the kernel after a grid rendezvous)                         */
 size_t dn4gl_bn_bwd_sums_workspace_bytes(int64_t N, int32_t M);
 int dn4gl_bn_bwd_sums_f32(const float *G, const float *Gseg, const int32_t *row2seg, const float *Y, int64_t N, int32_t M,
-                          const float *bn, int32_t act, float slope, float *sums, void *ws, size_t ws_bytes, void *stream);
+                          const float *bn, int32_t act, float slope, float *sums, void *ws, size_t ws_bytes,
+                          int32_t *counters, void *stream);
 /* out = act(bn(Y)) and pooled[b,:] = sum (mode 0) / mean (mode 1) of out over rows [seg_ptr[b], seg_ptr[b+1]) in one pass
  * (the layer output handed to the next aggregation + its global_add_pool / global_mean_pool readout, gconv.py:213)   */
 int dn4gl_bn_act_pool_f32(const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope, float *out,
