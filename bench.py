@@ -188,7 +188,7 @@ def build_counting_model(name, kw, device):
     return model.to(device)
 
 
-def gpu_counting_run(key, dev, world, rank, steps, warmup=8):
+def gpu_counting_run(key, dev, world, rank, steps, warmup=20):
     """C3 / C4: augmentation (dummy) + CSR builds + model forward + loss + backward (+ all-reduce) + clip + AdamW(amsgrad)
     per step, inputs resident in HBM, device-timed, max over ranks."""
     from dummynode4graphlearning_b200 import synth, transforms as T
@@ -210,10 +210,13 @@ def gpu_counting_run(key, dev, world, rank, steps, warmup=8):
         torch.distributed.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nmalloc = lambda: int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))
+    m0, t_host = nmalloc(), time.perf_counter()
     e0.record()
     for _ in range(steps):
         loss = pipe.step_resident(pd_, gd_, cd, assume_ready=True)
     e1.record()
+    host_ms = 1e3 * (time.perf_counter() - t_host) / steps      # time to SUBMIT a step (the loop throttles on the device)
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
@@ -222,7 +225,7 @@ def gpu_counting_run(key, dev, world, rank, steps, warmup=8):
                        "CSR builds + forward + loss + backward + clip + AdamW(amsgrad) per step" % (key, name, shape, bs),
            "metric": "train graphs/sec", "value": bs * world / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms, "steps": steps,
            "n_gpus": world, "graphs_per_gpu": bs, "graph_nodes": int(g["node_ptr"][-1]), "graph_edges": int(g["edge_ptr"][-1]),
-           "loss": float(loss.item())}
+           "loss": float(loss.item()), "host_submit_ms_per_step": host_ms, "cudaMalloc_calls_in_timed_region": nmalloc() - m0}
     pipe._graphs.clear()
     return out, (p, g, counts, cfg, kw, name)
 
