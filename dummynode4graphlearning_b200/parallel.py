@@ -68,6 +68,7 @@ class GradientBucket:
         self.params = uniq
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
+        self._peer = None       # PeerAllReduce once set up, False if unavailable
 
     def _ensure(self):
         """built after the first backward: only parameters that actually received a gradient join the bucket
@@ -116,14 +117,110 @@ class GradientBucket:
             torch._foreach_copy_(dst, src)
 
     def all_reduce(self, local_weight=None):
-        """sum over ranks of local_weight * grad (local_weight = B_r / B for mean-reduced losses)."""
+        """sum over ranks of local_weight * grad (local_weight = B_r / B for mean-reduced losses).  On GPUs of one node:
+        ONE kernel per rank that reads every rank's bucket over NVLink peer memory (``PeerAllReduce``); otherwise -- CPU /
+        gloo, more than 8 ranks, peer mappings unavailable -- a scale kernel and the backend's all-reduce."""
         self.gather()
         if self.flat is None:
             return
+        if is_distributed():
+            if self._peer is None and self.flat.is_cuda and not torch.cuda.is_current_stream_capturing():
+                self._peer = PeerAllReduce.create(self.flat)          # collective: every rank reaches this at its first step
+            if self._peer:
+                self._peer.run(1.0 if local_weight is None else float(local_weight))
+                return
         if local_weight is not None and local_weight != 1.0:
             self.flat.mul_(local_weight)
         if is_distributed():
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+
+
+class PeerAllReduce:
+    """the flat gradient bucket summed over the ranks of ONE node by ``dn4gl_peer_allreduce_f32`` (csrc/peer.cu): every
+    rank exposes ``weight * bucket`` in a buffer that every other rank has mapped (CUDA IPC handles exchanged once through
+    the process group) and adds all ranks' exposed buffers in rank order inside one kernel -- no library collective and no
+    separate scaling kernel on the step's critical path.
+
+    ``create`` is itself a collective and returns False (on every rank alike) when any rank cannot set the mappings up:
+    backend not NCCL, more than 8 ranks, ``DN4GL_PEER_ALLREDUCE=0``, no peer access between two of the devices, IPC
+    refused by the platform; the caller then stays on ``dist.all_reduce``."""
+
+    MAX_WORLD = 8
+    SIGNAL_WORDS = 2048     # DN4GL_PEER_SIGNAL_WORDS
+
+    def __init__(self, flat, area, exposed_ptrs, signal_ptrs, mapped, rank, world):
+        import ctypes
+        self.flat, self.area, self.rank, self.world = flat, area, rank, world
+        self._mapped = mapped                                      # base pointers of the peer mappings (dn4gl_ipc_close)
+        self._exposed = (ctypes.c_void_p * world)(*exposed_ptrs)
+        self._signals = (ctypes.c_void_p * world)(*signal_ptrs)
+
+    @staticmethod
+    def _export(t):
+        """(cudaIpcMemHandle bytes of the allocation holding t, byte offset of t inside it) -- torch's own export of the
+        caching allocator's segment (storage._share_cuda_)"""
+        h = t.untyped_storage()._share_cuda_()
+        handle = bytes(h[1])
+        if len(handle) == 66:       # torch >= 2.5: version byte + kind byte ('c' = cudaMalloc segment) + cudaIpcMemHandle_t
+            if handle[1:2] != b"c":
+                raise RuntimeError("the buffer lives in an expandable segment: no cudaIpcMemHandle for it")
+            handle = handle[2:]
+        if len(handle) != 64:
+            raise RuntimeError("unexpected CUDA IPC handle of %d bytes" % len(handle))
+        return handle, int(h[3]) + t.storage_offset() * t.element_size()
+
+    @classmethod
+    def create(cls, flat):
+        import ctypes
+        import os
+        from ._lib import lib
+        world, rank = dist.get_world_size(), dist.get_rank()
+        n = flat.numel()
+        ok, err, mine, area = True, "", None, None
+        try:
+            if os.environ.get("DN4GL_PEER_ALLREDUCE", "1") == "0" or dist.get_backend() != "nccl" or world > cls.MAX_WORLD \
+                    or n % 4 != 0 or flat.dtype != torch.float32:
+                raise RuntimeError("not applicable")
+            # ONE allocation per rank: [signal words | exposed buffer 0 | exposed buffer 1], zeroed once
+            area = torch.zeros(cls.SIGNAL_WORDS + 2 * n, dtype=torch.float32, device=flat.device)
+            torch.cuda.synchronize(flat.device)
+            mine = cls._export(area)
+        except Exception as e:      # noqa: BLE001 -- any failure here means "use the library collective", on every rank
+            ok, err = False, repr(e)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        bases, mapped = [], []
+        if ok and all(h is not None for h in handles):
+            try:
+                with torch.cuda.device(flat.device):
+                    for r, h in enumerate(handles):
+                        if r == rank:
+                            bases.append(area.data_ptr())
+                            continue
+                        base = ctypes.c_void_p()
+                        lib().call("dn4gl_ipc_open", h[0], ctypes.byref(base))
+                        mapped.append(base.value)
+                        bases.append(base.value + h[1])
+            except Exception as e:      # noqa: BLE001
+                ok, err = False, repr(e)
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=flat.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            for base in mapped:
+                lib().call("dn4gl_ipc_close", base)
+            if err and "not applicable" not in err:
+                import warnings
+                warnings.warn("peer-memory all-reduce unavailable on rank %d (%s): using dist.all_reduce" % (rank, err))
+            return False
+        return cls(flat, area, [b + 4 * cls.SIGNAL_WORDS for b in bases], bases, mapped, rank, world)
+
+    def run(self, weight):
+        from ._lib import lib
+        from .graph import _stream
+        lib().call("dn4gl_peer_allreduce_f32", self.flat.data_ptr(), self.flat.numel(), float(weight), self._exposed,
+                   self._signals, self.rank, self.world, _stream())
 
 
 def sync_padded_lengths(*lengths):

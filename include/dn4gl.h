@@ -480,6 +480,25 @@ int dn4gl_bn_act_pool_f32(const float *Y, int64_t N, int32_t M, const float *bn,
 int dn4gl_segment_ids_i32(const int32_t *seg_ptr, int32_t B, int64_t N, int32_t *out, void *stream);
 
 /* ---- optimizer step ---------------------------------------------------------------------------------------- */
+/* ---- data-parallel exchange (the reference is single-device) --------------------------------
+ * One-shot all-reduce of the flat gradient bucket over NVLink peer memory, one node, world <= 8:
+ *   bucket[i] <- sum_{s = 0 .. world-1} weight_s * bucket_s[i]      on every rank, added in rank order (every rank
+ * computes the same bits).  bucket: this rank's n floats (n % 4 == 0, 16-byte aligned), updated in place.  exposed /
+ * signals: HOST arrays of `world` device pointers -- entry `rank` is this rank's own exposed area (2 n floats) / signal
+ * words (DN4GL_PEER_SIGNAL_WORDS int32, zeroed once at set-up, never reset afterwards), the others are peer mappings of
+ * the other ranks' (CUDA IPC handles opened with dn4gl_ipc_open).  weight: this rank's weight (B_r / B for a
+ * mean-reduced loss).  Every rank must issue the call the same number of times with the same n (it is a collective: block
+ * b of a rank waits for block b of every other rank inside the kernel, bounded -- a missing peer traps).  Replaces
+ * `flat *= weight; dist.all_reduce(flat)` of the pipelines; the library collective remains the fallback when the mappings
+ * cannot be set up.                                                                                                */
+#define DN4GL_PEER_SIGNAL_WORDS 2048
+int dn4gl_ipc_open(const void *handle, void **base_out);   /* handle: the 64 bytes of a cudaIpcMemHandle_t; maps it for the
+                                                               current device, peer access enabled on demand           */
+int dn4gl_ipc_close(void *base);
+int32_t dn4gl_peer_allreduce_grid(int64_t n);
+int dn4gl_peer_allreduce_f32(float *bucket, int64_t n, float weight, float *const *exposed, int32_t *const *signals,
+                             int32_t rank, int32_t world, void *stream);
+
 /* One Adam / AdamW (optionally amsgrad) update over FLAT fp32 buffers of n elements -- replaces the per-tensor kernels
  * of torch.optim.Adam.step() (graph_neural_networks/main.py:43) and torch.optim.AdamW(amsgrad=True).step()
  * (subgraph_isomorphism/train.py:831-838), same update rule and operation order as torch's single-tensor path:

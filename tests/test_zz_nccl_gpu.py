@@ -1,6 +1,6 @@
 """GPU, two ranks over NCCL (skipped on a one-GPU box; run with ``gpurun --gpus 2``): a mini-batch sharded over two
 processes -- one per GPU, each building its own CSR, gradients all-reduced through ONE flat bucket with weights
-B_r / B (pipelines.py / parallel.py, the path bench.py takes at N > 1) -- against the SAME mini-batch evaluated by a
+B_r / B by the peer-memory kernel of csrc/peer.cu (pipelines.py / parallel.py, the path bench.py takes at N > 1) -- against the SAME mini-batch evaluated by a
 single process on one GPU:
 
 * C3-style counting step (RGIN + dummy, no BatchNorm, ``exact_sharding=True``: padded lengths agreed over NCCL):
@@ -102,7 +102,29 @@ def _worker(rank, world, port, out_dir, total_c, total_g):
         half_c, half_g = total_c // 2, total_g // 2
         lc, gc = _counting_grads(dev, rank * half_c, (rank + 1) * half_c, True, total_c)
         lg, gg = _classification_grads(dev, rank * half_g, (rank + 1) * half_g, total_g)
-        torch.save(dict(loss_c=lc, grad_c=gc, loss_g=lg, grad_g=gg), os.path.join(out_dir, "rank%d.pt" % rank))
+        res = dict(loss_c=lc, grad_c=gc, loss_g=lg, grad_g=gg)
+        # the peer-memory all-reduce on its own: small (one block) and large (32 blocks) buckets, three rounds each so the
+        # epochs advance and the buckets are rewritten in between; against the library collective on the same data
+        from dummynode4graphlearning_b200.parallel import PeerAllReduce
+        for tag, n in (("small", 4 * 1037), ("large", 4 * 75001)):
+            torch.manual_seed(100 + rank)
+            ref = torch.randn(n, device=dev)
+            flat = torch.empty_like(ref)
+            peer = PeerAllReduce.create(flat)
+            res["peer_" + tag] = bool(peer)
+            if not peer:
+                continue
+            w = 0.25 + 0.5 * rank
+            errs = []
+            for it in range(3):
+                flat.copy_(ref * (it + 1))
+                peer.run(w)
+                expect = ref * (it + 1) * w
+                dist.all_reduce(expect)
+                errs.append(float((flat - expect).abs().max() / expect.abs().max()))
+            res["peer_err_" + tag] = max(errs)
+            res["peer_out_" + tag] = flat.cpu()
+        torch.save(res, os.path.join(out_dir, "rank%d.pt" % rank))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -119,6 +141,11 @@ def test_two_rank_nccl_step_equals_single_process(device):
         r0, r1 = torch.load(os.path.join(d, "rank0.pt")), torch.load(os.path.join(d, "rank1.pt"))
     # both ranks hold the same reduced bucket
     assert torch.equal(r0["grad_c"], r1["grad_c"]) and torch.equal(r0["grad_g"], r1["grad_g"])
+    # the exchange ran through dn4gl_peer_allreduce_f32 (NVLink peer memory), not through the library fallback ...
+    for tag in ("small", "large"):
+        assert r0["peer_" + tag] and r1["peer_" + tag], "peer-memory all-reduce was not set up"
+        assert r0["peer_err_" + tag] <= 1e-6 and r1["peer_err_" + tag] <= 1e-6, (r0["peer_err_" + tag], r1["peer_err_" + tag])
+        assert torch.equal(r0["peer_out_" + tag], r1["peer_out_" + tag])     # ... and every rank computed the same bits
     # counting (no BatchNorm, padded lengths agreed): == the single-process gradient of the whole batch
     _, ref_c = _counting_grads(device, 0, total_c, False, total_c)
     e = rel_err(r0["grad_c"], ref_c)
