@@ -11,9 +11,10 @@
 //   epilogue warps (4)        tcgen05.ld -> bias / statistics / masks -> coalesced 128-bit global stores
 //
 // so that the load of tile t+2, the conversion of tile t+1, the MMAs of tile t+1 and the epilogue of tile t overlap.
-// The few-CTA reduction kernels that used to follow every stage (bn_finalize, lin_bwd_reduce) are gone: the LAST CTA to
-// finish (atomic ticket) merges the per-CTA partials with all its threads, in a fixed order -- the result does not
-// depend on which CTA that is.
+// The few-CTA reduction kernels that used to follow every stage (bn_finalize, lin_bwd_reduce) are gone: the grid is
+// launched cooperatively, every CTA publishes its partials and is counted (tc_common.cuh: grid_arrive), and the merge is
+// spread over the CTAs -- each takes a few output entries and adds the partials in a fixed order, so the result does
+// not depend on which CTA arrives last.
 //
 // Accuracy of the fp32 emulation (3xTF32, x = hi + lo): the tensor core truncates after every accumulation, a BIASED
 // error that grows with the number of MMAs added into one accumulator at full magnitude.  Two
@@ -152,7 +153,7 @@ __device__ __forceinline__ float act_t(float x, float slope) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward stage  Y = act(bn_in(X)) W^T + b  (+ batch statistics of Y and the BatchNorm record, merged by the last CTA)
+// forward stage  Y = act(bn_in(X)) W^T + b  (+ batch statistics of Y and the BatchNorm record, merged after the grid rendezvous)
 // ------------------------------------------------------------------------------------------------------------------
 template <int KP, int MP, int NACC, int NBUF_A, int RING, int NCV, int NEPI, int NACCBUF>
 struct FwdCfg {

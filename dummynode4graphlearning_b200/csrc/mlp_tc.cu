@@ -1011,7 +1011,7 @@ int dn4gl_lin_fwd_f32(const float *X, int64_t N, int32_t K, const float *in_bn, 
     const bool ring_ok = (K % 4 == 0) && aligned16(X);
     int rc = 0, grid = 0;
     // warp-specialised pipeline (mlp_pipe.cu) whenever the slabs are 16-byte granular; it also merges the batch statistics
-    // in its last CTA (no bn_finalize launch).  DN4GL_LIN_SERIAL=1 keeps the phase-serial kernels (A/B, debugging).
+    // after a grid rendezvous (no bn_finalize launch).  DN4GL_LIN_SERIAL=1 keeps the phase-serial kernels (A/B, debugging).
     static const bool serial_only = getenv("DN4GL_LIN_SERIAL") != nullptr;
     if (!serial_only && (M % 4 == 0) && aligned16(Y) && (bn_out == nullptr || counters != nullptr)) {
         a.x_direct = (ring_ok && aligned16(W)) ? 0 : 1;     // e.g. the 2-feature first layer: X / W through bounds-checked loads
@@ -1067,7 +1067,7 @@ int dn4gl_lin_bwd_f32(const float *G, const float *Gseg, const int32_t *row2seg,
     a.num_tiles = static_cast<int>(ceil_div64(N, 128));
     const bool ring_ok = (K % 4 == 0) && (M % 4 == 0) && aligned16(X) && (G == nullptr || aligned16(G)) && (Yout == nullptr || aligned16(Yout));
     int rc = 0, grid = 0;
-    // warp-specialised pipeline with last-finisher merges (mlp_pipe.cu): no lin_bwd_reduce launch
+    // warp-specialised pipeline, partials merged after a grid rendezvous (mlp_pipe.cu): no lin_bwd_reduce launch
     static const bool serial_only = getenv("DN4GL_LIN_SERIAL") != nullptr;
     const bool gy_ok = (M % 4 == 0) && (G == nullptr || aligned16(G)) && (Yout == nullptr || aligned16(Yout));
     const bool x_ok = (K % 4 == 0) && aligned16(X) && aligned16(W);
