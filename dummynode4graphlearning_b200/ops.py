@@ -379,11 +379,56 @@ def atb(A, B, want_colsum=False):
     return C, cs
 
 
+# Forward and data-gradient products on the tensor cores (dn4gl_gemm_f32: 3xTF32 with fp32 register accumulation across
+# the contraction, csrc/gemm3x.cu) instead of the library's SIMT SGEMM.  DN4GL_GEMM_TC=0 restores the library GEMMs.
+GEMM_TENSOR_CORES = os.environ.get("DN4GL_GEMM_TC", "1") == "1"
+B_IS_WEIGHT, B_IS_KXM = 0, 1      # b_layout of dn4gl_gemm_f32: (M x K) nn.Linear weight / (K x M) matrix
+
+_gemm_ws = {}
+
+
+def gemm(a, b, b_layout, bias=None):
+    """a (N, K) @ b^T (b: (M, K), b_layout 0) or a @ b (b: (K, M), b_layout 1), + bias; fp32, no autograd."""
+    require_cuda(a, "the left operand")
+    a, b = _f32c(a), _f32c(b)
+    N, K = a.shape
+    M = b.size(0) if b_layout == B_IS_WEIGHT else b.size(1)
+    assert (b.size(1) if b_layout == B_IS_WEIGHT else b.size(0)) == K, "inner dimensions differ"
+    out = torch.empty((N, M), dtype=torch.float32, device=a.device)
+    if N == 0 or M == 0:
+        return out
+    if K == 0:
+        return out.zero_() if bias is None else out.copy_(bias.expand(N, M))
+    L = lib()
+    wsb = L.size("dn4gl_gemm_workspace_bytes", K, M)
+    if torch.cuda.is_current_stream_capturing():
+        ws = torch.empty(wsb, dtype=torch.uint8, device=a.device)
+    else:                       # one growing workspace per (device, stream): consumed before the next launch on that stream
+        key = (a.device.index, _stream())
+        ws = _gemm_ws.get(key)
+        if ws is None or ws.numel() < wsb:
+            ws = _gemm_ws[key] = torch.empty(max(wsb, 1 << 20), dtype=torch.uint8, device=a.device)
+    L.call("dn4gl_gemm_f32", ptr(a), N, K, K, ptr(b), b.size(1), int(b_layout), M, ptr(None if bias is None else _f32c(bias)),
+           ptr(out), M, ptr(ws), wsb, _stream())
+    return out
+
+
+GEMM_MIN_MACS = float(os.environ.get("DN4GL_GEMM_MIN_MACS", "0"))      # below N * K * M: the library GEMM (measurement switch)
+
+
+def _use_gemm(a, b):
+    if not (GEMM_TENSOR_CORES and a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32):
+        return False
+    return GEMM_MIN_MACS <= 0 or a.size(0) * b.numel() >= GEMM_MIN_MACS
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        if _use_gemm(x, weight):
+            return gemm(x, weight, B_IS_WEIGHT, bias)
         return torch.addmm(bias, x, weight.t()) if bias is not None else x @ weight.t()
 
     @staticmethod
@@ -391,7 +436,7 @@ class _Linear(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = g @ weight
+            gx = gemm(g, weight, B_IS_KXM) if _use_gemm(g, weight) else g @ weight
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw, gb = atb(g, x, want_colsum=ctx.has_bias)
         return gx, gw, gb
@@ -408,12 +453,14 @@ class _MatmulXW(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
         ctx.save_for_backward(x, w)
-        return x @ w
+        return gemm(x, w, B_IS_KXM) if _use_gemm(x, w) else x @ w
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
-        gx = g @ w.t() if ctx.needs_input_grad[0] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(g, w, B_IS_WEIGHT) if _use_gemm(g, w) else g @ w.t()
         gw = atb(x, g)[0] if ctx.needs_input_grad[1] else None
         return gx, gw
 

@@ -481,6 +481,20 @@ int dn4gl_bn_act_pool_f32(const float *Y, int64_t N, int32_t M, const float *bn,
 int dn4gl_segment_ids_i32(const int32_t *seg_ptr, int32_t B, int64_t N, int32_t *out, void *stream);
 
 /* ---- optimizer step ---------------------------------------------------------------------------------------- */
+/* ---- general fp32 GEMM on the tensor cores (3xTF32, csrc/gemm3x.cu) ----------------------------------------
+ * C (N x M, leading dimension ldc) = A (N x K, leading dimension lda) * B (+ bias[M] if non-NULL), fp32 in and out.
+ *   b_layout 0: B is an nn.Linear weight, (M x K) row-major with leading dimension ldb:  C = A B^T  -- the layers of
+ *               rgin.py:52 / dmpnn.py:47,55 / pred.py and the data gradient of `x @ w`;
+ *   b_layout 1: B is (K x M) row-major with leading dimension ldb:  C = A B  -- the relation-table, loop, P|Q and T
+ *               products (rgin.py:137-154, dmpnn.py:111-156, rgconv.py:48-51) and the data gradient of nn.Linear.
+ * Any N, K >= 1, M; any alignment (rows that are not 16-byte aligned take scalar loads / stores).  Every operand is
+ * split hi + lo in tf32, hi*hi + hi*lo + lo*hi is formed per 32-wide chunk of K in tensor memory (lo products first) and
+ * the chunks are added in fp32 registers with round-to-nearest: errors at the level of an fp32 FMA loop, not of a
+ * single-pass TF32 GEMM.  ws: dn4gl_gemm_workspace_bytes(K, M) bytes, 16-byte aligned (the split, swizzled copy of B).  */
+size_t dn4gl_gemm_workspace_bytes(int32_t K, int32_t M);
+int dn4gl_gemm_f32(const float *A, int64_t N, int32_t K, int32_t lda, const float *B, int32_t ldb, int32_t b_layout,
+                   int32_t M, const float *bias, float *C, int32_t ldc, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- data-parallel exchange (the reference is single-device) --------------------------------
  * One-shot all-reduce of the flat gradient bucket over NVLink peer memory, one node, world <= 8:
  *   bucket[i] <- sum_{s = 0 .. world-1} weight_s * bucket_s[i]      on every rank, added in rank order (every rank
