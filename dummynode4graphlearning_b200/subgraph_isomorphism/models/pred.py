@@ -27,11 +27,11 @@ class PredictNet(nn.Module):
         self.drop = nn.Dropout(dropout)
         self.p_fc = ops.Linear(input_dim, hidden_dim)
         self.g_fc = ops.Linear(input_dim, hidden_dim)
-        self.pred_fc1 = nn.Linear(hidden_dim * 4 + 4, hidden_dim)
-        self.pred_fc2 = nn.Linear(hidden_dim + 4, 1)
+        self.pred_fc1 = ops.Linear(hidden_dim * 4 + 4, hidden_dim)
+        self.pred_fc2 = ops.Linear(hidden_dim + 4, 1)
         if return_weights:
-            self.weight_fc1 = nn.Linear(hidden_dim * 4 + 2, hidden_dim)
-            self.weight_fc2 = nn.Linear(hidden_dim + 2, 1)
+            self.weight_fc1 = ops.Linear(hidden_dim * 4 + 2, hidden_dim)
+            self.weight_fc2 = ops.Linear(hidden_dim + 2, 1)
         else:
             self.weight_fc1 = self.weight_fc2 = None
         for m, how in ((self.p_fc, "normal"), (self.g_fc, "normal"), (self.pred_fc1, "normal"),
