@@ -276,15 +276,18 @@ def gpu_classification_run(shape, graphs, mode, hid, layers, num_labels, dev, st
         pipe.step_resident(dev_batch, assume_ready=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nmalloc = lambda: int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))
+    m0, t_host = nmalloc(), time.perf_counter()
     e0.record()
     for _ in range(steps):
         loss = pipe.step_resident(dev_batch, assume_ready=True)
     e1.record()
+    host_ms = 1e3 * (time.perf_counter() - t_host) / steps
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     pipe._graphs.clear()
     return {"metric": "train graphs/sec", "value": graphs / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms, "steps": steps,
-            "loss": float(loss.item())}, raw
+            "loss": float(loss.item()), "host_submit_ms_per_step": host_ms, "cudaMalloc_calls_in_timed_region": nmalloc() - m0}, raw
 
 
 def reference_arm(a):

@@ -414,10 +414,41 @@ def gemm(a, b, b_layout, bias=None):
 
 
 GEMM_MIN_MACS = float(os.environ.get("DN4GL_GEMM_MIN_MACS", "0"))      # below N * K * M: the library GEMM (measurement switch)
+# Products with fewer rows than this stay on the library GEMM: they are the per-GRAPH layers of the counting head (B = 8 .. 512
+# rows), not the per-node / per-edge products of the message-passing path.  Two reasons, both measured: at 512 rows the
+# two-kernel tensor-core GEMM takes 8-11 us against 2-4 us (profiles/r4j_bench_gemm.txt), and the head multiplies sum-pooled
+# representations of magnitude 1e3 straight into the prediction -- the tensor core's truncating accumulation, harmless
+# everywhere else, moved the DMPNN 'large' loss from 3e-6 to 3.4e-5 of the oracle when pred_fc1 / pred_fc2 ran on it
+# (profiles/r4l_parity_errors_head_on_tensor_cores.json).
+GEMM_MIN_ROWS = int(os.environ.get("DN4GL_GEMM_MIN_ROWS", "1024"))
+
+
+_gemm_scope = [None]      # innermost gemm_tensor_cores(...) override, None = the module default
+
+
+class gemm_tensor_cores:
+    """``with ops.gemm_tensor_cores(False): ...`` -- products issued inside use the library fp32 GEMM (True: dn4gl_gemm_f32)
+    whatever the module default is; the decision taken in a forward is kept for its backward."""
+
+    def __init__(self, flag):
+        self.flag = None if flag is None else bool(flag)
+
+    def __enter__(self):
+        self.prev = _gemm_scope[0]
+        if self.flag is not None:
+            _gemm_scope[0] = self.flag
+        return self
+
+    def __exit__(self, *exc):
+        _gemm_scope[0] = self.prev
+        return False
 
 
 def _use_gemm(a, b):
-    if not (GEMM_TENSOR_CORES and a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32):
+    on = GEMM_TENSOR_CORES if _gemm_scope[0] is None else (_gemm_scope[0] and os.environ.get("DN4GL_GEMM_TC", "1") == "1")
+    if not (on and a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32):
+        return False
+    if a.size(0) < GEMM_MIN_ROWS:
         return False
     return GEMM_MIN_MACS <= 0 or a.size(0) * b.numel() >= GEMM_MIN_MACS
 
@@ -427,7 +458,8 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        if _use_gemm(x, weight):
+        ctx.use_gemm = _use_gemm(x, weight)
+        if ctx.use_gemm:
             return gemm(x, weight, B_IS_WEIGHT, bias)
         return torch.addmm(bias, x, weight.t()) if bias is not None else x @ weight.t()
 
@@ -436,7 +468,7 @@ class _Linear(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm(g, weight, B_IS_KXM) if _use_gemm(g, weight) else g @ weight
+            gx = gemm(g, weight, B_IS_KXM) if ctx.use_gemm else g @ weight
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw, gb = atb(g, x, want_colsum=ctx.has_bias)
         return gx, gw, gb
@@ -453,14 +485,15 @@ class _MatmulXW(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
         ctx.save_for_backward(x, w)
-        return gemm(x, w, B_IS_KXM) if _use_gemm(x, w) else x @ w
+        ctx.use_gemm = _use_gemm(x, w)
+        return gemm(x, w, B_IS_KXM) if ctx.use_gemm else x @ w
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = gemm(g, w, B_IS_WEIGHT) if _use_gemm(g, w) else g @ w.t()
+            gx = gemm(g, w, B_IS_WEIGHT) if ctx.use_gemm else g @ w.t()
         gw = atb(x, g)[0] if ctx.needs_input_grad[1] else None
         return gx, gw
 

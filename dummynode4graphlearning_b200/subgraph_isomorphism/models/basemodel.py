@@ -12,6 +12,8 @@ are produced by single CUDA kernels on the batched graph (``ops.pad_segments``, 
 """
 from collections import OrderedDict
 
+import os
+
 import torch as th
 import torch.nn as nn
 
@@ -45,6 +47,18 @@ def _padded_mask(g, kind, dummy=True, reversed_=False):
 
 class _CountingBase(nn.Module):
     """shared constructor plumbing (BaseModel.__init__, basemodel.py:22-59)."""
+
+    # The counting models' wide products (relation table, loop, P|Q, T: section 4 K7 of DESIGN.md) take the library fp32 GEMM
+    # unless this is True (DN4GL_COUNTING_GEMM_TC=1 flips the default).  These networks have no normalisation layer and sum
+    # over 512-node graphs: the tensor core's truncating (biased) accumulation adds 1e-6 .. 5e-6 to the relative error of the
+    # loss, and on an ill-conditioned batch -- where the all-library GPU path is already 8e-6 from float64 -- that is 1.2e-5,
+    # over the 1e-5 bar (profiles/r4n_counting_loss_error_sweep.txt).  Speed is a wash either way
+    # (profiles/r4k_models_native_gemm_vs_library.txt), so parity decides.
+    tensor_core_gemm = os.environ.get("DN4GL_COUNTING_GEMM_TC", "0") == "1"
+
+    def __call__(self, *args, **kwargs):
+        with ops.gemm_tensor_cores(self.tensor_core_gemm):
+            return super().__call__(*args, **kwargs)
 
     has_edge_stream = False
 

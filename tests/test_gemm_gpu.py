@@ -45,11 +45,11 @@ def test_gemm_large_magnitude_spread_and_views(device):
     out = ops.gemm(a.to(device), w.to(device), 0).double().cpu()
     assert float(((out - ref).abs() / (a.double().abs() @ w.double().abs().t())).max()) <= 1e-6
 
-    x = torch.randn(500, 40, generator=g)
+    x = torch.randn(1500, 40, generator=g)      # >= ops.GEMM_MIN_ROWS: the wrappers take the kernel
     W = torch.randn(96, 40, generator=g) * 0.3
     bb = torch.randn(96, generator=g)
     Wk = torch.randn(40, 72, generator=g) * 0.3
-    wt1, wt2 = torch.randn(500, 96, generator=g), torch.randn(500, 72, generator=g)
+    wt1, wt2 = torch.randn(1500, 96, generator=g), torch.randn(1500, 72, generator=g)
 
     def run(dt, dev, lin, mm):
         xs, Ws, bs, Wks = (t.to(dev, dt).requires_grad_() for t in (x, W, bb, Wk))
@@ -58,8 +58,49 @@ def test_gemm_large_magnitude_spread_and_views(device):
         return [float(y)] + [t.grad.double().cpu() for t in (xs, Ws, bs, Wks)]
 
     import torch.nn.functional as F
+    assert x.size(0) >= ops.GEMM_MIN_ROWS and ops.GEMM_TENSOR_CORES
     r = run(torch.float64, "cpu", F.linear, lambda u, v: u @ v)
     o = run(torch.float32, device, ops.linear, ops.matmul_xw)
     assert abs(o[0] - r[0]) <= 1e-5 * abs(r[0])
     for got, want in zip(o[1:], r[1:]):
         assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+def test_counting_model_with_tensor_core_gemm_opt_in(device):
+    """the counting models keep their wide products on the library GEMM by default (basemodel._CountingBase.tensor_core_gemm,
+    DESIGN.md section 4 K7); with the switch on, RGIN 'small' must give the same prediction and gradients within 1e-5 of the
+    default path -- the opt-in path is exercised, and the scope taken in the forward is the one its backward uses."""
+    from dummynode4graphlearning_b200 import ops, synth, transforms as T
+    from dummynode4graphlearning_b200.graph import BatchedGraph
+    from dummynode4graphlearning_b200.subgraph_isomorphism.models import RGIN
+    p, g, counts = synth.counting_batch("small", 256, seed=3)
+    cfg = dict(synth.counting_config("small"), add_dummy=True)
+    mc = T.process_model_config(cfg)
+    pd_ = T.sub_add_dummy(T.to_device(p, device), cfg["max_npv"], cfg["max_npvl"], cfg["max_npe"], cfg["max_npel"])
+    gd_ = T.sub_add_dummy(T.to_device(g, device), cfg["max_ngv"], cfg["max_ngvl"], cfg["max_nge"], cfg["max_ngel"])
+    kw = dict({k: v for k, v in mc.items() if k.startswith("max_")}, hid_dim=64, rep_num_graph_layers=2, rep_num_pattern_layers=2,
+              rep_act_func="relu", pred_act_func="relu", pred_net="SumPredictNet", pred_hid_dim=32, emb_net="Equivariant",
+              enc_net="Multihot", filter_net="ScalarFilter", pred_with_enc=True, pred_with_deg=True,
+              rep_rgin_regularizer="bdd", rep_rgin_num_bases=4)
+    results = []
+    for flag in (False, True):
+        torch.manual_seed(2)
+        model = RGIN(**kw)
+        with torch.no_grad():
+            for n, q in model.named_parameters():
+                if "pred_fc2" in n:
+                    q.normal_(0.0, 0.1)
+        model = model.to(device).train()
+        model.tensor_core_gemm = flag
+        lib0 = ops.lib().launches
+        out = model(BatchedGraph.from_batch(pd_, device), BatchedGraph.from_batch(gd_, device))
+        loss = ((out["pred_c"].view(-1) - torch.from_numpy(counts).to(device).float()) ** 2).mean()
+        loss.backward()
+        results.append((float(loss), [q.grad.detach().clone() for q in model.parameters() if q.grad is not None],
+                        ops.lib().launches - lib0))
+    (l0, g0, n0), (l1, g1, n1) = results
+    assert n1 > n0, "the opt-in path did not issue any additional library call (dn4gl_gemm_f32)"
+    assert abs(l1 - l0) <= 1e-5 * abs(l0)
+    gmax = max(float(a.abs().max()) for a in g0)
+    for a, b in zip(g0, g1):
+        assert float((a - b).abs().max()) <= 1e-5 * max(float(a.abs().max()), 1e-3 * gmax)
