@@ -842,6 +842,95 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float *__restric
     grid_depart(counters, counters + 1, passed, Gc < NE ? Gc : NE);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stand-alone training-mode BatchNorm1d for widths the fused stages do not take (65 .. 128 columns: main.py:174's default
+// hidden 128): batch statistics as per-CTA shifted sums {n, a, S1 = sum (y - a), S2 = sum (y - a)^2} merged by
+// bn_finalize_kernel (the same fixed-order double-precision merge as the stage kernels' statistics), and the backward
+// elementwise pass  gx = gamma rstd (gm - s1 / N - xhat s2 / N),  gm = g act'(bn(y)).  ATen's batch-norm backward
+// reduces the 1.5e5 rows of a full PROTEINS batch in fp32 and lands 3e-4 from float64 on the BatchNorm parameter
+// gradients (profiles/*parity_errors*.json, hid 128); these are at 1e-6.
+template <int CHP>
+__global__ void __launch_bounds__(256) bn_stats_partial_kernel(const float *__restrict__ Y, int64_t N, int M, int MP,
+                                                               float4 *__restrict__ part /* [grid][MP] */) {
+    DN_PDL_WAIT();
+    constexpr int RP = 256 / CHP;
+    __shared__ float red[8][8 * CHP];
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31, c = t % CHP, r0 = t / CHP;
+    const bool vec = (M % 4 == 0) && aligned16_dev(Y);
+    const int64_t first = static_cast<int64_t>(blockIdx.x) * RP;          // < N: the host sizes the grid by row groups
+    float4 s1 = zero4(), s2 = zero4(), a4 = zero4();
+    if (4 * c < M) {
+        a4 = load_chunk(Y, first, M, c, vec);                               // the CTA's shift: its first row
+        const int64_t stride = static_cast<int64_t>(gridDim.x) * RP;
+        auto accumulate = [&](const float4 &y) {
+            const float dx = y.x - a4.x, dy = y.y - a4.y, dz = y.z - a4.z, dw = y.w - a4.w;
+            s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+            s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+        };
+        int64_t r = first + r0;
+        for (; r + 3 * stride < N; r += 4 * stride) {
+            float4 y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) y[u] = load_chunk(Y, r + u * stride, M, c, vec);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) accumulate(y[u]);
+        }
+        for (; r < N; r += stride) accumulate(load_chunk(Y, r, M, c, vec));
+    }
+    chunk_allreduce<CHP>(s1);
+    chunk_allreduce<CHP>(s2);
+    if (lane < CHP) {
+        const int c0 = 4 * c;
+        red[w][c0] = s1.x; red[w][c0 + 1] = s1.y; red[w][c0 + 2] = s1.z; red[w][c0 + 3] = s1.w;
+        red[w][4 * CHP + c0] = s2.x; red[w][4 * CHP + c0 + 1] = s2.y; red[w][4 * CHP + c0 + 2] = s2.z; red[w][4 * CHP + c0 + 3] = s2.w;
+    }
+    __shared__ float shift_s[4 * CHP];
+    if (r0 == 0) { shift_s[4 * c] = a4.x; shift_s[4 * c + 1] = a4.y; shift_s[4 * c + 2] = a4.z; shift_s[4 * c + 3] = a4.w; }
+    __syncthreads();
+    // rows this CTA saw: its row groups are blockIdx.x, blockIdx.x + G, ...; only the last group of the matrix may be short
+    const int64_t groups = (N + RP - 1) / RP, G = gridDim.x;
+    const int64_t mine = (groups - 1 - blockIdx.x) / G + 1;
+    int64_t n_rows = mine * RP;
+    if ((groups - 1) % G == blockIdx.x) n_rows -= groups * RP - N;
+    for (int i = t; i < MP; i += 256) {
+        float S1 = 0.f, S2 = 0.f;
+        if (i < 4 * CHP && i < M) {
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) { S1 += red[ww][i]; S2 += red[ww][4 * CHP + i]; }
+            part[static_cast<size_t>(blockIdx.x) * MP + i] = make_float4(static_cast<float>(n_rows), shift_s[i], S1, S2);
+        } else {
+            part[static_cast<size_t>(blockIdx.x) * MP + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+template <int CHP>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float *__restrict__ G, const float *__restrict__ Y, int64_t N, int M,
+                                                           const float *__restrict__ bn, const float *__restrict__ sums, int act,
+                                                           float slope, float *__restrict__ GX) {
+    DN_PDL_WAIT();
+    constexpr int RP = 256 / CHP;
+    const int t = threadIdx.x, c = t % CHP, r0 = t / CHP;
+    if (4 * c >= M) return;
+    const bool vec = (M % 4 == 0) && aligned16_dev(G) && aligned16_dev(Y) && aligned16_dev(GX);
+    const Bn4 b = load_bn4(bn, M, c);
+    const float invN = 1.f / static_cast<float>(N);
+    const float4 s1 = load_vec4(sums, M, c), s2 = load_vec4(sums + M, M, c);
+    const float4 m1 = make_float4(s1.x * invN, s1.y * invN, s1.z * invN, s1.w * invN);
+    const float4 m2 = make_float4(s2.x * invN, s2.y * invN, s2.z * invN, s2.w * invN);
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * RP + r0; r < N; r += static_cast<int64_t>(gridDim.x) * RP) {
+        float4 g = load_chunk(G, r, M, c, vec);
+        const float4 y = load_chunk(Y, r, M, c, vec);
+        const float4 xc = make_float4(y.x - b.mean.x, y.y - b.mean.y, y.z - b.mean.z, y.w - b.mean.w);
+        g.x *= dact_f(fmaf(xc.x, b.k.x, b.beta.x), act, slope); g.y *= dact_f(fmaf(xc.y, b.k.y, b.beta.y), act, slope);
+        g.z *= dact_f(fmaf(xc.z, b.k.z, b.beta.z), act, slope); g.w *= dact_f(fmaf(xc.w, b.k.w, b.beta.w), act, slope);
+        float4 o;
+        o.x = b.k.x * (g.x - m1.x - xc.x * b.rstd.x * m2.x); o.y = b.k.y * (g.y - m1.y - xc.y * b.rstd.y * m2.y);
+        o.z = b.k.z * (g.z - m1.z - xc.z * b.rstd.z * m2.z); o.w = b.k.w * (g.w - m1.w - xc.w * b.rstd.w * m2.w);
+        store_chunk(GX, r, M, c, o, vec);
+    }
+}
+
 // fixed-order dot product: per-CTA partial (tree in shared memory), the last CTA adds the partials in index order
 __global__ void __launch_bounds__(256) dot_kernel(const float *__restrict__ a, const float *__restrict__ b, int64_t n,
                                                   float *__restrict__ out, float *__restrict__ part, int *counter) {
@@ -1193,6 +1282,64 @@ int dn4gl_bn_bwd_sums_f32(const float *G, const float *Gseg, const int32_t *row2
     default: rc = launch_coop(bn_bwd_sums_kernel<32>, grid, 256, 0, s, G, Gseg, row2seg, Y, N, M, bn, act, slope, part, sums, counters); break;
     }
     DN_CUDA(rc);
+    DN_LAUNCHED();
+    return DN4GL_OK;
+}
+
+static int bn_chp(int M) {
+    const int CH = (M + 3) / 4;
+    int CHP = 1;
+    while (CHP < CH) CHP <<= 1;
+    return CHP;
+}
+
+size_t dn4gl_bn_stats_workspace_bytes(int64_t N, int32_t M) {
+    (void)N;
+    const size_t MP = (static_cast<size_t>(M) + 31) / 32 * 32;
+    return static_cast<size_t>(dn4gl_num_sms()) * 4 * MP * sizeof(float4);
+}
+
+int dn4gl_bn_stats_f32(const float *Y, int64_t N, int32_t M, const float *gamma, const float *beta, float eps, float momentum,
+                       float *running_mean, float *running_var, int64_t *num_batches_tracked, float *bn_out, void *ws,
+                       size_t ws_bytes, void *stream) {
+    DN_ARG(N >= 1 && M >= 1 && M <= 128 && Y != nullptr && bn_out != nullptr && ws != nullptr);
+    DN_ARG(ws_bytes >= dn4gl_bn_stats_workspace_bytes(N, M));
+    cudaStream_t s = as_stream(stream);
+    const int CHP = bn_chp(M), RP = 256 / CHP, MP = (M + 31) / 32 * 32;
+    const int64_t groups = ceil_div64(N, RP), want = ceil_div64(groups, 8), cap = static_cast<int64_t>(dn4gl_num_sms()) * 4;
+    const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);       // <= groups: every CTA has a first row
+    float4 *part = static_cast<float4 *>(ws);
+    switch (CHP) {
+    case 1: DN_LAUNCH(bn_stats_partial_kernel<1>, grid, 256, 0, s, Y, N, M, MP, part); break;
+    case 2: DN_LAUNCH(bn_stats_partial_kernel<2>, grid, 256, 0, s, Y, N, M, MP, part); break;
+    case 4: DN_LAUNCH(bn_stats_partial_kernel<4>, grid, 256, 0, s, Y, N, M, MP, part); break;
+    case 8: DN_LAUNCH(bn_stats_partial_kernel<8>, grid, 256, 0, s, Y, N, M, MP, part); break;
+    case 16: DN_LAUNCH(bn_stats_partial_kernel<16>, grid, 256, 0, s, Y, N, M, MP, part); break;
+    default: DN_LAUNCH(bn_stats_partial_kernel<32>, grid, 256, 0, s, Y, N, M, MP, part); break;
+    }
+    DN_LAUNCH(bn_finalize_kernel, MP / 32, 1024, 0, s, reinterpret_cast<const float4 *>(part), grid, MP, M, N, gamma, beta, eps, momentum,
+              bn_out, running_mean, running_var, reinterpret_cast<long long *>(num_batches_tracked));
+    DN_LAUNCHED_N(2);
+    return DN4GL_OK;
+}
+
+int dn4gl_bn_bwd_apply_f32(const float *G, const float *Y, int64_t N, int32_t M, const float *bn, const float *sums, int32_t act,
+                           float slope, float *GX, void *stream) {
+    DN_ARG(N >= 0 && M >= 1 && M <= 128);
+    if (N == 0) return DN4GL_OK;
+    DN_ARG(G != nullptr && Y != nullptr && bn != nullptr && sums != nullptr && GX != nullptr);
+    cudaStream_t s = as_stream(stream);
+    const int CHP = bn_chp(M), RP = 256 / CHP;
+    const int64_t want = ceil_div64(N, static_cast<int64_t>(RP) * 4), cap = static_cast<int64_t>(dn4gl_num_sms()) * 8;
+    const int grid = static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
+    switch (CHP) {
+    case 1: DN_LAUNCH(bn_bwd_apply_kernel<1>, grid, 256, 0, s, G, Y, N, M, bn, sums, act, slope, GX); break;
+    case 2: DN_LAUNCH(bn_bwd_apply_kernel<2>, grid, 256, 0, s, G, Y, N, M, bn, sums, act, slope, GX); break;
+    case 4: DN_LAUNCH(bn_bwd_apply_kernel<4>, grid, 256, 0, s, G, Y, N, M, bn, sums, act, slope, GX); break;
+    case 8: DN_LAUNCH(bn_bwd_apply_kernel<8>, grid, 256, 0, s, G, Y, N, M, bn, sums, act, slope, GX); break;
+    case 16: DN_LAUNCH(bn_bwd_apply_kernel<16>, grid, 256, 0, s, G, Y, N, M, bn, sums, act, slope, GX); break;
+    default: DN_LAUNCH(bn_bwd_apply_kernel<32>, grid, 256, 0, s, G, Y, N, M, bn, sums, act, slope, GX); break;
+    }
     DN_LAUNCHED();
     return DN4GL_OK;
 }

@@ -47,7 +47,7 @@ class GINConv(nn.Module):
             out = ops.spmm_sum(x, s.csr_in, s.csr_out, 0.0) + (1 + self.eps) * x
         else:
             out = ops.spmm_sum(x, s.csr_in, s.csr_out, 1.0 + float(self.eps))
-        return self.nn(out)
+        return ops.apply_gin_mlp(self.nn, out)
 
 
 def _ptr_of(batch, size=None):
@@ -157,7 +157,7 @@ class GIN(torch.nn.Module):
         out = 0
         for layer in range(self.no_layers):
             if layer == 0:
-                x = self.first_h(x)
+                x = ops.apply_gin_mlp(self.first_h, x)
                 out += F.dropout(self.pooling(self.linears[layer](x), data.batch, node_ptr=s.node_ptr), p=self.dropout)
             else:
                 x = self.convs[layer - 1](x, data.edge_index, structure=s)

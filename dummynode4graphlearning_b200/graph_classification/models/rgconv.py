@@ -95,11 +95,11 @@ class RGIN(torch.nn.Module):
         out = 0
         for layer in range(self.no_layers):
             if layer == 0:
-                x = self.first_h(x)
+                x = ops.apply_gin_mlp(self.first_h, x)
                 out += F.dropout(self.pooling(self.linears[layer](x), data.batch, node_ptr=s.node_ptr), p=self.dropout)
             else:
                 x = self.convs[layer - 1](x, data.edge_index, edge_type, structure=s)
-                x = self.nns[layer - 1](x)
+                x = ops.apply_gin_mlp(self.nns[layer - 1], x)
                 out += F.dropout(self.linears[layer](self.pooling(x, data.batch, node_ptr=s.node_ptr)),
                                  p=self.dropout, training=self.training)
         return F.log_softmax(out, dim=-1)

@@ -743,6 +743,76 @@ class _GinLayer(torch.autograd.Function):
                 None, None, None, None, None, None, None)
 
 
+class _BnActTrain(torch.autograd.Function):
+    """act(BatchNorm1d(y)) in training mode for widths above the fused stages' (<= 128): batch statistics, running-statistics
+    update and both backward reductions by the fixed-order kernels (dn4gl_bn_stats_f32, dn4gl_bn_bwd_sums_f32,
+    dn4gl_bn_bwd_apply_f32) instead of ATen's fp32 batch-norm reductions."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, bn, act):
+        require_cuda(y, "rows")
+        y = _f32c(y)
+        N, M = y.shape
+        L = lib()
+        rec = torch.empty(4 * M, dtype=torch.float32, device=y.device)
+        wsb = L.size("dn4gl_bn_stats_workspace_bytes", N, M)
+        ws, _ = _tc_ws(y.device, wsb)
+        L.call("dn4gl_bn_stats_f32", ptr(y), N, M, ptr(gamma), ptr(beta), float(bn["eps"]), float(bn.get("momentum") or 0.0),
+               ptr(bn.get("running_mean")), ptr(bn.get("running_var")), ptr(bn.get("num_batches_tracked")), ptr(rec), ptr(ws), wsb,
+               _stream())
+        out = bn_act(y, rec, act)
+        ctx.save_for_backward(y, rec)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, rec = ctx.saved_tensors
+        g = _f32c(g)
+        N, M = y.shape
+        sums = bn_bwd_sums(g, y, rec, ctx.act)
+        gx = torch.empty_like(y)
+        lib().call("dn4gl_bn_bwd_apply_f32", ptr(g), ptr(y), N, M, ptr(rec), ptr(sums), int(ctx.act), 0.0, ptr(gx), _stream())
+        return gx, sums[M:], sums[:M], None, None
+
+
+def gin_mlp_wide_ok(seq):
+    """True for the reference's GIN MLP (Linear, BatchNorm1d, ReLU, Linear, BatchNorm1d, ReLU) in training mode at widths the
+    fused stages do not take but the stand-alone BatchNorm kernels do (<= 128 columns per BatchNorm)."""
+    import torch.nn as nn
+    if not (isinstance(seq, nn.Sequential) and len(seq) == 6):
+        return False
+    l1, n1, a1, l2, n2, a2 = seq
+    if not (isinstance(l1, nn.Linear) and isinstance(l2, nn.Linear) and isinstance(n1, nn.BatchNorm1d)
+            and isinstance(n2, nn.BatchNorm1d) and isinstance(a1, nn.ReLU) and isinstance(a2, nn.ReLU)):
+        return False
+    for n in (n1, n2):
+        if not (n.training and n.affine and n.track_running_stats and n.momentum is not None and n.num_features <= 128):
+            return False
+    return True
+
+
+def gin_mlp_wide(seq, z):
+    """the GIN MLP `seq` on z (N >= 1 rows): Linear through ops.linear (tensor-core GEMM), BatchNorm + ReLU through the
+    stand-alone fixed-order BatchNorm kernels; gin_mlp_wide_ok(seq) must hold."""
+    l1, n1, _, l2, n2, _ = seq
+    for lin, bn in ((l1, n1), (l2, n2)):
+        z = linear(z, lin.weight, lin.bias)
+        z = _BnActTrain.apply(z, bn.weight, bn.bias, _bn_dict(bn), ACT_RELU)
+    return z
+
+
+def apply_gin_mlp(seq, z):
+    """the GIN MLP on CUDA rows by the best available path: fused tensor-core stages (widths <= 64), stand-alone
+    BatchNorm kernels + tensor-core GEMM (<= 128), else the module as it is."""
+    if z.is_cuda and z.size(0) > 0:
+        if gin_mlp_fusable(seq):
+            return gin_mlp(seq, z)
+        if gin_mlp_wide_ok(seq):
+            return gin_mlp_wide(seq, z)
+    return seq(z)
+
+
 def gin_layer(seq, x, eps=None, csr_in=None, csr_out=None, seg_ptr=None, row2seg=None, mean=False):
     """fused GIN layer -> (h, pooled | None); gin_mlp_fusable(seq) must hold.  csr_in None: no aggregation (layer 0)."""
     l1, n1, _, l2, n2, _ = seq

@@ -473,6 +473,17 @@ size_t dn4gl_bn_bwd_sums_workspace_bytes(int64_t N, int32_t M);
 int dn4gl_bn_bwd_sums_f32(const float *G, const float *Gseg, const int32_t *row2seg, const float *Y, int64_t N, int32_t M,
                           const float *bn, int32_t act, float slope, float *sums, void *ws, size_t ws_bytes,
                           int32_t *counters, void *stream);
+/* Stand-alone training-mode BatchNorm1d for widths above the fused stages' (M <= 128; gconv.py:190-196 with main.py:174's
+ * hidden 128): _stats writes the record {mean, rstd, gamma*rstd, beta} of Y's batch statistics to bn_out[4*M] (fixed-order
+ * double-precision merge of per-CTA shifted sums) and updates running_mean / running_var / num_batches_tracked like
+ * nn.BatchNorm1d (NULL = skip); dn4gl_bn_act_f32 applies it.  _bwd_apply: GX = gamma rstd (gm - s1 / N - xhat s2 / N) with
+ * gm = G * act'(bn(Y)) and sums = {s1, s2} from dn4gl_bn_bwd_sums_f32 (d beta = s1, d gamma = s2).                      */
+size_t dn4gl_bn_stats_workspace_bytes(int64_t N, int32_t M);
+int dn4gl_bn_stats_f32(const float *Y, int64_t N, int32_t M, const float *gamma, const float *beta, float eps, float momentum,
+                       float *running_mean, float *running_var, int64_t *num_batches_tracked, float *bn_out, void *ws,
+                       size_t ws_bytes, void *stream);
+int dn4gl_bn_bwd_apply_f32(const float *G, const float *Y, int64_t N, int32_t M, const float *bn, const float *sums, int32_t act,
+                           float slope, float *GX, void *stream);
 /* out = act(bn(Y)) and pooled[b,:] = sum (mode 0) / mean (mode 1) of out over rows [seg_ptr[b], seg_ptr[b+1]) in one pass
  * (the layer output handed to the next aggregation + its global_add_pool / global_mean_pool readout, gconv.py:213)   */
 int dn4gl_bn_act_pool_f32(const float *Y, int64_t N, int32_t M, const float *bn, int32_t act, float slope, float *out,
